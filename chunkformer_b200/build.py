@@ -1,0 +1,48 @@
+"""Build the C-ABI shared library in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m chunkformer_b200.build            # -> chunkformer_b200/csrc/libchunkformer_b200.so
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libchunkformer_b200.so")
+SOURCES = ["api.cu", "plan.cpp"]
+HEADERS = ["common.cuh", "gemm.cuh", "gemm_host.cuh", "norm_conv.cuh", "frontend.cuh", "attention_simt.cuh",
+           "attention_tc.cuh", "misc_kernels.cuh", "plan.h", os.path.join("..", "..", "include", "chunkformer_b200.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC,-fvisibility=hidden", "--shared", "-cudart", "static",
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,786 @@
+// C ABI of chunkformer_b200 (include/chunkformer_b200.h): handle, weight conversion, encoder driver, CTC head,
+// kernel-level entry points.  One translation unit: all sm_100a kernels are header templates instantiated here.
+#include "../../include/chunkformer_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "attention_simt.cuh"
+#include "attention_tc.cuh"
+#include "frontend.cuh"
+#include "gemm_host.cuh"
+#include "misc_kernels.cuh"
+#include "norm_conv.cuh"
+#include "plan.h"
+
+using namespace cf;
+typedef __nv_bfloat16 bf16;
+
+static thread_local std::string g_last_error = "";
+
+// --------------------------------------------------------------------------------------------------------------------
+// handle
+// --------------------------------------------------------------------------------------------------------------------
+struct LayerW {
+  bf16 *ffm_w1, *ffm_w2, *ff_w1, *ff_w2, *qkv_w, *o_w, *pos_w, *pw1_w, *pw2_w;
+  float *ffm_b1, *ffm_b2, *ff_b1, *ff_b2, *qkv_b, *bias_u, *bias_v, *o_b, *pw1_b, *dw_w, *dw_b, *cn_w, *cn_b, *pw2_b;
+  float *ln_ffm_w, *ln_ffm_b, *ln_mha_w, *ln_mha_b, *ln_conv_w, *ln_conv_b, *ln_ff_w, *ln_ff_b, *ln_fin_w, *ln_fin_b;
+};
+
+struct PosTable {  // projected relative-position tables, one per layer, cached per (c, l, r)
+  int c, l, r, R, Rpad;
+  bf16* dev = nullptr;  // [L][Rpad][d]
+};
+
+struct cf_handle {
+  cf_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  int F3 = 9;  // frequency bins after the three stride-2 convs
+  std::string err;
+  std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, std::vector<int64_t>> host_shape;
+  bool finalized = false;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<LayerW> layers;
+  float *fe_wpack = nullptr, *fe_b3 = nullptr, *fe_dw2_w = nullptr, *fe_dw2_b = nullptr, *fe_b6 = nullptr, *fe_bout = nullptr;
+  bf16 *fe_w3 = nullptr, *fe_w6 = nullptr, *fe_wout = nullptr;
+  float *cmvn_mean = nullptr, *cmvn_istd = nullptr;
+  float *after_w = nullptr, *after_b = nullptr;
+  bf16* ctc_w = nullptr;
+  float* ctc_b = nullptr;
+  float* zeros = nullptr;  // max(N) zero floats (bias-free GEMMs)
+  std::vector<PosTable> pos_tables;
+};
+
+static int fail(cf_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_last_error = msg;
+  return code;
+}
+#define CF_CUDA(h, call)                                                                              \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) {                                                                         \
+      return fail(h, CF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+    }                                                                                                 \
+  } while (0)
+
+extern "C" const char* cf_version(void) { return "chunkformer_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* cf_last_error(const cf_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int cf_create(const cf_config* cfg, int device, cf_handle** out) {
+  if (!cfg || !out) return fail(nullptr, CF_ERR_INVALID, "cf_create: null argument");
+  *out = nullptr;
+  const int d = cfg->d_model;
+  if (!(d == 256 || d == 512)) return fail(nullptr, CF_ERR_INVALID, "cf_create: d_model must be 256 or 512");
+  if (cfg->heads <= 0 || d % cfg->heads != 0 || !((d / cfg->heads) == 64 || (d / cfg->heads) == 128))
+    return fail(nullptr, CF_ERR_INVALID, "cf_create: d_model / heads must be 64 or 128");
+  if (cfg->ffn <= 0 || cfg->ffn % 64 != 0) return fail(nullptr, CF_ERR_INVALID, "cf_create: ffn must be a multiple of 64");
+  if (cfg->kernel != 15) return fail(nullptr, CF_ERR_INVALID, "cf_create: cnn_module_kernel must be 15");
+  if (cfg->layers <= 0 || cfg->feat_dim < 15 || cfg->vocab < 0)
+    return fail(nullptr, CF_ERR_INVALID, "cf_create: bad layers / feat_dim / vocab");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
+    cudaGetLastError();
+    return fail(nullptr, CF_ERR_CUDA, "cf_create: no CUDA device (there is no CPU fallback)");
+  }
+  cudaDeviceProp prop;
+  CF_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, CF_ERR_CUDA, "cf_create: device is not sm_100 (kernels are built for sm_100a only)");
+  CF_CUDA(nullptr, cudaSetDevice(device));
+  std::unique_ptr<cf_handle> h(new cf_handle());
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  int f = cfg->feat_dim;
+  for (int i = 0; i < 3; ++i) f = (f - 3) / 2 + 1;
+  h->F3 = f;
+  *out = h.release();
+  return CF_OK;
+}
+
+extern "C" void cf_destroy(cf_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->arena) cudaFree(h->arena);
+  for (auto& t : h->pos_tables)
+    if (t.dev) cudaFree(t.dev);
+  delete h;
+}
+
+extern "C" int cf_load_tensor(cf_handle* h, const char* key, const void* data, int dtype, int ndim, const int64_t* shape) {
+  if (!h || !key || !data || ndim < 0 || (ndim > 0 && !shape)) return fail(h, CF_ERR_INVALID, "cf_load_tensor: null argument");
+  if (dtype != CF_F32) return fail(h, CF_ERR_INVALID, "cf_load_tensor: only fp32 host tensors are accepted");
+  if (h->finalized) return fail(h, CF_ERR_STATE, "cf_load_tensor: weights already finalized");
+  const std::string k(key);
+  if (k.rfind("encoder.", 0) != 0 && k.rfind("ctc.ctc_lo.", 0) != 0) return CF_OK;  // strict=False
+  int64_t n = 1;
+  std::vector<int64_t> shp;
+  for (int i = 0; i < ndim; ++i) { n *= shape[i]; shp.push_back(shape[i]); }
+  const float* src = static_cast<const float*>(data);
+  h->host_w[k].assign(src, src + n);
+  h->host_shape[k] = shp;
+  return CF_OK;
+}
+
+namespace {
+
+struct ArenaBuilder {
+  std::vector<uint8_t> host;
+  std::vector<std::pair<void**, size_t>> fixups;
+  size_t add_raw(const void* src, size_t bytes, void** target) {
+    size_t off = (host.size() + 255) & ~size_t(255);
+    host.resize(off + bytes);
+    if (src) memcpy(host.data() + off, src, bytes);
+    else memset(host.data() + off, 0, bytes);
+    fixups.push_back({target, off});
+    return off;
+  }
+  template <typename T> void f32(const std::vector<float>& v, T** target) {
+    add_raw(v.data(), v.size() * sizeof(float), reinterpret_cast<void**>(target));
+  }
+  template <typename T> void b16(const std::vector<float>& v, T** target) {
+    std::vector<uint16_t> t(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+      __nv_bfloat16 b = __float2bfloat16_rn(v[i]);
+      memcpy(&t[i], &b, 2);
+    }
+    add_raw(t.data(), t.size() * 2, reinterpret_cast<void**>(target));
+  }
+};
+
+}  // namespace
+
+extern "C" int cf_finalize_weights(cf_handle* h) {
+  if (!h) return fail(nullptr, CF_ERR_INVALID, "cf_finalize_weights: null handle");
+  if (h->finalized) return CF_OK;
+  const int d = h->cfg.d_model, F = h->cfg.ffn, L = h->cfg.layers, KW = h->cfg.kernel, V = h->cfg.vocab;
+  const int F3 = h->F3;
+  std::string missing;
+  auto get = [&](const std::string& key, int64_t expect) -> const std::vector<float>& {
+    static const std::vector<float> empty;
+    auto it = h->host_w.find(key);
+    if (it == h->host_w.end() || int64_t(it->second.size()) != expect) {
+      if (missing.empty()) missing = key + (it == h->host_w.end() ? " (absent)" : " (wrong size)");
+      return empty;
+    }
+    return it->second;
+  };
+  ArenaBuilder ab;
+  h->layers.assign(L, LayerW());
+  // ---- front-end
+  {
+    const auto& w0 = get("encoder.embed.conv.0.weight", int64_t(d) * 9);
+    const auto& b0 = get("encoder.embed.conv.0.bias", d);
+    const auto& w2 = get("encoder.embed.conv.2.weight", int64_t(d) * 9);
+    const auto& b2 = get("encoder.embed.conv.2.bias", d);
+    const auto& w3 = get("encoder.embed.conv.3.weight", int64_t(d) * d);
+    const auto& b3 = get("encoder.embed.conv.3.bias", d);
+    const auto& w5 = get("encoder.embed.conv.5.weight", int64_t(d) * 9);
+    const auto& b5 = get("encoder.embed.conv.5.bias", d);
+    const auto& w6 = get("encoder.embed.conv.6.weight", int64_t(d) * d);
+    const auto& b6 = get("encoder.embed.conv.6.bias", d);
+    const auto& wo = get("encoder.embed.out.weight", int64_t(d) * d * F3);
+    const auto& bo = get("encoder.embed.out.bias", d);
+    if (!missing.empty()) return fail(h, CF_ERR_STATE, "cf_finalize_weights: missing tensor " + missing);
+    std::vector<float> pack(size_t(d) * 20), dw2(size_t(9) * d), wperm(wo.size());
+    for (int ch = 0; ch < d; ++ch) {
+      for (int t = 0; t < 9; ++t) { pack[ch * 20 + t] = w0[ch * 9 + t]; pack[ch * 20 + 10 + t] = w2[ch * 9 + t]; }
+      pack[ch * 20 + 9] = b0[ch];
+      pack[ch * 20 + 19] = b2[ch];
+      for (int t = 0; t < 9; ++t) dw2[t * d + ch] = w5[ch * 9 + t];
+    }
+    // embed.out consumes features ordered (channel, freq) (subsampling.py:163-164); our rows are (freq, channel)
+    for (int o = 0; o < d; ++o)
+      for (int ch = 0; ch < d; ++ch)
+        for (int fq = 0; fq < F3; ++fq) wperm[size_t(o) * d * F3 + size_t(fq) * d + ch] = wo[size_t(o) * d * F3 + size_t(ch) * F3 + fq];
+    ab.f32(pack, &h->fe_wpack);
+    ab.b16(w3, &h->fe_w3); ab.f32(b3, &h->fe_b3);
+    ab.f32(dw2, &h->fe_dw2_w); ab.f32(b5, &h->fe_dw2_b);
+    ab.b16(w6, &h->fe_w6); ab.f32(b6, &h->fe_b6);
+    ab.b16(wperm, &h->fe_wout); ab.f32(bo, &h->fe_bout);
+    if (h->cfg.has_cmvn) {
+      const auto& mean = get("encoder.global_cmvn.mean", h->cfg.feat_dim);
+      const auto& istd = get("encoder.global_cmvn.istd", h->cfg.feat_dim);
+      if (!missing.empty()) return fail(h, CF_ERR_STATE, "cf_finalize_weights: missing tensor " + missing);
+      ab.f32(mean, &h->cmvn_mean); ab.f32(istd, &h->cmvn_istd);
+    }
+  }
+  // ---- layers
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "encoder.encoders." + std::to_string(i) + ".";
+    LayerW& w = h->layers[i];
+    auto lin = [&](const std::string& name, int64_t out_f, int64_t in_f, bf16** wt, float** bt) {
+      const auto& W = get(p + name + ".weight", out_f * in_f);
+      if (bt) { const auto& B = get(p + name + ".bias", out_f); if (missing.empty()) ab.f32(B, bt); }
+      if (missing.empty()) ab.b16(W, wt);
+    };
+    auto nrm = [&](const std::string& name, float** wt, float** bt) {
+      const auto& W = get(p + name + ".weight", d);
+      const auto& B = get(p + name + ".bias", d);
+      if (missing.empty()) { ab.f32(W, wt); ab.f32(B, bt); }
+    };
+    lin("feed_forward_macaron.w_1", F, d, &w.ffm_w1, &w.ffm_b1);
+    lin("feed_forward_macaron.w_2", d, F, &w.ffm_w2, &w.ffm_b2);
+    lin("feed_forward.w_1", F, d, &w.ff_w1, &w.ff_b1);
+    lin("feed_forward.w_2", d, F, &w.ff_w2, &w.ff_b2);
+    {
+      const auto& wq = get(p + "self_attn.linear_q.weight", int64_t(d) * d);
+      const auto& wk = get(p + "self_attn.linear_k.weight", int64_t(d) * d);
+      const auto& wv = get(p + "self_attn.linear_v.weight", int64_t(d) * d);
+      const auto& bq = get(p + "self_attn.linear_q.bias", d);
+      const auto& bk = get(p + "self_attn.linear_k.bias", d);
+      const auto& bv = get(p + "self_attn.linear_v.bias", d);
+      const auto& bu = get(p + "self_attn.pos_bias_u", d);
+      const auto& bvv = get(p + "self_attn.pos_bias_v", d);
+      if (missing.empty()) {
+        std::vector<float> W(wq); W.insert(W.end(), wk.begin(), wk.end()); W.insert(W.end(), wv.begin(), wv.end());
+        std::vector<float> B(bq); B.insert(B.end(), bk.begin(), bk.end()); B.insert(B.end(), bv.begin(), bv.end());
+        ab.b16(W, &w.qkv_w); ab.f32(B, &w.qkv_b); ab.f32(bu, &w.bias_u); ab.f32(bvv, &w.bias_v);
+      }
+    }
+    lin("self_attn.linear_out", d, d, &w.o_w, &w.o_b);
+    lin("self_attn.linear_pos", d, d, &w.pos_w, nullptr);
+    {
+      // pointwise_conv1 (2d, d, 1): interleave value / gate rows so GLU pairs sit in adjacent accumulator columns
+      const auto& W = get(p + "conv_module.pointwise_conv1.weight", int64_t(2) * d * d);
+      const auto& B = get(p + "conv_module.pointwise_conv1.bias", 2 * d);
+      if (missing.empty()) {
+        std::vector<float> Wi(W.size()), Bi(B.size());
+        for (int c = 0; c < d; ++c) {
+          memcpy(&Wi[size_t(2 * c) * d], &W[size_t(c) * d], d * sizeof(float));
+          memcpy(&Wi[size_t(2 * c + 1) * d], &W[size_t(d + c) * d], d * sizeof(float));
+          Bi[2 * c] = B[c]; Bi[2 * c + 1] = B[d + c];
+        }
+        ab.b16(Wi, &w.pw1_w); ab.f32(Bi, &w.pw1_b);
+      }
+    }
+    {
+      const auto& W = get(p + "conv_module.depthwise_conv.weight", int64_t(d) * KW);
+      const auto& B = get(p + "conv_module.depthwise_conv.bias", d);
+      if (missing.empty()) { ab.f32(W, &w.dw_w); ab.f32(B, &w.dw_b); }
+    }
+    nrm("conv_module.norm", &w.cn_w, &w.cn_b);
+    lin("conv_module.pointwise_conv2", d, d, &w.pw2_w, &w.pw2_b);
+    nrm("norm_ff_macaron", &w.ln_ffm_w, &w.ln_ffm_b);
+    nrm("norm_mha", &w.ln_mha_w, &w.ln_mha_b);
+    nrm("norm_conv", &w.ln_conv_w, &w.ln_conv_b);
+    nrm("norm_ff", &w.ln_ff_w, &w.ln_ff_b);
+    nrm("norm_final", &w.ln_fin_w, &w.ln_fin_b);
+    if (!missing.empty()) return fail(h, CF_ERR_STATE, "cf_finalize_weights: missing tensor " + missing);
+  }
+  {
+    const auto& W = get("encoder.after_norm.weight", d);
+    const auto& B = get("encoder.after_norm.bias", d);
+    if (!missing.empty()) return fail(h, CF_ERR_STATE, "cf_finalize_weights: missing tensor " + missing);
+    ab.f32(W, &h->after_w); ab.f32(B, &h->after_b);
+  }
+  if (V > 0) {
+    const auto& W = get("ctc.ctc_lo.weight", int64_t(V) * d);
+    const auto& B = get("ctc.ctc_lo.bias", V);
+    if (!missing.empty()) return fail(h, CF_ERR_STATE, "cf_finalize_weights: missing tensor " + missing);
+    ab.b16(W, &h->ctc_w); ab.f32(B, &h->ctc_b);
+  }
+  {
+    std::vector<float> z(size_t(std::max(std::max(4 * d, F), 2 * d)), 0.f);
+    ab.f32(z, &h->zeros);
+  }
+  CF_CUDA(h, cudaSetDevice(h->device));
+  CF_CUDA(h, cudaMalloc(&h->arena, ab.host.size()));
+  h->arena_bytes = ab.host.size();
+  CF_CUDA(h, cudaMemcpy(h->arena, ab.host.data(), ab.host.size(), cudaMemcpyHostToDevice));
+  for (auto& fx : ab.fixups) *fx.first = h->arena + fx.second;
+  h->host_w.clear();
+  h->host_shape.clear();
+  h->finalized = true;
+  return CF_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// plan
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" int cf_plan_create(int c, int l, int r, int kernel, int B, const int32_t* lens, const int32_t* offsets,
+                              const int64_t* feat_row_offsets, cf_plan** out) {
+  if (!lens || !out) return fail(nullptr, CF_ERR_INVALID, "cf_plan_create: null argument");
+  std::unique_ptr<cf_plan> p(new cf_plan());
+  std::string err;
+  if (!cfplan::build_masked(p.get(), c, l, r, kernel, B, lens, offsets, feat_row_offsets, &err))
+    return fail(nullptr, CF_ERR_INVALID, err);
+  *out = p.release();
+  return CF_OK;
+}
+extern "C" int cf_plan_create_padded(int c, int l, int r, int kernel, int B, int T, const int32_t* lens, cf_plan** out) {
+  if (!lens || !out) return fail(nullptr, CF_ERR_INVALID, "cf_plan_create_padded: null argument");
+  std::unique_ptr<cf_plan> p(new cf_plan());
+  std::string err;
+  if (!cfplan::build_padded(p.get(), c, l, r, kernel, B, T, lens, &err)) return fail(nullptr, CF_ERR_INVALID, err);
+  *out = p.release();
+  return CF_OK;
+}
+extern "C" void cf_plan_destroy(cf_plan* p) { delete p; }
+extern "C" int cf_plan_num_chunks(const cf_plan* p) { return p ? p->n : 0; }
+extern "C" int cf_plan_rows(const cf_plan* p) { return p ? p->n * p->c : 0; }
+extern "C" int cf_plan_tables(const cf_plan* p, int32_t* n_chunks_out, int32_t* enc_lens_out) {
+  if (!p) return fail(nullptr, CF_ERR_INVALID, "cf_plan_tables: null plan");
+  for (int u = 0; u < p->B; ++u) {
+    if (n_chunks_out) n_chunks_out[u] = p->n_chunks[u];
+    if (enc_lens_out) enc_lens_out[u] = p->enc_lens[u];
+  }
+  return CF_OK;
+}
+extern "C" int cf_plan_masks(const cf_plan* p, uint8_t* att_mask, uint8_t* conv_mask) {
+  if (!p) return fail(nullptr, CF_ERR_INVALID, "cf_plan_masks: null plan");
+  const int W = p->l + p->c + p->r, CW = p->c + 2 * p->lorder;
+  for (int g = 0; g < p->n; ++g) {
+    const cf_chunk_entry& e = p->chunks[g];
+    if (att_mask)
+      for (int q = 0; q < W; ++q) att_mask[size_t(g) * W + q] = (q >= e.att_lo && q < e.att_hi) ? 1 : 0;
+    if (conv_mask)
+      for (int q = 0; q < CW; ++q) conv_mask[size_t(g) * CW + q] = (q >= e.conv_lo && q < e.conv_hi) ? 1 : 0;
+  }
+  return CF_OK;
+}
+extern "C" int cf_plan_chunk_table(const cf_plan* p, int32_t* table) {
+  if (!p || !table) return fail(nullptr, CF_ERR_INVALID, "cf_plan_chunk_table: null argument");
+  static_assert(sizeof(cf_chunk_entry) == 32, "chunk entry layout");
+  memcpy(table, p->chunks.data(), size_t(p->n) * sizeof(cf_chunk_entry));
+  return CF_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// kernel dispatch helpers
+// --------------------------------------------------------------------------------------------------------------------
+namespace {
+
+bool run_layernorm(int mode, int d, const LnParams& p, cudaStream_t st, std::string* err) {
+  if (p.rows == 0) return true;
+  const int warps = 8;
+  const unsigned grid = unsigned((p.rows + warps - 1) / warps);
+#define CF_LN(D, MODE) layernorm_kernel<D, MODE><<<grid, warps * 32, 0, st>>>(p)
+  if (d == 512) { if (mode == 0) CF_LN(512, 0); else if (mode == 1) CF_LN(512, 1); else CF_LN(512, 2); }
+  else if (d == 256) { if (mode == 0) CF_LN(256, 0); else if (mode == 1) CF_LN(256, 1); else CF_LN(256, 2); }
+  else { *err = "layernorm: d must be 256 or 512"; return false; }
+#undef CF_LN
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("layernorm launch: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+
+template <int D>
+bool run_dwconv_d(const DwConvParams& p, cudaStream_t st, std::string* err) {
+  const int c = p.c;
+#define CF_DW(FG) dwconv_ln_silu_kernel<D, 15, FG><<<p.n_chunks * (c / FG), D / 2, 0, st>>>(p)
+  if (c % 32 == 0) CF_DW(32);
+  else if (c % 16 == 0) CF_DW(16);
+  else if (c % 8 == 0) CF_DW(8);
+  else if (c % 4 == 0) CF_DW(4);
+  else if (c % 2 == 0) CF_DW(2);
+  else CF_DW(1);
+#undef CF_DW
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("dwconv launch: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+bool run_dwconv(int d, int kernel, const DwConvParams& p, cudaStream_t st, std::string* err) {
+  if (kernel != 15) { *err = "dwconv: kernel must be 15"; return false; }
+  if (p.n_chunks == 0) return true;
+  if (d == 512) return run_dwconv_d<512>(p, st, err);
+  if (d == 256) return run_dwconv_d<256>(p, st, err);
+  *err = "dwconv: d must be 256 or 512";
+  return false;
+}
+
+bool attention_tc_supported(int c, int l, int r, int dk) {
+  return c == 64 && dk == 64 && (l % 64) == 0 && (r % 64) == 0 && (l + r) <= 256;
+}
+
+bool run_attention(int impl, const AttnParams& p, cudaStream_t st, std::string* err) {
+  if (p.n_chunks == 0) return true;
+  const int dk = p.d / p.heads;
+  if (impl == 1) {
+    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernel needs c=64, d_k=64, l,r multiples of 64, l+r<=256"; return false; }
+    return launch_attention_tc(p, st, err);
+  }
+  const int W = p.l + p.c + p.r;
+  const size_t smem = size_t(4) * (2 * dk + W) * sizeof(float);
+  dim3 grid(p.n_chunks, p.heads);
+  cudaError_t e;
+  if (dk == 64) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(attention_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attention_simt_kernel<64><<<grid, 128, smem, st>>>(p);
+  } else if (dk == 128) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(attention_simt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attention_simt_kernel<128><<<grid, 128, smem, st>>>(p);
+  } else { *err = "attention: d_k must be 64 or 128"; return false; }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("attention launch: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+
+struct Carver {  // carve a caller-provided workspace into 256-byte aligned pieces
+  uint8_t* base; size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <typename T> T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+constexpr int FE_SLAB_CHUNKS = 256;
+
+struct EncodeWs {
+  ChunkSrc* chunk_src; int2 *att_range, *conv_range, *out_range; int* seq_limit;
+  float* x; bf16 *y, *hbuf, *qkv, *ctx, *g, *z, *a1, *b1, *a2, *b2;
+  size_t qkv_rows, g_rows;
+  size_t total;
+};
+
+EncodeWs carve_encode(const cf_handle* h, const cf_plan* p, void* base) {
+  const int d = h->cfg.d_model, F = h->cfg.ffn, c = p->c;
+  const size_t n = size_t(p->n), Mr = n * c;
+  const int T2 = 2 * c + 1, F2 = (((h->cfg.feat_dim - 3) / 2 + 1) - 3) / 2 + 1;
+  const size_t S = std::min<size_t>(n, FE_SLAB_CHUNKS);
+  EncodeWs w;
+  Carver cv(base);
+  w.chunk_src = cv.take<ChunkSrc>(n);
+  w.att_range = cv.take<int2>(n + 2);
+  w.conv_range = cv.take<int2>(n);
+  w.out_range = cv.take<int2>(n);
+  w.seq_limit = cv.take<int>(size_t(p->B));
+  w.x = cv.take<float>(Mr * d);
+  w.y = cv.take<bf16>(Mr * d);
+  w.hbuf = cv.take<bf16>(Mr * F);
+  w.qkv_rows = size_t(p->l) + Mr + size_t(p->r) + 2 * size_t(c) + 128;
+  w.qkv = cv.take<bf16>(w.qkv_rows * 4 * d);
+  w.ctx = cv.take<bf16>(Mr * d);
+  w.g_rows = Mr + 2 * size_t(p->lorder) + 64;
+  w.g = cv.take<bf16>(w.g_rows * d);
+  w.z = cv.take<bf16>(Mr * d);
+  w.a1 = cv.take<bf16>(S * T2 * F2 * d);
+  w.b1 = cv.take<bf16>(S * T2 * F2 * d);
+  w.a2 = cv.take<bf16>(S * c * h->F3 * d);
+  w.b2 = cv.take<bf16>(S * c * h->F3 * d);
+  w.total = cv.off + 256;
+  return w;
+}
+
+// Projected relative-position tables P_l = linear_pos_l(PE) for all layers (embedding.py:119-174, attention.py:482):
+// input independent, computed once per (c, l, r) and cached on the handle.
+int get_pos_table(cf_handle* h, int c, int l, int r, cudaStream_t st, const PosTable** out) {
+  for (auto& t : h->pos_tables)
+    if (t.c == c && t.l == l && t.r == r) { *out = &t; return CF_OK; }
+  const int d = h->cfg.d_model, L = h->cfg.layers;
+  PosTable t;
+  t.c = c; t.l = l; t.r = r; t.R = 2 * c + l + r - 1;
+  t.Rpad = ((t.R + 127) / 128) * 128;
+  std::vector<uint16_t> pe(size_t(t.Rpad) * d, 0);
+  for (int p = 0; p < t.R; ++p) {
+    const float rho = float(c + l - 1 - p);
+    for (int m = 0; m < d / 2; ++m) {
+      const float w = expf(float(2 * m) * -(logf(10000.0f) / float(d)));
+      const float ang = fabsf(rho) * w;
+      const float s = sinf(ang) * (rho < 0 ? -1.f : (rho > 0 ? 1.f : 0.f)), co = cosf(ang);
+      __nv_bfloat16 bs = __float2bfloat16_rn(s), bc = __float2bfloat16_rn(co);
+      memcpy(&pe[size_t(p) * d + 2 * m], &bs, 2);
+      memcpy(&pe[size_t(p) * d + 2 * m + 1], &bc, 2);
+    }
+  }
+  bf16* pe_dev = nullptr;
+  CF_CUDA(h, cudaMalloc(&pe_dev, pe.size() * 2));
+  CF_CUDA(h, cudaMalloc(&t.dev, size_t(L) * t.Rpad * d * 2));
+  CF_CUDA(h, cudaMemcpyAsync(pe_dev, pe.data(), pe.size() * 2, cudaMemcpyHostToDevice, st));
+  CF_CUDA(h, cudaMemsetAsync(t.dev, 0, size_t(L) * t.Rpad * d * 2, st));
+  for (int i = 0; i < L; ++i) {
+    GemmLaunch g{};
+    g.A = pe_dev; g.lda = d; g.B = h->layers[i].pos_w; g.ldb = d; g.M = t.R; g.N = d; g.K = d; g.epi = EPI_BF16;
+    g.ep.bias = h->zeros; g.ep.out = t.dev + size_t(i) * t.Rpad * d; g.ep.ldo = d; g.ep.act = ACT_NONE;
+    std::string err;
+    if (!launch_gemm(g, h->num_sms, st, &err)) { cudaFree(pe_dev); return fail(h, CF_ERR_CUDA, err); }
+  }
+  CF_CUDA(h, cudaStreamSynchronize(st));
+  cudaFree(pe_dev);
+  h->pos_tables.push_back(t);
+  *out = &h->pos_tables.back();
+  return CF_OK;
+}
+
+}  // namespace
+
+extern "C" size_t cf_workspace_bytes(const cf_handle* h, const cf_plan* p) {
+  if (!h || !p) return 0;
+  return carve_encode(h, p, nullptr).total;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// encoder driver
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, void* att_cache, void* cnn_cache,
+                         int trunc, void* out, int out_dtype, void* out_bf16, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (!h || !p || !feats || !out || !workspace) return fail(h, CF_ERR_INVALID, "cf_encode: null argument");
+  if (!h->finalized) return fail(h, CF_ERR_STATE, "cf_encode: call cf_finalize_weights first");
+  if (out_dtype != CF_F32 && out_dtype != CF_BF16) return fail(h, CF_ERR_INVALID, "cf_encode: bad out_dtype");
+  if (p->kernel != h->cfg.kernel) return fail(h, CF_ERR_INVALID, "cf_encode: plan conv kernel differs from the model's");
+  if ((att_cache || cnn_cache) && (p->mode != 0 || p->B != 1))
+    return fail(h, CF_ERR_INVALID, "cf_encode: streaming caches need a masked-batch plan with one utterance");
+  if ((att_cache != nullptr) != (cnn_cache != nullptr))
+    return fail(h, CF_ERR_INVALID, "cf_encode: pass both caches or neither");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CF_CUDA(h, cudaSetDevice(h->device));
+  const EncodeWs w = carve_encode(h, p, workspace);
+  if (w.total > workspace_bytes) return fail(h, CF_ERR_WORKSPACE, "cf_encode: workspace too small");
+  const int d = h->cfg.d_model, F = h->cfg.ffn, L = h->cfg.layers, H = h->cfg.heads, dk = d / H;
+  const int c = p->c, l = p->l, r = p->r, lo = p->lorder;
+  const int n = p->n;
+  const long long Mr = (long long)n * c;
+  if (Mr == 0) return CF_OK;
+  if (att_cache && (trunc < 0 || trunc > Mr)) return fail(h, CF_ERR_INVALID, "cf_encode: truncated_context_size out of range");
+  std::string err;
+  const PosTable* pos = nullptr;
+  int rc = get_pos_table(h, c, l, r, st, &pos);
+  if (rc != CF_OK) return rc;
+
+  // ---- tables
+  {
+    std::vector<ChunkSrc> cs(n);
+    std::vector<int2> ar(n + 2), cr(n), orr(n);
+    for (int g = 0; g < n; ++g) {
+      cs[g].feat_row = p->chunk_feat_row[g]; cs[g].in_len = p->chunk_in_len[g]; cs[g].pad_ = 0;
+      const cf_chunk_entry& e = p->chunks[g];
+      ar[g] = make_int2(e.att_lo, e.att_hi); cr[g] = make_int2(e.conv_lo, e.conv_hi); orr[g] = make_int2(e.out_lo, e.out_hi);
+    }
+    ar[n] = ar[n + 1] = make_int2(0, 0);   // phantom chunks read by the chunk-pair attention kernel
+    CF_CUDA(h, cudaMemcpyAsync(w.chunk_src, cs.data(), n * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaMemcpyAsync(w.att_range, ar.data(), (n + 2) * sizeof(int2), cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaMemcpyAsync(w.conv_range, cr.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaMemcpyAsync(w.out_range, orr.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
+    if (p->mode == 1)
+      CF_CUDA(h, cudaMemcpyAsync(w.seq_limit, p->seq_valid_rows.data(), p->B * sizeof(int), cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaStreamSynchronize(st));  // host vectors go out of scope
+  }
+  // zero the halo rows of the flat buffers once (cache rows are rewritten per layer when streaming)
+  CF_CUDA(h, cudaMemsetAsync(w.qkv, 0, size_t(l) * 4 * d * sizeof(bf16), st));
+  CF_CUDA(h, cudaMemsetAsync(w.qkv + (size_t(l) + Mr) * 4 * d, 0, (w.qkv_rows - size_t(l) - Mr) * 4 * d * sizeof(bf16), st));
+  CF_CUDA(h, cudaMemsetAsync(w.g, 0, size_t(lo) * d * sizeof(bf16), st));
+  CF_CUDA(h, cudaMemsetAsync(w.g + (size_t(lo) + Mr) * d, 0, (w.g_rows - size_t(lo) - Mr) * d * sizeof(bf16), st));
+
+  auto gemm = [&](const void* A, long long lda, const void* B, long long ldb, long long M, int N, int K, int epi,
+                  const GemmEpiParams& ep) -> bool {
+    GemmLaunch g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = int(M); g.N = N; g.K = K; g.epi = epi; g.ep = ep;
+    return launch_gemm(g, h->num_sms, st, &err);
+  };
+#define CF_TRY(expr) do { if (!(expr)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err); } while (0)
+
+  // ---- front-end: slabs of chunks through conv0+dw1 -> pw1 -> dw2 -> pw2 -> out Linear
+  {
+    const int T2 = 2 * c + 1, F1 = (h->cfg.feat_dim - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1, F3 = h->F3;
+    const size_t fe_smem = (size_t(d) * 20 + size_t(39) * h->cfg.feat_dim) * sizeof(float) + 128 * 33 * sizeof(uint32_t);
+    if (d == 512) CF_CUDA(h, cudaFuncSetAttribute(frontend_conv0_dw1_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fe_smem)));
+    else CF_CUDA(h, cudaFuncSetAttribute(frontend_conv0_dw1_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fe_smem)));
+    if (F2 < 16) return fail(h, CF_ERR_INVALID, "cf_encode: feat_dim too small for the front-end tiling");
+    for (int g0 = 0; g0 < n; g0 += FE_SLAB_CHUNKS) {
+      const int S = std::min(FE_SLAB_CHUNKS, n - g0);
+      Fe1Params f1{};
+      f1.feats = feats; f1.chunks = w.chunk_src + g0; f1.wpack = h->fe_wpack; f1.cmvn_mean = h->cmvn_mean; f1.cmvn_istd = h->cmvn_istd;
+      f1.out = w.a1; f1.n_chunks = S; f1.feat_dim = h->cfg.feat_dim; f1.T2 = T2; f1.F2 = F2; f1.in_rows = p->in_rows;
+      const int bpc = (T2 * F2 + 127) / 128;
+      if (d == 512) frontend_conv0_dw1_kernel<512><<<S * bpc, 128, fe_smem, st>>>(f1);
+      else frontend_conv0_dw1_kernel<256><<<S * bpc, 128, fe_smem, st>>>(f1);
+      CF_CUDA(h, cudaGetLastError());
+      GemmEpiParams e1; e1.bias = h->fe_b3; e1.out = w.b1; e1.ldo = d; e1.act = ACT_RELU;
+      CF_TRY(gemm(w.a1, d, h->fe_w3, d, (long long)S * T2 * F2, d, d, EPI_BF16, e1));
+      Fe2Params f2{};
+      f2.in = w.b1; f2.out = w.a2; f2.w = h->fe_dw2_w; f2.bias = h->fe_dw2_b; f2.T2 = T2; f2.F2 = F2; f2.T3 = c; f2.F3 = F3;
+      f2.total = (long long)S * c * F3 * (d / 8);
+      const unsigned g2 = unsigned((f2.total + 255) / 256);
+      if (d == 512) frontend_dw2_kernel<512><<<g2, 256, 0, st>>>(f2);
+      else frontend_dw2_kernel<256><<<g2, 256, 0, st>>>(f2);
+      CF_CUDA(h, cudaGetLastError());
+      GemmEpiParams e2; e2.bias = h->fe_b6; e2.out = w.b2; e2.ldo = d; e2.act = ACT_RELU;
+      CF_TRY(gemm(w.a2, d, h->fe_w6, d, (long long)S * c * F3, d, d, EPI_BF16, e2));
+      // (xW + b) * sqrt(d)  (subsampling.py:164, embedding.py:198)
+      GemmEpiParams e3; e3.bias = h->fe_bout; e3.out = w.x + (size_t)g0 * c * d; e3.ldo = d; e3.alpha = sqrtf(float(d));
+      CF_TRY(gemm(w.b2, (long long)F3 * d, h->fe_wout, (long long)F3 * d, (long long)S * c, d, F3 * d, EPI_F32, e3));
+    }
+  }
+
+  // ---- layers (encoder_layer.py:155-248)
+  auto ln = [&](int mode, const float* w1, const float* b1, const float* w2, const float* b2, float* xo, bf16* y,
+                bool limit) -> bool {
+    LnParams q{};
+    q.x_in = w.x; q.x_out = xo; q.y = y; q.w1 = w1; q.b1 = b1; q.w2 = w2; q.b2 = b2; q.rows = Mr;
+    q.row_limit = limit ? w.seq_limit : nullptr; q.rows_per_seq = limit ? p->rows_per_seq : 1;
+    return run_layernorm(mode, d, q, st, &err);
+  };
+  const bool use_tc = kAttentionTcReady && attention_tc_supported(c, l, r, dk);
+  CF_TRY(ln(0, h->layers[0].ln_ffm_w, h->layers[0].ln_ffm_b, nullptr, nullptr, nullptr, w.y, false));
+  for (int i = 0; i < L; ++i) {
+    const LayerW& lw = h->layers[i];
+    // macaron FFN: x += 0.5 * W2 SiLU(W1 LN(x) + b1) + b2
+    { GemmEpiParams e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
+      CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
+    { GemmEpiParams e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
+      CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
+    // self-attention
+    CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
+    if (att_cache && l > 0) {
+      const int tot = l * H * 2 * dk;
+      att_cache_import_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<const float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d);
+    }
+    { GemmEpiParams e; e.bias = lw.qkv_b; e.bias_u = lw.bias_u; e.bias_v = lw.bias_v; e.qkv_d = d;
+      e.out = w.qkv + size_t(l) * 4 * d; e.ldo = 4 * d;
+      CF_TRY(gemm(w.y, d, lw.qkv_w, d, Mr, 3 * d, d, EPI_QKV, e)); }
+    if (att_cache && l > 0) {
+      const int tot = l * H * 2 * dk;
+      att_cache_export_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d, trunc);
+    }
+    { AttnParams a{};
+      a.qkv = w.qkv; a.pos = pos->dev + size_t(i) * pos->Rpad * d; a.range = w.att_range; a.ctx = w.ctx;
+      a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk));
+      CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
+    { GemmEpiParams e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
+      CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
+    // convolution module
+    CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
+    if (cnn_cache) cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo);
+    { GemmEpiParams e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
+      CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mr, 2 * d, d, EPI_GLU, e)); }
+    if (cnn_cache) cnn_cache_export_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo, trunc);
+    { DwConvParams q{};
+      q.g = w.g; q.z = w.z; q.w = lw.dw_w; q.bias = lw.dw_b; q.ln_w = lw.cn_w; q.ln_b = lw.cn_b; q.range = w.conv_range; q.c = c; q.n_chunks = n;
+      CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err)); }
+    { GemmEpiParams e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
+      e.row_range = w.out_range; e.rows_per_chunk = c;
+      CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
+    // FFN
+    CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
+    { GemmEpiParams e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
+      CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mr, F, d, EPI_BF16, e)); }
+    { GemmEpiParams e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
+      CF_TRY(gemm(w.hbuf, F, lw.ff_w2, F, Mr, d, F, EPI_F32, e)); }
+    if (i + 1 < L) {
+      CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));
+    } else {
+      // norm_final of the last layer + after_norm (encoder.py:670-671)
+      LnParams q{};
+      q.x_in = w.x; q.w1 = lw.ln_fin_w; q.b1 = lw.ln_fin_b; q.w2 = h->after_w; q.b2 = h->after_b; q.rows = Mr;
+      q.x_out = out_dtype == CF_F32 ? static_cast<float*>(out) : nullptr;
+      q.y = out_dtype == CF_BF16 ? static_cast<bf16*>(out) : static_cast<bf16*>(out_bf16);
+      q.rows_per_seq = 1;
+      CF_TRY(run_layernorm(2, d, q, st, &err));
+      if (out_dtype == CF_BF16 && out_bf16 && out_bf16 != out)
+        CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  CF_CUDA(h, cudaGetLastError());
+  return CF_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// CTC head
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows) {
+  if (!h || rows <= 0) return 256;
+  const size_t nt = size_t((h->cfg.vocab + 255) / 256);
+  return 3 * (size_t(rows) * nt * 4 + 256) + 256;
+}
+
+extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, int64_t* tokens_out, float* margin_out,
+                             float* logp_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !enc_bf16 || !tokens_out || !workspace) return fail(h, CF_ERR_INVALID, "cf_ctc_greedy: null argument");
+  if (!h->finalized || h->cfg.vocab <= 0 || !h->ctc_w) return fail(h, CF_ERR_STATE, "cf_ctc_greedy: no CTC head loaded");
+  if (rows <= 0) return CF_OK;
+  if (workspace_bytes < cf_ctc_workspace_bytes(h, rows)) return fail(h, CF_ERR_WORKSPACE, "cf_ctc_greedy: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CF_CUDA(h, cudaSetDevice(h->device));
+  const int d = h->cfg.d_model, V = h->cfg.vocab;
+  const int nt = (V + 255) / 256;
+  Carver cv(workspace);
+  float* best = cv.take<float>(size_t(rows) * nt);
+  float* second = cv.take<float>(size_t(rows) * nt);
+  int* index = cv.take<int>(size_t(rows) * nt);
+  std::string err;
+  GemmLaunch g{};
+  g.A = enc_bf16; g.lda = d; g.B = h->ctc_w; g.ldb = d; g.M = int(rows); g.N = V; g.K = d; g.epi = EPI_ARGMAX;
+  g.ep.bias = h->ctc_b; g.ep.part_best = best; g.ep.part_second = second; g.ep.part_index = index;
+  if (!launch_gemm(g, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_ctc_greedy: " + err);
+  ctc_reduce_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(best, second, index, nt, rows,
+                                                                   reinterpret_cast<long long*>(tokens_out), margin_out);
+  CF_CUDA(h, cudaGetLastError());
+  if (logp_out) {
+    GemmLaunch q{};
+    q.A = enc_bf16; q.lda = d; q.B = h->ctc_w; q.ldb = d; q.M = int(rows); q.N = V; q.K = d; q.epi = EPI_F32;
+    q.ep.bias = h->ctc_b; q.ep.out = logp_out; q.ep.ldo = V; q.ep.alpha = 1.0f;
+    if (V % 4 != 0) return fail(h, CF_ERR_INVALID, "cf_ctc_greedy: logp_out needs vocab % 4 == 0");
+    if (!launch_gemm(q, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_ctc_greedy: " + err);
+    log_softmax_rows_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(logp_out, rows, V);
+    CF_CUDA(h, cudaGetLastError());
+  }
+  return CF_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// kernel-level entry points
+// --------------------------------------------------------------------------------------------------------------------
+static int current_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+extern "C" int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, int act,
+                          const float* bias, const float* bias_u, const float* bias_v, int qkv_d, const float* resid,
+                          int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk, void* out,
+                          int64_t ldo, float* part_best, float* part_second, int32_t* part_index, void* stream) {
+  if (!A || !B || !bias) return fail(nullptr, CF_ERR_INVALID, "cf_op_gemm: null argument");
+  GemmLaunch g{};
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.epi = epi;
+  g.ep.bias = bias; g.ep.bias_u = bias_u; g.ep.bias_v = bias_v; g.ep.qkv_d = qkv_d; g.ep.resid = resid;
+  g.ep.ld_resid = ld_resid; g.ep.alpha = alpha; g.ep.act = act; g.ep.row_range = reinterpret_cast<const int2*>(row_range);
+  g.ep.rows_per_chunk = rows_per_chunk > 0 ? rows_per_chunk : 1; g.ep.out = out; g.ep.ldo = ldo;
+  g.ep.part_best = part_best; g.ep.part_second = part_second; g.ep.part_index = part_index;
+  std::string err;
+  if (!launch_gemm(g, current_sms(), static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  return CF_OK;
+}
+
+extern "C" int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1,
+                               const float* b1, const float* w2, const float* b2, int64_t rows, void* stream) {
+  LnParams q{};
+  q.x_in = x_in; q.x_out = x_out; q.y = static_cast<bf16*>(y_bf16); q.w1 = w1; q.b1 = b1; q.w2 = w2; q.b2 = b2;
+  q.rows = rows; q.row_limit = nullptr; q.rows_per_seq = 1;
+  std::string err;
+  if (!run_layernorm(mode, d, q, static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  return CF_OK;
+}
+
+extern "C" int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16, const float* w, const float* bias,
+                            const float* ln_w, const float* ln_b, const int32_t* range, int c, int n_chunks, void* stream) {
+  DwConvParams q{};
+  q.g = static_cast<const bf16*>(g_bf16); q.z = static_cast<bf16*>(z_bf16); q.w = w; q.bias = bias; q.ln_w = ln_w;
+  q.ln_b = ln_b; q.range = reinterpret_cast<const int2*>(range); q.c = c; q.n_chunks = n_chunks;
+  std::string err;
+  if (!run_dwconv(d, kernel, q, static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  return CF_OK;
+}
+
+extern "C" int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_bf16, const int32_t* range, void* ctx_bf16,
+                               int n_chunks, int c, int l, int r, int d, int heads, void* stream) {
+  AttnParams a{};
+  a.qkv = static_cast<const bf16*>(qkv_bf16); a.pos = static_cast<const bf16*>(pos_bf16);
+  a.range = reinterpret_cast<const int2*>(range); a.ctx = static_cast<bf16*>(ctx_bf16);
+  a.n_chunks = n_chunks; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = heads; a.scale = 1.0f / sqrtf(float(d / heads));
+  std::string err;
+  if (!run_attention(impl, a, static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  return CF_OK;
+}

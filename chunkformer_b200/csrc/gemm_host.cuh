@@ -1,0 +1,105 @@
+// Host-side launcher for the tcgen05 GEMM: tensor-map encoding (driver entry point fetched at run time so the
+// library links only against the static CUDA runtime and loads on a machine without a driver).
+#pragma once
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <string>
+
+#include "gemm.cuh"
+
+namespace cf {
+
+inline PFN_cuTensorMapEncodeTiled_v12000 get_tensor_map_encoder(std::string* err) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  static std::string init_err;
+  std::call_once(once, [&]() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+      init_err = std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e);
+      cudaGetLastError();
+    } else {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  if (!fn && err) *err = init_err;
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
+inline bool make_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows, uint32_t box_cols, std::string* err) {
+  auto enc = get_tensor_map_encoder(err);
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r));
+    return false;
+  }
+  return true;
+}
+
+struct GemmLaunch {
+  const void* A; long long lda;  // [M, K] bf16
+  const void* B; long long ldb;  // [N, K] bf16 (nn.Linear weight layout)
+  int M, N, K;
+  int epi;
+  GemmEpiParams ep;
+};
+
+template <int EPI>
+inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
+  constexpr int BN = 256;
+  CUtensorMap ta, tb;
+  if (!make_tma_2d_bf16(&ta, g.A, g.M, g.K, g.lda, GEMM_BM, GEMM_BK, err)) return false;
+  if (!make_tma_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, BN, GEMM_BK, err)) return false;
+  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  static bool attr_set = false;
+  const size_t smem = gemm_smem_bytes<BN>();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e);
+      return false;
+    }
+    attr_set = true;
+  }
+  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  if (tiles == 0) return true;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, g.M, g.N, g.K, g.ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("gemm launch: ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+inline bool launch_gemm(const GemmLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
+  if (g.K % GEMM_BK != 0 || g.lda % 8 != 0 || g.ldb % 8 != 0) {
+    if (err) *err = "gemm: K must be a multiple of 64 and leading dimensions multiples of 8";
+    return false;
+  }
+  switch (g.epi) {
+    case EPI_BF16: return launch_gemm_epi<EPI_BF16>(g, num_sms, stream, err);
+    case EPI_GLU: return launch_gemm_epi<EPI_GLU>(g, num_sms, stream, err);
+    case EPI_F32: return launch_gemm_epi<EPI_F32>(g, num_sms, stream, err);
+    case EPI_QKV: return launch_gemm_epi<EPI_QKV>(g, num_sms, stream, err);
+    case EPI_ARGMAX: return launch_gemm_epi<EPI_ARGMAX>(g, num_sms, stream, err);
+  }
+  if (err) *err = "gemm: unknown epilogue";
+  return false;
+}
+
+}  // namespace cf

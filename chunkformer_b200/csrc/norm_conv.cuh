@@ -1,0 +1,215 @@
+// Bandwidth-bound kernels of the encoder layer: LayerNorm variants and the chunk-aware depthwise-conv core.
+#pragma once
+#include "common.cuh"
+
+namespace cf {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over d channels, one warp per row, fp32 statistics (eps 1e-5; encoder_layer.py:46-57).
+//   MODE 0: y_bf16 = LN1(x)
+//   MODE 1: x_f32 <- LN1(x) in place, y_bf16 = LN2(LN1(x))     (norm_final of layer i + norm_ff_macaron of layer i+1)
+//   MODE 2: out = LN2(LN1(x))  (norm_final of the last layer + after_norm, encoder.py:670-671), fp32 and/or bf16 out
+// Rows >= `zero_from` per batch element are written as zeros in MODE 0 when row_limit != nullptr (forward_encoder's
+// x.masked_fill_ before pointwise_conv1, convolution.py:125-127).
+// ---------------------------------------------------------------------------------------------
+struct LnParams {
+  const float* x_in;
+  float* x_out;            // MODE 1: normalised residual stream (may alias x_in); MODE 2: fp32 output (nullable)
+  __nv_bfloat16* y;        // bf16 output (MODE 2: nullable)
+  const float* w1; const float* b1;
+  const float* w2; const float* b2;
+  long long rows;
+  const int* row_limit;    // optional [rows / rows_per_seq]: rows with (row % rows_per_seq) >= limit are zeroed in y
+  int rows_per_seq;
+};
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(256) layernorm_kernel(LnParams p) {
+  constexpr int PER = D / 32;      // floats per lane
+  constexpr int V4 = PER / 4;      // float4 per lane
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const float* xr = p.x_in + row * D;
+  float v[PER];
+#pragma unroll
+  for (int k = 0; k < V4; ++k) {
+    const float4 t = *reinterpret_cast<const float4*>(xr + k * 128 + lane * 4);
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+  auto normalise = [&](const float* w, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { const float dlt = v[i] - mean; q += dlt * dlt; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < V4; ++k) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + k * 128 + lane * 4));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + k * 128 + lane * 4));
+      v[4 * k] = (v[4 * k] - mean) * rstd * ww.x + bb.x;
+      v[4 * k + 1] = (v[4 * k + 1] - mean) * rstd * ww.y + bb.y;
+      v[4 * k + 2] = (v[4 * k + 2] - mean) * rstd * ww.z + bb.z;
+      v[4 * k + 3] = (v[4 * k + 3] - mean) * rstd * ww.w + bb.w;
+    }
+  };
+  normalise(p.w1, p.b1);
+  if (MODE == 1) {
+    float* xo = p.x_out + row * D;
+#pragma unroll
+    for (int k = 0; k < V4; ++k)
+      *reinterpret_cast<float4*>(xo + k * 128 + lane * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+  if (MODE >= 1) normalise(p.w2, p.b2);
+  if (MODE == 2 && p.x_out) {
+    float* xo = p.x_out + row * D;
+#pragma unroll
+    for (int k = 0; k < V4; ++k)
+      *reinterpret_cast<float4*>(xo + k * 128 + lane * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+  if (p.y) {
+    bool zero = false;
+    if (MODE == 0 && p.row_limit) {
+      const long long s = row / p.rows_per_seq;
+      zero = (row - s * p.rows_per_seq) >= p.row_limit[s];
+    }
+    __nv_bfloat16* yr = p.y + row * D;
+#pragma unroll
+    for (int k = 0; k < V4; ++k) {
+      uint2 o;
+      o.x = zero ? 0u : pack_bf16(v[4 * k], v[4 * k + 1]);
+      o.y = zero ? 0u : pack_bf16(v[4 * k + 2], v[4 * k + 3]);
+      *reinterpret_cast<uint2*>(yr + k * 128 + lane * 4) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chunk-aware depthwise conv core (convolution.py:224-249): for every chunk, 15-tap depthwise conv over the GLU
+// output with context halos read by index from the flat buffer (no unfold copy), + bias, LayerNorm over channels,
+// SiLU.  One CTA = FG consecutive frames of one chunk x all D channels; thread = 2 adjacent channels.
+//   g      : [halo + frames + halo, D] bf16, row (lorder + flat_frame)
+//   window slot q of chunk (frame c*chunk - lorder + q) contributes iff range[chunk].x <= q < range[chunk].y
+//   z      : [frames, D] bf16
+// Bytes per frame: read 2*D (each row once from HBM; halo re-reads hit L2), write 2*D.
+// ---------------------------------------------------------------------------------------------
+struct DwConvParams {
+  const __nv_bfloat16* g;
+  __nv_bfloat16* z;
+  const float* w;       // [D, KW] depthwise taps (depthwise_conv.weight (d,1,15))
+  const float* bias;    // [D]
+  const float* ln_w; const float* ln_b;
+  const int2* range;    // [n_chunks] valid window-slot range
+  int c;                // chunk size (frames)
+  int n_chunks;
+};
+
+
+// Sum v[f] over all threads of the CTA for every frame f; result (scaled, optionally rsqrt(x + eps)) lands in s_out[f].
+// FG == 32 uses a lane-transposing butterfly (31 shuffles for 32 values) instead of 32 full warp reductions.
+template <int FG, int NW>
+CF_DEVINL void frame_reduce(float (&v)[FG], float (*s_part)[FG], float* s_out, float scale, bool to_rstd) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (FG == 32) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = up ? v[i] : v[i + off];
+        const float keep = up ? v[i + off] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    s_part[warp][lane] = v[0];
+  } else {
+#pragma unroll
+    for (int f = 0; f < FG; ++f) {
+      const float a = warp_sum(v[f]);
+      if (lane == 0) s_part[warp][f] = a;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < FG) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) a += s_part[w][threadIdx.x];
+    a *= scale;
+    s_out[threadIdx.x] = to_rstd ? rsqrtf(a + 1e-5f) : a;
+  }
+  __syncthreads();
+}
+
+template <int D, int KW, int FG>
+__global__ void __launch_bounds__(D / 2) dwconv_ln_silu_kernel(DwConvParams p) {
+  constexpr int NT = D / 2;
+  constexpr int NW = NT / 32;
+  constexpr int LO = KW / 2;
+  constexpr int ROWS = FG + KW - 1;
+  __shared__ float s_part[NW][FG];
+  __shared__ float s_mean[FG];
+  __shared__ float s_rstd[FG];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = p.c / FG;
+  const int chunk = blockIdx.x / groups;
+  const int f0 = (blockIdx.x - chunk * groups) * FG;   // first frame of this group inside the chunk
+  const int2 rg = p.range[chunk];
+  const long long base_row = (long long)chunk * p.c + f0;  // buffer row of window slot (f0 + 0)
+
+  // all loads up front: ROWS independent 4-byte loads per thread
+  uint32_t in[ROWS];
+  const uint32_t* gp = reinterpret_cast<const uint32_t*>(p.g) + base_row * (D / 2) + tid;
+#pragma unroll
+  for (int t = 0; t < ROWS; ++t) {
+    const int q = f0 + t;
+    in[t] = (q >= rg.x && q < rg.y) ? __ldg(gp + (long long)t * (D / 2)) : 0u;
+  }
+  float w0[KW], w1[KW];
+#pragma unroll
+  for (int t = 0; t < KW; ++t) {
+    w0[t] = __ldg(p.w + (2 * tid) * KW + t);
+    w1[t] = __ldg(p.w + (2 * tid + 1) * KW + t);
+  }
+  const float bias0 = __ldg(p.bias + 2 * tid), bias1 = __ldg(p.bias + 2 * tid + 1);
+
+  float o0[FG], o1[FG];
+#pragma unroll
+  for (int f = 0; f < FG; ++f) {
+    float a0 = bias0, a1 = bias1;
+#pragma unroll
+    for (int t = 0; t < KW; ++t) {
+      a0 = fmaf(w0[t], bf16_lo(in[f + t]), a0);
+      a1 = fmaf(w1[t], bf16_hi(in[f + t]), a1);
+    }
+    o0[f] = a0; o1[f] = a1;
+  }
+
+  // LayerNorm statistics per frame over the D channels, two-pass (mean, then squared deviations) in fp32
+  float ps[FG];
+#pragma unroll
+  for (int f = 0; f < FG; ++f) ps[f] = o0[f] + o1[f];
+  frame_reduce<FG, NW>(ps, s_part, s_mean, 1.0f / D, false);
+#pragma unroll
+  for (int f = 0; f < FG; ++f) {
+    const float m = s_mean[f];
+    const float d0 = o0[f] - m, d1 = o1[f] - m;
+    ps[f] = d0 * d0 + d1 * d1;
+  }
+  frame_reduce<FG, NW>(ps, s_part, s_rstd, 1.0f / D, true);
+  const float lw0 = __ldg(p.ln_w + 2 * tid), lw1 = __ldg(p.ln_w + 2 * tid + 1);
+  const float lb0 = __ldg(p.ln_b + 2 * tid), lb1 = __ldg(p.ln_b + 2 * tid + 1);
+  uint32_t* zp = reinterpret_cast<uint32_t*>(p.z) + ((long long)chunk * p.c + f0) * (D / 2) + tid;
+#pragma unroll
+  for (int f = 0; f < FG; ++f) {
+    const float mean = s_mean[f], rstd = s_rstd[f];
+    const float y0 = (o0[f] - mean) * rstd * lw0 + lb0;
+    const float y1 = (o1[f] - mean) * rstd * lw1 + lb1;
+    zp[(long long)f * (D / 2)] = pack_bf16(silu(y0), silu(y1));
+  }
+}
+
+}  // namespace cf

@@ -1,0 +1,185 @@
+"""Host-side mirror of the reference encoder interface for the hot path.
+
+`ChunkFormerEncoderB200` exposes the methods the reference's facade calls on `model.encoder`
+(chunkformer/modules/encoder.py): `forward_parallel_chunk` (:503-681) and `forward_encoder` (:220-274), with the same
+argument names, return tuples and error behaviour, and runs them on the sm_100a kernels through the C ABI
+(include/chunkformer_b200.h).  PyTorch is only the owner of device memory and streams here.
+"""
+import ctypes
+from ctypes import POINTER, c_int64, c_void_p
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as _lib
+from .geometry import EncoderGeometry
+from .plan import Plan
+
+_EMPTY = (0,)
+
+
+class ChunkFormerEncoderB200:
+    """B200 encoder + CTC head built from a reference-layout state_dict (keys `encoder.*`, `ctc.ctc_lo.*`)."""
+
+    def __init__(self, geometry: EncoderGeometry, state_dict: Dict[str, torch.Tensor], device="cuda:0"):
+        self.geo = geometry
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ChunkFormerEncoderB200 runs on CUDA devices only (no CPU fallback)")
+        self._L = _lib.load()
+        cfg = _lib.CfConfig(geometry.d_model, geometry.heads, geometry.ffn, geometry.layers, geometry.kernel,
+                            geometry.vocab, geometry.feat_dim, 1 if geometry.has_cmvn else 0)
+        h = c_void_p()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(self._L.cf_create(ctypes.byref(cfg), int(idx), ctypes.byref(h)), None, "cf_create")
+        self._h = h
+        for key, t in state_dict.items():
+            if not (key.startswith("encoder.") or key.startswith("ctc.ctc_lo.")):
+                continue
+            t = t.detach().to("cpu", torch.float32).contiguous()
+            shape = (c_int64 * max(t.dim(), 1))(*t.shape)
+            _lib.check(self._L.cf_load_tensor(self._h, key.encode(), c_void_p(t.data_ptr()), _lib.CF_F32, t.dim(), shape),
+                       self._h, "cf_load_tensor")
+        _lib.check(self._L.cf_finalize_weights(self._h), self._h, "cf_finalize_weights")
+        self._ws: Optional[torch.Tensor] = None
+        self._ctc_ws: Optional[torch.Tensor] = None
+        # attributes the reference facade reads (chunkformer_model.py:344-389)
+        self.num_blocks = geometry.layers
+        self.attention_heads = geometry.heads
+        self._output_size = geometry.d_model
+        self.cnn_module_kernel = geometry.kernel
+        self.subsampling_rate = 8
+
+    def output_size(self) -> int:
+        return self._output_size
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.cf_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, plan: Plan) -> torch.Tensor:
+        need = int(self._L.cf_workspace_bytes(self._h, plan.handle))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _flat_feats(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
+        if all(x.device.type == "cpu" for x in xs):
+            total = sum(int(x.shape[0]) for x in xs)
+            host = torch.empty((total, self.geo.feat_dim), dtype=torch.float32, pin_memory=True)
+            row = 0
+            for x in xs:
+                host[row:row + x.shape[0]] = x
+                row += x.shape[0]
+            return host.to(self.device, non_blocking=True)
+        return torch.cat([x.to(self.device, torch.float32) for x in xs], dim=0).contiguous()
+
+    def encode_plan(self, plan: Plan, feats: torch.Tensor, att_cache=None, cnn_cache=None, trunc: int = 0,
+                    out_dtype=torch.float32, want_bf16: bool = False):
+        """Run cf_encode on a prepared plan and a flat device feature buffer. Returns (out (rows, d), out_bf16|None)."""
+        d = self.geo.d_model
+        out = torch.empty((plan.rows, d), dtype=out_dtype, device=self.device)
+        out16 = torch.empty((plan.rows, d), dtype=torch.bfloat16, device=self.device) \
+            if (want_bf16 and out_dtype != torch.bfloat16) else None
+        ws = self._workspace(plan)
+        rc = self._L.cf_encode(self._h, plan.handle, c_void_p(feats.data_ptr()), _lib.ptr(att_cache), _lib.ptr(cnn_cache),
+                               int(trunc), c_void_p(out.data_ptr()),
+                               _lib.CF_F32 if out_dtype == torch.float32 else _lib.CF_BF16, _lib.ptr(out16),
+                               c_void_p(ws.data_ptr()), ws.numel(), self._stream())
+        _lib.check(rc, self._h, "cf_encode")
+        return out, (out if out_dtype == torch.bfloat16 else out16)
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_parallel_chunk(self, xs: List[torch.Tensor], xs_origin_lens: torch.Tensor, chunk_size: int = -1,
+                               left_context_size: int = -1, right_context_size: int = -1,
+                               att_cache: torch.Tensor = torch.zeros((0, 0, 0)),
+                               cnn_cache: torch.Tensor = torch.zeros((0, 0)), truncated_context_size: int = 0,
+                               offset: torch.Tensor = torch.zeros(0)
+                               ) -> Tuple[torch.Tensor, torch.Tensor, List[int], torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Masked-batch encoder forward; drop-in for ChunkFormerEncoder.forward_parallel_chunk (encoder.py:503-681).
+
+        Returns (xs (n, c, d) fp32, xs_lens int32 (B), n_chunks list, att_cache, cnn_cache, offset); like the reference,
+        `offset` is advanced in place and the caches come back empty ((L,0,0,0) / (L,0,0)) when none were passed."""
+        if chunk_size <= 0 or left_context_size < 0 or right_context_size < 0:
+            raise ValueError("forward_parallel_chunk needs chunk_size > 0 and non-negative context sizes")
+        lens = [int(v) for v in xs_origin_lens.tolist()]
+        if len(lens) != len(xs):
+            raise ValueError("xs and xs_origin_lens disagree on the batch size")
+        if offset.shape[0] == 0:
+            offset = torch.zeros(len(xs), dtype=torch.long, device=xs_origin_lens.device)
+        offs = [int(v) for v in offset.tolist()]
+        plan = Plan(chunk_size, left_context_size, right_context_size, lens, offs, self.geo.kernel)
+        feats = self._flat_feats([x[:t] for x, t in zip(xs, lens)])
+        streaming = att_cache.dim() == 4 and att_cache.size(0) > 0 and att_cache.size(1) > 0
+        L, H, d, lo = self.geo.layers, self.geo.heads, self.geo.d_model, self.geo.kernel // 2
+        new_att = new_cnn = None
+        if streaming:
+            if tuple(att_cache.shape) != (L, left_context_size, H, 2 * d // H) or tuple(cnn_cache.shape) != (L, d, lo):
+                raise ValueError("cache shapes must be (L, left_context, H, 2*d_k) and (L, d, kernel//2)")
+            new_att = att_cache.to(self.device, torch.float32).contiguous().clone()
+            new_cnn = cnn_cache.to(self.device, torch.float32).contiguous().clone()
+        out, _ = self.encode_plan(plan, feats, new_att, new_cnn, truncated_context_size)
+        xs_lens = torch.as_tensor(plan.enc_lens, dtype=torch.int32, device=xs_origin_lens.device)
+        offset += xs_lens.to(offset.dtype)
+        if not streaming:
+            new_att = torch.zeros((L, 0, 0, 0), device=self.device)
+            new_cnn = torch.zeros((L, 0, 0), device=self.device)
+        return out.view(plan.n, chunk_size, d), xs_lens, plan.n_chunks, new_att, new_cnn, offset
+
+    @torch.no_grad()
+    def forward_encoder(self, xs: torch.Tensor, xs_lens: torch.Tensor, chunk_size: int = 0, left_context_size: int = 0,
+                        right_context_size: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Padded-batch encoder forward; drop-in for ChunkFormerEncoder.forward_encoder (encoder.py:220-274).
+        Returns (xs (B, T', d) fp32, masks (B, 1, T') bool)."""
+        if xs.dim() != 3:
+            raise ValueError("xs must be (B, T, feat)")
+        B, T, _ = xs.shape
+        Tp = (T - 15) // 8 + 1
+        if chunk_size is None or chunk_size <= 0:
+            # full attention = one chunk spanning the utterance (attention.py:411 / encoder.py:490-493)
+            chunk_size, left_context_size, right_context_size = Tp, 0, 0
+        lens = [int(v) for v in xs_lens.tolist()]
+        plan = Plan(chunk_size, left_context_size, right_context_size, lens, None, self.geo.kernel, padded_T=T)
+        feats = xs.to(self.device, torch.float32).contiguous().view(B * T, -1)
+        out, _ = self.encode_plan(plan, feats)
+        nck = plan.n_chunks[0]
+        out = out.view(B, nck * chunk_size, self.geo.d_model)[:, :Tp]
+        enc_lens = torch.as_tensor(plan.enc_lens, device=self.device).clamp_min(0)
+        masks = (torch.arange(Tp, device=self.device).unsqueeze(0) < enc_lens.unsqueeze(1)).unsqueeze(1)
+        return out, masks
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def ctc_greedy(self, enc: torch.Tensor, want_margin: bool = False, want_logp: bool = False):
+        """argmax(log_softmax(ctc_lo(enc))) (ctc.py:73-91). enc (..., d) fp32 or bf16 on the device.
+        Returns tokens int64 (...,) [, margin fp32 (...,)] [, logp fp32 (..., V)]."""
+        if self.geo.vocab <= 0:
+            raise ValueError("model has no CTC head")
+        lead = enc.shape[:-1]
+        e = enc.reshape(-1, self.geo.d_model).to(self.device, torch.bfloat16).contiguous()
+        rows = e.shape[0]
+        tokens = torch.empty(rows, dtype=torch.int64, device=self.device)
+        margin = torch.empty(rows, dtype=torch.float32, device=self.device) if want_margin else None
+        logp = torch.empty((rows, self.geo.vocab), dtype=torch.float32, device=self.device) if want_logp else None
+        need = int(self._L.cf_ctc_workspace_bytes(self._h, rows))
+        if self._ctc_ws is None or self._ctc_ws.numel() < need:
+            self._ctc_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        rc = self._L.cf_ctc_greedy(self._h, c_void_p(e.data_ptr()), rows, c_void_p(tokens.data_ptr()), _lib.ptr(margin),
+                                   _lib.ptr(logp), c_void_p(self._ctc_ws.data_ptr()), self._ctc_ws.numel(), self._stream())
+        _lib.check(rc, self._h, "cf_ctc_greedy")
+        res = [tokens.view(lead)]
+        if want_margin:
+            res.append(margin.view(lead))
+        if want_logp:
+            res.append(logp.view(*lead, self.geo.vocab))
+        return res[0] if len(res) == 1 else tuple(res)

@@ -1,0 +1,139 @@
+/*
+ * chunkformer_b200 — C ABI of the B200-native (sm_100a) ChunkFormer encoder hot path.
+ *
+ * The reference (ishine/chunkformer) has no FFI / plugin interface: its boundary for this path is the Python method
+ * surface of ChunkFormerEncoder plus the checkpoint layout.  Each entry point below names the reference
+ * interface it stands in for (file:line relative to /root/reference).  The Python mirror of that surface
+ * (chunkformer_b200/encoder.py, model.py) binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative cf_status and records a
+ * message retrievable with cf_last_error(); no exception crosses the ABI; the caller owns all input/output buffers;
+ * the library owns converted weights; a handle belongs to one device and is not thread-safe; all device work is
+ * enqueued on the caller's stream (cudaStream_t passed as void*).  There is no CPU fallback: compute entry points fail
+ * with CF_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef CHUNKFORMER_B200_H_
+#define CHUNKFORMER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CF_API __attribute__((visibility("default")))
+#else
+#define CF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cf_handle cf_handle;
+typedef struct cf_plan cf_plan;
+
+enum cf_status {
+  CF_OK = 0,
+  CF_ERR_INVALID = -1,     /* bad argument / unsupported geometry */
+  CF_ERR_CUDA = -2,        /* CUDA runtime / driver error, or no device */
+  CF_ERR_STATE = -3,       /* call order (weights not finalized, missing tensor, ...) */
+  CF_ERR_WORKSPACE = -4    /* workspace too small */
+};
+
+enum cf_dtype { CF_F32 = 0, CF_BF16 = 1 };
+
+/* Encoder geometry = ChunkFormerEncoder.__init__ arguments that shape the inference path
+ * (chunkformer/modules/encoder.py:36-193) + CTC vocabulary (chunkformer/modules/ctc.py:44). */
+typedef struct cf_config {
+  int32_t d_model;    /* output_size (256 | 512) */
+  int32_t heads;      /* attention_heads; d_model / heads in {64, 128} */
+  int32_t ffn;        /* linear_units */
+  int32_t layers;     /* num_blocks */
+  int32_t kernel;     /* cnn_module_kernel (15) */
+  int32_t vocab;      /* CTC output size, 0 = no CTC head */
+  int32_t feat_dim;   /* input_size (80) */
+  int32_t has_cmvn;   /* encoder.global_cmvn.{mean,istd} present */
+} cf_config;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------------- */
+/* Replaces: init_speech_model(...) building ChunkFormerEncoder + CTC (chunkformer/utils/init_model.py:61-145). */
+CF_API int cf_create(const cf_config* cfg, int device, cf_handle** out);
+CF_API void cf_destroy(cf_handle* h);
+/* Last error message of `h` (or of the last failed cf_create / plan call when h == NULL). Never NULL. */
+CF_API const char* cf_last_error(const cf_handle* h);
+CF_API const char* cf_version(void);
+
+/* ---- weights ----------------------------------------------------------------------------------------------------- */
+/* Replaces: load_checkpoint -> model.load_state_dict(strict=False) (chunkformer/utils/checkpoint.py:26-41).
+ * One call per checkpoint tensor, any order, keyed exactly as in the reference state_dict ("encoder.embed.conv.0.weight",
+ * "encoder.encoders.3.self_attn.pos_bias_u", "ctc.ctc_lo.weight", ...). `data` is host memory, fp32, C-contiguous.
+ * Keys outside encoder.* / ctc.ctc_lo.* are ignored (returns CF_OK), like strict=False. */
+CF_API int cf_load_tensor(cf_handle* h, const char* key, const void* data, int dtype, int ndim, const int64_t* shape);
+/* Converts to device layouts (bf16 GEMM operands, fused QKV, GLU-interleaved pointwise_conv1, permuted embed.out, packed
+ * stencil weights). Fails with CF_ERR_STATE and names the first missing tensor if the checkpoint is incomplete. */
+CF_API int cf_finalize_weights(cf_handle* h);
+
+/* ---- packer / plan (pure host code: usable without a GPU) -------------------------------------------------------- */
+/* Replaces: the masked-batch packer and bound tables of ChunkFormerEncoder.forward_parallel_chunk
+ * (chunkformer/modules/encoder.py:538-612, 627-645).  lens[B] = input frames per utterance, offsets[B] = stream offsets
+ * (NULL = zeros). feat_row_offsets[B] = first row of each utterance in the flat feature buffer (NULL = utterances are
+ * concatenated back to back). */
+CF_API int cf_plan_create(int chunk_size, int left_context, int right_context, int conv_kernel, int B, const int32_t* lens,
+                   const int32_t* offsets, const int64_t* feat_row_offsets, cf_plan** out);
+/* Replaces: the padded-batch geometry of ChunkFormerEncoder.forward_encoder (encoder.py:220-274, attention.py:337-383,
+ * convolution.py:125-167): xs is (B, T, feat) row-major, lens[B] valid frames. Output rows per utterance: 1+(T-15)/8. */
+CF_API int cf_plan_create_padded(int chunk_size, int left_context, int right_context, int conv_kernel, int B, int T,
+                          const int32_t* lens, cf_plan** out);
+CF_API void cf_plan_destroy(cf_plan* p);
+CF_API int cf_plan_num_chunks(const cf_plan* p);               /* n = total chunks */
+CF_API int cf_plan_rows(const cf_plan* p);                     /* n * chunk_size encoder rows computed */
+/* n_chunks_out[B] (encoder.py:562) and enc_lens_out[B] = calc_length(lens) (subsampling.py:270-288). */
+CF_API int cf_plan_tables(const cf_plan* p, int32_t* n_chunks_out, int32_t* enc_lens_out);
+/* The two boolean masks handed to the layers by the reference, for bit-exact tests:
+ * att_mask[n * (l+c+r)] (encoder.py:637-645) and conv_mask[n * (c + 2*(kernel/2))] (encoder.py:627-633); 0/1 bytes. */
+CF_API int cf_plan_masks(const cf_plan* p, uint8_t* att_mask, uint8_t* conv_mask);
+/* Per-chunk int32 table, 8 ints per chunk: {utt, j, att_lo, att_hi, conv_lo, conv_hi, out_lo, out_hi}. */
+CF_API int cf_plan_chunk_table(const cf_plan* p, int32_t* table);
+
+/* ---- encoder ----------------------------------------------------------------------------------------------------- */
+CF_API size_t cf_workspace_bytes(const cf_handle* h, const cf_plan* p);
+/* Replaces: ChunkFormerEncoder.forward_parallel_chunk / forward_encoder from CMVN to after_norm
+ * (encoder.py:615-671; encoder_layer.py:155-248; attention.py:420-505; convolution.py:194-255; subsampling.py:120-175).
+ *   feats          device, fp32, flat [rows, feat_dim] (all utterances; see feat_row_offsets of the plan)
+ *   att_cache      device, fp32 (L, l, H, 2*d_k) in/out or NULL  (attention.py:459-467)
+ *   cnn_cache      device, fp32 (L, d, kernel/2) in/out or NULL  (convolution.py:228-232)
+ *   truncated_context_size  rows kept for the next segment's caches (chunkformer_model.py:364-365)
+ *   out            device, [n * c, d_model] in out_dtype (CF_F32 | CF_BF16); rows >= enc_len of an utterance are undefined
+ *   out_bf16       optional second output (bf16 copy used as the CTC GEMM operand), may be NULL
+ */
+CF_API int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, void* att_cache, void* cnn_cache,
+              int truncated_context_size, void* out, int out_dtype, void* out_bf16, void* workspace,
+              size_t workspace_bytes, void* stream);
+
+/* ---- CTC head ---------------------------------------------------------------------------------------------------- */
+CF_API size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows);
+/* Replaces: CTC.log_softmax + argmax (chunkformer/modules/ctc.py:73-91; chunkformer_model.py:437-438, 526-527).
+ * enc: device bf16 [rows, d_model]. tokens_out: device int64 [rows]. margin_out: optional device fp32 [rows] = best logit
+ * minus runner-up (for tolerance-aware comparisons). logp_out: optional device fp32 [rows, vocab] log-softmax. */
+CF_API int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, int64_t* tokens_out, float* margin_out,
+                  float* logp_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- kernel-level entry points (parity tests, profiling) --------------------------------------------------------- */
+/* C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 GEMM with a fused epilogue; epi: 0 bf16(bias,act) 1 GLU 2 f32(resid,alpha,
+ * rowmask) 3 QKV 4 argmax partials; act: 0 none 1 relu 2 silu. All pointers device. */
+CF_API int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, int act,
+               const float* bias, const float* bias_u, const float* bias_v, int qkv_d, const float* resid,
+               int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk, void* out, int64_t ldo,
+               float* part_best, float* part_second, int32_t* part_index, void* stream);
+/* mode 0: y=LN1(x); 1: x<-LN1(x), y=LN2(x); 2: out=LN2(LN1(x)). */
+CF_API int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1, const float* b1,
+                    const float* w2, const float* b2, int64_t rows, void* stream);
+CF_API int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16, const float* w, const float* bias,
+                 const float* ln_w, const float* ln_b, const int32_t* range, int c, int n_chunks, void* stream);
+/* impl 0 = generic CUDA-core kernel, 1 = tcgen05 kernel (c=64, d_k=64, l+c+r <= 320 multiple of 64). */
+CF_API int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_bf16, const int32_t* range, void* ctx_bf16,
+                    int n_chunks, int c, int l, int r, int d, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHUNKFORMER_B200_H_ */

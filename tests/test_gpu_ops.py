@@ -1,0 +1,250 @@
+"""Kernel-level parity on a B200: every hand-written kernel, called through the C ABI, against a plain PyTorch fp32
+restatement of the same op on the same (bf16-rounded) operands."""
+import ctypes
+import math
+from ctypes import c_void_p
+
+import numpy as np
+import pytest
+import torch
+
+from chunkformer_b200 import lib as cflib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _p(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _gemm(A, B, epi, out, bias, act=0, bias_u=None, bias_v=None, qkv_d=0, resid=None, alpha=1.0, row_range=None,
+          rows_per_chunk=1, parts=(None, None, None)):
+    L = cflib.load()
+    M, K = A.shape
+    N = B.shape[0]
+    rc = L.cf_op_gemm(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, epi, act, _p(bias), _p(bias_u), _p(bias_v), qkv_d,
+                      _p(resid), resid.stride(0) if resid is not None else 0, alpha, _p(row_range), rows_per_chunk,
+                      _p(out), out.stride(0) if out is not None else 0, _p(parts[0]), _p(parts[1]), _p(parts[2]), _stream())
+    cflib.check(rc, None, "cf_op_gemm")
+    torch.cuda.synchronize()
+
+
+def _rand(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 512, 512), (1000, 2048, 512), (777, 512, 2048), (64, 256, 4608),
+                                   (40000, 512, 512)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_bias_act_bf16(M, N, K, act):
+    A = _rand((M, K), 1.0, 1).bfloat16()
+    B = _rand((N, K), 1.0 / math.sqrt(K), 2).bfloat16()
+    bias = _rand((N,), 0.5, 3)
+    out = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    _gemm(A, B, cflib.EPI_BF16, out, bias, act=act)
+    ref = A.float() @ B.float().T + bias
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = ref * torch.sigmoid(ref)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, err
+    assert (out.float() - ref).abs().mean().item() < 3e-3
+
+
+def test_gemm_glu():
+    M, d = 300, 512
+    A = _rand((M, d), 1.0, 1).bfloat16()
+    W = _rand((2 * d, d), 1.0 / math.sqrt(d), 2)
+    b = _rand((2 * d,), 0.5, 3)
+    Wi = torch.empty_like(W)
+    bi = torch.empty_like(b)
+    Wi[0::2], Wi[1::2] = W[:d], W[d:]
+    bi[0::2], bi[1::2] = b[:d], b[d:]
+    out = torch.zeros((M, d), device=DEV, dtype=torch.bfloat16)
+    _gemm(A, Wi.bfloat16().contiguous(), cflib.EPI_GLU, out, bi.contiguous())
+    h = A.float() @ W.bfloat16().float().T + b
+    ref = h[:, :d] * torch.sigmoid(h[:, d:])
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+def test_gemm_f32_residual_rowmask():
+    c, n, d, K = 64, 5, 512, 2048
+    M = n * c
+    A = _rand((M, K), 1.0, 1).bfloat16()
+    B = _rand((d, K), 1.0 / math.sqrt(K), 2).bfloat16()
+    bias = _rand((d,), 0.5, 3)
+    x = _rand((M, d), 1.0, 4)
+    rng = torch.tensor([[0, 64], [3, 60], [0, 0], [10, 64], [0, 17]], dtype=torch.int32, device=DEV)
+    out = x.clone()
+    _gemm(A, B, cflib.EPI_F32, out, bias, resid=out, alpha=0.5, row_range=rng, rows_per_chunk=c)
+    keep = torch.zeros(M, dtype=torch.bool, device=DEV)
+    for g, (lo, hi) in enumerate(rng.tolist()):
+        keep[g * c + lo: g * c + hi] = True
+    ref = x + keep.unsqueeze(1) * 0.5 * (A.float() @ B.float().T + bias)
+    assert (out - ref).abs().max().item() < 2e-3
+    assert torch.equal(out[~keep], x[~keep])          # masked rows: exactly the residual
+    # no residual, scale only, ragged N (vocab-like)
+    Nv = 5000
+    Bv = _rand((Nv, 512), 0.05, 5).bfloat16()
+    bv = _rand((Nv,), 0.5, 6)
+    Av = _rand((300, 512), 1.0, 7).bfloat16()
+    outv = torch.full((300, Nv), -1.0, device=DEV)
+    _gemm(Av, Bv, cflib.EPI_F32, outv, bv, alpha=2.0)
+    refv = 2.0 * (Av.float() @ Bv.float().T + bv)
+    assert (outv - refv).abs().max().item() < 2e-3
+
+
+def test_gemm_qkv():
+    M, d = 333, 512
+    A = _rand((M, d), 1.0, 1).bfloat16()
+    W = _rand((3 * d, d), 1.0 / math.sqrt(d), 2).bfloat16()
+    b = _rand((3 * d,), 0.5, 3)
+    u, v = _rand((d,), 0.2, 4), _rand((d,), 0.2, 5)
+    out = torch.zeros((M, 4 * d), device=DEV, dtype=torch.bfloat16)
+    _gemm(A, W, cflib.EPI_QKV, out, b, bias_u=u, bias_v=v, qkv_d=d)
+    h = A.float() @ W.float().T + b
+    ref = torch.cat([h[:, :d] + u, h[:, :d] + v, h[:, d:]], dim=1)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+def test_gemm_argmax_partials():
+    M, d, V = 500, 512, 5000
+    A = _rand((M, d), 1.0, 1).bfloat16()
+    W = _rand((V, d), 1.0 / math.sqrt(d), 2).bfloat16()
+    b = _rand((V,), 0.5, 3)
+    nt = (V + 255) // 256
+    best = torch.zeros((M, nt), device=DEV)
+    second = torch.zeros((M, nt), device=DEV)
+    index = torch.zeros((M, nt), device=DEV, dtype=torch.int32)
+    _gemm(A, W, cflib.EPI_ARGMAX, None, b, parts=(best, second, index))
+    logits = A.float() @ W.float().T + b
+    top2 = logits.topk(2, -1)
+    got_best, pos = best.max(-1)
+    got_idx = index.gather(1, pos.unsqueeze(1)).squeeze(1).long()
+    margin = top2.values[:, 0] - top2.values[:, 1]
+    ok = (got_idx == top2.indices[:, 0]) | (margin < 1e-3)
+    assert bool(ok.all())
+    assert (got_best - top2.values[:, 0]).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("d", [256, 512])
+def test_layernorm_modes(d):
+    L = cflib.load()
+    rows = 1031
+    x = _rand((rows, d), 2.0, 1) + 0.3
+    w1, b1 = 1 + _rand((d,), 0.1, 2), _rand((d,), 0.1, 3)
+    w2, b2 = 1 + _rand((d,), 0.1, 4), _rand((d,), 0.1, 5)
+    ln1 = torch.nn.functional.layer_norm(x, (d,), w1, b1, 1e-5)
+    ln2 = torch.nn.functional.layer_norm(ln1, (d,), w2, b2, 1e-5)
+    y = torch.zeros((rows, d), device=DEV, dtype=torch.bfloat16)
+    cflib.check(L.cf_op_layernorm(0, d, _p(x), None, _p(y), _p(w1), _p(b1), None, None, rows, _stream()))
+    torch.cuda.synchronize()
+    assert (y.float() - ln1).abs().max().item() < 3e-2
+    xo = x.clone()
+    cflib.check(L.cf_op_layernorm(1, d, _p(xo), _p(xo), _p(y), _p(w1), _p(b1), _p(w2), _p(b2), rows, _stream()))
+    torch.cuda.synchronize()
+    assert (xo - ln1).abs().max().item() < 1e-4
+    assert (y.float() - ln2).abs().max().item() < 3e-2
+    o32 = torch.zeros((rows, d), device=DEV)
+    cflib.check(L.cf_op_layernorm(2, d, _p(x), _p(o32), _p(y), _p(w1), _p(b1), _p(w2), _p(b2), rows, _stream()))
+    torch.cuda.synchronize()
+    assert (o32 - ln2).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("d,c", [(512, 64), (256, 16), (512, 8), (256, 4)])
+def test_dwconv_ln_silu(d, c):
+    L = cflib.load()
+    n, lo = 7, 7
+    rows = n * c
+    g = torch.zeros((rows + 2 * lo + 64, d), device=DEV, dtype=torch.bfloat16)
+    g[: rows + 2 * lo] = _rand((rows + 2 * lo, d), 1.0, 1).bfloat16()
+    w, b = _rand((d, 15), 0.3, 2), _rand((d,), 0.2, 3)
+    lw, lb = 1 + _rand((d,), 0.1, 4), _rand((d,), 0.1, 5)
+    rng_np = np.array([[0, c + 14], [7, c + 14], [0, c + 7], [3, c + 2], [0, 0], [5, 9], [0, c + 14]], dtype=np.int32)
+    rng = torch.from_numpy(rng_np).to(DEV)
+    z = torch.zeros((rows, d), device=DEV, dtype=torch.bfloat16)
+    cflib.check(L.cf_op_dwconv(d, 15, _p(g), _p(z), _p(w), _p(b), _p(lw), _p(lb), _p(rng), c, n, _stream()))
+    torch.cuda.synchronize()
+    gf = g.float()
+    for ch in range(n):
+        win = gf[ch * c: ch * c + c + 14].clone()
+        m = torch.zeros(c + 14, dtype=torch.bool, device=DEV)
+        m[rng_np[ch, 0]: rng_np[ch, 1]] = True
+        win = win * m.unsqueeze(1)
+        conv = torch.stack([(win[i:i + 15] * w.T).sum(0) for i in range(c)], 0) + b
+        ref = torch.nn.functional.layer_norm(conv, (d,), lw, lb, 1e-5)
+        ref = ref * torch.sigmoid(ref)
+        assert (z[ch * c:(ch + 1) * c].float() - ref).abs().max().item() < 3e-2, ch
+
+
+def _attention_reference(qkv, pos, rng, n, c, l, r, d, H):
+    dk = d // H
+    W = l + c + r
+    q = qkv.float()
+    out = torch.zeros((n * c, d), device=qkv.device)
+    idx = (c - 1) - torch.arange(c, device=qkv.device).unsqueeze(1) + torch.arange(W, device=qkv.device).unsqueeze(0)
+    for g in range(n):
+        lo, hi = rng[g]
+        for h in range(H):
+            qu = q[l + g * c: l + (g + 1) * c, h * dk:(h + 1) * dk]
+            qv = q[l + g * c: l + (g + 1) * c, d + h * dk: d + (h + 1) * dk]
+            k = q[g * c: g * c + W, 2 * d + h * dk: 2 * d + (h + 1) * dk]
+            v = q[g * c: g * c + W, 3 * d + h * dk: 3 * d + (h + 1) * dk]
+            p = pos.float()[:, h * dk:(h + 1) * dk]
+            s = (qu @ k.T + (qv @ p.T).gather(1, idx)) / math.sqrt(dk)
+            m = torch.zeros(W, dtype=torch.bool, device=qkv.device)
+            m[lo:hi] = True
+            s = s.masked_fill(~m, float("-inf"))
+            if hi > lo:
+                a = torch.softmax(s, -1)
+            else:
+                a = torch.zeros_like(s)
+            out[g * c:(g + 1) * c, h * dk:(h + 1) * dk] = a @ v
+    return out
+
+
+def _attention_case(impl, c, l, r, d, H, n, seed=0):
+    L = cflib.load()
+    W = l + c + r
+    R = 2 * c + l + r - 1
+    rows = l + n * c + r + 2 * c + 128
+    qkv = torch.zeros((rows, 4 * d), device=DEV, dtype=torch.bfloat16)
+    qkv[: l + n * c] = _rand((l + n * c, 4 * d), 1.0, seed).bfloat16()
+    Rpad = (R + 127) // 128 * 128
+    pos = torch.zeros((Rpad, d), device=DEV, dtype=torch.bfloat16)
+    pos[:R] = _rand((R, d), 1.0, seed + 1).bfloat16()
+    rs = np.random.RandomState(seed)
+    rng_np = np.zeros((n + 2, 2), dtype=np.int32)
+    for g in range(n):
+        kind = g % 4
+        if kind == 0:
+            rng_np[g] = (0, W)
+        elif kind == 1:
+            rng_np[g] = (rs.randint(0, l + 1), W)
+        elif kind == 2:
+            rng_np[g] = (0, rs.randint(l + 1, W + 1))
+        else:
+            rng_np[g] = (rs.randint(0, l + 1), rs.randint(l + 1, W + 1))
+    if n > 5:
+        rng_np[5] = (0, 0)          # chunk with no valid key: zero context, not NaN
+    rng = torch.from_numpy(rng_np).to(DEV)
+    ctx = torch.full((n * c, d), 9.0, device=DEV, dtype=torch.bfloat16)
+    cflib.check(L.cf_op_attention(impl, _p(qkv), _p(pos), _p(rng), _p(ctx), n, c, l, r, d, H, _stream()), None, "attention")
+    torch.cuda.synchronize()
+    ref = _attention_reference(qkv, pos, rng_np, n, c, l, r, d, H)
+    assert torch.isfinite(ctx.float()).all()
+    err = (ctx.float() - ref).abs().max().item()
+    assert err < 4e-2, err
+
+
+@pytest.mark.parametrize("c,l,r,d,H,n", [(64, 128, 128, 512, 8, 7), (16, 64, 0, 256, 4, 9), (8, 16, 16, 256, 2, 6),
+                                         (64, 64, 64, 512, 4, 4)])
+def test_attention_generic(c, l, r, d, H, n):
+    _attention_case(0, c, l, r, d, H, n)
