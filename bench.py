@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: masked-chunk Conformer encoder forward + greedy CTC, CTC-large, chunk 64 / left 128 /
+right 128 (BASELINE.json).  One "step" = one pass of the path over one masked batch of synthetic fbank.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); every rank encodes its own batch (weak scaling, no data-path
+collective; token ids are gathered once per step).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from chunkformer_b200.geometry import CTC_LARGE  # noqa: E402
+from chunkformer_b200.synth import MASKED_BATCH_SECONDS, masked_batch_lengths, synth_fbank, synth_state_dict  # noqa: E402
+
+METRIC = "encoder audio-hours/sec (RTFx), CTC-large chunk64/L128/R128"
+UNIT = "audio-hours/s"
+C, L, R = 64, 128, 128
+
+
+def audio_seconds(frames):
+    return (frames + 2) / 100.0
+
+
+def layer_flops_per_chunk(geo, c, l, r):
+    d, F = geo.d_model, geo.ffn
+    W, Rr = l + c + r, 2 * c + l + r - 1
+    return 2 * (4 * c * d * F + 4 * c * d * d + c * d * (2 * W + Rr) + 3 * c * d * d + 15 * c * d)
+
+
+def path_flops_per_chunk(geo, c, l, r):
+    """sub + L * layer + ctc, 2*MAC."""
+    d, V = geo.d_model, geo.vocab
+    t1, t2 = 4 * c + 3, 2 * c + 1
+    f1, f2, f3 = 39, 19, 9
+    sub = 2 * (9 * t1 * f1 * d + 9 * t2 * f2 * d + t2 * f2 * d * d + 9 * c * f3 * d + c * f3 * d * d + c * f3 * d * d)
+    return sub + geo.layers * layer_flops_per_chunk(geo, c, l, r) + 2 * c * d * V
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_baseline(threads, steps=2, warmup=1):
+    """The oracle (a port of the reference's algorithm, oracle/chunkformer_oracle.py) on the host cores, fp32, on a bounded
+    sample of the same workload: the {1 s, 30 s, 60 s} utterances of the masked batch (91 s of audio) as one masked batch."""
+    from oracle import chunkformer_oracle as O
+    torch.set_num_threads(threads)
+    sd = synth_state_dict(CTC_LARGE, 0)
+    secs = [1, 30, 60]
+    lens = [int(round(s * 100)) - 2 for s in secs]
+    xs = [synth_fbank(t, seed=1 + k) for k, t in enumerate(lens)]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out, enc_lens, n_chunks, _, _, _ = O.forward_parallel_chunk(sd, CTC_LARGE.heads, xs, lens, C, L, R)
+        O.ctc_greedy(sd, out)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    audio = sum(audio_seconds(t) for t in lens)
+    best = min(times)
+    return {"value": audio / best / 3600.0, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"masked batch of the {secs} s utterances ({audio:.0f} s audio), fp32 torch CPU oracle, best of {steps}",
+            "seconds_per_sample": best}, times, audio
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    base, times, audio = cpu_oracle_baseline(threads, steps=args.steps, warmup=max(args.warmup, 1))
+    total = sum(times)
+    value = audio * len(times) / total / 3600.0
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": max(args.warmup, 1),
+            "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "bounded sample of the CTC-large 64/128/128 masked batch: the 1 s, 30 s and 60 s utterances "
+                                   "(91 s audio) per step, CPU oracle port of the reference path", "chunk": C, "left": L, "right": R},
+            "cpu_baseline": dict(base, value=value),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="scale every utterance duration (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from chunkformer_b200 import lib as cflib
+    from chunkformer_b200.encoder import ChunkFormerEncoderB200
+    from chunkformer_b200.plan import Plan
+
+    geo = CTC_LARGE
+    enc = ChunkFormerEncoderB200(geo, synth_state_dict(geo, 0), dev)
+    lens = masked_batch_lengths(args.scale)
+    xs_host = [synth_fbank(t, seed=1 + 100 * rank + k).pin_memory() for k, t in enumerate(lens)]
+    lens_t = torch.tensor(lens, dtype=torch.int32)
+    audio = sum(audio_seconds(t) for t in lens)
+    feats_dev = torch.cat(xs_host, 0).to(dev)
+    Llib = cflib.load()
+
+    def step_resident():
+        plan = Plan(C, L, R, lens, None, geo.kernel)                       # host packer is part of the path
+        out, out16 = enc.encode_plan(plan, feats_dev, out_dtype=torch.bfloat16)
+        tokens = enc.ctc_greedy(out16)
+        return plan, tokens
+
+    def step_e2e():
+        out, enc_lens, n_chunks, _, _, _ = enc.forward_parallel_chunk(xs_host, lens_t, C, L, R,
+                                                                      offset=torch.zeros(len(lens), dtype=torch.int32))
+        tokens = enc.ctc_greedy(out)
+        return tokens.to("cpu", non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(args.warmup):
+        plan, tokens = step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = Llib.cf_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        plan, tokens = step_resident()
+        if world > 1:
+            gathered = [torch.empty_like(tokens) for _ in range(world)]
+            dist.all_gather(gathered, tokens)
+    ev1.record()
+    barrier()
+    launches = Llib.cf_launch_count() - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * audio * args.steps / (ms_total / 1000.0) / 3600.0
+
+    # ---- end to end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tok_host = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * audio * args.steps / float(e2e_s.item()) / 3600.0
+    h2d = int(sum(x.numel() * 4 for x in xs_host))
+    d2h = int(tok_host.numel() * tok_host.element_size())
+
+    # ---- roofline of the dominant kernel: the FFN up-projection GEMM (tcgen05, bf16 -> fp32 accumulate, SiLU epilogue)
+    rows = plan.rows
+    roofline = None
+    if rank == 0:
+        from ctypes import c_void_p
+        d, F = geo.d_model, geo.ffn
+        A = torch.randn((rows, d), device=dev).bfloat16()
+        Wt = (torch.randn((F, d), device=dev) / d ** 0.5).bfloat16()
+        bias = torch.zeros(F, device=dev)
+        Hbuf = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+        st = c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def ffn1():
+            rc = Llib.cf_op_gemm(c_void_p(A.data_ptr()), d, c_void_p(Wt.data_ptr()), d, rows, F, d, cflib.EPI_BF16,
+                                 cflib.ACT_SILU, c_void_p(bias.data_ptr()), None, 0, 1.0, None, 1,
+                                 c_void_p(Hbuf.data_ptr()), F, None, None, None, st)
+            cflib.check(rc, None, "cf_op_gemm")
+        for _ in range(3):
+            ffn1()
+        torch.cuda.synchronize()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ffn1()
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        flops = 2.0 * rows * d * F
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EPI_BF16, ACT_SILU> (FFN w_1 + SiLU, M=%d N=%d K=%d)" % (rows, F, d),
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s",
+                    "traffic": None, "ms_per_launch": k_ms,
+                    "path_tflops": path_flops_per_chunk(geo, C, L, R) * plan.n * args.steps * world / (ms_total * 1e-3) / 1e12,
+                    "path_frac_of_sustained": None}
+        sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        roofline["path_frac_of_sustained"] = roofline["path_tflops"] / (sustained * world)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _, _ = cpu_oracle_baseline(os.cpu_count() or 1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "masked batch of 19 utterances %s s (14400 s audio, %d chunks, %d encoder rows) per GPU, "
+                                       "CTC-large d512 H8 F2048 L17 V5000, chunk 64 / left 128 / right 128, encoder + greedy CTC"
+                                       % (MASKED_BATCH_SECONDS, plan.n, plan.rows),
+                           "chunk": C, "left": L, "right": R, "global_batch_audio_s": world * audio,
+                           "l2": "working set per step (>4 GB) exceeds the 126 MB L2; no flush needed",
+                           "parallelism": f"dp{world} (one batch per GPU, token ids gathered once per step)"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1000.0 * float(e2e_s.item()) / args.steps,
+                        "api": "ChunkFormerEncoderB200.forward_parallel_chunk(host fbank) + ctc_greedy + tokens.cpu()"},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,7 @@
 // kernel-level entry points.  One translation unit: all sm_100a kernels are header templates instantiated here.
 #include "../../include/chunkformer_b200.h"
 
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -22,12 +23,14 @@ typedef __nv_bfloat16 bf16;
 
 static thread_local std::string g_last_error = "";
 
+namespace cf { std::atomic<long long> g_kernel_launches{0}; }
+
 // --------------------------------------------------------------------------------------------------------------------
 // handle
 // --------------------------------------------------------------------------------------------------------------------
 struct LayerW {
   bf16 *ffm_w1, *ffm_w2, *ff_w1, *ff_w2, *qkv_w, *o_w, *pos_w, *pw1_w, *pw2_w;
-  float *ffm_b1, *ffm_b2, *ff_b1, *ff_b2, *qkv_b, *bias_u, *bias_v, *o_b, *pw1_b, *dw_w, *dw_b, *cn_w, *cn_b, *pw2_b;
+  float *ffm_b1, *ffm_b2, *ff_b1, *ff_b2, *qkv_b, *o_b, *pw1_b, *dw_w, *dw_b, *cn_w, *cn_b, *pw2_b;
   float *ln_ffm_w, *ln_ffm_b, *ln_mha_w, *ln_mha_b, *ln_conv_w, *ln_conv_b, *ln_ff_w, *ln_ff_b, *ln_fin_w, *ln_fin_b;
 };
 
@@ -71,6 +74,7 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
     }                                                                                                 \
   } while (0)
 
+extern "C" long long cf_launch_count(void) { return cf::g_kernel_launches.load(); }
 extern "C" const char* cf_version(void) { return "chunkformer_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cf_last_error(const cf_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
@@ -241,9 +245,13 @@ extern "C" int cf_finalize_weights(cf_handle* h) {
       const auto& bu = get(p + "self_attn.pos_bias_u", d);
       const auto& bvv = get(p + "self_attn.pos_bias_v", d);
       if (missing.empty()) {
-        std::vector<float> W(wq); W.insert(W.end(), wk.begin(), wk.end()); W.insert(W.end(), wv.begin(), wv.end());
-        std::vector<float> B(bq); B.insert(B.end(), bk.begin(), bk.end()); B.insert(B.end(), bv.begin(), bv.end());
-        ab.b16(W, &w.qkv_w); ab.f32(B, &w.qkv_b); ab.f32(bu, &w.bias_u); ab.f32(bvv, &w.bias_v);
+        // fused projection with output columns [Q+u | Q+v | K | V]: W_q appears twice, pos_bias_u / pos_bias_v
+        // (attention.py:486-488) are folded into the two Q biases.
+        std::vector<float> W(wq); W.insert(W.end(), wq.begin(), wq.end());
+        W.insert(W.end(), wk.begin(), wk.end()); W.insert(W.end(), wv.begin(), wv.end());
+        std::vector<float> B(size_t(4) * d);
+        for (int c = 0; c < d; ++c) { B[c] = bq[c] + bu[c]; B[d + c] = bq[c] + bvv[c]; B[2 * d + c] = bk[c]; B[3 * d + c] = bv[c]; }
+        ab.b16(W, &w.qkv_w); ab.f32(B, &w.qkv_b);
       }
     }
     lin("self_attn.linear_out", d, d, &w.o_w, &w.o_b);
@@ -363,7 +371,7 @@ bool run_layernorm(int mode, int d, const LnParams& p, cudaStream_t st, std::str
   if (p.rows == 0) return true;
   const int warps = 8;
   const unsigned grid = unsigned((p.rows + warps - 1) / warps);
-#define CF_LN(D, MODE) layernorm_kernel<D, MODE><<<grid, warps * 32, 0, st>>>(p)
+#define CF_LN(D, MODE) (++cf::g_kernel_launches, layernorm_kernel<D, MODE><<<grid, warps * 32, 0, st>>>(p))
   if (d == 512) { if (mode == 0) CF_LN(512, 0); else if (mode == 1) CF_LN(512, 1); else CF_LN(512, 2); }
   else if (d == 256) { if (mode == 0) CF_LN(256, 0); else if (mode == 1) CF_LN(256, 1); else CF_LN(256, 2); }
   else { *err = "layernorm: d must be 256 or 512"; return false; }
@@ -376,7 +384,7 @@ bool run_layernorm(int mode, int d, const LnParams& p, cudaStream_t st, std::str
 template <int D>
 bool run_dwconv_d(const DwConvParams& p, cudaStream_t st, std::string* err) {
   const int c = p.c;
-#define CF_DW(FG) dwconv_ln_silu_kernel<D, 15, FG><<<p.n_chunks * (c / FG), D / 2, 0, st>>>(p)
+#define CF_DW(FG) (++cf::g_kernel_launches, dwconv_ln_silu_kernel<D, 15, FG><<<p.n_chunks * (c / FG), D / 2, 0, st>>>(p))
   if (c % 32 == 0) CF_DW(32);
   else if (c % 16 == 0) CF_DW(16);
   else if (c % 8 == 0) CF_DW(8);
@@ -415,9 +423,11 @@ bool run_attention(int impl, const AttnParams& p, cudaStream_t st, std::string* 
   if (dk == 64) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(attention_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     attention_simt_kernel<64><<<grid, 128, smem, st>>>(p);
+    ++cf::g_kernel_launches;
   } else if (dk == 128) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(attention_simt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     attention_simt_kernel<128><<<grid, 128, smem, st>>>(p);
+    ++cf::g_kernel_launches;
   } else { *err = "attention: d_k must be 64 or 128"; return false; }
   e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("attention launch: ") + cudaGetErrorString(e); return false; }
@@ -502,7 +512,7 @@ int get_pos_table(cf_handle* h, int c, int l, int r, cudaStream_t st, const PosT
   for (int i = 0; i < L; ++i) {
     GemmLaunch g{};
     g.A = pe_dev; g.lda = d; g.B = h->layers[i].pos_w; g.ldb = d; g.M = t.R; g.N = d; g.K = d; g.epi = EPI_BF16;
-    g.ep.bias = h->zeros; g.ep.out = t.dev + size_t(i) * t.Rpad * d; g.ep.ldo = d; g.ep.act = ACT_NONE;
+    g.act = ACT_NONE; g.ep.bias = h->zeros; g.out = t.dev + size_t(i) * t.Rpad * d; g.ldo = d;
     std::string err;
     if (!launch_gemm(g, h->num_sms, st, &err)) { cudaFree(pe_dev); return fail(h, CF_ERR_CUDA, err); }
   }
@@ -573,10 +583,16 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   CF_CUDA(h, cudaMemsetAsync(w.g, 0, size_t(lo) * d * sizeof(bf16), st));
   CF_CUDA(h, cudaMemsetAsync(w.g + (size_t(lo) + Mr) * d, 0, (w.g_rows - size_t(lo) - Mr) * d * sizeof(bf16), st));
 
+  struct EpiArgs { const float* bias = nullptr; void* out = nullptr; long long ldo = 0; int act = ACT_NONE;
+                   const float* resid = nullptr; long long ld_resid = 0; float alpha = 1.0f;
+                   const int2* row_range = nullptr; int rows_per_chunk = 1; };
   auto gemm = [&](const void* A, long long lda, const void* B, long long ldb, long long M, int N, int K, int epi,
-                  const GemmEpiParams& ep) -> bool {
+                  const EpiArgs& e) -> bool {
     GemmLaunch g{};
-    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = int(M); g.N = N; g.K = K; g.epi = epi; g.ep = ep;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = int(M); g.N = N; g.K = K; g.epi = epi; g.act = e.act;
+    g.out = e.out; g.ldo = e.ldo;
+    g.ep.bias = e.bias; g.ep.resid = e.resid; g.ep.ld_resid = e.ld_resid; g.ep.alpha = e.alpha;
+    g.ep.row_range = e.row_range; g.ep.rows_per_chunk = e.rows_per_chunk;
     return launch_gemm(g, h->num_sms, st, &err);
   };
 #define CF_TRY(expr) do { if (!(expr)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err); } while (0)
@@ -596,8 +612,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       const int bpc = (T2 * F2 + 127) / 128;
       if (d == 512) frontend_conv0_dw1_kernel<512><<<S * bpc, 128, fe_smem, st>>>(f1);
       else frontend_conv0_dw1_kernel<256><<<S * bpc, 128, fe_smem, st>>>(f1);
+      ++cf::g_kernel_launches;
       CF_CUDA(h, cudaGetLastError());
-      GemmEpiParams e1; e1.bias = h->fe_b3; e1.out = w.b1; e1.ldo = d; e1.act = ACT_RELU;
+      EpiArgs e1; e1.bias = h->fe_b3; e1.out = w.b1; e1.ldo = d; e1.act = ACT_RELU;
       CF_TRY(gemm(w.a1, d, h->fe_w3, d, (long long)S * T2 * F2, d, d, EPI_BF16, e1));
       Fe2Params f2{};
       f2.in = w.b1; f2.out = w.a2; f2.w = h->fe_dw2_w; f2.bias = h->fe_dw2_b; f2.T2 = T2; f2.F2 = F2; f2.T3 = c; f2.F3 = F3;
@@ -605,11 +622,12 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       const unsigned g2 = unsigned((f2.total + 255) / 256);
       if (d == 512) frontend_dw2_kernel<512><<<g2, 256, 0, st>>>(f2);
       else frontend_dw2_kernel<256><<<g2, 256, 0, st>>>(f2);
+      ++cf::g_kernel_launches;
       CF_CUDA(h, cudaGetLastError());
-      GemmEpiParams e2; e2.bias = h->fe_b6; e2.out = w.b2; e2.ldo = d; e2.act = ACT_RELU;
+      EpiArgs e2; e2.bias = h->fe_b6; e2.out = w.b2; e2.ldo = d; e2.act = ACT_RELU;
       CF_TRY(gemm(w.a2, d, h->fe_w6, d, (long long)S * c * F3, d, d, EPI_BF16, e2));
       // (xW + b) * sqrt(d)  (subsampling.py:164, embedding.py:198)
-      GemmEpiParams e3; e3.bias = h->fe_bout; e3.out = w.x + (size_t)g0 * c * d; e3.ldo = d; e3.alpha = sqrtf(float(d));
+      EpiArgs e3; e3.bias = h->fe_bout; e3.out = w.x + (size_t)g0 * c * d; e3.ldo = d; e3.alpha = sqrtf(float(d));
       CF_TRY(gemm(w.b2, (long long)F3 * d, h->fe_wout, (long long)F3 * d, (long long)S * c, d, F3 * d, EPI_F32, e3));
     }
   }
@@ -627,46 +645,47 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = h->layers[i];
     // macaron FFN: x += 0.5 * W2 SiLU(W1 LN(x) + b1) + b2
-    { GemmEpiParams e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
+    { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
       CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
-    { GemmEpiParams e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
+    { EpiArgs e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
       CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
     // self-attention
     CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
     if (att_cache && l > 0) {
       const int tot = l * H * 2 * dk;
       att_cache_import_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<const float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d);
+      ++cf::g_kernel_launches;
     }
-    { GemmEpiParams e; e.bias = lw.qkv_b; e.bias_u = lw.bias_u; e.bias_v = lw.bias_v; e.qkv_d = d;
-      e.out = w.qkv + size_t(l) * 4 * d; e.ldo = 4 * d;
-      CF_TRY(gemm(w.y, d, lw.qkv_w, d, Mr, 3 * d, d, EPI_QKV, e)); }
+    { EpiArgs e; e.bias = lw.qkv_b; e.out = w.qkv + size_t(l) * 4 * d; e.ldo = 4 * d;
+      CF_TRY(gemm(w.y, d, lw.qkv_w, d, Mr, 4 * d, d, EPI_BF16, e)); }
     if (att_cache && l > 0) {
       const int tot = l * H * 2 * dk;
       att_cache_export_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d, trunc);
+      ++cf::g_kernel_launches;
     }
     { AttnParams a{};
       a.qkv = w.qkv; a.pos = pos->dev + size_t(i) * pos->Rpad * d; a.range = w.att_range; a.ctx = w.ctx;
       a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk));
       CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
-    { GemmEpiParams e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
+    { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
     // convolution module
     CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
-    if (cnn_cache) cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo);
-    { GemmEpiParams e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
+    if (cnn_cache) { cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo); ++cf::g_kernel_launches; }
+    { EpiArgs e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
       CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mr, 2 * d, d, EPI_GLU, e)); }
-    if (cnn_cache) cnn_cache_export_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo, trunc);
+    if (cnn_cache) { cnn_cache_export_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo, trunc); ++cf::g_kernel_launches; }
     { DwConvParams q{};
       q.g = w.g; q.z = w.z; q.w = lw.dw_w; q.bias = lw.dw_b; q.ln_w = lw.cn_w; q.ln_b = lw.cn_b; q.range = w.conv_range; q.c = c; q.n_chunks = n;
       CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err)); }
-    { GemmEpiParams e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
+    { EpiArgs e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       e.row_range = w.out_range; e.rows_per_chunk = c;
       CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
     // FFN
     CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
-    { GemmEpiParams e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
+    { EpiArgs e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
       CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mr, F, d, EPI_BF16, e)); }
-    { GemmEpiParams e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
+    { EpiArgs e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
       CF_TRY(gemm(w.hbuf, F, lw.ff_w2, F, Mr, d, F, EPI_F32, e)); }
     if (i + 1 < L) {
       CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));
@@ -691,7 +710,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
 // --------------------------------------------------------------------------------------------------------------------
 extern "C" size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows) {
   if (!h || rows <= 0) return 256;
-  const size_t nt = size_t((h->cfg.vocab + 255) / 256);
+  const size_t nt = 2 * size_t((h->cfg.vocab + 255) / 256);
   return 3 * (size_t(rows) * nt * 4 + 256) + 256;
 }
 
@@ -704,7 +723,7 @@ extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CF_CUDA(h, cudaSetDevice(h->device));
   const int d = h->cfg.d_model, V = h->cfg.vocab;
-  const int nt = (V + 255) / 256;
+  const int nt = 2 * ((V + 255) / 256);
   Carver cv(workspace);
   float* best = cv.take<float>(size_t(rows) * nt);
   float* second = cv.take<float>(size_t(rows) * nt);
@@ -712,7 +731,7 @@ extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, i
   std::string err;
   GemmLaunch g{};
   g.A = enc_bf16; g.lda = d; g.B = h->ctc_w; g.ldb = d; g.M = int(rows); g.N = V; g.K = d; g.epi = EPI_ARGMAX;
-  g.ep.bias = h->ctc_b; g.ep.part_best = best; g.ep.part_second = second; g.ep.part_index = index;
+  g.act = ACT_NONE; g.ep.bias = h->ctc_b; g.ep.part_best = best; g.ep.part_second = second; g.ep.part_index = index;
   if (!launch_gemm(g, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_ctc_greedy: " + err);
   ctc_reduce_kernel<<<unsigned((rows + 255) / 256), 256, 0, st>>>(best, second, index, nt, rows,
                                                                    reinterpret_cast<long long*>(tokens_out), margin_out);
@@ -720,10 +739,11 @@ extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, i
   if (logp_out) {
     GemmLaunch q{};
     q.A = enc_bf16; q.lda = d; q.B = h->ctc_w; q.ldb = d; q.M = int(rows); q.N = V; q.K = d; q.epi = EPI_F32;
-    q.ep.bias = h->ctc_b; q.ep.out = logp_out; q.ep.ldo = V; q.ep.alpha = 1.0f;
+    q.act = ACT_NONE; q.ep.bias = h->ctc_b; q.out = logp_out; q.ldo = V; q.ep.alpha = 1.0f;
     if (V % 4 != 0) return fail(h, CF_ERR_INVALID, "cf_ctc_greedy: logp_out needs vocab % 4 == 0");
     if (!launch_gemm(q, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_ctc_greedy: " + err);
     log_softmax_rows_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(logp_out, rows, V);
+    ++cf::g_kernel_launches;
     CF_CUDA(h, cudaGetLastError());
   }
   return CF_OK;
@@ -739,15 +759,15 @@ static int current_sms() {
 }
 
 extern "C" int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, int act,
-                          const float* bias, const float* bias_u, const float* bias_v, int qkv_d, const float* resid,
-                          int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk, void* out,
-                          int64_t ldo, float* part_best, float* part_second, int32_t* part_index, void* stream) {
+                          const float* bias, const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range,
+                          int rows_per_chunk, void* out, int64_t ldo, float* part_best, float* part_second,
+                          int32_t* part_index, void* stream) {
   if (!A || !B || !bias) return fail(nullptr, CF_ERR_INVALID, "cf_op_gemm: null argument");
   GemmLaunch g{};
-  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.epi = epi;
-  g.ep.bias = bias; g.ep.bias_u = bias_u; g.ep.bias_v = bias_v; g.ep.qkv_d = qkv_d; g.ep.resid = resid;
-  g.ep.ld_resid = ld_resid; g.ep.alpha = alpha; g.ep.act = act; g.ep.row_range = reinterpret_cast<const int2*>(row_range);
-  g.ep.rows_per_chunk = rows_per_chunk > 0 ? rows_per_chunk : 1; g.ep.out = out; g.ep.ldo = ldo;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.epi = epi; g.act = act; g.out = out; g.ldo = ldo;
+  g.ep.bias = bias; g.ep.resid = resid; g.ep.ld_resid = ld_resid; g.ep.alpha = alpha;
+  g.ep.row_range = reinterpret_cast<const int2*>(row_range);
+  g.ep.rows_per_chunk = rows_per_chunk > 0 ? rows_per_chunk : 1;
   g.ep.part_best = part_best; g.ep.part_second = part_second; g.ep.part_index = part_index;
   std::string err;
   if (!launch_gemm(g, current_sms(), static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);

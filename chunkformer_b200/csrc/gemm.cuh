@@ -2,7 +2,9 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor 2-D tiles, 128B swizzle, 4-stage mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x 256 x 16, accumulators in TMEM)
-//   warps 2..5  : epilogue (tcgen05.ld -> registers -> fused bias / activation / GLU / residual / argmax -> global)
+//   warps 2..9  : epilogue, two groups of four warps (one warp per TMEM lane quadrant), each group owns 128 of the
+//                 tile's 256 columns: tcgen05.ld -> registers -> fused bias / activation / GLU / residual -> 128B-swizzled
+//                 staging tile in shared memory -> TMA store (cp.async.bulk.tensor ... bulk_group), or argmax partials.
 //
 // TMEM holds two 128x256 fp32 accumulators (512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Covers every projection of the path (SURVEY.md 2.3 K5,K6,K9,K10,K14,K15,K18,K20): the reference issues these as
@@ -17,44 +19,67 @@ enum GemmEpi : int {
   EPI_BF16 = 0,    // out_bf16 = act(acc + bias)
   EPI_GLU = 1,     // weights row-interleaved (value, gate): out_bf16[:, j] = (acc[2j]+b[2j]) * sigmoid(acc[2j+1]+b[2j+1])
   EPI_F32 = 2,     // out_f32 = resid + rowmask * alpha * (acc + bias)      (resid / rowmask optional)
-  EPI_QKV = 3,     // cols [0,d): Q -> (Q+u) at col, (Q+v) at d+col ; cols [d,3d): K,V at d+col     (bf16)
-  EPI_ARGMAX = 4,  // per (row, n-tile): best logit, runner-up, index of best
+  EPI_ARGMAX = 4,  // per (row, n-tile half): best logit, runner-up, index of best
 };
 enum GemmAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
 
 struct GemmEpiParams {
   const float* bias = nullptr;   // [N]
-  const float* bias_u = nullptr; // EPI_QKV: pos_bias_u flattened [d]
-  const float* bias_v = nullptr; // EPI_QKV: pos_bias_v flattened [d]
-  void* out = nullptr;
-  long long ldo = 0;             // leading dimension of out, in elements
   const float* resid = nullptr;  // EPI_F32
   long long ld_resid = 0;
   float alpha = 1.0f;
-  int act = ACT_NONE;
   const int2* row_range = nullptr;  // EPI_F32: row valid iff range[row / rows_per_chunk].x <= row % rows_per_chunk < .y
   int rows_per_chunk = 1;
-  int qkv_d = 0;
-  float* part_best = nullptr;    // EPI_ARGMAX: [M, n_tiles]
+  float* part_best = nullptr;    // EPI_ARGMAX: [M, 2 * n_tiles]
   float* part_second = nullptr;
   int* part_index = nullptr;
 };
 
 constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr uint32_t GEMM_STAGING_BYTES = 128 * 128;  // 128 rows x 128 bytes, one per epilogue group
 
-template <int BN>
 constexpr size_t gemm_smem_bytes() {
-  return size_t(GEMM_STAGES) * (GEMM_BM * 128 + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return size_t(GEMM_STAGES) * (GEMM_BM * 128 + GEMM_BN * 128) + 2 * GEMM_STAGING_BYTES + 1024 /*align slack*/ + 256;
 }
 
-template <int BN, int EPI>
+// sigmoid / SiLU through one MUFU op (tanh.approx), so the SiLU epilogue stays under the MMA time of a K=512 tile.
+CF_DEVINL float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+CF_DEVINL float silu_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+CF_DEVINL float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+
+CF_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+CF_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+CF_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+CF_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+CF_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 16-byte store into a 128B-swizzled [128 rows][128 B] staging tile (matches CU_TENSOR_MAP_SWIZZLE_128B).
+CF_DEVINL void stage_store16(uint8_t* tile, int row, int slot, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((slot ^ (row & 7)) << 4)) = v;
+}
+
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M, int N,
-                    int K, GemmEpiParams ep) {
-  static_assert(BN == 128 || BN == 256, "BN");
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, GemmEpiParams ep) {
+  constexpr int BN = GEMM_BN;
   constexpr uint32_t A_BYTES = GEMM_BM * 128;
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -63,7 +88,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + GEMM_STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + GEMM_STAGES * B_BYTES);
+  uint8_t* sStage = sB + GEMM_STAGES * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * GEMM_STAGING_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + GEMM_STAGES;      // [STAGES]
   uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;  // [2]
@@ -80,13 +106,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (EPI != EPI_ARGMAX) tma_prefetch_desc(&tma_c);
     for (int s = 0; s < GEMM_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 32 * GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -139,126 +166,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
-    const int quad = warp & 3;
+    // ------------------------------------------------ epilogue: group g = columns [128 g, 128 g + 128) of the tile
+    const int ew = warp - 2;
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int grp = ew >> 2;
+    const bool issuer = ((ew & 3) == 0) && lane == 0;
+    const int bar_id = 1 + grp;
+    uint8_t* stg = sStage + grp * GEMM_STAGING_BYTES;
+    const int trow = quad * 32 + lane;  // row inside the tile
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + quad * 32 + lane;
+      const int row = m_blk * GEMM_BM + trow;
       const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + grp * 128;
+      const int gcol0 = n_blk * BN + grp * 128;   // first global accumulator column of this group
 
-      bool keep = true;   // EPI_F32 row mask: masked rows get exactly +0 (masked_fill_, convolution.py:253)
-      if (EPI == EPI_F32 && ep.row_range != nullptr && row_ok) {
-        const int ch = row / ep.rows_per_chunk;
-        const int rr = row - ch * ep.rows_per_chunk;
-        const int2 rg = ep.row_range[ch];
-        keep = (rr >= rg.x && rr < rg.y);
-      }
-      float best = -INFINITY, second = -INFINITY;
-      int best_idx = 0;
-
+      if (EPI == EPI_ARGMAX) {
+        float best = -INFINITY, second = -INFINITY;
+        int best_idx = 0;
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        const int col0 = n_blk * BN + cc * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + cc * 32, r);
-        tmem_ld_wait();
-        if (EPI == EPI_BF16) {
-          if (row_ok) {
-            uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float v0 = __uint_as_float(r[j]) + __ldg(ep.bias + col0 + j);
-              float v1 = __uint_as_float(r[j + 1]) + __ldg(ep.bias + col0 + j + 1);
-              if (ep.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-              if (ep.act == ACT_SILU) { v0 = silu(v0); v1 = silu(v1); }
-              o[j >> 1] = pack_bf16(v0, v1);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldo + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          }
-        } else if (EPI == EPI_GLU) {
-          if (row_ok) {
-            uint32_t o[8];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float a0 = __uint_as_float(r[j]) + __ldg(ep.bias + col0 + j);
-              float g0 = __uint_as_float(r[j + 1]) + __ldg(ep.bias + col0 + j + 1);
-              float a1 = __uint_as_float(r[j + 2]) + __ldg(ep.bias + col0 + j + 2);
-              float g1 = __uint_as_float(r[j + 3]) + __ldg(ep.bias + col0 + j + 3);
-              o[j >> 2] = pack_bf16(a0 * sigmoidf_(g0), a1 * sigmoidf_(g1));
-            }
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldo + (col0 >> 1));
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          }
-        } else if (EPI == EPI_F32) {
-          if (row_ok) {
-            float* dst = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + col0;
-            const float* rs = ep.resid ? ep.resid + (long long)row * ep.ld_resid + col0 : nullptr;
-            const float sc = ep.alpha;
-            if (col0 + 32 > N) {   // ragged last column block (e.g. vocab 5000): scalar, bounds-checked
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (col0 + j < N) {
-                  float v = keep ? sc * (__uint_as_float(r[j]) + __ldg(ep.bias + col0 + j)) : 0.f;
-                  if (rs) v += rs[j];
-                  dst[j] = v;
-                }
-              }
-            } else
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v;
-              v.x = sc * (__uint_as_float(r[j]) + __ldg(ep.bias + col0 + j));
-              v.y = sc * (__uint_as_float(r[j + 1]) + __ldg(ep.bias + col0 + j + 1));
-              v.z = sc * (__uint_as_float(r[j + 2]) + __ldg(ep.bias + col0 + j + 2));
-              v.w = sc * (__uint_as_float(r[j + 3]) + __ldg(ep.bias + col0 + j + 3));
-              if (!keep) v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rs) {
-                const float4 x = *reinterpret_cast<const float4*>(rs + j);
-                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-              }
-              *reinterpret_cast<float4*>(dst + j) = v;
-            }
-          }
-        } else if (EPI == EPI_QKV) {
-          if (row_ok) {
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldo;
-            if (col0 < ep.qkv_d) {
-              uint32_t ou[16], ov[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float q0 = __uint_as_float(r[j]) + __ldg(ep.bias + col0 + j);
-                const float q1 = __uint_as_float(r[j + 1]) + __ldg(ep.bias + col0 + j + 1);
-                ou[j >> 1] = pack_bf16(q0 + __ldg(ep.bias_u + col0 + j), q1 + __ldg(ep.bias_u + col0 + j + 1));
-                ov[j >> 1] = pack_bf16(q0 + __ldg(ep.bias_v + col0 + j), q1 + __ldg(ep.bias_v + col0 + j + 1));
-              }
-              uint4* du = reinterpret_cast<uint4*>(orow + col0);
-              uint4* dv = reinterpret_cast<uint4*>(orow + ep.qkv_d + col0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                du[q] = make_uint4(ou[4 * q], ou[4 * q + 1], ou[4 * q + 2], ou[4 * q + 3]);
-                dv[q] = make_uint4(ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]);
-              }
-            } else {
-              uint32_t o[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 2)
-                o[j >> 1] = pack_bf16(__uint_as_float(r[j]) + __ldg(ep.bias + col0 + j),
-                                      __uint_as_float(r[j + 1]) + __ldg(ep.bias + col0 + j + 1));
-              uint4* dst = reinterpret_cast<uint4*>(orow + ep.qkv_d + col0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-            }
-          }
-        } else if (EPI == EPI_ARGMAX) {
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col0 = gcol0 + cc * 32;
+          if (col0 >= N) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
@@ -269,16 +205,118 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           }
         }
-      }
-      if (EPI == EPI_ARGMAX && row_ok) {
-        const long long p = (long long)row * n_tiles + n_blk;
-        ep.part_best[p] = best;
-        ep.part_second[p] = second;
-        ep.part_index[p] = best_idx;
+        if (row_ok) {
+          const long long p = (long long)row * (2 * n_tiles) + 2 * n_blk + grp;
+          ep.part_best[p] = best;
+          ep.part_second[p] = second;
+          ep.part_index[p] = best_idx;
+        }
+      } else if (EPI == EPI_F32) {
+        bool keep = true;   // masked rows get exactly +0 added (masked_fill_, convolution.py:253)
+        if (ep.row_range != nullptr && row_ok) {
+          const int ch = row / ep.rows_per_chunk;
+          const int rr = row - ch * ep.rows_per_chunk;
+          const int2 rg = ep.row_range[ch];
+          keep = (rr >= rg.x && rr < rg.y);
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {   // one 32-column fp32 sub-tile (128 B per row) per round
+          const int col0 = gcol0 + cc * 32;
+          if (col0 >= N) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          float4 x[8];
+          const bool has_res = ep.resid != nullptr && row_ok;
+          if (has_res) {
+            const float4* rs = reinterpret_cast<const float4*>(ep.resid + (long long)row * ep.ld_resid + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = (col0 + 4 * q < N) ? rs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (issuer) tma_store_wait_read();
+          named_bar_sync(bar_id, 128);       // staging tile free again
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col0 + 4 * q < N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
+            float4 v;
+            v.x = ep.alpha * (__uint_as_float(r[4 * q]) + b.x);
+            v.y = ep.alpha * (__uint_as_float(r[4 * q + 1]) + b.y);
+            v.z = ep.alpha * (__uint_as_float(r[4 * q + 2]) + b.z);
+            v.w = ep.alpha * (__uint_as_float(r[4 * q + 3]) + b.w);
+            if (!keep) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res) { v.x += x[q].x; v.y += x[q].y; v.z += x[q].z; v.w += x[q].w; }
+            stage_store16(stg, trow, q, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+          }
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (issuer) { tma_store_2d(&tma_c, stg, col0, m_blk * GEMM_BM); tma_store_commit(); }
+        }
+      } else {
+        // bf16 outputs: EPI_BF16 -> two 64-column sub-tiles per group; EPI_GLU -> one 64-column sub-tile (128 acc columns)
+        constexpr int ROUNDS = (EPI == EPI_GLU) ? 1 : 2;
+        constexpr int CH_PER_ROUND = (EPI == EPI_GLU) ? 4 : 2;
+#pragma unroll 1
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+          const int acol0 = gcol0 + rd * 64;       // accumulator column of this round (EPI_BF16)
+          if (acol0 >= N) break;
+          if (issuer) tma_store_wait_read();
+          named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int cc = 0; cc < CH_PER_ROUND; ++cc) {
+            const int tcol = (EPI == EPI_GLU) ? cc * 32 : rd * 64 + cc * 32;   // column inside the group's 128
+            const int col0 = gcol0 + tcol;
+            uint32_t r[32];
+            tmem_ld32(taddr + tcol, r);
+            float b[32];
+            if (col0 < N) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
+                b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) b[j] = 0.f;
+            }
+            tmem_ld_wait();
+            if (EPI == EPI_GLU) {
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float a0 = __uint_as_float(r[j]) + b[j], g0 = __uint_as_float(r[j + 1]) + b[j + 1];
+                const float a1 = __uint_as_float(r[j + 2]) + b[j + 2], g1 = __uint_as_float(r[j + 3]) + b[j + 3];
+                o[j >> 2] = pack_bf16(a0 * sigmoid_fast(g0), a1 * sigmoid_fast(g1));
+              }
+              stage_store16(stg, trow, 2 * cc, make_uint4(o[0], o[1], o[2], o[3]));
+              stage_store16(stg, trow, 2 * cc + 1, make_uint4(o[4], o[5], o[6], o[7]));
+            } else {
+              uint32_t o[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float v0 = __uint_as_float(r[j]) + b[j], v1 = __uint_as_float(r[j + 1]) + b[j + 1];
+                if (ACT == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                if (ACT == ACT_SILU) { v0 = silu_fast(v0); v1 = silu_fast(v1); }
+                o[j >> 1] = pack_bf16(v0, v1);
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                stage_store16(stg, trow, 4 * cc + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            const int ocol = (EPI == EPI_GLU) ? (gcol0 >> 1) : acol0;
+            tma_store_2d(&tma_c, stg, ocol, m_blk * GEMM_BM);
+            tma_store_commit();
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
+    if (issuer && EPI != EPI_ARGMAX) tma_store_wait_all();   // global writes complete before the CTA exits
   }
 
   tc_fence_before();

@@ -3,12 +3,15 @@
 #pragma once
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
 #include "gemm.cuh"
 
 namespace cf {
+
+extern std::atomic<long long> g_kernel_launches;
 
 inline PFN_cuTensorMapEncodeTiled_v12000 get_tensor_map_encoder(std::string* err) {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -29,42 +32,59 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_tensor_map_encoder(std::string* err
   return fn;
 }
 
-// 2-D bf16 row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
-inline bool make_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-                             uint32_t box_rows, uint32_t box_cols, std::string* err) {
+// 2-D row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols]; 128B swizzle
+// (box_cols * elem_bytes must be 128).
+inline bool make_tma_2d(CUtensorMap* map, const void* ptr, bool is_f32, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_rows, uint32_t box_cols, std::string* err) {
   auto enc = get_tensor_map_encoder(err);
   if (!enc) return false;
+  const size_t esz = is_f32 ? 4 : 2;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(__nv_bfloat16)};
+  cuuint64_t strides[1] = {ld * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r));
     return false;
   }
   return true;
 }
+inline bool make_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows, uint32_t box_cols, std::string* err) {
+  return make_tma_2d(map, ptr, false, rows, cols, ld, box_rows, box_cols, err);
+}
 
 struct GemmLaunch {
   const void* A; long long lda;  // [M, K] bf16
   const void* B; long long ldb;  // [N, K] bf16 (nn.Linear weight layout)
   int M, N, K;
-  int epi;
+  int epi, act;
+  void* out; long long ldo;      // bf16 [M, N] (EPI_BF16), bf16 [M, N/2] (EPI_GLU), fp32 [M, N] (EPI_F32); unused for EPI_ARGMAX
   GemmEpiParams ep;
 };
 
-template <int EPI>
+template <int EPI, int ACT>
 inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
-  constexpr int BN = 256;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   if (!make_tma_2d_bf16(&ta, g.A, g.M, g.K, g.lda, GEMM_BM, GEMM_BK, err)) return false;
-  if (!make_tma_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, BN, GEMM_BK, err)) return false;
-  auto kern = gemm_tcgen05_kernel<BN, EPI>;
+  if (!make_tma_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, GEMM_BN, GEMM_BK, err)) return false;
+  if (EPI == EPI_ARGMAX) {
+    tc = ta;
+  } else {
+    const bool f32 = EPI == EPI_F32;
+    const uint64_t ocols = EPI == EPI_GLU ? uint64_t(g.N / 2) : uint64_t(g.N);
+    if (g.out == nullptr || (g.ldo * (f32 ? 4 : 2)) % 16 != 0) {
+      if (err) *err = "gemm: output pointer missing or leading dimension not 16-byte aligned";
+      return false;
+    }
+    if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
+  }
+  auto kern = gemm_tcgen05_kernel<EPI, ACT>;
   static bool attr_set = false;
-  const size_t smem = gemm_smem_bytes<BN>();
+  const size_t smem = gemm_smem_bytes();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) {
@@ -73,11 +93,12 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
     }
     attr_set = true;
   }
-  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + BN - 1) / BN;
+  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + GEMM_BN - 1) / GEMM_BN;
   const int tiles = m_tiles * n_tiles;
   if (tiles == 0) return true;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, g.M, g.N, g.K, g.ep);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, g.M, g.N, g.K, g.ep);
+  ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm launch: ") + cudaGetErrorString(e);
@@ -91,12 +112,18 @@ inline bool launch_gemm(const GemmLaunch& g, int num_sms, cudaStream_t stream, s
     if (err) *err = "gemm: K must be a multiple of 64 and leading dimensions multiples of 8";
     return false;
   }
+  if (g.epi != EPI_ARGMAX && g.N % 8 != 0) {
+    if (err) *err = "gemm: N must be a multiple of 8 for stored outputs";
+    return false;
+  }
   switch (g.epi) {
-    case EPI_BF16: return launch_gemm_epi<EPI_BF16>(g, num_sms, stream, err);
-    case EPI_GLU: return launch_gemm_epi<EPI_GLU>(g, num_sms, stream, err);
-    case EPI_F32: return launch_gemm_epi<EPI_F32>(g, num_sms, stream, err);
-    case EPI_QKV: return launch_gemm_epi<EPI_QKV>(g, num_sms, stream, err);
-    case EPI_ARGMAX: return launch_gemm_epi<EPI_ARGMAX>(g, num_sms, stream, err);
+    case EPI_BF16:
+      if (g.act == ACT_RELU) return launch_gemm_epi<EPI_BF16, ACT_RELU>(g, num_sms, stream, err);
+      if (g.act == ACT_SILU) return launch_gemm_epi<EPI_BF16, ACT_SILU>(g, num_sms, stream, err);
+      return launch_gemm_epi<EPI_BF16, ACT_NONE>(g, num_sms, stream, err);
+    case EPI_GLU: return launch_gemm_epi<EPI_GLU, ACT_NONE>(g, num_sms, stream, err);
+    case EPI_F32: return launch_gemm_epi<EPI_F32, ACT_NONE>(g, num_sms, stream, err);
+    case EPI_ARGMAX: return launch_gemm_epi<EPI_ARGMAX, ACT_NONE>(g, num_sms, stream, err);
   }
   if (err) *err = "gemm: unknown epilogue";
   return false;

@@ -73,15 +73,14 @@ class ChunkFormerEncoderB200:
         return self._ws
 
     def _flat_feats(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
-        if all(x.device.type == "cpu" for x in xs):
-            total = sum(int(x.shape[0]) for x in xs)
-            host = torch.empty((total, self.geo.feat_dim), dtype=torch.float32, pin_memory=True)
-            row = 0
-            for x in xs:
-                host[row:row + x.shape[0]] = x
-                row += x.shape[0]
-            return host.to(self.device, non_blocking=True)
-        return torch.cat([x.to(self.device, torch.float32) for x in xs], dim=0).contiguous()
+        """Ragged utterances -> one flat device buffer [sum T_i, feat] (pinned host tensors copy asynchronously)."""
+        total = sum(int(x.shape[0]) for x in xs)
+        flat = torch.empty((total, self.geo.feat_dim), dtype=torch.float32, device=self.device)
+        row = 0
+        for x in xs:
+            flat[row:row + x.shape[0]].copy_(x, non_blocking=True)
+            row += x.shape[0]
+        return flat
 
     def encode_plan(self, plan: Plan, feats: torch.Tensor, att_cache=None, cnn_cache=None, trunc: int = 0,
                     out_dtype=torch.float32, want_bf16: bool = False):

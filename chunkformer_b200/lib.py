@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 from . import build as _build
 
 CF_F32, CF_BF16 = 0, 1
-EPI_BF16, EPI_GLU, EPI_F32, EPI_QKV, EPI_ARGMAX = 0, 1, 2, 3, 4
+EPI_BF16, EPI_GLU, EPI_F32, EPI_ARGMAX = 0, 1, 2, 4
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 
 
@@ -24,6 +24,7 @@ SIGNATURES = {
     "cf_destroy": (None, [c_void_p]),
     "cf_last_error": (c_char_p, [c_void_p]),
     "cf_version": (c_char_p, []),
+    "cf_launch_count": (ctypes.c_longlong, []),
     "cf_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),
     "cf_finalize_weights": (c_int, [c_void_p]),
     "cf_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int64),
@@ -41,8 +42,7 @@ SIGNATURES = {
     "cf_ctc_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "cf_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cf_op_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                           c_void_p, c_int, c_void_p, c_int64, c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p,
-                           c_void_p, c_void_p, c_void_p]),
+                           c_int64, c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_op_layernorm": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_void_p]),
     "cf_op_dwconv": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

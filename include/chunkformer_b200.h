@@ -61,6 +61,8 @@ CF_API void cf_destroy(cf_handle* h);
 /* Last error message of `h` (or of the last failed cf_create / plan call when h == NULL). Never NULL. */
 CF_API const char* cf_last_error(const cf_handle* h);
 CF_API const char* cf_version(void);
+/* Number of kernels this library has launched in the process so far (bench.py reports the per-step count). */
+CF_API long long cf_launch_count(void);
 
 /* ---- weights ----------------------------------------------------------------------------------------------------- */
 /* Replaces: load_checkpoint -> model.load_state_dict(strict=False) (chunkformer/utils/checkpoint.py:26-41).
@@ -118,12 +120,13 @@ CF_API int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, int64
                   float* logp_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- kernel-level entry points (parity tests, profiling) --------------------------------------------------------- */
-/* C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 GEMM with a fused epilogue; epi: 0 bf16(bias,act) 1 GLU 2 f32(resid,alpha,
- * rowmask) 3 QKV 4 argmax partials; act: 0 none 1 relu 2 silu. All pointers device. */
+/* C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 GEMM with a fused epilogue; epi: 0 bf16 out = act(acc+bias), 1 GLU (bf16,
+ * N/2 columns, value/gate rows interleaved), 2 fp32 out = resid + rowmask*alpha*(acc+bias), 4 argmax partials
+ * [M, 2*ceil(N/256)]; act: 0 none 1 relu 2 silu. All pointers device. */
 CF_API int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, int act,
-               const float* bias, const float* bias_u, const float* bias_v, int qkv_d, const float* resid,
-               int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk, void* out, int64_t ldo,
-               float* part_best, float* part_second, int32_t* part_index, void* stream);
+               const float* bias, const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range,
+               int rows_per_chunk, void* out, int64_t ldo, float* part_best, float* part_second, int32_t* part_index,
+               void* stream);
 /* mode 0: y=LN1(x); 1: x<-LN1(x), y=LN2(x); 2: out=LN2(LN1(x)). */
 CF_API int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1, const float* b1,
                     const float* w2, const float* b2, int64_t rows, void* stream);

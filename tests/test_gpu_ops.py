@@ -22,12 +22,11 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _gemm(A, B, epi, out, bias, act=0, bias_u=None, bias_v=None, qkv_d=0, resid=None, alpha=1.0, row_range=None,
-          rows_per_chunk=1, parts=(None, None, None)):
+def _gemm(A, B, epi, out, bias, act=0, resid=None, alpha=1.0, row_range=None, rows_per_chunk=1, parts=(None, None, None)):
     L = cflib.load()
     M, K = A.shape
     N = B.shape[0]
-    rc = L.cf_op_gemm(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, epi, act, _p(bias), _p(bias_u), _p(bias_v), qkv_d,
+    rc = L.cf_op_gemm(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, epi, act, _p(bias),
                       _p(resid), resid.stride(0) if resid is not None else 0, alpha, _p(row_range), rows_per_chunk,
                       _p(out), out.stride(0) if out is not None else 0, _p(parts[0]), _p(parts[1]), _p(parts[2]), _stream())
     cflib.check(rc, None, "cf_op_gemm")
@@ -101,17 +100,17 @@ def test_gemm_f32_residual_rowmask():
     assert (outv - refv).abs().max().item() < 2e-3
 
 
-def test_gemm_qkv():
-    M, d = 333, 512
+def test_gemm_strided_output_view():
+    """The fused [Q+u | Q+v | K | V] projection writes into a row-offset view of the flat QKV buffer."""
+    M, d, lead = 333, 512, 128
     A = _rand((M, d), 1.0, 1).bfloat16()
-    W = _rand((3 * d, d), 1.0 / math.sqrt(d), 2).bfloat16()
-    b = _rand((3 * d,), 0.5, 3)
-    u, v = _rand((d,), 0.2, 4), _rand((d,), 0.2, 5)
-    out = torch.zeros((M, 4 * d), device=DEV, dtype=torch.bfloat16)
-    _gemm(A, W, cflib.EPI_QKV, out, b, bias_u=u, bias_v=v, qkv_d=d)
-    h = A.float() @ W.float().T + b
-    ref = torch.cat([h[:, :d] + u, h[:, :d] + v, h[:, d:]], dim=1)
-    assert (out.float() - ref).abs().max().item() < 3e-2
+    W = _rand((4 * d, d), 1.0 / math.sqrt(d), 2).bfloat16()
+    b = _rand((4 * d,), 0.5, 3)
+    buf = torch.full((lead + M + 64, 4 * d), 3.0, device=DEV, dtype=torch.bfloat16)
+    _gemm(A, W, cflib.EPI_BF16, buf[lead:lead + M], b)
+    ref = A.float() @ W.float().T + b
+    assert (buf[lead:lead + M].float() - ref).abs().max().item() < 3e-2
+    assert bool((buf[:lead] == 3.0).all()) and bool((buf[lead + M:] == 3.0).all())   # rows outside [0, M) untouched
 
 
 def test_gemm_argmax_partials():
@@ -119,7 +118,7 @@ def test_gemm_argmax_partials():
     A = _rand((M, d), 1.0, 1).bfloat16()
     W = _rand((V, d), 1.0 / math.sqrt(d), 2).bfloat16()
     b = _rand((V,), 0.5, 3)
-    nt = (V + 255) // 256
+    nt = 2 * ((V + 255) // 256)
     best = torch.zeros((M, nt), device=DEV)
     second = torch.zeros((M, nt), device=DEV)
     index = torch.zeros((M, nt), device=DEV, dtype=torch.int32)
