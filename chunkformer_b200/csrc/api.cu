@@ -553,7 +553,10 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   const int n = p->n;
   const long long Mr = (long long)n * c;
   if (Mr == 0) return CF_OK;
-  if (att_cache && (trunc < 0 || trunc > Mr)) return fail(h, CF_ERR_INVALID, "cf_encode: truncated_context_size out of range");
+  if (att_cache && trunc < 0) return fail(h, CF_ERR_INVALID, "cf_encode: truncated_context_size must be >= 0");
+  // kv[: trunc + l][-l:] (attention.py:466-467) and x[:, : trunc + lorder][:, -lorder:] (convolution.py:228-230) clamp at
+  // the end of the buffer: a final segment shorter than the kept context hands over its last rows.
+  if (trunc > Mr) trunc = int(Mr);
   std::string err;
   const PosTable* pos = nullptr;
   int rc = get_pos_table(h, c, l, r, st, &pos);

@@ -1,0 +1,76 @@
+"""Host-side token post-processing (stays Python on the host, as in the reference: chunkformer/utils/model_utils.py).
+
+Same observable behaviour as `remove_duplicates_and_blank` (:23-32), `class2str` (:135-139), `get_output` (:164-171) and
+`get_output_with_timestamps` (:174-222): CTC collapse, id -> text with the sentencepiece space marker, and
+silence-based segmentation with hh:mm:ss:ms stamps (80 ms per encoder frame)."""
+import math
+from typing import Dict, List, Sequence
+
+import torch
+
+
+def ctc_collapse(tokens: Sequence[int], blank_id: int = 0) -> List[int]:
+    out: List[int] = []
+    prev = None
+    for t in tokens:
+        t = int(t)
+        if t != prev and t != blank_id:
+            out.append(t)
+        prev = t
+    return out
+
+
+def ids_to_text(ids: Sequence[int], char_dict: Dict[int, str]) -> str:
+    return "".join(char_dict[int(i)] for i in ids).replace("▁", " ")
+
+
+def format_ms(ms: int) -> str:
+    h, rem = divmod(int(ms), 3600 * 1000)
+    m, rem = divmod(rem, 60 * 1000)
+    s, rem = divmod(rem, 1000)
+    return f"{h:02}:{m:02}:{s:02}:{rem:03}"
+
+
+def get_output(hyps, char_dict: Dict[int, str], model_type: str = "asr_model") -> List[str]:
+    res = []
+    for hyp in hyps:
+        ids = [int(v) for v in (hyp.tolist() if torch.is_tensor(hyp) else hyp)]
+        if model_type == "asr_model":
+            ids = ctc_collapse(ids)
+        res.append(ids_to_text(ids, char_dict).strip())
+    return res
+
+
+def get_output_with_timestamps(hyps, char_dict: Dict[int, str], model_type: str, max_silence_duration: float):
+    """hyps: iterable of (T', k) token tensors (k = 1 for CTC). A segment closes after `max_silence_duration // 0.08`
+    consecutive blank frames; its start is pulled back by up to 2 frames (midpoint to the previous segment's end)."""
+    results = []
+    max_silence = max_silence_duration // 0.08
+    for tokens in hyps:
+        tokens = tokens.cpu()
+        rows = tokens.reshape(tokens.shape[0], -1).tolist()
+        start = end = prev_end = -1
+        silence = 0
+        pending: List[int] = []
+        segs = []
+        t = -1
+        for t, row in enumerate(rows):
+            nonblank = [v for v in row if v != 0]
+            if not nonblank:
+                silence += 1
+            else:
+                if start == -1 and end == -1:
+                    start = max(math.ceil((t + prev_end) / 2), t - 2) if prev_end != -1 else max(t - 2, 0)
+                silence = 0
+                pending.extend(nonblank)
+            if silence == max_silence and start != -1:
+                end = t
+                prev_end = end
+                segs.append({"decode": get_output([pending], char_dict, model_type)[0],
+                             "start": format_ms(start * 80), "end": format_ms(end * 80)})
+                pending, start, end, silence = [], -1, -1, 0
+        if start != -1 and end == -1 and pending:
+            segs.append({"decode": get_output([pending], char_dict, model_type)[0],
+                         "start": format_ms(start * 80), "end": format_ms(t * 80)})
+        results.append(segs)
+    return results

@@ -217,7 +217,8 @@ def _attention(sd, p, H, y, plan: Plan, pe, att_cache, trunc):
     vf = torch.cat([vc, v, torch.zeros(r, H, dk)], 0)
     new_cache = None
     if att_cache is not None:
-        new_cache = torch.cat([kf, vf], -1)[trunc:trunc + l].clone()
+        t0 = min(trunc, n * c)              # kv[: trunc + l][-l:] clamps at the end of the buffer (attention.py:466-467)
+        new_cache = torch.cat([kf, vf], -1)[t0:t0 + l].clone()
     win = (c * torch.arange(n)).unsqueeze(1) + torch.arange(W).unsqueeze(0)      # (n, W)
     kw = kf[win].permute(0, 2, 1, 3)                                                # (n, H, W, dk)
     vw = vf[win].permute(0, 2, 1, 3)
@@ -253,7 +254,8 @@ def _conv_module(sd, p, y, plan: Plan, cnn_cache, trunc):
     gf = torch.cat([left, g, torch.zeros(lo, d)], 0)                                # row f + lo  <->  frame f
     new_cache = None
     if cnn_cache is not None:
-        new_cache = gf[trunc:trunc + lo].T.clone()
+        t0 = min(trunc, n * c)              # x[:, : trunc + lo][:, -lo:] (convolution.py:228-230)
+        new_cache = gf[t0:t0 + lo].T.clone()
     win = (c * torch.arange(n)).unsqueeze(1) + torch.arange(c + 2 * lo).unsqueeze(0)
     gw = gf[win] * torch.from_numpy(plan.conv_mask).unsqueeze(-1)                   # (n, c+2lo, d)
     wd = sd[p + "depthwise_conv.weight"].view(d, -1)                                # (d, K)

@@ -1,0 +1,192 @@
+"""Drop-in facade on a B200: from_pretrained on a reference-layout checkpoint directory, encode, endless_decode,
+batch_decode, classify_audio, and chunk-range sharding of one long recording — each against the CPU oracle driven the
+way the reference's facade drives its encoder (chunkformer_model.py:256-640)."""
+import json
+import os
+
+import pytest
+import torch
+import yaml
+
+from chunkformer_b200.geometry import EncoderGeometry
+from chunkformer_b200.model import ChunkFormerModel
+from chunkformer_b200.shard import split_recording
+from chunkformer_b200.synth import synth_fbank, synth_state_dict
+from oracle import chunkformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GEO = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=3, kernel=15, vocab=120, has_cmvn=True)
+MARGIN_TOL = 0.08
+
+
+def _encoder_conf(geo):
+    return dict(output_size=geo.d_model, attention_heads=geo.heads, linear_units=geo.ffn, num_blocks=geo.layers,
+                input_layer="dw_striding", cnn_module_kernel=geo.kernel, cnn_module_norm="layer_norm", dynamic_conv=True,
+                activation_type="swish", pos_enc_layer_type="chunk_rel_pos", selfattention_layer_type="chunk_rel_seflattn")
+
+
+@pytest.fixture(scope="module")
+def asr_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("asr_model")
+    sd = synth_state_dict(GEO, 21)
+    mean, istd = sd.pop("encoder.global_cmvn.mean"), sd.pop("encoder.global_cmvn.istd")
+    sd["decoder.embed.0.weight"] = torch.zeros(4, 4)            # ignored like load_state_dict(strict=False)
+    torch.save(sd, d / "pytorch_model.bin")
+    yaml.safe_dump(dict(input_dim=80, output_dim=GEO.vocab, model="asr_model", encoder="chunkformer",
+                        encoder_conf=_encoder_conf(GEO), ctc_conf=dict(ctc_blank_id=0)), open(d / "config.yaml", "w"))
+    n = 1000.0   # global_cmvn json: mean_stat / var_stat / frame_num (utils/cmvn.py:23-46)
+    var = (1.0 / istd) ** 2
+    json.dump(dict(mean_stat=(mean * n).tolist(), var_stat=((var + mean * mean) * n).tolist(), frame_num=n),
+              open(d / "global_cmvn", "w"))
+    with open(d / "vocab.txt", "w", encoding="utf8") as f:
+        f.write("<blank> 0\n<unk> 1\n")
+        for i in range(2, GEO.vocab):
+            f.write(("▁" if i % 4 == 0 else "") + f"t{i} {i}\n")
+    return str(d)
+
+
+@pytest.fixture(scope="module")
+def asr(asr_dir):
+    return ChunkFormerModel.from_pretrained(asr_dir, device=DEV)
+
+
+def _oracle_sd():
+    sd = synth_state_dict(GEO, 21)
+    # the json round trip of the CMVN statistics is exact to fp32 rounding; use the same values the model loaded
+    return sd
+
+
+def test_from_pretrained_errors(tmp_path):
+    with pytest.raises(ValueError):
+        ChunkFormerModel.from_pretrained(str(tmp_path), device=DEV)          # no config
+    yaml.safe_dump(dict(input_dim=80, output_dim=10, encoder_conf=_encoder_conf(GEO)), open(tmp_path / "config.yaml", "w"))
+    with pytest.raises(ValueError):
+        ChunkFormerModel.from_pretrained(str(tmp_path), device=DEV)          # no checkpoint
+
+
+def test_encode_matches_oracle(asr):
+    sd = _oracle_sd()
+    lens = [280, 150]
+    xb = torch.zeros(2, 280, 80)
+    for k, t in enumerate(lens):
+        xb[k, :t] = synth_fbank(t, seed=30 + k)
+    out, out_lens = asr.encode(xb, torch.tensor(lens), chunk_size=16, left_context_size=32, right_context_size=16)
+    ref, mask = O.forward_encoder(sd, GEO.heads, xb, lens, 16, 32, 16)
+    assert out_lens.tolist() == mask.squeeze(1).sum(-1).tolist()
+    for b, m in enumerate(out_lens.tolist()):
+        assert (out[b, :m].cpu() - ref[b, :m]).abs().max().item() < 0.12
+    with pytest.raises(NotImplementedError):
+        asr.forward()
+
+
+def test_endless_decode_matches_reference_driver(asr):
+    """Segmented long-form decoding with carried caches == the oracle driven by the reference's segment arithmetic."""
+    sd = _oracle_sd()
+    c, l, r, tbd = 16, 32, 16, 20
+    T = 3300
+    x = synth_fbank(T, seed=40)
+    res = asr.endless_decode(x, c, l, r, total_batch_duration=tbd, return_timestamps=True, max_silence_duration=0.16)
+    text = asr.endless_decode(x, c, l, r, total_batch_duration=tbd, return_timestamps=False, max_silence_duration=0.16)
+    assert isinstance(res, list) and isinstance(text, str) and all(set(i) == {"decode", "start", "end"} for i in res)
+    # oracle driven exactly like chunkformer_model.py:391-434
+    trunc, rel_right, segs = O.endless_segments(T, c, r, GEO.layers, tbd)
+    assert len(segs) >= 3
+    L, H, d = GEO.layers, GEO.heads, GEO.d_model
+    att, cnn, off, outs = torch.zeros(L, l, H, 2 * d // H), torch.zeros(L, d, 7), [0], []
+    for (s, e, last) in segs:
+        o, ol, _, att, cnn, noff = O.forward_parallel_chunk(sd, H, [x[s:e]], [e - s], c, l, r, att, cnn, trunc, off)
+        o = o.reshape(-1, d)[: int(ol[0])]
+        if not last:
+            o = o[:trunc]
+        off = [int(noff[0]) - int(ol[0]) + o.shape[0]]
+        outs.append(o)
+    enc = torch.cat(outs, 0)
+    tok, margin = O.ctc_greedy(sd, enc)
+    asr.char_dict, keep = None, asr.char_dict
+    got = asr.endless_decode(x, c, l, r, total_batch_duration=tbd).reshape(-1).cpu()
+    asr.char_dict = keep
+    assert got.shape == tok.shape
+    assert bool(((got == tok) | (margin < MARGIN_TOL)).all())
+
+
+def test_batch_decode_matches_oracle(asr):
+    sd = _oracle_sd()
+    lens = [900, 77, 1500, 300, 2200]
+    xs = [synth_fbank(t, seed=60 + k) for k, t in enumerate(lens)]
+    texts = asr.batch_decode(xs, 16, 32, 16, total_batch_duration=30)      # budget 1500 frames -> several groups
+    assert len(texts) == len(lens) and all(isinstance(t, str) for t in texts)
+    groups = O.batch_groups(lens, 30)
+    assert len(groups) > 1
+    asr.char_dict, keep = None, asr.char_dict
+    hyps = asr.batch_decode(xs, 16, 32, 16, total_batch_duration=30)
+    asr.char_dict = keep
+    k = 0
+    for grp in groups:
+        out, enc_lens, n_chunks, _, _, _ = O.forward_parallel_chunk(sd, GEO.heads, [xs[i] for i in grp], [lens[i] for i in grp], 16, 32, 16)
+        tok, margin = O.ctc_greedy(sd, out)
+        row = 0
+        for u, nck in enumerate(n_chunks):
+            m = max(int(enc_lens[u]), 0)
+            a = hyps[k].cpu()
+            b = tok[row:row + nck].reshape(-1)[:m]
+            mg = margin[row:row + nck].reshape(-1)[:m]
+            assert a.shape == b.shape and bool(((a == b) | (mg < MARGIN_TOL)).all())
+            row += nck
+            k += 1
+
+
+def test_classify_audio_full_and_chunked(tmp_path):
+    geo = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=2, kernel=15, vocab=0)
+    sd = synth_state_dict(geo, 31)
+    g = torch.Generator().manual_seed(9)
+    tasks = {"gender": 2, "emotion": 7}
+    for name, n in tasks.items():
+        sd[f"classification_heads.{name}.linear.weight"] = torch.randn(n, 256, generator=g) * 0.2
+        sd[f"classification_heads.{name}.linear.bias"] = torch.randn(n, generator=g) * 0.1
+    torch.save(sd, tmp_path / "pytorch_model.pt")
+    yaml.safe_dump(dict(input_dim=80, model="classification", encoder="chunkformer", encoder_conf=_encoder_conf(geo),
+                        model_conf=dict(tasks=tasks)), open(tmp_path / "config.yaml", "w"))
+    json.dump({"gender": {"0": "female", "1": "male"}}, open(tmp_path / "label_mapping.json", "w"))
+    m = ChunkFormerModel.from_pretrained(str(tmp_path), device=DEV)
+    assert m.is_classification and m.get_tasks() == tasks
+    x = synth_fbank(500, seed=70)
+    for cfg in ((-1, -1, -1), (16, 32, 16)):
+        res = m.classify_audio(x, *cfg)
+        c, l, r = (61, 0, 0) if cfg[0] < 0 else cfg          # full attention = one chunk of T' = 61 frames
+        ref, mask = O.forward_encoder(sd, geo.heads, x.unsqueeze(0), [500], c, l, r)
+        pooled = (ref * mask.transpose(1, 2).float()).sum(1) / mask.sum()
+        for name in tasks:
+            logits = pooled @ sd[f"classification_heads.{name}.linear.weight"].T + sd[f"classification_heads.{name}.linear.bias"]
+            p = torch.softmax(logits, -1)[0]
+            assert set(res[name]) == {"label", "label_id", "prob"}
+            top2 = p.topk(2).values
+            if float(top2[0] - top2[1]) > 0.05:
+                assert res[name]["label_id"] == int(p.argmax())
+                assert abs(res[name]["prob"] - float(p.max())) < 0.03
+        assert res["gender"]["label"] in ("female", "male")
+    res2 = m.classify_audio(x, -1, -1, -1)
+    assert abs(res2["emotion"]["prob"] - m.classify_audio(x, -1, -1, -1)["emotion"]["prob"]) < 1e-6   # deterministic
+    with pytest.raises(ValueError):
+        m.endless_decode(x)
+
+
+def test_long_recording_chunk_range_shards_equal_unsharded(asr):
+    """contiguous chunk ranges with recomputed halos, each run as a stand-alone utterance, reproduce the
+    one-shot result (ranks emulated one after another on one GPU)."""
+    c, l, r = 16, 32, 16
+    T = 9000
+    x = synth_fbank(T, seed=80)
+    enc = asr.encoder
+
+    def encode(frames):
+        out, el, *_ = enc.forward_parallel_chunk([frames], torch.tensor([frames.shape[0]], dtype=torch.int32), c, l, r,
+                                                 offset=torch.zeros(1, dtype=torch.int32))
+        return out.reshape(-1, GEO.d_model)[: int(el[0])]
+    full = encode(x)
+    parts = []
+    for sh in split_recording(T, c, l, r, GEO.layers, 4, "exact"):
+        parts.append(encode(x[sh.in_start:sh.in_end])[sh.keep_lo:sh.keep_hi])
+    sharded = torch.cat(parts, 0)
+    assert sharded.shape == full.shape
+    assert (sharded - full).abs().max().item() < 0.03
