@@ -249,8 +249,12 @@ extern "C" int cf_finalize_weights(cf_handle* h) {
         // (attention.py:486-488) are folded into the two Q biases.
         std::vector<float> W(wq); W.insert(W.end(), wq.begin(), wq.end());
         W.insert(W.end(), wk.begin(), wk.end()); W.insert(W.end(), wv.begin(), wv.end());
+        // The two Q blocks also absorb the softmax scale in the log2 domain, (1/sqrt(d_k)) * log2(e) (attention.py:503),
+        // so the attention kernel adds S_ac + S_bd and feeds exp2 directly.
+        const float qs = (1.0f / sqrtf(float(d / h->cfg.heads))) * 1.4426950408889634f;
+        for (size_t e = 0; e < size_t(2) * d * d; ++e) W[e] *= qs;
         std::vector<float> B(size_t(4) * d);
-        for (int c = 0; c < d; ++c) { B[c] = bq[c] + bu[c]; B[d + c] = bq[c] + bvv[c]; B[2 * d + c] = bk[c]; B[3 * d + c] = bv[c]; }
+        for (int c = 0; c < d; ++c) { B[c] = (bq[c] + bu[c]) * qs; B[d + c] = (bq[c] + bvv[c]) * qs; B[2 * d + c] = bk[c]; B[3 * d + c] = bv[c]; }
         ab.b16(W, &w.qkv_w); ab.f32(B, &w.qkv_b);
       }
     }
@@ -668,7 +672,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     }
     { AttnParams a{};
       a.qkv = w.qkv; a.pos = pos->dev + size_t(i) * pos->Rpad * d; a.range = w.att_range; a.ctx = w.ctx;
-      a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk));
+      a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk)); a.prescaled = 1;
       CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
     { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
@@ -798,11 +802,12 @@ extern "C" int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16,
 }
 
 extern "C" int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_bf16, const int32_t* range, void* ctx_bf16,
-                               int n_chunks, int c, int l, int r, int d, int heads, void* stream) {
+                               int n_chunks, int c, int l, int r, int d, int heads, int prescaled, void* stream) {
   AttnParams a{};
   a.qkv = static_cast<const bf16*>(qkv_bf16); a.pos = static_cast<const bf16*>(pos_bf16);
   a.range = reinterpret_cast<const int2*>(range); a.ctx = static_cast<bf16*>(ctx_bf16);
   a.n_chunks = n_chunks; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = heads; a.scale = 1.0f / sqrtf(float(d / heads));
+  a.prescaled = prescaled;
   std::string err;
   if (!run_attention(impl, a, static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
   return CF_OK;

@@ -16,6 +16,7 @@ struct AttnParams {
   __nv_bfloat16* ctx;         // [frames, d]
   int n_chunks, c, l, r, d, heads;
   float scale;                // 1/sqrt(d_k)
+  int prescaled;              // Q+u / Q+v already carry scale * log2(e) (folded into the QKV projection weights)
 };
 
 template <int DK>
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(AttnParams p) {
   float* s_s = s_q + 2 * DK;
   const int chunk = blockIdx.x, h = blockIdx.y;
   const int2 rg = p.range[chunk];
+  const float k_log2 = p.prescaled ? 1.0f : p.scale * 1.4426950408889634f;   // scores live in the log2 domain
   const long long ld = 4LL * p.d;
   const __nv_bfloat16* kbase = p.qkv + (long long)chunk * p.c * ld + 2 * p.d + h * DK;
   const __nv_bfloat16* vbase = kbase + p.d;
@@ -53,14 +55,14 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(AttnParams p) {
         acc += qv[0] * bf16_lo(pv.x) + qv[1] * bf16_hi(pv.x) + qv[2] * bf16_lo(pv.y) + qv[3] * bf16_hi(pv.y) +
                qv[4] * bf16_lo(pv.z) + qv[5] * bf16_hi(pv.z) + qv[6] * bf16_lo(pv.w) + qv[7] * bf16_hi(pv.w);
       }
-      acc *= p.scale;
+      acc *= k_log2;
       s_s[q] = acc;
       mx = fmaxf(mx, acc);
     }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int q = rg.x + lane; q < rg.y; q += 32) {
-      const float e = __expf(s_s[q] - mx);
+      const float e = exp2f(s_s[q] - mx);
       s_s[q] = e;
       sum += e;
     }

@@ -15,8 +15,11 @@
 //
 //   warp 0 : TMA producer (Q tiles per item, K/V blocks in a 2-stage ring, the head's position table once)
 //   warp 1 : TMEM allocator + single-thread MMA issuer (S of block j+1 is issued before waiting for P of block j)
-//   warps 2..5 : softmax / correction / output (thread = query row)
+//   warps 2..9 : softmax / correction / output; two threads share a query row (64 of each block's 128 keys each),
+//                exchanging row maxima / sums through shared memory; fp16 staging of the pre-scaled S_bd values
 #pragma once
+#include <cuda_fp16.h>
+
 #include <string>
 
 #include "attention_simt.cuh"
@@ -26,17 +29,22 @@ namespace cf {
 
 constexpr bool kAttentionTcReady = true;
 
-constexpr int ATC_THREADS = 192;
-constexpr int ATC_SKEW_PITCH = 66;   // floats per thread row; 8-byte stores and 4-byte skewed loads are conflict free
-constexpr uint32_t ATC_PTAB_BYTES = 512 * 128;
+constexpr int ATC_THREADS = 320;                 // TMA warp, MMA warp, 8 softmax warps
+constexpr int ATC_STAGE_PITCH = 144;             // bytes per thread-private skew row (64 fp16 + pad; 16-byte stores conflict free)
+constexpr uint32_t ATC_PTAB_ROWS = 448;          // table rows -64 .. 383 of the head
+constexpr uint32_t ATC_PTAB_BYTES = ATC_PTAB_ROWS * 128;
 constexpr uint32_t ATC_TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16
 constexpr size_t ATC_SMEM_BYTES = ATC_PTAB_BYTES + 2 * ATC_TILE_BYTES /*Qu,Qv*/ + 4 * ATC_TILE_BYTES /*K,V x2*/ +
-                                  2 * ATC_TILE_BYTES /*P probs*/ + 128 * ATC_SKEW_PITCH * 4 + 1024 + 128;
+                                  2 * ATC_TILE_BYTES /*P probs*/ + 256 * ATC_STAGE_PITCH + 2048 + 1024 + 1024 + 128;
 
 CF_DEVINL float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+CF_DEVINL uint32_t pack_half2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 struct AttnTcParams {
@@ -47,18 +55,22 @@ struct AttnTcParams {
   float scale_log2e;
 };
 
+// PRE: Q+u / Q+v already carry (1/sqrt(d_k)) * log2(e) (folded into the fused QKV projection at weight load).
+template <bool PRE>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_pos, AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_ptab = smem;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
+  uint8_t* s_ptab = smem;                        // smem row rr <-> table row rr - 64
   uint8_t* s_qu = s_ptab + ATC_PTAB_BYTES;
   uint8_t* s_qv = s_qu + ATC_TILE_BYTES;
   uint8_t* s_k = s_qv + ATC_TILE_BYTES;          // [2]
   uint8_t* s_v = s_k + 2 * ATC_TILE_BYTES;       // [2]
   uint8_t* s_pp = s_v + 2 * ATC_TILE_BYTES;      // 2 atoms of 64 keys
-  float* s_skew = reinterpret_cast<float*>(s_pp + 2 * ATC_TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_skew + 128 * ATC_SKEW_PITCH);
+  uint8_t* s_stage = s_pp + 2 * ATC_TILE_BYTES;  // 256 thread-private rows
+  float* s_xch = reinterpret_cast<float*>(s_stage + 256 * ATC_STAGE_PITCH);   // [2 parity][2 set][128] row maxima
+  float* s_lx = s_xch + 512;                                                   // [2 set][128] row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lx + 256);
   uint64_t* ptab_full = bars + 0;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = bars + 2;
@@ -84,8 +96,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -100,8 +112,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_arrive_expect_tx(ptab_full, ATC_PTAB_BYTES);
-      tma_load_2d(s_ptab, &tma_pos, ptab_full, h * 64, -64);                   // rows -64..191 (negative rows read as 0)
-      tma_load_2d(s_ptab + 256 * 128, &tma_pos, ptab_full, h * 64, 192);       // rows 192..447
+      for (int i = 0; i < 7; ++i)                                              // table rows -64 .. 383 (rows < 0 read as 0)
+        tma_load_2d(s_ptab + i * 64 * 128, &tma_pos, ptab_full, h * 64, -64 + 64 * i);
       uint32_t item = 0, blk = 0;
       for (int pair = first_pair; pair < p.n_pairs; pair += p.items_per_cta_stride, ++item) {
         const int g0 = 2 * pair;
@@ -123,6 +135,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     if (lane == 0) {
       constexpr uint32_t idesc_ac = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_bd = make_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_bd_last = make_idesc_bf16(128, 192);   // the last block never needs table rows >= 384
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
       mbar_wait(ptab_full, 0);
       uint32_t item = 0, blk = 0;
@@ -154,8 +167,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
           const uint64_t dp = make_sw128_desc(smem_u32(s_ptab + b * 128 * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + TM_AC, dqu + 2 * k, dk + 2 * k, idesc_ac, k != 0);
+          const uint32_t idbd = (b == nb - 1) ? idesc_bd_last : idesc_bd;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + TM_BD, dqv + 2 * k, dp + 2 * k, idesc_bd, k != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + TM_BD, dqv + 2 * k, dp + 2 * k, idbd, k != 0);
           umma_commit(s_full);
           if (b == nb - 1) umma_commit(q_empty);       // Q tiles may be overwritten once these MMAs retire
           if (have_prev) issue_pv(blk - 1, prev_st, prev_b);
@@ -165,15 +179,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       if (have_prev) issue_pv(blk - 1, prev_st, prev_b);
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps: thread = query row
-    const int quad = warp & 3;
-    const int rho = quad * 32 + lane;                  // row of the 128-row tile
+    // ------------------------------------------------------------------ softmax warps
+    // thread = (query row rho, key half `set` of every 128-key block); two threads share a row
+    const int sw = warp - 2;
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int set = sw >> 2;
+    const int rho = quad * 32 + lane;
     const int half = rho >> 6, qi = rho & 63;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    float* skew = s_skew + (warp - 2) * 32 * ATC_SKEW_PITCH + lane * ATC_SKEW_PITCH;
-    // careful: TMEM quadrant is warp % 4, the skew row just needs to be private to the thread
-    const int cb_warp = 96 - 32 * quad;                // warp-uniform part of the skew offset
-    uint8_t* pp_row = s_pp + rho * 128;
+    uint8_t* stage = s_stage + (threadIdx.x - 64) * ATC_STAGE_PITCH;
+    const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
+    const int cb_thread = 96 - 32 * quad + 64 * set;   // first S_bd column this warp stages (warp-uniform)
+    uint8_t* pp_row = s_pp + set * ATC_TILE_BYTES + rho * 128;
     uint32_t blk = 0;
     for (int pair = first_pair; pair < p.n_pairs; pair += p.items_per_cta_stride) {
       const int g = 2 * pair + half;
@@ -183,42 +200,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       for (int b = 0; b < nb; ++b, ++blk) {
         mbar_wait(s_full, blk & 1);
         tc_fence_after();
-        float s[128];
+        float s[64];
         float mx = -1e30f;
 #pragma unroll
-        for (int sb = 0; sb < 4; ++sb) {
-          uint32_t r[32];
-          const uint32_t cbase = TM_BD + cb_warp + 32 * sb;
-          tmem_ld32(tmem_base + lane_addr + cbase, r);
-          tmem_ld_wait();
+        for (int sb = 0; sb < 2; ++sb) {
+          uint32_t r0[32];
+          const uint32_t cbase = TM_BD + cb_thread + 32 * sb;
+          const float sc = PRE ? 1.0f : p.scale_log2e;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(skew + j) = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-          tmem_ld32(tmem_base + lane_addr + cbase + 32, r);
-          tmem_ld_wait();
+          for (int hh = 0; hh < 2; ++hh) {             // stage 64 S_bd columns as fp16 (two 32-column TMEM loads)
+            tmem_ld32(tmem_base + lane_addr + cbase + 32 * hh, r0);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) *reinterpret_cast<float2*>(skew + 32 + j) = make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-          tmem_ld32(tmem_base + lane_addr + TM_AC + 32 * sb, r);
+            for (int q = 0; q < 4; ++q) {
+              uint4 w0;
+              w0.x = pack_half2(__uint_as_float(r0[8 * q]) * sc, __uint_as_float(r0[8 * q + 1]) * sc);
+              w0.y = pack_half2(__uint_as_float(r0[8 * q + 2]) * sc, __uint_as_float(r0[8 * q + 3]) * sc);
+              w0.z = pack_half2(__uint_as_float(r0[8 * q + 4]) * sc, __uint_as_float(r0[8 * q + 5]) * sc);
+              w0.w = pack_half2(__uint_as_float(r0[8 * q + 6]) * sc, __uint_as_float(r0[8 * q + 7]) * sc);
+              *reinterpret_cast<uint4*>(stage + 64 * hh + 16 * q) = w0;
+            }
+          }
+          tmem_ld32(tmem_base + lane_addr + TM_AC + 64 * set + 32 * sb, r0);
           tmem_ld_wait();
-          const float* bd = skew + (31 - lane);
-          const int u0 = 128 * b + 32 * sb;
+          const int u0 = 128 * b + 64 * set + 32 * sb;
+          const bool edge = (u0 < ulo) || (u0 + 32 > uhi);
+          if (__any_sync(0xffffffffu, edge)) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const int uq = u0 + k;
-            float v = (__uint_as_float(r[k]) + bd[k]) * p.scale_log2e;
-            v = (uq >= ulo && uq < uhi) ? v : -INFINITY;
-            s[32 * sb + k] = v;
-            mx = fmaxf(mx, v);
+            for (int k = 0; k < 32; ++k) {
+              const int uq = u0 + k;
+              float v = PRE ? __uint_as_float(r0[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(r0[k]), p.scale_log2e, __half2float(stage_rd[k]));
+              v = (uq >= ulo && uq < uhi) ? v : -INFINITY;
+              s[32 * sb + k] = v;
+              mx = fmaxf(mx, v);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float v = PRE ? __uint_as_float(r0[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(r0[k]), p.scale_log2e, __half2float(stage_rd[k]));
+              s[32 * sb + k] = v;
+              mx = fmaxf(mx, v);
+            }
           }
         }
         tc_fence_before();
-        mbar_arrive(s_free);                           // S block is in registers: TMEM S region may be overwritten
-        const float m_new = fmaxf(m_run, mx);
+        mbar_arrive(s_free);                           // this thread's part of S is in registers
+        float* xch = s_xch + (blk & 1) * 256;
+        xch[set * 128 + rho] = mx;
+        named_bar_sync(1, 256);
+        const float m_new = fmaxf(m_run, fmaxf(mx, xch[(set ^ 1) * 128 + rho]));
         const float alpha = fast_exp2(m_run - m_new);
         float sum = 0.f;
         if (blk > 0) mbar_wait(pv_done, (blk - 1) & 1);   // previous P V retired: P tile and O are ours again
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {                 // 16 x (8 keys -> 16 bytes) into the swizzled K-major A tile
+        for (int j = 0; j < 8; ++j) {                  // 8 x (8 keys -> 16 bytes) into this set's 64-key K-major atom
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -226,36 +262,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             sum += p0 + p1;
             w[e] = pack_bf16(p0, p1);
           }
-          const int atom = j >> 3, slot = j & 7;
-          *reinterpret_cast<uint4*>(pp_row + atom * ATC_TILE_BYTES + ((slot ^ (rho & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(pp_row + ((j ^ (rho & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         l_run = l_run * alpha + sum;
         m_run = m_new;
-        if (b > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale the running output (warp-uniform branch)
+        if (b > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale this set's half of the running output
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_addr + TM_O + 32 * set, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + lane_addr + TM_O + 32 * cc, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-            tmem_st32(tmem_base + lane_addr + TM_O + 32 * cc, r);
-          }
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+          tmem_st32(tmem_base + lane_addr + TM_O + 32 * set, r);
           tmem_st_wait();
         }
         tc_fence_before();
         fence_proxy_async();                           // P tile (generic-proxy stores) -> visible to the MMA (async proxy)
         mbar_arrive(p_full);
       }
-      // ---- item epilogue: O / l -> ctx
+      // ---- item epilogue: O / l -> ctx (this set writes 32 of the head's 64 output columns)
+      s_lx[set * 128 + rho] = l_run;
+      named_bar_sync(1, 256);
+      const float l_tot = l_run + s_lx[(set ^ 1) * 128 + rho];
       mbar_wait(pv_done, (blk - 1) & 1);
       tc_fence_after();
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;        // no valid key: zero context (attention.py:133-136)
-      __nv_bfloat16* orow = p.ctx + ((long long)g * 64 + qi) * d + h * 64;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;        // no valid key: zero context (attention.py:133-136)
+      __nv_bfloat16* orow = p.ctx + ((long long)g * 64 + qi) * d + h * 64 + 32 * set;
+      {
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_addr + TM_O + 32 * cc, r);
+        tmem_ld32(tmem_base + lane_addr + TM_O + 32 * set, r);
         tmem_ld_wait();
         if (g < p.n_chunks) {
 #pragma unroll
@@ -265,7 +299,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             o.y = pack_bf16(__uint_as_float(r[8 * q + 2]) * inv, __uint_as_float(r[8 * q + 3]) * inv);
             o.z = pack_bf16(__uint_as_float(r[8 * q + 4]) * inv, __uint_as_float(r[8 * q + 5]) * inv);
             o.w = pack_bf16(__uint_as_float(r[8 * q + 6]) * inv, __uint_as_float(r[8 * q + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + 32 * cc + 8 * q) = o;
+            *reinterpret_cast<uint4*>(orow + 8 * q) = o;
           }
         }
       }
@@ -293,18 +327,20 @@ inline bool launch_attention_tc(const AttnParams& a, cudaStream_t st, std::strin
   if (per_head < 1) per_head = 1;
   if (per_head > p.n_pairs) per_head = p.n_pairs;
   p.items_per_cta_stride = per_head;
-  // tensor maps: flat QKV buffer [rows, 4d] (box 128 rows x 64 cols) and this layer's position table [Rpad, d] (box 256 x 64)
+  // tensor maps: flat QKV buffer [rows, 4d] (box 128 rows x 64 cols) and this layer's position table [Rpad, d] (box 64 x 64)
   const uint64_t qkv_rows = uint64_t(a.l) + uint64_t(a.n_chunks) * 64 + uint64_t(a.r) + 2 * 64 + 128;
   CUtensorMap tq, tp;
   if (!make_tma_2d_bf16(&tq, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 128, 64, err)) return false;
-  if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 256, 64, err)) return false;
+  if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 64, 64, err)) return false;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC_SMEM_BYTES));
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC_SMEM_BYTES));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC_SMEM_BYTES));
     if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(attention_tc): ") + cudaGetErrorString(e); return false; }
     attr_set = true;
   }
-  attention_tc_kernel<<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
+  if (a.prescaled) attention_tc_kernel<true><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
+  else attention_tc_kernel<false><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("attention_tc launch: ") + cudaGetErrorString(e); return false; }

@@ -55,6 +55,7 @@ CF_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 CF_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"

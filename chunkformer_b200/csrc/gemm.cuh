@@ -84,8 +84,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // align with pointer arithmetic (not an integer round trip) so the compiler keeps the shared address space (STS, not ST.E)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + GEMM_STAGES * A_BYTES;
   uint8_t* sStage = sB + GEMM_STAGES * B_BYTES;

@@ -48,7 +48,7 @@ SIGNATURES = {
     "cf_op_dwconv": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                              c_int, c_void_p]),
     "cf_op_attention": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_void_p]),
+                                c_int, c_void_p]),
 }
 
 _LIB = None

@@ -132,9 +132,10 @@ CF_API int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, voi
                     const float* w2, const float* b2, int64_t rows, void* stream);
 CF_API int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16, const float* w, const float* bias,
                  const float* ln_w, const float* ln_b, const int32_t* range, int c, int n_chunks, void* stream);
-/* impl 0 = generic CUDA-core kernel, 1 = tcgen05 kernel (c=64, d_k=64, l+c+r <= 320 multiple of 64). */
+/* impl 0 = generic CUDA-core kernel, 1 = tcgen05 kernel (c=64, d_k=64, l+c+r <= 320 multiple of 64).
+ * prescaled != 0: the Q+u / Q+v columns already carry (1/sqrt(d_k)) * log2(e), as cf_encode's fused projection writes them. */
 CF_API int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_bf16, const int32_t* range, void* ctx_bf16,
-                    int n_chunks, int c, int l, int r, int d, int heads, void* stream);
+                    int n_chunks, int c, int l, int r, int d, int heads, int prescaled, void* stream);
 
 #ifdef __cplusplus
 }

@@ -209,7 +209,7 @@ def _attention_reference(qkv, pos, rng, n, c, l, r, d, H):
     return out
 
 
-def _attention_case(impl, c, l, r, d, H, n, seed=0):
+def _attention_case(impl, c, l, r, d, H, n, seed=0, prescaled=0):
     L = cflib.load()
     W = l + c + r
     R = 2 * c + l + r - 1
@@ -235,9 +235,17 @@ def _attention_case(impl, c, l, r, d, H, n, seed=0):
         rng_np[5] = (0, 0)          # chunk with no valid key: zero context, not NaN
     rng = torch.from_numpy(rng_np).to(DEV)
     ctx = torch.full((n * c, d), 9.0, device=DEV, dtype=torch.bfloat16)
-    cflib.check(L.cf_op_attention(impl, _p(qkv), _p(pos), _p(rng), _p(ctx), n, c, l, r, d, H, _stream()), None, "attention")
+    qkv_ref = qkv
+    if prescaled:
+        # the product path stores (Q+u), (Q+v) multiplied by (1/sqrt(d_k)) * log2(e); undo it for the reference
+        alpha = (1.0 / math.sqrt(d // H)) * 1.4426950408889634
+        qkv = qkv.clone()
+        qkv[:, : 2 * d] = (qkv[:, : 2 * d].float() * alpha).bfloat16()
+        qkv_ref = qkv.float()
+        qkv_ref[:, : 2 * d] /= alpha
+    cflib.check(L.cf_op_attention(impl, _p(qkv), _p(pos), _p(rng), _p(ctx), n, c, l, r, d, H, prescaled, _stream()), None, "attention")
     torch.cuda.synchronize()
-    ref = _attention_reference(qkv, pos, rng_np, n, c, l, r, d, H)
+    ref = _attention_reference(qkv_ref, pos, rng_np, n, c, l, r, d, H)
     assert torch.isfinite(ctx.float()).all()
     err = (ctx.float() - ref).abs().max().item()
     assert err < 4e-2, err
@@ -245,14 +253,16 @@ def _attention_case(impl, c, l, r, d, H, n, seed=0):
 
 @pytest.mark.parametrize("c,l,r,d,H,n", [(64, 128, 128, 512, 8, 7), (16, 64, 0, 256, 4, 9), (8, 16, 16, 256, 2, 6),
                                          (64, 64, 64, 512, 4, 4)])
-def test_attention_generic(c, l, r, d, H, n):
-    _attention_case(0, c, l, r, d, H, n)
+@pytest.mark.parametrize("prescaled", [0, 1])
+def test_attention_generic(c, l, r, d, H, n, prescaled):
+    _attention_case(0, c, l, r, d, H, n, prescaled=prescaled)
 
 
 @pytest.mark.parametrize("l,r,n", [(128, 128, 7), (128, 128, 12), (64, 64, 5), (128, 0, 6), (0, 0, 3), (192, 64, 9)])
-def test_attention_tcgen05(l, r, n):
+@pytest.mark.parametrize("prescaled", [0, 1])
+def test_attention_tcgen05(l, r, n, prescaled):
     """Chunk-pair tcgen05 kernel (c=64, d_k=64), odd and even chunk counts, several window shapes."""
-    _attention_case(1, 64, l, r, 512, 8, n, seed=3)
+    _attention_case(1, 64, l, r, 512, 8, n, seed=3, prescaled=prescaled)
 
 
 def test_attention_tcgen05_matches_generic_large():
@@ -271,7 +281,7 @@ def test_attention_tcgen05_matches_generic_large():
     rng = rng.to(DEV)
     a = torch.zeros((n * c, d), device=DEV, dtype=torch.bfloat16)
     b = torch.zeros((n * c, d), device=DEV, dtype=torch.bfloat16)
-    cflib.check(L.cf_op_attention(0, _p(qkv), _p(pos), _p(rng), _p(a), n, c, l, r, d, H, _stream()))
-    cflib.check(L.cf_op_attention(1, _p(qkv), _p(pos), _p(rng), _p(b), n, c, l, r, d, H, _stream()))
+    cflib.check(L.cf_op_attention(0, _p(qkv), _p(pos), _p(rng), _p(a), n, c, l, r, d, H, 0, _stream()))
+    cflib.check(L.cf_op_attention(1, _p(qkv), _p(pos), _p(rng), _p(b), n, c, l, r, d, H, 0, _stream()))
     torch.cuda.synchronize()
     assert (a.float() - b.float()).abs().max().item() < 4e-2
