@@ -409,6 +409,40 @@ bool run_dwconv(int d, int kernel, const DwConvParams& p, cudaStream_t st, std::
   return false;
 }
 
+bool run_frontend_conv(int impl, int d, const Fe1Params& f1, int num_sms, cudaStream_t st, std::string* err) {
+  if (f1.n_chunks == 0) return true;
+  if (f1.feat_dim > 80 || f1.F2 < 16) { *err = "frontend: feat_dim must be <= 80 with at least 16 bins after two convs"; return false; }
+  const int per_chunk = f1.T2 * f1.F2;
+  const int bpc = (per_chunk + 127) / 128;
+  cudaError_t e = cudaSuccess;
+  if (impl == 0) {
+    const size_t smem = (size_t(d) * 20 + size_t(39) * f1.feat_dim) * sizeof(float) + 128 * 33 * sizeof(uint32_t);
+    if (d == 512) {
+      e = cudaFuncSetAttribute(frontend_conv0_dw1_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) frontend_conv0_dw1_kernel<512><<<f1.n_chunks * bpc, 128, smem, st>>>(f1);
+    } else if (d == 256) {
+      e = cudaFuncSetAttribute(frontend_conv0_dw1_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) frontend_conv0_dw1_kernel<256><<<f1.n_chunks * bpc, 128, smem, st>>>(f1);
+    } else { *err = "frontend: d must be 256 or 512"; return false; }
+  } else {
+    const int tiles = f1.n_chunks * bpc;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    if (d == 512) {
+      const size_t smem = frontend_tc_smem_bytes<512>();
+      e = cudaFuncSetAttribute(frontend_conv0_dw1_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) frontend_conv0_dw1_tc_kernel<512><<<grid, FETC_THREADS, smem, st>>>(f1, tiles);
+    } else if (d == 256) {
+      const size_t smem = frontend_tc_smem_bytes<256>();
+      e = cudaFuncSetAttribute(frontend_conv0_dw1_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) frontend_conv0_dw1_tc_kernel<256><<<grid, FETC_THREADS, smem, st>>>(f1, tiles);
+    } else { *err = "frontend: d must be 256 or 512"; return false; }
+  }
+  ++cf::g_kernel_launches;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("frontend conv launch: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+
 bool attention_tc_supported(int c, int l, int r, int dk) {
   return c == 64 && dk == 64 && (l % 64) == 0 && (r % 64) == 0 && (l + r) <= 256;
 }
@@ -607,20 +641,13 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   // ---- front-end: slabs of chunks through conv0+dw1 -> pw1 -> dw2 -> pw2 -> out Linear
   {
     const int T2 = 2 * c + 1, F1 = (h->cfg.feat_dim - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1, F3 = h->F3;
-    const size_t fe_smem = (size_t(d) * 20 + size_t(39) * h->cfg.feat_dim) * sizeof(float) + 128 * 33 * sizeof(uint32_t);
-    if (d == 512) CF_CUDA(h, cudaFuncSetAttribute(frontend_conv0_dw1_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fe_smem)));
-    else CF_CUDA(h, cudaFuncSetAttribute(frontend_conv0_dw1_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fe_smem)));
     if (F2 < 16) return fail(h, CF_ERR_INVALID, "cf_encode: feat_dim too small for the front-end tiling");
     for (int g0 = 0; g0 < n; g0 += FE_SLAB_CHUNKS) {
       const int S = std::min(FE_SLAB_CHUNKS, n - g0);
       Fe1Params f1{};
       f1.feats = feats; f1.chunks = w.chunk_src + g0; f1.wpack = h->fe_wpack; f1.cmvn_mean = h->cmvn_mean; f1.cmvn_istd = h->cmvn_istd;
       f1.out = w.a1; f1.n_chunks = S; f1.feat_dim = h->cfg.feat_dim; f1.T2 = T2; f1.F2 = F2; f1.in_rows = p->in_rows;
-      const int bpc = (T2 * F2 + 127) / 128;
-      if (d == 512) frontend_conv0_dw1_kernel<512><<<S * bpc, 128, fe_smem, st>>>(f1);
-      else frontend_conv0_dw1_kernel<256><<<S * bpc, 128, fe_smem, st>>>(f1);
-      ++cf::g_kernel_launches;
-      CF_CUDA(h, cudaGetLastError());
+      if (!run_frontend_conv(1, d, f1, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err);
       EpiArgs e1; e1.bias = h->fe_b3; e1.out = w.b1; e1.ldo = d; e1.act = ACT_RELU;
       CF_TRY(gemm(w.a1, d, h->fe_w3, d, (long long)S * T2 * F2, d, d, EPI_BF16, e1));
       Fe2Params f2{};
@@ -810,5 +837,28 @@ extern "C" int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_b
   a.prescaled = prescaled;
   std::string err;
   if (!run_attention(impl, a, static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  return CF_OK;
+}
+
+extern "C" int cf_op_frontend_conv(int impl, int d, const float* feats, const int64_t* chunk_feat_row, const int32_t* chunk_in_len,
+                                   int n_chunks, int chunk_size, int feat_dim, const float* wpack, const float* cmvn_mean,
+                                   const float* cmvn_istd, void* out_bf16, void* stream) {
+  if (!feats || !chunk_feat_row || !chunk_in_len || !wpack || !out_bf16) return fail(nullptr, CF_ERR_INVALID, "cf_op_frontend_conv: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<ChunkSrc> cs(n_chunks);
+  for (int g = 0; g < n_chunks; ++g) { cs[g].feat_row = chunk_feat_row[g]; cs[g].in_len = chunk_in_len[g]; cs[g].pad_ = 0; }
+  ChunkSrc* dev = nullptr;
+  CF_CUDA(nullptr, cudaMalloc(&dev, sizeof(ChunkSrc) * size_t(n_chunks)));
+  CF_CUDA(nullptr, cudaMemcpyAsync(dev, cs.data(), sizeof(ChunkSrc) * size_t(n_chunks), cudaMemcpyHostToDevice, st));
+  Fe1Params f1{};
+  const int F1 = (feat_dim - 3) / 2 + 1;
+  f1.feats = feats; f1.chunks = dev; f1.wpack = wpack; f1.cmvn_mean = cmvn_mean; f1.cmvn_istd = cmvn_istd;
+  f1.out = static_cast<bf16*>(out_bf16); f1.n_chunks = n_chunks; f1.feat_dim = feat_dim; f1.T2 = 2 * chunk_size + 1;
+  f1.F2 = (F1 - 3) / 2 + 1; f1.in_rows = 8 * (chunk_size - 1) + 15;
+  std::string err;
+  const bool ok = run_frontend_conv(impl, d, f1, current_sms(), st, &err);
+  cudaStreamSynchronize(st);
+  cudaFree(dev);
+  if (!ok) return fail(nullptr, CF_ERR_CUDA, err);
   return CF_OK;
 }

@@ -47,6 +47,8 @@ SIGNATURES = {
                                 c_int64, c_void_p]),
     "cf_op_dwconv": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                              c_int, c_void_p]),
+    "cf_op_frontend_conv": (c_int, [c_int, c_int, c_void_p, POINTER(c_int64), POINTER(c_int32), c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_op_attention": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p]),
 }

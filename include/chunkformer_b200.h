@@ -137,6 +137,13 @@ CF_API int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16, con
 CF_API int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_bf16, const int32_t* range, void* ctx_bf16,
                     int n_chunks, int c, int l, int r, int d, int heads, int prescaled, void* stream);
 
+/* conv0 + ReLU + depthwise conv1 of the subsampling front-end (subsampling.py:70-92) for n_chunks chunks read from the flat
+ * feature buffer; impl 0 = CUDA-core kernel, 1 = tcgen05 kernel. wpack: device fp32 [d][20] = {w0[9], b0, w1[9], b1};
+ * chunk_feat_row / chunk_in_len: host arrays; out: device bf16 [n_chunks * (2c+1) * F2, d]. Synchronises the stream. */
+CF_API int cf_op_frontend_conv(int impl, int d, const float* feats, const int64_t* chunk_feat_row, const int32_t* chunk_in_len,
+                        int n_chunks, int chunk_size, int feat_dim, const float* wpack, const float* cmvn_mean,
+                        const float* cmvn_istd, void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,3 +285,44 @@ def test_attention_tcgen05_matches_generic_large():
     cflib.check(L.cf_op_attention(1, _p(qkv), _p(pos), _p(rng), _p(b), n, c, l, r, d, H, 0, _stream()))
     torch.cuda.synchronize()
     assert (a.float() - b.float()).abs().max().item() < 4e-2
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("d,c,cmvn", [(512, 64, False), (256, 16, True), (512, 8, True)])
+def test_frontend_conv0_dw1(impl, d, c, cmvn):
+    """conv0 + ReLU + depthwise conv1 (subsampling.py:70-92) on ragged chunks, CUDA-core and tcgen05 versions."""
+    import ctypes
+    from ctypes import POINTER, c_int32, c_int64
+    L = cflib.load()
+    size = 8 * (c - 1) + 15
+    in_lens = [size, size, size - 37, 5, size]              # chunks 2 and 3 are zero padded at the end
+    n = len(in_lens)
+    feats = _rand((n * size + 11, 80), 1.0, 1)
+    rows = np.array([k * size + (3 if k else 0) for k in range(n)], dtype=np.int64)
+    w0, b0 = _rand((d, 1, 3, 3), 0.3, 2), _rand((d,), 0.3, 3)
+    w1, b1 = _rand((d, 1, 3, 3), 0.3, 4), _rand((d,), 0.3, 5)
+    wpack = torch.cat([w0.view(d, 9), b0.view(d, 1), w1.view(d, 9), b1.view(d, 1)], 1).contiguous()
+    mean = _rand((80,), 0.5, 6) if cmvn else None
+    istd = (1.0 / (1.0 + 0.2 * torch.rand(80, device=DEV))) if cmvn else None
+    T2, F2 = 2 * c + 1, 19
+    out = torch.zeros((n * T2 * F2, d), device=DEV, dtype=torch.bfloat16)
+    lens_a = np.array(in_lens, dtype=np.int32)
+    cflib.check(L.cf_op_frontend_conv(impl, d, _p(feats), rows.ctypes.data_as(POINTER(c_int64)),
+                                      lens_a.ctypes.data_as(POINTER(c_int32)), n, c, 80, _p(wpack), _p(mean), _p(istd),
+                                      _p(out), _stream()), None, "frontend")
+    torch.cuda.synchronize()
+    x = torch.zeros((n, size, 80), device=DEV)
+    for k in range(n):
+        m = min(in_lens[k], size)
+        x[k, :m] = feats[rows[k]: rows[k] + m]
+    if cmvn:
+        x = (x - mean) * istd
+    if impl == 1:
+        x = x.bfloat16().float()       # the tensor-core version rounds inputs and conv0 weights to bf16
+        w0, b0 = w0.bfloat16().float(), b0.bfloat16().float()
+    y = torch.relu(torch.nn.functional.conv2d(x.unsqueeze(1), w0, b0, stride=2))
+    y = torch.nn.functional.conv2d(y, w1, b1, stride=2, groups=d)                  # (n, d, T2, F2)
+    ref = y.permute(0, 2, 3, 1).reshape(n * T2 * F2, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 5e-2, err
+    assert (out.float() - ref).abs().mean().item() < 5e-3
