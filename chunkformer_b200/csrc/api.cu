@@ -75,6 +75,7 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
   } while (0)
 
 extern "C" long long cf_launch_count(void) { return cf::g_kernel_launches.load(); }
+extern "C" void cf_set_gemm_variant(int v) { cf::gemm_variant_override() = v; }
 extern "C" const char* cf_version(void) { return "chunkformer_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cf_last_error(const cf_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 

@@ -75,6 +75,145 @@ CF_DEVINL void stage_store16(uint8_t* tile, int row, int slot, uint4 v) {
   *reinterpret_cast<uint4*>(tile + row * 128 + ((slot ^ (row & 7)) << 4)) = v;
 }
 
+// Epilogue of one 128-row x 128-column accumulator slab (one epilogue group): shared by the 1-CTA and 2-CTA kernels.
+//   taddr : TMEM address of the slab's first column for this warp's lane quadrant;  row0 : global row of tile row 0
+//   gcol0 : first global accumulator column of the slab;  stg : the group's 16 KB staging tile
+template <int EPI, int ACT>
+CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0, int n_blk, int grp, int n_tiles, int M, int N,
+                                  uint8_t* stg, int bar_id, bool issuer, const CUtensorMap* tma_c, const GemmEpiParams& ep) {
+  const int row = row0 + trow;
+  const bool row_ok = row < M;
+
+  if (EPI == EPI_ARGMAX) {
+    float best = -INFINITY, second = -INFINITY;
+    int best_idx = 0;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      const int col0 = gcol0 + cc * 32;
+      if (col0 >= N) break;
+      uint32_t r[32];
+      tmem_ld32(taddr + cc * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        if (col < N) {
+          const float v = __uint_as_float(r[j]) + __ldg(ep.bias + col);
+          if (v > best) { second = best; best = v; best_idx = col; }
+          else if (v > second) { second = v; }
+        }
+      }
+    }
+    if (row_ok) {
+      const long long p = (long long)row * (2 * n_tiles) + 2 * n_blk + grp;
+      ep.part_best[p] = best;
+      ep.part_second[p] = second;
+      ep.part_index[p] = best_idx;
+    }
+  } else if (EPI == EPI_F32) {
+    bool keep = true;   // masked rows get exactly +0 added (masked_fill_, convolution.py:253)
+    if (ep.row_range != nullptr && row_ok) {
+      const int ch = row / ep.rows_per_chunk;
+      const int rr = row - ch * ep.rows_per_chunk;
+      const int2 rg = ep.row_range[ch];
+      keep = (rr >= rg.x && rr < rg.y);
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {   // one 32-column fp32 sub-tile (128 B per row) per round
+      const int col0 = gcol0 + cc * 32;
+      if (col0 >= N) break;
+      uint32_t r[32];
+      tmem_ld32(taddr + cc * 32, r);
+      float4 x[8];
+      const bool has_res = ep.resid != nullptr && row_ok;
+      if (has_res) {
+        const float4* rs = reinterpret_cast<const float4*>(ep.resid + (long long)row * ep.ld_resid + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = (col0 + 4 * q < N) ? rs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (issuer) tma_store_wait_read();
+      named_bar_sync(bar_id, 128);       // staging tile free again
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col0 + 4 * q < N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
+        float4 v;
+        v.x = ep.alpha * (__uint_as_float(r[4 * q]) + b.x);
+        v.y = ep.alpha * (__uint_as_float(r[4 * q + 1]) + b.y);
+        v.z = ep.alpha * (__uint_as_float(r[4 * q + 2]) + b.z);
+        v.w = ep.alpha * (__uint_as_float(r[4 * q + 3]) + b.w);
+        if (!keep) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res) { v.x += x[q].x; v.y += x[q].y; v.z += x[q].z; v.w += x[q].w; }
+        stage_store16(stg, trow, q, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+      }
+      fence_proxy_async();
+      named_bar_sync(bar_id, 128);
+      if (issuer) { tma_store_2d(tma_c, stg, col0, row0); tma_store_commit(); }
+    }
+  } else {
+    // bf16 outputs: EPI_BF16 -> two 64-column sub-tiles per group; EPI_GLU -> one 64-column sub-tile (128 acc columns)
+    constexpr int ROUNDS = (EPI == EPI_GLU) ? 1 : 2;
+    constexpr int CH_PER_ROUND = (EPI == EPI_GLU) ? 4 : 2;
+#pragma unroll 1
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int acol0 = gcol0 + rd * 64;       // accumulator column of this round (EPI_BF16)
+      if (acol0 >= N) break;
+      if (issuer) tma_store_wait_read();
+      named_bar_sync(bar_id, 128);
+#pragma unroll
+      for (int cc = 0; cc < CH_PER_ROUND; ++cc) {
+        const int tcol = (EPI == EPI_GLU) ? cc * 32 : rd * 64 + cc * 32;   // column inside the group's 128
+        const int col0 = gcol0 + tcol;
+        uint32_t r[32];
+        tmem_ld32(taddr + tcol, r);
+        float b[32];
+        if (col0 < N) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
+            b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) b[j] = 0.f;
+        }
+        tmem_ld_wait();
+        if (EPI == EPI_GLU) {
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float a0 = __uint_as_float(r[j]) + b[j], g0 = __uint_as_float(r[j + 1]) + b[j + 1];
+            const float a1 = __uint_as_float(r[j + 2]) + b[j + 2], g1 = __uint_as_float(r[j + 3]) + b[j + 3];
+            o[j >> 2] = pack_bf16(a0 * sigmoid_fast(g0), a1 * sigmoid_fast(g1));
+          }
+          stage_store16(stg, trow, 2 * cc, make_uint4(o[0], o[1], o[2], o[3]));
+          stage_store16(stg, trow, 2 * cc + 1, make_uint4(o[4], o[5], o[6], o[7]));
+        } else {
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float v0 = __uint_as_float(r[j]) + b[j], v1 = __uint_as_float(r[j + 1]) + b[j + 1];
+            if (ACT == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (ACT == ACT_SILU) { v0 = silu_fast(v0); v1 = silu_fast(v1); }
+            o[j >> 1] = pack_bf16(v0, v1);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            stage_store16(stg, trow, 4 * cc + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        const int ocol = (EPI == EPI_GLU) ? (gcol0 >> 1) : acol0;
+        tma_store_2d(tma_c, stg, ocol, row0);
+        tma_store_commit();
+      }
+    }
+  }
+}
+
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -181,139 +320,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + trow;
-      const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + grp * 128;
-      const int gcol0 = n_blk * BN + grp * 128;   // first global accumulator column of this group
-
-      if (EPI == EPI_ARGMAX) {
-        float best = -INFINITY, second = -INFINITY;
-        int best_idx = 0;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int col0 = gcol0 + cc * 32;
-          if (col0 >= N) break;
-          uint32_t r[32];
-          tmem_ld32(taddr + cc * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < N) {
-              const float v = __uint_as_float(r[j]) + __ldg(ep.bias + col);
-              if (v > best) { second = best; best = v; best_idx = col; }
-              else if (v > second) { second = v; }
-            }
-          }
-        }
-        if (row_ok) {
-          const long long p = (long long)row * (2 * n_tiles) + 2 * n_blk + grp;
-          ep.part_best[p] = best;
-          ep.part_second[p] = second;
-          ep.part_index[p] = best_idx;
-        }
-      } else if (EPI == EPI_F32) {
-        bool keep = true;   // masked rows get exactly +0 added (masked_fill_, convolution.py:253)
-        if (ep.row_range != nullptr && row_ok) {
-          const int ch = row / ep.rows_per_chunk;
-          const int rr = row - ch * ep.rows_per_chunk;
-          const int2 rg = ep.row_range[ch];
-          keep = (rr >= rg.x && rr < rg.y);
-        }
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {   // one 32-column fp32 sub-tile (128 B per row) per round
-          const int col0 = gcol0 + cc * 32;
-          if (col0 >= N) break;
-          uint32_t r[32];
-          tmem_ld32(taddr + cc * 32, r);
-          float4 x[8];
-          const bool has_res = ep.resid != nullptr && row_ok;
-          if (has_res) {
-            const float4* rs = reinterpret_cast<const float4*>(ep.resid + (long long)row * ep.ld_resid + col0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) x[q] = (col0 + 4 * q < N) ? rs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (issuer) tma_store_wait_read();
-          named_bar_sync(bar_id, 128);       // staging tile free again
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 + 4 * q < N) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
-            float4 v;
-            v.x = ep.alpha * (__uint_as_float(r[4 * q]) + b.x);
-            v.y = ep.alpha * (__uint_as_float(r[4 * q + 1]) + b.y);
-            v.z = ep.alpha * (__uint_as_float(r[4 * q + 2]) + b.z);
-            v.w = ep.alpha * (__uint_as_float(r[4 * q + 3]) + b.w);
-            if (!keep) v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_res) { v.x += x[q].x; v.y += x[q].y; v.z += x[q].z; v.w += x[q].w; }
-            stage_store16(stg, trow, q, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
-          }
-          fence_proxy_async();
-          named_bar_sync(bar_id, 128);
-          if (issuer) { tma_store_2d(&tma_c, stg, col0, m_blk * GEMM_BM); tma_store_commit(); }
-        }
-      } else {
-        // bf16 outputs: EPI_BF16 -> two 64-column sub-tiles per group; EPI_GLU -> one 64-column sub-tile (128 acc columns)
-        constexpr int ROUNDS = (EPI == EPI_GLU) ? 1 : 2;
-        constexpr int CH_PER_ROUND = (EPI == EPI_GLU) ? 4 : 2;
-#pragma unroll 1
-        for (int rd = 0; rd < ROUNDS; ++rd) {
-          const int acol0 = gcol0 + rd * 64;       // accumulator column of this round (EPI_BF16)
-          if (acol0 >= N) break;
-          if (issuer) tma_store_wait_read();
-          named_bar_sync(bar_id, 128);
-#pragma unroll
-          for (int cc = 0; cc < CH_PER_ROUND; ++cc) {
-            const int tcol = (EPI == EPI_GLU) ? cc * 32 : rd * 64 + cc * 32;   // column inside the group's 128
-            const int col0 = gcol0 + tcol;
-            uint32_t r[32];
-            tmem_ld32(taddr + tcol, r);
-            float b[32];
-            if (col0 < N) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
-                b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) b[j] = 0.f;
-            }
-            tmem_ld_wait();
-            if (EPI == EPI_GLU) {
-              uint32_t o[8];
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float a0 = __uint_as_float(r[j]) + b[j], g0 = __uint_as_float(r[j + 1]) + b[j + 1];
-                const float a1 = __uint_as_float(r[j + 2]) + b[j + 2], g1 = __uint_as_float(r[j + 3]) + b[j + 3];
-                o[j >> 2] = pack_bf16(a0 * sigmoid_fast(g0), a1 * sigmoid_fast(g1));
-              }
-              stage_store16(stg, trow, 2 * cc, make_uint4(o[0], o[1], o[2], o[3]));
-              stage_store16(stg, trow, 2 * cc + 1, make_uint4(o[4], o[5], o[6], o[7]));
-            } else {
-              uint32_t o[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float v0 = __uint_as_float(r[j]) + b[j], v1 = __uint_as_float(r[j + 1]) + b[j + 1];
-                if (ACT == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                if (ACT == ACT_SILU) { v0 = silu_fast(v0); v1 = silu_fast(v1); }
-                o[j >> 1] = pack_bf16(v0, v1);
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                stage_store16(stg, trow, 4 * cc + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
-            }
-          }
-          fence_proxy_async();
-          named_bar_sync(bar_id, 128);
-          if (issuer) {
-            const int ocol = (EPI == EPI_GLU) ? (gcol0 >> 1) : acol0;
-            tma_store_2d(&tma_c, stg, ocol, m_blk * GEMM_BM);
-            tma_store_commit();
-          }
-        }
-      }
+      gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * GEMM_BM, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg, bar_id,
+                                   issuer, &tma_c, ep);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -323,6 +332,179 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile with UMMA 256x256x16.  Each CTA
+// loads its own 128 rows of A and 128 of the 256 B rows (so the L2 -> shared traffic per FLOP drops by a third), the
+// leader CTA issues the MMAs for the pair, each CTA keeps the accumulator rows of its own M half in its TMEM and runs the
+// same epilogue on it.  Producer of the peer CTA signals the leader's full barrier (complete_tx on a cluster-mapped
+// address); tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the epilogues of both
+// CTAs arrive on the leader's "accumulator drained" barrier.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GEMM2_STAGES = 6;
+constexpr size_t gemm2_smem_bytes() {
+  return size_t(GEMM2_STAGES) * (GEMM_BM * 128 + 128 * 128) + 2 * GEMM_STAGING_BYTES + 1024 + 256;
+}
+
+CF_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+CF_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+CF_DEVINL uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {   // shared::cta address -> shared::cluster address in `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+CF_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+CF_DEVINL void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+CF_DEVINL void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+CF_DEVINL void umma_commit_2sm(uint64_t* bar) {   // arrive on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(uint16_t(3))
+               : "memory");
+}
+CF_DEVINL void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+CF_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int EPI, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, GemmEpiParams ep) {
+  constexpr int BN = GEMM_BN;                 // 256 accumulator columns per CTA
+  constexpr uint32_t A_BYTES = GEMM_BM * 128; // this CTA's 128 rows of A
+  constexpr uint32_t B_BYTES = 128 * 128;     // this CTA's 128 of the tile's 256 B rows
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + GEMM2_STAGES * A_BYTES;
+  uint8_t* sStage = sB + GEMM2_STAGES * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * GEMM_STAGING_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]  (used in the leader CTA)
+  uint64_t* empty_bar = bars + GEMM2_STAGES;      // [STAGES]  (one per CTA)
+  uint64_t* tfull_bar = bars + 2 * GEMM2_STAGES;  // [2]       (one per CTA)
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]       (used in the leader CTA, 2 x 256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int m_tiles = (M + 255) / 256;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    if (EPI != EPI_ARGMAX) tma_prefetch_desc(&tma_c);
+    for (int s = 0; s < GEMM2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * 32 * GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs; completion lands on the leader's barrier)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
+          const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, m_blk * 256 + int(rank) * 128);
+          tma_load_2d_2sm(sB + stage * B_BYTES, &tma_b, fb, kb * GEMM_BK, n_blk * BN + int(rank) * 128);
+          if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
+          const uint64_t db = make_sw128_desc(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit_2sm(&tfull_bar[acc]);
+          if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (both CTAs, each on the accumulator rows of its M half)
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int grp = ew >> 2;
+    const bool issuer = ((ew & 3) == 0) && lane == 0;
+    const int bar_id = 1 + grp;
+    uint8_t* stg = sStage + grp * GEMM_STAGING_BYTES;
+    const int trow = quad * 32 + lane;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + grp * 128;
+      gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * 256 + int(rank) * 128, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg,
+                                   bar_id, issuer, &tma_c, ep);
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+    }
+    if (issuer && EPI != EPI_ARGMAX) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // no CTA of the pair may exit (or free TMEM) while the other can still signal it
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
 }  // namespace cf

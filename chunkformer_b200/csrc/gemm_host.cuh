@@ -66,11 +66,18 @@ struct GemmLaunch {
   GemmEpiParams ep;
 };
 
+// 0 = 1-CTA kernel, 1 = 2-CTA (cta_group::2) kernel; set by launch_gemm from the problem size / CF_GEMM_2CTA.
+inline int& gemm_variant_override() { static int v = -1; return v; }
+
 template <int EPI, int ACT>
 inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
+  int use2 = gemm_variant_override();
+  // Measured on B200 (tools/bench_gemm_shapes.py): the pair kernel wins when the K loop dominates (K >= 1024: FFN w_2,
+  // embed.out); for K = 512 the epilogue dominates and the 1-CTA kernel is faster. Small M: a 256-row tile is mostly padding.
+  if (use2 < 0) use2 = (g.M >= 2048 && g.K >= 1024) ? 1 : 0;
   CUtensorMap ta, tb, tc;
   if (!make_tma_2d_bf16(&ta, g.A, g.M, g.K, g.lda, GEMM_BM, GEMM_BK, err)) return false;
-  if (!make_tma_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, GEMM_BN, GEMM_BK, err)) return false;
+  if (!make_tma_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, use2 ? 128 : GEMM_BN, GEMM_BK, err)) return false;
   if (EPI == EPI_ARGMAX) {
     tc = ta;
   } else {
@@ -81,6 +88,31 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
       return false;
     }
     if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
+  }
+  if (use2) {
+    auto kern2 = gemm2_tcgen05_kernel<EPI, ACT>;
+    static bool attr2_set = false;
+    const size_t smem2 = gemm2_smem_bytes();
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2));
+      if (e != cudaSuccess) {
+        if (err) *err = std::string("cudaFuncSetAttribute(gemm2): ") + cudaGetErrorString(e);
+        return false;
+      }
+      attr2_set = true;
+    }
+    const int tiles2 = ((g.M + 255) / 256) * ((g.N + GEMM_BN - 1) / GEMM_BN);
+    if (tiles2 == 0) return true;
+    int clusters = num_sms / 2;
+    if (clusters > tiles2) clusters = tiles2;
+    kern2<<<2 * clusters, GEMM_THREADS, smem2, stream>>>(ta, tb, tc, g.M, g.N, g.K, g.ep);
+    ++g_kernel_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("gemm2 launch: ") + cudaGetErrorString(e);
+      return false;
+    }
+    return true;
   }
   auto kern = gemm_tcgen05_kernel<EPI, ACT>;
   static bool attr_set = false;

@@ -63,6 +63,8 @@ CF_API const char* cf_last_error(const cf_handle* h);
 CF_API const char* cf_version(void);
 /* Number of kernels this library has launched in the process so far (bench.py reports the per-step count). */
 CF_API long long cf_launch_count(void);
+/* Force the GEMM kernel variant: 0 = 1-CTA, 1 = 2-CTA pair (cta_group::2), -1 = choose by problem size (default). */
+CF_API void cf_set_gemm_variant(int variant);
 
 /* ---- weights ----------------------------------------------------------------------------------------------------- */
 /* Replaces: load_checkpoint -> model.load_state_dict(strict=False) (chunkformer/utils/checkpoint.py:26-41).

@@ -33,6 +33,15 @@ def _gemm(A, B, epi, out, bias, act=0, resid=None, alpha=1.0, row_range=None, ro
     torch.cuda.synchronize()
 
 
+@pytest.fixture(params=[0, 1], ids=["gemm1cta", "gemm2cta"])
+def gemm_variant(request):
+    """Run a GEMM test on the 1-CTA kernel and on the 2-CTA pair (cta_group::2) kernel."""
+    L = cflib.load()
+    L.cf_set_gemm_variant(request.param)
+    yield request.param
+    L.cf_set_gemm_variant(-1)
+
+
 def _rand(shape, scale=1.0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(DEV)
@@ -41,7 +50,7 @@ def _rand(shape, scale=1.0, seed=0):
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (200, 512, 512), (1000, 2048, 512), (777, 512, 2048), (64, 256, 4608),
                                    (40000, 512, 512)])
 @pytest.mark.parametrize("act", [0, 1, 2])
-def test_gemm_bias_act_bf16(M, N, K, act):
+def test_gemm_bias_act_bf16(M, N, K, act, gemm_variant):
     A = _rand((M, K), 1.0, 1).bfloat16()
     B = _rand((N, K), 1.0 / math.sqrt(K), 2).bfloat16()
     bias = _rand((N,), 0.5, 3)
@@ -57,7 +66,7 @@ def test_gemm_bias_act_bf16(M, N, K, act):
     assert (out.float() - ref).abs().mean().item() < 3e-3
 
 
-def test_gemm_glu():
+def test_gemm_glu(gemm_variant):
     M, d = 300, 512
     A = _rand((M, d), 1.0, 1).bfloat16()
     W = _rand((2 * d, d), 1.0 / math.sqrt(d), 2)
@@ -73,7 +82,7 @@ def test_gemm_glu():
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
-def test_gemm_f32_residual_rowmask():
+def test_gemm_f32_residual_rowmask(gemm_variant):
     c, n, d, K = 64, 5, 512, 2048
     M = n * c
     A = _rand((M, K), 1.0, 1).bfloat16()
@@ -100,7 +109,7 @@ def test_gemm_f32_residual_rowmask():
     assert (outv - refv).abs().max().item() < 2e-3
 
 
-def test_gemm_strided_output_view():
+def test_gemm_strided_output_view(gemm_variant):
     """The fused [Q+u | Q+v | K | V] projection writes into a row-offset view of the flat QKV buffer."""
     M, d, lead = 333, 512, 128
     A = _rand((M, d), 1.0, 1).bfloat16()
@@ -113,7 +122,7 @@ def test_gemm_strided_output_view():
     assert bool((buf[:lead] == 3.0).all()) and bool((buf[lead + M:] == 3.0).all())   # rows outside [0, M) untouched
 
 
-def test_gemm_argmax_partials():
+def test_gemm_argmax_partials(gemm_variant):
     M, d, V = 500, 512, 5000
     A = _rand((M, d), 1.0, 1).bfloat16()
     W = _rand((V, d), 1.0 / math.sqrt(d), 2).bfloat16()
