@@ -47,6 +47,20 @@ def path_flops_per_chunk(geo, c, l, r):
     return sub + geo.layers * layer_flops_per_chunk(geo, c, l, r) + 2 * c * d * V
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/r01_ncu_gemm_ffn1_full.csv); None if the summary is absent."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_ffn1_full.csv")):
+            name, unit, val = line.strip().split(",", 2)
+            if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return tot or None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -270,7 +284,7 @@ def main():
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EPI_BF16, ACT_SILU> (FFN w_1 + SiLU, M=%d N=%d K=%d)" % (rows, F, d),
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s",
-                    "traffic": None, "ms_per_launch": k_ms,
+                    "traffic": ncu_traffic_bytes(), "ms_per_launch": k_ms,
                     "path_tflops": path_flops_per_chunk(geo, C, L, R) * plan.n * args.steps * world / (ms_total * 1e-3) / 1e12,
                     "path_frac_of_sustained": None}
         sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
