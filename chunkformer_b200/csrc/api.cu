@@ -401,9 +401,34 @@ bool run_dwconv_d(const DwConvParams& p, cudaStream_t st, std::string* err) {
   if (e != cudaSuccess) { *err = std::string("dwconv launch: ") + cudaGetErrorString(e); return false; }
   return true;
 }
-bool run_dwconv(int d, int kernel, const DwConvParams& p, cudaStream_t st, std::string* err) {
+template <int D>
+bool run_dwconv_tma(const DwConvParams& p, long long g_rows, int num_sms, cudaStream_t st, std::string* err) {
+  CUtensorMap tm;
+  if (!make_tma_2d(&tm, p.g, false, uint64_t(g_rows), uint64_t(D), uint64_t(D), 46, 256, err, /*swizzle128=*/false)) return false;
+  const size_t smem = dwconv_tma_smem_bytes<D>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_silu_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(dwconv): ") + cudaGetErrorString(e); return false; }
+    attr_set = true;
+  }
+  const int groups = p.n_chunks * (p.c / 32);
+  const int grid = groups < 2 * num_sms ? groups : 2 * num_sms;
+  dwconv_ln_silu_tma_kernel<D><<<grid, D / 2, smem, st>>>(tm, p, groups);
+  ++cf::g_kernel_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("dwconv launch: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+
+// g_rows: rows of the GLU buffer that may be read (>= n_chunks * c + kernel - 1); 0 = use the CUDA-core (non-TMA) kernel
+bool run_dwconv(int d, int kernel, const DwConvParams& p, cudaStream_t st, std::string* err, long long g_rows = 0, int num_sms = 148) {
   if (kernel != 15) { *err = "dwconv: kernel must be 15"; return false; }
   if (p.n_chunks == 0) return true;
+  if (g_rows > 0 && p.c % 32 == 0) {
+    if (d == 512) return run_dwconv_tma<512>(p, g_rows, num_sms, st, err);
+    if (d == 256) return run_dwconv_tma<256>(p, g_rows, num_sms, st, err);
+  }
   if (d == 512) return run_dwconv_d<512>(p, st, err);
   if (d == 256) return run_dwconv_d<256>(p, st, err);
   *err = "dwconv: d must be 256 or 512";
@@ -712,7 +737,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     if (cnn_cache) { cnn_cache_export_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo, trunc); ++cf::g_kernel_launches; }
     { DwConvParams q{};
       q.g = w.g; q.z = w.z; q.w = lw.dw_w; q.bias = lw.dw_b; q.ln_w = lw.cn_w; q.ln_b = lw.cn_b; q.range = w.conv_range; q.c = c; q.n_chunks = n;
-      CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err)); }
+      CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, (long long)w.g_rows, h->num_sms)); }
     { EpiArgs e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       e.row_range = w.out_range; e.rows_per_chunk = c;
       CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
@@ -825,7 +850,9 @@ extern "C" int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16,
   q.g = static_cast<const bf16*>(g_bf16); q.z = static_cast<bf16*>(z_bf16); q.w = w; q.bias = bias; q.ln_w = ln_w;
   q.ln_b = ln_b; q.range = reinterpret_cast<const int2*>(range); q.c = c; q.n_chunks = n_chunks;
   std::string err;
-  if (!run_dwconv(d, kernel, q, static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  // the TMA-staged kernel is used when the caller guarantees c % 32 == 0 (g then holds n_chunks*c + 14 readable rows)
+  if (!run_dwconv(d, kernel, q, static_cast<cudaStream_t>(stream), &err, (long long)n_chunks * c + 14, current_sms()))
+    return fail(nullptr, CF_ERR_CUDA, err);
   return CF_OK;
 }
 

@@ -202,24 +202,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         tc_fence_after();
         float s[64];
         float mx = -1e30f;
+        uint4 keep[4];                                 // packed fp16 S_bd columns [32, 64) of this thread's window:
+                                                       // staged as the upper half for sub-block 0, lower half for sub-block 1
 #pragma unroll
         for (int sb = 0; sb < 2; ++sb) {
           uint32_t r0[32];
-          const uint32_t cbase = TM_BD + cb_thread + 32 * sb;
+          const uint32_t cbase = TM_BD + cb_thread;
           const float sc = PRE ? 1.0f : p.scale_log2e;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {             // stage 64 S_bd columns as fp16 (two 32-column TMEM loads)
-            tmem_ld32(tmem_base + lane_addr + cbase + 32 * hh, r0);
+          auto pack4 = [&](int q) {
+            uint4 w0;
+            w0.x = pack_half2(__uint_as_float(r0[8 * q]) * sc, __uint_as_float(r0[8 * q + 1]) * sc);
+            w0.y = pack_half2(__uint_as_float(r0[8 * q + 2]) * sc, __uint_as_float(r0[8 * q + 3]) * sc);
+            w0.z = pack_half2(__uint_as_float(r0[8 * q + 4]) * sc, __uint_as_float(r0[8 * q + 5]) * sc);
+            w0.w = pack_half2(__uint_as_float(r0[8 * q + 6]) * sc, __uint_as_float(r0[8 * q + 7]) * sc);
+            return w0;
+          };
+          if (sb == 0) {                               // window columns [0, 32) and [32, 64): two TMEM loads
+            tmem_ld32(tmem_base + lane_addr + cbase, r0);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 w0;
-              w0.x = pack_half2(__uint_as_float(r0[8 * q]) * sc, __uint_as_float(r0[8 * q + 1]) * sc);
-              w0.y = pack_half2(__uint_as_float(r0[8 * q + 2]) * sc, __uint_as_float(r0[8 * q + 3]) * sc);
-              w0.z = pack_half2(__uint_as_float(r0[8 * q + 4]) * sc, __uint_as_float(r0[8 * q + 5]) * sc);
-              w0.w = pack_half2(__uint_as_float(r0[8 * q + 6]) * sc, __uint_as_float(r0[8 * q + 7]) * sc);
-              *reinterpret_cast<uint4*>(stage + 64 * hh + 16 * q) = w0;
-            }
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stage + 16 * q) = pack4(q);
+            tmem_ld32(tmem_base + lane_addr + cbase + 32, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { keep[q] = pack4(q); *reinterpret_cast<uint4*>(stage + 64 + 16 * q) = keep[q]; }
+          } else {                                     // window columns [32, 64) come from registers, [64, 96) from TMEM
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stage + 16 * q) = keep[q];
+            tmem_ld32(tmem_base + lane_addr + cbase + 64, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stage + 64 + 16 * q) = pack4(q);
           }
           tmem_ld32(tmem_base + lane_addr + TM_AC + 64 * set + 32 * sb, r0);
           tmem_ld_wait();

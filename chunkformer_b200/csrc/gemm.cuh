@@ -85,6 +85,7 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
   const bool row_ok = row < M;
 
   if (EPI == EPI_ARGMAX) {
+    // running (best, runner-up) without branches; the index is recovered only for chunks that raise the maximum
     float best = -INFINITY, second = -INFINITY;
     int best_idx = 0;
 #pragma unroll 1
@@ -93,15 +94,30 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       if (col0 >= N) break;
       uint32_t r[32];
       tmem_ld32(taddr + cc * 32, r);
+      float v[32];
+      if (col0 + 32 <= N) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
+          v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (col0 + j < N) ? __ldg(ep.bias + col0 + j) : -INFINITY;
+      }
       tmem_ld_wait();
+      const float before = best;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int col = col0 + j;
-        if (col < N) {
-          const float v = __uint_as_float(r[j]) + __ldg(ep.bias + col);
-          if (v > best) { second = best; best = v; best_idx = col; }
-          else if (v > second) { second = v; }
-        }
+        v[j] += __uint_as_float(r[j]);
+        second = fmaxf(second, fminf(best, v[j]));
+        best = fmaxf(best, v[j]);
+      }
+      if (best > before) {                    // first column of this chunk that attains the new maximum (torch.argmax ties)
+        int idx = 31;
+#pragma unroll
+        for (int j = 30; j >= 0; --j) idx = (v[j] == best) ? j : idx;
+        best_idx = col0 + idx;
       }
     }
     if (row_ok) {

@@ -35,7 +35,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_tensor_map_encoder(std::string* err
 // 2-D row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols]; 128B swizzle
 // (box_cols * elem_bytes must be 128).
 inline bool make_tma_2d(CUtensorMap* map, const void* ptr, bool is_f32, uint64_t rows, uint64_t cols, uint64_t ld,
-                        uint32_t box_rows, uint32_t box_cols, std::string* err) {
+                        uint32_t box_rows, uint32_t box_cols, std::string* err, bool swizzle128 = true) {
   auto enc = get_tensor_map_encoder(err);
   if (!enc) return false;
   const size_t esz = is_f32 ? 4 : 2;
@@ -45,7 +45,8 @@ inline bool make_tma_2d(CUtensorMap* map, const void* ptr, bool is_f32, uint64_t
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r));
     return false;
