@@ -165,3 +165,40 @@ def test_ctc_large_60s_against_reference_golden(golden_dir):
     assert bool(ok.all())
     logp = enc.ctc_greedy(flat, want_logp=True)[1]
     assert abs(float(torch.logsumexp(logp[0], -1))) < 1e-3
+
+
+def test_full_size_masked_batch_properties():
+    """BASELINE.json configs[1] at full size (19 utterances, 14 400 s, 2821 chunks): size-independent properties.
+    * packing: chunk counts / encoder lengths equal the oracle's closed forms;
+    * isolation: a short utterance encoded inside the big batch == the same utterance encoded alone
+      (the reference's own self-consistency, SURVEY.md 8c), checked for the 1 s, 10 s and 30 s utterances;
+    * the CPU oracle agrees on those utterances (so the full-size run is tied to the reference through them);
+    * every valid output row is finite with unit-order rms (final LayerNorm), tokens are in range."""
+    from chunkformer_b200.synth import masked_batch_lengths
+    sd, enc = _model(LARGE, 0)
+    lens = masked_batch_lengths()
+    assert len(lens) == 19 and abs(sum((t + 2) / 100 for t in lens) - 14400) < 1e-6
+    xs = [synth_fbank(t, seed=1 + k) for k, t in enumerate(lens)]
+    out, out_lens, nck, *_ = enc.forward_parallel_chunk(xs, torch.tensor(lens, dtype=torch.int32), 64, 128, 128,
+                                                        offset=torch.zeros(len(lens), dtype=torch.int32))
+    plan = O.make_plan(lens, None, 64, 128, 128)
+    assert sum(nck) == 2821 and nck == [int(v) for v in plan.n_chunks]
+    assert out_lens.tolist() == [int(v) for v in plan.enc_lens] and int(out_lens.sum()) == 179964
+    tokens = enc.ctc_greedy(out)
+    starts = np.concatenate([[0], np.cumsum(nck)[:-1]])
+    rms = []
+    for u in range(len(lens)):
+        rows = out[starts[u]: starts[u] + nck[u]].reshape(-1, 512)[: int(out_lens[u])]
+        assert torch.isfinite(rows).all()
+        rms.append(float(rows.pow(2).mean().sqrt()))
+    assert 0.7 < min(rms) and max(rms) < 1.5
+    assert int(tokens.min()) >= 0 and int(tokens.max()) < LARGE.vocab
+    for u in (0, 15, 1):                                   # 1 s, 10 s, 30 s
+        single, sl, *_ = enc.forward_parallel_chunk([xs[u]], torch.tensor([lens[u]], dtype=torch.int32), 64, 128, 128,
+                                                    offset=torch.zeros(1, dtype=torch.int32))
+        m = int(sl[0])
+        a = out[starts[u]: starts[u] + nck[u]].reshape(-1, 512)[:m]
+        b = single.reshape(-1, 512)[:m]
+        assert (a - b).abs().max().item() < 2e-2, u
+        ref, _, _, _, _, _ = O.forward_parallel_chunk(sd, LARGE.heads, [xs[u]], [lens[u]], 64, 128, 128)
+        _compare(a, ref.reshape(-1, 512)[:m], f"utterance {u} inside the 14 400 s batch vs oracle")
