@@ -22,6 +22,8 @@ using namespace cf;
 typedef __nv_bfloat16 bf16;
 
 static thread_local std::string g_last_error = "";
+static int g_fuse_layernorm = 0;   // LayerNorm fused behind the residual GEMMs: measured slower on B200 (85.3 vs 92.4 ms/step),
+                                   // kept selectable for experiments (cf_set_fused_layernorm)
 
 namespace cf { std::atomic<long long> g_kernel_launches{0}; }
 
@@ -75,6 +77,7 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
   } while (0)
 
 extern "C" long long cf_launch_count(void) { return cf::g_kernel_launches.load(); }
+extern "C" void cf_set_fused_layernorm(int on) { g_fuse_layernorm = on; }
 extern "C" void cf_set_gemm_variant(int v) { cf::gemm_variant_override() = v; }
 extern "C" const char* cf_version(void) { return "chunkformer_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cf_last_error(const cf_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
@@ -652,7 +655,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
 
   struct EpiArgs { const float* bias = nullptr; void* out = nullptr; long long ldo = 0; int act = ACT_NONE;
                    const float* resid = nullptr; long long ld_resid = 0; float alpha = 1.0f;
-                   const int2* row_range = nullptr; int rows_per_chunk = 1; };
+                   const int2* row_range = nullptr; int rows_per_chunk = 1;
+                   int ln_mode = 0; bf16* ln_y = nullptr; const float* ln1_w = nullptr; const float* ln1_b = nullptr;
+                   const float* ln2_w = nullptr; const float* ln2_b = nullptr; bool ln_limit = false; };
   auto gemm = [&](const void* A, long long lda, const void* B, long long ldb, long long M, int N, int K, int epi,
                   const EpiArgs& e) -> bool {
     GemmLaunch g{};
@@ -660,8 +665,14 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.out = e.out; g.ldo = e.ldo;
     g.ep.bias = e.bias; g.ep.resid = e.resid; g.ep.ld_resid = e.ld_resid; g.ep.alpha = e.alpha;
     g.ep.row_range = e.row_range; g.ep.rows_per_chunk = e.rows_per_chunk;
+    if (e.ln_mode != 0) {
+      g.ep.ln_mode = e.ln_mode; g.ep.ln_x = static_cast<float*>(e.out); g.ep.ln_ldx = e.ldo; g.ep.ln_y = e.ln_y;
+      g.ep.ln1_w = e.ln1_w; g.ep.ln1_b = e.ln1_b; g.ep.ln2_w = e.ln2_w; g.ep.ln2_b = e.ln2_b;
+      g.ep.ln_row_limit = e.ln_limit ? w.seq_limit : nullptr; g.ep.ln_rows_per_seq = e.ln_limit ? p->rows_per_seq : 1;
+    }
     return launch_gemm(g, h->num_sms, st, &err);
   };
+  const bool fuse_ln = g_fuse_layernorm != 0;
 #define CF_TRY(expr) do { if (!(expr)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err); } while (0)
 
   // ---- front-end: slabs of chunks through conv0+dw1 -> pw1 -> dw2 -> pw2 -> out Linear
@@ -688,6 +699,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(gemm(w.a2, d, h->fe_w6, d, (long long)S * c * F3, d, d, EPI_BF16, e2));
       // (xW + b) * sqrt(d)  (subsampling.py:164, embedding.py:198)
       EpiArgs e3; e3.bias = h->fe_bout; e3.out = w.x + (size_t)g0 * c * d; e3.ldo = d; e3.alpha = sqrtf(float(d));
+      if (fuse_ln) { e3.ln_mode = 1; e3.ln_y = w.y + (size_t)g0 * c * d; e3.ln1_w = h->layers[0].ln_ffm_w; e3.ln1_b = h->layers[0].ln_ffm_b; }
       CF_TRY(gemm(w.b2, (long long)F3 * d, h->fe_wout, (long long)F3 * d, (long long)S * c, d, F3 * d, EPI_F32, e3));
     }
   }
@@ -701,16 +713,17 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     return run_layernorm(mode, d, q, st, &err);
   };
   const bool use_tc = kAttentionTcReady && attention_tc_supported(c, l, r, dk);
-  CF_TRY(ln(0, h->layers[0].ln_ffm_w, h->layers[0].ln_ffm_b, nullptr, nullptr, nullptr, w.y, false));
+  if (!fuse_ln) CF_TRY(ln(0, h->layers[0].ln_ffm_w, h->layers[0].ln_ffm_b, nullptr, nullptr, nullptr, w.y, false));
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = h->layers[i];
     // macaron FFN: x += 0.5 * W2 SiLU(W1 LN(x) + b1) + b2
     { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
       CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
+      if (fuse_ln) { e.ln_mode = 1; e.ln_y = w.y; e.ln1_w = lw.ln_mha_w; e.ln1_b = lw.ln_mha_b; }
       CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
     // self-attention
-    CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
+    if (!fuse_ln) CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
     if (att_cache && l > 0) {
       const int tot = l * H * 2 * dk;
       att_cache_import_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<const float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d);
@@ -728,9 +741,10 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk)); a.prescaled = 1;
       CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
     { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
+      if (fuse_ln) { e.ln_mode = 1; e.ln_y = w.y; e.ln1_w = lw.ln_conv_w; e.ln1_b = lw.ln_conv_b; e.ln_limit = p->mode == 1; }
       CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
     // convolution module
-    CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
+    if (!fuse_ln) CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
     if (cnn_cache) { cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo); ++cf::g_kernel_launches; }
     { EpiArgs e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
       CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mr, 2 * d, d, EPI_GLU, e)); }
@@ -740,15 +754,20 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, (long long)w.g_rows, h->num_sms)); }
     { EpiArgs e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       e.row_range = w.out_range; e.rows_per_chunk = c;
+      if (fuse_ln) { e.ln_mode = 1; e.ln_y = w.y; e.ln1_w = lw.ln_ff_w; e.ln1_b = lw.ln_ff_b; }
       CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
     // FFN
-    CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
+    if (!fuse_ln) CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
     { EpiArgs e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
       CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mr, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
+      if (fuse_ln && i + 1 < L) {
+        e.ln_mode = 2; e.ln_y = w.y; e.ln1_w = lw.ln_fin_w; e.ln1_b = lw.ln_fin_b;
+        e.ln2_w = h->layers[i + 1].ln_ffm_w; e.ln2_b = h->layers[i + 1].ln_ffm_b;
+      }
       CF_TRY(gemm(w.hbuf, F, lw.ff_w2, F, Mr, d, F, EPI_F32, e)); }
     if (i + 1 < L) {
-      CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));
+      if (!fuse_ln) CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));
     } else {
       // norm_final of the last layer + after_norm (encoder.py:670-671)
       LnParams q{};

@@ -33,6 +33,17 @@ struct GemmEpiParams {
   float* part_best = nullptr;    // EPI_ARGMAX: [M, 2 * n_tiles]
   float* part_second = nullptr;
   int* part_index = nullptr;
+  // EPI_F32 only: LayerNorm fused behind the residual update.  After a CTA has stored every column tile of a 128-row
+  // block it normalises those rows straight from L2 (the fp32 rows it has just written), so the stand-alone LayerNorm
+  // pass and its HBM read of x disappear.  ln_mode 1: y = LN1(x);  2: x <- LN1(x), y = LN2(x) (norm_final + next norm).
+  int ln_mode = 0;
+  float* ln_x = nullptr;            // = the GEMM output (fp32, row pitch ln_ldx)
+  long long ln_ldx = 0;
+  __nv_bfloat16* ln_y = nullptr;    // [M, N] bf16
+  const float* ln1_w = nullptr; const float* ln1_b = nullptr;
+  const float* ln2_w = nullptr; const float* ln2_b = nullptr;
+  const int* ln_row_limit = nullptr;   // optional: rows with (row % ln_rows_per_seq) >= limit[row / ln_rows_per_seq] give y = 0
+  int ln_rows_per_seq = 1;
 };
 
 constexpr int GEMM_BM = 128;
@@ -73,6 +84,93 @@ CF_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;"
 // 16-byte store into a 128B-swizzled [128 rows][128 B] staging tile (matches CU_TENSOR_MAP_SWIZZLE_128B).
 CF_DEVINL void stage_store16(uint8_t* tile, int row, int slot, uint4 v) {
   *reinterpret_cast<uint4*>(tile + row * 128 + ((slot ^ (row & 7)) << 4)) = v;
+}
+
+// Tile schedule of a persistent CTA (or CTA pair) `cta` of `ncta`: by default tiles are dealt round-robin in (m, n) order
+// (balanced to one tile); with the fused LayerNorm a CTA owns whole 128/256-row blocks (all their column tiles back to back).
+CF_DEVINL bool gemm_tile_of(int t, int cta, int ncta, int m_tiles, int n_tiles, bool block_major, int& m_blk, int& n_blk) {
+  if (block_major) {
+    m_blk = cta + (t / n_tiles) * ncta;
+    n_blk = t % n_tiles;
+    return m_blk < m_tiles;
+  }
+  const int tile = cta + t * ncta;
+  m_blk = tile / n_tiles;
+  n_blk = tile - m_blk * n_tiles;
+  return tile < m_tiles * n_tiles;
+}
+
+// LayerNorm of `nrows` freshly stored fp32 rows (N = 256 or 512 columns) by the 8 epilogue warps of a CTA: warp per row,
+// fp32 two-pass statistics, reads through L2 (ld.global.cg: the rows were written by this CTA's TMA stores).
+CF_DEVINL void gemm_fused_layernorm(const GemmEpiParams& ep, int row0, int M, int N, int epi_warp, int lane) {
+  const int v4 = N >> 7;                       // float4 per lane (2 or 4)
+  const float inv_n = 1.0f / float(N);
+  constexpr int RB = 4;                        // rows in flight per warp (latency hiding for the L2 reads)
+  for (int r0 = epi_warp * RB; r0 < GEMM_BM; r0 += GEMM_EPI_WARPS * RB) {
+    float4 raw[RB][4];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+      const int row = row0 + r0 + j;
+      const float* xr = ep.ln_x + (long long)row * ep.ln_ldx;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        raw[j][k] = (row < M && k < v4) ? __ldcg(reinterpret_cast<const float4*>(xr + k * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+      const int row = row0 + r0 + j;
+      if (row >= M) break;
+      float* xr = ep.ln_x + (long long)row * ep.ln_ldx;
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[4 * k] = raw[j][k].x; v[4 * k + 1] = raw[j][k].y; v[4 * k + 2] = raw[j][k].z; v[4 * k + 3] = raw[j][k].w; }
+      auto normalise = [&](const float* w, const float* b) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += v[i];
+        const float mean = warp_sum(s) * inv_n;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < v4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float dlt = v[4 * k + i] - mean; q += dlt * dlt; }
+          }
+        const float rstd = rsqrtf(warp_sum(q) * inv_n + 1e-5f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < v4) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + k * 128 + lane * 4));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b + k * 128 + lane * 4));
+            v[4 * k] = (v[4 * k] - mean) * rstd * ww.x + bb.x;
+            v[4 * k + 1] = (v[4 * k + 1] - mean) * rstd * ww.y + bb.y;
+            v[4 * k + 2] = (v[4 * k + 2] - mean) * rstd * ww.z + bb.z;
+            v[4 * k + 3] = (v[4 * k + 3] - mean) * rstd * ww.w + bb.w;
+          }
+      };
+      normalise(ep.ln1_w, ep.ln1_b);
+      if (ep.ln_mode == 2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < v4) *reinterpret_cast<float4*>(xr + k * 128 + lane * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        normalise(ep.ln2_w, ep.ln2_b);
+      }
+      bool zero = false;
+      if (ep.ln_row_limit) {
+        const int sq = row / ep.ln_rows_per_seq;
+        zero = (row - sq * ep.ln_rows_per_seq) >= ep.ln_row_limit[sq];
+      }
+      __nv_bfloat16* yr = ep.ln_y + (long long)row * N;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < v4) {
+          uint2 o;
+          o.x = zero ? 0u : pack_bf16(v[4 * k], v[4 * k + 1]);
+          o.y = zero ? 0u : pack_bf16(v[4 * k + 2], v[4 * k + 3]);
+          *reinterpret_cast<uint2*>(yr + k * 128 + lane * 4) = o;
+        }
+    }
+  }
 }
 
 // Epilogue of one 128-row x 128-column accumulator slab (one epilogue group): shared by the 1-CTA and 2-CTA kernels.
@@ -256,8 +354,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const bool block_major = (EPI == EPI_F32) && ep.ln_mode != 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -283,8 +381,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int t = 0;; ++t) {
+        int m_blk, n_blk;
+        if (!gemm_tile_of(t, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -299,8 +398,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
       uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0;; ++it) {
+        int m_blk, n_blk;
+        if (!gemm_tile_of(it, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -330,9 +430,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int bar_id = 1 + grp;
     uint8_t* stg = sStage + grp * GEMM_STAGING_BYTES;
     const int trow = quad * 32 + lane;  // row inside the tile
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    int pending_row0 = -1;              // row block whose stores are in flight and whose LayerNorm is still to do
+    auto run_pending_ln = [&](bool last) {
+      if (pending_row0 < 0) return;
+      // the block's stores were committed one tile ago (4 newer bulk groups per issuer), so this wait is normally free
+      if (issuer) {
+        if (last) tma_store_wait_all(); else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      named_bar_sync(3, 32 * GEMM_EPI_WARPS);
+      gemm_fused_layernorm(ep, pending_row0, M, N, ew, lane);
+      pending_row0 = -1;
+    };
+    for (int it = 0;; ++it) {
+      int m_blk, n_blk;
+      if (!gemm_tile_of(it, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -341,7 +453,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                    issuer, &tma_c, ep);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (EPI == EPI_F32 && block_major) {
+        run_pending_ln(false);
+        if (n_blk == n_tiles - 1) pending_row0 = m_blk * GEMM_BM;
+      }
     }
+    if (EPI == EPI_F32 && block_major) run_pending_ln(true);
     if (issuer && EPI != EPI_ARGMAX) tma_store_wait_all();   // global writes complete before the CTA exits
   }
 
@@ -431,8 +548,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   const int num_clusters = gridDim.x >> 1;
   const int m_tiles = (M + 255) / 256;
   const int n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const bool block_major = (EPI == EPI_F32) && ep.ln_mode != 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -458,8 +575,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     // ------------------------------------------------ TMA producer (both CTAs; completion lands on the leader's barrier)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int t = 0;; ++t) {
+        int m_blk, n_blk;
+        if (!gemm_tile_of(t, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
@@ -475,8 +593,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
       uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      for (int it = 0;; ++it) {
+        int m_blk, n_blk;
+        if (!gemm_tile_of(it, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -503,9 +622,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const int bar_id = 1 + grp;
     uint8_t* stg = sStage + grp * GEMM_STAGING_BYTES;
     const int trow = quad * 32 + lane;
-    int it = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    int pending_row0 = -1;
+    auto run_pending_ln = [&](bool last) {
+      if (pending_row0 < 0) return;
+      if (issuer) {
+        if (last) tma_store_wait_all(); else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      named_bar_sync(3, 32 * GEMM_EPI_WARPS);
+      gemm_fused_layernorm(ep, pending_row0, M, N, ew, lane);
+      pending_row0 = -1;
+    };
+    for (int it = 0;; ++it) {
+      int m_blk, n_blk;
+      if (!gemm_tile_of(it, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -514,7 +644,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                                    bar_id, issuer, &tma_c, ep);
       tc_fence_before();
       mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+      if (EPI == EPI_F32 && block_major) {
+        run_pending_ln(false);
+        if (n_blk == n_tiles - 1) pending_row0 = m_blk * 256 + int(rank) * 128;
+      }
     }
+    if (EPI == EPI_F32 && block_major) run_pending_ln(true);
     if (issuer && EPI != EPI_ARGMAX) tma_store_wait_all();
   }
 

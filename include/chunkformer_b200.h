@@ -65,6 +65,9 @@ CF_API const char* cf_version(void);
 CF_API long long cf_launch_count(void);
 /* Force the GEMM kernel variant: 0 = 1-CTA, 1 = 2-CTA pair (cta_group::2), -1 = choose by problem size (default). */
 CF_API void cf_set_gemm_variant(int variant);
+/* 0 (default): LayerNorms run as separate HBM-roofline kernels; 1: fused behind the residual GEMMs (the epilogue warps
+ * normalise the rows they just stored, out of L2) - measured slower on B200, kept for A/B measurements. */
+CF_API void cf_set_fused_layernorm(int on);
 
 /* ---- weights ----------------------------------------------------------------------------------------------------- */
 /* Replaces: load_checkpoint -> model.load_state_dict(strict=False) (chunkformer/utils/checkpoint.py:26-41).
