@@ -453,6 +453,20 @@ bool run_frontend_conv(int impl, int d, const Fe1Params& f1, int num_sms, cudaSt
       e = cudaFuncSetAttribute(frontend_conv0_dw1_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
       if (e == cudaSuccess) frontend_conv0_dw1_kernel<256><<<f1.n_chunks * bpc, 128, smem, st>>>(f1);
     } else { *err = "frontend: d must be 256 or 512"; return false; }
+  } else if (impl == 2) {
+    // channel-major kernel: one unit per output time row, needs the 80-bin geometry (39 / 19 bins after conv0 / dw1)
+    if (f1.feat_dim != 80) { *err = "frontend: the channel-major kernel needs feat_dim == 80"; return false; }
+    const int units = f1.n_chunks * f1.T2;
+    const int grid = units < num_sms ? units : num_sms;
+    if (d == 512) {
+      const size_t smem = frontend_cm_smem_bytes<512>();
+      e = cudaFuncSetAttribute(frontend_conv0_dw1_cm_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) frontend_conv0_dw1_cm_kernel<512><<<grid, fecm_threads<512>(), smem, st>>>(f1, units);
+    } else if (d == 256) {
+      const size_t smem = frontend_cm_smem_bytes<256>();
+      e = cudaFuncSetAttribute(frontend_conv0_dw1_cm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) frontend_conv0_dw1_cm_kernel<256><<<grid, fecm_threads<256>(), smem, st>>>(f1, units);
+    } else { *err = "frontend: d must be 256 or 512"; return false; }
   } else {
     const int tiles = f1.n_chunks * bpc;
     const int grid = tiles < num_sms ? tiles : num_sms;
@@ -684,7 +698,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       Fe1Params f1{};
       f1.feats = feats; f1.chunks = w.chunk_src + g0; f1.wpack = h->fe_wpack; f1.cmvn_mean = h->cmvn_mean; f1.cmvn_istd = h->cmvn_istd;
       f1.out = w.a1; f1.n_chunks = S; f1.feat_dim = h->cfg.feat_dim; f1.T2 = T2; f1.F2 = F2; f1.in_rows = p->in_rows;
-      if (!run_frontend_conv(1, d, f1, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err);
+      if (!run_frontend_conv(h->cfg.feat_dim == 80 ? 2 : 1, d, f1, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err);
       EpiArgs e1; e1.bias = h->fe_b3; e1.out = w.b1; e1.ldo = d; e1.act = ACT_RELU;
       CF_TRY(gemm(w.a1, d, h->fe_w3, d, (long long)S * T2 * F2, d, d, EPI_BF16, e1));
       Fe2Params f2{};

@@ -314,6 +314,211 @@ template <int D>
 constexpr size_t frontend_tc_smem_bytes() { return 9 * 4096 + (D / 16) * 512 + (D / 16) * 160 * 4 + 39 * 80 * 4 + 128; }
 
 // ---------------------------------------------------------------------------------------------
+// Channel-major tensor-core version of conv0 + ReLU + depthwise conv1 (same output as the two kernels above).
+// Work unit = one output time row (chunk, t2): the three conv0 rows t1 = 2*t2 + {0,1,2} it depends on are ONE UMMA per
+// block of 128 channels, with the roles swapped relative to the kernel above:
+//     G[ch, p] = W0'[ch, 0..15] . X[p, 0..15],   p = 3*f1 + r   (f1 < 39 conv0 frequency bins, r < 3 conv0 rows)
+// so TMEM lanes are channels and TMEM columns are conv0 positions.  An epilogue thread owns one channel: its nine
+// depthwise taps and bias live in registers for the whole kernel, every conv0 value is read from TMEM and rectified
+// exactly once per unit (6.2 per output instead of 9), and the depthwise conv is 9 register FMAs per output.
+// Outputs of neighbouring channels are paired with one shuffle so each lane stores a bf16x2.
+//   warps [0, 4*NWG)   : epilogue, warpgroup g owns channels [128g, 128g+128) and TMEM columns [128g, 128g+128)
+//   warp  4*NWG        : TMEM allocator + MMA issuer
+//   warps 4*NWG + 1, 2 : producers: thread = conv0 frequency bin, 7x3 input patch -> three im2col rows (bf16)
+// ---------------------------------------------------------------------------------------------
+template <int D> constexpr int fecm_threads() { return (4 * (D / 128) + 3) * 32; }
+constexpr int FECM_STAGES = 3;
+constexpr int FECM_F1 = 39, FECM_F2 = 19;      // maxima (feat_dim <= 80)
+
+template <int D>
+__global__ void __launch_bounds__(fecm_threads<D>(), 1) frontend_conv0_dw1_cm_kernel(Fe1Params p, int total_units) {
+  static_assert(D % 128 == 0, "D");
+  constexpr int NWG = D / 128;
+  constexpr int EPI_WARPS = 4 * NWG;
+  extern __shared__ __align__(1024) uint8_t fec_smem[];
+  uint8_t* sW = fec_smem;                                   // NWG x [128 ch x 16 k] bf16 (A operands)
+  uint8_t* sB = sW + NWG * 4096;                            // FECM_STAGES x [128 pos x 16 k] bf16 (B operands)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + FECM_STAGES * 4096);
+  uint64_t* b_full = bars;                                  // [STAGES] producers -> MMA (64 arrivals)
+  uint64_t* b_empty = bars + FECM_STAGES;                   // [STAGES] MMA -> producers (commit)
+  uint64_t* t_full = bars + 2 * FECM_STAGES;                // [NWG] MMA -> warpgroup (commit)
+  uint64_t* t_free = bars + 2 * FECM_STAGES + NWG;          // [NWG] warpgroup -> MMA (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FECM_STAGES + 2 * NWG);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int upc = (total_units + gridDim.x - 1) / gridDim.x;
+  const int u_begin = blockIdx.x * upc;
+  const int u_end = min(total_units, u_begin + upc);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < FECM_STAGES; ++s) { mbar_init(&b_full[s], 64); mbar_init(&b_empty[s], 1); }
+    for (int g = 0; g < NWG; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_free[g], 4); }
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) tmem_alloc(tmem_slot, NWG * 128);
+  // conv0 weights -> A operand images (no-swizzle K-major core matrices: 8 rows x 16 B, K groups 128 B apart)
+  for (int ch = threadIdx.x; ch < D; ch += blockDim.x) {
+    const float* wp = p.wpack + ch * 20;
+    const int blk = ch >> 7, row = ch & 127;
+    __nv_bfloat16* k0 = reinterpret_cast<__nv_bfloat16*>(sW + blk * 4096 + (row >> 3) * 256 + (row & 7) * 16);
+    __nv_bfloat16* k8 = k0 + 64;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) k0[k] = __float2bfloat16(wp[k]);
+    k8[0] = __float2bfloat16(wp[8]);
+    k8[1] = __float2bfloat16(wp[9]);        // conv0 bias rides on the constant-1 input column
+#pragma unroll
+    for (int k = 2; k < 8; ++k) k8[k] = __float2bfloat16(0.f);
+  }
+  for (int i = threadIdx.x; i < FECM_STAGES * 4096 / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);   // positions past 3*F1 stay zero
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue: thread = channel
+    const int g = warp >> 2, quad = warp & 3;
+    const int ch = g * 128 + quad * 32 + lane;
+    float w1[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w1[t] = __ldg(p.wpack + ch * 20 + 10 + t);
+    const float bias1 = __ldg(p.wpack + ch * 20 + 19);
+    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + g * 128;
+    const int odd = lane & 1;
+    __nv_bfloat16* out_ch = p.out + g * 128 + quad * 32 + (lane & ~1);
+    uint32_t it = 0;
+    for (int u = u_begin; u < u_end; ++u, ++it) {
+      mbar_wait(&t_full[g], it & 1);
+      tc_fence_after();
+      __nv_bfloat16* orow = out_ch + (long long)u * FECM_F2 * D;
+      uint32_t v[4][32];
+      float acc = 0.f, acc_prev = 0.f, held = 0.f;
+#pragma unroll
+      for (int ck = 0; ck < 4; ++ck) {
+        tmem_ld32(taddr + ck * 32, v[ck]);
+        tmem_ld_wait();
+        if (ck == 3) {                                    // every column of this unit is in registers
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&t_free[g]);
+        }
+#pragma unroll
+        for (int f1 = 0; f1 < FECM_F1; ++f1) {
+          if ((3 * f1 + 2) / 32 != ck) continue;          // handled when its last column arrives (compile-time)
+          const float y0 = fmaxf(__uint_as_float(v[(3 * f1) / 32][(3 * f1) % 32]), 0.f);
+          const float y1 = fmaxf(__uint_as_float(v[(3 * f1 + 1) / 32][(3 * f1 + 1) % 32]), 0.f);
+          const float y2 = fmaxf(__uint_as_float(v[(3 * f1 + 2) / 32][(3 * f1 + 2) % 32]), 0.f);
+          if ((f1 & 1) == 0) {
+            const int k = f1 >> 1;                        // closes output k-1 (tap column 2), opens output k (column 0)
+            if (k > 0) {
+              acc_prev = fmaf(w1[2], y0, acc);
+              acc_prev = fmaf(w1[5], y1, acc_prev);
+              acc_prev = fmaf(w1[8], y2, acc_prev);
+              const int ko = k - 1;
+              if (ko & 1) {                               // pair (ko-1, ko) complete: exchange with the neighbour channel
+                const float send = odd ? held : acc_prev;
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                const uint32_t pk = odd ? pack_bf16(recv, acc_prev) : pack_bf16(held, recv);
+                *reinterpret_cast<uint32_t*>(orow + (long long)(ko - 1 + odd) * D) = pk;
+              } else {
+                held = acc_prev;
+              }
+            }
+            if (k < FECM_F2) {
+              acc = fmaf(w1[0], y0, bias1);
+              acc = fmaf(w1[3], y1, acc);
+              acc = fmaf(w1[6], y2, acc);
+            }
+          } else {
+            acc = fmaf(w1[1], y0, acc);
+            acc = fmaf(w1[4], y1, acc);
+            acc = fmaf(w1[7], y2, acc);
+          }
+        }
+      }
+      (orow + (long long)(FECM_F2 - 1) * D)[odd] = __float2bfloat16(held);   // F2 = 19 is odd: the last output has no partner
+    }
+  } else if (warp == EPI_WARPS) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      uint32_t it = 0;
+      for (int u = u_begin; u < u_end; ++u, ++it) {
+        const int s = it % FECM_STAGES;
+        mbar_wait(&b_full[s], (it / FECM_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t db = make_nosw_desc(smem_u32(sB + s * 4096), 128, 256);
+#pragma unroll
+        for (int g = 0; g < NWG; ++g) {
+          mbar_wait(&t_free[g], (it & 1) ^ 1);
+          tc_fence_after();
+          umma_bf16_ss(tmem_base + g * 128, make_nosw_desc(smem_u32(sW + g * 4096), 128, 256), db, idesc, 0);
+          umma_commit(&t_full[g]);
+        }
+        umma_commit(&b_empty[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ producers: thread = conv0 frequency bin
+    const int f1 = threadIdx.x - (EPI_WARPS + 1) * 32;          // 0..63
+    const int F1 = (p.feat_dim - 3) / 2 + 1;
+    const bool live = f1 < F1 && f1 < FECM_F1;
+    float mean[3] = {0.f, 0.f, 0.f}, istd[3] = {1.f, 1.f, 1.f};
+    if (live && p.cmvn_mean) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { mean[j] = __ldg(p.cmvn_mean + 2 * f1 + j); istd[j] = __ldg(p.cmvn_istd + 2 * f1 + j); }
+    }
+    auto load_patch = [&](int u, float (&x)[7][3]) {
+      const int chunk = u / p.T2, t2 = u - chunk * p.T2;
+      const ChunkSrc cs = p.chunks[chunk];
+      const int lim = min(cs.in_len, p.in_rows);
+      const float* src = p.feats + (cs.feat_row + 4 * t2) * p.feat_dim + 2 * f1;
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float vv = 0.f;
+          if (4 * t2 + i < lim) vv = __ldg(src + i * p.feat_dim + j);
+          x[i][j] = (vv - mean[j]) * istd[j];               // CMVN after zero padding (encoder.py:615-616)
+        }
+    };
+    float x[7][3], xn[7][3];
+    if (live && u_begin < u_end) load_patch(u_begin, xn);
+    uint32_t it = 0;
+    for (int u = u_begin; u < u_end; ++u, ++it) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x[i][j] = xn[i][j];
+      if (live && u + 1 < u_end) load_patch(u + 1, xn);     // next unit's loads fly while this one is written
+      const int s = it % FECM_STAGES;
+      mbar_wait(&b_empty[s], ((it / FECM_STAGES) & 1) ^ 1);
+      if (live) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int pos = 3 * f1 + r;
+          uint8_t* dst = sB + s * 4096 + (pos >> 3) * 256 + (pos & 7) * 16;
+          const uint4 lo = make_uint4(pack_bf16(x[2 * r][0], x[2 * r][1]), pack_bf16(x[2 * r][2], x[2 * r + 1][0]),
+                                      pack_bf16(x[2 * r + 1][1], x[2 * r + 1][2]), pack_bf16(x[2 * r + 2][0], x[2 * r + 2][1]));
+          const uint4 hi = make_uint4(pack_bf16(x[2 * r + 2][2], 1.0f), 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst) = lo;
+          *reinterpret_cast<uint4*>(dst + 128) = hi;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&b_full[s]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, NWG * 128);
+}
+
+template <int D>
+constexpr size_t frontend_cm_smem_bytes() { return (D / 128) * 4096 + FECM_STAGES * 4096 + 256; }
+
+// ---------------------------------------------------------------------------------------------
 // depthwise conv2 (3x3, stride 2, per channel) on the pw1 output: [(chunk, t2, f2), ch] -> [(chunk, t3, f3), ch].
 // Pure bandwidth: thread = 8 channels of one output position, 16-byte loads/stores. Weights as [9][D] + bias [D].
 // ---------------------------------------------------------------------------------------------

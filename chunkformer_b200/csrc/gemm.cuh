@@ -30,6 +30,7 @@ struct GemmEpiParams {
   float alpha = 1.0f;
   const int2* row_range = nullptr;  // EPI_F32: row valid iff range[row / rows_per_chunk].x <= row % rows_per_chunk < .y
   int rows_per_chunk = 1;
+  int resid_tma = 0;             // EPI_F32: residual sub-tiles are TMA-loaded into the staging tiles (set by launch_gemm)
   float* part_best = nullptr;    // EPI_ARGMAX: [M, 2 * n_tiles]
   float* part_second = nullptr;
   int* part_index = nullptr;
@@ -54,8 +55,12 @@ constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr uint32_t GEMM_STAGING_BYTES = 128 * 128;  // 128 rows x 128 bytes, one per epilogue group
 
-constexpr size_t gemm_smem_bytes() {
-  return size_t(GEMM_STAGES) * (GEMM_BM * 128 + GEMM_BN * 128) + 2 * GEMM_STAGING_BYTES + 1024 /*align slack*/ + 256;
+// The fp32 + residual epilogue double-buffers its staging tiles (the residual sub-tile of the next round is TMA-loaded into
+// one while the other is processed and stored) and gives up one pipeline stage for them.
+__host__ __device__ constexpr int gemm_stages(int epi) { return epi == 2 /*EPI_F32*/ ? 3 : GEMM_STAGES; }
+__host__ __device__ constexpr int gemm_staging_slots(int epi) { return epi == 2 ? 4 : 2; }
+constexpr size_t gemm_smem_bytes(int epi) {
+  return size_t(gemm_stages(epi)) * (GEMM_BM * 128 + GEMM_BN * 128) + gemm_staging_slots(epi) * GEMM_STAGING_BYTES + 1024 /*align slack*/ + 256;
 }
 
 // sigmoid / SiLU through one MUFU op (tanh.approx), so the SiLU epilogue stays under the MMA time of a K=512 tile.
@@ -173,12 +178,80 @@ CF_DEVINL void gemm_fused_layernorm(const GemmEpiParams& ep, int row0, int M, in
   }
 }
 
+CF_DEVINL uint4 stage_load16(const uint8_t* tile, int row, int slot) {
+  return *reinterpret_cast<const uint4*>(tile + row * 128 + ((slot ^ (row & 7)) << 4));
+}
+CF_DEVINL void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// fp32 + residual epilogue of one 128 x 128 accumulator slab with the residual moved by TMA (N % 256 == 0, so every group
+// of every tile runs exactly four 32-column rounds).  A thread owns one accumulator row; reading its 128-byte residual
+// segment straight from global memory costs 32 L1 wavefronts per warp instruction and was the bottleneck of the K = 512
+// GEMMs.  Instead the residual sub-tile [128 rows x 32 cols] of round rc+1 is TMA-loaded into the group's other staging
+// slot while round rc is processed; threads add their accumulator row to it in shared memory (swizzled, conflict free)
+// and the same slot is TMA-stored.  `rc` counts the group's rounds across tiles (slot = rc & 1, mbarrier phase = rc >> 1).
+CF_DEVINL void gemm_epilogue_f32_tma(uint32_t taddr, int row0, int trow, int gcol0, int M, uint8_t* stg2, int bar_id, bool issuer,
+                                     const CUtensorMap* tma_c, const CUtensorMap* tma_r, const GemmEpiParams& ep,
+                                     uint64_t* res_full, uint32_t& rc, int next_row0, int next_gcol0) {
+  const int row = row0 + trow;
+  bool keep = true;
+  if (ep.row_range != nullptr && row < M) {
+    const int ch = row / ep.rows_per_chunk;
+    const int rr = row - ch * ep.rows_per_chunk;
+    const int2 rg = ep.row_range[ch];
+    keep = (rr >= rg.x && rr < rg.y);
+  }
+  // masked rows get exactly +0 added (masked_fill_, convolution.py:253)
+  if (issuer && next_row0 >= 0) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) tma_prefetch_2d(tma_r, next_gcol0 + cc * 32, next_row0);   // next tile's residual -> L2
+  }
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc, ++rc) {
+    const int col0 = gcol0 + cc * 32;
+    const uint32_t slot = rc & 1u, ph = (rc >> 1) & 1u;
+    uint8_t* tile = stg2 + slot * GEMM_STAGING_BYTES;
+    uint32_t r[32];
+    tmem_ld32(taddr + cc * 32, r);
+    if (issuer) {
+      const bool in_tile = cc < 3;
+      const int nr0 = in_tile ? row0 : next_row0, nc0 = in_tile ? col0 + 32 : next_gcol0;
+      if (nr0 >= 0) {
+        tma_store_wait_read();                      // the store that last used the other slot has drained it
+        mbar_arrive_expect_tx(&res_full[slot ^ 1u], GEMM_STAGING_BYTES);
+        tma_load_2d(stg2 + (slot ^ 1u) * GEMM_STAGING_BYTES, tma_r, &res_full[slot ^ 1u], nc0, nr0);
+      }
+    }
+    float4 b[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) b[q] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
+    mbar_wait(&res_full[slot], ph);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint4 xr = stage_load16(tile, trow, q);
+      float4 v;
+      v.x = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * q]) + b[q].x, __uint_as_float(xr.x)) : __uint_as_float(xr.x);
+      v.y = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * q + 1]) + b[q].y, __uint_as_float(xr.y)) : __uint_as_float(xr.y);
+      v.z = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * q + 2]) + b[q].z, __uint_as_float(xr.z)) : __uint_as_float(xr.z);
+      v.w = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * q + 3]) + b[q].w, __uint_as_float(xr.w)) : __uint_as_float(xr.w);
+      stage_store16(tile, trow, q, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+    }
+    fence_proxy_async();
+    named_bar_sync(bar_id, 128);
+    if (issuer) { tma_store_2d(tma_c, tile, col0, row0); tma_store_commit(); }
+  }
+}
+
 // Epilogue of one 128-row x 128-column accumulator slab (one epilogue group): shared by the 1-CTA and 2-CTA kernels.
 //   taddr : TMEM address of the slab's first column for this warp's lane quadrant;  row0 : global row of tile row 0
 //   gcol0 : first global accumulator column of the slab;  stg : the group's 16 KB staging tile
 template <int EPI, int ACT>
 CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0, int n_blk, int grp, int n_tiles, int M, int N,
-                                  uint8_t* stg, int bar_id, bool issuer, const CUtensorMap* tma_c, const GemmEpiParams& ep) {
+                                  uint8_t* stg, int bar_id, bool issuer, const CUtensorMap* tma_c, const GemmEpiParams& ep,
+                                  const float* pf_next = nullptr, uint32_t pf_bytes = 0) {
   const int row = row0 + trow;
   const bool row_ok = row < M;
 
@@ -232,6 +305,21 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       const int2 rg = ep.row_range[ch];
       keep = (rr >= rg.x && rr < rg.y);
     }
+    // The residual is read straight from global memory by the thread that owns the row.  Two things keep enough bytes in
+    // flight for an HBM-bound K = 512 GEMM: the NEXT tile's residual rows are pulled into L2 with one bulk prefetch per
+    // row as soon as this tile's epilogue starts, and inside the tile the loads of round cc+1 are issued before round cc
+    // is consumed.
+    if (pf_next != nullptr && pf_bytes != 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf_next), "r"(pf_bytes) : "memory");
+    const bool has_res = ep.resid != nullptr && row_ok;
+    const float* rs_row = has_res ? ep.resid + (long long)row * ep.ld_resid : nullptr;
+    float4 xn[8];
+    auto load_resid = [&](int col0) {
+      const float4* rs = reinterpret_cast<const float4*>(rs_row + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) xn[q] = (col0 + 4 * q < N) ? rs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (has_res && gcol0 < N) load_resid(gcol0);
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {   // one 32-column fp32 sub-tile (128 B per row) per round
       const int col0 = gcol0 + cc * 32;
@@ -239,12 +327,9 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       uint32_t r[32];
       tmem_ld32(taddr + cc * 32, r);
       float4 x[8];
-      const bool has_res = ep.resid != nullptr && row_ok;
-      if (has_res) {
-        const float4* rs = reinterpret_cast<const float4*>(ep.resid + (long long)row * ep.ld_resid + col0);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) x[q] = (col0 + 4 * q < N) ? rs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int q = 0; q < 8; ++q) x[q] = xn[q];
+      if (has_res && cc < 3 && col0 + 32 < N) load_resid(col0 + 32);
       if (issuer) tma_store_wait_read();
       named_bar_sync(bar_id, 128);       // staging tile free again
       tmem_ld_wait();
@@ -331,24 +416,28 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, GemmEpiParams ep) {
+                    const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, int M, int N, int K,
+                    GemmEpiParams ep) {
   constexpr int BN = GEMM_BN;
   constexpr uint32_t A_BYTES = GEMM_BM * 128;
   constexpr uint32_t B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr int STAGES = gemm_stages(EPI);
+  constexpr int SLOTS = gemm_staging_slots(EPI);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align with pointer arithmetic (not an integer round trip) so the compiler keeps the shared address space (STS, not ST.E)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + GEMM_STAGES * A_BYTES;
-  uint8_t* sStage = sB + GEMM_STAGES * B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * GEMM_STAGING_BYTES);
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sStage = sB + STAGES * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + SLOTS * GEMM_STAGING_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
-  uint64_t* empty_bar = bars + GEMM_STAGES;      // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;  // [2]
+  uint64_t* empty_bar = bars + STAGES;      // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_full = tempty_bar + 2;            // [2 groups][2 slots]  (EPI_F32 with TMA residual)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -361,7 +450,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (EPI != EPI_ARGMAX) tma_prefetch_desc(&tma_c);
-    for (int s = 0; s < GEMM_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -369,6 +458,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 32 * GEMM_EPI_WARPS);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -389,7 +479,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
           tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -417,7 +507,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           umma_commit(&empty_bar[stage]);
           if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -428,8 +518,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int grp = ew >> 2;
     const bool issuer = ((ew & 3) == 0) && lane == 0;
     const int bar_id = 1 + grp;
-    uint8_t* stg = sStage + grp * GEMM_STAGING_BYTES;
+    uint8_t* stg = sStage + grp * (SLOTS / 2) * GEMM_STAGING_BYTES;
     const int trow = quad * 32 + lane;  // row inside the tile
+    const bool res_tma = (EPI == EPI_F32) && ep.resid_tma != 0;
+    uint32_t rc = 0;                    // rounds of this group so far (TMA-residual epilogue)
+    if (res_tma && issuer) {            // residual sub-tile of the very first round
+      int m0, n0;
+      if (gemm_tile_of(0, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m0, n0)) {
+        mbar_arrive_expect_tx(&res_full[grp * 2], GEMM_STAGING_BYTES);
+        tma_load_2d(stg, &tma_r, &res_full[grp * 2], n0 * BN + grp * 128, m0 * GEMM_BM);
+      }
+    }
     int pending_row0 = -1;              // row block whose stores are in flight and whose LayerNorm is still to do
     auto run_pending_ln = [&](bool last) {
       if (pending_row0 < 0) return;
@@ -449,8 +548,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + grp * 128;
-      gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * GEMM_BM, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg, bar_id,
-                                   issuer, &tma_c, ep);
+      const float* pf_next = nullptr;
+      uint32_t pf_bytes = 0;
+      if (EPI == EPI_F32 && ep.resid != nullptr && !res_tma) {
+        int m2, n2;
+        if (gemm_tile_of(it + 1, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m2, n2)) {
+          const int prow = m2 * GEMM_BM + trow, pcol = n2 * BN + grp * 128;
+          if (prow < M && pcol < N) { pf_next = ep.resid + (long long)prow * ep.ld_resid + pcol; pf_bytes = uint32_t(min(128, N - pcol)) * 4u; }
+        }
+      }
+      if (res_tma) {
+        int m2, n2, nrow0 = -1, ncol0 = 0;
+        if (gemm_tile_of(it + 1, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m2, n2)) { nrow0 = m2 * GEMM_BM; ncol0 = n2 * BN + grp * 128; }
+        gemm_epilogue_f32_tma(taddr, m_blk * GEMM_BM, trow, n_blk * BN + grp * 128, M, stg, bar_id, issuer, &tma_c, &tma_r, ep,
+                              &res_full[grp * 2], rc, nrow0, ncol0);
+      } else {
+        gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * GEMM_BM, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg, bar_id,
+                                     issuer, &tma_c, ep, pf_next, pf_bytes);
+      }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       if (EPI == EPI_F32 && block_major) {
@@ -476,8 +591,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 // CTAs arrive on the leader's "accumulator drained" barrier.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int GEMM2_STAGES = 6;
-constexpr size_t gemm2_smem_bytes() {
-  return size_t(GEMM2_STAGES) * (GEMM_BM * 128 + 128 * 128) + 2 * GEMM_STAGING_BYTES + 1024 + 256;
+__host__ __device__ constexpr int gemm2_stages(int epi) { return epi == 2 ? 5 : GEMM2_STAGES; }
+constexpr size_t gemm2_smem_bytes(int epi) {
+  return size_t(gemm2_stages(epi)) * (GEMM_BM * 128 + 128 * 128) + gemm_staging_slots(epi) * GEMM_STAGING_BYTES + 1024 + 256;
 }
 
 CF_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -522,7 +638,10 @@ CF_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
 template <int EPI, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, GemmEpiParams ep) {
+                     const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_r, int M, int N, int K,
+                     GemmEpiParams ep) {
+  constexpr int STAGES = gemm2_stages(EPI);
+  constexpr int SLOTS = gemm_staging_slots(EPI);
   constexpr int BN = GEMM_BN;                 // 256 accumulator columns per CTA
   constexpr uint32_t A_BYTES = GEMM_BM * 128; // this CTA's 128 rows of A
   constexpr uint32_t B_BYTES = 128 * 128;     // this CTA's 128 of the tile's 256 B rows
@@ -531,14 +650,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + GEMM2_STAGES * A_BYTES;
-  uint8_t* sStage = sB + GEMM2_STAGES * B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * GEMM_STAGING_BYTES);
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sStage = sB + STAGES * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + SLOTS * GEMM_STAGING_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]  (used in the leader CTA)
-  uint64_t* empty_bar = bars + GEMM2_STAGES;      // [STAGES]  (one per CTA)
-  uint64_t* tfull_bar = bars + 2 * GEMM2_STAGES;  // [2]       (one per CTA)
+  uint64_t* empty_bar = bars + STAGES;      // [STAGES]  (one per CTA)
+  uint64_t* tfull_bar = bars + 2 * STAGES;  // [2]       (one per CTA)
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]       (used in the leader CTA, 2 x 256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_full = tempty_bar + 2;            // [2 groups][2 slots]  (EPI_F32 with TMA residual; one set per CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -555,7 +675,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (EPI != EPI_ARGMAX) tma_prefetch_desc(&tma_c);
-    for (int s = 0; s < GEMM2_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -563,6 +683,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * 32 * GEMM_EPI_WARPS);
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
@@ -584,7 +705,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
           tma_load_2d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, m_blk * 256 + int(rank) * 128);
           tma_load_2d_2sm(sB + stage * B_BYTES, &tma_b, fb, kb * GEMM_BK, n_blk * BN + int(rank) * 128);
-          if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -609,7 +730,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           umma_commit_2sm(&empty_bar[stage]);
           if (kb == k_blocks - 1) umma_commit_2sm(&tfull_bar[acc]);
-          if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -620,8 +741,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const int grp = ew >> 2;
     const bool issuer = ((ew & 3) == 0) && lane == 0;
     const int bar_id = 1 + grp;
-    uint8_t* stg = sStage + grp * GEMM_STAGING_BYTES;
+    uint8_t* stg = sStage + grp * (SLOTS / 2) * GEMM_STAGING_BYTES;
     const int trow = quad * 32 + lane;
+    const bool res_tma = (EPI == EPI_F32) && ep.resid_tma != 0;
+    uint32_t rc = 0;
+    if (res_tma && issuer) {
+      int m0, n0;
+      if (gemm_tile_of(0, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m0, n0)) {
+        mbar_arrive_expect_tx(&res_full[grp * 2], GEMM_STAGING_BYTES);
+        tma_load_2d(stg, &tma_r, &res_full[grp * 2], n0 * BN + grp * 128, m0 * 256 + int(rank) * 128);
+      }
+    }
     int pending_row0 = -1;
     auto run_pending_ln = [&](bool last) {
       if (pending_row0 < 0) return;
@@ -640,8 +770,24 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + grp * 128;
-      gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * 256 + int(rank) * 128, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg,
-                                   bar_id, issuer, &tma_c, ep);
+      const float* pf_next = nullptr;
+      uint32_t pf_bytes = 0;
+      if (EPI == EPI_F32 && ep.resid != nullptr && !res_tma) {
+        int m2, n2;
+        if (gemm_tile_of(it + 1, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m2, n2)) {
+          const int prow = m2 * 256 + int(rank) * 128 + trow, pcol = n2 * BN + grp * 128;
+          if (prow < M && pcol < N) { pf_next = ep.resid + (long long)prow * ep.ld_resid + pcol; pf_bytes = uint32_t(min(128, N - pcol)) * 4u; }
+        }
+      }
+      if (res_tma) {
+        int m2, n2, nrow0 = -1, ncol0 = 0;
+        if (gemm_tile_of(it + 1, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m2, n2)) { nrow0 = m2 * 256 + int(rank) * 128; ncol0 = n2 * BN + grp * 128; }
+        gemm_epilogue_f32_tma(taddr, m_blk * 256 + int(rank) * 128, trow, n_blk * BN + grp * 128, M, stg, bar_id, issuer, &tma_c, &tma_r, ep,
+                              &res_full[grp * 2], rc, nrow0, ncol0);
+      } else {
+        gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * 256 + int(rank) * 128, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg,
+                                     bar_id, issuer, &tma_c, ep, pf_next, pf_bytes);
+      }
       tc_fence_before();
       mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
       if (EPI == EPI_F32 && block_major) {

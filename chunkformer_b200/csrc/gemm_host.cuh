@@ -76,7 +76,8 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
   // Measured on B200 (tools/bench_gemm_shapes.py): the pair kernel wins when the K loop dominates (K >= 1024: FFN w_2,
   // embed.out); for K = 512 the epilogue dominates and the 1-CTA kernel is faster. Small M: a 256-row tile is mostly padding.
   if (use2 < 0) use2 = (g.M >= 2048 && g.K >= 1024) ? 1 : 0;
-  CUtensorMap ta, tb, tc;
+  CUtensorMap ta, tb, tc, tr;
+  GemmEpiParams ep = g.ep;
   if (!make_tma_2d_bf16(&ta, g.A, g.M, g.K, g.lda, GEMM_BM, GEMM_BK, err)) return false;
   if (!make_tma_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, use2 ? 128 : GEMM_BN, GEMM_BK, err)) return false;
   if (EPI == EPI_ARGMAX) {
@@ -90,10 +91,18 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
     }
     if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
   }
+  tr = tc;
+  ep.resid_tma = 0;
+  // residual through TMA when every epilogue group of every tile has four full rounds and the pitch is TMA-legal
+  if (EPI == EPI_F32 && g.ep.resid != nullptr && g.N % GEMM_BN == 0 && (g.ep.ld_resid * 4) % 16 == 0 &&
+      (reinterpret_cast<uintptr_t>(g.ep.resid) & 15) == 0) {
+    if (!make_tma_2d(&tr, g.ep.resid, true, g.M, uint64_t(g.N), g.ep.ld_resid, GEMM_BM, 32, err)) return false;
+    ep.resid_tma = 1;
+  }
   if (use2) {
     auto kern2 = gemm2_tcgen05_kernel<EPI, ACT>;
     static bool attr2_set = false;
-    const size_t smem2 = gemm2_smem_bytes();
+    const size_t smem2 = gemm2_smem_bytes(EPI);
     if (!attr2_set) {
       cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2));
       if (e != cudaSuccess) {
@@ -106,7 +115,7 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
     if (tiles2 == 0) return true;
     int clusters = num_sms / 2;
     if (clusters > tiles2) clusters = tiles2;
-    kern2<<<2 * clusters, GEMM_THREADS, smem2, stream>>>(ta, tb, tc, g.M, g.N, g.K, g.ep);
+    kern2<<<2 * clusters, GEMM_THREADS, smem2, stream>>>(ta, tb, tc, tr, g.M, g.N, g.K, ep);
     ++g_kernel_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -117,7 +126,7 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
   }
   auto kern = gemm_tcgen05_kernel<EPI, ACT>;
   static bool attr_set = false;
-  const size_t smem = gemm_smem_bytes();
+  const size_t smem = gemm_smem_bytes(EPI);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) {
@@ -130,7 +139,7 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
   const int tiles = m_tiles * n_tiles;
   if (tiles == 0) return true;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, g.M, g.N, g.K, g.ep);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, tr, g.M, g.N, g.K, ep);
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -296,10 +296,11 @@ def test_attention_tcgen05_matches_generic_large():
     assert (a.float() - b.float()).abs().max().item() < 4e-2
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("d,c,cmvn", [(512, 64, False), (256, 16, True), (512, 8, True)])
 def test_frontend_conv0_dw1(impl, d, c, cmvn):
-    """conv0 + ReLU + depthwise conv1 (subsampling.py:70-92) on ragged chunks, CUDA-core and tcgen05 versions."""
+    """conv0 + ReLU + depthwise conv1 (subsampling.py:70-92) on ragged chunks: CUDA-core (0), position-major tcgen05 (1)
+    and channel-major tcgen05 (2) versions."""
     import ctypes
     from ctypes import POINTER, c_int32, c_int64
     L = cflib.load()
@@ -326,7 +327,7 @@ def test_frontend_conv0_dw1(impl, d, c, cmvn):
         x[k, :m] = feats[rows[k]: rows[k] + m]
     if cmvn:
         x = (x - mean) * istd
-    if impl == 1:
+    if impl >= 1:
         x = x.bfloat16().float()       # the tensor-core version rounds inputs and conv0 weights to bf16
         w0, b0 = w0.bfloat16().float(), b0.bfloat16().float()
     y = torch.relu(torch.nn.functional.conv2d(x.unsqueeze(1), w0, b0, stride=2))
