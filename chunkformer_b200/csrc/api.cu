@@ -22,6 +22,7 @@ using namespace cf;
 typedef __nv_bfloat16 bf16;
 
 static thread_local std::string g_last_error = "";
+static int g_attention_version = 1;   // tcgen05 attention kernel generation (1: 8 softmax warps, P through smem; 2: 16 warps, P in TMEM)
 static int g_fuse_layernorm = 0;   // LayerNorm fused behind the residual GEMMs: measured slower on B200 (85.3 vs 92.4 ms/step),
                                    // kept selectable for experiments (cf_set_fused_layernorm)
 
@@ -79,6 +80,8 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
 extern "C" long long cf_launch_count(void) { return cf::g_kernel_launches.load(); }
 extern "C" void cf_set_fused_layernorm(int on) { g_fuse_layernorm = on; }
 extern "C" void cf_set_gemm_variant(int v) { cf::gemm_variant_override() = v; }
+extern "C" void cf_debug_attention_trace(long long* device_buffer) { cf::attention_trace_buffer() = device_buffer; }
+extern "C" void cf_set_attention_version(int v) { g_attention_version = (v == 2) ? 2 : 1; }
 extern "C" const char* cf_version(void) { return "chunkformer_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cf_last_error(const cf_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
@@ -493,9 +496,9 @@ bool attention_tc_supported(int c, int l, int r, int dk) {
 bool run_attention(int impl, const AttnParams& p, cudaStream_t st, std::string* err) {
   if (p.n_chunks == 0) return true;
   const int dk = p.d / p.heads;
-  if (impl == 1) {
+  if (impl == 1 || impl == 2) {
     if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernel needs c=64, d_k=64, l,r multiples of 64, l+r<=256"; return false; }
-    return launch_attention_tc(p, st, err);
+    return launch_attention_tc(p, impl, st, err);
   }
   const int W = p.l + p.c + p.r;
   const size_t smem = size_t(4) * (2 * dk + W) * sizeof(float);
@@ -753,7 +756,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     { AttnParams a{};
       a.qkv = w.qkv; a.pos = pos->dev + size_t(i) * pos->Rpad * d; a.range = w.att_range; a.ctx = w.ctx;
       a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk)); a.prescaled = 1;
-      CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
+      CF_TRY(run_attention(use_tc ? g_attention_version : 0, a, st, &err)); }
     { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       if (fuse_ln) { e.ln_mode = 1; e.ln_y = w.y; e.ln1_w = lw.ln_conv_w; e.ln1_b = lw.ln_conv_b; e.ln_limit = p->mode == 1; }
       CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }

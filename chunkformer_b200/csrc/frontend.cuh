@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(fecm_threads<D>(), 1) frontend_conv0_dw1_cm_ke
   uint64_t* t_free = bars + 2 * FECM_STAGES + NWG;          // [NWG] warpgroup -> MMA (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * FECM_STAGES + 2 * NWG);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int upc = (total_units + gridDim.x - 1) / gridDim.x;
   const int u_begin = blockIdx.x * upc;
   const int u_end = min(total_units, u_begin + upc);
@@ -440,23 +440,29 @@ __global__ void __launch_bounds__(fecm_threads<D>(), 1) frontend_conv0_dw1_cm_ke
       (orow + (long long)(FECM_F2 - 1) * D)[odd] = __float2bfloat16(held);   // F2 = 19 is odd: the last output has no partner
     }
   } else if (warp == EPI_WARPS) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (convergent warp, elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      const uint64_t dw0 = make_nosw_desc(smem_u32(sW), 128, 256);
+      const uint64_t db0 = make_nosw_desc(smem_u32(sB), 128, 256);
       uint32_t it = 0;
       for (int u = u_begin; u < u_end; ++u, ++it) {
         const int s = it % FECM_STAGES;
         mbar_wait(&b_full[s], (it / FECM_STAGES) & 1);
         tc_fence_after();
-        const uint64_t db = make_nosw_desc(smem_u32(sB + s * 4096), 128, 256);
+        const uint64_t db = db0 + uint64_t((s * 4096) >> 4);
 #pragma unroll
         for (int g = 0; g < NWG; ++g) {
           mbar_wait(&t_free[g], (it & 1) ^ 1);
           tc_fence_after();
-          umma_bf16_ss(tmem_base + g * 128, make_nosw_desc(smem_u32(sW + g * 4096), 128, 256), db, idesc, 0);
-          umma_commit(&t_full[g]);
+          if (elect_one()) {
+            umma_bf16_ss(tmem_base + g * 128, dw0 + uint64_t((g * 4096) >> 4), db, idesc, 0);
+            umma_commit(&t_full[g]);
+          }
+          __syncwarp();
         }
-        umma_commit(&b_empty[s]);
+        if (elect_one()) umma_commit(&b_empty[s]);
+        __syncwarp();
       }
     }
   } else {

@@ -439,7 +439,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* res_full = tempty_bar + 2;            // [2 groups][2 slots]  (EPI_F32 with TMA residual)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: keeps the role branches convergent
   const int lane = threadIdx.x & 31;
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (N + BN - 1) / BN;
@@ -468,25 +468,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer (whole warp walks the ring, one elected lane issues)
+    {
       uint32_t stage = 0, phase = 0;
       for (int t = 0;; ++t) {
         int m_blk, n_blk;
         if (!gemm_tile_of(t, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-          tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+            tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------ MMA issuer: the whole warp walks the pipeline (convergent control flow,
+    // warp-uniform descriptors in uniform registers), one elected lane issues the tcgen05 instructions
+    {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+      const uint64_t da0 = make_sw128_desc(smem_u32(sA));
+      const uint64_t db0 = make_sw128_desc(smem_u32(sB));
       uint32_t stage = 0, phase = 0;
       for (int it = 0;; ++it) {
         int m_blk, n_blk;
@@ -498,15 +504,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
-          const uint64_t db = make_sw128_desc(smem_u32(sB + stage * B_BYTES));
+          if (elect_one()) {
+            const uint64_t da = da0 + uint64_t((stage * A_BYTES) >> 4);
+            const uint64_t db = db0 + uint64_t((stage * B_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 K-elements = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // advance 16 K-elements = 32 bytes inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -660,7 +669,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   uint64_t* res_full = tempty_bar + 2;            // [2 groups][2 slots]  (EPI_F32 with TMA residual; one set per CTA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -694,25 +703,30 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs; completion lands on the leader's barrier)
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       for (int t = 0;; ++t) {
         int m_blk, n_blk;
         if (!gemm_tile_of(t, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
-          const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, m_blk * 256 + int(rank) * 128);
-          tma_load_2d_2sm(sB + stage * B_BYTES, &tma_b, fb, kb * GEMM_BK, n_blk * BN + int(rank) * 128);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
+            const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, m_blk * 256 + int(rank) * 128);
+            tma_load_2d_2sm(sB + stage * B_BYTES, &tma_b, fb, kb * GEMM_BK, n_blk * BN + int(rank) * 128);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // ------------------------------------------------ MMA issuer (leader CTA only; convergent warp, elected lane issues)
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      const uint64_t da0 = make_sw128_desc(smem_u32(sA));
+      const uint64_t db0 = make_sw128_desc(smem_u32(sB));
       uint32_t stage = 0, phase = 0;
       for (int it = 0;; ++it) {
         int m_blk, n_blk;
@@ -724,12 +738,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_sw128_desc(smem_u32(sA + stage * A_BYTES));
-          const uint64_t db = make_sw128_desc(smem_u32(sB + stage * B_BYTES));
+          if (elect_one()) {
+            const uint64_t da = da0 + uint64_t((stage * A_BYTES) >> 4);
+            const uint64_t db = db0 + uint64_t((stage * B_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_2sm(&empty_bar[stage]);
-          if (kb == k_blocks - 1) umma_commit_2sm(&tfull_bar[acc]);
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == k_blocks - 1) umma_commit_2sm(&tfull_bar[acc]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -26,6 +26,8 @@ SIGNATURES = {
     "cf_version": (c_char_p, []),
     "cf_launch_count": (ctypes.c_longlong, []),
     "cf_set_gemm_variant": (None, [c_int]),
+    "cf_set_attention_version": (None, [c_int]),
+    "cf_debug_attention_trace": (None, [c_void_p]),
     "cf_set_fused_layernorm": (None, [c_int]),
     "cf_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),
     "cf_finalize_weights": (c_int, [c_void_p]),

@@ -65,6 +65,12 @@ CF_API const char* cf_version(void);
 CF_API long long cf_launch_count(void);
 /* Force the GEMM kernel variant: 0 = 1-CTA, 1 = 2-CTA pair (cta_group::2), -1 = choose by problem size (default). */
 CF_API void cf_set_gemm_variant(int variant);
+/* tcgen05 attention kernel generation used by cf_encode: 1 = 8 softmax warps, P through shared memory; 2 (default) = 16
+ * softmax warps, P kept in TMEM. */
+CF_API void cf_set_attention_version(int version);
+/* Debug: device buffer of 3 * 512 int64 that receives an SM-clock timeline of CTA 0 of the version-2 attention kernel
+ * (producer / MMA issuer / one softmax thread; see tools/attention_timeline.py); NULL switches it off. */
+CF_API void cf_debug_attention_trace(long long* device_buffer);
 /* 0 (default): LayerNorms run as separate HBM-roofline kernels; 1: fused behind the residual GEMMs (the epilogue warps
  * normalise the rows they just stored, out of L2) - measured slower on B200, kept for A/B measurements. */
 CF_API void cf_set_fused_layernorm(int on);

@@ -269,12 +269,15 @@ def test_attention_generic(c, l, r, d, H, n, prescaled):
 
 @pytest.mark.parametrize("l,r,n", [(128, 128, 7), (128, 128, 12), (64, 64, 5), (128, 0, 6), (0, 0, 3), (192, 64, 9)])
 @pytest.mark.parametrize("prescaled", [0, 1])
-def test_attention_tcgen05(l, r, n, prescaled):
-    """Chunk-pair tcgen05 kernel (c=64, d_k=64), odd and even chunk counts, several window shapes."""
-    _attention_case(1, 64, l, r, 512, 8, n, seed=3, prescaled=prescaled)
+@pytest.mark.parametrize("version", [1, 2])
+def test_attention_tcgen05(l, r, n, prescaled, version):
+    """Chunk-pair tcgen05 kernels (c=64, d_k=64; version 1 = P through smem, 2 = P in TMEM), odd and even chunk counts,
+    several window shapes."""
+    _attention_case(version, 64, l, r, 512, 8, n, seed=3, prescaled=prescaled)
 
 
-def test_attention_tcgen05_matches_generic_large():
+@pytest.mark.parametrize("version", [1, 2])
+def test_attention_tcgen05_matches_generic_large(version):
     L = cflib.load()
     c, l, r, d, H, n = 64, 128, 128, 512, 8, 301
     rows = l + n * c + r + 2 * c + 128
@@ -291,7 +294,7 @@ def test_attention_tcgen05_matches_generic_large():
     a = torch.zeros((n * c, d), device=DEV, dtype=torch.bfloat16)
     b = torch.zeros((n * c, d), device=DEV, dtype=torch.bfloat16)
     cflib.check(L.cf_op_attention(0, _p(qkv), _p(pos), _p(rng), _p(a), n, c, l, r, d, H, 0, _stream()))
-    cflib.check(L.cf_op_attention(1, _p(qkv), _p(pos), _p(rng), _p(b), n, c, l, r, d, H, 0, _stream()))
+    cflib.check(L.cf_op_attention(version, _p(qkv), _p(pos), _p(rng), _p(b), n, c, l, r, d, H, 0, _stream()))
     torch.cuda.synchronize()
     assert (a.float() - b.float()).abs().max().item() < 4e-2
 
