@@ -62,6 +62,9 @@ struct cf_handle {
   float* ctc_b = nullptr;
   float* zeros = nullptr;  // max(N) zero floats (bias-free GEMMs)
   std::vector<PosTable> pos_tables;
+  // feature-arrival events of the next cf_encode call (cf_encode_feature_events): rows < ev_rows[i] are present once ev[i] fires
+  std::vector<int64_t> ev_rows;
+  std::vector<cudaEvent_t> ev;
 };
 
 static int fail(cf_handle* h, int code, const std::string& msg) {
@@ -617,6 +620,14 @@ extern "C" size_t cf_workspace_bytes(const cf_handle* h, const cf_plan* p) {
 // --------------------------------------------------------------------------------------------------------------------
 // encoder driver
 // --------------------------------------------------------------------------------------------------------------------
+extern "C" int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_ready, void* const* events) {
+  if (!h || n < 0 || (n > 0 && (!rows_ready || !events))) return fail(h, CF_ERR_INVALID, "cf_encode_feature_events: bad argument");
+  h->ev_rows.assign(rows_ready, rows_ready + n);
+  h->ev.resize(n);
+  for (int i = 0; i < n; ++i) h->ev[i] = static_cast<cudaEvent_t>(events[i]);
+  return CF_OK;
+}
+
 extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, void* att_cache, void* cnn_cache,
                          int trunc, void* out, int out_dtype, void* out_bf16, void* workspace, size_t workspace_bytes,
                          void* stream) {
@@ -696,8 +707,18 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   {
     const int T2 = 2 * c + 1, F1 = (h->cfg.feat_dim - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1, F3 = h->F3;
     if (F2 < 16) return fail(h, CF_ERR_INVALID, "cf_encode: feat_dim too small for the front-end tiling");
+    size_t ev_next = 0;
     for (int g0 = 0; g0 < n; g0 += FE_SLAB_CHUNKS) {
       const int S = std::min(FE_SLAB_CHUNKS, n - g0);
+      if (!h->ev.empty()) {
+        // features may still be arriving on another stream: wait only for the rows this slab reads
+        long long need = 0;
+        for (int g = g0; g < g0 + S; ++g) need = std::max<long long>(need, p->chunk_feat_row[g] + std::max(p->chunk_in_len[g], 0));
+        while (ev_next < h->ev.size() && (ev_next == 0 || h->ev_rows[ev_next - 1] < need)) {
+          CF_CUDA(h, cudaStreamWaitEvent(st, h->ev[ev_next], 0));
+          ++ev_next;
+        }
+      }
       Fe1Params f1{};
       f1.feats = feats; f1.chunks = w.chunk_src + g0; f1.wpack = h->fe_wpack; f1.cmvn_mean = h->cmvn_mean; f1.cmvn_istd = h->cmvn_istd;
       f1.out = w.a1; f1.n_chunks = S; f1.feat_dim = h->cfg.feat_dim; f1.T2 = T2; f1.F2 = F2; f1.in_rows = p->in_rows;
@@ -720,6 +741,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(gemm(w.b2, (long long)F3 * d, h->fe_wout, (long long)F3 * d, (long long)S * c, d, F3 * d, EPI_F32, e3));
     }
   }
+
+  for (size_t i = 0; i < h->ev.size(); ++i) CF_CUDA(h, cudaStreamWaitEvent(st, h->ev[i], 0));   // (no-op for events already waited on)
+  h->ev.clear(); h->ev_rows.clear();
 
   // ---- layers (encoder_layer.py:155-248)
   auto ln = [&](int mode, const float* w1, const float* b1, const float* w2, const float* b2, float* xo, bf16* y,

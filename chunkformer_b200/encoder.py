@@ -43,6 +43,8 @@ class ChunkFormerEncoderB200:
         _lib.check(self._L.cf_finalize_weights(self._h), self._h, "cf_finalize_weights")
         self._ws: Optional[torch.Tensor] = None
         self._ctc_ws: Optional[torch.Tensor] = None
+        self._copy_stream = None
+        self._live_events = []
         # attributes the reference facade reads (chunkformer_model.py:344-389)
         self.num_blocks = geometry.layers
         self.attention_heads = geometry.heads
@@ -73,13 +75,43 @@ class ChunkFormerEncoderB200:
         return self._ws
 
     def _flat_feats(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
-        """Ragged utterances -> one flat device buffer [sum T_i, feat] (pinned host tensors copy asynchronously)."""
+        """Ragged utterances -> one flat device buffer [sum T_i, feat].
+
+        Host tensors are copied on a side stream in pieces of about 32 MB, each followed by an event that is handed to the
+        library (cf_encode_feature_events): the front-end of the following cf_encode starts on the first rows while the rest
+        of the batch is still crossing PCIe (pinned host tensors copy asynchronously; pageable ones are staged by the
+        driver).  Device tensors are copied on the current stream."""
         total = sum(int(x.shape[0]) for x in xs)
-        flat = torch.empty((total, self.geo.feat_dim), dtype=torch.float32, device=self.device)
+        F = self.geo.feat_dim
+        flat = torch.empty((total, F), dtype=torch.float32, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        cs.wait_stream(cur)                      # the block may have been used by work queued earlier on this stream
+        flat.record_stream(cs)
+        piece = max(1, (32 << 20) // (4 * F))    # rows per piece
+        rows_ready, events = [], []
         row = 0
-        for x in xs:
-            flat[row:row + x.shape[0]].copy_(x, non_blocking=True)
-            row += x.shape[0]
+        with torch.cuda.stream(cs):
+            for x in xs:
+                t = int(x.shape[0])
+                if x.dtype != torch.float32:
+                    x = x.float()
+                for a in range(0, t, piece):
+                    b = min(t, a + piece)
+                    flat[row + a:row + b].copy_(x[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    events.append(ev)
+                    rows_ready.append(row + b)
+                row += t
+        self._live_events = events               # keep the events alive until the next call
+        n = len(events)
+        if n:
+            rr = (c_int64 * n)(*rows_ready)
+            evp = (c_void_p * n)(*[c_void_p(e.cuda_event) for e in events])
+            _lib.check(self._L.cf_encode_feature_events(self._h, n, rr, evp), self._h, "cf_encode_feature_events")
         return flat
 
     def encode_plan(self, plan: Plan, feats: torch.Tensor, att_cache=None, cnn_cache=None, trunc: int = 0,

@@ -25,6 +25,7 @@ SIGNATURES = {
     "cf_last_error": (c_char_p, [c_void_p]),
     "cf_version": (c_char_p, []),
     "cf_launch_count": (ctypes.c_longlong, []),
+    "cf_encode_feature_events": (c_int, [c_void_p, c_int, POINTER(c_int64), POINTER(c_void_p)]),
     "cf_set_gemm_variant": (None, [c_int]),
     "cf_set_attention_version": (None, [c_int]),
     "cf_debug_attention_trace": (None, [c_void_p]),

@@ -64,6 +64,11 @@ CF_API const char* cf_version(void);
 /* Number of kernels this library has launched in the process so far (bench.py reports the per-step count). */
 CF_API long long cf_launch_count(void);
 /* Force the GEMM kernel variant: 0 = 1-CTA, 1 = 2-CTA pair (cta_group::2), -1 = choose by problem size (default). */
+/* Optional, before cf_encode: the feature buffer is still being filled by copies on another stream.  events[i] (cudaEvent_t)
+ * fires when feature rows < rows_ready[i] are in place (rows_ready ascending).  cf_encode makes its stream wait only for the
+ * rows each front-end slab reads, so the host-to-device copy overlaps the front-end; the list is consumed by that call.
+ * Replaces the reference's blocking xs.to(device) (chunkformer_model.py:395-401). */
+CF_API int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_ready, void* const* events);
 CF_API void cf_set_gemm_variant(int variant);
 /* tcgen05 attention kernel generation used by cf_encode: 1 = 8 softmax warps, P through shared memory; 2 (default) = 16
  * softmax warps, P kept in TMEM. */
