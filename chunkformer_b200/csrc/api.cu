@@ -728,9 +728,10 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       Fe2Params f2{};
       f2.in = w.b1; f2.out = w.a2; f2.w = h->fe_dw2_w; f2.bias = h->fe_dw2_b; f2.T2 = T2; f2.F2 = F2; f2.T3 = c; f2.F3 = F3;
       f2.total = (long long)S * c * F3 * (d / 8);
-      const unsigned g2 = unsigned((f2.total + 255) / 256);
-      if (d == 512) frontend_dw2_kernel<512><<<g2, 256, 0, st>>>(f2);
-      else frontend_dw2_kernel<256><<<g2, 256, 0, st>>>(f2);
+      const long long rows2 = (long long)S * c;                       // output time rows of the slab
+      const unsigned g2 = unsigned((rows2 * (d / 8) + 191) / 192);
+      if (d == 512) frontend_dw2_rows_kernel<512><<<g2, 192, 0, st>>>(f2, rows2);
+      else frontend_dw2_rows_kernel<256><<<g2, 192, 0, st>>>(f2, rows2);
       ++cf::g_kernel_launches;
       CF_CUDA(h, cudaGetLastError());
       EpiArgs e2; e2.bias = h->fe_b6; e2.out = w.b2; e2.ldo = d; e2.act = ACT_RELU;

@@ -573,4 +573,75 @@ __global__ void __launch_bounds__(256) frontend_dw2_kernel(Fe2Params p) {
       make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
 }
 
+
+// Row-walking version of depthwise conv2: thread = 8 channels of one output time row (chunk, t3); it keeps its 72 taps in
+// registers and slides a 3x3 window of 16-byte vectors across the row's F2 input columns, so every input vector is
+// loaded once per thread (6.3 loads per output instead of 9) and the taps are loaded once per row instead of once per
+// output (the per-output tap loads were most of the L1 traffic of the kernel above).
+template <int D>
+__global__ void __launch_bounds__(192, 2) frontend_dw2_rows_kernel(Fe2Params p, long long total_rows) {
+  constexpr int G = D / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_rows * G) return;
+  const int cg = int(idx % G);
+  const long long orow = idx / G;                 // chunk * T3 + t3
+  const int t3 = int(orow % p.T3);
+  const long long chunk = orow / p.T3;
+  float w[9][8], bias[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.w + t * D + cg * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.w + t * D + cg * 8 + 4));
+    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
+  }
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias + cg * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cg * 8 + 4));
+    bias[0] = a.x; bias[1] = a.y; bias[2] = a.z; bias[3] = a.w; bias[4] = b.x; bias[5] = b.y; bias[6] = b.z; bias[7] = b.w;
+  }
+  const __nv_bfloat16* in0 = p.in + ((chunk * p.T2 + 2 * t3) * p.F2) * D + cg * 8;   // input row 2*t3, column 0
+  const long long rstride = (long long)p.F2 * D;                                      // one input time row
+  __nv_bfloat16* out = p.out + (orow * p.F3) * D + cg * 8;
+  uint4 win[3][3];                                                                   // [input row a][column slot]
+  uint4 nxt[3][2];                                                                   // the two new columns of the next output
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    win[a][2] = __ldg(reinterpret_cast<const uint4*>(in0 + a * rstride));
+    nxt[a][0] = __ldg(reinterpret_cast<const uint4*>(in0 + a * rstride + D));
+    nxt[a][1] = __ldg(reinterpret_cast<const uint4*>(in0 + a * rstride + 2 * D));
+  }
+#pragma unroll 1
+  for (int f3 = 0; f3 < p.F3; ++f3) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      win[a][0] = win[a][2];
+      win[a][1] = nxt[a][0];
+      win[a][2] = nxt[a][1];
+    }
+    if (f3 + 1 < p.F3) {                          // loads of the next output fly while this one is computed
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        nxt[a][0] = __ldg(reinterpret_cast<const uint4*>(in0 + a * rstride + (long long)(2 * f3 + 3) * D));
+        nxt[a][1] = __ldg(reinterpret_cast<const uint4*>(in0 + a * rstride + (long long)(2 * f3 + 4) * D));
+      }
+    }
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias[e];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const uint4 v = win[a][b];
+        const float* ww = w[a * 3 + b];
+        acc[0] = fmaf(ww[0], bf16_lo(v.x), acc[0]); acc[1] = fmaf(ww[1], bf16_hi(v.x), acc[1]);
+        acc[2] = fmaf(ww[2], bf16_lo(v.y), acc[2]); acc[3] = fmaf(ww[3], bf16_hi(v.y), acc[3]);
+        acc[4] = fmaf(ww[4], bf16_lo(v.z), acc[4]); acc[5] = fmaf(ww[5], bf16_hi(v.z), acc[5]);
+        acc[6] = fmaf(ww[6], bf16_lo(v.w), acc[6]); acc[7] = fmaf(ww[7], bf16_hi(v.w), acc[7]);
+      }
+    *reinterpret_cast<uint4*>(out + (long long)f3 * D) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
 }  // namespace cf

@@ -55,8 +55,10 @@ constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr uint32_t GEMM_STAGING_BYTES = 128 * 128;  // 128 rows x 128 bytes, one per epilogue group
 
-// The fp32 + residual epilogue double-buffers its staging tiles (the residual sub-tile of the next round is TMA-loaded into
-// one while the other is processed and stored) and gives up one pipeline stage for them.
+// The fp32 epilogues double-buffer their staging tiles (a round fills one slot while the TMA store of the previous round still
+// drains the other; with a residual, the residual sub-tile of the next round is TMA-loaded into the free slot) and give up one
+// pipeline stage for them.  The bf16 epilogues keep four stages and one slot per group: measured on B200, trading the fourth
+// stage for a second slot makes the K = 512 GEMMs 10 % slower (FFN w_1 306 -> 336 us).
 __host__ __device__ constexpr int gemm_stages(int epi) { return epi == 2 /*EPI_F32*/ ? 3 : GEMM_STAGES; }
 __host__ __device__ constexpr int gemm_staging_slots(int epi) { return epi == 2 ? 4 : 2; }
 constexpr size_t gemm_smem_bytes(int epi) {
@@ -250,8 +252,10 @@ CF_DEVINL void gemm_epilogue_f32_tma(uint32_t taddr, int row0, int trow, int gco
 //   gcol0 : first global accumulator column of the slab;  stg : the group's 16 KB staging tile
 template <int EPI, int ACT>
 CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0, int n_blk, int grp, int n_tiles, int M, int N,
-                                  uint8_t* stg, int bar_id, bool issuer, const CUtensorMap* tma_c, const GemmEpiParams& ep,
-                                  const float* pf_next = nullptr, uint32_t pf_bytes = 0) {
+                                  uint8_t* stg2, int bar_id, bool issuer, const CUtensorMap* tma_c, const GemmEpiParams& ep,
+                                  uint32_t& rc, const float* pf_next = nullptr, uint32_t pf_bytes = 0) {
+  // stg2: the group's staging slots (two for EPI_F32, one otherwise), used alternately (rc counts the group's store rounds);
+  // with two slots only the store that used the slot two rounds ago has to be drained before it is refilled
   const int row = row0 + trow;
   const bool row_ok = row < M;
 
@@ -330,8 +334,10 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
 #pragma unroll
       for (int q = 0; q < 8; ++q) x[q] = xn[q];
       if (has_res && cc < 3 && col0 + 32 < N) load_resid(col0 + 32);
-      if (issuer) tma_store_wait_read();
-      named_bar_sync(bar_id, 128);       // staging tile free again
+      constexpr uint32_t SLOT_MASK = gemm_staging_slots(EPI) / 2 - 1;
+      uint8_t* stg = stg2 + (rc++ & SLOT_MASK) * GEMM_STAGING_BYTES;
+      if (issuer) { if (SLOT_MASK) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else tma_store_wait_read(); }
+      named_bar_sync(bar_id, 128);       // staging slot free again
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -358,7 +364,9 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
     for (int rd = 0; rd < ROUNDS; ++rd) {
       const int acol0 = gcol0 + rd * 64;       // accumulator column of this round (EPI_BF16)
       if (acol0 >= N) break;
-      if (issuer) tma_store_wait_read();
+      constexpr uint32_t SLOT_MASK = gemm_staging_slots(EPI) / 2 - 1;
+      uint8_t* stg = stg2 + (rc++ & SLOT_MASK) * GEMM_STAGING_BYTES;
+      if (issuer) { if (SLOT_MASK) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else tma_store_wait_read(); }
       named_bar_sync(bar_id, 128);
 #pragma unroll
       for (int cc = 0; cc < CH_PER_ROUND; ++cc) {
@@ -573,7 +581,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                               &res_full[grp * 2], rc, nrow0, ncol0);
       } else {
         gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * GEMM_BM, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg, bar_id,
-                                     issuer, &tma_c, ep, pf_next, pf_bytes);
+                                     issuer, &tma_c, ep, rc, pf_next, pf_bytes);
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
@@ -803,7 +811,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                               &res_full[grp * 2], rc, nrow0, ncol0);
       } else {
         gemm_epilogue_slab<EPI, ACT>(taddr, m_blk * 256 + int(rank) * 128, trow, n_blk * BN + grp * 128, n_blk, grp, n_tiles, M, N, stg,
-                                     bar_id, issuer, &tma_c, ep, pf_next, pf_bytes);
+                                     bar_id, issuer, &tma_c, ep, rc, pf_next, pf_bytes);
       }
       tc_fence_before();
       mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));

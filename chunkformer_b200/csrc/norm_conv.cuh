@@ -1,5 +1,7 @@
 // Bandwidth-bound kernels of the encoder layer: LayerNorm variants and the chunk-aware depthwise-conv core.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -245,6 +247,7 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
   uint8_t* s_in = dw_smem;                        // [2 stages][HALVES][ROWS][256 ch] bf16
   uint64_t* full = reinterpret_cast<uint64_t*>(s_in + 2 * STAGE_BYTES);
   __shared__ float s_part2[2][NW][FG];   // double-buffered by iteration parity: no barrier needed at the end of a group
+  __shared__ float s_partq2[2][NW][FG];
   __shared__ float s_mean2[2][FG];
   __shared__ float s_rstd2[2][FG];
 
@@ -294,43 +297,73 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
 
     unsigned long long o[FG];
     unsigned long long win[KW];
+    auto conv = [&](auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-    for (int t = 0; t < KW - 1; ++t) {
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(src + t * 512);
-      const bool ok = (f0 + t >= rg.x) && (f0 + t < rg.y);
-      win[t] = ok ? pack_f32x2(bf16_lo(v), bf16_hi(v)) : 0ull;
-    }
-#pragma unroll
-    for (int f = 0; f < FG; ++f) {
-      {
-        const int t = f + KW - 1;
+      for (int t = 0; t < KW - 1; ++t) {
         const uint32_t v = *reinterpret_cast<const uint32_t*>(src + t * 512);
-        const bool ok = (f0 + t >= rg.x) && (f0 + t < rg.y);
-        win[(f + KW - 1) % KW] = ok ? pack_f32x2(bf16_lo(v), bf16_hi(v)) : 0ull;
+        const bool ok = !MASKED || ((f0 + t >= rg.x) && (f0 + t < rg.y));
+        win[t] = ok ? pack_f32x2(bf16_lo(v), bf16_hi(v)) : 0ull;
       }
-      unsigned long long acc = bias2;
 #pragma unroll
-      for (int t = 0; t < KW; ++t) acc = ffma2(w[t], win[(f + t) % KW], acc);
-      o[f] = acc;
-    }
-    // LayerNorm over the D channels of every frame (two-pass), then SiLU
-    float ps[FG];
+      for (int f = 0; f < FG; ++f) {
+        {
+          const int t = f + KW - 1;
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + t * 512);
+          const bool ok = !MASKED || ((f0 + t >= rg.x) && (f0 + t < rg.y));
+          win[(f + KW - 1) % KW] = ok ? pack_f32x2(bf16_lo(v), bf16_hi(v)) : 0ull;
+        }
+        unsigned long long acc = bias2;
 #pragma unroll
-    for (int f = 0; f < FG; ++f) ps[f] = f32x2_lo(o[f]) + f32x2_hi(o[f]);
-    frame_reduce<FG, NW>(ps, s_part, s_mean, 1.0f / D, false);
+        for (int t = 0; t < KW; ++t) acc = ffma2(w[t], win[(f + t) % KW], acc);
+        o[f] = acc;
+      }
+    };
+    // groups whose 46 window slots are all valid (the bulk of a long utterance) skip the per-row mask tests
+    if (f0 >= rg.x && f0 + ROWS <= rg.y) conv(std::false_type{}); else conv(std::true_type{});
+
+    // LayerNorm over the D channels of every frame: sum and sum of squares reduced together (one barrier pair), then SiLU
+    float ps[FG], pq[FG];
 #pragma unroll
     for (int f = 0; f < FG; ++f) {
-      const float m = s_mean[f];
-      const float d0 = f32x2_lo(o[f]) - m, d1 = f32x2_hi(o[f]) - m;
-      ps[f] = d0 * d0 + d1 * d1;
+      const float lo = f32x2_lo(o[f]), hi = f32x2_hi(o[f]);
+      ps[f] = lo + hi;
+      pq[f] = fmaf(lo, lo, hi * hi);
     }
-    frame_reduce<FG, NW>(ps, s_part, s_rstd, 1.0f / D, true);
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float s1 = up ? ps[i] : ps[i + off], k1 = up ? ps[i + off] : ps[i];
+          const float s2 = up ? pq[i] : pq[i + off], k2 = up ? pq[i + off] : pq[i];
+          ps[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, off);
+          pq[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, off);
+        }
+      }
+      s_part[warp][lane] = ps[0];
+      s_partq2[stage][warp][lane] = pq[0];
+      __syncthreads();
+      if (tid < FG) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) { a += s_part[w2][tid]; q += s_partq2[stage][w2][tid]; }
+        const float mean = a * (1.0f / D);
+        const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
+        s_mean[tid] = mean;
+        s_rstd[tid] = rsqrtf(var + 1e-5f);
+      }
+      __syncthreads();
+    }
     uint32_t* zp = reinterpret_cast<uint32_t*>(p.z) + ((long long)chunk * p.c + f0) * (D / 2) + tid;
 #pragma unroll
     for (int f = 0; f < FG; ++f) {
       const float mean = s_mean[f], rstd = s_rstd[f];
-      const float y0 = (f32x2_lo(o[f]) - mean) * rstd * lw0 + lb0;
-      const float y1 = (f32x2_hi(o[f]) - mean) * rstd * lw1 + lb1;
+      const float a0 = rstd * lw0, a1 = rstd * lw1;
+      const float y0 = fmaf(f32x2_lo(o[f]), a0, fmaf(-mean, a0, lb0));
+      const float y1 = fmaf(f32x2_hi(o[f]), a1, fmaf(-mean, a1, lb1));
       zp[(long long)f * (D / 2)] = pack_bf16(silu_fast(y0), silu_fast(y1));
     }
   }
