@@ -49,11 +49,19 @@ def path_flops_per_chunk(geo, c, l, r):
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture (profiles/r01_ncu_gemm_ffn1_full.csv); None if the summary is absent."""
+    capture (profiles/r01_ncu_gemm_ffn1_full.csv, first profiled launch); None if the summary is absent."""
     try:
-        tot = 0.0
+        tot, seen = 0.0, 0
         for line in open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_ffn1_full.csv")):
-            name, unit, val = line.strip().split(",", 2)
+            if line.startswith("#"):
+                seen += 1
+                if seen > 1:
+                    break
+                continue
+            parts = line.strip().split(",", 2)
+            if len(parts) != 3:
+                continue
+            name, unit, val = parts
             if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(val) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
         return tot or None
@@ -213,6 +221,8 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = Llib.cf_launch_count()
+    if rank == 0:
+        Llib.cf_gemm_timing_begin(cflib.EPI_BF16, cflib.ACT_SILU)    # CUDA events around every FFN w_1 launch of the timed steps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -223,6 +233,12 @@ def main():
     ev1.record()
     barrier()
     launches = Llib.cf_launch_count() - launches0
+    dom_ms, dom_n = 0.0, 0
+    if rank == 0:
+        import ctypes
+        tot_ms, n_l = ctypes.c_double(0.0), ctypes.c_int(0)
+        cflib.check(Llib.cf_gemm_timing_end(ctypes.byref(tot_ms), ctypes.byref(n_l)), None, "cf_gemm_timing_end")
+        dom_ms, dom_n = float(tot_ms.value), int(n_l.value)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -245,12 +261,27 @@ def main():
     h2d = int(sum(x.numel() * 4 for x in xs_host))
     d2h = int(tok_host.numel() * tok_host.element_size())
 
-    # ---- roofline of the dominant kernel: the FFN up-projection GEMM (tcgen05, bf16 -> fp32 accumulate, SiLU epilogue)
+    # ---- roofline of the dominant kernel family: the FFN up-projection GEMM (tcgen05, bf16 -> fp32 accumulate, SiLU epilogue;
+    # 34 launches per step).  `achieved` = algorithmic flops per launch / average launch duration measured with CUDA events on
+    # the launching stream inside the timed steps above; the denominator is therefore the SUSTAINED measured bf16 peak (the
+    # kernel runs inside a long, power-capped step).  The same kernel timed alone (best single launch) is given against the
+    # burst peak for reference.
     rows = plan.rows
     roofline = None
     if rank == 0:
         from ctypes import c_void_p
         d, F = geo.d_model, geo.ffn
+        flops = 2.0 * rows * d * F
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        burst = float(peaks.get("bf16_tflops", 1590.0))
+        k_ms = dom_ms / max(dom_n, 1)
+        achieved = flops / (k_ms * 1e-3) / 1e12 if dom_n else None
+        # the same kernel alone: best of 10 individually timed launches (burst methodology of MEASURED_PEAKS.json)
         A = torch.randn((rows, d), device=dev).bfloat16()
         Wt = (torch.randn((F, d), device=dev) / d ** 0.5).bfloat16()
         bias = torch.zeros(F, device=dev)
@@ -265,29 +296,24 @@ def main():
         for _ in range(3):
             ffn1()
         torch.cuda.synchronize()
-        reps = 10
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            ffn1()
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        flops = 2.0 * rows * d * F
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("bf16_tflops", 1590.0))
-        achieved = flops / (k_ms * 1e-3) / 1e12
+        alone = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ffn1(); e1.record()
+            torch.cuda.synchronize()
+            alone.append(e0.elapsed_time(e1))
+            time.sleep(0.02)
+        best_alone = min(alone)
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EPI_BF16, ACT_SILU> (FFN w_1 + SiLU, M=%d N=%d K=%d)" % (rows, F, d),
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s",
-                    "traffic": ncu_traffic_bytes(), "ms_per_launch": k_ms,
+                    "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": (achieved / sustained) if achieved else None,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the timed steps, %d launches)" % dom_n)
+                    if peaks else "fallback 1.4 PFLOP/s sustained",
+                    "traffic": ncu_traffic_bytes(), "ms_per_launch": k_ms, "launches_timed": dom_n,
+                    "flops_per_launch": flops,
+                    "alone": {"ms_best_of_10": best_alone, "achieved": flops / (best_alone * 1e-3) / 1e12, "peak": burst,
+                              "frac": flops / (best_alone * 1e-3) / 1e12 / burst, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"},
                     "path_tflops": path_flops_per_chunk(geo, C, L, R) * plan.n * args.steps * world / (ms_total * 1e-3) / 1e12,
                     "path_frac_of_sustained": None}
-        sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
         roofline["path_frac_of_sustained"] = roofline["path_tflops"] / (sustained * world)
 
     cpu_base = None

@@ -83,6 +83,26 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
 extern "C" long long cf_launch_count(void) { return cf::g_kernel_launches.load(); }
 extern "C" void cf_set_fused_layernorm(int on) { g_fuse_layernorm = on; }
 extern "C" void cf_set_gemm_variant(int v) { cf::gemm_variant_override() = v; }
+extern "C" void cf_gemm_timing_begin(int epi, int act) {
+  cf::GemmTiming& t = cf::gemm_timing();
+  t.select = (epi < 0) ? -1 : epi * 16 + act;
+  t.used = 0;
+}
+extern "C" int cf_gemm_timing_end(double* total_ms, int* launches) {
+  cf::GemmTiming& t = cf::gemm_timing();
+  t.select = -1;
+  double tot = 0.0;
+  for (size_t i = 0; i < t.used; ++i) {
+    if (cudaEventSynchronize(t.pool[i].second) != cudaSuccess) return CF_ERR_CUDA;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.pool[i].first, t.pool[i].second) != cudaSuccess) return CF_ERR_CUDA;
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = int(t.used);
+  t.used = 0;
+  return CF_OK;
+}
 extern "C" void cf_debug_attention_trace(long long* device_buffer) { cf::attention_trace_buffer() = device_buffer; }
 extern "C" void cf_set_attention_version(int v) { g_attention_version = (v == 2) ? 2 : 1; }
 extern "C" const char* cf_version(void) { return "chunkformer_b200 0.1.0 (sm_100a)"; }

@@ -31,6 +31,7 @@ struct GemmEpiParams {
   const int2* row_range = nullptr;  // EPI_F32: row valid iff range[row / rows_per_chunk].x <= row % rows_per_chunk < .y
   int rows_per_chunk = 1;
   int resid_tma = 0;             // EPI_F32: residual sub-tiles are TMA-loaded into the staging tiles (set by launch_gemm)
+  int debug = 0;                 // tools only (CF_GEMM_DEBUG): 1 = epilogue does nothing, 2 = no loads / MMAs (timing ablations)
   float* part_best = nullptr;    // EPI_ARGMAX: [M, 2 * n_tiles]
   float* part_second = nullptr;
   int* part_index = nullptr;
@@ -464,7 +465,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 32 * GEMM_EPI_WARPS);
+      mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);      // one arrival per epilogue warp
     }
     for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     fence_barrier_init();
@@ -482,7 +483,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int t = 0;; ++t) {
         int m_blk, n_blk;
         if (!gemm_tile_of(t, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < k_blocks && !(ep.debug & 2); ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -509,6 +510,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        if (ep.debug & 2) {
+          if (elect_one()) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
+          continue;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -574,7 +580,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (prow < M && pcol < N) { pf_next = ep.resid + (long long)prow * ep.ld_resid + pcol; pf_bytes = uint32_t(min(128, N - pcol)) * 4u; }
         }
       }
-      if (res_tma) {
+      if (ep.debug & 1) {
+      } else if (res_tma) {
         int m2, n2, nrow0 = -1, ncol0 = 0;
         if (gemm_tile_of(it + 1, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m2, n2)) { nrow0 = m2 * GEMM_BM; ncol0 = n2 * BN + grp * 128; }
         gemm_epilogue_f32_tma(taddr, m_blk * GEMM_BM, trow, n_blk * BN + grp * 128, M, stg, bar_id, issuer, &tma_c, &tma_r, ep,
@@ -584,7 +591,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                      issuer, &tma_c, ep, rc, pf_next, pf_bytes);
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (EPI == EPI_F32 && block_major) {
         run_pending_ln(false);
         if (n_blk == n_tiles - 1) pending_row0 = m_blk * GEMM_BM;
@@ -698,7 +706,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 2 * 32 * GEMM_EPI_WARPS);
+      mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);  // one (remote) arrival per epilogue warp of either CTA
     }
     for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     fence_barrier_init();
@@ -716,7 +724,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       for (int t = 0;; ++t) {
         int m_blk, n_blk;
         if (!gemm_tile_of(t, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < k_blocks && !(ep.debug & 2); ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
@@ -743,6 +751,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        if (ep.debug & 2) {
+          if (elect_one()) umma_commit_2sm(&tfull_bar[acc]);
+          __syncwarp();
+          continue;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -804,7 +817,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           if (prow < M && pcol < N) { pf_next = ep.resid + (long long)prow * ep.ld_resid + pcol; pf_bytes = uint32_t(min(128, N - pcol)) * 4u; }
         }
       }
-      if (res_tma) {
+      if (ep.debug & 1) {
+      } else if (res_tma) {
         int m2, n2, nrow0 = -1, ncol0 = 0;
         if (gemm_tile_of(it + 1, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m2, n2)) { nrow0 = m2 * 256 + int(rank) * 128; ncol0 = n2 * BN + grp * 128; }
         gemm_epilogue_f32_tma(taddr, m_blk * 256 + int(rank) * 128, trow, n_blk * BN + grp * 128, M, stg, bar_id, issuer, &tma_c, &tma_r, ep,
@@ -814,7 +828,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                                      bar_id, issuer, &tma_c, ep, rc, pf_next, pf_bytes);
       }
       tc_fence_before();
-      mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
       if (EPI == EPI_F32 && block_major) {
         run_pending_ln(false);
         if (n_blk == n_tiles - 1) pending_row0 = m_blk * 256 + int(rank) * 128;

@@ -4,8 +4,11 @@
 #include <cudaTypedefs.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "gemm.cuh"
 
@@ -67,6 +70,15 @@ struct GemmLaunch {
   GemmEpiParams ep;
 };
 
+// Optional event timing of one GEMM family inside a real step (bench.py roofline: average duration of the dominant kernel
+// over the timed region, on the launching stream).  timing_select(): epi * 16 + act of the family to time, or -1 = off.
+struct GemmTiming {
+  int select = -1;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  size_t used = 0;
+};
+inline GemmTiming& gemm_timing() { static GemmTiming t; return t; }
+
 // 0 = 1-CTA kernel, 1 = 2-CTA (cta_group::2) kernel; set by launch_gemm from the problem size / CF_GEMM_2CTA.
 inline int& gemm_variant_override() { static int v = -1; return v; }
 
@@ -93,6 +105,7 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
   }
   tr = tc;
   ep.resid_tma = 0;
+  { const char* dbg = getenv("CF_GEMM_DEBUG"); ep.debug = dbg ? atoi(dbg) : 0; }
   // residual through TMA when every epilogue group of every tile has four full rounds and the pitch is TMA-legal
   if (EPI == EPI_F32 && g.ep.resid != nullptr && g.N % GEMM_BN == 0 && (g.ep.ld_resid * 4) % 16 == 0 &&
       (reinterpret_cast<uintptr_t>(g.ep.resid) & 15) == 0) {
@@ -115,7 +128,14 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
     if (tiles2 == 0) return true;
     int clusters = num_sms / 2;
     if (clusters > tiles2) clusters = tiles2;
+    GemmTiming& tm2 = gemm_timing();
+    const bool timed2 = tm2.select == EPI * 16 + ACT;
+    if (timed2) {
+      if (tm2.used == tm2.pool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); tm2.pool.push_back({a, b}); }
+      cudaEventRecord(tm2.pool[tm2.used].first, stream);
+    }
     kern2<<<2 * clusters, GEMM_THREADS, smem2, stream>>>(ta, tb, tc, tr, g.M, g.N, g.K, ep);
+    if (timed2) cudaEventRecord(tm2.pool[tm2.used++].second, stream);
     ++g_kernel_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -139,7 +159,14 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
   const int tiles = m_tiles * n_tiles;
   if (tiles == 0) return true;
   const int grid = tiles < num_sms ? tiles : num_sms;
+  GemmTiming& tm = gemm_timing();
+  const bool timed = tm.select == EPI * 16 + ACT;
+  if (timed) {
+    if (tm.used == tm.pool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); tm.pool.push_back({a, b}); }
+    cudaEventRecord(tm.pool[tm.used].first, stream);
+  }
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, tr, g.M, g.N, g.K, ep);
+  if (timed) cudaEventRecord(tm.pool[tm.used++].second, stream);
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

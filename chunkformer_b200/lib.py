@@ -28,6 +28,8 @@ SIGNATURES = {
     "cf_encode_feature_events": (c_int, [c_void_p, c_int, POINTER(c_int64), POINTER(c_void_p)]),
     "cf_set_gemm_variant": (None, [c_int]),
     "cf_set_attention_version": (None, [c_int]),
+    "cf_gemm_timing_begin": (None, [c_int, c_int]),
+    "cf_gemm_timing_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int)]),
     "cf_debug_attention_trace": (None, [c_void_p]),
     "cf_set_fused_layernorm": (None, [c_int]),
     "cf_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),

@@ -70,6 +70,11 @@ CF_API long long cf_launch_count(void);
  * Replaces the reference's blocking xs.to(device) (chunkformer_model.py:395-401). */
 CF_API int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_ready, void* const* events);
 CF_API void cf_set_gemm_variant(int variant);
+/* Measurement: CUDA events around every launch of one GEMM family (epilogue kind `epi`, activation `act`; the FFN
+ * up-projection is CF_EPI_BF16 + SiLU) on the launching stream, from cf_gemm_timing_begin until cf_gemm_timing_end, which
+ * returns the summed device time and the number of launches (bench.py: roofline of the dominant kernel inside real steps). */
+CF_API void cf_gemm_timing_begin(int epi, int act);
+CF_API int cf_gemm_timing_end(double* total_ms, int* launches);
 /* tcgen05 attention kernel generation used by cf_encode: 1 = 8 softmax warps, P through shared memory; 2 (default) = 16
  * softmax warps, P kept in TMEM. */
 CF_API void cf_set_attention_version(int version);
