@@ -513,14 +513,15 @@ bool run_frontend_conv(int impl, int d, const Fe1Params& f1, int num_sms, cudaSt
 }
 
 bool attention_tc_supported(int c, int l, int r, int dk) {
-  return c == 64 && dk == 64 && (l % 64) == 0 && (r % 64) == 0 && (l + r) <= 256;
+  return c == 64 && (dk == 64 || dk == 128) && (l % 64) == 0 && (r % 64) == 0 && (l + r) <= 256;
 }
 
 bool run_attention(int impl, const AttnParams& p, cudaStream_t st, std::string* err) {
   if (p.n_chunks == 0) return true;
   const int dk = p.d / p.heads;
   if (impl == 1 || impl == 2) {
-    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernel needs c=64, d_k=64, l,r multiples of 64, l+r<=256"; return false; }
+    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernels need c=64, d_k=64 or 128, l,r multiples of 64, l+r<=256"; return false; }
+    if (dk == 128) return launch_attention_tc128(p, st, err);
     return launch_attention_tc(p, impl, st, err);
   }
   const int W = p.l + p.c + p.r;

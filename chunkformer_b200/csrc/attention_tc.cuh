@@ -746,6 +746,371 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// d_k = 128 variant (chunkformer-rnnt-large / classification geometry: d = 512, H = 4), chunk 64, l / r multiples of 64.
+// Same chunk-pair tiling, but a head row is twice as wide, so per item the operands no longer fit beside a resident position
+// table: keys go in blocks of 64 (S_ac N = 64, S_bd N = 192), the projected position table streams through a ring of four
+// 64-row chunks (block b reads chunks b, b+1, b+2; only chunk b+2 is new), K is double-buffered, V single-buffered, every
+// operand has its own full / empty barrier pair and one polling thread issues each TMA load the moment its buffer is free.
+// P never touches shared memory (TMEM columns [384, 416), A operand of the P V MMAs).
+// TMEM map: S_ac [0,64)  S_bd [64,256)  O [256,384)  P [384,416).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int ATC128_THREADS = 320;
+constexpr uint32_t ATC128_ATOM = 64 * 128;          // 64 rows x 64 bf16
+constexpr size_t ATC128_SMEM_BYTES = 4 * 2 * ATC128_ATOM /*Qu, Qv: 2 atoms x 128 rows*/ + 2 * 2 * ATC128_ATOM /*K x2 stages*/ +
+                                     2 * ATC128_ATOM /*V*/ + 4 * 2 * ATC128_ATOM /*table ring*/ + 256 * ATC_STAGE_PITCH +
+                                     2048 + 1024 + 256 + 1024;
+
+template <bool PRE>
+__global__ void __launch_bounds__(ATC128_THREADS, 1)
+attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/, const __grid_constant__ CUtensorMap tma_kv /*box 64 x 64*/,
+                       const __grid_constant__ CUtensorMap tma_pos /*box 64 x 64*/, AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_qu = smem;                                 // [2 atoms][128 rows x 128 B]
+  uint8_t* s_qv = s_qu + 4 * ATC128_ATOM;
+  uint8_t* s_k = s_qv + 4 * ATC128_ATOM;                // [2 stages][2 atoms][64 keys x 128 B]
+  uint8_t* s_v = s_k + 4 * ATC128_ATOM;                 // [2 atoms][64 keys x 128 B]   (MN-major B operand)
+  uint8_t* s_pt = s_v + 2 * ATC128_ATOM;                // [4 slots][2 atoms][64 table rows x 128 B]
+  uint8_t* s_stage = s_pt + 8 * ATC128_ATOM;            // 256 thread-private skew rows
+  float* s_xch = reinterpret_cast<float*>(s_stage + 256 * ATC_STAGE_PITCH);   // [2 parity][2 set][128] row maxima
+  float* s_lx = s_xch + 512;                                                   // [2 set][128] row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lx + 256);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;     // [2]
+  uint64_t* k_empty = bars + 4;    // [2]
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* pt_full = bars + 8;    // [4]
+  uint64_t* pt_empty = bars + 12;  // [4]
+  uint64_t* s_full = bars + 16;
+  uint64_t* s_free = bars + 17;
+  uint64_t* p_full = bars + 18;
+  uint64_t* pv_done = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int h = blockIdx.x % p.heads;
+  const int first_pair = blockIdx.x / p.heads;
+  const int d = p.d;
+  const int nb = p.nb;                                  // key blocks of 64 union slots
+  const int nch = nb + 2;                               // table chunks per item
+  const int stride = p.items_per_cta_stride;
+  const int n_items = first_pair < p.n_pairs ? (p.n_pairs - first_pair + stride - 1) / stride : 0;
+  const uint32_t total = uint32_t(n_items) * uint32_t(nb);
+  const uint32_t total_ch = uint32_t(n_items) * uint32_t(nch);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    tma_prefetch_desc(&tma_pos);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(&pt_full[s], 1); mbar_init(&pt_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 8);
+    mbar_init(p_full, 8);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_AC = 0, TM_BD = 64, TM_O = 256, TM_P = 384;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: four streams polled by one thread
+    if (elect_one()) {
+      uint32_t kb = 0, vb = 0, cb = 0;
+      int qi = 0;
+      while (kb < total || vb < total || cb < total_ch || qi < n_items) {
+        bool issued = false;
+        if (qi < n_items && mbar_test(q_empty, (qi & 1) ^ 1)) {
+          const int row = p.l + 128 * (first_pair + qi * stride);
+          mbar_arrive_expect_tx(q_full, 8 * ATC128_ATOM);
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            tma_load_2d(s_qu + a * 2 * ATC128_ATOM, &tma_q, q_full, h * 128 + 64 * a, row);
+            tma_load_2d(s_qv + a * 2 * ATC128_ATOM, &tma_q, q_full, d + h * 128 + 64 * a, row);
+          }
+          ++qi; issued = true;
+        }
+        if (kb < total && mbar_test(&k_empty[kb & 1], ((kb >> 1) & 1) ^ 1)) {
+          const int it = int(kb) / nb, b = int(kb) - it * nb;
+          const int row = 128 * (first_pair + it * stride) + 64 * b;
+          mbar_arrive_expect_tx(&k_full[kb & 1], 2 * ATC128_ATOM);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+            tma_load_2d(s_k + ((kb & 1) * 2 + a) * ATC128_ATOM, &tma_kv, &k_full[kb & 1], 2 * d + h * 128 + 64 * a, row);
+          ++kb; issued = true;
+        }
+        if (cb < total_ch && mbar_test(&pt_empty[cb & 3], ((cb >> 2) & 1) ^ 1)) {
+          const int ct = int(cb % uint32_t(nch));           // chunk ct = table rows [64 ct - 64, 64 ct)
+          mbar_arrive_expect_tx(&pt_full[cb & 3], 2 * ATC128_ATOM);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+            tma_load_2d(s_pt + ((cb & 3) * 2 + a) * ATC128_ATOM, &tma_pos, &pt_full[cb & 3], h * 128 + 64 * a, 64 * ct - 64);
+          ++cb; issued = true;
+        }
+        if (vb < total && mbar_test(v_empty, (vb & 1) ^ 1)) {
+          const int it = int(vb) / nb, b = int(vb) - it * nb;
+          const int row = 128 * (first_pair + it * stride) + 64 * b;
+          mbar_arrive_expect_tx(v_full, 2 * ATC128_ATOM);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+            tma_load_2d(s_v + a * ATC128_ATOM, &tma_kv, v_full, 3 * d + h * 128 + 64 * a, row);
+          ++vb; issued = true;
+        }
+        if (!issued) __nanosleep(64);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (convergent warp, elected lane issues)
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // A = P from TMEM, B (= V) MN-major
+    const uint64_t dqu = make_sw128_desc(smem_u32(s_qu)), dqv = make_sw128_desc(smem_u32(s_qv));
+    const uint64_t dk0 = make_sw128_desc(smem_u32(s_k)), dv0 = make_sw128_desc(smem_u32(s_v)), dpt0 = make_sw128_desc(smem_u32(s_pt));
+    auto issue_pv = [&](uint32_t pblk, uint32_t pb) {
+      mbar_wait(v_full, pblk & 1);
+      mbar_wait(p_full, pblk & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)          // 16 keys per step: 8 packed P columns; V: 16 key rows = 2048 B inside an atom
+#pragma unroll
+          for (int hn = 0; hn < 2; ++hn)
+            umma_bf16_ts(tmem_base + TM_O + 64 * hn, tmem_base + TM_P + 8 * t, dv0 + uint64_t((hn * ATC128_ATOM + t * 2048) >> 4),
+                         idesc_pv, (pb | uint32_t(t)) != 0);
+        umma_commit(pv_done);
+        umma_commit(v_empty);
+      }
+      __syncwarp();
+    };
+    uint32_t blk = 0, ch0 = 0;                            // ch0: global index of the item's chunk 0
+    for (int item = 0; item < n_items; ++item, ch0 += uint32_t(nch)) {
+      mbar_wait(q_full, item & 1);
+      for (int b = 0; b < nb; ++b, ++blk) {
+        const uint32_t st = blk & 1;
+        const int nchunks = (b == nb - 1) ? 2 : 3;        // the last block never needs table rows >= 64 (nb + 1) - 64
+        mbar_wait(&k_full[st], (blk >> 1) & 1);
+        for (int j = (b == 0 ? 0 : 2); j < 3; ++j) {     // chunks b, b+1 were waited for by the previous block; the item's last
+          const uint32_t gc = ch0 + uint32_t(b + j);     // chunk is not read but must have landed before its slot is released
+          mbar_wait(&pt_full[gc & 3], (gc >> 2) & 1);
+        }
+        mbar_wait(s_free, (blk & 1) ^ 1);                 // softmax finished reading the previous S block
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + TM_AC, dqu + uint64_t((a * 2 * ATC128_ATOM) >> 4) + 2 * k,
+                           dk0 + uint64_t(((st * 2 + a) * ATC128_ATOM) >> 4) + 2 * k, idesc_s, (a | k) != 0);
+          for (int j = 0; j < nchunks; ++j) {
+            const uint32_t slot = (ch0 + uint32_t(b + j)) & 3;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(tmem_base + TM_BD + 64 * j, dqv + uint64_t((a * 2 * ATC128_ATOM) >> 4) + 2 * k,
+                             dpt0 + uint64_t(((slot * 2 + a) * ATC128_ATOM) >> 4) + 2 * k, idesc_s, (a | k) != 0);
+          }
+          umma_commit(s_full);
+          umma_commit(&k_empty[st]);
+          umma_commit(&pt_empty[(ch0 + uint32_t(b)) & 3]);      // chunk b is not read by later blocks
+          if (b == nb - 1) {
+            umma_commit(&pt_empty[(ch0 + uint32_t(b + 1)) & 3]);  // ... nor are the item's last chunks
+            umma_commit(&pt_empty[(ch0 + uint32_t(b + 2)) & 3]);
+            umma_commit(q_empty);
+          }
+        }
+        __syncwarp();
+        if (blk > 0) issue_pv(blk - 1, uint32_t(b == 0 ? nb - 1 : b - 1));
+      }
+    }
+    if (total > 0) issue_pv(total - 1, uint32_t(nb - 1));
+  } else {
+    // ------------------------------------------------------------------ softmax warps: thread = (query row, 32 of the block's 64 keys)
+    const int sw = warp - 2;
+    const int quad = warp & 3;
+    const int set = sw >> 2;
+    const int rho = quad * 32 + lane;
+    const int half = rho >> 6, qi = rho & 63;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    uint8_t* stage = s_stage + (threadIdx.x - 64) * ATC_STAGE_PITCH;
+    const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
+    const int cbw = 96 - 32 * quad + 32 * set;          // first S_bd column this warp stages (warp-uniform)
+    uint32_t blk = 0;
+    int ep_g = -1;
+    float ep_l = 0.f;
+    auto write_out = [&]() {                            // O / l -> ctx: this thread's 64 of the head's 128 output columns
+      const float l_tot = ep_l + s_lx[(set ^ 1) * 128 + rho];
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;      // no valid key: zero context (attention.py:133-136)
+      __nv_bfloat16* orow = p.ctx + ((long long)ep_g * 64 + qi) * d + h * 128 + 64 * set;
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_addr + TM_O + 64 * set + 32 * hc, r);
+        tmem_ld_wait();
+        if (ep_g < p.n_chunks) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint32_t o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = pack_bf16(__uint_as_float(r[16 * q + 2 * e]) * inv, __uint_as_float(r[16 * q + 2 * e + 1]) * inv);
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + 32 * hc + 16 * q), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                         : "memory");
+          }
+        }
+      }
+      ep_g = -1;
+    };
+    for (int pair = first_pair; pair < p.n_pairs; pair += stride) {
+      const int g = 2 * pair + half;
+      const int2 rg = p.range[g];
+      const int ulo = rg.x + 64 * half, uhi = rg.y + 64 * half;   // valid union slots for this row
+      float m_run = -1e30f, l_run = 0.f;
+      for (int b = 0; b < nb; ++b, ++blk) {
+        mbar_wait(s_full, blk & 1);
+        tc_fence_after();
+        float s[32];
+        float mx = -1e30f;
+        {
+          const float sc = PRE ? 1.0f : p.scale_log2e;
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            uint32_t rb[32];
+            tmem_ld32(tmem_base + lane_addr + TM_BD + cbw + 32 * hb, rb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w0;
+              w0.x = pack_half2(__uint_as_float(rb[8 * q]) * sc, __uint_as_float(rb[8 * q + 1]) * sc);
+              w0.y = pack_half2(__uint_as_float(rb[8 * q + 2]) * sc, __uint_as_float(rb[8 * q + 3]) * sc);
+              w0.z = pack_half2(__uint_as_float(rb[8 * q + 4]) * sc, __uint_as_float(rb[8 * q + 5]) * sc);
+              w0.w = pack_half2(__uint_as_float(rb[8 * q + 6]) * sc, __uint_as_float(rb[8 * q + 7]) * sc);
+              *reinterpret_cast<uint4*>(stage + 64 * hb + 16 * q) = w0;
+            }
+          }
+          uint32_t ra[32];
+          tmem_ld32(tmem_base + lane_addr + TM_AC + 32 * set, ra);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);            // this warp's part of S is in registers / shared memory
+          const int u0 = 64 * b + 32 * set;
+          const bool edge = (u0 < ulo) || (u0 + 32 > uhi);
+          if (__any_sync(0xffffffffu, edge)) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int uq = u0 + k;
+              float v = PRE ? __uint_as_float(ra[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(ra[k]), p.scale_log2e, __half2float(stage_rd[k]));
+              v = (uq >= ulo && uq < uhi) ? v : -INFINITY;
+              s[k] = v;
+              mx = fmaxf(mx, v);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float v = PRE ? __uint_as_float(ra[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(ra[k]), p.scale_log2e, __half2float(stage_rd[k]));
+              s[k] = v;
+              mx = fmaxf(mx, v);
+            }
+          }
+        }
+        float* xch = s_xch + (blk & 1) * 256;
+        xch[set * 128 + rho] = mx;
+        named_bar_sync(1, 256);
+        const float m_new = fmaxf(m_run, fmaxf(mx, xch[(set ^ 1) * 128 + rho]));
+        const float alpha = fast_exp2(m_run - m_new);
+        float sum = 0.f;
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = fast_exp2(s[2 * e] - m_new), p1 = fast_exp2(s[2 * e + 1] - m_new);
+          sum += p0 + p1;
+          pk[e] = pack_bf16(p0, p1);
+        }
+        l_run = l_run * alpha + sum;
+        m_run = m_new;
+        if (blk > 0) mbar_wait(pv_done, (blk - 1) & 1);   // previous P V retired: the P columns and O are ours again
+        tc_fence_after();
+        if (ep_g >= 0) write_out();                      // previous item (its row sums were published before the barrier above)
+        tmem_st16(tmem_base + lane_addr + TM_P + 16 * set, pk);
+        if (b > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale this thread's 64 columns of the running output
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_addr + TM_O + 64 * set + 32 * hc, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+            tmem_st32(tmem_base + lane_addr + TM_O + 64 * set + 32 * hc, r);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      s_lx[set * 128 + rho] = l_run;                     // read by the partner thread after the next named barrier
+      ep_g = g; ep_l = l_run;
+    }
+    if (ep_g >= 0) {
+      named_bar_sync(1, 256);
+      mbar_wait(pv_done, (blk - 1) & 1);
+      tc_fence_after();
+      write_out();
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+inline bool launch_attention_tc128(const AttnParams& a, cudaStream_t st, std::string* err) {
+  const int W = a.l + a.c + a.r;
+  const int U = W + 64;
+  const int R = 2 * a.c + a.l + a.r - 1;
+  const int Rpad = ((R + 127) / 128) * 128;
+  AttnTcParams p{};
+  p.range = a.range; p.ctx = a.ctx; p.n_chunks = a.n_chunks; p.n_pairs = (a.n_chunks + 1) / 2; p.l = a.l; p.d = a.d;
+  p.heads = a.heads; p.nb = U / 64; p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.trace = nullptr; p.experiment = 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_head = sms / a.heads;
+  if (per_head < 1) per_head = 1;
+  if (per_head > p.n_pairs) per_head = p.n_pairs;
+  p.items_per_cta_stride = per_head;
+  const uint64_t qkv_rows = uint64_t(a.l) + uint64_t(a.n_chunks) * 64 + uint64_t(a.r) + 2 * 64 + 128;
+  CUtensorMap tq, tk, tp;
+  if (!make_tma_2d_bf16(&tq, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 128, 64, err)) return false;
+  if (!make_tma_2d_bf16(&tk, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 64, 64, err)) return false;
+  if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 64, 64, err)) return false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC128_SMEM_BYTES));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC128_SMEM_BYTES));
+    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(attention_tc128): ") + cudaGetErrorString(e); return false; }
+    attr_set = true;
+  }
+  if (a.prescaled) attention_tc128_kernel<true><<<per_head * a.heads, ATC128_THREADS, ATC128_SMEM_BYTES, st>>>(tq, tk, tp, p);
+  else attention_tc128_kernel<false><<<per_head * a.heads, ATC128_THREADS, ATC128_SMEM_BYTES, st>>>(tq, tk, tp, p);
+  ++g_kernel_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { if (err) *err = std::string("attention_tc128 launch: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+
 inline bool launch_attention_tc(const AttnParams& a, int version, cudaStream_t st, std::string* err) {
   const int W = a.l + a.c + a.r;
   const int U = W + 64;

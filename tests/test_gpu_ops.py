@@ -276,6 +276,35 @@ def test_attention_tcgen05(l, r, n, prescaled, version):
     _attention_case(version, 64, l, r, 512, 8, n, seed=3, prescaled=prescaled)
 
 
+@pytest.mark.parametrize("l,r,n", [(128, 128, 7), (128, 128, 12), (64, 64, 5), (128, 0, 6), (0, 0, 3), (192, 64, 9)])
+@pytest.mark.parametrize("prescaled", [0, 1])
+def test_attention_tcgen05_dk128(l, r, n, prescaled):
+    """d_k = 128 chunk-pair tcgen05 kernel (rnnt-large / classification geometry: d 512, 4 heads)."""
+    _attention_case(1, 64, l, r, 512, 4, n, seed=4, prescaled=prescaled)
+
+
+def test_attention_tcgen05_dk128_matches_generic_large():
+    L = cflib.load()
+    c, l, r, d, H, n = 64, 128, 128, 512, 4, 301
+    rows = l + n * c + r + 2 * c + 128
+    qkv = torch.zeros((rows, 4 * d), device=DEV, dtype=torch.bfloat16)
+    qkv[: l + n * c] = _rand((l + n * c, 4 * d), 1.0, 5).bfloat16()
+    R = 2 * c + l + r - 1
+    pos = torch.zeros(((R + 127) // 128 * 128, d), device=DEV, dtype=torch.bfloat16)
+    pos[:R] = _rand((R, d), 1.0, 6).bfloat16()
+    rng = torch.zeros((n + 2, 2), dtype=torch.int32)
+    rng[:n, 1] = l + c + r
+    rng[0, 0] = l
+    rng[n - 1, 1] = l + 40
+    rng = rng.to(DEV)
+    a = torch.zeros((n * c, d), device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros((n * c, d), device=DEV, dtype=torch.bfloat16)
+    cflib.check(L.cf_op_attention(0, _p(qkv), _p(pos), _p(rng), _p(a), n, c, l, r, d, H, 0, _stream()))
+    cflib.check(L.cf_op_attention(1, _p(qkv), _p(pos), _p(rng), _p(b), n, c, l, r, d, H, 0, _stream()))
+    torch.cuda.synchronize()
+    assert (a.float() - b.float()).abs().max().item() < 4e-2
+
+
 @pytest.mark.parametrize("version", [1, 2])
 def test_attention_tcgen05_matches_generic_large(version):
     L = cflib.load()
