@@ -513,16 +513,22 @@ bool run_frontend_conv(int impl, int d, const Fe1Params& f1, int num_sms, cudaSt
 }
 
 bool attention_tc_supported(int c, int l, int r, int dk) {
-  return c == 64 && (dk == 64 || dk == 128) && (l % 64) == 0 && (r % 64) == 0 && (l + r) <= 256;
+  if (l < 0 || r < 0 || l + r > 256) return false;
+  if (dk == 128) return c == 64 && (l % 64) == 0 && (r % 64) == 0;
+  if (dk != 64 || !(c == 8 || c == 16 || c == 32 || c == 64)) return false;
+  // tile = 128 / c chunks, key blocks of 128 union slots; the resident table slice holds 448 rows
+  const int W = l + c + r, nb = (l + 128 + r + 127) / 128;
+  const int n_last = (W - 128 * (nb - 1) <= 65) ? 192 : 256;
+  return 128 * (nb - 1) + n_last <= 448;
 }
 
 bool run_attention(int impl, const AttnParams& p, cudaStream_t st, std::string* err) {
   if (p.n_chunks == 0) return true;
   const int dk = p.d / p.heads;
   if (impl == 1 || impl == 2) {
-    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernels need c=64, d_k=64 or 128, l,r multiples of 64, l+r<=256"; return false; }
+    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernels need d_k=64 with c in {8,16,32,64} or d_k=128 with c=64, and l+r<=256"; return false; }
     if (dk == 128) return launch_attention_tc128(p, st, err);
-    return launch_attention_tc(p, impl, st, err);
+    return launch_attention_tc(p, (impl == 2 && p.c == 64 && p.l % 64 == 0 && p.r % 64 == 0) ? 2 : 1, st, err);
   }
   const int W = p.l + p.c + p.r;
   const size_t smem = size_t(4) * (2 * dk + W) * sizeof(float);
@@ -570,7 +576,7 @@ EncodeWs carve_encode(const cf_handle* h, const cf_plan* p, void* base) {
   EncodeWs w;
   Carver cv(base);
   w.chunk_src = cv.take<ChunkSrc>(n);
-  w.att_range = cv.take<int2>(n + 2);
+  w.att_range = cv.take<int2>(n + 16);
   w.conv_range = cv.take<int2>(n);
   w.out_range = cv.take<int2>(n);
   w.seq_limit = cv.take<int>(size_t(p->B));
@@ -681,15 +687,14 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   // ---- tables
   {
     std::vector<ChunkSrc> cs(n);
-    std::vector<int2> ar(n + 2), cr(n), orr(n);
+    std::vector<int2> ar(n + 16, make_int2(0, 0)), cr(n), orr(n);   // phantom chunks of the last attention tile stay empty
     for (int g = 0; g < n; ++g) {
       cs[g].feat_row = p->chunk_feat_row[g]; cs[g].in_len = p->chunk_in_len[g]; cs[g].pad_ = 0;
       const cf_chunk_entry& e = p->chunks[g];
       ar[g] = make_int2(e.att_lo, e.att_hi); cr[g] = make_int2(e.conv_lo, e.conv_hi); orr[g] = make_int2(e.out_lo, e.out_hi);
     }
-    ar[n] = ar[n + 1] = make_int2(0, 0);   // phantom chunks read by the chunk-pair attention kernel
     CF_CUDA(h, cudaMemcpyAsync(w.chunk_src, cs.data(), n * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaMemcpyAsync(w.att_range, ar.data(), (n + 2) * sizeof(int2), cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaMemcpyAsync(w.att_range, ar.data(), (n + 16) * sizeof(int2), cudaMemcpyHostToDevice, st));
     CF_CUDA(h, cudaMemcpyAsync(w.conv_range, cr.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
     CF_CUDA(h, cudaMemcpyAsync(w.out_range, orr.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
     if (p->mode == 1)

@@ -53,7 +53,8 @@ inline long long*& attention_trace_buffer() { static long long* b = nullptr; ret
 struct AttnTcParams {
   const int2* range;      // [n_chunks + 2] valid key slots per chunk (entries beyond n_chunks are empty)
   __nv_bfloat16* ctx;     // [n_chunks * 64, d]
-  int n_chunks, n_pairs, l, d, heads, nb;   // nb = key blocks of 128 union slots
+  int n_chunks, n_pairs, l, d, heads, nb;   // n_pairs = tiles of 128 query rows; nb = key blocks of 128 union slots
+  int c_log2, tab_row0, n_last;              // chunk size (log2); first resident table row (c - 128); S_bd columns of the last block
   int items_per_cta_stride;                  // CTAs per head
   float scale_log2e;
   int experiment;         // debug bit mask (CF_ATTN_EXPERIMENT): 1 skip ctx stores, 2 skip skew reads, 4 skip exp
@@ -118,18 +119,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     {
       if (elect_one()) {
         mbar_arrive_expect_tx(ptab_full, ATC_PTAB_BYTES);
-        for (int i = 0; i < 7; ++i)                                            // table rows -64 .. 383 (rows < 0 read as 0)
-          tma_load_2d(s_ptab + i * 64 * 128, &tma_pos, ptab_full, h * 64, -64 + 64 * i);
+        for (int i = 0; i < 7; ++i)                                            // table rows c-128 .. c+319 (rows < 0 read as 0)
+          tma_load_2d(s_ptab + i * 64 * 128, &tma_pos, ptab_full, h * 64, p.tab_row0 + 64 * i);
       }
       __syncwarp();
       uint32_t item = 0, blk = 0;
       for (int pair = first_pair; pair < p.n_pairs; pair += p.items_per_cta_stride, ++item) {
-        const int g0 = 2 * pair;
+        const int trow = 128 * pair;                 // first flat row of the tile = first buffer row of its union key window
         mbar_wait(q_empty, (item & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(q_full, 2 * ATC_TILE_BYTES);
-          tma_load_2d(s_qu, &tma_qkv, q_full, h * 64, p.l + 64 * g0);
-          tma_load_2d(s_qv, &tma_qkv, q_full, d + h * 64, p.l + 64 * g0);
+          tma_load_2d(s_qu, &tma_qkv, q_full, h * 64, p.l + trow);
+          tma_load_2d(s_qv, &tma_qkv, q_full, d + h * 64, p.l + trow);
         }
         __syncwarp();
         for (int b = 0; b < nb; ++b, ++blk) {
@@ -137,8 +138,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
           mbar_wait(&kv_empty[st], ph ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&kv_full[st], 2 * ATC_TILE_BYTES);
-            tma_load_2d(s_k + st * ATC_TILE_BYTES, &tma_qkv, &kv_full[st], 2 * d + h * 64, 64 * g0 + 128 * b);
-            tma_load_2d(s_v + st * ATC_TILE_BYTES, &tma_qkv, &kv_full[st], 3 * d + h * 64, 64 * g0 + 128 * b);
+            tma_load_2d(s_k + st * ATC_TILE_BYTES, &tma_qkv, &kv_full[st], 2 * d + h * 64, trow + 128 * b);
+            tma_load_2d(s_v + st * ATC_TILE_BYTES, &tma_qkv, &kv_full[st], 3 * d + h * 64, trow + 128 * b);
           }
           __syncwarp();
         }
@@ -149,7 +150,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     {
       constexpr uint32_t idesc_ac = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_bd = make_idesc_bf16(128, 256);
-      constexpr uint32_t idesc_bd_last = make_idesc_bf16(128, 192);   // the last block never needs table rows >= 384
+      const uint32_t idesc_bd_last = p.n_last == 192 ? make_idesc_bf16(128, 192) : make_idesc_bf16(128, 256);   // 192: the last block never reads resident table rows >= 448
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
       mbar_wait(ptab_full, 0);
       const uint64_t dqu = make_sw128_desc(smem_u32(s_qu)), dqv = make_sw128_desc(smem_u32(s_qv));
@@ -206,7 +207,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
     const int set = sw >> 2;
     const int rho = quad * 32 + lane;
-    const int half = rho >> 6, qi = rho & 63;
+    const int cj = rho >> p.c_log2;                    // chunk of this row inside the tile
+    const int uoff = cj << p.c_log2;                   // its window starts at this union slot
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     uint8_t* stage = s_stage + (threadIdx.x - 64) * ATC_STAGE_PITCH;
     const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
@@ -214,6 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     uint8_t* pp_row = s_pp + set * ATC_TILE_BYTES + rho * 128;
     uint32_t blk = 0;
     int ep_g = -1;                                     // chunk (of this row) whose item is finished but not yet written out
+    long long ep_row0 = 0;                             // first flat row of that item's tile
     float ep_l = 0.f;
     // O / l -> ctx for the finished item (this set writes 32 of the head's 64 output columns).  Called once the item's
     // last P V has retired and before this thread lets the next item's first P V start, so it costs no extra wait.
@@ -224,7 +227,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       tmem_ld32(tmem_base + lane_addr + TM_O + 32 * set, r);
       tmem_ld_wait();
       if (ep_g < p.n_chunks) {
-        __nv_bfloat16* orow = p.ctx + ((long long)ep_g * 64 + qi) * d + h * 64 + 32 * set;
+        __nv_bfloat16* orow = p.ctx + ((long long)ep_row0 + rho) * d + h * 64 + 32 * set;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint32_t o[8];
@@ -238,9 +241,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       ep_g = -1;
     };
     for (int pair = first_pair; pair < p.n_pairs; pair += p.items_per_cta_stride) {
-      const int g = 2 * pair + half;
+      const int g = (pair << (7 - p.c_log2)) + cj;
       const int2 rg = p.range[g];
-      const int ulo = rg.x + 64 * half, uhi = rg.y + 64 * half;   // valid union slots for this row
+      const int ulo = rg.x + uoff, uhi = rg.y + uoff;   // valid union slots for this row
       float m_run = -1e30f, l_run = 0.f;
       for (int b = 0; b < nb; ++b, ++blk) {
         mbar_wait(s_full, blk & 1);
@@ -343,7 +346,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       // ---- item finished: publish the row sum (read by the partner thread after the next named barrier) and defer the
       // output to the next block's P V wait
       s_lx[set * 128 + rho] = l_run;
-      ep_g = g; ep_l = l_run;
+      ep_g = g; ep_l = l_run; ep_row0 = 128LL * pair;
     }
     if (ep_g >= 0) {
       named_bar_sync(1, 256);
@@ -1112,13 +1115,19 @@ inline bool launch_attention_tc128(const AttnParams& a, cudaStream_t st, std::st
 }
 
 inline bool launch_attention_tc(const AttnParams& a, int version, cudaStream_t st, std::string* err) {
+  // tile = 128 query rows = 128 / c consecutive chunks; their union key window has l + 128 + r slots
   const int W = a.l + a.c + a.r;
-  const int U = W + 64;
+  const int U = a.l + 128 + a.r;
   const int R = 2 * a.c + a.l + a.r - 1;
   const int Rpad = ((R + 127) / 128) * 128;
+  int c_log2 = 0;
+  while ((1 << c_log2) < a.c) ++c_log2;
+  const int cpt = 128 / a.c;
   AttnTcParams p{};
-  p.range = a.range; p.ctx = a.ctx; p.n_chunks = a.n_chunks; p.n_pairs = (a.n_chunks + 1) / 2; p.l = a.l; p.d = a.d;
+  p.range = a.range; p.ctx = a.ctx; p.n_chunks = a.n_chunks; p.n_pairs = (a.n_chunks + cpt - 1) / cpt; p.l = a.l; p.d = a.d;
   p.heads = a.heads; p.nb = (U + 127) / 128; p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.c_log2 = c_log2; p.tab_row0 = a.c - 128;
+  p.n_last = (W - 128 * (p.nb - 1) <= 65) ? 192 : 256;   // widest S_bd column a valid score of the last block can need
   p.trace = attention_trace_buffer();
   { const char* ex = getenv("CF_ATTN_EXPERIMENT"); p.experiment = ex ? atoi(ex) : 0; }
   int dev = 0, sms = 148;
@@ -1129,7 +1138,7 @@ inline bool launch_attention_tc(const AttnParams& a, int version, cudaStream_t s
   if (per_head > p.n_pairs) per_head = p.n_pairs;
   p.items_per_cta_stride = per_head;
   // tensor maps: flat QKV buffer [rows, 4d] (box 128 rows x 64 cols) and this layer's position table [Rpad, d] (box 64 x 64)
-  const uint64_t qkv_rows = uint64_t(a.l) + uint64_t(a.n_chunks) * 64 + uint64_t(a.r) + 2 * 64 + 128;
+  const uint64_t qkv_rows = uint64_t(a.l) + uint64_t(a.n_chunks) * a.c + uint64_t(a.r) + 2 * a.c + 128;
   CUtensorMap tq, tp;
   if (!make_tma_2d_bf16(&tq, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 128, 64, err)) return false;
   if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 64, 64, err)) return false;

@@ -229,7 +229,7 @@ def _attention_case(impl, c, l, r, d, H, n, seed=0, prescaled=0):
     pos = torch.zeros((Rpad, d), device=DEV, dtype=torch.bfloat16)
     pos[:R] = _rand((R, d), 1.0, seed + 1).bfloat16()
     rs = np.random.RandomState(seed)
-    rng_np = np.zeros((n + 2, 2), dtype=np.int32)
+    rng_np = np.zeros((n + 16, 2), dtype=np.int32)   # phantom chunks of the last 128-row attention tile stay empty
     for g in range(n):
         kind = g % 4
         if kind == 0:
@@ -276,6 +276,16 @@ def test_attention_tcgen05(l, r, n, prescaled, version):
     _attention_case(version, 64, l, r, 512, 8, n, seed=3, prescaled=prescaled)
 
 
+@pytest.mark.parametrize("c,l,r,d,H,n", [(16, 64, 0, 512, 8, 37), (16, 64, 0, 256, 4, 9), (32, 64, 64, 512, 8, 11),
+                                         (8, 16, 16, 256, 4, 21), (64, 100, 30, 512, 8, 7), (16, 50, 10, 512, 8, 8),
+                                         (32, 128, 96, 256, 4, 5), (8, 40, 0, 512, 8, 16)])
+@pytest.mark.parametrize("prescaled", [0, 1])
+def test_attention_tcgen05_small_chunks(c, l, r, d, H, n, prescaled):
+    """The tcgen05 kernel with tiles of 128 / c chunks (streaming presets such as 16/64/0) and context sizes that are not
+    multiples of 64."""
+    _attention_case(1, c, l, r, d, H, n, seed=7, prescaled=prescaled)
+
+
 @pytest.mark.parametrize("l,r,n", [(128, 128, 7), (128, 128, 12), (64, 64, 5), (128, 0, 6), (0, 0, 3), (192, 64, 9)])
 @pytest.mark.parametrize("prescaled", [0, 1])
 def test_attention_tcgen05_dk128(l, r, n, prescaled):
@@ -292,7 +302,7 @@ def test_attention_tcgen05_dk128_matches_generic_large():
     R = 2 * c + l + r - 1
     pos = torch.zeros(((R + 127) // 128 * 128, d), device=DEV, dtype=torch.bfloat16)
     pos[:R] = _rand((R, d), 1.0, 6).bfloat16()
-    rng = torch.zeros((n + 2, 2), dtype=torch.int32)
+    rng = torch.zeros((n + 16, 2), dtype=torch.int32)
     rng[:n, 1] = l + c + r
     rng[0, 0] = l
     rng[n - 1, 1] = l + 40
@@ -315,7 +325,7 @@ def test_attention_tcgen05_matches_generic_large(version):
     R = 2 * c + l + r - 1
     pos = torch.zeros(((R + 127) // 128 * 128, d), device=DEV, dtype=torch.bfloat16)
     pos[:R] = _rand((R, d), 1.0, 6).bfloat16()
-    rng = torch.zeros((n + 2, 2), dtype=torch.int32)
+    rng = torch.zeros((n + 16, 2), dtype=torch.int32)
     rng[:n, 1] = l + c + r
     rng[0, 0] = l
     rng[n - 1, 1] = l + 40
