@@ -512,23 +512,31 @@ bool run_frontend_conv(int impl, int d, const Fe1Params& f1, int num_sms, cudaSt
   return true;
 }
 
-bool attention_tc_supported(int c, int l, int r, int dk) {
-  if (l < 0 || r < 0 || l + r > 256) return false;
-  if (dk == 128) return c == 64 && (l % 64) == 0 && (r % 64) == 0;
-  if (dk != 64 || !(c == 8 || c == 16 || c == 32 || c == 64)) return false;
-  // tile = 128 / c chunks, key blocks of 128 union slots; the resident table slice holds 448 rows
+// 128-key-block kernel with a resident position-table slice: d_k = 64, tiles of 128 / c chunks, short windows
+bool attention_tc_fast_supported(int c, int l, int r, int dk) {
+  if (dk != 64 || !(c == 8 || c == 16 || c == 32 || c == 64) || l < 0 || r < 0 || l + r > 256) return false;
   const int W = l + c + r, nb = (l + 128 + r + 127) / 128;
   const int n_last = (W - 128 * (nb - 1) <= 65) ? 192 : 256;
   return 128 * (nb - 1) + n_last <= 448;
+}
+// ring kernel: d_k 64 / 128, chunk sizes dividing 128 or >= 128, any context
+bool attention_tc_supported(int c, int l, int r, int dk) {
+  if (!(dk == 64 || dk == 128) || l < 0 || r < 0) return false;
+  return c == 8 || c == 16 || c == 32 || c == 64 || c >= 128;
 }
 
 bool run_attention(int impl, const AttnParams& p, cudaStream_t st, std::string* err) {
   if (p.n_chunks == 0) return true;
   const int dk = p.d / p.heads;
   if (impl == 1 || impl == 2) {
-    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernels need d_k=64 with c in {8,16,32,64} or d_k=128 with c=64, and l+r<=256"; return false; }
-    if (dk == 128) return launch_attention_tc128(p, st, err);
-    return launch_attention_tc(p, (impl == 2 && p.c == 64 && p.l % 64 == 0 && p.r % 64 == 0) ? 2 : 1, st, err);
+    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernels need d_k 64 or 128 and a chunk size in {8,16,32,64} or >= 128"; return false; }
+    if (attention_tc_fast_supported(p.c, p.l, p.r, dk))
+      return launch_attention_tc(p, (impl == 2 && p.c == 64 && p.l % 64 == 0 && p.r % 64 == 0) ? 2 : 1, st, err);
+    return launch_attention_ring(p, st, err);
+  }
+  if (impl == 3) {      // tests / tools: force the ring kernel
+    if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: ring kernel does not cover this shape"; return false; }
+    return launch_attention_ring(p, st, err);
   }
   const int W = p.l + p.c + p.r;
   const size_t smem = size_t(4) * (2 * dk + W) * sizeof(float);

@@ -750,32 +750,61 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// d_k = 128 variant (chunkformer-rnnt-large / classification geometry: d = 512, H = 4), chunk 64, l / r multiples of 64.
-// Same chunk-pair tiling, but a head row is twice as wide, so per item the operands no longer fit beside a resident position
-// table: keys go in blocks of 64 (S_ac N = 64, S_bd N = 192), the projected position table streams through a ring of four
-// 64-row chunks (block b reads chunks b, b+1, b+2; only chunk b+2 is new), K is double-buffered, V single-buffered, every
-// operand has its own full / empty barrier pair and one polling thread issues each TMA load the moment its buffer is free.
-// P never touches shared memory (TMEM columns [384, 416), A operand of the P V MMAs).
-// TMEM map: S_ac [0,64)  S_bd [64,256)  O [256,384)  P [384,416).
+// General ring kernel: d_k = 64 or 128, any chunk size that divides 128 (tile = 128 / c chunks) or is >= 128 (tiles of 128
+// rows inside one chunk: chunk 128 / 256 configurations, full attention = one chunk per utterance), any context sizes.
+// Used for everything the 128-key-block kernel above does not cover (chunkformer-rnnt-large / classification geometry with
+// d_k = 128, long contexts, long chunks).  Per item (tile, head) the operands no longer fit beside a resident position
+// table, so keys go in blocks of 64 (S_ac N = 64, S_bd N = 192) and the projected position table streams through a ring of
+// four 64-row chunks: block b reads table rows [tb + 64 b, tb + 64 b + 192) = chunks b, b+1, b+2, of which only b+2 is
+// new.  K is double-buffered, V single-buffered, every operand has its own full / empty barrier pair and one polling
+// thread issues each TMA load the moment its buffer is free.  P never touches shared memory (TMEM, A operand of P V).
+//   score(rho, u) = S_ac[rho, u] + S_bd[rho, 127 - rho + (u - 64 b)]   with table row = tb + 64 b + column, where
+//   tb = c - 128 (multi-chunk tiles) or c - 128 - 128 t (tile t of a long chunk);   u = key slot in the tile's window.
+// TMEM map: S_ac [0,64)  S_bd [64,256)  O [256,256+DK)  P [256+DK, 288+DK).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int ATC128_THREADS = 320;
-constexpr uint32_t ATC128_ATOM = 64 * 128;          // 64 rows x 64 bf16
-constexpr size_t ATC128_SMEM_BYTES = 4 * 2 * ATC128_ATOM /*Qu, Qv: 2 atoms x 128 rows*/ + 2 * 2 * ATC128_ATOM /*K x2 stages*/ +
-                                     2 * ATC128_ATOM /*V*/ + 4 * 2 * ATC128_ATOM /*table ring*/ + 256 * ATC_STAGE_PITCH +
-                                     2048 + 1024 + 256 + 1024;
+constexpr int ATCR_THREADS = 320;
+constexpr uint32_t ATCR_ATOM = 64 * 128;            // 64 rows x 64 bf16
+template <int DK>
+constexpr size_t atcr_smem_bytes() {
+  return size_t(DK / 64) * (2 + 2 + 2 + 1 + 4) * ATCR_ATOM /*Qu, Qv (128 rows each) + K x2 + V + table ring x4*/ + 256 * ATC_STAGE_PITCH +
+         2048 + 1024 + 256 + 1024;
+}
 
-template <bool PRE>
-__global__ void __launch_bounds__(ATC128_THREADS, 1)
-attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/, const __grid_constant__ CUtensorMap tma_kv /*box 64 x 64*/,
-                       const __grid_constant__ CUtensorMap tma_pos /*box 64 x 64*/, AttnTcParams p) {
+struct AttnRingParams {
+  const int2* range;      // [n_chunks (+ phantoms)] valid key slots per chunk
+  __nv_bfloat16* ctx;     // [n_chunks * c, d]
+  int n_chunks, n_tiles, c, l, d, heads, nb;   // nb = key blocks of 64 window slots
+  int c_log2;             // c < 128: log2(c) (tile = 128 / c chunks);  c >= 128: -1 (tiles_per_chunk tiles inside one chunk)
+  int tiles_per_chunk;    // c >= 128
+  int last_chunks;        // table chunks read by the last block (2 when no valid score there needs columns >= 128)
+  int items_per_cta_stride;
+  float scale_log2e;
+};
+
+struct AttnRingTile { int qrow0, krow0, tb; };
+CF_DEVINL AttnRingTile atcr_tile(const AttnRingParams& p, int ti) {
+  AttnRingTile t;
+  if (p.c_log2 >= 0) { t.qrow0 = 128 * ti; t.krow0 = 128 * ti; t.tb = p.c - 128; }
+  else {
+    const int g = ti / p.tiles_per_chunk, tt = ti - g * p.tiles_per_chunk;
+    t.qrow0 = p.c * g + 128 * tt; t.krow0 = p.c * g; t.tb = p.c - 128 - 128 * tt;
+  }
+  return t;
+}
+
+template <int DK, bool PRE>
+__global__ void __launch_bounds__(ATCR_THREADS, 1)
+attention_ring_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/, const __grid_constant__ CUtensorMap tma_kv /*box 64 x 64*/,
+                      const __grid_constant__ CUtensorMap tma_pos /*box 64 x 64*/, AttnRingParams p) {
+  constexpr int NA = DK / 64;                            // 64-column swizzle atoms per operand row
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_qu = smem;                                 // [2 atoms][128 rows x 128 B]
-  uint8_t* s_qv = s_qu + 4 * ATC128_ATOM;
-  uint8_t* s_k = s_qv + 4 * ATC128_ATOM;                // [2 stages][2 atoms][64 keys x 128 B]
-  uint8_t* s_v = s_k + 4 * ATC128_ATOM;                 // [2 atoms][64 keys x 128 B]   (MN-major B operand)
-  uint8_t* s_pt = s_v + 2 * ATC128_ATOM;                // [4 slots][2 atoms][64 table rows x 128 B]
-  uint8_t* s_stage = s_pt + 8 * ATC128_ATOM;            // 256 thread-private skew rows
+  uint8_t* s_qu = smem;                                 // [NA atoms][128 rows x 128 B]
+  uint8_t* s_qv = s_qu + NA * 2 * ATCR_ATOM;
+  uint8_t* s_k = s_qv + NA * 2 * ATCR_ATOM;             // [2 stages][NA atoms][64 keys x 128 B]
+  uint8_t* s_v = s_k + 2 * NA * ATCR_ATOM;              // [NA atoms][64 keys x 128 B]   (MN-major B operand)
+  uint8_t* s_pt = s_v + NA * ATCR_ATOM;                 // [4 slots][NA atoms][64 table rows x 128 B]
+  uint8_t* s_stage = s_pt + 4 * NA * ATCR_ATOM;         // 256 thread-private skew rows
   float* s_xch = reinterpret_cast<float*>(s_stage + 256 * ATC_STAGE_PITCH);   // [2 parity][2 set][128] row maxima
   float* s_lx = s_xch + 512;                                                   // [2 set][128] row sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_lx + 256);
@@ -795,12 +824,12 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int h = blockIdx.x % p.heads;
-  const int first_pair = blockIdx.x / p.heads;
+  const int first_tile = blockIdx.x / p.heads;
   const int d = p.d;
-  const int nb = p.nb;                                  // key blocks of 64 union slots
+  const int nb = p.nb;
   const int nch = nb + 2;                               // table chunks per item
   const int stride = p.items_per_cta_stride;
-  const int n_items = first_pair < p.n_pairs ? (p.n_pairs - first_pair + stride - 1) / stride : 0;
+  const int n_items = first_tile < p.n_tiles ? (p.n_tiles - first_tile + stride - 1) / stride : 0;
   const uint32_t total = uint32_t(n_items) * uint32_t(nb);
   const uint32_t total_ch = uint32_t(n_items) * uint32_t(nch);
 
@@ -823,7 +852,7 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t TM_AC = 0, TM_BD = 64, TM_O = 256, TM_P = 384;
+  constexpr uint32_t TM_AC = 0, TM_BD = 64, TM_O = 256, TM_P = 256 + DK;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: four streams polled by one thread
@@ -833,39 +862,40 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
       while (kb < total || vb < total || cb < total_ch || qi < n_items) {
         bool issued = false;
         if (qi < n_items && mbar_test(q_empty, (qi & 1) ^ 1)) {
-          const int row = p.l + 128 * (first_pair + qi * stride);
-          mbar_arrive_expect_tx(q_full, 8 * ATC128_ATOM);
+          const int row = p.l + atcr_tile(p, first_tile + qi * stride).qrow0;
+          mbar_arrive_expect_tx(q_full, NA * 4 * ATCR_ATOM);
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            tma_load_2d(s_qu + a * 2 * ATC128_ATOM, &tma_q, q_full, h * 128 + 64 * a, row);
-            tma_load_2d(s_qv + a * 2 * ATC128_ATOM, &tma_q, q_full, d + h * 128 + 64 * a, row);
+          for (int a = 0; a < NA; ++a) {
+            tma_load_2d(s_qu + a * 2 * ATCR_ATOM, &tma_q, q_full, h * DK + 64 * a, row);
+            tma_load_2d(s_qv + a * 2 * ATCR_ATOM, &tma_q, q_full, d + h * DK + 64 * a, row);
           }
           ++qi; issued = true;
         }
         if (kb < total && mbar_test(&k_empty[kb & 1], ((kb >> 1) & 1) ^ 1)) {
           const int it = int(kb) / nb, b = int(kb) - it * nb;
-          const int row = 128 * (first_pair + it * stride) + 64 * b;
-          mbar_arrive_expect_tx(&k_full[kb & 1], 2 * ATC128_ATOM);
+          const int row = atcr_tile(p, first_tile + it * stride).krow0 + 64 * b;
+          mbar_arrive_expect_tx(&k_full[kb & 1], NA * ATCR_ATOM);
 #pragma unroll
-          for (int a = 0; a < 2; ++a)
-            tma_load_2d(s_k + ((kb & 1) * 2 + a) * ATC128_ATOM, &tma_kv, &k_full[kb & 1], 2 * d + h * 128 + 64 * a, row);
+          for (int a = 0; a < NA; ++a)
+            tma_load_2d(s_k + ((kb & 1) * NA + a) * ATCR_ATOM, &tma_kv, &k_full[kb & 1], 2 * d + h * DK + 64 * a, row);
           ++kb; issued = true;
         }
         if (cb < total_ch && mbar_test(&pt_empty[cb & 3], ((cb >> 2) & 1) ^ 1)) {
-          const int ct = int(cb % uint32_t(nch));           // chunk ct = table rows [64 ct - 64, 64 ct)
-          mbar_arrive_expect_tx(&pt_full[cb & 3], 2 * ATC128_ATOM);
+          const int it = int(cb / uint32_t(nch)), ct = int(cb) - it * nch;
+          const int row = atcr_tile(p, first_tile + it * stride).tb + 64 * ct;        // rows outside [0, R) read as zeros
+          mbar_arrive_expect_tx(&pt_full[cb & 3], NA * ATCR_ATOM);
 #pragma unroll
-          for (int a = 0; a < 2; ++a)
-            tma_load_2d(s_pt + ((cb & 3) * 2 + a) * ATC128_ATOM, &tma_pos, &pt_full[cb & 3], h * 128 + 64 * a, 64 * ct - 64);
+          for (int a = 0; a < NA; ++a)
+            tma_load_2d(s_pt + ((cb & 3) * NA + a) * ATCR_ATOM, &tma_pos, &pt_full[cb & 3], h * DK + 64 * a, row);
           ++cb; issued = true;
         }
         if (vb < total && mbar_test(v_empty, (vb & 1) ^ 1)) {
           const int it = int(vb) / nb, b = int(vb) - it * nb;
-          const int row = 128 * (first_pair + it * stride) + 64 * b;
-          mbar_arrive_expect_tx(v_full, 2 * ATC128_ATOM);
+          const int row = atcr_tile(p, first_tile + it * stride).krow0 + 64 * b;
+          mbar_arrive_expect_tx(v_full, NA * ATCR_ATOM);
 #pragma unroll
-          for (int a = 0; a < 2; ++a)
-            tma_load_2d(s_v + a * ATC128_ATOM, &tma_kv, v_full, 3 * d + h * 128 + 64 * a, row);
+          for (int a = 0; a < NA; ++a)
+            tma_load_2d(s_v + a * ATCR_ATOM, &tma_kv, v_full, 3 * d + h * DK + 64 * a, row);
           ++vb; issued = true;
         }
         if (!issued) __nanosleep(64);
@@ -885,8 +915,8 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
 #pragma unroll
         for (int t = 0; t < 4; ++t)          // 16 keys per step: 8 packed P columns; V: 16 key rows = 2048 B inside an atom
 #pragma unroll
-          for (int hn = 0; hn < 2; ++hn)
-            umma_bf16_ts(tmem_base + TM_O + 64 * hn, tmem_base + TM_P + 8 * t, dv0 + uint64_t((hn * ATC128_ATOM + t * 2048) >> 4),
+          for (int hn = 0; hn < NA; ++hn)
+            umma_bf16_ts(tmem_base + TM_O + 64 * hn, tmem_base + TM_P + 8 * t, dv0 + uint64_t((hn * ATCR_ATOM + t * 2048) >> 4),
                          idesc_pv, (pb | uint32_t(t)) != 0);
         umma_commit(pv_done);
         umma_commit(v_empty);
@@ -898,29 +928,29 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
       mbar_wait(q_full, item & 1);
       for (int b = 0; b < nb; ++b, ++blk) {
         const uint32_t st = blk & 1;
-        const int nchunks = (b == nb - 1) ? 2 : 3;        // the last block never needs table rows >= 64 (nb + 1) - 64
+        const int nchunks = (b == nb - 1) ? p.last_chunks : 3;
         mbar_wait(&k_full[st], (blk >> 1) & 1);
         for (int j = (b == 0 ? 0 : 2); j < 3; ++j) {     // chunks b, b+1 were waited for by the previous block; the item's last
-          const uint32_t gc = ch0 + uint32_t(b + j);     // chunk is not read but must have landed before its slot is released
+          const uint32_t gc = ch0 + uint32_t(b + j);     // chunk may not be read but must have landed before its slot is released
           mbar_wait(&pt_full[gc & 3], (gc >> 2) & 1);
         }
         mbar_wait(s_free, (blk & 1) ^ 1);                 // softmax finished reading the previous S block
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int a = 0; a < 2; ++a)
+          for (int a = 0; a < NA; ++a)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_base + TM_AC, dqu + uint64_t((a * 2 * ATC128_ATOM) >> 4) + 2 * k,
-                           dk0 + uint64_t(((st * 2 + a) * ATC128_ATOM) >> 4) + 2 * k, idesc_s, (a | k) != 0);
+              umma_bf16_ss(tmem_base + TM_AC, dqu + uint64_t((a * 2 * ATCR_ATOM) >> 4) + 2 * k,
+                           dk0 + uint64_t(((st * NA + a) * ATCR_ATOM) >> 4) + 2 * k, idesc_s, (a | k) != 0);
           for (int j = 0; j < nchunks; ++j) {
             const uint32_t slot = (ch0 + uint32_t(b + j)) & 3;
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16_ss(tmem_base + TM_BD + 64 * j, dqv + uint64_t((a * 2 * ATC128_ATOM) >> 4) + 2 * k,
-                             dpt0 + uint64_t(((slot * 2 + a) * ATC128_ATOM) >> 4) + 2 * k, idesc_s, (a | k) != 0);
+                umma_bf16_ss(tmem_base + TM_BD + 64 * j, dqv + uint64_t((a * 2 * ATCR_ATOM) >> 4) + 2 * k,
+                             dpt0 + uint64_t(((slot * NA + a) * ATCR_ATOM) >> 4) + 2 * k, idesc_s, (a | k) != 0);
           }
           umma_commit(s_full);
           umma_commit(&k_empty[st]);
@@ -942,41 +972,51 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
     const int quad = warp & 3;
     const int set = sw >> 2;
     const int rho = quad * 32 + lane;
-    const int half = rho >> 6, qi = rho & 63;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     uint8_t* stage = s_stage + (threadIdx.x - 64) * ATC_STAGE_PITCH;
     const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
     const int cbw = 96 - 32 * quad + 32 * set;          // first S_bd column this warp stages (warp-uniform)
+    constexpr int OC = DK / 2;                          // output columns per thread
     uint32_t blk = 0;
-    int ep_g = -1;
+    long long ep_row = -1;                              // flat output row of the finished item (-1: none / not a real row)
+    bool ep_pending = false;
     float ep_l = 0.f;
-    auto write_out = [&]() {                            // O / l -> ctx: this thread's 64 of the head's 128 output columns
+    auto write_out = [&]() {                            // O / l -> ctx: this thread's half of the head's output columns
       const float l_tot = ep_l + s_lx[(set ^ 1) * 128 + rho];
       const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;      // no valid key: zero context (attention.py:133-136)
-      __nv_bfloat16* orow = p.ctx + ((long long)ep_g * 64 + qi) * d + h * 128 + 64 * set;
 #pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {
+      for (int hc = 0; hc < OC / 32; ++hc) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + lane_addr + TM_O + 64 * set + 32 * hc, r);
+        tmem_ld32(tmem_base + lane_addr + TM_O + OC * set + 32 * hc, r);
         tmem_ld_wait();
-        if (ep_g < p.n_chunks) {
+        if (ep_row >= 0) {
+          __nv_bfloat16* orow = p.ctx + ep_row * d + h * DK + OC * set + 32 * hc;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             uint32_t o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = pack_bf16(__uint_as_float(r[16 * q + 2 * e]) * inv, __uint_as_float(r[16 * q + 2 * e + 1]) * inv);
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + 32 * hc + 16 * q), "r"(o[0]), "r"(o[1]),
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + 16 * q), "r"(o[0]), "r"(o[1]),
                          "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
                          : "memory");
           }
         }
       }
-      ep_g = -1;
+      ep_pending = false;
     };
-    for (int pair = first_pair; pair < p.n_pairs; pair += stride) {
-      const int g = 2 * pair + half;
+    for (int ti = first_tile; ti < p.n_tiles; ti += stride) {
+      // this row's chunk, its valid key slots inside the tile's window and its flat output row
+      int g, uoff;
+      bool real;
+      const AttnRingTile tl = atcr_tile(p, ti);
+      if (p.c_log2 >= 0) {
+        const int cj = rho >> p.c_log2;
+        g = (ti << (7 - p.c_log2)) + cj; uoff = cj << p.c_log2; real = g < p.n_chunks;
+      } else {
+        g = ti / p.tiles_per_chunk; uoff = 0; real = (tl.qrow0 - tl.krow0) + rho < p.c;
+      }
       const int2 rg = p.range[g];
-      const int ulo = rg.x + 64 * half, uhi = rg.y + 64 * half;   // valid union slots for this row
+      const int ulo = rg.x + uoff, uhi = rg.y + uoff;
       float m_run = -1e30f, l_run = 0.f;
       for (int b = 0; b < nb; ++b, ++blk) {
         mbar_wait(s_full, blk & 1);
@@ -1043,17 +1083,17 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
         m_run = m_new;
         if (blk > 0) mbar_wait(pv_done, (blk - 1) & 1);   // previous P V retired: the P columns and O are ours again
         tc_fence_after();
-        if (ep_g >= 0) write_out();                      // previous item (its row sums were published before the barrier above)
+        if (ep_pending) write_out();                     // previous item (its row sums were published before the barrier above)
         tmem_st16(tmem_base + lane_addr + TM_P + 16 * set, pk);
-        if (b > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale this thread's 64 columns of the running output
+        if (b > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale this thread's columns of the running output
 #pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
+          for (int hc = 0; hc < OC / 32; ++hc) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + lane_addr + TM_O + 64 * set + 32 * hc, r);
+            tmem_ld32(tmem_base + lane_addr + TM_O + OC * set + 32 * hc, r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-            tmem_st32(tmem_base + lane_addr + TM_O + 64 * set + 32 * hc, r);
+            tmem_st32(tmem_base + lane_addr + TM_O + OC * set + 32 * hc, r);
           }
         }
         tmem_st_wait();
@@ -1062,9 +1102,9 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
         if (lane == 0) mbar_arrive(p_full);
       }
       s_lx[set * 128 + rho] = l_run;                     // read by the partner thread after the next named barrier
-      ep_g = g; ep_l = l_run;
+      ep_pending = true; ep_l = l_run; ep_row = real ? (long long)tl.qrow0 + rho : -1;
     }
-    if (ep_g >= 0) {
+    if (ep_pending) {
       named_bar_sync(1, 256);
       mbar_wait(pv_done, (blk - 1) & 1);
       tc_fence_after();
@@ -1078,40 +1118,57 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-inline bool launch_attention_tc128(const AttnParams& a, cudaStream_t st, std::string* err) {
+template <int DK>
+inline bool launch_attention_ring_dk(const AttnParams& a, cudaStream_t st, std::string* err) {
   const int W = a.l + a.c + a.r;
-  const int U = W + 64;
   const int R = 2 * a.c + a.l + a.r - 1;
   const int Rpad = ((R + 127) / 128) * 128;
-  AttnTcParams p{};
-  p.range = a.range; p.ctx = a.ctx; p.n_chunks = a.n_chunks; p.n_pairs = (a.n_chunks + 1) / 2; p.l = a.l; p.d = a.d;
-  p.heads = a.heads; p.nb = U / 64; p.scale_log2e = a.scale * 1.4426950408889634f;
-  p.trace = nullptr; p.experiment = 0;
+  AttnRingParams p{};
+  p.range = a.range; p.ctx = a.ctx; p.n_chunks = a.n_chunks; p.c = a.c; p.l = a.l; p.d = a.d; p.heads = a.heads;
+  p.scale_log2e = a.scale * 1.4426950408889634f;
+  int U;
+  if (a.c < 128) {
+    int c_log2 = 0;
+    while ((1 << c_log2) < a.c) ++c_log2;
+    p.c_log2 = c_log2; p.tiles_per_chunk = 1;
+    p.n_tiles = (a.n_chunks + (128 / a.c) - 1) / (128 / a.c);
+    U = a.l + 128 + a.r;
+  } else {
+    p.c_log2 = -1; p.tiles_per_chunk = (a.c + 127) / 128;
+    p.n_tiles = a.n_chunks * p.tiles_per_chunk;
+    U = W;
+  }
+  p.nb = (U + 63) / 64;
+  p.last_chunks = (W - 64 * (p.nb - 1) <= 1) ? 2 : 3;   // no valid score of the last block needs S_bd columns >= 128
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_head = sms / a.heads;
   if (per_head < 1) per_head = 1;
-  if (per_head > p.n_pairs) per_head = p.n_pairs;
+  if (per_head > p.n_tiles) per_head = p.n_tiles;
   p.items_per_cta_stride = per_head;
-  const uint64_t qkv_rows = uint64_t(a.l) + uint64_t(a.n_chunks) * 64 + uint64_t(a.r) + 2 * 64 + 128;
+  const uint64_t qkv_rows = uint64_t(a.l) + uint64_t(a.n_chunks) * a.c + uint64_t(a.r) + 2 * uint64_t(a.c) + 128;   // = the buffer the caller allocates
   CUtensorMap tq, tk, tp;
   if (!make_tma_2d_bf16(&tq, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 128, 64, err)) return false;
   if (!make_tma_2d_bf16(&tk, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 64, 64, err)) return false;
   if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 64, 64, err)) return false;
   static bool attr_set = false;
+  const size_t smem = atcr_smem_bytes<DK>();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC128_SMEM_BYTES));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC128_SMEM_BYTES));
-    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(attention_tc128): ") + cudaGetErrorString(e); return false; }
+    cudaError_t e = cudaFuncSetAttribute(attention_ring_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ring_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(attention_ring): ") + cudaGetErrorString(e); return false; }
     attr_set = true;
   }
-  if (a.prescaled) attention_tc128_kernel<true><<<per_head * a.heads, ATC128_THREADS, ATC128_SMEM_BYTES, st>>>(tq, tk, tp, p);
-  else attention_tc128_kernel<false><<<per_head * a.heads, ATC128_THREADS, ATC128_SMEM_BYTES, st>>>(tq, tk, tp, p);
+  if (a.prescaled) attention_ring_kernel<DK, true><<<per_head * a.heads, ATCR_THREADS, smem, st>>>(tq, tk, tp, p);
+  else attention_ring_kernel<DK, false><<<per_head * a.heads, ATCR_THREADS, smem, st>>>(tq, tk, tp, p);
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { if (err) *err = std::string("attention_tc128 launch: ") + cudaGetErrorString(e); return false; }
+  if (e != cudaSuccess) { if (err) *err = std::string("attention_ring launch: ") + cudaGetErrorString(e); return false; }
   return true;
+}
+inline bool launch_attention_ring(const AttnParams& a, cudaStream_t st, std::string* err) {
+  return (a.d / a.heads) == 128 ? launch_attention_ring_dk<128>(a, st, err) : launch_attention_ring_dk<64>(a, st, err);
 }
 
 inline bool launch_attention_tc(const AttnParams& a, int version, cudaStream_t st, std::string* err) {

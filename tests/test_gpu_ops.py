@@ -286,6 +286,17 @@ def test_attention_tcgen05_small_chunks(c, l, r, d, H, n, prescaled):
     _attention_case(1, c, l, r, d, H, n, seed=7, prescaled=prescaled)
 
 
+@pytest.mark.parametrize("c,l,r,d,H,n", [(64, 128, 128, 512, 8, 7), (16, 64, 0, 512, 8, 19), (128, 128, 128, 512, 8, 5),
+                                         (256, 64, 64, 512, 4, 3), (374, 0, 0, 512, 4, 3), (64, 256, 256, 512, 8, 9),
+                                         (128, 0, 0, 256, 4, 4), (200, 37, 11, 512, 8, 3), (32, 300, 20, 256, 2, 7),
+                                         (1000, 0, 0, 512, 8, 2)])
+@pytest.mark.parametrize("prescaled", [0, 1])
+def test_attention_tcgen05_ring(c, l, r, d, H, n, prescaled):
+    """The ring kernel (64-key blocks, streamed position table): d_k 64 and 128, multi-chunk tiles, long chunks (chunk
+    128 / 256, full attention = one chunk per utterance with a ragged last tile), long and odd contexts."""
+    _attention_case(3, c, l, r, d, H, n, seed=9, prescaled=prescaled)
+
+
 @pytest.mark.parametrize("l,r,n", [(128, 128, 7), (128, 128, 12), (64, 64, 5), (128, 0, 6), (0, 0, 3), (192, 64, 9)])
 @pytest.mark.parametrize("prescaled", [0, 1])
 def test_attention_tcgen05_dk128(l, r, n, prescaled):

@@ -33,3 +33,12 @@ for ev in prof.events():
 total = sum(v[1] for v in tot.values())
 for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:8]:
     print(f"  {name[:70]:70s} {n:5d} {us / 1e3:8.3f} ms {100 * us / total:5.1f}%")
+
+if which == "rnnt_large":
+    # full-attention padded batch (classification-style call: forward_encoder with chunk_size = -1), 64 x 30 s
+    xs = torch.randn((64, 2998, 80), device="cuda")
+    xl = torch.full((64,), 2998, dtype=torch.int32)
+    for _ in range(2): enc.forward_encoder(xs, xl, -1, -1, -1)
+    torch.cuda.synchronize()
+    e0.record(); o, m = enc.forward_encoder(xs, xl, -1, -1, -1); e1.record(); torch.cuda.synchronize()
+    print(f"full attention, padded batch 64 x 30 s (T' = {o.shape[1]}): {e0.elapsed_time(e1):.1f} ms = {64 * 30 / e0.elapsed_time(e1) / 3.6:.1f} audio-h/s")
