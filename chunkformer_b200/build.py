@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libchunkformer_b200.so")
 SOURCES = ["api.cu", "plan.cpp"]
 HEADERS = ["common.cuh", "gemm.cuh", "gemm_host.cuh", "norm_conv.cuh", "frontend.cuh", "attention_simt.cuh",
-           "attention_tc.cuh", "misc_kernels.cuh", "plan.h", os.path.join("..", "..", "include", "chunkformer_b200.h")]
+           "attention_tc.cuh", "fbank.cuh", "misc_kernels.cuh", "plan.h", os.path.join("..", "..", "include", "chunkformer_b200.h")]
 
 
 def _nvcc() -> str:

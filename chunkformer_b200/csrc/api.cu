@@ -12,6 +12,7 @@
 
 #include "attention_simt.cuh"
 #include "attention_tc.cuh"
+#include "fbank.cuh"
 #include "frontend.cuh"
 #include "gemm_host.cuh"
 #include "misc_kernels.cuh"
@@ -62,6 +63,8 @@ struct cf_handle {
   float* ctc_b = nullptr;
   float* zeros = nullptr;  // max(N) zero floats (bias-free GEMMs)
   std::vector<PosTable> pos_tables;
+  struct FbankTables { int sr = 0, bins = 0, flen = 0, fshift = 0; float* window = nullptr; float* mel_w = nullptr; int2* mel_rng = nullptr; int* mel_cnt = nullptr; };
+  std::vector<FbankTables> fbank_tables;
   // feature-arrival events of the next cf_encode call (cf_encode_feature_events): rows < ev_rows[i] are present once ev[i] fires
   std::vector<int64_t> ev_rows;
   std::vector<cudaEvent_t> ev;
@@ -146,6 +149,7 @@ extern "C" void cf_destroy(cf_handle* h) {
   if (h->arena) cudaFree(h->arena);
   for (auto& t : h->pos_tables)
     if (t.dev) cudaFree(t.dev);
+  for (auto& t : h->fbank_tables) { cudaFree(t.window); cudaFree(t.mel_w); cudaFree(t.mel_rng); cudaFree(t.mel_cnt); }
   delete h;
 }
 
@@ -856,6 +860,79 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
         CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
     }
   }
+  CF_CUDA(h, cudaGetLastError());
+  return CF_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// fbank (the step before the path)
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" int64_t cf_fbank_num_frames(int64_t n_samples, int sample_rate, int frame_length_ms, int frame_shift_ms) {
+  const int64_t flen = int64_t(sample_rate) * frame_length_ms / 1000, fshift = int64_t(sample_rate) * frame_shift_ms / 1000;
+  if (flen <= 0 || fshift <= 0 || n_samples < flen) return 0;
+  return 1 + (n_samples - flen) / fshift;                 // snip_edges=True (kaldi.py _get_strided)
+}
+
+extern "C" int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int sample_rate, int num_mel_bins, int frame_length_ms,
+                        int frame_shift_ms, float* out, void* stream) {
+  if (!h || !pcm || !out) return fail(h, CF_ERR_INVALID, "cf_fbank: null argument");
+  const int flen = sample_rate * frame_length_ms / 1000, fshift = sample_rate * frame_shift_ms / 1000;
+  if (flen <= FB_PAD / 2 || flen > FB_PAD || fshift <= 0 || num_mel_bins <= 0 || num_mel_bins > FB_MAX_BINS)
+    return fail(h, CF_ERR_INVALID, "cf_fbank: the frame must pad to 512 samples (e.g. 25 ms at 16 kHz) and num_mel_bins <= 96");
+  const int64_t T = cf_fbank_num_frames(n_samples, sample_rate, frame_length_ms, frame_shift_ms);
+  if (T == 0) return CF_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CF_CUDA(h, cudaSetDevice(h->device));
+  const cf_handle::FbankTables* tb = nullptr;
+  for (auto& t : h->fbank_tables)
+    if (t.sr == sample_rate && t.bins == num_mel_bins && t.flen == flen && t.fshift == fshift) tb = &t;
+  if (!tb) {
+    // povey window and mel filters exactly as torchaudio builds them (kaldi.py _feature_window_function, get_mel_banks)
+    std::vector<float> win(flen);
+    for (int i = 0; i < flen; ++i) win[i] = float(pow(0.5 - 0.5 * cos(2.0 * M_PI * double(i) / double(flen - 1)), 0.85));
+    const int nfb = FB_PAD / 2;
+    const double nyq = 0.5 * sample_rate, width = double(sample_rate) / FB_PAD;
+    auto mel = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };
+    const double lo = mel(20.0), hi = mel(nyq), delta = (hi - lo) / (num_mel_bins + 1);
+    std::vector<float> w;
+    std::vector<int2> rng(num_mel_bins);
+    std::vector<int> cnt(num_mel_bins);
+    for (int b = 0; b < num_mel_bins; ++b) {
+      const double left = lo + b * delta, center = left + delta, right = center + delta;
+      int first = -1, last = -1;
+      std::vector<float> row(nfb);
+      for (int i = 0; i < nfb; ++i) {
+        const double m = mel(width * i);
+        const double v = std::max(0.0, std::min((m - left) / (center - left), (right - m) / (right - center)));
+        row[i] = float(v);
+        if (v > 0.0) { if (first < 0) first = i; last = i; }
+      }
+      if (first < 0) { first = 0; last = -1; }
+      rng[b] = make_int2(first, int(w.size()));
+      cnt[b] = last - first + 1;
+      for (int i = first; i <= last; ++i) w.push_back(row[i]);
+    }
+    if (w.empty()) w.push_back(0.f);
+    cf_handle::FbankTables t;
+    t.sr = sample_rate; t.bins = num_mel_bins; t.flen = flen; t.fshift = fshift;
+    CF_CUDA(h, cudaMalloc(&t.window, win.size() * sizeof(float)));
+    CF_CUDA(h, cudaMalloc(&t.mel_w, w.size() * sizeof(float)));
+    CF_CUDA(h, cudaMalloc(&t.mel_rng, rng.size() * sizeof(int2)));
+    CF_CUDA(h, cudaMalloc(&t.mel_cnt, cnt.size() * sizeof(int)));
+    CF_CUDA(h, cudaMemcpy(t.window, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CF_CUDA(h, cudaMemcpy(t.mel_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CF_CUDA(h, cudaMemcpy(t.mel_rng, rng.data(), rng.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CF_CUDA(h, cudaMemcpy(t.mel_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->fbank_tables.push_back(t);
+    tb = &h->fbank_tables.back();
+  }
+  FbankParams q{};
+  q.pcm = pcm; q.out = out; q.window = tb->window; q.mel_w = tb->mel_w; q.mel_rng = tb->mel_rng; q.mel_cnt = tb->mel_cnt;
+  q.n_frames = T; q.frame_len = flen; q.frame_shift = fshift; q.num_bins = num_mel_bins; q.preemph = 0.97f;
+  const long long blocks_needed = (T + FB_WARPS - 1) / FB_WARPS;
+  const unsigned grid = unsigned(std::min<long long>(blocks_needed, 8LL * h->num_sms));
+  fbank_kernel<<<grid, FB_WARPS * 32, 0, st>>>(q);
+  ++cf::g_kernel_launches;
   CF_CUDA(h, cudaGetLastError());
   return CF_OK;
 }

@@ -191,6 +191,22 @@ class ChunkFormerEncoderB200:
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
+    def fbank(self, waveform: torch.Tensor, num_mel_bins: int = 80, frame_length: int = 25, frame_shift: int = 10,
+              sample_frequency: int = 16000) -> torch.Tensor:
+        """Kaldi-compatible log-mel filterbank on the device; drop-in for the call the reference makes right before the path,
+        torchaudio.compliance.kaldi.fbank(waveform, num_mel_bins=..., frame_length=..., frame_shift=..., dither=0.0,
+        energy_floor=0.0, sample_frequency=...) (chunkformer_model.py:307-315).  waveform (1, n) or (n,) in 16-bit range."""
+        w = waveform.reshape(-1).to(self.device, torch.float32).contiguous()
+        T = int(self._L.cf_fbank_num_frames(w.numel(), int(sample_frequency), int(frame_length), int(frame_shift)))
+        out = torch.empty((T, num_mel_bins), dtype=torch.float32, device=self.device)
+        if T:
+            _lib.check(self._L.cf_fbank(self._h, c_void_p(w.data_ptr()), w.numel(), int(sample_frequency), int(num_mel_bins),
+                                        int(frame_length), int(frame_shift), c_void_p(out.data_ptr()), self._stream()),
+                       self._h, "cf_fbank")
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
     def ctc_greedy(self, enc: torch.Tensor, want_margin: bool = False, want_logp: bool = False):
         """argmax(log_softmax(ctc_lo(enc))) (ctc.py:73-91). enc (..., d) fp32 or bf16 on the device.
         Returns tokens int64 (...,) [, margin fp32 (...,)] [, logp fp32 (..., V)]."""

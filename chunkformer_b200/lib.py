@@ -26,6 +26,8 @@ SIGNATURES = {
     "cf_version": (c_char_p, []),
     "cf_launch_count": (ctypes.c_longlong, []),
     "cf_encode_feature_events": (c_int, [c_void_p, c_int, POINTER(c_int64), POINTER(c_void_p)]),
+    "cf_fbank_num_frames": (c_int64, [c_int64, c_int, c_int, c_int]),
+    "cf_fbank": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cf_set_gemm_variant": (None, [c_int]),
     "cf_set_attention_version": (None, [c_int]),
     "cf_gemm_timing_begin": (None, [c_int, c_int]),

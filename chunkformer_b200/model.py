@@ -133,22 +133,30 @@ class ChunkFormerModel:
         return self.tasks if self.is_classification else None
 
     # ---------------------------------------------------------------------------------------------- features
+    def extract_features(self, waveform: torch.Tensor, sample_rate: Optional[int] = None):
+        """16-bit-range mono waveform (1, n) or (n,) at the model's sample rate -> fbank (T, num_mel_bins) on the device, by
+        the CUDA kernel behind cf_fbank (Kaldi-compatible; same values as the reference's kaldi.fbank call,
+        chunkformer_model.py:307-315, within 2e-3)."""
+        fbank_conf = self.config.get("fbank_conf", {})
+        sr = sample_rate or self.config.get("resample_conf", {}).get("resample_rate", 16000)
+        x = self.encoder.fbank(waveform, num_mel_bins=fbank_conf.get("num_mel_bins", 80),
+                               frame_length=fbank_conf.get("frame_length", 25), frame_shift=fbank_conf.get("frame_shift", 10),
+                               sample_frequency=sr)
+        return x, int(x.shape[0])
+
     def _load_audio_and_extract_features(self, audio):
-        """chunkformer_model.py:276-318. Accepts an fbank tensor (T, feat) or a wav path (torchaudio + kaldi fbank)."""
+        """chunkformer_model.py:276-318. Accepts an fbank tensor (T, feat) or a wav path; the file is decoded and resampled by
+        torchaudio on the host (the reference uses pydub), the fbank itself runs on the GPU (cf_fbank)."""
         if torch.is_tensor(audio):
             return audio, int(audio.shape[0])
         import torchaudio
-        import torchaudio.compliance.kaldi as kaldi
-        fbank_conf = self.config.get("fbank_conf", {})
         sr = self.config.get("resample_conf", {}).get("resample_rate", 16000)
         wav, in_sr = torchaudio.load(audio)
         wav = wav.mean(0, keepdim=True)
         if in_sr != sr:
             wav = torchaudio.functional.resample(wav, in_sr, sr)
-        wav = wav * (1 << 15)
-        x = kaldi.fbank(wav, num_mel_bins=fbank_conf.get("num_mel_bins", 80), frame_length=fbank_conf.get("frame_length", 25),
-                        frame_shift=fbank_conf.get("frame_shift", 10), dither=0.0, energy_floor=0.0, sample_frequency=sr)
-        return x, int(x.shape[0])
+        wav = torch.round(wav * (1 << 15)).clamp_(-32768, 32767)     # 16-bit samples as floats, like set_sample_width(2)
+        return self.extract_features(wav, sr)
 
     # ---------------------------------------------------------------------------------------------- encode
     @torch.no_grad()

@@ -70,6 +70,13 @@ CF_API long long cf_launch_count(void);
  * Replaces the reference's blocking xs.to(device) (chunkformer_model.py:395-401). */
 CF_API int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_ready, void* const* events);
 CF_API void cf_set_gemm_variant(int variant);
+/* Kaldi-compatible log-mel filterbank on the device: replaces torchaudio.compliance.kaldi.fbank(waveform, num_mel_bins,
+ * frame_length, frame_shift, dither=0.0, energy_floor=0.0, sample_frequency) as called right before the path
+ * (chunkformer_model.py:307-315).  pcm: n_samples device floats in 16-bit range; out: [cf_fbank_num_frames(...), num_mel_bins]
+ * device floats.  The frame must pad to 512 samples (25 ms at 16 kHz). */
+CF_API int64_t cf_fbank_num_frames(int64_t n_samples, int sample_rate, int frame_length_ms, int frame_shift_ms);
+CF_API int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int sample_rate, int num_mel_bins, int frame_length_ms,
+                    int frame_shift_ms, float* out, void* stream);
 /* Measurement: CUDA events around every launch of one GEMM family (epilogue kind `epi`, activation `act`; the FFN
  * up-projection is CF_EPI_BF16 + SiLU) on the launching stream, from cf_gemm_timing_begin until cf_gemm_timing_end, which
  * returns the summed device time and the number of launches (bench.py: roofline of the dominant kernel inside real steps). */
