@@ -50,6 +50,9 @@ CF_DEVINL uint32_t pack_half2(float lo, float hi) {
 
 inline long long*& attention_trace_buffer() { static long long* b = nullptr; return b; }
 
+__device__ const int kSkewRowPerm[32] = {20, 3, 6, 13, 31, 18, 17, 0, 7, 25, 11, 5, 10, 22, 24, 28,
+                                       9, 15, 29, 27, 30, 2, 8, 4, 12, 21, 26, 19, 14, 1, 16, 23};
+
 struct AttnTcParams {
   const int2* range;      // [n_chunks + 2] valid key slots per chunk (entries beyond n_chunks are empty)
   __nv_bfloat16* ctx;     // [n_chunks * 64, d]
@@ -210,7 +213,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     const int cj = rho >> p.c_log2;                    // chunk of this row inside the tile
     const int uoff = cj << p.c_log2;                   // its window starts at this union slot
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    uint8_t* stage = s_stage + (threadIdx.x - 64) * ATC_STAGE_PITCH;
+    // skew row of this thread: a lane permutation inside the warp's 32 rows (found by local search, tools/skew_row_perm.py)
+    // cuts the bank-conflict replays of the 2-byte skew reads from 2.0 to 1.5 wavefronts per load at the 144-byte pitch
+    // while the 16-byte staging stores stay conflict free
+    uint8_t* stage = s_stage + ((warp - 2) * 32 + kSkewRowPerm[lane]) * ATC_STAGE_PITCH;
     const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
     const int cb_thread = 96 - 32 * quad + 64 * set;   // first S_bd column this warp stages (warp-uniform)
     uint8_t* pp_row = s_pp + set * ATC_TILE_BYTES + rho * 128;
@@ -973,7 +979,7 @@ attention_ring_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/
     const int set = sw >> 2;
     const int rho = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    uint8_t* stage = s_stage + (threadIdx.x - 64) * ATC_STAGE_PITCH;
+    uint8_t* stage = s_stage + ((warp - 2) * 32 + kSkewRowPerm[lane]) * ATC_STAGE_PITCH;   // see attention_tc_kernel
     const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
     const int cbw = 96 - 32 * quad + 32 * set;          // first S_bd column this warp stages (warp-uniform)
     constexpr int OC = DK / 2;                          // output columns per thread
