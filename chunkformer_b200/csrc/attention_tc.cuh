@@ -9,7 +9,7 @@
 //     S_bd = (Q+v) P[128b-64 .. 128b+192)^T     UMMA 128x256x64  -> TMEM cols [128,384)
 //     s[rho, kk] = S_ac[rho, kk] + S_bd[rho, 127 - rho + kk]      (rel_shift, attention.py:242-266: the same skew
 //                                                                  formula holds for both chunks of the pair)
-//     P = exp2(s*scale*log2e - m)  (bf16, written to smem as the K-major A operand),  O += P V_blk  UMMA 128x64x128
+//     P = exp2(s*scale*log2e - m)  (bf16, kept in TMEM as the A operand),  O += P V_blk  UMMA 128x64x128
 // The row-dependent skew goes through a thread-private shared-memory row (each thread owns one query row after
 // tcgen05.ld 32x32b), so no cross-thread synchronisation is needed for it.  The score matrix never reaches HBM.
 //
@@ -35,8 +35,9 @@ constexpr int ATC_STAGE_PITCH = 144;             // bytes per thread-private ske
 constexpr uint32_t ATC_PTAB_ROWS = 448;          // table rows -64 .. 383 of the head
 constexpr uint32_t ATC_PTAB_BYTES = ATC_PTAB_ROWS * 128;
 constexpr uint32_t ATC_TILE_BYTES = 128 * 128;   // 128 rows x 64 bf16
-constexpr size_t ATC_SMEM_BYTES = ATC_PTAB_BYTES + 2 * ATC_TILE_BYTES /*Qu,Qv*/ + 4 * ATC_TILE_BYTES /*K,V x2*/ +
-                                  2 * ATC_TILE_BYTES /*P probs*/ + 256 * ATC_STAGE_PITCH + 2048 + 1024 + 1024 + 128;
+constexpr int ATC_KV_STAGES = 2;
+constexpr size_t ATC_SMEM_BYTES = ATC_PTAB_BYTES + 2 * ATC_TILE_BYTES /*Qu,Qv*/ + 2 * ATC_KV_STAGES * ATC_TILE_BYTES /*K,V ring*/ +
+                                  256 * ATC_STAGE_PITCH + 2048 + 1024 + 1024 + 128;
 
 CF_DEVINL float fast_exp2(float x) {
   float y;
@@ -49,6 +50,35 @@ CF_DEVINL uint32_t pack_half2(float lo, float hi) {
 }
 
 inline long long*& attention_trace_buffer() { static long long* b = nullptr; return b; }
+
+CF_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+CF_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+CF_DEVINL bool mbar_test(uint64_t* bar, uint32_t parity) {     // non-blocking probe
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 
 __device__ const int kSkewRowPerm[32] = {20, 3, 6, 13, 31, 18, 17, 0, 7, 25, 11, 5, 10, 22, 24, 28,
                                        9, 15, 29, 27, 30, 2, 8, 4, 12, 21, 26, 19, 14, 1, 16, 23};
@@ -73,23 +103,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
   uint8_t* s_ptab = smem;                        // smem row rr <-> table row rr - 64
   uint8_t* s_qu = s_ptab + ATC_PTAB_BYTES;
   uint8_t* s_qv = s_qu + ATC_TILE_BYTES;
-  uint8_t* s_k = s_qv + ATC_TILE_BYTES;          // [2]
-  uint8_t* s_v = s_k + 2 * ATC_TILE_BYTES;       // [2]
-  uint8_t* s_pp = s_v + 2 * ATC_TILE_BYTES;      // 2 atoms of 64 keys
-  uint8_t* s_stage = s_pp + 2 * ATC_TILE_BYTES;  // 256 thread-private rows
+  uint8_t* s_k = s_qv + ATC_TILE_BYTES;                      // [ATC_KV_STAGES]
+  uint8_t* s_v = s_k + ATC_KV_STAGES * ATC_TILE_BYTES;       // [ATC_KV_STAGES]
+  uint8_t* s_stage = s_v + ATC_KV_STAGES * ATC_TILE_BYTES;   // 256 thread-private rows
   float* s_xch = reinterpret_cast<float*>(s_stage + 256 * ATC_STAGE_PITCH);   // [2 parity][2 set][128] row maxima
   float* s_lx = s_xch + 512;                                                   // [2 set][128] row sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_lx + 256);
   uint64_t* ptab_full = bars + 0;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = bars + 2;
-  uint64_t* kv_full = bars + 3;    // [2]
-  uint64_t* kv_empty = bars + 5;   // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* s_free = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* pv_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars + 3;    // [ATC_KV_STAGES]
+  uint64_t* kv_empty = bars + 6;   // [ATC_KV_STAGES]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_free = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index provably uniform
   const int h = blockIdx.x % p.heads;
@@ -103,7 +132,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     mbar_init(ptab_full, 1);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < ATC_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
     mbar_init(s_free, 8);      // one arrival per softmax warp
     mbar_init(p_full, 8);
@@ -115,7 +144,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t TM_AC = 0, TM_BD = 128, TM_O = 384;
+  constexpr uint32_t TM_AC = 0, TM_BD = 128, TM_O = 384, TM_P = 448;   // P (bf16, 128 keys = 64 packed columns) stays in TMEM
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (convergent warp, elected lane issues)
@@ -137,7 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         }
         __syncwarp();
         for (int b = 0; b < nb; ++b, ++blk) {
-          const uint32_t st = blk & 1, ph = (blk >> 1) & 1;
+          const uint32_t st = blk % ATC_KV_STAGES, ph = (blk / ATC_KV_STAGES) & 1;
           mbar_wait(&kv_empty[st], ph ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&kv_full[st], 2 * ATC_TILE_BYTES);
@@ -154,11 +183,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       constexpr uint32_t idesc_ac = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_bd = make_idesc_bf16(128, 256);
       const uint32_t idesc_bd_last = p.n_last == 192 ? make_idesc_bf16(128, 192) : make_idesc_bf16(128, 256);   // 192: the last block never reads resident table rows >= 448
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // B (= V) is MN-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // A = P from TMEM, B (= V) is MN-major
       mbar_wait(ptab_full, 0);
       const uint64_t dqu = make_sw128_desc(smem_u32(s_qu)), dqv = make_sw128_desc(smem_u32(s_qv));
       const uint64_t dk0 = make_sw128_desc(smem_u32(s_k)), dv0 = make_sw128_desc(smem_u32(s_v));
-      const uint64_t dp0 = make_sw128_desc(smem_u32(s_ptab)), dpp = make_sw128_desc(smem_u32(s_pp));
+      const uint64_t dp0 = make_sw128_desc(smem_u32(s_ptab));
       uint32_t item = 0, blk = 0;
       bool have_prev = false;
       uint32_t prev_st = 0, prev_b = 0;
@@ -169,9 +198,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
           const uint64_t db = dv0 + uint64_t((st * ATC_TILE_BYTES) >> 4);
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            // A: 16 keys = 32 B inside a 64-key atom, atoms 16 KB apart; B (MN-major): 16 key rows = 2048 B
-            umma_bf16_ss(tmem_base + TM_O, dpp + uint64_t(((t >> 2) * ATC_TILE_BYTES + (t & 3) * 32) >> 4),
-                         db + uint64_t((t * 2048) >> 4), idesc_pv, (b | t) != 0);
+            // A: 16 keys = 8 packed P columns in TMEM; B (MN-major): 16 key rows = 2048 B
+            umma_bf16_ts(tmem_base + TM_O, tmem_base + TM_P + 8 * t, db + uint64_t((t * 2048) >> 4), idesc_pv, (b | t) != 0);
           }
           umma_commit(pv_done);
           umma_commit(&kv_empty[st]);
@@ -181,7 +209,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       for (int pair = first_pair; pair < p.n_pairs; pair += p.items_per_cta_stride, ++item) {
         mbar_wait(q_full, item & 1);
         for (int b = 0; b < nb; ++b, ++blk) {
-          const uint32_t st = blk & 1, ph = (blk >> 1) & 1;
+          const uint32_t st = blk % ATC_KV_STAGES, ph = (blk / ATC_KV_STAGES) & 1;
           mbar_wait(&kv_full[st], ph);
           mbar_wait(s_free, (blk & 1) ^ 1);            // softmax finished reading the previous S block
           tc_fence_after();
@@ -219,7 +247,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     uint8_t* stage = s_stage + ((warp - 2) * 32 + kSkewRowPerm[lane]) * ATC_STAGE_PITCH;
     const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
     const int cb_thread = 96 - 32 * quad + 64 * set;   // first S_bd column this warp stages (warp-uniform)
-    uint8_t* pp_row = s_pp + set * ATC_TILE_BYTES + rho * 128;
     uint32_t blk = 0;
     int ep_g = -1;                                     // chunk (of this row) whose item is finished but not yet written out
     long long ep_row0 = 0;                             // first flat row of that item's tile
@@ -322,16 +349,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         if (blk > 0) mbar_wait(pv_done, (blk - 1) & 1);   // previous P V retired: P tile and O are ours again
         tc_fence_after();
         if (ep_g >= 0) write_out();                    // previous item: its row sums were published before the barrier above
+        {
+          uint32_t pk[32];                             // this thread's 64 probabilities as 32 packed bf16 pairs
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                  // 8 x (8 keys -> 16 bytes) into this set's 64-key K-major atom
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float p0 = fast_exp2(s[8 * j + 2 * e] - m_new), p1 = fast_exp2(s[8 * j + 2 * e + 1] - m_new);
+          for (int e = 0; e < 32; ++e) {
+            const float p0 = fast_exp2(s[2 * e] - m_new), p1 = fast_exp2(s[2 * e + 1] - m_new);
             sum += p0 + p1;
-            w[e] = pack_bf16(p0, p1);
+            pk[e] = pack_bf16(p0, p1);
           }
-          *reinterpret_cast<uint4*>(pp_row + ((j ^ (rho & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          tmem_st32(tmem_base + lane_addr + TM_P + 32 * set, pk);
         }
         l_run = l_run * alpha + sum;
         m_run = m_new;
@@ -342,10 +368,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
           tmem_st32(tmem_base + lane_addr + TM_O + 32 * set, r);
-          tmem_st_wait();
         }
+        tmem_st_wait();
         tc_fence_before();
-        fence_proxy_async();                           // P tile (generic-proxy stores) -> visible to the MMA (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
       }
@@ -382,35 +407,6 @@ constexpr int ATC2_SOFT_WARPS = 16;
 constexpr int ATC2_THREADS = 64 + 32 * ATC2_SOFT_WARPS;
 constexpr size_t ATC2_SMEM_BYTES = ATC_PTAB_BYTES + 2 * ATC_TILE_BYTES + 4 * ATC_TILE_BYTES +
                                    size_t(32 * ATC2_SOFT_WARPS) * ATC_STAGE_PITCH + 256 + 1024;
-
-CF_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-CF_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-
-CF_DEVINL bool mbar_test(uint64_t* bar, uint32_t parity) {     // non-blocking probe
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}\n"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return done != 0;
-}
 
 template <bool PRE>
 __global__ void __launch_bounds__(ATC2_THREADS, 1)
