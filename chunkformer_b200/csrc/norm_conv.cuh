@@ -230,6 +230,11 @@ CF_DEVINL unsigned long long ffma2(unsigned long long a, unsigned long long b, u
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+CF_DEVINL unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 CF_DEVINL float f32x2_lo(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 CF_DEVINL float f32x2_hi(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
@@ -246,10 +251,7 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
   extern __shared__ __align__(1024) uint8_t dw_smem[];
   uint8_t* s_in = dw_smem;                        // [2 stages][HALVES][ROWS][256 ch] bf16
   uint64_t* full = reinterpret_cast<uint64_t*>(s_in + 2 * STAGE_BYTES);
-  __shared__ float s_part2[2][NW][FG];   // double-buffered by iteration parity: no barrier needed at the end of a group
-  __shared__ float s_partq2[2][NW][FG];
-  __shared__ float s_mean2[2][FG];
-  __shared__ float s_rstd2[2][FG];
+  __shared__ unsigned long long s_part2[2][NW][FG];   // double-buffered by iteration parity: no barrier at the end of a group
 
   const int tid = threadIdx.x;
   const int groups_per_chunk = p.c / FG;
@@ -275,96 +277,87 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
 #pragma unroll
   for (int t = 0; t < KW; ++t) w[t] = pack_f32x2(__ldg(p.w + (2 * tid) * KW + t), __ldg(p.w + (2 * tid + 1) * KW + t));
   const unsigned long long bias2 = pack_f32x2(__ldg(p.bias + 2 * tid), __ldg(p.bias + 2 * tid + 1));
-  const float lw0 = __ldg(p.ln_w + 2 * tid), lw1 = __ldg(p.ln_w + 2 * tid + 1);
-  const float lb0 = __ldg(p.ln_b + 2 * tid), lb1 = __ldg(p.ln_b + 2 * tid + 1);
+  // SiLU(x) = h + h tanh(h), h = x / 2: the halving is folded into the LayerNorm affine
+  const unsigned long long lwh2 = pack_f32x2(0.5f * __ldg(p.ln_w + 2 * tid), 0.5f * __ldg(p.ln_w + 2 * tid + 1));
+  const unsigned long long lbh2 = pack_f32x2(0.5f * __ldg(p.ln_b + 2 * tid), 0.5f * __ldg(p.ln_b + 2 * tid + 1));
   const int hb = tid >> 7;                        // which 256-channel box this thread's channels live in
   const uint32_t col_off = hb * (ROWS * 512) + (tid & 127) * 4;
+  const int lane = tid & 31, warp = tid >> 5;
 
+  int2 rg_next = (int(blockIdx.x) < total_groups) ? __ldg(&p.range[blockIdx.x / groups_per_chunk]) : make_int2(0, 0);
   int it = 0;
   for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x, ++it) {
     const int stage = it & 1;
-    float (*s_part)[FG] = s_part2[stage];
-    float* s_mean = s_mean2[stage];
-    float* s_rstd = s_rstd2[stage];
     const int nxt = grp + gridDim.x;
     // every thread finished reading the other stage's tile before the LayerNorm barriers of the previous iteration
     if (tid == 0 && nxt < total_groups) issue(nxt, stage ^ 1);
     const int chunk = grp / groups_per_chunk;
     const int f0 = (grp - chunk * groups_per_chunk) * FG;
-    const int2 rg = p.range[chunk];
+    const int2 rg = rg_next;
+    if (nxt < total_groups) rg_next = __ldg(&p.range[nxt / groups_per_chunk]);   // consumed one iteration later
     mbar_wait(&full[stage], (it >> 1) & 1);
     const uint8_t* src = s_in + stage * STAGE_BYTES + col_off;
 
+    // Row-outer order: input row s feeds the 15 frames s-14 .. s, so the 15 FMAs issued per loaded row are independent
+    // (no sliding register window, no serial accumulator chain); frame f still sums bias, tap 0, ..., tap 14 in that order.
     unsigned long long o[FG];
-    unsigned long long win[KW];
     auto conv = [&](auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-      for (int t = 0; t < KW - 1; ++t) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(src + t * 512);
-        const bool ok = !MASKED || ((f0 + t >= rg.x) && (f0 + t < rg.y));
-        win[t] = ok ? pack_f32x2(bf16_lo(v), bf16_hi(v)) : 0ull;
-      }
+      for (int s = 0; s < ROWS; ++s) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(src + s * 512);
+        const bool ok = !MASKED || ((f0 + s >= rg.x) && (f0 + s < rg.y));
+        const unsigned long long x = ok ? pack_f32x2(bf16_lo(v), bf16_hi(v)) : 0ull;
 #pragma unroll
-      for (int f = 0; f < FG; ++f) {
-        {
-          const int t = f + KW - 1;
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(src + t * 512);
-          const bool ok = !MASKED || ((f0 + t >= rg.x) && (f0 + t < rg.y));
-          win[(f + KW - 1) % KW] = ok ? pack_f32x2(bf16_lo(v), bf16_hi(v)) : 0ull;
+        for (int t = 0; t < KW; ++t) {
+          const int f = s - t;
+          if (f >= 0 && f < FG) o[f] = ffma2(w[t], x, t == 0 ? bias2 : o[f]);
         }
-        unsigned long long acc = bias2;
-#pragma unroll
-        for (int t = 0; t < KW; ++t) acc = ffma2(w[t], win[(f + t) % KW], acc);
-        o[f] = acc;
       }
     };
     // groups whose 46 window slots are all valid (the bulk of a long utterance) skip the per-row mask tests
     if (f0 >= rg.x && f0 + ROWS <= rg.y) conv(std::false_type{}); else conv(std::true_type{});
 
-    // LayerNorm over the D channels of every frame: sum and sum of squares reduced together (one barrier pair), then SiLU
-    float ps[FG], pq[FG];
+    // LayerNorm over the D channels of every frame: (sum, sum of squares) travel as one f32x2 pair through a
+    // lane-transposing butterfly (lane f ends with frame f's warp total), one barrier pair per group
+    unsigned long long P[FG];
 #pragma unroll
     for (int f = 0; f < FG; ++f) {
       const float lo = f32x2_lo(o[f]), hi = f32x2_hi(o[f]);
-      ps[f] = lo + hi;
-      pq[f] = fmaf(lo, lo, hi * hi);
+      P[f] = pack_f32x2(lo + hi, fmaf(lo, lo, hi * hi));
     }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const unsigned long long send = up ? P[i] : P[i + off];
+        const unsigned long long keep = up ? P[i + off] : P[i];
+        P[i] = fadd2(keep, __shfl_xor_sync(0xffffffffu, send, off));
+      }
+    }
+    s_part2[stage][warp][lane] = P[0];
+    __syncthreads();
+    // every warp finishes the statistics itself (lane f owns frame f), the output loop fetches them by shuffle: one
+    // barrier per group, no single-warp finalize step on the critical path
+    float rs, nm;
     {
-      const int lane = tid & 31, warp = tid >> 5;
+      float a = 0.f, q = 0.f;
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; ++i) {
-          const float s1 = up ? ps[i] : ps[i + off], k1 = up ? ps[i + off] : ps[i];
-          const float s2 = up ? pq[i] : pq[i + off], k2 = up ? pq[i + off] : pq[i];
-          ps[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, off);
-          pq[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, off);
-        }
-      }
-      s_part[warp][lane] = ps[0];
-      s_partq2[stage][warp][lane] = pq[0];
-      __syncthreads();
-      if (tid < FG) {
-        float a = 0.f, q = 0.f;
-#pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) { a += s_part[w2][tid]; q += s_partq2[stage][w2][tid]; }
-        const float mean = a * (1.0f / D);
-        const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
-        s_mean[tid] = mean;
-        s_rstd[tid] = rsqrtf(var + 1e-5f);
-      }
-      __syncthreads();
+      for (int w2 = 0; w2 < NW; ++w2) { const unsigned long long v = s_part2[stage][w2][lane]; a += f32x2_lo(v); q += f32x2_hi(v); }
+      const float mean = a * (1.0f / D);
+      const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
+      rs = rsqrtf(var + 1e-5f);
+      nm = -mean * rs;
     }
     uint32_t* zp = reinterpret_cast<uint32_t*>(p.z) + ((long long)chunk * p.c + f0) * (D / 2) + tid;
 #pragma unroll
     for (int f = 0; f < FG; ++f) {
-      const float mean = s_mean[f], rstd = s_rstd[f];
-      const float a0 = rstd * lw0, a1 = rstd * lw1;
-      const float y0 = fmaf(f32x2_lo(o[f]), a0, fmaf(-mean, a0, lb0));
-      const float y1 = fmaf(f32x2_hi(o[f]), a1, fmaf(-mean, a1, lb1));
-      zp[(long long)f * (D / 2)] = pack_bf16(silu_fast(y0), silu_fast(y1));
+      const float rf = __shfl_sync(0xffffffffu, rs, f), mf = __shfl_sync(0xffffffffu, nm, f);
+      const unsigned long long h = ffma2(ffma2(o[f], pack_f32x2(rf, rf), pack_f32x2(mf, mf)), lwh2, lbh2);   // half the LayerNorm output
+      const unsigned long long th = pack_f32x2(tanh_approx(f32x2_lo(h)), tanh_approx(f32x2_hi(h)));
+      const unsigned long long z = ffma2(h, th, h);
+      zp[(long long)f * (D / 2)] = pack_bf16(f32x2_lo(z), f32x2_hi(z));
     }
   }
 }
