@@ -981,6 +981,38 @@ extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, i
   return CF_OK;
 }
 
+extern "C" size_t cf_ctc_compact_workspace_bytes(int64_t rows) {
+  const int64_t blocks = (rows + CTC_COMPACT_TILE - 1) / CTC_COMPACT_TILE;
+  return size_t(blocks > 0 ? blocks : 1) * sizeof(int) + 256;
+}
+
+extern "C" int cf_ctc_compact(const int64_t* tokens, int64_t rows, const int64_t* seg_start, const int32_t* seg_len, int n_seg,
+                              int mode, int64_t blank_id, int64_t* out_tokens, int32_t* out_frames, int64_t* out_offsets,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!tokens || !seg_start || !seg_len || !out_tokens || !out_frames || !out_offsets || !workspace)
+    return fail(nullptr, CF_ERR_INVALID, "cf_ctc_compact: null argument");
+  if (rows < 0 || n_seg < 0 || (mode != 0 && mode != 1)) return fail(nullptr, CF_ERR_INVALID, "cf_ctc_compact: bad size or mode");
+  if (workspace_bytes < cf_ctc_compact_workspace_bytes(rows)) return fail(nullptr, CF_ERR_WORKSPACE, "cf_ctc_compact: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows == 0) {   // nothing to scan: every offset is 0
+    cudaError_t e = cudaMemsetAsync(out_offsets, 0, sizeof(int64_t) * (size_t(n_seg) + 1), st);
+    if (e != cudaSuccess) return fail(nullptr, CF_ERR_CUDA, std::string("cf_ctc_compact: ") + cudaGetErrorString(e));
+    return CF_OK;
+  }
+  CtcCompactParams p{};
+  p.tokens = reinterpret_cast<const long long*>(tokens); p.rows = rows;
+  p.seg_start = reinterpret_cast<const long long*>(seg_start); p.seg_len = seg_len; p.n_seg = n_seg; p.mode = mode;
+  p.blank = blank_id; p.out_tokens = reinterpret_cast<long long*>(out_tokens); p.out_frames = out_frames;
+  p.out_offsets = reinterpret_cast<long long*>(out_offsets); p.block_counts = static_cast<int*>(workspace);
+  const unsigned blocks = unsigned((rows + CTC_COMPACT_TILE - 1) / CTC_COMPACT_TILE);
+  ctc_compact_count_kernel<<<blocks, CTC_COMPACT_THREADS, 0, st>>>(p);
+  ctc_compact_scatter_kernel<<<blocks, CTC_COMPACT_THREADS, 0, st>>>(p);
+  cf::g_kernel_launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, CF_ERR_CUDA, std::string("cf_ctc_compact: ") + cudaGetErrorString(e));
+  return CF_OK;
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // kernel-level entry points
 // --------------------------------------------------------------------------------------------------------------------

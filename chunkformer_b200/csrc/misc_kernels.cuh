@@ -74,4 +74,130 @@ __global__ void log_softmax_rows_kernel(float* x, long long rows, int V) {
   for (int i = lane; i < V; i += 32) r[i] -= lse;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-side CTC token compaction (utils/model_utils.py:23-32 and the blank filter of :186-196).
+// Greedy token ids stay on the device as a flat row buffer in which utterance s owns rows [seg_start[s], seg_start[s] +
+// seg_len[s]) (chunk padding rows in between belong to nobody).  mode 0 keeps a row when its token is not blank and differs
+// from the previous row of the same utterance (remove_duplicates_and_blank); mode 1 keeps every non-blank row (the frames
+// get_output_with_timestamps collects before it collapses each segment).  Kept (token, frame-in-utterance) pairs are
+// written compactly in row order; out_offsets[s] is the position of utterance s's first pair, out_offsets[n_seg] the total.
+// Two launches, no spin-waits: per-block keep counts, then every block sums the counts of the blocks before it (at most a
+// few hundred values), scans its own 2048 rows and scatters.
+// ---------------------------------------------------------------------------------------------
+constexpr int CTC_COMPACT_THREADS = 256;
+constexpr int CTC_COMPACT_ITEMS = 8;
+constexpr int CTC_COMPACT_TILE = CTC_COMPACT_THREADS * CTC_COMPACT_ITEMS;
+
+struct CtcCompactParams {
+  const long long* tokens;
+  long long rows;
+  const long long* seg_start;   // [n_seg] ascending
+  const int* seg_len;           // [n_seg]
+  int n_seg;
+  int mode;
+  long long blank;
+  long long* out_tokens;
+  int* out_frames;
+  long long* out_offsets;       // [n_seg + 1]
+  int* block_counts;            // [num_blocks]
+};
+
+// last segment whose first row is <= row (-1 if none)
+CF_DEVINL int ctc_segment_of(const long long* seg_start, int n_seg, long long row) {
+  int lo = 0, hi = n_seg;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(seg_start + mid) <= row) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+CF_DEVINL bool ctc_keep(const CtcCompactParams& p, long long row, int* seg_out, long long* frame_out) {
+  if (row >= p.rows) return false;
+  const int s = ctc_segment_of(p.seg_start, p.n_seg, row);
+  if (s < 0) return false;
+  const long long f = row - __ldg(p.seg_start + s);
+  *seg_out = s; *frame_out = f;
+  if (f >= (long long)__ldg(p.seg_len + s)) return false;
+  const long long tok = __ldg(p.tokens + row);
+  if (tok == p.blank) return false;
+  if (p.mode == 0 && f > 0 && __ldg(p.tokens + row - 1) == tok) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(CTC_COMPACT_THREADS) ctc_compact_count_kernel(CtcCompactParams p) {
+  __shared__ int s_warp[CTC_COMPACT_THREADS / 32];
+  const long long base = (long long)blockIdx.x * CTC_COMPACT_TILE + (long long)threadIdx.x * CTC_COMPACT_ITEMS;
+  int n = 0, seg; long long fr;
+#pragma unroll
+  for (int i = 0; i < CTC_COMPACT_ITEMS; ++i) n += ctc_keep(p, base + i, &seg, &fr) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < CTC_COMPACT_THREADS / 32; ++w) t += s_warp[w];
+    p.block_counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(CTC_COMPACT_THREADS) ctc_compact_scatter_kernel(CtcCompactParams p) {
+  __shared__ long long s_red[CTC_COMPACT_THREADS / 32];
+  __shared__ int s_warp[CTC_COMPACT_THREADS / 32];
+  __shared__ long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // exclusive prefix of this block = sum of the counts of all earlier blocks
+  long long acc = 0;
+  for (int b = threadIdx.x; b < int(blockIdx.x); b += CTC_COMPACT_THREADS) acc += p.block_counts[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) s_red[warp] = acc;
+  const long long base = (long long)blockIdx.x * CTC_COMPACT_TILE + (long long)threadIdx.x * CTC_COMPACT_ITEMS;
+  bool keep[CTC_COMPACT_ITEMS]; int seg[CTC_COMPACT_ITEMS]; long long fr[CTC_COMPACT_ITEMS];
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < CTC_COMPACT_ITEMS; ++i) {
+    seg[i] = -1; fr[i] = -1;
+    keep[i] = ctc_keep(p, base + i, &seg[i], &fr[i]);
+    n += keep[i] ? 1 : 0;
+  }
+  int incl = n;                                   // inclusive scan of the per-thread counts inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < CTC_COMPACT_THREADS / 32; ++w) t += s_red[w];
+    s_base = t;
+  }
+  __syncthreads();
+  long long pos = s_base + (incl - n);
+  for (int w = 0; w < warp; ++w) pos += s_warp[w];
+#pragma unroll
+  for (int i = 0; i < CTC_COMPACT_ITEMS; ++i) {
+    const long long row = base + i;
+    // the row an utterance starts on publishes that utterance's output offset (and that of empty utterances sharing the row)
+    if (row < p.rows && fr[i] == 0) {
+      for (int s = seg[i]; s >= 0 && __ldg(p.seg_start + s) == row; --s) p.out_offsets[s] = pos;
+    }
+    if (keep[i]) {
+      p.out_tokens[pos] = __ldg(p.tokens + row);
+      p.out_frames[pos] = int(fr[i]);
+      ++pos;
+    }
+  }
+  // the thread that owns the last row closes the table: total, and utterances that start at or beyond the end of the buffer
+  if (base <= p.rows - 1 && p.rows - 1 < base + CTC_COMPACT_ITEMS) {
+    p.out_offsets[p.n_seg] = pos;
+    for (int s = p.n_seg - 1; s >= 0 && __ldg(p.seg_start + s) >= p.rows; --s) p.out_offsets[s] = pos;
+  }
+}
+
 }  // namespace cf

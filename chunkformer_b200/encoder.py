@@ -230,3 +230,27 @@ class ChunkFormerEncoderB200:
         if want_logp:
             res.append(logp.view(*lead, self.geo.vocab))
         return res[0] if len(res) == 1 else tuple(res)
+
+    @torch.no_grad()
+    def ctc_compact(self, tokens: torch.Tensor, seg_start: Sequence[int], seg_len: Sequence[int], mode: int = 0,
+                    blank_id: int = 0):
+        """Device-side CTC compaction of greedy token ids (utils/model_utils.py:23-32, :186-196), so that only the kept
+        tokens are copied to the host.  tokens: device int64, flat rows; utterance s owns rows [seg_start[s], seg_start[s] +
+        seg_len[s]).  mode 0 = remove_duplicates_and_blank, mode 1 = drop blanks only.
+        Returns one (token ids int64, frame indices int32) pair of host tensors per utterance."""
+        t = tokens.reshape(-1).to(self.device, torch.int64).contiguous()
+        rows, n = t.numel(), len(seg_start)
+        st = torch.tensor([int(v) for v in seg_start], dtype=torch.int64).to(self.device, non_blocking=True)
+        ln = torch.tensor([max(int(v), 0) for v in seg_len], dtype=torch.int32).to(self.device, non_blocking=True)
+        out_tok = torch.empty(max(rows, 1), dtype=torch.int64, device=self.device)
+        out_fr = torch.empty(max(rows, 1), dtype=torch.int32, device=self.device)
+        offs = torch.empty(n + 1, dtype=torch.int64, device=self.device)
+        ws = torch.empty(int(self._L.cf_ctc_compact_workspace_bytes(rows)), dtype=torch.uint8, device=self.device)
+        rc = self._L.cf_ctc_compact(c_void_p(t.data_ptr()), rows, c_void_p(st.data_ptr()), c_void_p(ln.data_ptr()), n, int(mode),
+                                    int(blank_id), c_void_p(out_tok.data_ptr()), c_void_p(out_fr.data_ptr()),
+                                    c_void_p(offs.data_ptr()), c_void_p(ws.data_ptr()), ws.numel(), self._stream())
+        _lib.check(rc, None, "cf_ctc_compact")
+        o = offs.cpu().tolist()
+        total = o[-1]
+        tok_h, fr_h = out_tok[:total].cpu(), out_fr[:total].cpu()
+        return [(tok_h[o[s]:o[s + 1]], fr_h[o[s]:o[s + 1]]) for s in range(n)]

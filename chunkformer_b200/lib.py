@@ -50,6 +50,9 @@ SIGNATURES = {
                           c_size_t, c_void_p]),
     "cf_ctc_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "cf_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cf_ctc_compact_workspace_bytes": (c_size_t, [c_int64]),
+    "cf_ctc_compact": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
     "cf_op_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_int64, c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_op_layernorm": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

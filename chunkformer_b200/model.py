@@ -14,7 +14,7 @@ import torch
 
 from .encoder import ChunkFormerEncoderB200
 from .geometry import EncoderGeometry
-from .postprocess import get_output, get_output_with_timestamps
+from .postprocess import get_output, get_output_with_timestamps, get_output_with_timestamps_compact, ids_to_text
 
 
 def load_cmvn_json(path: str):
@@ -207,7 +207,12 @@ class ChunkFormerModel:
         enc = torch.cat(outs, dim=1)
         tokens = self.ctc.argmax(enc).reshape(1, -1, 1)
         if self.char_dict is not None:
-            res = get_output_with_timestamps(tokens, self.char_dict, self.model_type, max_silence_duration)[0]
+            # only the non-blank frames cross PCIe (cf_ctc_compact mode 1); segmentation runs on that short list and gives
+            # exactly what get_output_with_timestamps gives on the full frame sequence (tests/test_postprocess.py)
+            n_frames = tokens.shape[1]
+            (tok, frames), = self.encoder.ctc_compact(tokens, [0], [n_frames], mode=1)
+            res = get_output_with_timestamps_compact(frames, tok, n_frames, self.char_dict, self.model_type,
+                                                     max_silence_duration) if n_frames > 0 else []
             if not return_timestamps:
                 res = " ".join(item["decode"] for item in res).strip()
             return res
@@ -234,10 +239,20 @@ class ChunkFormerModel:
                 out, enc_lens, n_chunks, _, _, _ = self.encoder.forward_parallel_chunk(
                     xs=xs, xs_origin_lens=torch.tensor(lens, dtype=torch.int), chunk_size=c, left_context_size=l,
                     right_context_size=r, offset=torch.zeros(len(xs), dtype=torch.int))
-                hyps = self.ctc.argmax(out).split(n_chunks, dim=0)
-                hyps = [h.flatten()[:max(int(m), 0)] for h, m in zip(hyps, enc_lens)]
-                if self.char_dict is not None:
-                    hyps = get_output(hyps, self.char_dict, self.model_type)
+                tokens = self.ctc.argmax(out)
+                if self.char_dict is not None and self.model_type == "asr_model":
+                    # CTC collapse on the device (cf_ctc_compact mode 0): one short id list per utterance comes back
+                    starts, row = [], 0
+                    for n in n_chunks:
+                        starts.append(row * c)
+                        row += int(n)
+                    pairs = self.encoder.ctc_compact(tokens, starts, [max(int(m), 0) for m in enc_lens], mode=0)
+                    hyps = [ids_to_text(tok.tolist(), self.char_dict).strip() for tok, _ in pairs]
+                else:
+                    hyps = tokens.split(n_chunks, dim=0)
+                    hyps = [h.flatten()[:max(int(m), 0)] for h, m in zip(hyps, enc_lens)]
+                    if self.char_dict is not None:
+                        hyps = get_output(hyps, self.char_dict, self.model_type)
                 decodes.extend(hyps)
                 xs, lens, budget = [], [], budget0
         return decodes

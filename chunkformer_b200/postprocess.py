@@ -74,3 +74,43 @@ def get_output_with_timestamps(hyps, char_dict: Dict[int, str], model_type: str,
                          "start": format_ms(start * 80), "end": format_ms(t * 80)})
         results.append(segs)
     return results
+
+
+def get_output_with_timestamps_compact(frames: Sequence[int], tokens: Sequence[int], n_frames: int, char_dict: Dict[int, str],
+                                       model_type: str, max_silence_duration: float):
+    """`get_output_with_timestamps` for ONE CTC hypothesis given only its non-blank frames (ascending frame indices and
+    their token ids, as produced on the device by `cf_ctc_compact` mode 1) and the number of encoder frames: the same
+    segments, texts and stamps as the frame-by-frame loop (utils/model_utils.py:174-222), in O(#non-blank) host work.
+
+    A segment that saw its last non-blank frame at `last` closes at frame `last + max_silence` when no other non-blank
+    frame arrives up to and including that frame and the frame exists; otherwise it runs to the last frame."""
+    max_silence = max_silence_duration // 0.08
+    frames = [int(f) for f in (frames.tolist() if torch.is_tensor(frames) else frames)]
+    tokens = [int(t) for t in (tokens.tolist() if torch.is_tensor(tokens) else tokens)]
+    segs = []
+    prev_end = -1
+    i, n = 0, len(frames)
+    while i < n:
+        t0 = frames[i]
+        start = max(math.ceil((t0 + prev_end) / 2), t0 - 2) if prev_end != -1 else max(t0 - 2, 0)
+        pending = [tokens[i]]
+        last = t0
+        i += 1
+        while i < n and max_silence > 0 and frames[i] - last <= max_silence:
+            pending.append(tokens[i])
+            last = frames[i]
+            i += 1
+        end = last + max_silence
+        if max_silence >= 0 and end <= n_frames - 1:
+            end = int(end)
+            prev_end = end
+            segs.append({"decode": get_output([pending], char_dict, model_type)[0],
+                         "start": format_ms(start * 80), "end": format_ms(end * 80)})
+        else:
+            # the silence counter never reaches the threshold before the stream ends: every remaining frame joins this segment
+            while i < n:
+                pending.append(tokens[i])
+                i += 1
+            segs.append({"decode": get_output([pending], char_dict, model_type)[0],
+                         "start": format_ms(start * 80), "end": format_ms((n_frames - 1) * 80)})
+    return segs

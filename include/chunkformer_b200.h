@@ -147,6 +147,17 @@ CF_API size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows);
 CF_API int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, int64_t* tokens_out, float* margin_out,
                   float* logp_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Replaces: remove_duplicates_and_blank (chunkformer/utils/model_utils.py:23-32) and the per-frame blank filter of
+ * get_output_with_timestamps (:186-196), so that only the kept tokens cross PCIe instead of one id per encoder frame.
+ * tokens: device int64 [rows] (cf_ctc_greedy output); utterance s owns rows [seg_start[s], seg_start[s] + seg_len[s]),
+ * seg_start ascending (device int64 [n_seg], device int32 [n_seg]).  mode 0: CTC collapse (drop repeats, then blanks);
+ * mode 1: drop blanks only.  out_tokens / out_frames: device [rows] capacity, kept tokens and their frame index inside the
+ * utterance, in row order; out_offsets: device int64 [n_seg + 1], first output position of every utterance and the total. */
+CF_API size_t cf_ctc_compact_workspace_bytes(int64_t rows);
+CF_API int cf_ctc_compact(const int64_t* tokens, int64_t rows, const int64_t* seg_start, const int32_t* seg_len, int n_seg,
+                   int mode, int64_t blank_id, int64_t* out_tokens, int32_t* out_frames, int64_t* out_offsets,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- kernel-level entry points (parity tests, profiling) --------------------------------------------------------- */
 /* C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 GEMM with a fused epilogue; epi: 0 bf16 out = act(acc+bias), 1 GLU (bf16,
  * N/2 columns, value/gate rows interleaved), 2 fp32 out = resid + rowmask*alpha*(acc+bias), 4 argmax partials

@@ -190,3 +190,66 @@ def test_long_recording_chunk_range_shards_equal_unsharded(asr):
     sharded = torch.cat(parts, 0)
     assert sharded.shape == full.shape
     assert (sharded - full).abs().max().item() < 0.03
+
+
+# ------------------------------------------------------------------------------------------------ device CTC compaction
+def _host_compact(tokens, starts, lens, mode):
+    from chunkformer_b200.postprocess import ctc_collapse
+    res = []
+    for s, n in zip(starts, lens):
+        seg = tokens[s:s + n].tolist()
+        if mode == 1:
+            keep = [(t, i) for i, t in enumerate(seg) if t != 0]
+        else:
+            keep = [(t, i) for i, t in enumerate(seg) if t != 0 and (i == 0 or seg[i - 1] != t)]
+            assert [t for t, _ in keep] == ctc_collapse(seg)
+        res.append(keep)
+    return res
+
+
+@pytest.mark.parametrize("rows,blank_p", [(1, 0.5), (37, 0.0), (2048, 0.9), (2049, 0.5), (50000, 0.97), (70001, 0.3)])
+def test_ctc_compact_bit_exact(asr, rows, blank_p):
+    """cf_ctc_compact == remove_duplicates_and_blank / blank filter per utterance (bit-exact ids, frame indices, offsets):
+    ragged utterances with chunk padding rows between them, empty utterances (also sharing a start row, also at the very
+    end of the buffer), runs of repeats crossing the 2048-row tile boundary."""
+    gen = torch.Generator().manual_seed(rows)
+    tok = torch.randint(1, 6, (rows,), generator=gen)
+    tok = tok.repeat_interleave(torch.randint(1, 4, (rows,), generator=gen))[:rows]       # runs of repeated ids
+    tok[torch.rand(rows, generator=gen) < blank_p] = 0
+    starts, lens, pos = [], [], 0
+    while pos < rows:
+        n = int(torch.randint(0, max(2, rows // 3), (1,), generator=gen))
+        n = min(n, rows - pos)
+        starts.append(pos); lens.append(n)
+        if torch.rand(1, generator=gen) < 0.3:
+            starts.append(pos); lens.append(0)            # empty utterance in front of the next one's rows
+            starts[-2], starts[-1] = starts[-1], starts[-2]; lens[-2], lens[-1] = lens[-1], lens[-2]
+        pos += n + int(torch.randint(0, 70, (1,), generator=gen))                           # padding rows owned by nobody
+    starts.append(rows); lens.append(0)                   # empty utterance at the end of the buffer
+    dtok = tok.to(DEV)
+    for mode in (0, 1):
+        got = asr.encoder.ctc_compact(dtok, starts, lens, mode=mode)
+        want = _host_compact(tok, starts, lens, mode)
+        assert len(got) == len(want)
+        for (gt, gf), w in zip(got, want):
+            assert gt.tolist() == [t for t, _ in w] and gf.tolist() == [i for _, i in w]
+
+
+def test_decode_text_equals_host_postprocessing_of_raw_tokens(asr):
+    """endless_decode / batch_decode texts (device compaction + short-list segmentation) == the reference's host
+    post-processing (utils/model_utils.py:164-222, pinned in tests/test_postprocess.py) applied to the raw token ids."""
+    from chunkformer_b200.postprocess import get_output, get_output_with_timestamps
+    x = synth_fbank(3300, seed=40)
+    for ms in (0.0, 0.16, 0.5):
+        res = asr.endless_decode(x, 16, 32, 16, total_batch_duration=20, return_timestamps=True, max_silence_duration=ms)
+        cd, asr.char_dict = asr.char_dict, None
+        raw = asr.endless_decode(x, 16, 32, 16, total_batch_duration=20)
+        asr.char_dict = cd
+        assert res == get_output_with_timestamps(raw.cpu(), cd, "asr_model", ms)[0]
+    lens = [900, 77, 1500, 10, 300]
+    xs = [synth_fbank(t, seed=60 + k) for k, t in enumerate(lens)]
+    texts = asr.batch_decode(xs, 16, 32, 16, total_batch_duration=30)
+    cd, asr.char_dict = asr.char_dict, None
+    hyps = asr.batch_decode(xs, 16, 32, 16, total_batch_duration=30)
+    asr.char_dict = cd
+    assert texts == get_output([h.cpu() for h in hyps], cd, "asr_model")
