@@ -93,3 +93,32 @@ MASKED_BATCH_SECONDS: List[float] = [1, 30, 60, 900, 1800, 3600] * 2 + [1000, 50
 
 def masked_batch_lengths(scale: float = 1.0) -> List[int]:
     return [max(frames_of_seconds(s * scale), 16) for s in MASKED_BATCH_SECONDS]
+
+
+def synth_transducer_state_dict(vocab: int, embed: int, hidden: int, layers: int, pred_out: int, enc_dim: int, join_dim: int,
+                                blank_bias: float = 3.0, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Random predictor + joint weights keyed like the reference transducer checkpoint (`predictor.*`, `joint.*`;
+    transducer/predictor.py:69-96, joint.py:36-52).  `blank_bias` is added to the blank logit so that, as with a trained
+    model, most frames emit blank (a random joint would emit a symbol on nearly every step)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {"predictor.embed.weight": _n(g, (vocab, embed), 1.0)}
+    b = 1.0 / math.sqrt(hidden)
+    for layer in range(layers):
+        inp = embed if layer == 0 else hidden
+        sd[f"predictor.rnn.weight_ih_l{layer}"] = _u(g, (4 * hidden, inp), b)
+        sd[f"predictor.rnn.weight_hh_l{layer}"] = _u(g, (4 * hidden, hidden), b)
+        sd[f"predictor.rnn.bias_ih_l{layer}"] = _u(g, (4 * hidden,), b)
+        sd[f"predictor.rnn.bias_hh_l{layer}"] = _u(g, (4 * hidden,), b)
+
+    def linear(prefix, out_f, in_f, scale=1.0):
+        bound = scale / math.sqrt(in_f)
+        sd[prefix + ".weight"] = _u(g, (out_f, in_f), bound)
+        sd[prefix + ".bias"] = _u(g, (out_f,), bound)
+
+    linear("predictor.projection", pred_out, hidden, 2.0)
+    linear("joint.enc_ffn", join_dim, enc_dim, 2.0)
+    linear("joint.pred_ffn", join_dim, pred_out, 0.7)
+    linear("joint.ffn_out", vocab, join_dim, 4.0)
+    sd["joint.ffn_out.bias"][0] += blank_bias
+    return sd
