@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libchunkformer_b200.so")
 SOURCES = ["api.cu", "plan.cpp"]
-HEADERS = ["common.cuh", "gemm.cuh", "gemm_host.cuh", "norm_conv.cuh", "frontend.cuh", "attention_simt.cuh",
+HEADERS = ["common.cuh", "transducer.cuh", "gemm.cuh", "gemm_host.cuh", "norm_conv.cuh", "frontend.cuh", "attention_simt.cuh",
            "attention_tc.cuh", "fbank.cuh", "misc_kernels.cuh", "plan.h", os.path.join("..", "..", "include", "chunkformer_b200.h")]
 
 

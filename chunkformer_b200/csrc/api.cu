@@ -18,6 +18,7 @@
 #include "misc_kernels.cuh"
 #include "norm_conv.cuh"
 #include "plan.h"
+#include "transducer.cuh"
 
 using namespace cf;
 typedef __nv_bfloat16 bf16;
@@ -1010,6 +1011,229 @@ extern "C" int cf_ctc_compact(const int64_t* tokens, int64_t rows, const int64_t
   cf::g_kernel_launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(nullptr, CF_ERR_CUDA, std::string("cf_ctc_compact: ") + cudaGetErrorString(e));
+  return CF_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// transducer greedy search (transducer.cuh)
+// --------------------------------------------------------------------------------------------------------------------
+struct cf_rnnt {
+  cf_rnnt_config cfg{};
+  int device = 0;
+  bool finalized = false;
+  std::string err;
+  std::map<std::string, std::vector<float>> host;     // checkpoint tensors until finalize
+  std::map<std::string, std::vector<int64_t>> shape;
+  float *embed = nullptr, *enc_w = nullptr, *enc_b = nullptr, *wc = nullptr, *bc = nullptr, *woT = nullptr, *bo = nullptr;
+  std::vector<float*> w_ih, w_hh, b_ih, b_hh;
+  std::vector<void*> owned;
+  ~cf_rnnt() { for (void* q : owned) cudaFree(q); }
+};
+static int rfail(cf_rnnt* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_last_error = msg;
+  return code;
+}
+#define CF_RCUDA(h, call)                                                                                        \
+  do {                                                                                                           \
+    cudaError_t e__ = (call);                                                                                    \
+    if (e__ != cudaSuccess) return rfail(h, CF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+
+extern "C" const char* cf_rnnt_last_error(const cf_rnnt* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int cf_rnnt_create(const cf_rnnt_config* cfg, int device, cf_rnnt** out) {
+  if (!cfg || !out) return rfail(nullptr, CF_ERR_INVALID, "cf_rnnt_create: null argument");
+  *out = nullptr;
+  const cf_rnnt_config& c = *cfg;
+  if (c.vocab <= 1 || c.layers < 1 || c.layers > 8 || c.blank < 0 || c.blank >= c.vocab)
+    return rfail(nullptr, CF_ERR_INVALID, "cf_rnnt_create: bad vocab / layers / blank");
+  if (c.embed <= 0 || c.hidden <= 0 || c.pred_out <= 0 || c.enc_dim <= 0 || c.join_dim <= 0 || c.embed % 4 || c.hidden % 4 ||
+      c.join_dim % 4 || c.join_dim > 1024)
+    return rfail(nullptr, CF_ERR_INVALID, "cf_rnnt_create: embed / hidden / join_dim must be positive multiples of 4 (join_dim <= 1024)");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n)
+    return rfail(nullptr, CF_ERR_CUDA, "cf_rnnt_create: no such CUDA device (there is no CPU fallback)");
+  cf_rnnt* h = new cf_rnnt();
+  h->cfg = c; h->device = device;
+  *out = h;
+  return CF_OK;
+}
+extern "C" void cf_rnnt_destroy(cf_rnnt* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+extern "C" int cf_rnnt_load_tensor(cf_rnnt* h, const char* key, const float* host_f32, int ndim, const int64_t* shape) {
+  if (!h || !key || !host_f32 || ndim < 1 || ndim > 2 || !shape) return rfail(h, CF_ERR_INVALID, "cf_rnnt_load_tensor: bad argument");
+  if (h->finalized) return rfail(h, CF_ERR_STATE, "cf_rnnt_load_tensor: weights already finalized");
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= size_t(shape[i]);
+  h->host[key].assign(host_f32, host_f32 + n);
+  h->shape[key].assign(shape, shape + ndim);
+  return CF_OK;
+}
+
+extern "C" int cf_rnnt_finalize_weights(cf_rnnt* h) {
+  if (!h) return rfail(nullptr, CF_ERR_INVALID, "cf_rnnt_finalize_weights: null handle");
+  if (h->finalized) return CF_OK;
+  const cf_rnnt_config& c = h->cfg;
+  CF_RCUDA(h, cudaSetDevice(h->device));
+  auto need = [&](const std::string& k, std::vector<int64_t> want, const std::vector<float>** out) -> bool {
+    auto it = h->host.find(k);
+    if (it == h->host.end()) { h->err = "cf_rnnt_finalize_weights: missing tensor " + k; return false; }
+    if (h->shape[k] != want) { h->err = "cf_rnnt_finalize_weights: wrong shape for " + k; return false; }
+    *out = &it->second;
+    return true;
+  };
+  auto upload = [&](const float* src, size_t n, float** dst) -> bool {
+    void* d = nullptr;
+    if (cudaMalloc(&d, n * sizeof(float)) != cudaSuccess) { h->err = "cf_rnnt_finalize_weights: cudaMalloc failed"; return false; }
+    h->owned.push_back(d);
+    if (cudaMemcpy(d, src, n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "cf_rnnt_finalize_weights: copy failed"; return false; }
+    *dst = static_cast<float*>(d);
+    return true;
+  };
+#define RN_NEED(key, shape_, var) const std::vector<float>* var; if (!need(key, shape_, &var)) { g_last_error = h->err; return CF_ERR_STATE; }
+#define RN_UP(src, n, dst) if (!upload(src, n, dst)) { g_last_error = h->err; return CF_ERR_CUDA; }
+  const int64_t V = c.vocab, E = c.embed, H = c.hidden, P = c.pred_out, D = c.enc_dim, J = c.join_dim;
+  RN_NEED("predictor.embed.weight", (std::vector<int64_t>{V, E}), emb);
+  RN_UP(emb->data(), emb->size(), &h->embed);
+  h->w_ih.resize(c.layers); h->w_hh.resize(c.layers); h->b_ih.resize(c.layers); h->b_hh.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    const std::string sfx = "_l" + std::to_string(l);
+    const int64_t in = l == 0 ? E : H;
+    RN_NEED("predictor.rnn.weight_ih" + sfx, (std::vector<int64_t>{4 * H, in}), wih);
+    RN_NEED("predictor.rnn.weight_hh" + sfx, (std::vector<int64_t>{4 * H, H}), whh);
+    RN_NEED("predictor.rnn.bias_ih" + sfx, (std::vector<int64_t>{4 * H}), bih);
+    RN_NEED("predictor.rnn.bias_hh" + sfx, (std::vector<int64_t>{4 * H}), bhh);
+    RN_UP(wih->data(), wih->size(), &h->w_ih[l]); RN_UP(whh->data(), whh->size(), &h->w_hh[l]);
+    RN_UP(bih->data(), bih->size(), &h->b_ih[l]); RN_UP(bhh->data(), bhh->size(), &h->b_hh[l]);
+  }
+  RN_NEED("predictor.projection.weight", (std::vector<int64_t>{P, H}), pw);
+  RN_NEED("predictor.projection.bias", (std::vector<int64_t>{P}), pb);
+  RN_NEED("joint.enc_ffn.weight", (std::vector<int64_t>{J, D}), ew);
+  RN_NEED("joint.enc_ffn.bias", (std::vector<int64_t>{J}), eb);
+  RN_NEED("joint.pred_ffn.weight", (std::vector<int64_t>{J, P}), fw);
+  RN_NEED("joint.pred_ffn.bias", (std::vector<int64_t>{J}), fb);
+  RN_NEED("joint.ffn_out.weight", (std::vector<int64_t>{V, J}), ow);
+  RN_NEED("joint.ffn_out.bias", (std::vector<int64_t>{V}), ob);
+  RN_UP(ew->data(), ew->size(), &h->enc_w); RN_UP(eb->data(), eb->size(), &h->enc_b); RN_UP(ob->data(), ob->size(), &h->bo);
+  {  // pred_ffn o projection composed in fp64 (predictor.py:205 + joint.py:88)
+    std::vector<float> wc(size_t(J) * H), bcv(J);
+    std::vector<double> row(H);
+    for (int64_t r = 0; r < J; ++r) {
+      std::fill(row.begin(), row.end(), 0.0);
+      double bacc = (*fb)[r];
+      for (int64_t q = 0; q < P; ++q) {
+        const double f = (*fw)[r * P + q];
+        bacc += f * (*pb)[q];
+        const float* pr = pw->data() + q * H;
+        for (int64_t k = 0; k < H; ++k) row[k] += f * pr[k];
+      }
+      for (int64_t k = 0; k < H; ++k) wc[r * H + k] = float(row[k]);
+      bcv[r] = float(bacc);
+    }
+    RN_UP(wc.data(), wc.size(), &h->wc); RN_UP(bcv.data(), bcv.size(), &h->bc);
+    std::vector<float> wt(size_t(J) * V);
+    for (int64_t v = 0; v < V; ++v)
+      for (int64_t k = 0; k < J; ++k) wt[k * V + v] = (*ow)[v * J + k];
+    RN_UP(wt.data(), wt.size(), &h->woT);
+  }
+#undef RN_NEED
+#undef RN_UP
+  h->host.clear(); h->shape.clear();
+  h->finalized = true;
+  return CF_OK;
+}
+
+struct RnntWs {
+  RnntState s; float* E; long long* seg_start; int* seg_len; size_t bytes; size_t state_floats; int n_vtiles;
+};
+static RnntWs rnnt_carve(const cf_rnnt_config& c, int64_t rows, int B, void* base) {
+  Carver cv(base);
+  RnntWs w{};
+  w.n_vtiles = (c.vocab + RNNT_JV - 1) / RNNT_JV;
+  w.state_floats = size_t(2) * c.layers * B * c.hidden;
+  w.E = cv.take<float>(size_t(rows) * c.join_dim);
+  w.seg_start = cv.take<long long>(B); w.seg_len = cv.take<int>(B);
+  w.s.t = cv.take<int>(B); w.s.step = cv.take<int>(B); w.s.token = cv.take<int>(B); w.s.cur = cv.take<int>(B);
+  w.s.count = cv.take<int>(B); w.s.active = cv.take<int>(B);
+  w.s.n_active = cv.take<int>(1); w.s.remaining = cv.take<int>(1); w.s.overflow = cv.take<int>(1);
+  w.s.h = cv.take<float>(w.state_floats); w.s.c = cv.take<float>(w.state_floats);
+  w.s.g = cv.take<float>(size_t(B) * c.join_dim);
+  w.s.part_val = cv.take<float>(size_t(B) * RNNT_FB * w.n_vtiles);
+  w.s.part_idx = cv.take<int>(size_t(B) * RNNT_FB * w.n_vtiles);
+  w.bytes = cv.off + 256;
+  return w;
+}
+extern "C" size_t cf_rnnt_workspace_bytes(const cf_rnnt* h, int64_t rows, int n_utt) {
+  if (!h || rows < 0 || n_utt < 0) return 0;
+  return rnnt_carve(h->cfg, rows, n_utt > 0 ? n_utt : 1, nullptr).bytes;
+}
+
+extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, const int64_t* seg_start, const int32_t* seg_len,
+                              int n_utt, int n_steps, int capacity, int64_t* out_tokens, int32_t* out_frames,
+                              int32_t* out_counts, int64_t* iterations_out, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (!h || !enc_f32 || !seg_start || !seg_len || !out_tokens || !out_frames || !out_counts || !workspace)
+    return rfail(h, CF_ERR_INVALID, "cf_rnnt_greedy: null argument");
+  if (!h->finalized) return rfail(h, CF_ERR_STATE, "cf_rnnt_greedy: weights not finalized");
+  if (n_utt <= 0 || n_steps <= 0 || capacity <= 0 || rows < 0) return rfail(h, CF_ERR_INVALID, "cf_rnnt_greedy: bad sizes");
+  for (int b = 0; b < n_utt; ++b)
+    if (seg_len[b] < 0 || seg_start[b] < 0 || seg_start[b] + seg_len[b] > rows)
+      return rfail(h, CF_ERR_INVALID, "cf_rnnt_greedy: utterance rows outside the encoder buffer");
+  const cf_rnnt_config& c = h->cfg;
+  RnntWs w = rnnt_carve(c, rows, n_utt, workspace);
+  if (workspace_bytes < w.bytes) return rfail(h, CF_ERR_WORKSPACE, "cf_rnnt_greedy: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CF_RCUDA(h, cudaSetDevice(h->device));
+  CF_RCUDA(h, cudaMemcpyAsync(w.seg_start, seg_start, sizeof(int64_t) * n_utt, cudaMemcpyHostToDevice, st));
+  CF_RCUDA(h, cudaMemcpyAsync(w.seg_len, seg_len, sizeof(int32_t) * n_utt, cudaMemcpyHostToDevice, st));
+  if (rows > 0) {
+    dim3 grid(unsigned((c.join_dim + 63) / 64), unsigned((rows + 63) / 64));
+    rnnt_linear_f32_kernel<<<grid, 256, 0, st>>>(enc_f32, h->enc_w, h->enc_b, w.E, rows, c.join_dim, c.enc_dim);
+    ++cf::g_kernel_launches;
+  }
+  rnnt_init_kernel<<<64, 256, 0, st>>>(w.s, w.seg_len, out_counts, n_utt, c.blank, w.state_floats);
+  ++cf::g_kernel_launches;
+  CF_RCUDA(h, cudaGetLastError());
+  RnntJointParams jp{w.E, h->woT, h->bo, w.seg_start, w.seg_len, c.join_dim, c.vocab, w.n_vtiles};
+  RnntDecideParams dp{w.seg_len, reinterpret_cast<long long*>(out_tokens), out_frames, out_counts, n_utt, w.n_vtiles, n_steps,
+                      capacity, c.blank};
+  auto iteration = [&]() {
+    for (int l = 0; l < c.layers; ++l) {
+      RnntLstmParams lp{h->w_ih[l], h->w_hh[l], h->b_ih[l], h->b_hh[l], l == 0 ? h->embed : nullptr, l, l == 0 ? c.embed : c.hidden,
+                        c.hidden, n_utt, c.layers};
+      rnnt_lstm_kernel<<<unsigned((c.hidden + 3) / 4), 128, 0, st>>>(lp, w.s);
+    }
+    rnnt_predproj_kernel<<<unsigned((c.join_dim + 3) / 4), 128, 0, st>>>(h->wc, h->bc, c.join_dim, c.hidden, n_utt, c.layers, w.s);
+    dim3 jg(unsigned(w.n_vtiles), unsigned(n_utt));
+    if (c.join_dim <= 512) rnnt_joint_kernel<512><<<jg, RNNT_JV, 0, st>>>(jp, w.s);
+    else rnnt_joint_kernel<1024><<<jg, RNNT_JV, 0, st>>>(jp, w.s);
+    rnnt_decide_kernel<<<1, 256, 0, st>>>(dp, w.s);
+    cf::g_kernel_launches += c.layers + 3;
+  };
+  // the host only learns how far the search is by reading `remaining`; a burst of iterations is enqueued between reads
+  // (iterations after the last utterance finished are empty launches)
+  int state[2] = {1, 0};   // remaining, overflow
+  int64_t iters = 0, max_len = 0;
+  for (int b = 0; b < n_utt; ++b) max_len = seg_len[b] > max_len ? seg_len[b] : max_len;
+  // every iteration emits a symbol or moves at least one frame forward in each unfinished utterance
+  const int64_t bound = max_len * (int64_t(n_steps) + 1) + 1;
+  const int burst = 64;
+  while (state[0] > 0) {
+    if (iters > bound) return rfail(h, CF_ERR_STATE, "cf_rnnt_greedy: search did not terminate (internal error)");
+    for (int i = 0; i < burst; ++i) iteration();
+    iters += burst;
+    CF_RCUDA(h, cudaGetLastError());
+    CF_RCUDA(h, cudaMemcpyAsync(&state[0], w.s.remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CF_RCUDA(h, cudaMemcpyAsync(&state[1], w.s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CF_RCUDA(h, cudaStreamSynchronize(st));
+  }
+  if (iterations_out) *iterations_out = iters;
+  if (state[1]) return rfail(h, CF_ERR_WORKSPACE, "cf_rnnt_greedy: an utterance emitted more than `capacity` symbols");
   return CF_OK;
 }
 

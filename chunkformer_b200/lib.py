@@ -10,6 +10,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 from . import build as _build
 
 CF_F32, CF_BF16 = 0, 1
+CF_OK, CF_ERR_INVALID, CF_ERR_CUDA, CF_ERR_STATE, CF_ERR_WORKSPACE = 0, -1, -2, -3, -4
 EPI_BF16, EPI_GLU, EPI_F32, EPI_ARGMAX = 0, 1, 2, 4
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 
@@ -53,6 +54,14 @@ SIGNATURES = {
     "cf_ctc_compact_workspace_bytes": (c_size_t, [c_int64]),
     "cf_ctc_compact": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
+    "cf_rnnt_create": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    "cf_rnnt_destroy": (None, [c_void_p]),
+    "cf_rnnt_last_error": (c_char_p, [c_void_p]),
+    "cf_rnnt_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64)]),
+    "cf_rnnt_finalize_weights": (c_int, [c_void_p]),
+    "cf_rnnt_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int]),
+    "cf_rnnt_greedy": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int32), c_int, c_int, c_int, c_void_p,
+                               c_void_p, c_void_p, POINTER(c_int64), c_void_p, c_size_t, c_void_p]),
     "cf_op_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                            c_int64, c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cf_op_layernorm": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -158,6 +158,38 @@ CF_API int cf_ctc_compact(const int64_t* tokens, int64_t rows, const int64_t* se
                    int mode, int64_t blank_id, int64_t* out_tokens, int32_t* out_frames, int64_t* out_offsets,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- transducer greedy search (the step after the encoder for chunkformer-rnnt-* models) ------------------------------- */
+/* Replaces: optimized_search / batch_greedy_search (chunkformer/transducer/search/greedy_search.py:6-99) with
+ * RNNPredictor.forward_step (transducer/predictor.py:190-207, LSTM) and TransducerJoint.forward (transducer/joint.py:69-101,
+ * prejoin_linear, joint_mode add, tanh, non-HAT), as called from chunkformer_model.py:440-447 and :528-541. */
+typedef struct cf_rnnt cf_rnnt;
+typedef struct cf_rnnt_config {
+  int32_t vocab;      /* joint output size (blank included) */
+  int32_t embed;      /* predictor_conf.embed_size */
+  int32_t hidden;     /* predictor_conf.hidden_size */
+  int32_t layers;     /* predictor_conf.num_layers (LSTM) */
+  int32_t pred_out;   /* predictor_conf.output_size */
+  int32_t enc_dim;    /* joint_conf.enc_output_size = encoder output_size */
+  int32_t join_dim;   /* joint_conf.join_dim */
+  int32_t blank;      /* blank id (0) */
+} cf_rnnt_config;
+CF_API int cf_rnnt_create(const cf_rnnt_config* cfg, int device, cf_rnnt** out);
+CF_API void cf_rnnt_destroy(cf_rnnt* h);
+CF_API const char* cf_rnnt_last_error(const cf_rnnt* h);
+/* One call per checkpoint tensor under `predictor.` / `joint.` (host fp32, any order), then finalize. */
+CF_API int cf_rnnt_load_tensor(cf_rnnt* h, const char* state_dict_key, const float* host_f32, int ndim, const int64_t* shape);
+CF_API int cf_rnnt_finalize_weights(cf_rnnt* h);
+CF_API size_t cf_rnnt_workspace_bytes(const cf_rnnt* h, int64_t rows, int n_utt);
+/* enc: device fp32 [rows, enc_dim] (encoder output); utterance b owns rows [seg_start[b], seg_start[b] + seg_len[b]) (HOST
+ * arrays).  Emits at most n_steps symbols per frame (greedy_search.py:10).  out_tokens / out_frames: device [n_utt, capacity]
+ * = symbols in emission order and the frame each was emitted on; out_counts: device int32 [n_utt].  The dense
+ * (T, n_steps) grid of optimized_search is (frame, k-th symbol of that frame).  Synchronises the stream (the host polls the
+ * number of unfinished utterances); iterations_out (optional, host) = search iterations enqueued.
+ * CF_ERR_WORKSPACE if an utterance needs more than `capacity` symbols. */
+CF_API int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, const int64_t* seg_start, const int32_t* seg_len,
+                   int n_utt, int n_steps, int capacity, int64_t* out_tokens, int32_t* out_frames, int32_t* out_counts,
+                   int64_t* iterations_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- kernel-level entry points (parity tests, profiling) --------------------------------------------------------- */
 /* C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 GEMM with a fused epilogue; epi: 0 bf16 out = act(acc+bias), 1 GLU (bf16,
  * N/2 columns, value/gate rows interleaved), 2 fp32 out = resid + rowmask*alpha*(acc+bias), 4 argmax partials
