@@ -14,6 +14,7 @@ import torch
 
 from .encoder import ChunkFormerEncoderB200
 from .geometry import EncoderGeometry
+from .transducer import TransducerGreedyB200
 from .postprocess import get_output, get_output_with_timestamps, get_output_with_timestamps_compact, ids_to_text
 
 
@@ -68,6 +69,11 @@ class ChunkFormerModel:
         self.geometry = geo
         self.encoder = ChunkFormerEncoderB200(geo, state_dict, self.device)
         self.ctc = _CTCHead(self.encoder) if vocab else None
+        # chunkformer-rnnt-*: LSTM predictor + joint behind the encoder (utils/init_model.py:118-133)
+        self.transducer = None
+        if self.model_type == "transducer" and "predictor.embed.weight" in state_dict:
+            blank = int(self.config.get("ctc_conf", {}).get("ctc_blank_id", 0))
+            self.transducer = TransducerGreedyB200(state_dict, blank=blank, device=self.device)
         self.char_dict: Optional[Dict[int, str]] = None
         self.label_mapping = None
         self.tasks = None
@@ -172,8 +178,8 @@ class ChunkFormerModel:
                        right_context_size: Optional[int] = 128, total_batch_duration: int = 1800,
                        return_timestamps: bool = True, max_silence_duration: float = 0.5):
         """chunkformer_model.py:320-459: sequential segments with K/V + conv caches carried between them."""
-        if self.ctc is None:
-            raise ValueError("endless_decode needs a CTC model (transducer search is out of scope)")
+        if self.model_type == "asr_model" and self.ctc is None or self.model_type != "asr_model" and self.transducer is None:
+            raise ValueError("endless_decode needs a CTC head (asr_model) or an LSTM predictor + joint (transducer)")
         c = chunk_size if chunk_size is not None else 64
         l = left_context_size if left_context_size is not None else 128
         r = right_context_size if right_context_size is not None else 128
@@ -205,6 +211,17 @@ class ChunkFormerModel:
             if last:
                 break
         enc = torch.cat(outs, dim=1)
+        if self.model_type != "asr_model":
+            # chunkformer_model.py:440-447: optimized_search on the whole recording, (1, T', n_steps) symbol grid
+            n_frames = enc.shape[1]
+            if self.char_dict is None:
+                return self.transducer.optimized_search(enc, [n_frames]).reshape(1, n_frames, -1)
+            (tok, frames), = self.transducer.search_flat(enc[0], [0], [n_frames])
+            res = get_output_with_timestamps_compact(frames, tok, n_frames, self.char_dict, self.model_type,
+                                                     max_silence_duration) if n_frames > 0 else []
+            if not return_timestamps:
+                res = " ".join(item["decode"] for item in res).strip()
+            return res
         tokens = self.ctc.argmax(enc).reshape(1, -1, 1)
         if self.char_dict is not None:
             # only the non-blank frames cross PCIe (cf_ctc_compact mode 1); segmentation runs on that short list and gives
@@ -223,8 +240,8 @@ class ChunkFormerModel:
     def batch_decode(self, audio_paths: List, chunk_size: Optional[int] = 64, left_context_size: Optional[int] = 128,
                      right_context_size: Optional[int] = 128, total_batch_duration: int = 1800):
         """chunkformer_model.py:461-552: greedy arrival-order admission, one masked batch per group."""
-        if self.ctc is None:
-            raise ValueError("batch_decode needs a CTC model (transducer search is out of scope)")
+        if self.model_type == "asr_model" and self.ctc is None or self.model_type != "asr_model" and self.transducer is None:
+            raise ValueError("batch_decode needs a CTC head (asr_model) or an LSTM predictor + joint (transducer)")
         c = chunk_size if chunk_size is not None else 64
         l = left_context_size if left_context_size is not None else 128
         r = right_context_size if right_context_size is not None else 128
@@ -239,6 +256,20 @@ class ChunkFormerModel:
                 out, enc_lens, n_chunks, _, _, _ = self.encoder.forward_parallel_chunk(
                     xs=xs, xs_origin_lens=torch.tensor(lens, dtype=torch.int), chunk_size=c, left_context_size=l,
                     right_context_size=r, offset=torch.zeros(len(xs), dtype=torch.int))
+                if self.model_type != "asr_model":
+                    # chunkformer_model.py:532-543: batch_greedy_search; the flat chunk rows are searched in place
+                    starts, row = [], 0
+                    for n in n_chunks:
+                        starts.append(row * c)
+                        row += int(n)
+                    pairs = self.transducer.search_flat(out.reshape(-1, out.shape[-1]), starts,
+                                                        [max(int(m), 0) for m in enc_lens])
+                    hyps = [tok.tolist() for tok, _ in pairs]
+                    if self.char_dict is not None:
+                        hyps = get_output(hyps, self.char_dict, self.model_type)
+                    decodes.extend(hyps)
+                    xs, lens, budget = [], [], budget0
+                    continue
                 tokens = self.ctc.argmax(out)
                 if self.char_dict is not None and self.model_type == "asr_model":
                     # CTC collapse on the device (cf_ctc_compact mode 0): one short id list per utterance comes back

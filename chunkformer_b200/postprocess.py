@@ -78,8 +78,9 @@ def get_output_with_timestamps(hyps, char_dict: Dict[int, str], model_type: str,
 
 def get_output_with_timestamps_compact(frames: Sequence[int], tokens: Sequence[int], n_frames: int, char_dict: Dict[int, str],
                                        model_type: str, max_silence_duration: float):
-    """`get_output_with_timestamps` for ONE CTC hypothesis given only its non-blank frames (ascending frame indices and
-    their token ids, as produced on the device by `cf_ctc_compact` mode 1) and the number of encoder frames: the same
+    """`get_output_with_timestamps` for ONE hypothesis given only its non-blank symbols (non-decreasing frame indices and
+    token ids, as produced on the device by `cf_ctc_compact` mode 1 or by the transducer search, which may emit several
+    symbols on one frame) and the number of encoder frames: the same
     segments, texts and stamps as the frame-by-frame loop (utils/model_utils.py:174-222), in O(#non-blank) host work.
 
     A segment that saw its last non-blank frame at `last` closes at frame `last + max_silence` when no other non-blank
@@ -96,7 +97,7 @@ def get_output_with_timestamps_compact(frames: Sequence[int], tokens: Sequence[i
         pending = [tokens[i]]
         last = t0
         i += 1
-        while i < n and max_silence > 0 and frames[i] - last <= max_silence:
+        while i < n and frames[i] - last <= max_silence:
             pending.append(tokens[i])
             last = frames[i]
             i += 1

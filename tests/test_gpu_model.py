@@ -253,3 +253,65 @@ def test_decode_text_equals_host_postprocessing_of_raw_tokens(asr):
     hyps = asr.batch_decode(xs, 16, 32, 16, total_batch_duration=30)
     asr.char_dict = cd
     assert texts == get_output([h.cpu() for h in hyps], cd, "asr_model")
+
+
+# ------------------------------------------------------------------------------------------------ transducer facade
+@pytest.fixture(scope="module")
+def rnnt(tmp_path_factory):
+    from chunkformer_b200.synth import synth_transducer_state_dict
+    d = tmp_path_factory.mktemp("rnnt_model")
+    geo = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=3, kernel=15, vocab=0, has_cmvn=False)
+    sd = synth_state_dict(geo, 33)
+    sd.update(synth_transducer_state_dict(60, 32, 64, 2, 48, geo.d_model, 64, blank_bias=4.0, seed=34))
+    torch.save(sd, d / "pytorch_model.bin")
+    yaml.safe_dump(dict(input_dim=80, output_dim=60, model="transducer", encoder="chunkformer", encoder_conf=_encoder_conf(geo),
+                        predictor="rnn", predictor_conf=dict(embed_size=32, output_size=48, hidden_size=64, num_layers=2,
+                                                             rnn_type="lstm"),
+                        joint="transducer_joint", joint_conf=dict(enc_output_size=256, pred_output_size=48, join_dim=64,
+                                                                 prejoin_linear=True, postjoin_linear=False, joint_mode="add",
+                                                                 activation="tanh"),
+                        ctc_conf=dict(ctc_blank_id=0)), open(d / "config.yaml", "w"))
+    with open(d / "vocab.txt", "w", encoding="utf8") as f:
+        f.write("<blank> 0\n<unk> 1\n")
+        for i in range(2, 60):
+            f.write(("▁" if i % 4 == 0 else "") + f"t{i} {i}\n")
+    return ChunkFormerModel.from_pretrained(str(d), device=DEV), sd
+
+
+def test_transducer_decode_paths(rnnt):
+    """endless_decode / batch_decode on a `model: transducer` checkpoint: the facade's symbols are the CPU oracle's greedy
+    search on the facade's own encoder output (search parity with identical inputs is tests/test_gpu_transducer.py), and
+    texts / stamps equal the reference's host post-processing of the symbol grid (chunkformer_model.py:440-456, 532-543)."""
+    from chunkformer_b200.postprocess import get_output, get_output_with_timestamps
+    from oracle import transducer_oracle as TO
+    model, sd = rnnt
+    assert model.transducer is not None and model.ctc is None
+    x = synth_fbank(2500, seed=70)
+    cd, model.char_dict = model.char_dict, None
+    grid = model.endless_decode(x, 16, 32, 16, total_batch_duration=20)          # (1, T', 64) like optimized_search
+    model.char_dict = cd
+    assert grid.dim() == 3 and grid.shape[0] == 1 and grid.shape[2] == 64 and int((grid != 0).sum()) > 5
+    for ms in (0.0, 0.24):
+        res = model.endless_decode(x, 16, 32, 16, total_batch_duration=20, return_timestamps=True, max_silence_duration=ms)
+        assert res == get_output_with_timestamps([grid[0].cpu()], cd, "transducer", ms)[0]
+    # the same symbols as the oracle search on the encoder rows the facade computed
+    out, lens, n_chunks, _, _, _ = model.encoder.forward_parallel_chunk([x], torch.tensor([2500], dtype=torch.int), 16, 32, 16,
+                                                                        offset=torch.zeros(1, dtype=torch.int))
+    rows = out.reshape(-1, out.shape[-1])[: int(lens[0])].cpu()
+    want, margins = TO.greedy_search_one(sd, rows, rows.shape[0], 64, 0, want_margin=True)
+    lens5 = [600, 90, 1400]
+    xs = [synth_fbank(t, seed=80 + k) for k, t in enumerate(lens5)]
+    texts = model.batch_decode(xs, 16, 32, 16, total_batch_duration=30)
+    cd, model.char_dict = model.char_dict, None
+    hyps = model.batch_decode(xs, 16, 32, 16, total_batch_duration=30)
+    model.char_dict = cd
+    assert len(texts) == 3 and texts == get_output(hyps, cd, "transducer") and all(isinstance(h, list) for h in hyps)
+    got = model.batch_decode([x], 16, 32, 16, total_batch_duration=60)
+    cd, model.char_dict = model.char_dict, None
+    hyp = model.batch_decode([x], 16, 32, 16, total_batch_duration=60)[0]
+    model.char_dict = cd
+    want_list = want[want != 0].tolist()
+    if hyp != want_list:
+        k = next((i for i, (a, b) in enumerate(zip(hyp, want_list)) if a != b), min(len(hyp), len(want_list)))
+        assert min(m for _, _, m in margins) < 1e-4, f"diverges at symbol {k} without a near-tie"
+    assert isinstance(got[0], str)

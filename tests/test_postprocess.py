@@ -53,3 +53,22 @@ def test_compact_timestamps_match_frame_loop_random():
             want = get_output_with_timestamps([toks.reshape(-1, 1)], cd, "asr_model", ms)[0]
             fr, tk = _nonblank(toks.tolist())
             assert get_output_with_timestamps_compact(fr, tk, n, cd, "asr_model", ms) == want, (case, ms, toks.tolist())
+
+
+def test_compact_timestamps_multi_symbol_frames():
+    """Transducer grids (T', n_steps): several symbols on one frame, no CTC collapse (model type != asr_model)."""
+    from chunkformer_b200.postprocess import get_output_with_timestamps_compact
+    gen = torch.Generator().manual_seed(11)
+    cd = {i: f"▁w{i}" if i % 3 == 0 else f"s{i}" for i in range(12)}
+    for case in range(200):
+        n, k = int(torch.randint(1, 80, (1,), generator=gen)), 3
+        grid = torch.zeros((n, k), dtype=torch.long)
+        for t in range(n):
+            if float(torch.rand(1, generator=gen)) < 0.35:
+                m = int(torch.randint(1, k + 1, (1,), generator=gen))
+                grid[t, :m] = torch.randint(1, 12, (m,), generator=gen)
+        fr = [t for t in range(n) for j in range(k) if int(grid[t, j]) != 0]
+        tk = [int(grid[t, j]) for t in range(n) for j in range(k) if int(grid[t, j]) != 0]
+        for ms in (0.0, 0.08, 0.2, 0.5):
+            want = get_output_with_timestamps([grid], cd, "transducer", ms)[0]
+            assert get_output_with_timestamps_compact(fr, tk, n, cd, "transducer", ms) == want, (case, ms)
