@@ -1202,16 +1202,25 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   RnntJointParams jp{w.E, h->woT, h->bo, w.seg_start, w.seg_len, c.join_dim, c.vocab, w.n_vtiles};
   RnntDecideParams dp{w.seg_len, reinterpret_cast<long long*>(out_tokens), out_frames, out_counts, n_utt, w.n_vtiles, n_steps,
                       capacity, c.blank};
+  const unsigned tiles = unsigned(std::min((n_utt + RNNT_BT - 1) / RNNT_BT, 8));
+  const size_t jsmem = rnnt_joint_smem_bytes(c.join_dim);
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CF_RCUDA(h, cudaFuncSetAttribute(rnnt_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rnnt_joint_smem_bytes(1024))));
+      attr_set = true;
+    }
+  }
   auto iteration = [&]() {
     for (int l = 0; l < c.layers; ++l) {
       RnntLstmParams lp{h->w_ih[l], h->w_hh[l], h->b_ih[l], h->b_hh[l], l == 0 ? h->embed : nullptr, l, l == 0 ? c.embed : c.hidden,
                         c.hidden, n_utt, c.layers};
-      rnnt_lstm_kernel<<<unsigned((c.hidden + 3) / 4), 128, 0, st>>>(lp, w.s);
+      rnnt_lstm_kernel<<<dim3(unsigned((c.hidden + 3) / 4), tiles), 128, 0, st>>>(lp, w.s);
     }
-    rnnt_predproj_kernel<<<unsigned((c.join_dim + 3) / 4), 128, 0, st>>>(h->wc, h->bc, c.join_dim, c.hidden, n_utt, c.layers, w.s);
-    dim3 jg(unsigned(w.n_vtiles), unsigned(n_utt));
-    if (c.join_dim <= 512) rnnt_joint_kernel<512><<<jg, RNNT_JV, 0, st>>>(jp, w.s);
-    else rnnt_joint_kernel<1024><<<jg, RNNT_JV, 0, st>>>(jp, w.s);
+    rnnt_predproj_kernel<<<dim3(unsigned((c.join_dim + 3) / 4), tiles), 128, 0, st>>>(h->wc, h->bc, c.join_dim, c.hidden, n_utt,
+                                                                                      c.layers, w.s);
+    dim3 jg(unsigned(w.n_vtiles), unsigned((n_utt + RNNT_JU - 1) / RNNT_JU));
+    rnnt_joint_kernel<<<jg, RNNT_JV * RNNT_JK, jsmem, st>>>(jp, w.s, n_utt);
     rnnt_decide_kernel<<<1, 256, 0, st>>>(dp, w.s);
     cf::g_kernel_launches += c.layers + 3;
   };

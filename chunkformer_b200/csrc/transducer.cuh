@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(128) rnnt_lstm_kernel(RnntLstmParams p, RnntSt
   const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= p.H) return;
   const size_t half = size_t(p.layers) * p.B * p.H;
-  for (int b0 = 0; b0 < n_act; b0 += RNNT_BT) {
+  // tiles of RNNT_BT utterances run side by side (blockIdx.y): the step is a chain of L2 round trips, not throughput
+  for (int b0 = blockIdx.y * RNNT_BT; b0 < n_act; b0 += gridDim.y * RNNT_BT) {
     float acc[RNNT_BT][4];
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u)
@@ -114,28 +115,34 @@ __global__ void __launch_bounds__(128) rnnt_lstm_kernel(RnntLstmParams p, RnntSt
       xin[u] = p.embed ? p.embed + size_t(s.token[b]) * p.In
                        : s.h + (cur ^ 1) * half + (size_t(p.layer - 1) * p.B + b) * p.H;
     }
-    for (int k = lane * 4; k < p.In; k += 128) {
-      float4 w[4];
+    // both products in slabs of 512 columns: the slab's 16 weight vectors of this unit are all requested before the first
+    // FMA (the kernel is latency-bound: a few hundred FMAs per warp behind L2 round trips)
+    auto slab = [&](const float* wmat, int ld, const float* const* vec, int k0) {
+      float4 w[4][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = __ldg(reinterpret_cast<const float4*>(p.w_ih + size_t(q * p.H + j) * p.In + k));
+      for (int m = 0; m < 4; ++m) {
+        const int k = k0 + m * 128 + lane * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          w[q][m] = k < ld ? __ldg(reinterpret_cast<const float4*>(wmat + size_t(q * p.H + j) * ld + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < RNNT_BT; ++u) {
-        const float4 x = *reinterpret_cast<const float4*>(xin[u] + k);
+        float4 x[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[u][q] += w[q].x * x.x + w[q].y * x.y + w[q].z * x.z + w[q].w * x.w;
+        for (int m = 0; m < 4; ++m) {
+          const int k = k0 + m * 128 + lane * 4;
+          x[m] = k < ld ? *reinterpret_cast<const float4*>(vec[u] + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            acc[u][q] += w[q][m].x * x[m].x + w[q][m].y * x[m].y + w[q][m].z * x[m].z + w[q][m].w * x[m].w;
       }
-    }
-    for (int k = lane * 4; k < p.H; k += 128) {
-      float4 w[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = __ldg(reinterpret_cast<const float4*>(p.w_hh + size_t(q * p.H + j) * p.H + k));
-#pragma unroll
-      for (int u = 0; u < RNNT_BT; ++u) {
-        const float4 x = *reinterpret_cast<const float4*>(hin[u] + k);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[u][q] += w[q].x * x.x + w[q].y * x.y + w[q].z * x.z + w[q].w * x.w;
-      }
-    }
+    };
+    for (int k0 = 0; k0 < p.In; k0 += 512) slab(p.w_ih, p.In, xin, k0);
+    for (int k0 = 0; k0 < p.H; k0 += 512) slab(p.w_hh, p.H, hin, k0);
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u)
 #pragma unroll
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(128) rnnt_predproj_kernel(const float* __restr
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= J) return;
   const size_t half = size_t(layers) * B * H;
-  for (int b0 = 0; b0 < n_act; b0 += RNNT_BT) {
+  for (int b0 = blockIdx.y * RNNT_BT; b0 < n_act; b0 += gridDim.y * RNNT_BT) {
     float acc[RNNT_BT];
     const float* hin[RNNT_BT];
 #pragma unroll
@@ -178,12 +185,21 @@ __global__ void __launch_bounds__(128) rnnt_predproj_kernel(const float* __restr
       const int b = (b0 + u < n_act) ? s.active[b0 + u] : s.active[b0];
       hin[u] = s.h + (s.cur[b] ^ 1) * half + (size_t(layers - 1) * B + b) * H;
     }
-    for (int k = lane * 4; k < H; k += 128) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(Wc + size_t(r) * H + k));
+    for (int k0 = 0; k0 < H; k0 += 512) {
+      float4 w[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int k = k0 + m * 128 + lane * 4;
+        w[m] = k < H ? __ldg(reinterpret_cast<const float4*>(Wc + size_t(r) * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < RNNT_BT; ++u) {
-        const float4 x = *reinterpret_cast<const float4*>(hin[u] + k);
-        acc[u] += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int k = k0 + m * 128 + lane * 4;
+          const float4 x = k < H ? *reinterpret_cast<const float4*>(hin[u] + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          acc[u] += w[m].x * x.x + w[m].y * x.y + w[m].z * x.z + w[m].w * x.w;
+        }
       }
     }
 #pragma unroll
@@ -207,61 +223,115 @@ struct RnntJointParams {
   int J, V, n_vtiles;
 };
 
-template <int JMAX>
-__global__ void __launch_bounds__(RNNT_JV) rnnt_joint_kernel(RnntJointParams p, RnntState s) {
-  __shared__ __align__(16) float a[RNNT_FB][JMAX];
-  __shared__ float s_val[RNNT_FB][RNNT_JV / 32];
-  __shared__ int s_idx[RNNT_FB][RNNT_JV / 32];
-  const int b = blockIdx.y;
-  const int t0 = s.t[b], len = p.seg_len[b];
-  if (t0 >= len) return;
-  const int nf = min(RNNT_FB, len - t0);
-  const float* g = s.g + size_t(b) * p.J;
-  const float* e = p.E + (p.seg_start[b] + t0) * (long long)p.J;
-  for (int i = threadIdx.x; i < RNNT_FB * p.J; i += RNNT_JV) {
-    const int f = i / p.J, k = i - f * p.J;
-    a[f][k] = f < nf ? tanhf(e[(long long)f * p.J + k] + g[k]) : 0.f;
+constexpr int RNNT_JK = 4;        // K slices per vocabulary entry (threads per CTA = RNNT_JV * RNNT_JK)
+constexpr int RNNT_JU = 1;        // utterances per CTA (more share one read of the ffn_out tile, but leave SMs idle: measured slower)
+constexpr int RNNT_JR = RNNT_JU * RNNT_FB;   // activation rows per CTA
+
+inline size_t rnnt_joint_smem_bytes(int J) {
+  return size_t(RNNT_JR) * J * 4 + size_t(RNNT_JK - 1) * RNNT_JR * RNNT_JV * 4 + size_t(RNNT_JR) * (RNNT_JV / 32) * 8;
+}
+
+__global__ void __launch_bounds__(RNNT_JV * RNNT_JK) rnnt_joint_kernel(RnntJointParams p, RnntState s, int B) {
+  extern __shared__ __align__(16) float jsm[];
+  float* a = jsm;                                          // [JR][J]
+  float* s_acc = a + size_t(RNNT_JR) * p.J;                // [JK - 1][JR][JV]
+  float* s_val = s_acc + size_t(RNNT_JK - 1) * RNNT_JR * RNNT_JV;   // [JR][JV / 32]
+  int* s_idx = reinterpret_cast<int*>(s_val + RNNT_JR * (RNNT_JV / 32));
+  __shared__ int s_t0[RNNT_JU], s_nf[RNNT_JU];
+  const int b_first = blockIdx.y * RNNT_JU;
+  if (threadIdx.x < RNNT_JU) {
+    const int b = b_first + threadIdx.x;
+    int t0 = 0, nf = 0;
+    if (b < B) { t0 = s.t[b]; nf = max(0, min(RNNT_FB, p.seg_len[b] - t0)); }
+    s_t0[threadIdx.x] = t0; s_nf[threadIdx.x] = nf;
   }
   __syncthreads();
-  const int v = blockIdx.x * RNNT_JV + threadIdx.x;
+  {
+    int any = 0;
+#pragma unroll
+    for (int u = 0; u < RNNT_JU; ++u) any += s_nf[u];
+    if (any == 0) return;
+  }
+  for (int i = threadIdx.x; i < RNNT_JR * p.J; i += RNNT_JV * RNNT_JK) {
+    const int r = i / p.J, k = i - r * p.J;
+    const int u = r / RNNT_FB, f = r - u * RNNT_FB;
+    float val = 0.f;
+    if (f < s_nf[u]) {
+      const int b = b_first + u;
+      val = tanhf(p.E[(p.seg_start[b] + s_t0[u] + f) * (long long)p.J + k] + s.g[size_t(b) * p.J + k]);
+    }
+    a[i] = val;
+  }
+  __syncthreads();
+  const int tv = threadIdx.x & (RNNT_JV - 1), kq = threadIdx.x / RNNT_JV;   // a warp shares kq: the tile reads broadcast
+  const int v = blockIdx.x * RNNT_JV + tv;
   const int vc = min(v, p.V - 1);
-  float acc[RNNT_FB];
+  float acc[RNNT_JR];
 #pragma unroll
-  for (int f = 0; f < RNNT_FB; ++f) acc[f] = 0.f;
-  for (int k = 0; k < p.J; k += 4) {
-    const float w0 = __ldg(p.WoT + size_t(k) * p.V + vc), w1 = __ldg(p.WoT + size_t(k + 1) * p.V + vc);
-    const float w2 = __ldg(p.WoT + size_t(k + 2) * p.V + vc), w3 = __ldg(p.WoT + size_t(k + 3) * p.V + vc);
+  for (int r = 0; r < RNNT_JR; ++r) acc[r] = 0.f;
+  // slice kq takes the 4-wide k groups kq, kq + JK, ...; the 64 weights of a 256-column phase are all requested before the
+  // first FMA (two L2 round trips for J = 512 instead of one per step)
+  const float* wp = p.WoT + vc;
+  constexpr int GROUPS = 16;
+  for (int k0 = 0; k0 < p.J; k0 += GROUPS * 4 * RNNT_JK) {
+    float w[GROUPS][4];
 #pragma unroll
-    for (int f = 0; f < RNNT_FB; ++f) {
-      const float4 x = *reinterpret_cast<const float4*>(&a[f][k]);
-      acc[f] = fmaf(x.x, w0, acc[f]); acc[f] = fmaf(x.y, w1, acc[f]);
-      acc[f] = fmaf(x.z, w2, acc[f]); acc[f] = fmaf(x.w, w3, acc[f]);
+    for (int m = 0; m < GROUPS; ++m) {
+      const int km = k0 + 4 * (kq + RNNT_JK * m);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[m][i] = km < p.J ? __ldg(wp + size_t(km + i) * p.V) : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < GROUPS; ++m) {
+      const int km = k0 + 4 * (kq + RNNT_JK * m);
+      if (km < p.J) {
+#pragma unroll
+        for (int r = 0; r < RNNT_JR; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(&a[size_t(r) * p.J + km]);
+          acc[r] = fmaf(x.x, w[m][0], acc[r]); acc[r] = fmaf(x.y, w[m][1], acc[r]);
+          acc[r] = fmaf(x.z, w[m][2], acc[r]); acc[r] = fmaf(x.w, w[m][3], acc[r]);
+        }
+      }
     }
   }
-  const float bias = __ldg(p.bo + vc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (kq > 0) {
 #pragma unroll
-  for (int f = 0; f < RNNT_FB; ++f) {
-    float val = v < p.V ? acc[f] + bias : -INFINITY;
-    int idx = v;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, val, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-    }
-    if (lane == 0) { s_val[f][warp] = val; s_idx[f][warp] = idx; }
+    for (int r = 0; r < RNNT_JR; ++r) s_acc[(size_t(kq - 1) * RNNT_JR + r) * RNNT_JV + tv] = acc[r];
   }
   __syncthreads();
-  if (threadIdx.x < RNNT_FB) {
-    const int f = threadIdx.x;
-    float val = s_val[f][0]; int idx = s_idx[f][0];
+  if (kq == 0) {
+    const float bias = __ldg(p.bo + vc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int w = 1; w < RNNT_JV / 32; ++w)
-      if (s_val[f][w] > val || (s_val[f][w] == val && s_idx[f][w] < idx)) { val = s_val[f][w]; idx = s_idx[f][w]; }
-    const size_t at = (size_t(b) * RNNT_FB + f) * p.n_vtiles + blockIdx.x;
-    s.part_val[at] = val;
-    s.part_idx[at] = idx;
+    for (int r = 0; r < RNNT_JR; ++r) {
+      float sum = acc[r];
+#pragma unroll
+      for (int q = 0; q < RNNT_JK - 1; ++q) sum += s_acc[(size_t(q) * RNNT_JR + r) * RNNT_JV + tv];
+      float val = v < p.V ? sum + bias : -INFINITY;
+      int idx = v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+      }
+      if (lane == 0) { s_val[r * (RNNT_JV / 32) + warp] = val; s_idx[r * (RNNT_JV / 32) + warp] = idx; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < RNNT_JR) {
+    const int r = threadIdx.x, u = r / RNNT_FB, f = r - u * RNNT_FB;
+    if (f < s_nf[u]) {
+      float val = s_val[r * (RNNT_JV / 32)]; int idx = s_idx[r * (RNNT_JV / 32)];
+#pragma unroll
+      for (int w = 1; w < RNNT_JV / 32; ++w) {
+        const float ov = s_val[r * (RNNT_JV / 32) + w]; const int oi = s_idx[r * (RNNT_JV / 32) + w];
+        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+      }
+      const size_t at = (size_t(b_first + u) * RNNT_FB + f) * p.n_vtiles + blockIdx.x;
+      s.part_val[at] = val;
+      s.part_idx[at] = idx;
+    }
   }
 }
 
@@ -280,37 +350,57 @@ __global__ void __launch_bounds__(256) rnnt_decide_kernel(RnntDecideParams p, Rn
   __shared__ int s_nact, s_rem;
   if (threadIdx.x == 0) { s_nact = 0; s_rem = 0; }
   __syncthreads();
-  for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (int b = threadIdx.x >> 5; b < p.B; b += blockDim.x >> 5) {       // warp per utterance
     int t = s.t[b];
     const int len = p.seg_len[b];
     if (t >= len) continue;
-    int step = s.step[b];
-    bool emitted = false;
-    for (int f = 0; f < RNNT_FB && t < len; ++f) {
-      const size_t at = (size_t(b) * RNNT_FB + f) * p.n_vtiles;
-      float val = s.part_val[at]; int idx = s.part_idx[at];
-      for (int w = 1; w < p.n_vtiles; ++w) {
-        const float ov = s.part_val[at + w]; const int oi = s.part_idx[at + w];
-        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    // lane = 4 f + q: the four lanes of frame f split its vocabulary tiles, then combine (lowest index wins ties)
+    static_assert(RNNT_FB == 8, "lane layout assumes 8 frames x 4 lanes");
+    const int f_l = lane >> 2, q_l = lane & 3;
+    const size_t at = (size_t(b) * RNNT_FB + f_l) * p.n_vtiles;
+    float val = -INFINITY; int idx = 0x7fffffff;
+    for (int w = q_l; w < p.n_vtiles; w += 4) {
+      const float ov = s.part_val[at + w]; const int oi = s.part_idx[at + w];
+      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+    // first frame of the block (still inside the utterance) whose symbol is not blank
+    const unsigned nb = __ballot_sync(0xffffffffu, q_l == 0 && idx != p.blank && t + f_l < len);
+    const int limit = min(RNNT_FB, len - t);
+    const int f_hit = nb ? (__ffs(nb) - 1) >> 2 : limit;
+    const int sym = __shfl_sync(0xffffffffu, idx, (f_hit < RNNT_FB ? f_hit : 0) * 4);
+    if (lane == 0) {
+      int step = s.step[b];
+      bool emitted = false;
+      if (f_hit > 0) step = 1;                  // blanks before the hit: next frame, slot 1
+      t += f_hit;
+      if (f_hit < limit) {
+        const int n = s.count[b];
+        if (n >= p.cap) { *s.overflow = 1; t = len; }
+        else {
+          p.out_tokens[size_t(b) * p.cap + n] = sym;
+          p.out_frames[size_t(b) * p.cap + n] = t;
+          s.count[b] = n + 1;
+          s.token[b] = sym;
+          s.cur[b] ^= 1;
+          if (++step > p.n_steps) { ++t; step = 1; }
+          emitted = true;
+        }
       }
-      if (idx == p.blank) { ++t; step = 1; continue; }
-      const int n = s.count[b];
-      if (n >= p.cap) { *s.overflow = 1; t = len; break; }
-      p.out_tokens[size_t(b) * p.cap + n] = idx;
-      p.out_frames[size_t(b) * p.cap + n] = t;
-      s.count[b] = n + 1;
-      s.token[b] = idx;
-      s.cur[b] ^= 1;
-      if (++step > p.n_steps) { ++t; step = 1; }
-      emitted = true;
-      break;
+      s.t[b] = t; s.step[b] = step;
+      if (t < len) {
+        atomicAdd(&s_rem, 1);
+        if (emitted) s.active[atomicAdd(&s_nact, 1)] = b;
+      } else {
+        p.out_counts[b] = s.count[b];
+      }
     }
-    s.t[b] = t; s.step[b] = step;
-    if (t < len) {
-      atomicAdd(&s_rem, 1);
-      if (emitted) s.active[atomicAdd(&s_nact, 1)] = b;
-    }
-    if (t >= len) p.out_counts[b] = s.count[b];
   }
   __syncthreads();
   if (threadIdx.x == 0) { *s.n_active = s_nact; *s.remaining = s_rem; }
