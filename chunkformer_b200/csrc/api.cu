@@ -435,20 +435,21 @@ bool run_dwconv_d(const DwConvParams& p, cudaStream_t st, std::string* err) {
   if (e != cudaSuccess) { *err = std::string("dwconv launch: ") + cudaGetErrorString(e); return false; }
   return true;
 }
-template <int D>
+template <int D, int FG, int STAGES>
 bool run_dwconv_tma(const DwConvParams& p, long long g_rows, int num_sms, cudaStream_t st, std::string* err) {
   CUtensorMap tm;
-  if (!make_tma_2d(&tm, p.g, false, uint64_t(g_rows), uint64_t(D), uint64_t(D), 46, 256, err, /*swizzle128=*/false)) return false;
-  const size_t smem = dwconv_tma_smem_bytes<D>();
+  if (!make_tma_2d(&tm, p.g, false, uint64_t(g_rows), uint64_t(D), uint64_t(D), FG + 14, 256, err, /*swizzle128=*/false)) return false;
+  const size_t smem = dwconv_tma_smem_bytes<D, FG, STAGES>();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_silu_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_silu_tma_kernel<D, FG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(dwconv): ") + cudaGetErrorString(e); return false; }
     attr_set = true;
   }
-  const int groups = p.n_chunks * (p.c / 32);
-  const int grid = groups < 2 * num_sms ? groups : 2 * num_sms;
-  dwconv_ln_silu_tma_kernel<D><<<grid, D / 2, smem, st>>>(tm, p, groups);
+  constexpr int CTAS = (FG == 16 && STAGES == 2) ? 3 : 2;
+  const int groups = p.n_chunks * (p.c / FG);
+  const int grid = groups < CTAS * num_sms ? groups : CTAS * num_sms;
+  dwconv_ln_silu_tma_kernel<D, FG, STAGES><<<grid, D / 2, smem, st>>>(tm, p, groups);
   ++cf::g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("dwconv launch: ") + cudaGetErrorString(e); return false; }
@@ -459,9 +460,16 @@ bool run_dwconv_tma(const DwConvParams& p, long long g_rows, int num_sms, cudaSt
 bool run_dwconv(int d, int kernel, const DwConvParams& p, cudaStream_t st, std::string* err, long long g_rows = 0, int num_sms = 148) {
   if (kernel != 15) { *err = "dwconv: kernel must be 15"; return false; }
   if (p.n_chunks == 0) return true;
-  if (g_rows > 0 && p.c % 32 == 0) {
-    if (d == 512) return run_dwconv_tma<512>(p, g_rows, num_sms, st, err);
-    if (d == 256) return run_dwconv_tma<256>(p, g_rows, num_sms, st, err);
+  static const int fg_env = [] { const char* e = getenv("CF_DW_FG"); return e ? atoi(e) : 32; }();
+  if (g_rows > 0 && p.c % 32 == 0 && fg_env != 16) {
+    if (d == 512) return run_dwconv_tma<512, 32, 2>(p, g_rows, num_sms, st, err);
+    if (d == 256) return run_dwconv_tma<256, 32, 2>(p, g_rows, num_sms, st, err);
+  }
+  static const int st_env = [] { const char* e = getenv("CF_DW_STAGES"); return e ? atoi(e) : 2; }();
+  if (g_rows > 0 && p.c % 16 == 0 && fg_env == 16) {
+    if (d == 512 && st_env == 3) return run_dwconv_tma<512, 16, 3>(p, g_rows, num_sms, st, err);
+    if (d == 512) return run_dwconv_tma<512, 16, 2>(p, g_rows, num_sms, st, err);
+    if (d == 256) return run_dwconv_tma<256, 16, 2>(p, g_rows, num_sms, st, err);
   }
   if (d == 512) return run_dwconv_d<512>(p, st, err);
   if (d == 256) return run_dwconv_d<256>(p, st, err);

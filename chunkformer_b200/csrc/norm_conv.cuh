@@ -238,27 +238,28 @@ CF_DEVINL unsigned long long fadd2(unsigned long long a, unsigned long long b) {
 CF_DEVINL float f32x2_lo(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 CF_DEVINL float f32x2_hi(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
-template <int D>
-constexpr size_t dwconv_tma_smem_bytes() { return size_t(2) * 46 * D * 2 + 1024; }
+template <int D, int FG, int STAGES>
+constexpr size_t dwconv_tma_smem_bytes() { return size_t(STAGES) * (FG + 14) * D * 2 + 1024; }
 
-template <int D>
-__global__ void __launch_bounds__(D / 2, 2)
+// FG = frames per group: 32 (two CTAs per SM, 128 registers) or 16 (three CTAs per SM, 84 registers, 30-row tiles)
+template <int D, int FG, int STAGES>
+__global__ void __launch_bounds__(D / 2, FG == 16 ? 3 : 2)
 dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParams p, int total_groups) {
-  constexpr int KW = 15, FG = 32, ROWS = FG + KW - 1;
+  constexpr int KW = 15, ROWS = FG + KW - 1;
   constexpr int NT = D / 2, NW = NT / 32;
   constexpr int HALVES = D / 256;                 // TMA boxes of 256 channels
   constexpr uint32_t STAGE_BYTES = ROWS * D * 2;
   extern __shared__ __align__(1024) uint8_t dw_smem[];
-  uint8_t* s_in = dw_smem;                        // [2 stages][HALVES][ROWS][256 ch] bf16
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_in + 2 * STAGE_BYTES);
+  uint8_t* s_in = dw_smem;                        // [STAGES][HALVES][ROWS][256 ch] bf16
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_in + STAGES * STAGE_BYTES);
   __shared__ unsigned long long s_part2[2][NW][FG];   // double-buffered by iteration parity: no barrier at the end of a group
 
   const int tid = threadIdx.x;
   const int groups_per_chunk = p.c / FG;
   if (tid == 0) {
     tma_prefetch_desc(&tma_g);
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -271,7 +272,11 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
     for (int hb = 0; hb < HALVES; ++hb)
       tma_load_2d(s_in + stage * STAGE_BYTES + hb * (ROWS * 512), &tma_g, &full[stage], hb * 256, row);
   };
-  if (tid == 0 && int(blockIdx.x) < total_groups) issue(blockIdx.x, 0);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES - 1; ++i)
+      if (int(blockIdx.x) + i * int(gridDim.x) < total_groups) issue(blockIdx.x + i * gridDim.x, i);
+  }
 
   unsigned long long w[KW];
 #pragma unroll
@@ -287,15 +292,18 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
   int2 rg_next = (int(blockIdx.x) < total_groups) ? __ldg(&p.range[blockIdx.x / groups_per_chunk]) : make_int2(0, 0);
   int it = 0;
   for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x, ++it) {
-    const int stage = it & 1;
+    const int stage = it % STAGES;
+    const int par = it & 1;                       // parity of the double-buffered statistics
     const int nxt = grp + gridDim.x;
-    // every thread finished reading the other stage's tile before the LayerNorm barriers of the previous iteration
-    if (tid == 0 && nxt < total_groups) issue(nxt, stage ^ 1);
+    // the tile of group it + STAGES - 1 goes where group it - 1 was: every thread finished reading it before the LayerNorm
+    // barrier of the previous iteration
+    if (tid == 0 && grp + (STAGES - 1) * int(gridDim.x) < total_groups)
+      issue(grp + (STAGES - 1) * gridDim.x, (it + STAGES - 1) % STAGES);
     const int chunk = grp / groups_per_chunk;
     const int f0 = (grp - chunk * groups_per_chunk) * FG;
     const int2 rg = rg_next;
     if (nxt < total_groups) rg_next = __ldg(&p.range[nxt / groups_per_chunk]);   // consumed one iteration later
-    mbar_wait(&full[stage], (it >> 1) & 1);
+    mbar_wait(&full[stage], (it / STAGES) & 1);
     const uint8_t* src = s_in + stage * STAGE_BYTES + col_off;
 
     // Row-outer order: input row s feeds the 15 frames s-14 .. s, so the 15 FMAs issued per loaded row are independent
@@ -327,7 +335,7 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
       P[f] = pack_f32x2(lo + hi, fmaf(lo, lo, hi * hi));
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int off = FG / 2; off >= 1; off >>= 1) {
       const bool up = (lane & off) != 0;
 #pragma unroll
       for (int i = 0; i < off; ++i) {
@@ -336,7 +344,9 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
         P[i] = fadd2(keep, __shfl_xor_sync(0xffffffffu, send, off));
       }
     }
-    s_part2[stage][warp][lane] = P[0];
+#pragma unroll
+    for (int off = FG; off < 32; off <<= 1) P[0] = fadd2(P[0], __shfl_xor_sync(0xffffffffu, P[0], off));
+    if (lane < FG) s_part2[par][warp][lane] = P[0];
     __syncthreads();
     // every warp finishes the statistics itself (lane f owns frame f), the output loop fetches them by shuffle: one
     // barrier per group, no single-warp finalize step on the critical path
@@ -344,7 +354,7 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
     {
       float a = 0.f, q = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < NW; ++w2) { const unsigned long long v = s_part2[stage][w2][lane]; a += f32x2_lo(v); q += f32x2_hi(v); }
+      for (int w2 = 0; w2 < NW; ++w2) { const unsigned long long v = s_part2[par][w2][lane & (FG - 1)]; a += f32x2_lo(v); q += f32x2_hi(v); }
       const float mean = a * (1.0f / D);
       const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
       rs = rsqrtf(var + 1e-5f);
