@@ -167,6 +167,79 @@ class ChunkFormerEncoderB200:
             new_cnn = torch.zeros((L, 0, 0), device=self.device)
         return out.view(plan.n, chunk_size, d), xs_lens, plan.n_chunks, new_att, new_cnn, offset
 
+    # ------------------------------------------------------------------------------------------------------------
+    # frame-synchronous streaming
+    @torch.no_grad()
+    def forward_chunk(self, xs: torch.Tensor, att_cache: torch.Tensor = torch.zeros((0, 0, 0, 0, 0)),
+                      cnn_cache: torch.Tensor = torch.zeros((0, 0, 0, 0)), chunk_size: int = 0, left_context_size: int = 0,
+                      right_context_size: int = 0, offset: int = 0):
+        """One streaming step for B concurrent streams; drop-in for ChunkFormerEncoder.forward_chunk (encoder.py:310-390) at
+        right_context_size = 0 (every shipped streaming preset, apps/realtime-asr/config.py:86-110).
+
+        xs (B, 8 (c - 1) + 15, feat) = the new c encoder frames of every stream; att_cache (L, B, H, l, 2 d_k) and cnn_cache
+        (L, B, d, 7) as returned by the previous step (empty = zeros = start of the streams); offset = encoder frames already
+        consumed.  Returns (out (B, c, d), ones mask (B, 1, c), new att_cache, new cnn_cache).
+
+        With r = 0 a step is, per stream, the masked-chunk path on one chunk with that stream's caches and
+        truncated_context_size = c (oracle.forward_chunk, pinned against the reference).  The flat K/V buffer has one cache
+        region, so the streams of a step run as B back-to-back encoder passes on the stream; a per-stream cache stride in the
+        attention / conv kernels (one pass for all streams) is the next step."""
+        if right_context_size != 0:
+            raise NotImplementedError("forward_chunk is built for right_context_size = 0 (the shipped streaming presets)")
+        c, l = int(chunk_size), int(left_context_size)
+        if c <= 0 or l < 0 or xs.dim() != 3:
+            raise ValueError("forward_chunk needs xs (B, T, feat), chunk_size > 0 and left_context_size >= 0")
+        B, T, _ = xs.shape
+        if T != 8 * (c - 1) + 15:
+            raise ValueError(f"forward_chunk expects {8 * (c - 1) + 15} input frames per step for chunk_size {c}, got {T}")
+        L, H, d, lo = self.geo.layers, self.geo.heads, self.geo.d_model, self.geo.kernel // 2
+        if att_cache.numel() == 0:
+            att_cache = torch.zeros((L, B, H, l, 2 * d // H), device=self.device)
+        if cnn_cache.numel() == 0:
+            cnn_cache = torch.zeros((L, B, d, lo), device=self.device)
+        if tuple(att_cache.shape) != (L, B, H, l, 2 * d // H) or tuple(cnn_cache.shape) != (L, B, d, lo):
+            raise ValueError("cache shapes must be (L, B, H, left_context, 2*d_k) and (L, B, d, kernel//2)")
+        att_in = att_cache.to(self.device, torch.float32).permute(1, 0, 3, 2, 4).contiguous()      # (B, L, l, H, 2 d_k)
+        cnn_in = cnn_cache.to(self.device, torch.float32).permute(1, 0, 2, 3).contiguous()         # (B, L, d, 7)
+        x_dev = xs.to(self.device, torch.float32).contiguous()
+        out = torch.empty((B, c, d), dtype=torch.float32, device=self.device)
+        plan = Plan(c, l, 0, [T], [int(offset)], self.geo.kernel)
+        for b in range(B):
+            o, _ = self.encode_plan(plan, x_dev[b], att_in[b], cnn_in[b], c)      # caches are updated in place
+            out[b] = o[:c]
+        new_att = att_in.permute(1, 0, 3, 2, 4).contiguous()
+        new_cnn = cnn_in.permute(1, 0, 2, 3).contiguous()
+        return out, torch.ones((B, 1, c), dtype=torch.bool, device=self.device), new_att, new_cnn
+
+    @torch.no_grad()
+    def forward_chunk_by_chunk(self, xs: torch.Tensor, xs_lens: torch.Tensor, chunk_size: int = 0, left_context_size: int = 0,
+                               right_context_size: int = 0):
+        """Streaming simulation over whole utterances; drop-in for ChunkFormerEncoder.forward_chunk_by_chunk
+        (encoder.py:392-459) at right_context_size = 0.  Returns (out (B, steps * c, d), masks (B, 1, T'))."""
+        if right_context_size != 0:
+            raise NotImplementedError("forward_chunk_by_chunk is built for right_context_size = 0")
+        c, l = int(chunk_size), int(left_context_size)
+        B, T, _ = xs.shape
+        size, stride = 8 * (c - 1) + 15, 8 * c
+        pad = stride - ((T - size) % stride)
+        xp = torch.nn.functional.pad(xs.to(self.device, torch.float32), (0, 0, 0, pad))
+        att = torch.zeros((0, 0, 0, 0, 0))
+        cnn = torch.zeros((0, 0, 0, 0))
+        outs, offset = [], 0
+        for i in range(0, xp.shape[1] - size + stride, stride):
+            o, _, att, cnn = self.forward_chunk(xp[:, i:i + size], att, cnn, c, l, 0, offset)
+            outs.append(o)
+            offset += c
+        out = torch.cat(outs, dim=1)
+
+        def calc(n):                                     # subsampling.py:270-288
+            for _ in range(3):
+                n = (n - 3) // 2 + 1
+            return max(n, 0)
+        enc_lens = torch.tensor([calc(int(t) + pad) for t in xs_lens.tolist()])
+        masks = (torch.arange(int(enc_lens.max())).unsqueeze(0) < enc_lens.unsqueeze(1)).unsqueeze(1).to(self.device)
+        return out, masks
+
     @torch.no_grad()
     def forward_encoder(self, xs: torch.Tensor, xs_lens: torch.Tensor, chunk_size: int = 0, left_context_size: int = 0,
                         right_context_size: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:

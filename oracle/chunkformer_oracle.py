@@ -436,3 +436,55 @@ def forward_encoder(sd: Dict[str, torch.Tensor], heads: int, xs: torch.Tensor, x
         x = ln("norm_final", x)
     x = _ln(x, sd["encoder.after_norm.weight"], sd["encoder.after_norm.bias"])
     return x, valid.unsqueeze(1)
+
+
+# --------------------------------------------------------------------------------------------
+# frame-synchronous streaming: forward_chunk / forward_chunk_by_chunk with right context 0
+# --------------------------------------------------------------------------------------------
+def forward_chunk(sd, heads: int, xs: torch.Tensor, att_cache: torch.Tensor, cnn_cache: torch.Tensor, c: int, l: int, r: int = 0,
+                  offset: int = 0):
+    """ChunkFormerEncoder.forward_chunk (encoder.py:310-390) for right_context_size = 0 (every shipped streaming preset:
+    apps/realtime-asr/config.py:86-110).  xs (B, 8(c-1)+15, feat); att_cache (L, B, H, l, 2 d_k); cnn_cache (L, B, d, lorder).
+
+    With r = 0 one step is, per stream, exactly the masked-chunk call on a single chunk with the stream's caches and
+    truncated_context_size = c: the attention sees [cache (l rows, valid where >= l - offset) | c frames] (attention.py:323-330
+    + the flipped `< c + offset` mask of encoder.py:349-355), the conv sees [cache (7) | c frames | zeros], and the returned
+    caches are the last l / 7 rows (encoder.py:376-388) = rows [c, c + l) / [c - 7, c) of cache + frames.
+    Pinned against the reference in tests/test_oracle_golden.py::test_streaming_*.
+    Returns (out (B, c, d), new att_cache, new cnn_cache)."""
+    if r != 0:
+        raise NotImplementedError("forward_chunk is restated for right_context_size = 0 only")
+    B = xs.shape[0]
+    outs, atts, cnns = [], [], []
+    for b in range(B):
+        a_in = att_cache[:, b].transpose(1, 2)                      # (L, l, H, 2 d_k)
+        o, _, _, a, cv, _ = forward_parallel_chunk(sd, heads, [xs[b]], [int(xs.shape[1])], c, l, 0, a_in, cnn_cache[:, b], c,
+                                                   [int(offset)])
+        outs.append(o.reshape(-1, o.shape[-1])[:c])
+        atts.append(a.transpose(1, 2))                              # back to (L, H, l, 2 d_k)
+        cnns.append(cv)
+    return torch.stack(outs), torch.stack(atts, 1), torch.stack(cnns, 1)
+
+
+def forward_chunk_by_chunk(sd, heads: int, xs: torch.Tensor, xs_lens: Sequence[int], c: int, l: int, r: int = 0):
+    """ChunkFormerEncoder.forward_chunk_by_chunk (encoder.py:392-459), right context 0: (out (B, steps * c, d), mask (B, 1, T'))."""
+    if r != 0:
+        raise NotImplementedError("forward_chunk_by_chunk is restated for right_context_size = 0 only")
+    B, T, _ = xs.shape
+    L = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("encoder.encoders."))
+    d = sd["encoder.after_norm.weight"].shape[0]
+    lo = sd["encoder.encoders.0.conv_module.depthwise_conv.weight"].shape[-1] // 2
+    size, stride = SUB * (c - 1) + CTX, SUB * c
+    pad = stride - ((T - size) % stride)                            # encoder.py:417-419 (always pads, a full stride if aligned)
+    xp = F.pad(xs.float(), (0, 0, 0, pad))
+    att = torch.zeros((L, B, heads, l, 2 * d // heads))
+    cnn = torch.zeros((L, B, d, lo))
+    outs, offset = [], 0
+    for i in range(0, xp.shape[1] - size + stride, stride):
+        o, att, cnn = forward_chunk(sd, heads, xp[:, i:i + size], att, cnn, c, l, 0, offset)
+        outs.append(o)
+        offset += c
+    out = torch.cat(outs, 1)
+    enc_lens = [calc_length(int(t) + pad) for t in xs_lens]
+    mask = torch.arange(max(enc_lens)).unsqueeze(0) < torch.tensor(enc_lens).unsqueeze(1)
+    return out, mask.unsqueeze(1)

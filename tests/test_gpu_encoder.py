@@ -205,3 +205,40 @@ def test_full_size_masked_batch_properties():
         assert (a - b).abs().max().item() < 2e-2, u
         ref, _, _, _, _, _ = O.forward_parallel_chunk(sd, LARGE.heads, [xs[u]], [lens[u]], 64, 128, 128)
         _compare(a, ref.reshape(-1, 512)[:m], f"utterance {u} inside the 14 400 s batch vs oracle")
+
+
+# ------------------------------------------------------------------------------------------------ frame-synchronous streaming
+@pytest.mark.parametrize("c,l,B,T", [(8, 40, 2, 555), (4, 12, 1, 300), (6, 20, 3, 411), (16, 64, 2, 900)])
+def test_forward_chunk_by_chunk_matches_oracle(c, l, B, T):
+    """forward_chunk_by_chunk / forward_chunk (right context 0) against the oracle, which is pinned to the
+    reference's own streaming path (tests/test_oracle_golden.py::test_streaming_*).  Same tolerance as the offline path."""
+    sd, enc = _model(SMALL, 5)
+    xs = torch.stack([synth_fbank(T, seed=90 + b) for b in range(B)])
+    want, want_mask = O.forward_chunk_by_chunk(sd, SMALL.heads, xs, [T] * B, c, l, 0)
+    got, got_mask = enc.forward_chunk_by_chunk(xs.to(DEV), torch.full((B,), T), c, l, 0)
+    assert got.shape == want.shape and torch.equal(got_mask.cpu(), want_mask)
+    _compare(got, want, f"stream {c}/{l}")
+    # explicit steps: caches come back in the reference's layouts and carry the same values
+    L, H, d = SMALL.layers, SMALL.heads, SMALL.d_model
+    size, stride = 8 * (c - 1) + 15, 8 * c
+    att_o, cnn_o = torch.zeros((L, B, H, l, 2 * d // H)), torch.zeros((L, B, d, 7))
+    att_g, cnn_g = torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))
+    for step in range(3):
+        chunk = xs[:, step * stride: step * stride + size]
+        o_o, att_o, cnn_o = O.forward_chunk(sd, H, chunk, att_o, cnn_o, c, l, 0, offset=step * c)
+        o_g, m_g, att_g, cnn_g = enc.forward_chunk(chunk.to(DEV), att_g, cnn_g, c, l, 0, offset=step * c)
+    assert tuple(att_g.shape) == (L, B, H, l, 2 * d // H) and tuple(cnn_g.shape) == (L, B, d, 7) and bool(m_g.all())
+    _compare(o_g, o_o, "step out")
+    _compare(att_g, att_o, "att cache")
+    _compare(cnn_g, cnn_o, "cnn cache")
+
+
+def test_forward_chunk_argument_errors():
+    _, enc = _model(SMALL, 5)
+    x = torch.zeros((1, 8 * 7 + 15, 80), device=DEV)
+    with pytest.raises(NotImplementedError):
+        enc.forward_chunk(x, chunk_size=8, left_context_size=40, right_context_size=2)
+    with pytest.raises(ValueError):
+        enc.forward_chunk(x[:, :50], chunk_size=8, left_context_size=40)
+    with pytest.raises(ValueError):
+        enc.forward_chunk(x, torch.zeros((3, 1, 4, 39, 128)), torch.zeros((3, 1, 256, 7)), 8, 40)

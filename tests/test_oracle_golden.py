@@ -132,3 +132,36 @@ def test_ctc_large_60s(golden_dir):
     tok, margin = O.ctc_greedy(sd, flat)
     same = tok.numpy() == g["tokens"]
     assert bool((same | (margin.numpy() < 1e-3)).all())
+
+
+def _stream_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stream.npz"))
+    for k, (c, l, B, T) in enumerate(g["cases"].tolist()):
+        xs = torch.stack([synth_fbank(T, seed=20 + 7 * k + b) for b in range(B)])
+        yield k, c, l, B, T, xs, g
+
+
+def test_streaming_forward_chunk_by_chunk(golden_dir):
+    """Frame-synchronous streaming (right context 0) == the reference's forward_chunk_by_chunk."""
+    sd = synth_state_dict(TINY, 3)
+    for k, c, l, B, T, xs, g in _stream_cases(golden_dir):
+        out, mask = O.forward_chunk_by_chunk(sd, TINY.heads, xs, [T] * B, c, l, 0)
+        want = torch.from_numpy(g[f"c{k}_out"])
+        assert out.shape == want.shape and float((out - want).abs().max()) < FTOL
+        assert torch.equal(mask, torch.from_numpy(g[f"c{k}_mask"]))
+
+
+def test_streaming_forward_chunk_caches(golden_dir):
+    """Three explicit forward_chunk steps: outputs and the returned (L, B, H, l, 2 d_k) / (L, B, d, 7) caches."""
+    sd = synth_state_dict(TINY, 3)
+    L, H, d = TINY.layers, TINY.heads, TINY.d_model
+    for k, c, l, B, T, xs, g in _stream_cases(golden_dir):
+        size, stride = 8 * (c - 1) + 15, 8 * c
+        att, cnn = torch.zeros((L, B, H, l, 2 * d // H)), torch.zeros((L, B, d, 7))
+        for step in range(3):
+            o, att, cnn = O.forward_chunk(sd, H, xs[:, step * stride: step * stride + size], att, cnn, c, l, 0, offset=step * c)
+        for got, key in ((o, "out"), (att, "att"), (cnn, "cnn")):
+            want = torch.from_numpy(g[f"c{k}_step3_{key}"])
+            assert got.shape == want.shape and float((got - want).abs().max()) < FTOL, key
+    with pytest.raises(NotImplementedError):
+        O.forward_chunk(sd, H, xs[:, :size], att, cnn, c, l, 2, 0)
