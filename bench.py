@@ -70,7 +70,9 @@ def ncu_traffic_bytes():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The process is started before the warm-up steps (nvidia-smi
+    needs a few hundred ms to come up) and every line is stamped on arrival; `stop(t0, t1)` keeps the samples that fall inside
+    the timed region [t0, t1] (host clock around the barrier + synchronize pair)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -80,8 +82,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                                         text=True)
+                                          "50", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True, bufsize=1)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -89,18 +91,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)                     # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for (t, ln) in self.lines if t0 is None or (t0 <= t <= t1 + 0.06)]
+        window = "timed region"
+        if not inside and self.lines:        # region shorter than one sampling period: take the samples closest to it
+            mid = 0.5 * (t0 + t1)
+            inside = [ln for (_, ln) in sorted(self.lines, key=lambda tl: abs(tl[0] - mid))[:2]]
+            window = "nearest samples (timed region shorter than the 50 ms sampling period)"
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -113,7 +122,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_oracle_baseline(threads, steps=2, warmup=1):
@@ -214,12 +223,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value)
-    for _ in range(args.warmup):
-        plan, tokens = step_resident()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        plan, tokens = step_resident()
+    barrier()
+    t_region0 = time.perf_counter()
     launches0 = Llib.cf_launch_count()
     if rank == 0:
         Llib.cf_gemm_timing_begin(cflib.EPI_BF16, cflib.ACT_SILU)    # CUDA events around every FFN w_1 launch of the timed steps
@@ -232,6 +242,7 @@ def main():
             dist.all_gather(gathered, tokens)
     ev1.record()
     barrier()
+    t_region1 = time.perf_counter()
     launches = Llib.cf_launch_count() - launches0
     dom_ms, dom_n = 0.0, 0
     if rank == 0:
@@ -243,7 +254,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     value = world * audio * args.steps / (ms_total / 1000.0) / 3600.0
 
     # ---- end to end through the public API with host buffers
