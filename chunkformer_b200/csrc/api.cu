@@ -68,6 +68,7 @@ struct cf_handle {
   std::vector<FbankTables> fbank_tables;
   // feature-arrival events of the next cf_encode call (cf_encode_feature_events): rows < ev_rows[i] are present once ev[i] fires
   std::vector<int64_t> ev_rows;
+  int streams_n = 0, streams_ph = 0;   // multi-stream spec of the next cf_encode call (cf_encode_streams)
   std::vector<cudaEvent_t> ev;
 };
 
@@ -668,6 +669,14 @@ extern "C" size_t cf_workspace_bytes(const cf_handle* h, const cf_plan* p) {
 // --------------------------------------------------------------------------------------------------------------------
 // encoder driver
 // --------------------------------------------------------------------------------------------------------------------
+// The next cf_encode call carries `n_streams` concurrent streams (frame-synchronous streaming): the plan holds one utterance
+// of `placeholder_chunks` + 1 chunks per stream and the caches are (L, B, H, l, 2 d_k) / (L, B, d, lorder), updated in place.
+extern "C" int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_chunks) {
+  if (!h || n_streams < 0 || placeholder_chunks < 0) return fail(h, CF_ERR_INVALID, "cf_encode_streams: bad argument");
+  h->streams_n = n_streams; h->streams_ph = placeholder_chunks;
+  return CF_OK;
+}
+
 extern "C" int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_ready, void* const* events) {
   if (!h || n < 0 || (n > 0 && (!rows_ready || !events))) return fail(h, CF_ERR_INVALID, "cf_encode_feature_events: bad argument");
   h->ev_rows.assign(rows_ready, rows_ready + n);
@@ -683,7 +692,16 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   if (!h->finalized) return fail(h, CF_ERR_STATE, "cf_encode: call cf_finalize_weights first");
   if (out_dtype != CF_F32 && out_dtype != CF_BF16) return fail(h, CF_ERR_INVALID, "cf_encode: bad out_dtype");
   if (p->kernel != h->cfg.kernel) return fail(h, CF_ERR_INVALID, "cf_encode: plan conv kernel differs from the model's");
-  if ((att_cache || cnn_cache) && (p->mode != 0 || p->B != 1))
+  const int ns = h->streams_n, ph = h->streams_ph;
+  h->streams_n = 0; h->streams_ph = 0;
+  if (ns > 0) {
+    if (p->mode != 0 || p->B != ns || !att_cache || !cnn_cache)
+      return fail(h, CF_ERR_INVALID, "cf_encode: multi-stream call needs a masked-batch plan with one utterance per stream and both caches");
+    for (int u = 0; u < p->B; ++u)
+      if (p->n_chunks[u] != ph + 1) return fail(h, CF_ERR_INVALID, "cf_encode: every stream must span placeholder_chunks + 1 chunks");
+    if (ph * p->c < std::max(p->l, p->lorder) || p->r != 0)
+      return fail(h, CF_ERR_INVALID, "cf_encode: placeholder rows must cover the left context and the conv cache; right context must be 0");
+  } else if ((att_cache || cnn_cache) && (p->mode != 0 || p->B != 1))
     return fail(h, CF_ERR_INVALID, "cf_encode: streaming caches need a masked-batch plan with one utterance");
   if ((att_cache != nullptr) != (cnn_cache != nullptr))
     return fail(h, CF_ERR_INVALID, "cf_encode: pass both caches or neither");
@@ -813,17 +831,24 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
     // self-attention
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
-    if (att_cache && l > 0) {
+    if (att_cache && l > 0 && ns == 0) {
       const int tot = l * H * 2 * dk;
       att_cache_import_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<const float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d);
       ++cf::g_kernel_launches;
     }
     { EpiArgs e; e.bias = lw.qkv_b; e.out = w.qkv + size_t(l) * 4 * d; e.ldo = 4 * d;
       CF_TRY(gemm(w.y, d, lw.qkv_w, d, Mr, 4 * d, d, EPI_BF16, e)); }
-    if (att_cache && l > 0) {
+    if (att_cache && l > 0 && ns == 0) {
       const int tot = l * H * 2 * dk;
       att_cache_export_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d, trunc);
       ++cf::g_kernel_launches;
+    }
+    if (ns > 0 && l > 0) {   // placeholder rows <- caches, then caches <- last l rows of cache + frames, for every stream
+      const long long tot = (long long)ns * l * H * 2 * dk;
+      float* cl = static_cast<float*>(att_cache) + size_t(i) * tot;
+      att_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, c, l, 0);
+      att_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, c, l, 1);
+      cf::g_kernel_launches += 2;
     }
     { AttnParams a{};
       a.qkv = w.qkv; a.pos = pos->dev + size_t(i) * pos->Rpad * d; a.range = w.att_range; a.ctx = w.ctx;
@@ -834,10 +859,17 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
     // convolution module
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
-    if (cnn_cache) { cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo); ++cf::g_kernel_launches; }
+    if (cnn_cache && ns == 0) { cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo); ++cf::g_kernel_launches; }
     { EpiArgs e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
       CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mr, 2 * d, d, EPI_GLU, e)); }
-    if (cnn_cache) { cnn_cache_export_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo, trunc); ++cf::g_kernel_launches; }
+    if (cnn_cache && ns == 0) { cnn_cache_export_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo, trunc); ++cf::g_kernel_launches; }
+    if (ns > 0) {
+      const long long tot = (long long)ns * d * lo;
+      float* cl = static_cast<float*>(cnn_cache) + size_t(i) * tot;
+      cnn_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.g, ns, d, lo, (ph + 1) * c, ph * c, c, lo, 0);
+      cnn_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.g, ns, d, lo, (ph + 1) * c, ph * c, c, lo, 1);
+      cf::g_kernel_launches += 2;
+    }
     { DwConvParams q{};
       q.g = w.g; q.z = w.z; q.w = lw.dw_w; q.bias = lw.dw_b; q.ln_w = lw.cn_w; q.ln_b = lw.cn_b; q.range = w.conv_range; q.c = c; q.n_chunks = n;
       CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, (long long)w.g_rows, h->num_sms)); }

@@ -41,6 +41,40 @@ __global__ void cnn_cache_export_kernel(float* cache, const __nv_bfloat16* g, in
   cache[idx] = __bfloat162float(g[(long long)(trunc + t) * d + ch]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-stream caches (frame-synchronous streaming, encoder.py:310-390): B streams in one pass.  Stream s is an utterance of
+// `ph` placeholder chunks + one real chunk in the flat buffers (S = (ph + 1) * c rows per stream); after the projection GEMM
+// of a layer the last l (attention) / lo (conv) placeholder rows are overwritten with that stream's cache, so the real
+// chunk's window reads [cache | new frames] exactly as forward_chunk concatenates them; the new cache is the last l / lo
+// rows of cache + frames (encoder.py:376-388).  Layouts as the reference passes them: att (B, H, l, 2 d_k) and cnn (B, d, lo)
+// per layer.  `first` = buffer row of flat frame 0 (l for the K/V buffer, lo for the GLU buffer).
+// ---------------------------------------------------------------------------------------------
+__global__ void att_cache_streams_kernel(float* cache, __nv_bfloat16* qkv, int B, int l, int H, int dk, int d, int S, int ph_rows,
+                                         int c, int first, int do_export) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * l * 2 * dk;
+  if (idx >= total) return;
+  const int e = int(idx % (2 * dk));
+  const int t = int((idx / (2 * dk)) % l);
+  const int h = int((idx / ((long long)2 * dk * l)) % H);
+  const int s = int(idx / ((long long)2 * dk * l * H));
+  const int col = (e < dk) ? (2 * d + h * dk + e) : (3 * d + h * dk + (e - dk));
+  const long long row = (long long)first + (long long)s * S + ph_rows - l + t + (do_export ? c : 0);
+  if (do_export) cache[idx] = __bfloat162float(qkv[row * 4 * d + col]);
+  else qkv[row * 4 * d + col] = __float2bfloat16(cache[idx]);
+}
+__global__ void cnn_cache_streams_kernel(float* cache, __nv_bfloat16* g, int B, int d, int lo, int S, int ph_rows, int c, int first,
+                                         int do_export) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * d * lo) return;
+  const int t = int(idx % lo);
+  const int ch = int((idx / lo) % d);
+  const int s = int(idx / ((long long)lo * d));
+  const long long row = (long long)first + (long long)s * S + ph_rows - lo + t + (do_export ? c : 0);
+  if (do_export) cache[idx] = __bfloat162float(g[row * d + ch]);
+  else g[row * d + ch] = __float2bfloat16(cache[idx]);
+}
+
 // Greedy CTC: combine per-tile (best, runner-up, index) partials written by the GEMM epilogue; ties resolve to the
 // lowest index like torch.argmax (ctc.py:83-91).
 __global__ void ctc_reduce_kernel(const float* best, const float* second, const int* index, int n_tiles, long long rows,

@@ -181,14 +181,13 @@ class ChunkFormerEncoderB200:
         consumed.  Returns (out (B, c, d), ones mask (B, 1, c), new att_cache, new cnn_cache).
 
         With r = 0 a step is, per stream, the masked-chunk path on one chunk with that stream's caches and
-        truncated_context_size = c (oracle.forward_chunk, pinned against the reference).  The flat K/V buffer has one cache
-        region, so the streams of a step run as B back-to-back encoder passes on the stream; a per-stream cache stride in the
-        attention / conv kernels (one pass for all streams) is the next step."""
+        truncated_context_size = c (oracle.forward_chunk, pinned against the reference).  All B streams share one encoder pass
+        (cf_encode_streams): every stream carries its left context as placeholder rows that cf_encode fills from the caches."""
         if right_context_size != 0:
             raise NotImplementedError("forward_chunk is built for right_context_size = 0 (the shipped streaming presets)")
         c, l = int(chunk_size), int(left_context_size)
-        if c <= 0 or l < 0 or xs.dim() != 3:
-            raise ValueError("forward_chunk needs xs (B, T, feat), chunk_size > 0 and left_context_size >= 0")
+        if c <= 0 or l < self.geo.kernel // 2 or xs.dim() != 3:
+            raise ValueError("forward_chunk needs xs (B, T, feat), chunk_size > 0 and left_context_size >= kernel // 2")
         B, T, _ = xs.shape
         if T != 8 * (c - 1) + 15:
             raise ValueError(f"forward_chunk expects {8 * (c - 1) + 15} input frames per step for chunk_size {c}, got {T}")
@@ -199,16 +198,19 @@ class ChunkFormerEncoderB200:
             cnn_cache = torch.zeros((L, B, d, lo), device=self.device)
         if tuple(att_cache.shape) != (L, B, H, l, 2 * d // H) or tuple(cnn_cache.shape) != (L, B, d, lo):
             raise ValueError("cache shapes must be (L, B, H, left_context, 2*d_k) and (L, B, d, kernel//2)")
-        att_in = att_cache.to(self.device, torch.float32).permute(1, 0, 3, 2, 4).contiguous()      # (B, L, l, H, 2 d_k)
-        cnn_in = cnn_cache.to(self.device, torch.float32).permute(1, 0, 2, 3).contiguous()         # (B, L, d, 7)
-        x_dev = xs.to(self.device, torch.float32).contiguous()
-        out = torch.empty((B, c, d), dtype=torch.float32, device=self.device)
-        plan = Plan(c, l, 0, [T], [int(offset)], self.geo.kernel)
-        for b in range(B):
-            o, _ = self.encode_plan(plan, x_dev[b], att_in[b], cnn_in[b], c)      # caches are updated in place
-            out[b] = o[:c]
-        new_att = att_in.permute(1, 0, 3, 2, 4).contiguous()
-        new_cnn = cnn_in.permute(1, 0, 2, 3).contiguous()
+        # one pass for all streams: stream s = an utterance of `ph` placeholder chunks (zeros in, their K/V and conv rows are
+        # overwritten with the stream's caches inside cf_encode) + the real chunk; the negative plan offset masks the part of
+        # the left context that is not filled yet (valid cache rows = min(offset, l))
+        ph = -(-max(l, lo) // c)
+        new_att = att_cache.to(self.device, torch.float32).contiguous().clone()
+        new_cnn = cnn_cache.to(self.device, torch.float32).contiguous().clone()
+        t_tot = ph * 8 * c + T
+        x_dev = torch.zeros((B, t_tot, xs.shape[2]), dtype=torch.float32, device=self.device)
+        x_dev[:, ph * 8 * c:] = xs.to(self.device, torch.float32)
+        plan = Plan(c, l, 0, [t_tot] * B, [-(ph * c - min(int(offset), l))] * B, self.geo.kernel)
+        _lib.check(self._L.cf_encode_streams(self._h, B, ph), self._h, "cf_encode_streams")
+        o, _ = self.encode_plan(plan, x_dev.view(B * t_tot, -1), new_att, new_cnn, 0)
+        out = o.view(B, (ph + 1) * c, d)[:, ph * c:].contiguous()
         return out, torch.ones((B, 1, c), dtype=torch.bool, device=self.device), new_att, new_cnn
 
     @torch.no_grad()

@@ -139,6 +139,15 @@ CF_API int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, void* a
               int truncated_context_size, void* out, int out_dtype, void* out_bf16, void* workspace,
               size_t workspace_bytes, void* stream);
 
+/* Frame-synchronous streaming for many concurrent streams in ONE pass.  Replaces: ChunkFormerEncoder.forward_chunk
+ * (chunkformer/modules/encoder.py:310-390) at right_context_size = 0.  Call before cf_encode: the next cf_encode call then treats
+ * its masked-batch plan as `n_streams` utterances of `placeholder_chunks` + 1 chunks each (placeholder_chunks * chunk_size >=
+ * max(left_context, 7); the placeholder input frames may be zeros; offsets[s] = -(placeholder_chunks * chunk_size -
+ * min(frames already consumed, left_context)) masks the part of the cache that is not filled yet) and its caches as device fp32
+ * att_cache (L, n_streams, H, left_context, 2 d_k) / cnn_cache (L, n_streams, d, 7), the layouts forward_chunk takes and
+ * returns; both are updated in place.  The rows of the last chunk of every utterance are the step's output. */
+CF_API int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_chunks);
+
 /* ---- CTC head ---------------------------------------------------------------------------------------------------- */
 CF_API size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows);
 /* Replaces: CTC.log_softmax + argmax (chunkformer/modules/ctc.py:73-91; chunkformer_model.py:437-438, 526-527).

@@ -208,7 +208,7 @@ def test_full_size_masked_batch_properties():
 
 
 # ------------------------------------------------------------------------------------------------ frame-synchronous streaming
-@pytest.mark.parametrize("c,l,B,T", [(8, 40, 2, 555), (4, 12, 1, 300), (6, 20, 3, 411), (16, 64, 2, 900)])
+@pytest.mark.parametrize("c,l,B,T", [(8, 40, 2, 555), (4, 12, 1, 300), (6, 20, 3, 411), (16, 64, 2, 900), (8, 60, 9, 260)])
 def test_forward_chunk_by_chunk_matches_oracle(c, l, B, T):
     """forward_chunk_by_chunk / forward_chunk (right context 0) against the oracle, which is pinned to the
     reference's own streaming path (tests/test_oracle_golden.py::test_streaming_*).  Same tolerance as the offline path."""

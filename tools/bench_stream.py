@@ -1,5 +1,5 @@
-"""Frame-synchronous streaming step (forward_chunk) at the shipped presets: ms per step for B concurrent streams and the number
-of real-time streams one GPU sustains (a step consumes chunk x 80 ms of audio per stream).
+"""Frame-synchronous streaming step (forward_chunk, all streams in one encoder pass) at the shipped presets: ms per step for B
+concurrent streams and the number of real-time streams one GPU sustains (a step consumes chunk x 80 ms of audio per stream).
     python tools/bench_stream.py"""
 import os, sys, time
 import torch
@@ -11,7 +11,7 @@ from chunkformer_b200.synth import synth_state_dict
 for name, geo in (("ctc-small (d256 H4 L12)", CTC_SMALL), ("ctc-large (d512 H8 L17)", CTC_LARGE)):
     enc = ChunkFormerEncoderB200(geo, synth_state_dict(geo, 0), "cuda:0")
     for (c, l) in ((8, 60), (4, 40), (16, 64)):
-        for B in (1, 8, 32):
+        for B in (1, 32, 256):
             x = torch.randn((B, 8 * (c - 1) + 15, 80), device="cuda")
             att, cnn = torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))
             for s in range(3):
