@@ -1178,7 +1178,7 @@ extern "C" int cf_rnnt_finalize_weights(cf_rnnt* h) {
     RN_UP(wc.data(), wc.size(), &h->wc); RN_UP(bcv.data(), bcv.size(), &h->bc);
     std::vector<float> wt(size_t(J) * V);
     for (int64_t v = 0; v < V; ++v)
-      for (int64_t k = 0; k < J; ++k) wt[k * V + v] = (*ow)[v * J + k];
+      for (int64_t k = 0; k < J; ++k) wt[((k >> 2) * V + v) * 4 + (k & 3)] = (*ow)[v * J + k];   // [J / 4][V][4]
     RN_UP(wt.data(), wt.size(), &h->woT);
   }
 #undef RN_NEED
@@ -1199,7 +1199,7 @@ static RnntWs rnnt_carve(const cf_rnnt_config& c, int64_t rows, int B, void* bas
   w.E = cv.take<float>(size_t(rows) * c.join_dim);
   w.seg_start = cv.take<long long>(B); w.seg_len = cv.take<int>(B);
   w.s.t = cv.take<int>(B); w.s.step = cv.take<int>(B); w.s.token = cv.take<int>(B); w.s.cur = cv.take<int>(B);
-  w.s.count = cv.take<int>(B); w.s.active = cv.take<int>(B);
+  w.s.count = cv.take<int>(B); w.s.active = cv.take<int>(B); w.s.act_cur = cv.take<int>(B); w.s.act_tok = cv.take<int>(B);
   w.s.n_active = cv.take<int>(1); w.s.remaining = cv.take<int>(1); w.s.overflow = cv.take<int>(1);
   w.s.h = cv.take<float>(w.state_floats); w.s.c = cv.take<float>(w.state_floats);
   w.s.g = cv.take<float>(size_t(B) * c.join_dim);
@@ -1239,7 +1239,8 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   rnnt_init_kernel<<<64, 256, 0, st>>>(w.s, w.seg_len, out_counts, n_utt, c.blank, w.state_floats);
   ++cf::g_kernel_launches;
   CF_RCUDA(h, cudaGetLastError());
-  RnntJointParams jp{w.E, h->woT, h->bo, w.seg_start, w.seg_len, c.join_dim, c.vocab, w.n_vtiles};
+  RnntJointParams jp{w.E, h->woT, h->bo, w.seg_start, w.seg_len, c.join_dim, c.vocab, w.n_vtiles, 0};
+  { const char* e = getenv("CF_RNNT_DEBUG"); jp.debug = e ? atoi(e) : 0; }
   RnntDecideParams dp{w.seg_len, reinterpret_cast<long long*>(out_tokens), out_frames, out_counts, n_utt, w.n_vtiles, n_steps,
                       capacity, c.blank};
   const unsigned tiles = unsigned(std::min((n_utt + RNNT_BT - 1) / RNNT_BT, 8));
@@ -1259,8 +1260,8 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
     }
     rnnt_predproj_kernel<<<dim3(unsigned((c.join_dim + 3) / 4), tiles), 128, 0, st>>>(h->wc, h->bc, c.join_dim, c.hidden, n_utt,
                                                                                       c.layers, w.s);
-    dim3 jg(unsigned(w.n_vtiles), unsigned((n_utt + RNNT_JU - 1) / RNNT_JU));
-    rnnt_joint_kernel<<<jg, RNNT_JV * RNNT_JK, jsmem, st>>>(jp, w.s, n_utt);
+    dim3 jg(unsigned(w.n_vtiles), unsigned(n_utt));
+    rnnt_joint_kernel<<<jg, RNNT_JTHREADS, jsmem, st>>>(jp, w.s, n_utt);
     rnnt_decide_kernel<<<1, 256, 0, st>>>(dp, w.s);
     cf::g_kernel_launches += c.layers + 3;
   };

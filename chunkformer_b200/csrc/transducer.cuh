@@ -26,7 +26,9 @@ struct RnntState {                 // device arrays, one entry per utterance unl
   int* token;                      // predictor input (last emitted symbol, blank at start)
   int* cur;                        // which half of the state double-buffer is committed
   int* count;                      // symbols emitted so far
-  int* active;                     // [B] utterances that need a predictor step this iteration
+  int* active;                     // [B] utterances that need a predictor step this iteration (compact, -1 = empty slot)
+  int* act_cur;                    // [B] committed state half of active[i]   } read in ONE round trip by the predictor
+  int* act_tok;                    // [B] predictor input token of active[i]  } kernels (no n_active -> active -> cur chain)
   int* n_active;                   // [1]
   int* remaining;                  // [1] utterances not finished
   int* overflow;                   // [1] set when an utterance ran out of output capacity
@@ -93,27 +95,41 @@ struct RnntLstmParams {
 CF_DEVINL float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void __launch_bounds__(128) rnnt_lstm_kernel(RnntLstmParams p, RnntState s) {
-  const int n_act = *s.n_active;
-  if (n_act == 0) return;
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (j >= p.H) return;
   const size_t half = size_t(p.layers) * p.B * p.H;
+  // gate biases of this unit: no dependence on the utterances, requested first
+  float bias[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) bias[q] = __ldg(p.b_ih + q * p.H + j) + __ldg(p.b_hh + q * p.H + j);
   // tiles of RNNT_BT utterances run side by side (blockIdx.y): the step is a chain of L2 round trips, not throughput
-  for (int b0 = blockIdx.y * RNNT_BT; b0 < n_act; b0 += gridDim.y * RNNT_BT) {
+  for (int b0 = blockIdx.y * RNNT_BT; b0 < p.B; b0 += gridDim.y * RNNT_BT) {
+    int bs[RNNT_BT], curs[RNNT_BT], toks[RNNT_BT];
+#pragma unroll
+    for (int u = 0; u < RNNT_BT; ++u) {
+      const bool in = b0 + u < p.B;
+      bs[u] = in ? s.active[b0 + u] : -1;
+      curs[u] = in ? s.act_cur[b0 + u] : 0;
+      toks[u] = in ? s.act_tok[b0 + u] : 0;
+    }
+    if (bs[0] < 0) return;                      // the list is compact: an empty first slot ends the work
     float acc[RNNT_BT][4];
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
     const float* xin[RNNT_BT]; const float* hin[RNNT_BT];
+    float c_old[RNNT_BT];
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u) {
-      const int b = (b0 + u < n_act) ? s.active[b0 + u] : s.active[b0];
-      const int cur = s.cur[b];
+      const int b = bs[u] >= 0 ? bs[u] : bs[0];
+      const int cur = bs[u] >= 0 ? curs[u] : curs[0];
+      const int tok = bs[u] >= 0 ? toks[u] : toks[0];
       hin[u] = s.h + cur * half + (size_t(p.layer) * p.B + b) * p.H;
-      xin[u] = p.embed ? p.embed + size_t(s.token[b]) * p.In
+      xin[u] = p.embed ? p.embed + size_t(tok) * p.In
                        : s.h + (cur ^ 1) * half + (size_t(p.layer - 1) * p.B + b) * p.H;
+      c_old[u] = s.c[cur * half + (size_t(p.layer) * p.B + b) * p.H + j];
     }
     // both products in slabs of 512 columns: the slab's 16 weight vectors of this unit are all requested before the first
     // FMA (the kernel is latency-bound: a few hundred FMAs per warp behind L2 round trips)
@@ -150,15 +166,13 @@ __global__ void __launch_bounds__(128) rnnt_lstm_kernel(RnntLstmParams p, RnntSt
     // lane u finalises utterance u of the tile
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u) {
-      if (lane == u && b0 + u < n_act) {
-        const int b = s.active[b0 + u];
-        const int cur = s.cur[b];
+      if (lane == u && bs[u] >= 0) {
+        const int b = bs[u], cur = curs[u];
         float gate[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) gate[q] = acc[u][q] + p.b_ih[q * p.H + j] + p.b_hh[q * p.H + j];
+        for (int q = 0; q < 4; ++q) gate[q] = acc[u][q] + bias[q];
         const size_t at = (size_t(p.layer) * p.B + b) * p.H + j;
-        const float c_old = s.c[cur * half + at];
-        const float c_new = sigmoidf_acc(gate[1]) * c_old + sigmoidf_acc(gate[0]) * tanhf(gate[2]);
+        const float c_new = sigmoidf_acc(gate[1]) * c_old[u] + sigmoidf_acc(gate[0]) * tanhf(gate[2]);
         s.c[(cur ^ 1) * half + at] = c_new;
         s.h[(cur ^ 1) * half + at] = sigmoidf_acc(gate[3]) * tanhf(c_new);
       }
@@ -170,20 +184,28 @@ __global__ void __launch_bounds__(128) rnnt_lstm_kernel(RnntLstmParams p, RnntSt
 // (predictor.py:205 followed by joint.py:88; composed once at load time in fp64).  Warp = one output row.
 __global__ void __launch_bounds__(128) rnnt_predproj_kernel(const float* __restrict__ Wc, const float* __restrict__ bc, int J,
                                                             int H, int B, int layers, RnntState s) {
-  const int n_act = *s.n_active;
-  if (n_act == 0) return;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= J) return;
   const size_t half = size_t(layers) * B * H;
-  for (int b0 = blockIdx.y * RNNT_BT; b0 < n_act; b0 += gridDim.y * RNNT_BT) {
+  const float bias = __ldg(bc + r);
+  for (int b0 = blockIdx.y * RNNT_BT; b0 < B; b0 += gridDim.y * RNNT_BT) {
+    int bs[RNNT_BT], curs[RNNT_BT];
+#pragma unroll
+    for (int u = 0; u < RNNT_BT; ++u) {
+      const bool in = b0 + u < B;
+      bs[u] = in ? s.active[b0 + u] : -1;
+      curs[u] = in ? s.act_cur[b0 + u] : 0;
+    }
+    if (bs[0] < 0) return;
     float acc[RNNT_BT];
     const float* hin[RNNT_BT];
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u) {
       acc[u] = 0.f;
-      const int b = (b0 + u < n_act) ? s.active[b0 + u] : s.active[b0];
-      hin[u] = s.h + (s.cur[b] ^ 1) * half + (size_t(layers - 1) * B + b) * H;
+      const int b = bs[u] >= 0 ? bs[u] : bs[0];
+      const int cur = bs[u] >= 0 ? curs[u] : curs[0];
+      hin[u] = s.h + (cur ^ 1) * half + (size_t(layers - 1) * B + b) * H;
     }
     for (int k0 = 0; k0 < H; k0 += 512) {
       float4 w[4];
@@ -206,7 +228,7 @@ __global__ void __launch_bounds__(128) rnnt_predproj_kernel(const float* __restr
     for (int u = 0; u < RNNT_BT; ++u) acc[u] = warp_sum(acc[u]);
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u)
-      if (lane == u && b0 + u < n_act) s.g[size_t(s.active[b0 + u]) * J + r] = acc[u] + bc[r];
+      if (lane == u && bs[u] >= 0) s.g[size_t(bs[u]) * J + r] = acc[u] + bias;
   }
 }
 
@@ -217,118 +239,106 @@ __global__ void __launch_bounds__(128) rnnt_predproj_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 struct RnntJointParams {
   const float* E;            // [rows, J] enc_ffn output
-  const float* WoT;          // [J, V]
+  const float* WoT;          // [J / 4][V][4]: ffn_out transposed in groups of four k, one 16-byte load per (k group, v)
   const float* bo;           // [V]
   const long long* seg_start; const int* seg_len;   // device [B]
   int J, V, n_vtiles;
+  int debug;                 // timing experiments: 1 = no tanh / E loads, 2 = no K loop, 4 = no reductions
 };
 
-constexpr int RNNT_JK = 4;        // K slices per vocabulary entry (threads per CTA = RNNT_JV * RNNT_JK)
-constexpr int RNNT_JU = 1;        // utterances per CTA (more share one read of the ffn_out tile, but leave SMs idle: measured slower)
-constexpr int RNNT_JR = RNNT_JU * RNNT_FB;   // activation rows per CTA
+constexpr int RNNT_VPT = 4;       // vocabulary entries per thread: every activation read from shared memory feeds 16 FMAs
+constexpr int RNNT_JK = 16;       // K slices (warps) per CTA; a warp covers 32 x VPT = RNNT_JV vocabulary entries
+constexpr int RNNT_JR = RNNT_FB;  // activation rows per CTA (one utterance; sharing the ffn_out tile between utterances leaves
+                                  // SMs idle and was slower)
+constexpr int RNNT_JTHREADS = 32 * RNNT_JK;
+static_assert(RNNT_JV == 32 * RNNT_VPT, "a warp covers the CTA's vocabulary tile");
 
 inline size_t rnnt_joint_smem_bytes(int J) {
-  return size_t(RNNT_JR) * J * 4 + size_t(RNNT_JK - 1) * RNNT_JR * RNNT_JV * 4 + size_t(RNNT_JR) * (RNNT_JV / 32) * 8;
+  return size_t(RNNT_JR) * J * 4 + size_t(RNNT_JK) * RNNT_JR * RNNT_JV * 4;
 }
 
-__global__ void __launch_bounds__(RNNT_JV * RNNT_JK) rnnt_joint_kernel(RnntJointParams p, RnntState s, int B) {
+// Phase timings of the first version (thread = one vocabulary entry x one of 4 K-slices, 4-byte weight loads): 20 us =
+// 5 launch / prologue / reductions + 3.7 activation tile (encoder rows, tanh) + 11.4 K loop; the K loop was bound by the
+// shared-memory pipe (one 16-byte broadcast read per 4 FMAs), not by the weight loads (16-byte loads alone: 18.6 us).
+__global__ void __launch_bounds__(RNNT_JTHREADS) rnnt_joint_kernel(RnntJointParams p, RnntState s, int B) {
   extern __shared__ __align__(16) float jsm[];
   float* a = jsm;                                          // [JR][J]
-  float* s_acc = a + size_t(RNNT_JR) * p.J;                // [JK - 1][JR][JV]
-  float* s_val = s_acc + size_t(RNNT_JK - 1) * RNNT_JR * RNNT_JV;   // [JR][JV / 32]
-  int* s_idx = reinterpret_cast<int*>(s_val + RNNT_JR * (RNNT_JV / 32));
-  __shared__ int s_t0[RNNT_JU], s_nf[RNNT_JU];
-  const int b_first = blockIdx.y * RNNT_JU;
-  if (threadIdx.x < RNNT_JU) {
-    const int b = b_first + threadIdx.x;
-    int t0 = 0, nf = 0;
-    if (b < B) { t0 = s.t[b]; nf = max(0, min(RNNT_FB, p.seg_len[b] - t0)); }
-    s_t0[threadIdx.x] = t0; s_nf[threadIdx.x] = nf;
-  }
-  __syncthreads();
+  float* s_acc = a + size_t(RNNT_JR) * p.J;                // [JK][JR][JV]
+  const int b = blockIdx.y;
+  const int t0 = s.t[b];
+  const int nf = b < B ? max(0, min(RNNT_FB, p.seg_len[b] - t0)) : 0;
+  if (nf == 0) return;
   {
-    int any = 0;
-#pragma unroll
-    for (int u = 0; u < RNNT_JU; ++u) any += s_nf[u];
-    if (any == 0) return;
-  }
-  for (int i = threadIdx.x; i < RNNT_JR * p.J; i += RNNT_JV * RNNT_JK) {
-    const int r = i / p.J, k = i - r * p.J;
-    const int u = r / RNNT_FB, f = r - u * RNNT_FB;
-    float val = 0.f;
-    if (f < s_nf[u]) {
-      const int b = b_first + u;
-      val = tanhf(p.E[(p.seg_start[b] + s_t0[u] + f) * (long long)p.J + k] + s.g[size_t(b) * p.J + k]);
+    const float* e = p.E + (p.seg_start[b] + t0) * (long long)p.J;
+    const float* g = s.g + size_t(b) * p.J;
+    for (int i = threadIdx.x; i < RNNT_JR * p.J; i += RNNT_JTHREADS) {
+      const int f = i / p.J, k = i - f * p.J;
+      a[i] = f < nf ? ((p.debug & 1) ? 0.5f : tanhf(e[(long long)f * p.J + k] + g[k])) : 0.f;
     }
-    a[i] = val;
   }
   __syncthreads();
-  const int tv = threadIdx.x & (RNNT_JV - 1), kq = threadIdx.x / RNNT_JV;   // a warp shares kq: the tile reads broadcast
-  const int v = blockIdx.x * RNNT_JV + tv;
-  const int vc = min(v, p.V - 1);
-  float acc[RNNT_JR];
+  const int lane = threadIdx.x & 31, kq = threadIdx.x >> 5;
+  const int v0 = blockIdx.x * RNNT_JV + lane;             // this thread's entries: v0 + 32 i
+  float acc[RNNT_JR][RNNT_VPT];
 #pragma unroll
-  for (int r = 0; r < RNNT_JR; ++r) acc[r] = 0.f;
-  // slice kq takes the 4-wide k groups kq, kq + JK, ...; the 64 weights of a 256-column phase are all requested before the
-  // first FMA (two L2 round trips for J = 512 instead of one per step)
-  const float* wp = p.WoT + vc;
-  constexpr int GROUPS = 16;
-  for (int k0 = 0; k0 < p.J; k0 += GROUPS * 4 * RNNT_JK) {
-    float w[GROUPS][4];
+  for (int r = 0; r < RNNT_JR; ++r)
 #pragma unroll
-    for (int m = 0; m < GROUPS; ++m) {
+    for (int i = 0; i < RNNT_VPT; ++i) acc[r][i] = 0.f;
+  // warp kq takes the 4-wide k groups kq, kq + JK, ...; four groups (16 weight vectors of 16 bytes) in flight per step
+  const float4* wp = reinterpret_cast<const float4*>(p.WoT);
+  for (int k0 = 0; k0 < ((p.debug & 2) ? 0 : p.J); k0 += 4 * 4 * RNNT_JK) {
+    float4 w[4][RNNT_VPT];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
       const int km = k0 + 4 * (kq + RNNT_JK * m);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[m][i] = km < p.J ? __ldg(wp + size_t(km + i) * p.V) : 0.f;
+      for (int i = 0; i < RNNT_VPT; ++i) {
+        const int v = min(v0 + 32 * i, p.V - 1);
+        w[m][i] = km < p.J ? __ldg(wp + size_t(km >> 2) * p.V + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
-    for (int m = 0; m < GROUPS; ++m) {
+    for (int m = 0; m < 4; ++m) {
       const int km = k0 + 4 * (kq + RNNT_JK * m);
       if (km < p.J) {
 #pragma unroll
         for (int r = 0; r < RNNT_JR; ++r) {
           const float4 x = *reinterpret_cast<const float4*>(&a[size_t(r) * p.J + km]);
-          acc[r] = fmaf(x.x, w[m][0], acc[r]); acc[r] = fmaf(x.y, w[m][1], acc[r]);
-          acc[r] = fmaf(x.z, w[m][2], acc[r]); acc[r] = fmaf(x.w, w[m][3], acc[r]);
+#pragma unroll
+          for (int i = 0; i < RNNT_VPT; ++i) {
+            acc[r][i] = fmaf(x.x, w[m][i].x, acc[r][i]); acc[r][i] = fmaf(x.y, w[m][i].y, acc[r][i]);
+            acc[r][i] = fmaf(x.z, w[m][i].z, acc[r][i]); acc[r][i] = fmaf(x.w, w[m][i].w, acc[r][i]);
+          }
         }
       }
     }
   }
-  if (kq > 0) {
 #pragma unroll
-    for (int r = 0; r < RNNT_JR; ++r) s_acc[(size_t(kq - 1) * RNNT_JR + r) * RNNT_JV + tv] = acc[r];
-  }
+  for (int r = 0; r < RNNT_JR; ++r)
+#pragma unroll
+    for (int i = 0; i < RNNT_VPT; ++i) s_acc[(size_t(kq) * RNNT_JR + r) * RNNT_JV + lane + 32 * i] = acc[r][i];
   __syncthreads();
-  if (kq == 0) {
-    const float bias = __ldg(p.bo + vc);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // warp r (r < JR) finishes frame r: sum the K slices for its 128 entries, add the bias, argmax (lowest index on ties)
+  if (kq < RNNT_JR) {
+    const int r = kq;
+    float val = -INFINITY; int idx = 0x7fffffff;
 #pragma unroll
-    for (int r = 0; r < RNNT_JR; ++r) {
-      float sum = acc[r];
+    for (int i = 0; i < RNNT_VPT; ++i) {
+      const int v = v0 + 32 * i;
+      float sum = 0.f;
 #pragma unroll
-      for (int q = 0; q < RNNT_JK - 1; ++q) sum += s_acc[(size_t(q) * RNNT_JR + r) * RNNT_JV + tv];
-      float val = v < p.V ? sum + bias : -INFINITY;
-      int idx = v;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, val, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-      }
-      if (lane == 0) { s_val[r * (RNNT_JV / 32) + warp] = val; s_idx[r * (RNNT_JV / 32) + warp] = idx; }
+      for (int q = 0; q < RNNT_JK; ++q) sum += s_acc[(size_t(q) * RNNT_JR + r) * RNNT_JV + lane + 32 * i];
+      const float cand = v < p.V ? sum + __ldg(p.bo + v) : -INFINITY;
+      if (cand > val || (cand == val && v < idx)) { val = cand; idx = v; }
     }
-  }
-  __syncthreads();
-  if (threadIdx.x < RNNT_JR) {
-    const int r = threadIdx.x, u = r / RNNT_FB, f = r - u * RNNT_FB;
-    if (f < s_nf[u]) {
-      float val = s_val[r * (RNNT_JV / 32)]; int idx = s_idx[r * (RNNT_JV / 32)];
 #pragma unroll
-      for (int w = 1; w < RNNT_JV / 32; ++w) {
-        const float ov = s_val[r * (RNNT_JV / 32) + w]; const int oi = s_idx[r * (RNNT_JV / 32) + w];
-        if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-      }
-      const size_t at = (size_t(b_first + u) * RNNT_FB + f) * p.n_vtiles + blockIdx.x;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+    if (lane == 0 && r < nf) {
+      const size_t at = (size_t(b) * RNNT_FB + r) * p.n_vtiles + blockIdx.x;
       s.part_val[at] = val;
       s.part_idx[at] = idx;
     }
@@ -396,13 +406,17 @@ __global__ void __launch_bounds__(256) rnnt_decide_kernel(RnntDecideParams p, Rn
       s.t[b] = t; s.step[b] = step;
       if (t < len) {
         atomicAdd(&s_rem, 1);
-        if (emitted) s.active[atomicAdd(&s_nact, 1)] = b;
+        if (emitted) {
+          const int slot = atomicAdd(&s_nact, 1);
+          s.active[slot] = b; s.act_cur[slot] = s.cur[b]; s.act_tok[slot] = sym;
+        }
       } else {
         p.out_counts[b] = s.count[b];
       }
     }
   }
   __syncthreads();
+  for (int i = s_nact + threadIdx.x; i < p.B; i += blockDim.x) s.active[i] = -1;     // empty slots of the compact list
   if (threadIdx.x == 0) { *s.n_active = s_nact; *s.remaining = s_rem; }
 }
 
@@ -414,8 +428,9 @@ __global__ void rnnt_init_kernel(RnntState s, const int* seg_len, int* out_count
     int n = 0;
     for (int b = 0; b < B; ++b) {
       s.t[b] = 0; s.step[b] = 1; s.token[b] = blank; s.cur[b] = 0; s.count[b] = 0; out_counts[b] = 0;
-      if (seg_len[b] > 0) s.active[n++] = b;
+      if (seg_len[b] > 0) { s.active[n] = b; s.act_cur[n] = 0; s.act_tok[n] = blank; ++n; }
     }
+    for (int i = n; i < B; ++i) s.active[i] = -1;
     *s.n_active = n; *s.remaining = n; *s.overflow = 0;
   }
 }
