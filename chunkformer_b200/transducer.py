@@ -121,3 +121,10 @@ class TransducerGreedyB200:
         B, T, _ = encoder_out.shape
         lens = [min(int(v), T) for v in (encoder_out_lens.tolist() if torch.is_tensor(encoder_out_lens) else encoder_out_lens)]
         return [tok.tolist() for tok, _ in self.search_flat(encoder_out.reshape(B * T, -1), [b * T for b in range(B)], lens, n_steps)]
+
+    def greedy_search(self, encoder_out: torch.Tensor, encoder_out_lens, n_steps: int = 64) -> List[List[int]]:
+        """greedy_search.py:147-170 (the unified entry point: `basic_greedy_search` for one utterance, `batch_greedy_search`
+        otherwise; both emit the same symbols, so one device path serves them)."""
+        return self.batch_greedy_search(encoder_out, encoder_out_lens, n_steps)
+
+    basic_greedy_search = greedy_search

@@ -242,3 +242,23 @@ def test_forward_chunk_argument_errors():
         enc.forward_chunk(x[:, :50], chunk_size=8, left_context_size=40)
     with pytest.raises(ValueError):
         enc.forward_chunk(x, torch.zeros((3, 1, 4, 39, 128)), torch.zeros((3, 1, 256, 7)), 8, 40)
+
+
+def test_forward_chunk_many_streams_equals_single_stream_calls():
+    """Size-independent property at serving scale: one pass over 96 streams gives every stream what a pass with that stream
+    alone gives (rows of different streams never mix; only the bf16 tile grouping may differ)."""
+    _, enc = _model(SMALL, 5)
+    c, l, B = 8, 60, 96
+    size = 8 * (c - 1) + 15
+    gen = torch.Generator().manual_seed(17)
+    att, cnn = torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))
+    singles = {b: (torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))) for b in (0, 37, 95)}
+    for step in range(10):                                  # beyond l / c steps: the left context fills up and then slides
+        x = torch.randn((B, size, 80), generator=gen).to(DEV)
+        out, _, att, cnn = enc.forward_chunk(x, att, cnn, c, l, 0, offset=step * c)
+        for b, (a1, c1) in singles.items():
+            o1, _, a1, c1 = enc.forward_chunk(x[b:b + 1], a1, c1, c, l, 0, offset=step * c)
+            singles[b] = (a1, c1)
+            assert float((o1[0] - out[b]).abs().max()) < 2e-2, (step, b)
+            assert float((a1[:, 0] - att[:, b]).abs().max()) < 2e-2 and float((c1[:, 0] - cnn[:, b]).abs().max()) < 2e-2
+    assert torch.isfinite(out).all()
