@@ -83,6 +83,24 @@ CF_DEVINL bool mbar_test(uint64_t* bar, uint32_t parity) {     // non-blocking p
 __device__ const int kSkewRowPerm[32] = {20, 3, 6, 13, 31, 18, 17, 0, 7, 25, 11, 5, 10, 22, 24, 28,
                                        9, 15, 29, 27, 30, 2, 8, 4, 12, 21, 26, 19, 14, 1, 16, 23};
 
+// The 32 skew values a thread needs start at half (31 - lane) of its private row.  Read as 17 aligned 32-bit words and realign
+// with one funnel shift per pair: under kSkewRowPerm the word reads are bank-conflict free (17 wavefronts per warp instead of
+// the 48 of thirty-two 2-byte reads; tools/skew_row_perm.py).
+struct SkewWords {
+  uint32_t w[17];
+  uint32_t sh;
+  CF_DEVINL void load(const uint8_t* row, int lane) {
+    const uint32_t* p32 = reinterpret_cast<const uint32_t*>(row) + ((31 - lane) >> 1);
+    sh = uint32_t((31 - lane) & 1) * 16u;
+#pragma unroll
+    for (int i = 0; i < 17; ++i) w[i] = p32[i];
+  }
+  CF_DEVINL float2 pair(int j) const {              // halves (31 - lane) + 2 j and + 2 j + 1
+    const uint32_t pr = __funnelshift_r(w[j], w[j + 1], sh);
+    return __half22float2(*reinterpret_cast<const __half2*>(&pr));
+  }
+};
+
 struct AttnTcParams {
   const int2* range;      // [n_chunks + 2] valid key slots per chunk (entries beyond n_chunks are empty)
   __nv_bfloat16* ctx;     // [n_chunks * 64, d]
@@ -245,7 +263,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
     // cuts the bank-conflict replays of the 2-byte skew reads from 2.0 to 1.5 wavefronts per load at the 144-byte pitch
     // while the 16-byte staging stores stay conflict free
     uint8_t* stage = s_stage + ((warp - 2) * 32 + kSkewRowPerm[lane]) * ATC_STAGE_PITCH;
-    const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
     const int cb_thread = 96 - 32 * quad + 64 * set;   // first S_bd column this warp stages (warp-uniform)
     uint32_t blk = 0;
     int ep_g = -1;                                     // chunk (of this row) whose item is finished but not yet written out
@@ -319,21 +336,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
           tmem_ld_wait();
           const int u0 = 128 * b + 64 * set + 32 * sb;
           const bool edge = (u0 < ulo) || (u0 + 32 > uhi);
+          SkewWords sk;
+          sk.load(stage, lane);
           if (__any_sync(0xffffffffu, edge)) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int uq = u0 + k;
-              float v = PRE ? __uint_as_float(r0[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(r0[k]), p.scale_log2e, __half2float(stage_rd[k]));
-              v = (uq >= ulo && uq < uhi) ? v : -INFINITY;
-              s[32 * sb + k] = v;
-              mx = fmaxf(mx, v);
+            for (int k = 0; k < 32; k += 2) {
+              const float2 bd = sk.pair(k >> 1);
+              float v0 = PRE ? __uint_as_float(r0[k]) + bd.x : fmaf(__uint_as_float(r0[k]), p.scale_log2e, bd.x);
+              float v1 = PRE ? __uint_as_float(r0[k + 1]) + bd.y : fmaf(__uint_as_float(r0[k + 1]), p.scale_log2e, bd.y);
+              v0 = (u0 + k >= ulo && u0 + k < uhi) ? v0 : -INFINITY;
+              v1 = (u0 + k + 1 >= ulo && u0 + k + 1 < uhi) ? v1 : -INFINITY;
+              s[32 * sb + k] = v0; s[32 * sb + k + 1] = v1;
+              mx = fmaxf(mx, fmaxf(v0, v1));
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float v = PRE ? __uint_as_float(r0[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(r0[k]), p.scale_log2e, __half2float(stage_rd[k]));
-              s[32 * sb + k] = v;
-              mx = fmaxf(mx, v);
+            for (int k = 0; k < 32; k += 2) {
+              const float2 bd = sk.pair(k >> 1);
+              const float v0 = PRE ? __uint_as_float(r0[k]) + bd.x : fmaf(__uint_as_float(r0[k]), p.scale_log2e, bd.x);
+              const float v1 = PRE ? __uint_as_float(r0[k + 1]) + bd.y : fmaf(__uint_as_float(r0[k + 1]), p.scale_log2e, bd.y);
+              s[32 * sb + k] = v0; s[32 * sb + k + 1] = v1;
+              mx = fmaxf(mx, fmaxf(v0, v1));
             }
           }
         }
@@ -976,7 +999,6 @@ attention_ring_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/
     const int rho = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     uint8_t* stage = s_stage + ((warp - 2) * 32 + kSkewRowPerm[lane]) * ATC_STAGE_PITCH;   // see attention_tc_kernel
-    const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
     const int cbw = 96 - 32 * quad + 32 * set;          // first S_bd column this warp stages (warp-uniform)
     constexpr int OC = DK / 2;                          // output columns per thread
     uint32_t blk = 0;
@@ -1050,21 +1072,27 @@ attention_ring_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/
           if (lane == 0) mbar_arrive(s_free);            // this warp's part of S is in registers / shared memory
           const int u0 = 64 * b + 32 * set;
           const bool edge = (u0 < ulo) || (u0 + 32 > uhi);
+          SkewWords sk;
+          sk.load(stage, lane);
           if (__any_sync(0xffffffffu, edge)) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int uq = u0 + k;
-              float v = PRE ? __uint_as_float(ra[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(ra[k]), p.scale_log2e, __half2float(stage_rd[k]));
-              v = (uq >= ulo && uq < uhi) ? v : -INFINITY;
-              s[k] = v;
-              mx = fmaxf(mx, v);
+            for (int k = 0; k < 32; k += 2) {
+              const float2 bd = sk.pair(k >> 1);
+              float v0 = PRE ? __uint_as_float(ra[k]) + bd.x : fmaf(__uint_as_float(ra[k]), p.scale_log2e, bd.x);
+              float v1 = PRE ? __uint_as_float(ra[k + 1]) + bd.y : fmaf(__uint_as_float(ra[k + 1]), p.scale_log2e, bd.y);
+              v0 = (u0 + k >= ulo && u0 + k < uhi) ? v0 : -INFINITY;
+              v1 = (u0 + k + 1 >= ulo && u0 + k + 1 < uhi) ? v1 : -INFINITY;
+              s[k] = v0; s[k + 1] = v1;
+              mx = fmaxf(mx, fmaxf(v0, v1));
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float v = PRE ? __uint_as_float(ra[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(ra[k]), p.scale_log2e, __half2float(stage_rd[k]));
-              s[k] = v;
-              mx = fmaxf(mx, v);
+            for (int k = 0; k < 32; k += 2) {
+              const float2 bd = sk.pair(k >> 1);
+              const float v0 = PRE ? __uint_as_float(ra[k]) + bd.x : fmaf(__uint_as_float(ra[k]), p.scale_log2e, bd.x);
+              const float v1 = PRE ? __uint_as_float(ra[k + 1]) + bd.y : fmaf(__uint_as_float(ra[k + 1]), p.scale_log2e, bd.y);
+              s[k] = v0; s[k + 1] = v1;
+              mx = fmaxf(mx, fmaxf(v0, v1));
             }
           }
         }

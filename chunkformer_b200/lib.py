@@ -83,8 +83,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if build_if_missing and (not os.path.exists(path) or _build.needs_build()):
+    path = os.environ.get("CHUNKFORMER_B200_LIB") or _build.LIB      # A/B builds of the same tree (tools only)
+    if build_if_missing and path == _build.LIB and (not os.path.exists(path) or _build.needs_build()):
         try:
             _build.build()
         except Exception as e:  # no nvcc on this machine: use the shipped .so if there is one
