@@ -150,13 +150,12 @@ template <int D, int KW, int FG>
 __global__ void __launch_bounds__(D / 2) dwconv_ln_silu_kernel(DwConvParams p) {
   constexpr int NT = D / 2;
   constexpr int NW = NT / 32;
-  constexpr int LO = KW / 2;
   constexpr int ROWS = FG + KW - 1;
   __shared__ float s_part[NW][FG];
   __shared__ float s_mean[FG];
   __shared__ float s_rstd[FG];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int groups = p.c / FG;
   const int chunk = blockIdx.x / groups;
   const int f0 = (blockIdx.x - chunk * groups) * FG;   // first frame of this group inside the chunk

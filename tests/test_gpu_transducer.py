@@ -82,3 +82,25 @@ def test_unsupported_heads_are_rejected():
         TransducerGreedyB200(bad, device=DEV)
     with pytest.raises(ValueError):
         TransducerGreedyB200({k: v for k, v in sd.items() if not k.startswith("predictor.rnn")}, device=DEV)
+
+
+def test_many_utterances_use_several_predictor_tiles():
+    """21 utterances = three tiles of 8 in the predictor kernels, several joint CTAs per utterance (V = 300 -> 3 vocabulary
+    tiles), lengths 0 .. 40; every hypothesis against the oracle."""
+    V, emb, hid, nl, po, E, J = 300, 64, 128, 2, 96, 80, 112
+    sd = synth_transducer_state_dict(V, emb, hid, nl, po, E, J, blank_bias=4.5, seed=21)
+    gen = torch.Generator().manual_seed(22)
+    lens = [int(v) for v in torch.randint(0, 41, (21,), generator=gen)]
+    lens[3], lens[17] = 40, 1
+    starts, pos = [], 0
+    for n in lens:
+        starts.append(pos)
+        pos += n + 3
+    enc = torch.randn((pos, E), generator=gen)
+    srch = TransducerGreedyB200(sd, device=DEV)
+    res = srch.search_flat(enc.to(DEV), starts, lens, n_steps=5)
+    total = 0
+    for b, (tok, fr) in enumerate(res):
+        _assert_same_until_near_tie(sd, enc[starts[b]:starts[b] + lens[b]], lens[b], 5, tok, fr, f"utt{b}")
+        total += tok.numel()
+    assert total > 100
