@@ -1,6 +1,7 @@
 """Transducer greedy search (cf_rnnt_greedy) on the rnnt-large head sizes (examples/asr/rnnt/conf/chunkformer-rnnt-large-vie.yaml:
-vocab 1024, embed 256, LSTM 2 x 512, join 512) over the encoder rows of the benchmark batch (19 utterances, 14 400 s), next
-to the CPU oracle (= the reference's per-frame Python loop restated) on a bounded sample.
+vocab 1024, embed 256, LSTM 2 x 512, join 512) over the encoder rows of the benchmark batch (19 utterances, 14 400 s).  The CPU side of
+the comparison (the oracle, i.e. the reference's per-frame loop restated) lives in tests/perf_transducer_cpu_oracle.py: only
+tests/, smoke() and bench.py's CPU legs execute oracle/.
     python tools/bench_transducer.py [blank_bias ...]"""
 import os, sys, time
 import torch
@@ -31,11 +32,3 @@ for bb in biases:
     print(f"blank_bias {bb}: {len(enc_lens)} utterances, {sum(enc_lens)} frames (longest {max(enc_lens)}), {syms} symbols "
           f"(longest utterance {max(t.numel() for t, _ in res)}); {srch.last_iterations} iterations, {dt * 1e3:.1f} ms "
           f"= {dt * 1e6 / srch.last_iterations:.1f} us per iteration; {14400 / dt / 3600:.1f} audio-h/s")
-    # CPU oracle on a bounded sample: the first 1500 frames of the longest utterance
-    from oracle import transducer_oracle as T
-    b = max(range(len(enc_lens)), key=lambda i: enc_lens[i])
-    sample = enc[starts[b]:starts[b] + 1500].cpu()
-    torch.set_num_threads(os.cpu_count() or 1)
-    t0 = time.perf_counter(); grid = T.greedy_search_one(sd, sample, 1500, 64); dt_cpu = time.perf_counter() - t0
-    print(f"   CPU oracle ({os.cpu_count()} threads): 1500 frames, {int((grid != 0).sum())} symbols in {dt_cpu:.2f} s "
-          f"= {1500 * 0.08 / dt_cpu / 3600:.4f} audio-h/s")
