@@ -262,3 +262,30 @@ def test_forward_chunk_many_streams_equals_single_stream_calls():
             assert float((o1[0] - out[b]).abs().max()) < 2e-2, (step, b)
             assert float((a1[:, 0] - att[:, b]).abs().max()) < 2e-2 and float((c1[:, 0] - cnn[:, b]).abs().max()) < 2e-2
     assert torch.isfinite(out).all()
+
+
+def test_cf_encode_streams_rejects_inconsistent_plans():
+    """The multi-stream mode is armed per call and checked against the plan: wrong stream count, wrong chunks per stream,
+    missing caches and a right context are refused with a message; a refused call disarms the mode."""
+    from chunkformer_b200 import lib as cflib
+    from chunkformer_b200.plan import Plan
+    _, enc = _model(SMALL, 5)
+    L = cflib.load()
+    c, l, B, ph = 8, 40, 2, 5
+    T = ph * 8 * c + 8 * (c - 1) + 15
+    x = torch.zeros((B * T, 80), device=DEV)
+    Lr, H, d = SMALL.layers, SMALL.heads, SMALL.d_model
+    att = torch.zeros((Lr, B, H, l, 2 * d // H), device=DEV)
+    cnn = torch.zeros((Lr, B, d, 7), device=DEV)
+    plan = Plan(c, l, 0, [T] * B, [-(ph * c)] * B)
+    for n_streams, n_ph, a, cc, what in ((3, ph, att, cnn, "one utterance per stream"), (B, ph - 1, att, cnn, "placeholder_chunks"),
+                                         (B, ph, None, None, "both caches")):
+        cflib.check(L.cf_encode_streams(enc._h, n_streams, n_ph), enc._h, "cf_encode_streams")
+        with pytest.raises(RuntimeError, match=what):
+            enc.encode_plan(plan, x, a, cc, 0)
+    out, _ = enc.encode_plan(plan, x)                       # disarmed: an ordinary masked-batch call works
+    assert out.shape[0] == plan.rows
+    plan_r = Plan(c, l, 8, [T] * B, [-(ph * c)] * B)
+    cflib.check(L.cf_encode_streams(enc._h, B, plan_r.n_chunks[0] - 1), enc._h, "cf_encode_streams")
+    with pytest.raises(RuntimeError, match="right context"):
+        enc.encode_plan(plan_r, x, att, cnn, 0)
