@@ -1199,7 +1199,7 @@ static RnntWs rnnt_carve(const cf_rnnt_config& c, int64_t rows, int B, void* bas
   w.E = cv.take<float>(size_t(rows) * c.join_dim);
   w.seg_start = cv.take<long long>(B); w.seg_len = cv.take<int>(B);
   w.s.t = cv.take<int>(B); w.s.step = cv.take<int>(B); w.s.token = cv.take<int>(B); w.s.cur = cv.take<int>(B);
-  w.s.count = cv.take<int>(B); w.s.active = cv.take<int>(B); w.s.act_cur = cv.take<int>(B); w.s.act_tok = cv.take<int>(B);
+  w.s.count = cv.take<int>(B); w.s.active = cv.take<int>(B); w.s.act_cur = cv.take<int>(B); w.s.act_tok = cv.take<int>(B); w.s.need_g = cv.take<int>(B);
   w.s.n_active = cv.take<int>(1); w.s.remaining = cv.take<int>(1); w.s.overflow = cv.take<int>(1);
   w.s.h = cv.take<float>(w.state_floats); w.s.c = cv.take<float>(w.state_floats);
   w.s.g = cv.take<float>(size_t(B) * c.join_dim);
@@ -1239,7 +1239,7 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   rnnt_init_kernel<<<64, 256, 0, st>>>(w.s, w.seg_len, out_counts, n_utt, c.blank, w.state_floats);
   ++cf::g_kernel_launches;
   CF_RCUDA(h, cudaGetLastError());
-  RnntJointParams jp{w.E, h->woT, h->bo, w.seg_start, w.seg_len, c.join_dim, c.vocab, w.n_vtiles, 0};
+  RnntJointParams jp{w.E, h->woT, h->bo, w.seg_start, w.seg_len, c.join_dim, c.vocab, w.n_vtiles, 0, h->wc, h->bc, c.hidden, c.layers};
   { const char* e = getenv("CF_RNNT_DEBUG"); jp.debug = e ? atoi(e) : 0; }
   RnntDecideParams dp{w.seg_len, reinterpret_cast<long long*>(out_tokens), out_frames, out_counts, n_utt, w.n_vtiles, n_steps,
                       capacity, c.blank};
@@ -1248,22 +1248,38 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   {
     static bool attr_set = false;
     if (!attr_set) {
-      CF_RCUDA(h, cudaFuncSetAttribute(rnnt_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rnnt_joint_smem_bytes(1024))));
+      CF_RCUDA(h, cudaFuncSetAttribute(rnnt_joint_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rnnt_joint_smem_bytes(1024))));
+      CF_RCUDA(h, cudaFuncSetAttribute(rnnt_joint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rnnt_joint_smem_bytes(1024))));
       attr_set = true;
     }
   }
+  static const int fused_env = [] { const char* e = getenv("CF_RNNT_FUSED"); return e ? atoi(e) : 1; }();
+  const bool fused_proj = fused_env != 0 && (w.n_vtiles == 2 || w.n_vtiles == 4 || w.n_vtiles == 8);
+  cudaError_t launch_err = cudaSuccess;
   auto iteration = [&]() {
     for (int l = 0; l < c.layers; ++l) {
       RnntLstmParams lp{h->w_ih[l], h->w_hh[l], h->b_ih[l], h->b_hh[l], l == 0 ? h->embed : nullptr, l, l == 0 ? c.embed : c.hidden,
                         c.hidden, n_utt, c.layers};
       rnnt_lstm_kernel<<<dim3(unsigned((c.hidden + 3) / 4), tiles), 128, 0, st>>>(lp, w.s);
     }
-    rnnt_predproj_kernel<<<dim3(unsigned((c.join_dim + 3) / 4), tiles), 128, 0, st>>>(h->wc, h->bc, c.join_dim, c.hidden, n_utt,
-                                                                                      c.layers, w.s);
     dim3 jg(unsigned(w.n_vtiles), unsigned(n_utt));
-    rnnt_joint_kernel<<<jg, RNNT_JTHREADS, jsmem, st>>>(jp, w.s, n_utt);
+    if (fused_proj) {
+      // one cluster per utterance: its vocabulary-tile CTAs compute and share the projection themselves
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = jg; cfg.blockDim = dim3(RNNT_JTHREADS); cfg.dynamicSmemBytes = jsmem; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = unsigned(w.n_vtiles); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      launch_err = cudaLaunchKernelEx(&cfg, rnnt_joint_kernel<true>, jp, w.s, n_utt);
+      cf::g_kernel_launches += c.layers + 2;
+    } else {
+      rnnt_predproj_kernel<<<dim3(unsigned((c.join_dim + 3) / 4), tiles), 128, 0, st>>>(h->wc, h->bc, c.join_dim, c.hidden, n_utt,
+                                                                                        c.layers, w.s);
+      rnnt_joint_kernel<false><<<jg, RNNT_JTHREADS, jsmem, st>>>(jp, w.s, n_utt);
+      cf::g_kernel_launches += c.layers + 3;
+    }
     rnnt_decide_kernel<<<1, 256, 0, st>>>(dp, w.s);
-    cf::g_kernel_launches += c.layers + 3;
   };
   // the host only learns how far the search is by reading `remaining`; a burst of iterations is enqueued between reads
   // (iterations after the last utterance finished are empty launches)
@@ -1277,6 +1293,7 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
     if (iters > bound) return rfail(h, CF_ERR_STATE, "cf_rnnt_greedy: search did not terminate (internal error)");
     for (int i = 0; i < burst; ++i) iteration();
     iters += burst;
+    CF_RCUDA(h, launch_err);
     CF_RCUDA(h, cudaGetLastError());
     CF_RCUDA(h, cudaMemcpyAsync(&state[0], w.s.remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
     CF_RCUDA(h, cudaMemcpyAsync(&state[1], w.s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -29,6 +29,7 @@ struct RnntState {                 // device arrays, one entry per utterance unl
   int* active;                     // [B] utterances that need a predictor step this iteration (compact, -1 = empty slot)
   int* act_cur;                    // [B] committed state half of active[i]   } read in ONE round trip by the predictor
   int* act_tok;                    // [B] predictor input token of active[i]  } kernels (no n_active -> active -> cur chain)
+  int* need_g;                     // [B] 1 when the utterance emitted a symbol this iteration (its predictor vector is stale)
   int* n_active;                   // [1]
   int* remaining;                  // [1] utterances not finished
   int* overflow;                   // [1] set when an utterance ran out of output capacity
@@ -244,6 +245,8 @@ struct RnntJointParams {
   const long long* seg_start; const int* seg_len;   // device [B]
   int J, V, n_vtiles;
   int debug;                 // timing experiments: 1 = no tanh / E loads, 2 = no K loop, 4 = no reductions
+  // fused projection (cluster launch): g_b = Wc . h_top'(b) + bc computed by the cluster of the utterance's joint CTAs
+  const float* Wc; const float* bc; int H, layers;
 };
 
 constexpr int RNNT_VPT = 4;       // vocabulary entries per thread: every activation read from shared memory feeds 16 FMAs
@@ -254,30 +257,83 @@ constexpr int RNNT_JTHREADS = 32 * RNNT_JK;
 static_assert(RNNT_JV == 32 * RNNT_VPT, "a warp covers the CTA's vocabulary tile");
 
 inline size_t rnnt_joint_smem_bytes(int J) {
-  return size_t(RNNT_JR) * J * 4 + size_t(RNNT_JK) * RNNT_JR * RNNT_JV * 4;
+  return size_t(RNNT_JR) * J * 4 + size_t(RNNT_JK) * RNNT_JR * RNNT_JV * 4 + size_t(J) * 4;
 }
 
 // Phase timings of the first version (thread = one vocabulary entry x one of 4 K-slices, 4-byte weight loads): 20 us =
 // 5 launch / prologue / reductions + 3.7 activation tile (encoder rows, tanh) + 11.4 K loop; the K loop was bound by the
 // shared-memory pipe (one 16-byte broadcast read per 4 FMAs), not by the weight loads (16-byte loads alone: 18.6 us).
+//
+// FUSED (launched as one thread-block cluster per utterance = its vocabulary-tile CTAs, 2 / 4 / 8 of them): the projection
+// g_b = Wc . h_top'(b) + bc of an utterance that just emitted is computed by the cluster itself, J / n_vtiles rows per CTA, and
+// handed to every CTA of the cluster through distributed shared memory (one cluster barrier) instead of a separate launch
+// (a dependent launch costs about 4.5 us on this path whatever it computes).
+template <bool FUSED>
 __global__ void __launch_bounds__(RNNT_JTHREADS) rnnt_joint_kernel(RnntJointParams p, RnntState s, int B) {
   extern __shared__ __align__(16) float jsm[];
   float* a = jsm;                                          // [JR][J]
   float* s_acc = a + size_t(RNNT_JR) * p.J;                // [JK][JR][JV]
+  float* g_s = s_acc + size_t(RNNT_JK) * RNNT_JR * RNNT_JV;   // [J]
   const int b = blockIdx.y;
   const int t0 = s.t[b];
   const int nf = b < B ? max(0, min(RNNT_FB, p.seg_len[b] - t0)) : 0;
-  if (nf == 0) return;
+  if (nf == 0) return;                                      // the same for every CTA of the utterance's cluster
+  const int lane = threadIdx.x & 31, kq = threadIdx.x >> 5;
+  if (FUSED && s.need_g[b]) {
+    cluster_sync_all();                                     // every CTA of the cluster is running before its shared memory is written
+    const int nv = gridDim.x, rank = blockIdx.x;            // cluster = the grid's x extent
+    const int rows_per = (p.J + nv - 1) / nv;
+    const size_t half = size_t(p.layers) * B * p.H;
+    const float* hin = s.h + (s.cur[b] ^ 1) * half + (size_t(p.layers - 1) * B + b) * p.H;
+    const int r_end = min(p.J, (rank + 1) * rows_per);
+    // four rows per warp at a time, all their weight vectors requested before the first FMA
+    for (int r0 = rank * rows_per + kq; r0 < r_end; r0 += 4 * RNNT_JK) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k0 = 0; k0 < p.H; k0 += 512) {
+        float4 w[4][4], x[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int k = k0 + m * 128 + lane * 4;
+          x[m] = k < p.H ? *reinterpret_cast<const float4*>(hin + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i * RNNT_JK;
+            w[i][m] = (k < p.H && r < r_end) ? __ldg(reinterpret_cast<const float4*>(p.Wc + size_t(r) * p.H + k))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            acc[i] += w[i][m].x * x[m].x + w[i][m].y * x[m].y + w[i][m].z * x[m].z + w[i][m].w * x[m].w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i * RNNT_JK;
+        const float val = warp_sum(acc[i]) + (r < r_end ? __ldg(p.bc + r) : 0.f);
+        if (r < r_end) {
+          if (lane < nv) {                                   // lane i hands the value to CTA i of the cluster
+            const uint32_t remote = mapa_rank(smem_u32(g_s + r), uint32_t(lane));
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(val) : "memory");
+          }
+          if (lane == 0) s.g[size_t(b) * p.J + r] = val;     // kept for the iterations in which the utterance does not emit
+        }
+      }
+    }
+    cluster_sync_all();
+  } else {
+    for (int k = threadIdx.x; k < p.J; k += RNNT_JTHREADS) g_s[k] = s.g[size_t(b) * p.J + k];
+    __syncthreads();
+  }
   {
     const float* e = p.E + (p.seg_start[b] + t0) * (long long)p.J;
-    const float* g = s.g + size_t(b) * p.J;
     for (int i = threadIdx.x; i < RNNT_JR * p.J; i += RNNT_JTHREADS) {
       const int f = i / p.J, k = i - f * p.J;
-      a[i] = f < nf ? ((p.debug & 1) ? 0.5f : tanhf(e[(long long)f * p.J + k] + g[k])) : 0.f;
+      a[i] = f < nf ? ((p.debug & 1) ? 0.5f : tanhf(e[(long long)f * p.J + k] + g_s[k])) : 0.f;
     }
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, kq = threadIdx.x >> 5;
   const int v0 = blockIdx.x * RNNT_JV + lane;             // this thread's entries: v0 + 32 i
   float acc[RNNT_JR][RNNT_VPT];
 #pragma unroll
@@ -404,6 +460,7 @@ __global__ void __launch_bounds__(256) rnnt_decide_kernel(RnntDecideParams p, Rn
         }
       }
       s.t[b] = t; s.step[b] = step;
+      s.need_g[b] = emitted ? 1 : 0;
       if (t < len) {
         atomicAdd(&s_rem, 1);
         if (emitted) {
@@ -428,6 +485,7 @@ __global__ void rnnt_init_kernel(RnntState s, const int* seg_len, int* out_count
     int n = 0;
     for (int b = 0; b < B; ++b) {
       s.t[b] = 0; s.step[b] = 1; s.token[b] = blank; s.cur[b] = 0; s.count[b] = 0; out_counts[b] = 0;
+      s.need_g[b] = seg_len[b] > 0 ? 1 : 0;
       if (seg_len[b] > 0) { s.active[n] = b; s.act_cur[n] = 0; s.act_tok[n] = blank; ++n; }
     }
     for (int i = n; i < B; ++i) s.active[i] = -1;
