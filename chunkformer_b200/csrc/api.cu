@@ -1190,6 +1190,7 @@ extern "C" int cf_rnnt_finalize_weights(cf_rnnt* h) {
 
 struct RnntWs {
   RnntState s; float* E; long long* seg_start; int* seg_len; size_t bytes; size_t state_floats; int n_vtiles;
+  int *list_b, *list_cur, *list_tok, *cnt2, *rem2;     // [2][B] x 3, [2], [2]: double-buffered by iteration parity (fused control)
 };
 static RnntWs rnnt_carve(const cf_rnnt_config& c, int64_t rows, int B, void* base) {
   Carver cv(base);
@@ -1205,6 +1206,8 @@ static RnntWs rnnt_carve(const cf_rnnt_config& c, int64_t rows, int B, void* bas
   w.s.g = cv.take<float>(size_t(B) * c.join_dim);
   w.s.part_val = cv.take<float>(size_t(B) * RNNT_FB * w.n_vtiles);
   w.s.part_idx = cv.take<int>(size_t(B) * RNNT_FB * w.n_vtiles);
+  w.list_b = cv.take<int>(size_t(2) * B); w.list_cur = cv.take<int>(size_t(2) * B); w.list_tok = cv.take<int>(size_t(2) * B);
+  w.cnt2 = cv.take<int>(2); w.rem2 = cv.take<int>(2);
   w.bytes = cv.off + 256;
   return w;
 }
@@ -1236,10 +1239,15 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
     rnnt_linear_f32_kernel<<<grid, 256, 0, st>>>(enc_f32, h->enc_w, h->enc_b, w.E, rows, c.join_dim, c.enc_dim);
     ++cf::g_kernel_launches;
   }
-  rnnt_init_kernel<<<64, 256, 0, st>>>(w.s, w.seg_len, out_counts, n_utt, c.blank, w.state_floats);
+  rnnt_init_kernel<<<64, 256, 0, st>>>(w.s, w.seg_len, out_counts, n_utt, c.blank, w.state_floats, w.list_b, w.list_cur, w.list_tok,
+                                       w.cnt2, w.rem2);
   ++cf::g_kernel_launches;
   CF_RCUDA(h, cudaGetLastError());
-  RnntJointParams jp{w.E, h->woT, h->bo, w.seg_start, w.seg_len, c.join_dim, c.vocab, w.n_vtiles, 0, h->wc, h->bc, c.hidden, c.layers};
+  RnntJointParams jp{};
+  jp.E = w.E; jp.WoT = h->woT; jp.bo = h->bo; jp.seg_start = w.seg_start; jp.seg_len = w.seg_len; jp.J = c.join_dim; jp.V = c.vocab;
+  jp.n_vtiles = w.n_vtiles; jp.Wc = h->wc; jp.bc = h->bc; jp.H = c.hidden; jp.layers = c.layers;
+  jp.out_tokens = reinterpret_cast<long long*>(out_tokens); jp.out_frames = out_frames; jp.out_counts = out_counts;
+  jp.n_steps = n_steps; jp.cap = capacity; jp.blank = c.blank;
   { const char* e = getenv("CF_RNNT_DEBUG"); jp.debug = e ? atoi(e) : 0; }
   RnntDecideParams dp{w.seg_len, reinterpret_cast<long long*>(out_tokens), out_frames, out_counts, n_utt, w.n_vtiles, n_steps,
                       capacity, c.blank};
@@ -1256,10 +1264,13 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   static const int fused_env = [] { const char* e = getenv("CF_RNNT_FUSED"); return e ? atoi(e) : 1; }();
   const bool fused_proj = fused_env != 0 && (w.n_vtiles == 2 || w.n_vtiles == 4 || w.n_vtiles == 8);
   cudaError_t launch_err = cudaSuccess;
-  auto iteration = [&]() {
+  auto iteration = [&](int64_t it) {
+    const int par = int(it & 1);
     for (int l = 0; l < c.layers; ++l) {
       RnntLstmParams lp{h->w_ih[l], h->w_hh[l], h->b_ih[l], h->b_hh[l], l == 0 ? h->embed : nullptr, l, l == 0 ? c.embed : c.hidden,
-                        c.hidden, n_utt, c.layers};
+                        c.hidden, n_utt, c.layers,
+                        fused_proj ? w.list_b + (par ^ 1) * n_utt : w.s.active, fused_proj ? w.list_cur + (par ^ 1) * n_utt : w.s.act_cur,
+                        fused_proj ? w.list_tok + (par ^ 1) * n_utt : w.s.act_tok, fused_proj ? w.cnt2 + (par ^ 1) : nullptr};
       rnnt_lstm_kernel<<<dim3(unsigned((c.hidden + 3) / 4), tiles), 128, 0, st>>>(lp, w.s);
     }
     dim3 jg(unsigned(w.n_vtiles), unsigned(n_utt));
@@ -1271,8 +1282,13 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = unsigned(w.n_vtiles); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      launch_err = cudaLaunchKernelEx(&cfg, rnnt_joint_kernel<true>, jp, w.s, n_utt);
-      cf::g_kernel_launches += c.layers + 2;
+      RnntJointParams jq = jp;
+      jq.list_b = w.list_b + par * n_utt; jq.list_cur = w.list_cur + par * n_utt; jq.list_tok = w.list_tok + par * n_utt;
+      jq.cnt = w.cnt2 + par; jq.rem = w.rem2 + par; jq.cnt_next = w.cnt2 + (par ^ 1); jq.rem_next = w.rem2 + (par ^ 1);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, rnnt_joint_kernel<true>, jq, w.s, n_utt);
+      if (e != cudaSuccess) launch_err = e;
+      cf::g_kernel_launches += c.layers + 1;
+      return;                                   // the greedy control ran inside the clusters
     } else {
       rnnt_predproj_kernel<<<dim3(unsigned((c.join_dim + 3) / 4), tiles), 128, 0, st>>>(h->wc, h->bc, c.join_dim, c.hidden, n_utt,
                                                                                         c.layers, w.s);
@@ -1291,11 +1307,11 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   const int burst = 64;
   while (state[0] > 0) {
     if (iters > bound) return rfail(h, CF_ERR_STATE, "cf_rnnt_greedy: search did not terminate (internal error)");
-    for (int i = 0; i < burst; ++i) iteration();
+    for (int i = 0; i < burst; ++i) iteration(iters + i);
     iters += burst;
     CF_RCUDA(h, launch_err);
     CF_RCUDA(h, cudaGetLastError());
-    CF_RCUDA(h, cudaMemcpyAsync(&state[0], w.s.remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CF_RCUDA(h, cudaMemcpyAsync(&state[0], fused_proj ? w.rem2 + ((iters - 1) & 1) : w.s.remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
     CF_RCUDA(h, cudaMemcpyAsync(&state[1], w.s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     CF_RCUDA(h, cudaStreamSynchronize(st));
   }

@@ -91,6 +91,9 @@ struct RnntLstmParams {
   const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;   // [4H, In], [4H, H], [4H], [4H]
   const float* embed;       // layer 0: [V, In]; else null
   int layer, In, H, B, layers;
+  // compact list of the utterances that need a predictor step: (utterance, committed state half, input token); entries beyond
+  // *cnt are stale (cnt == null: the list ends at the first -1)
+  const int* act; const int* act_cur; const int* act_tok; const int* cnt;
 };
 
 CF_DEVINL float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -107,13 +110,17 @@ __global__ void __launch_bounds__(128) rnnt_lstm_kernel(RnntLstmParams p, RnntSt
   // tiles of RNNT_BT utterances run side by side (blockIdx.y): the step is a chain of L2 round trips, not throughput
   for (int b0 = blockIdx.y * RNNT_BT; b0 < p.B; b0 += gridDim.y * RNNT_BT) {
     int bs[RNNT_BT], curs[RNNT_BT], toks[RNNT_BT];
+    const int n_list = p.cnt ? *p.cnt : p.B;              // read in the same round trip as the entries
 #pragma unroll
     for (int u = 0; u < RNNT_BT; ++u) {
       const bool in = b0 + u < p.B;
-      bs[u] = in ? s.active[b0 + u] : -1;
-      curs[u] = in ? s.act_cur[b0 + u] : 0;
-      toks[u] = in ? s.act_tok[b0 + u] : 0;
+      bs[u] = in ? p.act[b0 + u] : -1;
+      curs[u] = in ? p.act_cur[b0 + u] : 0;
+      toks[u] = in ? p.act_tok[b0 + u] : 0;
     }
+#pragma unroll
+    for (int u = 0; u < RNNT_BT; ++u)
+      if (b0 + u >= n_list) bs[u] = -1;
     if (bs[0] < 0) return;                      // the list is compact: an empty first slot ends the work
     float acc[RNNT_BT][4];
 #pragma unroll
@@ -247,6 +254,10 @@ struct RnntJointParams {
   int debug;                 // timing experiments: 1 = no tanh / E loads, 2 = no K loop, 4 = no reductions
   // fused projection (cluster launch): g_b = Wc . h_top'(b) + bc computed by the cluster of the utterance's joint CTAs
   const float* Wc; const float* bc; int H, layers;
+  // in-cluster greedy control (FUSED): the decide step of the utterance runs in CTA 0 of its cluster
+  int* list_b; int* list_cur; int* list_tok; int* cnt; int* rem;        // this iteration's output list (appended atomically)
+  int* cnt_next; int* rem_next;                                         // zeroed here for the next iteration
+  long long* out_tokens; int* out_frames; int* out_counts; int n_steps, cap, blank;
 };
 
 constexpr int RNNT_VPT = 4;       // vocabulary entries per thread: every activation read from shared memory feeds 16 FMAs
@@ -257,7 +268,7 @@ constexpr int RNNT_JTHREADS = 32 * RNNT_JK;
 static_assert(RNNT_JV == 32 * RNNT_VPT, "a warp covers the CTA's vocabulary tile");
 
 inline size_t rnnt_joint_smem_bytes(int J) {
-  return size_t(RNNT_JR) * J * 4 + size_t(RNNT_JK) * RNNT_JR * RNNT_JV * 4 + size_t(J) * 4;
+  return size_t(RNNT_JR) * J * 4 + size_t(RNNT_JK) * RNNT_JR * RNNT_JV * 4 + size_t(J) * 4 + 8 * RNNT_FB * 8;
 }
 
 // Phase timings of the first version (thread = one vocabulary entry x one of 4 K-slices, 4-byte weight loads): 20 us =
@@ -274,13 +285,16 @@ __global__ void __launch_bounds__(RNNT_JTHREADS) rnnt_joint_kernel(RnntJointPara
   float* a = jsm;                                          // [JR][J]
   float* s_acc = a + size_t(RNNT_JR) * p.J;                // [JK][JR][JV]
   float* g_s = s_acc + size_t(RNNT_JK) * RNNT_JR * RNNT_JV;   // [J]
+  float* pv_s = g_s + p.J;                                  // [8 ranks][FB] per-tile maxima   } filled through DSMEM in
+  int* pi_s = reinterpret_cast<int*>(pv_s + 8 * RNNT_FB);   // [8 ranks][FB] their indices     } CTA 0 of the cluster
   const int b = blockIdx.y;
+  if (FUSED && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { *p.cnt_next = 0; *p.rem_next = 0; }
   const int t0 = s.t[b];
   const int nf = b < B ? max(0, min(RNNT_FB, p.seg_len[b] - t0)) : 0;
+  if (FUSED) cluster_sync_all();                            // every CTA of the cluster runs before its shared memory is written
   if (nf == 0) return;                                      // the same for every CTA of the utterance's cluster
   const int lane = threadIdx.x & 31, kq = threadIdx.x >> 5;
   if (FUSED && s.need_g[b]) {
-    cluster_sync_all();                                     // every CTA of the cluster is running before its shared memory is written
     const int nv = gridDim.x, rank = blockIdx.x;            // cluster = the grid's x extent
     const int rows_per = (p.J + nv - 1) / nv;
     const size_t half = size_t(p.layers) * B * p.H;
@@ -393,10 +407,70 @@ __global__ void __launch_bounds__(RNNT_JTHREADS) rnnt_joint_kernel(RnntJointPara
       const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
       if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
     }
-    if (lane == 0 && r < nf) {
-      const size_t at = (size_t(b) * RNNT_FB + r) * p.n_vtiles + blockIdx.x;
-      s.part_val[at] = val;
-      s.part_idx[at] = idx;
+    if (!FUSED) {
+      if (lane == 0 && r < nf) {
+        const size_t at = (size_t(b) * RNNT_FB + r) * p.n_vtiles + blockIdx.x;
+        s.part_val[at] = val;
+        s.part_idx[at] = idx;
+      }
+    } else if (lane == 0) {                                  // frame r's maximum of this tile -> CTA 0 of the cluster
+      const uint32_t rv = mapa_rank(smem_u32(pv_s + blockIdx.x * RNNT_FB + r), 0u);
+      const uint32_t ri = mapa_rank(smem_u32(pi_s + blockIdx.x * RNNT_FB + r), 0u);
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(rv), "f"(val) : "memory");
+      asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ri), "r"(idx) : "memory");
+    }
+  }
+  if (!FUSED) return;
+  cluster_sync_all();                                        // CTA 0 was running all along (it took part in the K loop)
+  if (blockIdx.x != 0 || kq != 0) return;
+  // ---- greedy control of utterance b (same rules as rnnt_decide_kernel), one warp
+  {
+    const int nv = gridDim.x;
+    int t = t0;
+    const int len = p.seg_len[b];
+    const int f_l = lane >> 2, q_l = lane & 3;
+    float val = -INFINITY; int idx = 0x7fffffff;
+    for (int w = q_l; w < nv; w += 4) {
+      const float ov = pv_s[w * RNNT_FB + f_l]; const int oi = pi_s[w * RNNT_FB + f_l];
+      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+    const unsigned nb = __ballot_sync(0xffffffffu, q_l == 0 && idx != p.blank && t + f_l < len);
+    const int limit = min(RNNT_FB, len - t);
+    const int f_hit = nb ? (__ffs(nb) - 1) >> 2 : limit;
+    const int sym = __shfl_sync(0xffffffffu, idx, (f_hit < RNNT_FB ? f_hit : 0) * 4);
+    if (lane == 0) {
+      int step = s.step[b];
+      bool emitted = false;
+      if (f_hit > 0) step = 1;
+      t += f_hit;
+      if (f_hit < limit) {
+        const int n = s.count[b];
+        if (n >= p.cap) { *s.overflow = 1; t = len; }
+        else {
+          p.out_tokens[size_t(b) * p.cap + n] = sym;
+          p.out_frames[size_t(b) * p.cap + n] = t;
+          s.count[b] = n + 1;
+          s.token[b] = sym;
+          const int cur = s.cur[b] ^ 1;
+          s.cur[b] = cur;
+          if (++step > p.n_steps) { ++t; step = 1; }
+          emitted = true;
+          if (t < len) {
+            const int slot = atomicAdd(p.cnt, 1);
+            p.list_b[slot] = b; p.list_cur[slot] = cur; p.list_tok[slot] = sym;
+          }
+        }
+      }
+      s.t[b] = t; s.step[b] = step;
+      s.need_g[b] = emitted ? 1 : 0;
+      if (t < len) atomicAdd(p.rem, 1);
+      else p.out_counts[b] = s.count[b];
     }
   }
 }
@@ -478,7 +552,8 @@ __global__ void __launch_bounds__(256) rnnt_decide_kernel(RnntDecideParams p, Rn
 }
 
 // start of a search: zero state, blank token, every non-empty utterance queued for its first predictor step
-__global__ void rnnt_init_kernel(RnntState s, const int* seg_len, int* out_counts, int B, int blank, size_t state_floats) {
+__global__ void rnnt_init_kernel(RnntState s, const int* seg_len, int* out_counts, int B, int blank, size_t state_floats,
+                                 int* list_b, int* list_cur, int* list_tok, int* cnt2, int* rem2) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   for (size_t k = i; k < state_floats; k += size_t(gridDim.x) * blockDim.x) { s.h[k] = 0.f; s.c[k] = 0.f; }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -489,6 +564,9 @@ __global__ void rnnt_init_kernel(RnntState s, const int* seg_len, int* out_count
       if (seg_len[b] > 0) { s.active[n] = b; s.act_cur[n] = 0; s.act_tok[n] = blank; ++n; }
     }
     for (int i = n; i < B; ++i) s.active[i] = -1;
+    // in-cluster control: iteration 0 reads the list of parity 1 and appends to parity 0
+    for (int i = 0; i < n; ++i) { list_b[B + i] = s.active[i]; list_cur[B + i] = 0; list_tok[B + i] = blank; }
+    cnt2[1] = n; rem2[1] = n; cnt2[0] = 0; rem2[0] = 0;
     *s.n_active = n; *s.remaining = n; *s.overflow = 0;
   }
 }
