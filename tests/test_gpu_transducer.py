@@ -84,10 +84,12 @@ def test_unsupported_heads_are_rejected():
         TransducerGreedyB200({k: v for k, v in sd.items() if not k.startswith("predictor.rnn")}, device=DEV)
 
 
-def test_many_utterances_use_several_predictor_tiles():
-    """21 utterances = three tiles of 8 in the predictor kernels, several joint CTAs per utterance (V = 300 -> 3 vocabulary
-    tiles), lengths 0 .. 40; every hypothesis against the oracle."""
-    V, emb, hid, nl, po, E, J = 300, 64, 128, 2, 96, 80, 112
+@pytest.mark.parametrize("V", [300, 512, 256])
+def test_many_utterances_use_several_predictor_tiles(V):
+    """21 utterances = three tiles of 8 in the predictor kernels, several joint CTAs per utterance, lengths 0 .. 40; every
+    hypothesis against the oracle.  V = 300 -> 3 vocabulary tiles (five-launch path), 512 / 256 -> clusters of 4 / 2 CTAs
+    (projection + joint + greedy control in one cluster launch; the golden `mid` case covers clusters of 8)."""
+    emb, hid, nl, po, E, J = 64, 128, 2, 96, 80, 112
     sd = synth_transducer_state_dict(V, emb, hid, nl, po, E, J, blank_bias=4.5, seed=21)
     gen = torch.Generator().manual_seed(22)
     lens = [int(v) for v in torch.randint(0, 41, (21,), generator=gen)]
