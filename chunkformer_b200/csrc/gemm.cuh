@@ -31,7 +31,11 @@ struct GemmEpiParams {
   const int2* row_range = nullptr;  // EPI_F32: row valid iff range[row / rows_per_chunk].x <= row % rows_per_chunk < .y
   int rows_per_chunk = 1;
   int resid_tma = 0;             // EPI_F32: residual sub-tiles are TMA-loaded into the staging tiles (set by launch_gemm)
-  int debug = 0;                 // tools only (CF_GEMM_DEBUG): 1 = epilogue does nothing, 2 = no loads / MMAs (timing ablations)
+  int debug = 0;                 // tools only (CF_GEMM_DEBUG): 1 = epilogue does nothing, 2 = no loads / MMAs (timing ablations),
+                                 // 4 = bf16 epilogue computes but neither stages nor stores, 8 = bf16 epilogue stores straight from registers,
+                                 // 16 = bf16 epilogue stores every tile to the first 128 rows (no DRAM write traffic)
+  void* raw_out = nullptr; long long raw_ldo = 0;   // output as a plain pointer (debug 8)
+  int half_slot = 0;             // EPI_BF16, 1-CTA kernel: 32-column store boxes through two 8 KB half slots (set by launch_gemm)
   float* part_best = nullptr;    // EPI_ARGMAX: [M, 2 * n_tiles]
   float* part_second = nullptr;
   int* part_index = nullptr;
@@ -358,6 +362,45 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       if (issuer) { tma_store_2d(tma_c, stg, col0, row0); tma_store_commit(); }
     }
   } else {
+    if (EPI == EPI_BF16 && ep.half_slot) {
+      // Four sub-rounds of 32 columns (64 bytes per row, 64-byte swizzle) through two 8 KB half slots of the group's staging
+      // tile: the TMA store of one half drains while the other is filled.  With one 16 KB slot per group every round waited
+      // for the previous store to finish reading shared memory; the ablation (CF_GEMM_DEBUG=4 / 16) put that wait, not the
+      // SiLU math or the DRAM writes, at 0.06 of the kernel's 0.35 ms.
+#pragma unroll 1
+      for (int sr = 0; sr < 4; ++sr) {
+        const int tcol = sr * 32;
+        const int col0 = gcol0 + tcol;
+        if (col0 >= N) break;
+        uint8_t* stg = stg2 + (rc++ & 1) * (GEMM_STAGING_BYTES / 2);
+        uint32_t r[32];
+        tmem_ld32(taddr + tcol, r);
+        float b[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
+          b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+        }
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store before last has read this half
+        named_bar_sync(bar_id, 128);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float v0 = __uint_as_float(r[j]) + b[j], v1 = __uint_as_float(r[j + 1]) + b[j + 1];
+          if (ACT == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          if (ACT == ACT_SILU) { v0 = silu_fast(v0); v1 = silu_fast(v1); }
+          o[j >> 1] = pack_bf16(v0, v1);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(stg + trow * 64 + ((q ^ ((trow >> 1) & 3)) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        fence_proxy_async();
+        named_bar_sync(bar_id, 128);
+        if (issuer) { tma_store_2d(tma_c, stg, col0, row0); tma_store_commit(); }
+      }
+      return;
+    }
     // bf16 outputs: EPI_BF16 -> two 64-column sub-tiles per group; EPI_GLU -> one 64-column sub-tile (128 acc columns)
     constexpr int ROUNDS = (EPI == EPI_GLU) ? 1 : 2;
     constexpr int CH_PER_ROUND = (EPI == EPI_GLU) ? 4 : 2;
@@ -367,8 +410,11 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       if (acol0 >= N) break;
       constexpr uint32_t SLOT_MASK = gemm_staging_slots(EPI) / 2 - 1;
       uint8_t* stg = stg2 + (rc++ & SLOT_MASK) * GEMM_STAGING_BYTES;
-      if (issuer) { if (SLOT_MASK) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else tma_store_wait_read(); }
-      named_bar_sync(bar_id, 128);
+      const bool no_stage = (ep.debug & 12) != 0;
+      if (!no_stage) {
+        if (issuer) { if (SLOT_MASK) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else tma_store_wait_read(); }
+        named_bar_sync(bar_id, 128);
+      }
 #pragma unroll
       for (int cc = 0; cc < CH_PER_ROUND; ++cc) {
         const int tcol = (EPI == EPI_GLU) ? cc * 32 : rd * 64 + cc * 32;   // column inside the group's 128
@@ -406,16 +452,31 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
             if (ACT == ACT_SILU) { v0 = silu_fast(v0); v1 = silu_fast(v1); }
             o[j >> 1] = pack_bf16(v0, v1);
           }
+          if (ep.debug & 8) {
+            if (row0 + trow < M && col0 < N) {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(ep.raw_out) + (long long)(row0 + trow) * ep.raw_ldo + col0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            stage_store16(stg, trow, 4 * cc + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+              for (int q = 0; q < 2; ++q)       // 256-bit stores: one full 32-byte sector per lane and instruction
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * q), "r"(o[8 * q]), "r"(o[8 * q + 1]),
+                             "r"(o[8 * q + 2]), "r"(o[8 * q + 3]), "r"(o[8 * q + 4]), "r"(o[8 * q + 5]), "r"(o[8 * q + 6]), "r"(o[8 * q + 7])
+                             : "memory");
+            }
+          } else if (ep.debug & 4) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) asm volatile("" ::"r"(o[q]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              stage_store16(stg, trow, 4 * cc + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+          }
         }
       }
+      if (no_stage) continue;
       fence_proxy_async();
       named_bar_sync(bar_id, 128);
-      if (issuer) {
+      if (issuer && !(ep.debug & 32)) {
         const int ocol = (EPI == EPI_GLU) ? (gcol0 >> 1) : acol0;
-        tma_store_2d(tma_c, stg, ocol, row0);
+        tma_store_2d(tma_c, stg, ocol, (ep.debug & 16) ? 0 : row0);   // debug 16: every tile lands on the first 128 rows (L2 only)
         tma_store_commit();
       }
     }

@@ -38,7 +38,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_tensor_map_encoder(std::string* err
 // 2-D row-major tensor [rows, cols] with row pitch `ld` elements; box = [box_rows, box_cols]; 128B swizzle
 // (box_cols * elem_bytes must be 128).
 inline bool make_tma_2d(CUtensorMap* map, const void* ptr, bool is_f32, uint64_t rows, uint64_t cols, uint64_t ld,
-                        uint32_t box_rows, uint32_t box_cols, std::string* err, bool swizzle128 = true) {
+                        uint32_t box_rows, uint32_t box_cols, std::string* err, bool swizzle128 = true, bool swizzle64 = false) {
   auto enc = get_tensor_map_encoder(err);
   if (!enc) return false;
   const size_t esz = is_f32 ? 4 : 2;
@@ -48,7 +48,8 @@ inline bool make_tma_2d(CUtensorMap* map, const void* ptr, bool is_f32, uint64_t
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r));
@@ -101,11 +102,19 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
       if (err) *err = "gemm: output pointer missing or leading dimension not 16-byte aligned";
       return false;
     }
-    if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
+    // measured: FFN w_1 0.335 -> 0.330 ms, QKV 0.325 -> 0.325 ms (the exposed cost of the epilogue is the TMA store itself,
+    // not the wait for the staging slot; profiles/README.md), so the simpler single-slot path stays the default
+    static const int half_env = [] { const char* e = getenv("CF_GEMM_HALFSLOT"); return e ? atoi(e) : 0; }();
+    ep.half_slot = (EPI == EPI_BF16 && !use2 && half_env) ? 1 : 0;
+    if (ep.half_slot) {
+      // 32-column (64-byte) store boxes: two half slots per staging tile, the store of one drains while the other is filled
+      if (!make_tma_2d(&tc, g.out, false, g.M, ocols, g.ldo, GEMM_BM, 32, err, false, true)) return false;
+    } else if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
   }
   tr = tc;
   ep.resid_tma = 0;
   { const char* dbg = getenv("CF_GEMM_DEBUG"); ep.debug = dbg ? atoi(dbg) : 0; }
+  ep.raw_out = g.out; ep.raw_ldo = g.ldo;
   // residual through TMA when every epilogue group of every tile has four full rounds and the pitch is TMA-legal
   if (EPI == EPI_F32 && g.ep.resid != nullptr && g.N % GEMM_BN == 0 && (g.ep.ld_resid * 4) % 16 == 0 &&
       (reinterpret_cast<uintptr_t>(g.ep.resid) & 15) == 0) {
