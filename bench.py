@@ -125,27 +125,37 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def cpu_oracle_baseline(threads, steps=2, warmup=1):
-    """The oracle (a port of the reference's algorithm, oracle/chunkformer_oracle.py) on the host cores, fp32, on a bounded
-    sample of the same workload: the {1 s, 30 s, 60 s} utterances of the masked batch (91 s of audio) as one masked batch."""
-    from oracle import chunkformer_oracle as O
+SAMPLE_SECONDS = [1, 30, 60]      # bounded CPU sample: the {1 s, 30 s, 60 s} utterances of the masked batch as one masked batch
+
+
+def cpu_reference_baseline(threads, steps=2, warmup=1):
+    """The reference's own CPU implementation of the path on the host cores, fp32, on a bounded sample of the workload.
+
+    kind "reference": the UNMODIFIED reference installed under baseline/_ref (baseline/reference_arm.py drives its
+    forward_parallel_chunk + ctc.log_softmax().argmax()); kind "port": the oracle restatement, only if baseline/_ref is absent."""
+    from baseline import reference_arm as RA
     torch.set_num_threads(threads)
     sd = synth_state_dict(CTC_LARGE, 0)
-    secs = [1, 30, 60]
-    lens = [int(round(s * 100)) - 2 for s in secs]
+    lens = [int(round(s * 100)) - 2 for s in SAMPLE_SECONDS]
     xs = [synth_fbank(t, seed=1 + k) for k, t in enumerate(lens)]
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        out, enc_lens, n_chunks, _, _, _ = O.forward_parallel_chunk(sd, CTC_LARGE.heads, xs, lens, C, L, R)
-        O.ctc_greedy(sd, out)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
     audio = sum(audio_seconds(t) for t in lens)
+    if RA.available():
+        model = RA.build_reference(CTC_LARGE, sd)
+        times = RA.time_reference_cpu(model, xs, lens, C, L, R, steps, warmup)
+        kind, what = "reference", "unmodified reference (baseline/_ref) forward_parallel_chunk + ctc.log_softmax().argmax(), fp32 torch CPU"
+    else:
+        from oracle import chunkformer_oracle as O
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out, enc_lens, n_chunks, _, _, _ = O.forward_parallel_chunk(sd, CTC_LARGE.heads, xs, lens, C, L, R)
+            O.ctc_greedy(sd, out)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        kind, what = "port", "oracle port of the reference path (baseline/_ref not installed), fp32 torch CPU"
     best = min(times)
-    return {"value": audio / best / 3600.0, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"masked batch of the {secs} s utterances ({audio:.0f} s audio), fp32 torch CPU oracle, best of {steps}",
+    return {"value": audio / best / 3600.0, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"masked batch of the {SAMPLE_SECONDS} s utterances ({audio:.0f} s audio), {what}, best of {steps}",
             "seconds_per_sample": best}, times, audio
 
 
@@ -153,18 +163,139 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    base, times, audio = cpu_oracle_baseline(threads, steps=args.steps, warmup=max(args.warmup, 1))
+    base, times, audio = cpu_reference_baseline(threads, steps=args.steps, warmup=max(args.warmup, 1))
     total = sum(times)
     value = audio * len(times) / total / 3600.0
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": max(args.warmup, 1),
             "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "bounded sample of the CTC-large 64/128/128 masked batch: the 1 s, 30 s and 60 s utterances "
-                                   "(91 s audio) per step, CPU oracle port of the reference path", "chunk": C, "left": L, "right": R},
+                                   "(91 s audio) per step, " + ("the unmodified reference on CPU" if base["kind"] == "reference"
+                                                                 else "CPU oracle port of the reference path"),
+                       "chunk": C, "left": L, "right": R},
             "cpu_baseline": dict(base, value=value),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+PARITY_MAX_ABS, PARITY_REL_RMS, PARITY_MARGIN_TOL = 0.05, 0.01, 0.08     # the bar of tests/test_gpu_encoder.py
+
+
+def strong_scaling_legs(enc, geo, dev, rank, world, barrier, steps=2):
+    """BASELINE.json north_star splits under the driver's own command, device-resident inputs, CUDA events,
+    max over ranks:
+      * batch: ONE global batch of world x 14 400 s (world copies of the 19-utterance list) split over the ranks by
+        chunk count (LPT, shard.partition_by_chunks); every rank encodes + greedy-decodes its share, token ids gathered once;
+      * recording: ONE 16 h recording (BASELINE configs[2]) split into contiguous chunk ranges with recomputed context halos
+        (shard.split_recording), "exact" halos (51 + 51 chunks) and the reference's own look-ahead ("reference": 34 right)."""
+    import torch.distributed as dist
+    from chunkformer_b200.plan import Plan
+    from chunkformer_b200.shard import chunks_of, gather_variable, halo_chunks, partition_by_chunks, split_recording
+
+    def timed(fn):
+        fn()                                             # warm-up (workspace growth, position tables)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def loads(mine):
+        t = torch.tensor([float(mine)], device=dev)
+        if world > 1:
+            all_t = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(all_t, t)
+            vals = [float(v.item()) for v in all_t]
+        else:
+            vals = [float(mine)]
+        return {"max": max(vals), "min": min(vals)}
+
+    res = {}
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    # ---- (a) one global masked batch, LPT by chunk count
+    lens_all = masked_batch_lengths() * world
+    mine = partition_by_chunks(lens_all, C, world)[rank]
+    my_lens = [lens_all[i] for i in mine]
+    feats = torch.randn((sum(my_lens), geo.feat_dim), device=dev, generator=gen)
+
+    def step_batch():
+        plan = Plan(C, L, R, my_lens, None, geo.kernel)
+        _, o16 = enc.encode_plan(plan, feats, out_dtype=torch.bfloat16)
+        tok = enc.ctc_greedy(o16)
+        if world > 1:
+            gather_variable(tok)
+    ms = timed(step_batch)
+    audio = sum(audio_seconds(t) for t in lens_all)
+    res["batch_lpt"] = {"what": "one global batch of %d utterances (%d s) split over %d GPU(s) by chunk count (LPT)" % (len(lens_all), round(audio), world),
+                        "ms_per_step": ms, "value": audio / (ms / 1e3) / 3600.0, "unit": UNIT,
+                        "rank_load_chunks": loads(sum(chunks_of(t, C) for t in my_lens))}
+    del feats
+    # ---- (b) one 16 h recording split by chunk range with halos
+    T = 16 * 3600 * 100 - 2
+    for mode in ("exact", "reference"):
+        sh = split_recording(T, C, L, R, geo.layers, world, mode)[rank]
+        n_in = sh.in_end - sh.in_start
+        x = torch.randn((n_in, geo.feat_dim), device=dev, generator=gen)
+
+        def step_rec():
+            plan = Plan(C, L, R, [n_in], None, geo.kernel)
+            _, o16 = enc.encode_plan(plan, x, out_dtype=torch.bfloat16)
+            tok = enc.ctc_greedy(o16)[sh.keep_lo:sh.keep_hi]
+            if world > 1:
+                gather_variable(tok)
+        ms = timed(step_rec)
+        res["recording_16h_" + mode] = {"what": "one 16 h recording (%d chunks) as %d contiguous chunk range(s), halos %s chunks (%s)"
+                                                % (chunks_of(T, C), world, halo_chunks(C, L, R, geo.layers, mode), mode),
+                                        "ms_per_step": ms, "value": audio_seconds(T) / (ms / 1e3) / 3600.0, "unit": UNIT,
+                                        "rank_load_chunks": loads(chunks_of(n_in, C))}
+        del x
+    enc._ws = None
+    torch.cuda.empty_cache()
+    return res
+
+
+def reference_gpu_legs(dev, xs_host, lens, audio):
+    """BASELINE.md section 3, second reference point: the UNMODIFIED reference's own eager path on this GPU (the existing
+    library path: cuBLAS / cuDNN / ATen kernels), the same masked batch, fp32 and bf16 autocast.  If the whole batch does not fit
+    (the reference materialises unfolded K/V windows and a (n, d, 259, 39) fp32 conv output: about 110 GiB), it is run as the
+    four masked sub-batches of tests/golden/make_golden_bench.py and the times are added."""
+    from baseline import reference_arm as RA
+    if not RA.available():
+        return {"unavailable": "baseline/_ref not installed"}
+    res = {}
+    try:
+        model = RA.build_reference(CTC_LARGE, synth_state_dict(CTC_LARGE, 0)).to(dev)
+        xs_dev = [x.to(dev) for x in xs_host]
+        groups_full = [list(range(len(lens)))]
+        groups_split = [[5], [11], [4, 10], [0, 1, 2, 3, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17, 18]]
+        for name, dt in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+            for groups in (groups_full, groups_split):
+                try:
+                    ms, peak = 0.0, 0
+                    for g in groups:
+                        m, pk, _ = RA.time_reference_gpu(model, [xs_dev[i] for i in g], [lens[i] for i in g], C, L, R, dev, dt)
+                        ms, peak = ms + m, max(peak, pk)
+                    res[name] = {"ms_per_step": ms, "value": audio / (ms / 1e3) / 3600.0, "unit": UNIT, "peak_memory_bytes": peak,
+                                 "sub_batches": len(groups)}
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    res[name] = {"unavailable": "out of memory"}
+        res["what"] = ("unmodified reference (baseline/_ref) on this GPU, torch eager: forward_parallel_chunk + "
+                       "ctc.log_softmax().argmax() on the same 14 400 s masked batch, 1 warm-up + 2 timed steps, CUDA events")
+        del model, xs_dev
+        torch.cuda.empty_cache()
+    except Exception as e:                                  # a reported baseline, never a reason to lose the bench line
+        res["unavailable"] = f"{type(e).__name__}: {e}"
+    return res
 
 
 def main():
@@ -175,6 +306,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale every utterance duration (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs (LPT batch split, 16 h recording)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the unmodified reference's eager path on the GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -209,7 +342,7 @@ def main():
         plan = Plan(C, L, R, lens, None, geo.kernel)                       # host packer is part of the path
         out, out16 = enc.encode_plan(plan, feats_dev, out_dtype=torch.bfloat16)
         tokens = enc.ctc_greedy(out16)
-        return plan, tokens
+        return plan, tokens, out16
 
     def step_e2e():
         out, enc_lens, n_chunks, _, _, _ = enc.forward_parallel_chunk(xs_host, lens_t, C, L, R,
@@ -227,16 +360,17 @@ def main():
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        plan, tokens = step_resident()
+        plan, tokens, out16 = step_resident()
     barrier()
     t_region0 = time.perf_counter()
     launches0 = Llib.cf_launch_count()
     if rank == 0:
-        Llib.cf_gemm_timing_begin(cflib.EPI_BF16, cflib.ACT_SILU)    # CUDA events around every FFN w_1 launch of the timed steps
+        # CUDA events around every FFN w_1 / w_2 launch of the timed steps
+        cflib.check(Llib.cf_kernel_timing_begin(enc._h, (1 << cflib.FAMILY_FFN_W1) | (1 << cflib.FAMILY_FFN_W2)), enc._h, "timing")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        plan, tokens = step_resident()
+        plan, tokens, out16 = step_resident()
         if world > 1:
             gathered = [torch.empty_like(tokens) for _ in range(world)]
             dist.all_gather(gathered, tokens)
@@ -247,9 +381,12 @@ def main():
     dom_ms, dom_n = 0.0, 0
     if rank == 0:
         import ctypes
-        tot_ms, n_l = ctypes.c_double(0.0), ctypes.c_int(0)
-        cflib.check(Llib.cf_gemm_timing_end(ctypes.byref(tot_ms), ctypes.byref(n_l)), None, "cf_gemm_timing_end")
-        dom_ms, dom_n = float(tot_ms.value), int(n_l.value)
+        fam = {}
+        for name, f in (("w1", cflib.FAMILY_FFN_W1), ("w2", cflib.FAMILY_FFN_W2)):
+            tot_ms, n_l = ctypes.c_double(0.0), ctypes.c_int(0)
+            cflib.check(Llib.cf_kernel_timing_end(enc._h, f, ctypes.byref(tot_ms), ctypes.byref(n_l)), enc._h, "cf_kernel_timing_end")
+            fam[name] = (float(tot_ms.value), int(n_l.value))
+        dom_ms, dom_n = fam["w1"]
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -271,6 +408,29 @@ def main():
     e2e_value = world * audio * args.steps / float(e2e_s.item()) / 3600.0
     h2d = int(sum(x.numel() * 4 for x in xs_host))
     d2h = int(tok_host.numel() * tok_host.element_size())
+
+    # ---- what was timed is what the reference computes: the last timed step of rank 0 (whose inputs are the golden's: weights
+    # seed 0, fbank seeds 1 + k) against the golden the UNMODIFIED reference produced for this batch (tests/golden/bench_batch.npz)
+    parity = None
+    if rank == 0 and args.scale == 1.0:
+        gpath = os.path.join(ROOT, "tests", "golden", "bench_batch.npz")
+        if os.path.exists(gpath):
+            import numpy as np
+            from chunkformer_b200.synth import check_bench_batch
+            rep = check_bench_batch(np.load(gpath), out16.view(plan.n, C, geo.d_model), tokens.view(plan.n, C), plan.n_chunks,
+                                    [int(v) for v in plan.enc_lens], PARITY_MARGIN_TOL)
+            rep["bar"] = {"max_abs": PARITY_MAX_ABS, "rel_rms": PARITY_REL_RMS, "token_mismatches_above_tol": 0}
+            rep["ok"] = bool(rep["max_abs"] <= PARITY_MAX_ABS and rep["rel_rms"] <= PARITY_REL_RMS and
+                             rep["token_mismatches_above_tol"] == 0)
+            rep["against"] = "tests/golden/bench_batch.npz (unmodified reference, fp32 CPU); bf16 output of the last timed step"
+            parity = rep
+            if not rep["ok"]:
+                raise SystemExit("bench.py: the timed output does not match the reference golden: " + json.dumps(rep))
+
+    # ---- the north-star splits, measured in the same run (strong scaling: fixed total work split over the ranks)
+    strong = None
+    if not args.no_strong:
+        strong = strong_scaling_legs(enc, geo, dev, rank, world, barrier)
 
     # ---- roofline of the dominant kernel family: the FFN up-projection GEMM (tcgen05, bf16 -> fp32 accumulate, SiLU epilogue;
     # 34 launches per step).  `achieved` = algorithmic flops per launch / average launch duration measured with CUDA events on
@@ -302,7 +462,7 @@ def main():
         def ffn1():
             rc = Llib.cf_op_gemm(c_void_p(A.data_ptr()), d, c_void_p(Wt.data_ptr()), d, rows, F, d, cflib.EPI_BF16,
                                  cflib.ACT_SILU, c_void_p(bias.data_ptr()), None, 0, 1.0, None, 1,
-                                 c_void_p(Hbuf.data_ptr()), F, None, None, None, st)
+                                 c_void_p(Hbuf.data_ptr()), F, None, None, None, -1, st)
             cflib.check(rc, None, "cf_op_gemm")
         for _ in range(3):
             ffn1()
@@ -323,13 +483,24 @@ def main():
                     "flops_per_launch": flops,
                     "alone": {"ms_best_of_10": best_alone, "achieved": flops / (best_alone * 1e-3) / 1e12, "peak": burst,
                               "frac": flops / (best_alone * 1e-3) / 1e12 / burst, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"},
+                    "also": {"kernel": "gemm2_tcgen05_kernel<EPI_F32> (FFN w_2 + 0.5 * residual, 2-CTA, M=%d N=%d K=%d)" % (rows, d, F),
+                             "ms_per_launch": fam["w2"][0] / max(fam["w2"][1], 1), "launches_timed": fam["w2"][1],
+                             "achieved": flops / (fam["w2"][0] / max(fam["w2"][1], 1) * 1e-3) / 1e12 if fam["w2"][1] else None,
+                             "frac": flops / (fam["w2"][0] / max(fam["w2"][1], 1) * 1e-3) / 1e12 / sustained if fam["w2"][1] else None},
                     "path_tflops": path_flops_per_chunk(geo, C, L, R) * plan.n * args.steps * world / (ms_total * 1e-3) / 1e12,
                     "path_frac_of_sustained": None}
         roofline["path_frac_of_sustained"] = roofline["path_tflops"] / (sustained * world)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base, _, _ = cpu_oracle_baseline(os.cpu_count() or 1)
+        cpu_base, _, _ = cpu_reference_baseline(os.cpu_count() or 1)
+
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_ref_gpu:
+        del out16, tokens
+        enc._ws = None
+        torch.cuda.empty_cache()
+        ref_gpu = reference_gpu_legs(dev, xs_host, lens, audio)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -345,7 +516,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1000.0 * float(e2e_s.item()) / args.steps,
                         "api": "ChunkFormerEncoderB200.forward_parallel_chunk(host fbank) + ctc_greedy + tokens.cpu()"},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base}
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base,
+                "parity_checked": bool(parity and parity["ok"]), "parity": parity, "strong": strong, "reference_gpu": ref_gpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

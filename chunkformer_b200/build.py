@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libchunkformer_b200.so")
+LIB_ABLATION = os.path.join(CSRC, "libchunkformer_b200_ablation.so")   # tools only: -DCF_ABLATION (timing / phase switches)
 SOURCES = ["api.cu", "plan.cpp"]
 HEADERS = ["common.cuh", "transducer.cuh", "gemm.cuh", "gemm_host.cuh", "norm_conv.cuh", "frontend.cuh", "attention_simt.cuh",
            "attention_tc.cuh", "fbank.cuh", "misc_kernels.cuh", "plan.h", os.path.join("..", "..", "include", "chunkformer_b200.h")]
@@ -28,12 +29,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, ablation: bool = False) -> str:
+    """Product library by default.  ablation=True builds the tools flavour next to it: the same sources with -DCF_ABLATION,
+    which compiles in the phase-ablation switches (CF_GEMM_DEBUG, CF_RNNT_DEBUG environment variables) that the product
+    library does not contain; select it with CHUNKFORMER_B200_LIB=<path> when running tools/."""
+    out = LIB_ABLATION if ablation else LIB
+    if not ablation and not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC,-fvisibility=hidden", "--shared", "-cudart", "static",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out] + (["-DCF_ABLATION"] if ablation else []) + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -41,8 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ablation="--ablation" in sys.argv))

@@ -24,9 +24,6 @@ using namespace cf;
 typedef __nv_bfloat16 bf16;
 
 static thread_local std::string g_last_error = "";
-static int g_attention_version = 1;   // tcgen05 attention kernel generation (1: 8 softmax warps, P through smem; 2: 16 warps, P in TMEM)
-static int g_fuse_layernorm = 0;   // LayerNorm fused behind the residual GEMMs: measured slower on B200 (85.3 vs 92.4 ms/step),
-                                   // kept selectable for experiments (cf_set_fused_layernorm)
 
 namespace cf { std::atomic<long long> g_kernel_launches{0}; }
 
@@ -42,6 +39,12 @@ struct LayerW {
 struct PosTable {  // projected relative-position tables, one per layer, cached per (c, l, r)
   int c, l, r, R, Rpad;
   bf16* dev = nullptr;  // [L][Rpad][d]
+  unsigned long long last_use = 0;
+};
+constexpr size_t kMaxPosTables = 8;   // least-recently-used tables beyond this are freed (full attention makes one per length)
+
+struct PinnedStage {   // pinned host staging for the per-call plan tables (async upload without a host synchronisation)
+  void* host = nullptr; size_t bytes = 0; cudaEvent_t done = nullptr; bool in_flight = false;
 };
 
 struct cf_handle {
@@ -64,6 +67,10 @@ struct cf_handle {
   float* ctc_b = nullptr;
   float* zeros = nullptr;  // max(N) zero floats (bias-free GEMMs)
   std::vector<PosTable> pos_tables;
+  unsigned long long use_clock = 0;
+  PinnedStage stage[4];
+  int stage_next = 0;
+  cf::KernelTiming timing;
   struct FbankTables { int sr = 0, bins = 0, flen = 0, fshift = 0; float* window = nullptr; float* mel_w = nullptr; int2* mel_rng = nullptr; int* mel_cnt = nullptr; };
   std::vector<FbankTables> fbank_tables;
   // feature-arrival events of the next cf_encode call (cf_encode_feature_events): rows < ev_rows[i] are present once ev[i] fires
@@ -86,30 +93,30 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
   } while (0)
 
 extern "C" long long cf_launch_count(void) { return cf::g_kernel_launches.load(); }
-extern "C" void cf_set_fused_layernorm(int on) { g_fuse_layernorm = on; }
-extern "C" void cf_set_gemm_variant(int v) { cf::gemm_variant_override() = v; }
-extern "C" void cf_gemm_timing_begin(int epi, int act) {
-  cf::GemmTiming& t = cf::gemm_timing();
-  t.select = (epi < 0) ? -1 : epi * 16 + act;
-  t.used = 0;
-}
-extern "C" int cf_gemm_timing_end(double* total_ms, int* launches) {
-  cf::GemmTiming& t = cf::gemm_timing();
-  t.select = -1;
-  double tot = 0.0;
-  for (size_t i = 0; i < t.used; ++i) {
-    if (cudaEventSynchronize(t.pool[i].second) != cudaSuccess) return CF_ERR_CUDA;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, t.pool[i].first, t.pool[i].second) != cudaSuccess) return CF_ERR_CUDA;
-    tot += ms;
-  }
-  if (total_ms) *total_ms = tot;
-  if (launches) *launches = int(t.used);
-  t.used = 0;
+extern "C" int cf_kernel_timing_begin(cf_handle* h, unsigned family_mask) {
+  if (!h) return fail(nullptr, CF_ERR_INVALID, "cf_kernel_timing_begin: null handle");
+  h->timing.mask = family_mask;
+  h->timing.used = 0;
   return CF_OK;
 }
-extern "C" void cf_debug_attention_trace(long long* device_buffer) { cf::attention_trace_buffer() = device_buffer; }
-extern "C" void cf_set_attention_version(int v) { g_attention_version = (v == 2) ? 2 : 1; }
+extern "C" int cf_kernel_timing_end(cf_handle* h, int family, double* total_ms, int* launches) {
+  if (!h) return fail(nullptr, CF_ERR_INVALID, "cf_kernel_timing_end: null handle");
+  cf::KernelTiming& t = h->timing;
+  t.mask = 0;
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i < t.used; ++i) {
+    if (t.pool[i].family != family) continue;
+    if (cudaEventSynchronize(t.pool[i].b) != cudaSuccess) return fail(h, CF_ERR_CUDA, "cf_kernel_timing_end: event synchronize failed");
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.pool[i].a, t.pool[i].b) != cudaSuccess) return fail(h, CF_ERR_CUDA, "cf_kernel_timing_end: elapsed time failed");
+    tot += ms;
+    ++n;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return CF_OK;
+}
 extern "C" const char* cf_version(void) { return "chunkformer_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cf_last_error(const cf_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
@@ -152,6 +159,10 @@ extern "C" void cf_destroy(cf_handle* h) {
   for (auto& t : h->pos_tables)
     if (t.dev) cudaFree(t.dev);
   for (auto& t : h->fbank_tables) { cudaFree(t.window); cudaFree(t.mel_w); cudaFree(t.mel_rng); cudaFree(t.mel_cnt); }
+  for (auto& sgt : h->stage) {
+    if (sgt.done) { cudaEventSynchronize(sgt.done); cudaEventDestroy(sgt.done); }
+    if (sgt.host) cudaFreeHost(sgt.host);
+  }
   delete h;
 }
 
@@ -441,12 +452,7 @@ bool run_dwconv_tma(const DwConvParams& p, long long g_rows, int num_sms, cudaSt
   CUtensorMap tm;
   if (!make_tma_2d(&tm, p.g, false, uint64_t(g_rows), uint64_t(D), uint64_t(D), FG + 14, 256, err, /*swizzle128=*/false)) return false;
   const size_t smem = dwconv_tma_smem_bytes<D, FG, STAGES>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_ln_silu_tma_kernel<D, FG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute(dwconv): ") + cudaGetErrorString(e); return false; }
-    attr_set = true;
-  }
+  if (!ensure_smem_optin(dwconv_ln_silu_tma_kernel<D, FG, STAGES>, smem, err, "dwconv")) return false;
   constexpr int CTAS = (FG == 16 && STAGES == 2) ? 3 : 2;
   const int groups = p.n_chunks * (p.c / FG);
   const int grid = groups < CTAS * num_sms ? groups : CTAS * num_sms;
@@ -461,16 +467,11 @@ bool run_dwconv_tma(const DwConvParams& p, long long g_rows, int num_sms, cudaSt
 bool run_dwconv(int d, int kernel, const DwConvParams& p, cudaStream_t st, std::string* err, long long g_rows = 0, int num_sms = 148) {
   if (kernel != 15) { *err = "dwconv: kernel must be 15"; return false; }
   if (p.n_chunks == 0) return true;
-  static const int fg_env = [] { const char* e = getenv("CF_DW_FG"); return e ? atoi(e) : 32; }();
-  if (g_rows > 0 && p.c % 32 == 0 && fg_env != 16) {
+  // 32-frame groups, two-stage TMA ring, two CTAs per SM: the fastest of the variants measured in round 1 (16-frame groups
+  // with three CTAs: 0.129 ms; three stages: 0.140 ms; this one: 0.127 ms; profiles/README.md)
+  if (g_rows > 0 && p.c % 32 == 0) {
     if (d == 512) return run_dwconv_tma<512, 32, 2>(p, g_rows, num_sms, st, err);
     if (d == 256) return run_dwconv_tma<256, 32, 2>(p, g_rows, num_sms, st, err);
-  }
-  static const int st_env = [] { const char* e = getenv("CF_DW_STAGES"); return e ? atoi(e) : 2; }();
-  if (g_rows > 0 && p.c % 16 == 0 && fg_env == 16) {
-    if (d == 512 && st_env == 3) return run_dwconv_tma<512, 16, 3>(p, g_rows, num_sms, st, err);
-    if (d == 512) return run_dwconv_tma<512, 16, 2>(p, g_rows, num_sms, st, err);
-    if (d == 256) return run_dwconv_tma<256, 16, 2>(p, g_rows, num_sms, st, err);
   }
   if (d == 512) return run_dwconv_d<512>(p, st, err);
   if (d == 256) return run_dwconv_d<256>(p, st, err);
@@ -507,19 +508,7 @@ bool run_frontend_conv(int impl, int d, const Fe1Params& f1, int num_sms, cudaSt
       e = cudaFuncSetAttribute(frontend_conv0_dw1_cm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
       if (e == cudaSuccess) frontend_conv0_dw1_cm_kernel<256><<<grid, fecm_threads<256>(), smem, st>>>(f1, units);
     } else { *err = "frontend: d must be 256 or 512"; return false; }
-  } else {
-    const int tiles = f1.n_chunks * bpc;
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    if (d == 512) {
-      const size_t smem = frontend_tc_smem_bytes<512>();
-      e = cudaFuncSetAttribute(frontend_conv0_dw1_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      if (e == cudaSuccess) frontend_conv0_dw1_tc_kernel<512><<<grid, FETC_THREADS, smem, st>>>(f1, tiles);
-    } else if (d == 256) {
-      const size_t smem = frontend_tc_smem_bytes<256>();
-      e = cudaFuncSetAttribute(frontend_conv0_dw1_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      if (e == cudaSuccess) frontend_conv0_dw1_tc_kernel<256><<<grid, FETC_THREADS, smem, st>>>(f1, tiles);
-    } else { *err = "frontend: d must be 256 or 512"; return false; }
-  }
+  } else { *err = "frontend: unknown implementation"; return false; }
   ++cf::g_kernel_launches;
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("frontend conv launch: ") + cudaGetErrorString(e); return false; }
@@ -542,10 +531,9 @@ bool attention_tc_supported(int c, int l, int r, int dk) {
 bool run_attention(int impl, const AttnParams& p, cudaStream_t st, std::string* err) {
   if (p.n_chunks == 0) return true;
   const int dk = p.d / p.heads;
-  if (impl == 1 || impl == 2) {
+  if (impl == 1) {
     if (!attention_tc_supported(p.c, p.l, p.r, dk)) { *err = "attention: tcgen05 kernels need d_k 64 or 128 and a chunk size in {8,16,32,64} or >= 128"; return false; }
-    if (attention_tc_fast_supported(p.c, p.l, p.r, dk))
-      return launch_attention_tc(p, (impl == 2 && p.c == 64 && p.l % 64 == 0 && p.r % 64 == 0) ? 2 : 1, st, err);
+    if (attention_tc_fast_supported(p.c, p.l, p.r, dk)) return launch_attention_tc(p, st, err);
     return launch_attention_ring(p, st, err);
   }
   if (impl == 3) {      // tests / tools: force the ring kernel
@@ -623,8 +611,20 @@ EncodeWs carve_encode(const cf_handle* h, const cf_plan* p, void* base) {
 // input independent, computed once per (c, l, r) and cached on the handle.
 int get_pos_table(cf_handle* h, int c, int l, int r, cudaStream_t st, const PosTable** out) {
   for (auto& t : h->pos_tables)
-    if (t.c == c && t.l == l && t.r == r) { *out = &t; return CF_OK; }
+    if (t.c == c && t.l == l && t.r == r) { t.last_use = ++h->use_clock; *out = &t; return CF_OK; }
   const int d = h->cfg.d_model, L = h->cfg.layers;
+  // Bounded cache: full attention (chunk = T') makes one table per utterance length, so a service fed varied lengths would
+  // otherwise grow device memory without limit.  Evict the least recently used table (work that reads it was enqueued on a
+  // stream; wait for it before freeing).
+  if (h->pos_tables.size() >= kMaxPosTables) {
+    size_t victim = 0;
+    for (size_t i = 1; i < h->pos_tables.size(); ++i)
+      if (h->pos_tables[i].last_use < h->pos_tables[victim].last_use) victim = i;
+    CF_CUDA(h, cudaStreamSynchronize(st));
+    CF_CUDA(h, cudaDeviceSynchronize());
+    cudaFree(h->pos_tables[victim].dev);
+    h->pos_tables.erase(h->pos_tables.begin() + victim);
+  }
   PosTable t;
   t.c = c; t.l = l; t.r = r; t.R = 2 * c + l + r - 1;
   t.Rpad = ((t.R + 127) / 128) * 128;
@@ -641,19 +641,27 @@ int get_pos_table(cf_handle* h, int c, int l, int r, cudaStream_t st, const PosT
     }
   }
   bf16* pe_dev = nullptr;
-  CF_CUDA(h, cudaMalloc(&pe_dev, pe.size() * 2));
-  CF_CUDA(h, cudaMalloc(&t.dev, size_t(L) * t.Rpad * d * 2));
-  CF_CUDA(h, cudaMemcpyAsync(pe_dev, pe.data(), pe.size() * 2, cudaMemcpyHostToDevice, st));
-  CF_CUDA(h, cudaMemsetAsync(t.dev, 0, size_t(L) * t.Rpad * d * 2, st));
+  auto bail = [&](int code, const std::string& msg) {
+    if (pe_dev) cudaFree(pe_dev);
+    if (t.dev) cudaFree(t.dev);
+    return fail(h, code, msg);
+  };
+  cudaError_t e = cudaMalloc(&pe_dev, pe.size() * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&t.dev, size_t(L) * t.Rpad * d * 2);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pe_dev, pe.data(), pe.size() * 2, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t.dev, 0, size_t(L) * t.Rpad * d * 2, st);
+  if (e != cudaSuccess) return bail(CF_ERR_CUDA, std::string("position table: ") + cudaGetErrorString(e));
   for (int i = 0; i < L; ++i) {
     GemmLaunch g{};
     g.A = pe_dev; g.lda = d; g.B = h->layers[i].pos_w; g.ldb = d; g.M = t.R; g.N = d; g.K = d; g.epi = EPI_BF16;
     g.act = ACT_NONE; g.ep.bias = h->zeros; g.out = t.dev + size_t(i) * t.Rpad * d; g.ldo = d;
     std::string err;
-    if (!launch_gemm(g, h->num_sms, st, &err)) { cudaFree(pe_dev); return fail(h, CF_ERR_CUDA, err); }
+    if (!launch_gemm(g, h->num_sms, st, &err)) return bail(CF_ERR_CUDA, err);
   }
-  CF_CUDA(h, cudaStreamSynchronize(st));
+  e = cudaStreamSynchronize(st);               // `pe` (pageable host memory) and pe_dev go out of scope
+  if (e != cudaSuccess) return bail(CF_ERR_CUDA, std::string("position table: ") + cudaGetErrorString(e));
   cudaFree(pe_dev);
+  t.last_use = ++h->use_clock;
   h->pos_tables.push_back(t);
   *out = &h->pos_tables.back();
   return CF_OK;
@@ -692,8 +700,13 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   if (!h->finalized) return fail(h, CF_ERR_STATE, "cf_encode: call cf_finalize_weights first");
   if (out_dtype != CF_F32 && out_dtype != CF_BF16) return fail(h, CF_ERR_INVALID, "cf_encode: bad out_dtype");
   if (p->kernel != h->cfg.kernel) return fail(h, CF_ERR_INVALID, "cf_encode: plan conv kernel differs from the model's");
+  // per-call state armed by cf_encode_streams / cf_encode_feature_events is consumed here, so that every exit path clears it
   const int ns = h->streams_n, ph = h->streams_ph;
   h->streams_n = 0; h->streams_ph = 0;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int64_t> ev_rows;
+  ev.swap(h->ev);
+  ev_rows.swap(h->ev_rows);
   if (ns > 0) {
     if (p->mode != 0 || p->B != ns || !att_cache || !cnn_cache)
       return fail(h, CF_ERR_INVALID, "cf_encode: multi-stream call needs a masked-batch plan with one utterance per stream and both caches");
@@ -715,6 +728,11 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   const long long Mr = (long long)n * c;
   if (Mr == 0) return CF_OK;
   if (att_cache && trunc < 0) return fail(h, CF_ERR_INVALID, "cf_encode: truncated_context_size must be >= 0");
+  if (!ev_rows.empty()) {
+    long long need_all = 0;
+    for (int g = 0; g < n; ++g) need_all = std::max<long long>(need_all, p->chunk_feat_row[g] + std::max(p->chunk_in_len[g], 0));
+    if (ev_rows.back() < need_all) return fail(h, CF_ERR_INVALID, "cf_encode: the feature events cover fewer rows than the plan reads");
+  }
   // kv[: trunc + l][-l:] (attention.py:466-467) and x[:, : trunc + lorder][:, -lorder:] (convolution.py:228-230) clamp at
   // the end of the buffer: a final segment shorter than the kept context hands over its last rows.
   if (trunc > Mr) trunc = int(Mr);
@@ -723,22 +741,44 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   int rc = get_pos_table(h, c, l, r, st, &pos);
   if (rc != CF_OK) return rc;
 
-  // ---- tables
+  // ---- tables: packed into one pinned staging block owned by the handle and uploaded asynchronously (no host
+  // synchronisation; a ring of four blocks, each guarded by an event recorded behind its copies)
   {
-    std::vector<ChunkSrc> cs(n);
-    std::vector<int2> ar(n + 16, make_int2(0, 0)), cr(n), orr(n);   // phantom chunks of the last attention tile stay empty
+    const size_t b_cs = size_t(n) * sizeof(ChunkSrc), b_ar = size_t(n + 16) * sizeof(int2), b_r = size_t(n) * sizeof(int2);
+    const size_t b_sl = p->mode == 1 ? size_t(p->B) * sizeof(int) : 0;
+    const size_t need = b_cs + b_ar + 2 * b_r + b_sl;
+    PinnedStage& sg = h->stage[h->stage_next];
+    h->stage_next = (h->stage_next + 1) % 4;
+    if (sg.in_flight) { CF_CUDA(h, cudaEventSynchronize(sg.done)); sg.in_flight = false; }
+    if (sg.bytes < need) {
+      if (sg.host) cudaFreeHost(sg.host);
+      sg.host = nullptr; sg.bytes = 0;
+      CF_CUDA(h, cudaHostAlloc(&sg.host, need + need / 2, cudaHostAllocDefault));
+      sg.bytes = need + need / 2;
+    }
+    if (!sg.done) CF_CUDA(h, cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
+    uint8_t* base = static_cast<uint8_t*>(sg.host);
+    ChunkSrc* cs = reinterpret_cast<ChunkSrc*>(base);
+    int2* ar = reinterpret_cast<int2*>(base + b_cs);
+    int2* cr = reinterpret_cast<int2*>(base + b_cs + b_ar);
+    int2* orr = reinterpret_cast<int2*>(base + b_cs + b_ar + b_r);
     for (int g = 0; g < n; ++g) {
       cs[g].feat_row = p->chunk_feat_row[g]; cs[g].in_len = p->chunk_in_len[g]; cs[g].pad_ = 0;
       const cf_chunk_entry& e = p->chunks[g];
       ar[g] = make_int2(e.att_lo, e.att_hi); cr[g] = make_int2(e.conv_lo, e.conv_hi); orr[g] = make_int2(e.out_lo, e.out_hi);
     }
-    CF_CUDA(h, cudaMemcpyAsync(w.chunk_src, cs.data(), n * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaMemcpyAsync(w.att_range, ar.data(), (n + 16) * sizeof(int2), cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaMemcpyAsync(w.conv_range, cr.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaMemcpyAsync(w.out_range, orr.data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
-    if (p->mode == 1)
-      CF_CUDA(h, cudaMemcpyAsync(w.seq_limit, p->seq_valid_rows.data(), p->B * sizeof(int), cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaStreamSynchronize(st));  // host vectors go out of scope
+    for (int g = n; g < n + 16; ++g) ar[g] = make_int2(0, 0);   // phantom chunks of the last attention tile stay empty
+    CF_CUDA(h, cudaMemcpyAsync(w.chunk_src, cs, b_cs, cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaMemcpyAsync(w.att_range, ar, b_ar, cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaMemcpyAsync(w.conv_range, cr, b_r, cudaMemcpyHostToDevice, st));
+    CF_CUDA(h, cudaMemcpyAsync(w.out_range, orr, b_r, cudaMemcpyHostToDevice, st));
+    if (p->mode == 1) {
+      int* sl = reinterpret_cast<int*>(base + b_cs + b_ar + 2 * b_r);
+      memcpy(sl, p->seq_valid_rows.data(), b_sl);
+      CF_CUDA(h, cudaMemcpyAsync(w.seq_limit, sl, b_sl, cudaMemcpyHostToDevice, st));
+    }
+    CF_CUDA(h, cudaEventRecord(sg.done, st));
+    sg.in_flight = true;
   }
   // zero the halo rows of the flat buffers once (cache rows are rewritten per layer when streaming)
   CF_CUDA(h, cudaMemsetAsync(w.qkv, 0, size_t(l) * 4 * d * sizeof(bf16), st));
@@ -748,9 +788,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
 
   struct EpiArgs { const float* bias = nullptr; void* out = nullptr; long long ldo = 0; int act = ACT_NONE;
                    const float* resid = nullptr; long long ld_resid = 0; float alpha = 1.0f;
-                   const int2* row_range = nullptr; int rows_per_chunk = 1;
-                   int ln_mode = 0; bf16* ln_y = nullptr; const float* ln1_w = nullptr; const float* ln1_b = nullptr;
-                   const float* ln2_w = nullptr; const float* ln2_b = nullptr; bool ln_limit = false; };
+                   const int2* row_range = nullptr; int rows_per_chunk = 1; int family = 0; };
   auto gemm = [&](const void* A, long long lda, const void* B, long long ldb, long long M, int N, int K, int epi,
                   const EpiArgs& e) -> bool {
     GemmLaunch g{};
@@ -758,14 +796,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.out = e.out; g.ldo = e.ldo;
     g.ep.bias = e.bias; g.ep.resid = e.resid; g.ep.ld_resid = e.ld_resid; g.ep.alpha = e.alpha;
     g.ep.row_range = e.row_range; g.ep.rows_per_chunk = e.rows_per_chunk;
-    if (e.ln_mode != 0) {
-      g.ep.ln_mode = e.ln_mode; g.ep.ln_x = static_cast<float*>(e.out); g.ep.ln_ldx = e.ldo; g.ep.ln_y = e.ln_y;
-      g.ep.ln1_w = e.ln1_w; g.ep.ln1_b = e.ln1_b; g.ep.ln2_w = e.ln2_w; g.ep.ln2_b = e.ln2_b;
-      g.ep.ln_row_limit = e.ln_limit ? w.seq_limit : nullptr; g.ep.ln_rows_per_seq = e.ln_limit ? p->rows_per_seq : 1;
-    }
+    g.timing = &h->timing; g.family = e.family;
     return launch_gemm(g, h->num_sms, st, &err);
   };
-  const bool fuse_ln = g_fuse_layernorm != 0;
 #define CF_TRY(expr) do { if (!(expr)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err); } while (0)
 
   // ---- front-end: slabs of chunks through conv0+dw1 -> pw1 -> dw2 -> pw2 -> out Linear
@@ -775,19 +808,19 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     size_t ev_next = 0;
     for (int g0 = 0; g0 < n; g0 += FE_SLAB_CHUNKS) {
       const int S = std::min(FE_SLAB_CHUNKS, n - g0);
-      if (!h->ev.empty()) {
+      if (!ev.empty()) {
         // features may still be arriving on another stream: wait only for the rows this slab reads
         long long need = 0;
         for (int g = g0; g < g0 + S; ++g) need = std::max<long long>(need, p->chunk_feat_row[g] + std::max(p->chunk_in_len[g], 0));
-        while (ev_next < h->ev.size() && (ev_next == 0 || h->ev_rows[ev_next - 1] < need)) {
-          CF_CUDA(h, cudaStreamWaitEvent(st, h->ev[ev_next], 0));
+        while (ev_next < ev.size() && (ev_next == 0 || ev_rows[ev_next - 1] < need)) {
+          CF_CUDA(h, cudaStreamWaitEvent(st, ev[ev_next], 0));
           ++ev_next;
         }
       }
       Fe1Params f1{};
       f1.feats = feats; f1.chunks = w.chunk_src + g0; f1.wpack = h->fe_wpack; f1.cmvn_mean = h->cmvn_mean; f1.cmvn_istd = h->cmvn_istd;
       f1.out = w.a1; f1.n_chunks = S; f1.feat_dim = h->cfg.feat_dim; f1.T2 = T2; f1.F2 = F2; f1.in_rows = p->in_rows;
-      if (!run_frontend_conv(h->cfg.feat_dim == 80 ? 2 : 1, d, f1, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err);
+      if (!run_frontend_conv(h->cfg.feat_dim == 80 ? 2 : 0, d, f1, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err);
       EpiArgs e1; e1.bias = h->fe_b3; e1.out = w.b1; e1.ldo = d; e1.act = ACT_RELU;
       CF_TRY(gemm(w.a1, d, h->fe_w3, d, (long long)S * T2 * F2, d, d, EPI_BF16, e1));
       Fe2Params f2{};
@@ -803,13 +836,11 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(gemm(w.a2, d, h->fe_w6, d, (long long)S * c * F3, d, d, EPI_BF16, e2));
       // (xW + b) * sqrt(d)  (subsampling.py:164, embedding.py:198)
       EpiArgs e3; e3.bias = h->fe_bout; e3.out = w.x + (size_t)g0 * c * d; e3.ldo = d; e3.alpha = sqrtf(float(d));
-      if (fuse_ln) { e3.ln_mode = 1; e3.ln_y = w.y + (size_t)g0 * c * d; e3.ln1_w = h->layers[0].ln_ffm_w; e3.ln1_b = h->layers[0].ln_ffm_b; }
       CF_TRY(gemm(w.b2, (long long)F3 * d, h->fe_wout, (long long)F3 * d, (long long)S * c, d, F3 * d, EPI_F32, e3));
     }
   }
 
-  for (size_t i = 0; i < h->ev.size(); ++i) CF_CUDA(h, cudaStreamWaitEvent(st, h->ev[i], 0));   // (no-op for events already waited on)
-  h->ev.clear(); h->ev_rows.clear();
+  for (size_t i = 0; i < ev.size(); ++i) CF_CUDA(h, cudaStreamWaitEvent(st, ev[i], 0));   // (no-op for events already waited on)
 
   // ---- layers (encoder_layer.py:155-248)
   auto ln = [&](int mode, const float* w1, const float* b1, const float* w2, const float* b2, float* xo, bf16* y,
@@ -820,17 +851,16 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     return run_layernorm(mode, d, q, st, &err);
   };
   const bool use_tc = kAttentionTcReady && attention_tc_supported(c, l, r, dk);
-  if (!fuse_ln) CF_TRY(ln(0, h->layers[0].ln_ffm_w, h->layers[0].ln_ffm_b, nullptr, nullptr, nullptr, w.y, false));
+  CF_TRY(ln(0, h->layers[0].ln_ffm_w, h->layers[0].ln_ffm_b, nullptr, nullptr, nullptr, w.y, false));
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = h->layers[i];
     // macaron FFN: x += 0.5 * W2 SiLU(W1 LN(x) + b1) + b2
-    { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
+    { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
       CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
-    { EpiArgs e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
-      if (fuse_ln) { e.ln_mode = 1; e.ln_y = w.y; e.ln1_w = lw.ln_mha_w; e.ln1_b = lw.ln_mha_b; }
+    { EpiArgs e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
       CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
     // self-attention
-    if (!fuse_ln) CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
+    CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
     if (att_cache && l > 0 && ns == 0) {
       const int tot = l * H * 2 * dk;
       att_cache_import_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<const float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d);
@@ -853,12 +883,11 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     { AttnParams a{};
       a.qkv = w.qkv; a.pos = pos->dev + size_t(i) * pos->Rpad * d; a.range = w.att_range; a.ctx = w.ctx;
       a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk)); a.prescaled = 1;
-      CF_TRY(run_attention(use_tc ? g_attention_version : 0, a, st, &err)); }
+      CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
     { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
-      if (fuse_ln) { e.ln_mode = 1; e.ln_y = w.y; e.ln1_w = lw.ln_conv_w; e.ln1_b = lw.ln_conv_b; e.ln_limit = p->mode == 1; }
       CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
     // convolution module
-    if (!fuse_ln) CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
+    CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
     if (cnn_cache && ns == 0) { cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo); ++cf::g_kernel_launches; }
     { EpiArgs e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
       CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mr, 2 * d, d, EPI_GLU, e)); }
@@ -875,20 +904,15 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, (long long)w.g_rows, h->num_sms)); }
     { EpiArgs e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       e.row_range = w.out_range; e.rows_per_chunk = c;
-      if (fuse_ln) { e.ln_mode = 1; e.ln_y = w.y; e.ln1_w = lw.ln_ff_w; e.ln1_b = lw.ln_ff_b; }
       CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
     // FFN
-    if (!fuse_ln) CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
-    { EpiArgs e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU;
+    CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
+    { EpiArgs e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
       CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mr, F, d, EPI_BF16, e)); }
-    { EpiArgs e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f;
-      if (fuse_ln && i + 1 < L) {
-        e.ln_mode = 2; e.ln_y = w.y; e.ln1_w = lw.ln_fin_w; e.ln1_b = lw.ln_fin_b;
-        e.ln2_w = h->layers[i + 1].ln_ffm_w; e.ln2_b = h->layers[i + 1].ln_ffm_b;
-      }
+    { EpiArgs e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
       CF_TRY(gemm(w.hbuf, F, lw.ff_w2, F, Mr, d, F, EPI_F32, e)); }
     if (i + 1 < L) {
-      if (!fuse_ln) CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));
+      CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));
     } else {
       // norm_final of the last layer + after_norm (encoder.py:670-671)
       LnParams q{};
@@ -981,18 +1005,20 @@ extern "C" int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int s
 // --------------------------------------------------------------------------------------------------------------------
 // CTC head
 // --------------------------------------------------------------------------------------------------------------------
-extern "C" size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows) {
+extern "C" size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows, int enc_dtype) {
   if (!h || rows <= 0) return 256;
   const size_t nt = 2 * size_t((h->cfg.vocab + 255) / 256);
-  return 3 * (size_t(rows) * nt * 4 + 256) + 256;
+  const size_t cast = enc_dtype == CF_F32 ? size_t(rows) * h->cfg.d_model * sizeof(bf16) + 256 : 0;
+  return 3 * (size_t(rows) * nt * 4 + 256) + cast + 256;
 }
 
-extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, int64_t* tokens_out, float* margin_out,
+extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc, int enc_dtype, int64_t rows, int64_t* tokens_out, float* margin_out,
                              float* logp_out, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h || !enc_bf16 || !tokens_out || !workspace) return fail(h, CF_ERR_INVALID, "cf_ctc_greedy: null argument");
+  if (!h || !enc || !tokens_out || !workspace) return fail(h, CF_ERR_INVALID, "cf_ctc_greedy: null argument");
+  if (enc_dtype != CF_F32 && enc_dtype != CF_BF16) return fail(h, CF_ERR_INVALID, "cf_ctc_greedy: bad enc_dtype");
   if (!h->finalized || h->cfg.vocab <= 0 || !h->ctc_w) return fail(h, CF_ERR_STATE, "cf_ctc_greedy: no CTC head loaded");
   if (rows <= 0) return CF_OK;
-  if (workspace_bytes < cf_ctc_workspace_bytes(h, rows)) return fail(h, CF_ERR_WORKSPACE, "cf_ctc_greedy: workspace too small");
+  if (workspace_bytes < cf_ctc_workspace_bytes(h, rows, enc_dtype)) return fail(h, CF_ERR_WORKSPACE, "cf_ctc_greedy: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CF_CUDA(h, cudaSetDevice(h->device));
   const int d = h->cfg.d_model, V = h->cfg.vocab;
@@ -1001,6 +1027,16 @@ extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, i
   float* best = cv.take<float>(size_t(rows) * nt);
   float* second = cv.take<float>(size_t(rows) * nt);
   int* index = cv.take<int>(size_t(rows) * nt);
+  const void* enc_bf16 = enc;
+  if (enc_dtype == CF_F32) {
+    bf16* tmp = cv.take<bf16>(size_t(rows) * d);
+    const long long n4 = (long long)rows * d / 4;
+    cast_f32_bf16_kernel<<<unsigned(std::min<long long>((n4 + 255) / 256, 16LL * h->num_sms)), 256, 0, st>>>(
+        static_cast<const float*>(enc), tmp, n4);
+    ++cf::g_kernel_launches;
+    CF_CUDA(h, cudaGetLastError());
+    enc_bf16 = tmp;
+  }
   std::string err;
   GemmLaunch g{};
   g.A = enc_bf16; g.lda = d; g.B = h->ctc_w; g.ldb = d; g.M = int(rows); g.N = V; g.K = d; g.epi = EPI_ARGMAX;
@@ -1248,21 +1284,21 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   jp.n_vtiles = w.n_vtiles; jp.Wc = h->wc; jp.bc = h->bc; jp.H = c.hidden; jp.layers = c.layers;
   jp.out_tokens = reinterpret_cast<long long*>(out_tokens); jp.out_frames = out_frames; jp.out_counts = out_counts;
   jp.n_steps = n_steps; jp.cap = capacity; jp.blank = c.blank;
+#ifdef CF_ABLATION
   { const char* e = getenv("CF_RNNT_DEBUG"); jp.debug = e ? atoi(e) : 0; }
+#endif
   RnntDecideParams dp{w.seg_len, reinterpret_cast<long long*>(out_tokens), out_frames, out_counts, n_utt, w.n_vtiles, n_steps,
                       capacity, c.blank};
   const unsigned tiles = unsigned(std::min((n_utt + RNNT_BT - 1) / RNNT_BT, 8));
   const size_t jsmem = rnnt_joint_smem_bytes(c.join_dim);
   {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CF_RCUDA(h, cudaFuncSetAttribute(rnnt_joint_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rnnt_joint_smem_bytes(1024))));
-      CF_RCUDA(h, cudaFuncSetAttribute(rnnt_joint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rnnt_joint_smem_bytes(1024))));
-      attr_set = true;
-    }
+    std::string aerr;
+    if (!ensure_smem_optin(rnnt_joint_kernel<false>, rnnt_joint_smem_bytes(1024), &aerr, "rnnt_joint") ||
+        !ensure_smem_optin(rnnt_joint_kernel<true>, rnnt_joint_smem_bytes(1024), &aerr, "rnnt_joint"))
+      return rfail(h, CF_ERR_CUDA, aerr);
   }
-  static const int fused_env = [] { const char* e = getenv("CF_RNNT_FUSED"); return e ? atoi(e) : 1; }();
-  const bool fused_proj = fused_env != 0 && (w.n_vtiles == 2 || w.n_vtiles == 4 || w.n_vtiles == 8);
+  // cluster-fused joint (projection + joint + greedy control in one launch) whenever the vocabulary makes 2 / 4 / 8 tiles
+  const bool fused_proj = (w.n_vtiles == 2 || w.n_vtiles == 4 || w.n_vtiles == 8);
   cudaError_t launch_err = cudaSuccess;
   auto iteration = [&](int64_t it) {
     const int par = int(it & 1);
@@ -1332,7 +1368,7 @@ static int current_sms() {
 extern "C" int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, int act,
                           const float* bias, const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range,
                           int rows_per_chunk, void* out, int64_t ldo, float* part_best, float* part_second,
-                          int32_t* part_index, void* stream) {
+                          int32_t* part_index, int variant, void* stream) {
   if (!A || !B || !bias) return fail(nullptr, CF_ERR_INVALID, "cf_op_gemm: null argument");
   GemmLaunch g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.epi = epi; g.act = act; g.out = out; g.ldo = ldo;
@@ -1340,6 +1376,7 @@ extern "C" int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb
   g.ep.row_range = reinterpret_cast<const int2*>(row_range);
   g.ep.rows_per_chunk = rows_per_chunk > 0 ? rows_per_chunk : 1;
   g.ep.part_best = part_best; g.ep.part_second = part_second; g.ep.part_index = part_index;
+  g.variant = variant;
   std::string err;
   if (!launch_gemm(g, current_sms(), static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
   return CF_OK;

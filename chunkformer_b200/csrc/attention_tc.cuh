@@ -49,8 +49,6 @@ CF_DEVINL uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-inline long long*& attention_trace_buffer() { static long long* b = nullptr; return b; }
-
 CF_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -108,8 +106,6 @@ struct AttnTcParams {
   int c_log2, tab_row0, n_last;              // chunk size (log2); first resident table row (c - 128); S_bd columns of the last block
   int items_per_cta_stride;                  // CTAs per head
   float scale_log2e;
-  int experiment;         // debug bit mask (CF_ATTN_EXPERIMENT): 1 skip ctx stores, 2 skip skew reads, 4 skip exp
-  long long* trace;       // optional timeline of CTA 0 (tools/attention_timeline.py): [role][block][event] SM clocks
 };
 
 // PRE: Q+u / Q+v already carry (1/sqrt(d_k)) * log2(e) (folded into the fused QKV projection at weight load).
@@ -407,364 +403,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       mbar_wait(pv_done, (blk - 1) & 1);
       tc_fence_after();
       write_out();
-      tc_fence_before();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Second-generation kernel: same tiling and MMA schedule, but
-//   * 16 softmax warps: four threads share a query row (32 keys of every 128-key block each), four resident warps per
-//     scheduler instead of two, so TMEM / shared-memory / MUFU latencies overlap across warps;
-//   * the probabilities never touch shared memory: P (bf16) is written to TMEM columns [448, 512) with tcgen05.st and
-//     O += P V runs with the A operand in TMEM (tcgen05.mma with [a_tmem]); the 32 KB P tile pays for the extra skew rows;
-//   * row maxima / sums are exchanged inside one TMEM lane quadrant (named barrier of 128 threads) through the padding
-//     bytes of the thread-private skew rows.
-// TMEM map: S_ac [0,128)  S_bd [128,384)  O [384,448)  P [448,512).
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int ATC2_SOFT_WARPS = 16;
-constexpr int ATC2_THREADS = 64 + 32 * ATC2_SOFT_WARPS;
-constexpr size_t ATC2_SMEM_BYTES = ATC_PTAB_BYTES + 2 * ATC_TILE_BYTES + 4 * ATC_TILE_BYTES +
-                                   size_t(32 * ATC2_SOFT_WARPS) * ATC_STAGE_PITCH + 256 + 1024;
-
-template <bool PRE>
-__global__ void __launch_bounds__(ATC2_THREADS, 1)
-attention_tc2_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_pos, AttnTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_ptab = smem;                        // smem row rr <-> table row rr - 64
-  uint8_t* s_qu = s_ptab + ATC_PTAB_BYTES;
-  uint8_t* s_qv = s_qu + ATC_TILE_BYTES;
-  uint8_t* s_k = s_qv + ATC_TILE_BYTES;          // [2]
-  uint8_t* s_v = s_k + 2 * ATC_TILE_BYTES;       // [2]
-  uint8_t* s_stage = s_v + 2 * ATC_TILE_BYTES;   // 512 thread-private rows: 128 B of fp16 skew data + 16 B of exchange slots
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 32 * ATC2_SOFT_WARPS * ATC_STAGE_PITCH);
-  // Every operand has its own full / empty pair so that each TMA load is issued as early as its buffer allows:
-  uint64_t* ptab_full = bars + 0;
-  uint64_t* qv_full = bars + 1;    // Q+v tile of an item (used by the S_bd MMAs)
-  uint64_t* qv_empty = bars + 2;
-  uint64_t* qu_full = bars + 3;    // Q+u tile of an item (used by the S_ac MMAs)
-  uint64_t* qu_empty = bars + 4;
-  uint64_t* k_full = bars + 5;     // [2]
-  uint64_t* k_empty = bars + 7;    // [2]
-  uint64_t* v_full = bars + 9;     // [2]
-  uint64_t* v_empty = bars + 11;   // [2]
-  uint64_t* bd_full = bars + 13;   // S_bd of a block is in TMEM
-  uint64_t* ac_full = bars + 14;   // S_ac of a block is in TMEM
-  uint64_t* bd_free = bars + 15;   // every softmax thread has staged its S_bd window
-  uint64_t* ac_free = bars + 16;   // every softmax thread has read its S_ac columns
-  uint64_t* p_full = bars + 17;
-  uint64_t* pv_done = bars + 18;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x % p.heads;
-  const int first_pair = blockIdx.x / p.heads;
-  const int d = p.d;
-  const int nb = p.nb;
-  const int stride = p.items_per_cta_stride;
-  const int n_items = first_pair < p.n_pairs ? (p.n_pairs - first_pair + stride - 1) / stride : 0;
-  const uint32_t total = uint32_t(n_items) * uint32_t(nb);
-  long long* tr = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
-  long long* trs = (tr != nullptr && warp == 2 && lane == 0) ? tr + 2 * 512 : nullptr;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tma_qkv);
-    tma_prefetch_desc(&tma_pos);
-    mbar_init(ptab_full, 1);
-    mbar_init(qv_full, 1); mbar_init(qv_empty, 1);
-    mbar_init(qu_full, 1); mbar_init(qu_empty, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    mbar_init(bd_full, 1);
-    mbar_init(ac_full, 1);
-    mbar_init(bd_free, ATC2_SOFT_WARPS);   // one arrival per warp (512 same-address arrivals per block serialise in the LSU)
-    mbar_init(ac_free, ATC2_SOFT_WARPS);
-    mbar_init(p_full, ATC2_SOFT_WARPS);
-    mbar_init(pv_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t TM_AC = 0, TM_BD = 128, TM_O = 384, TM_P = 448;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer: four independent streams polled by
-    // one thread (Q+v and Q+u per item, K and V per block), each issued the moment its buffer is released
-    if (lane == 0) {
-      mbar_arrive_expect_tx(ptab_full, ATC_PTAB_BYTES);
-      for (int i = 0; i < 7; ++i)                                              // table rows -64 .. 383 (rows < 0 read as 0)
-        tma_load_2d(s_ptab + i * 64 * 128, &tma_pos, ptab_full, h * 64, -64 + 64 * i);
-      uint32_t kb = 0, vb = 0;
-      int qvi = 0, qui = 0;
-      while (kb < total || vb < total || qvi < n_items || qui < n_items) {
-        bool issued = false;
-        if (qvi < n_items && mbar_test(qv_empty, (qvi & 1) ^ 1)) {
-          issued = true;
-          mbar_arrive_expect_tx(qv_full, ATC_TILE_BYTES);
-          tma_load_2d(s_qv, &tma_qkv, qv_full, d + h * 64, p.l + 128 * (first_pair + qvi * stride));
-          ++qvi;
-        }
-        if (qui < n_items && mbar_test(qu_empty, (qui & 1) ^ 1)) {
-          issued = true;
-          mbar_arrive_expect_tx(qu_full, ATC_TILE_BYTES);
-          tma_load_2d(s_qu, &tma_qkv, qu_full, h * 64, p.l + 128 * (first_pair + qui * stride));
-          ++qui;
-        }
-        if (kb < total && mbar_test(&k_empty[kb & 1], ((kb >> 1) & 1) ^ 1)) {
-          issued = true;
-          const int it = int(kb) / nb, b = int(kb) - it * nb;
-          mbar_arrive_expect_tx(&k_full[kb & 1], ATC_TILE_BYTES);
-          tma_load_2d(s_k + (kb & 1) * ATC_TILE_BYTES, &tma_qkv, &k_full[kb & 1], 2 * d + h * 64, 128 * (first_pair + it * stride) + 128 * b);
-          ++kb;
-        }
-        if (vb < total && mbar_test(&v_empty[vb & 1], ((vb >> 1) & 1) ^ 1)) {
-          issued = true;
-          const int it = int(vb) / nb, b = int(vb) - it * nb;
-          mbar_arrive_expect_tx(&v_full[vb & 1], ATC_TILE_BYTES);
-          tma_load_2d(s_v + (vb & 1) * ATC_TILE_BYTES, &tma_qkv, &v_full[vb & 1], 3 * d + h * 64, 128 * (first_pair + it * stride) + 128 * b);
-          ++vb;
-        }
-        if (!issued) __nanosleep(128);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_ac = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_bd = make_idesc_bf16(128, 256);
-      constexpr uint32_t idesc_bd_last = make_idesc_bf16(128, 192);   // the last block never needs table rows >= 384
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);   // A = P from TMEM, B (= V) is MN-major
-      mbar_wait(ptab_full, 0);
-      const uint64_t dqu = make_sw128_desc(smem_u32(s_qu)), dqv = make_sw128_desc(smem_u32(s_qv));
-      auto issue_pv = [&](uint32_t pblk, uint32_t pb) {
-        const uint32_t st = pblk & 1;
-        mbar_wait(&v_full[st], (pblk >> 1) & 1);
-        mbar_wait(p_full, pblk & 1);
-        tc_fence_after();
-        const uint64_t db = make_sw128_desc(smem_u32(s_v + st * ATC_TILE_BYTES));
-#pragma unroll
-        for (int t = 0; t < 8; ++t)      // A: 16 keys = 8 packed columns of the P region; B (MN-major): 16 key rows = 2048 B
-          umma_bf16_ts(tmem_base + TM_O, tmem_base + TM_P + 8 * t, db + uint64_t((t * 2048) >> 4), idesc_pv, (pb | uint32_t(t)) != 0);
-        umma_commit(pv_done);
-        umma_commit(&v_empty[st]);
-      };
-      uint32_t blk = 0;
-      for (int item = 0; item < n_items; ++item) {
-        for (int b = 0; b < nb; ++b, ++blk) {
-          const uint32_t st = blk & 1;
-          // S_bd = (Q+v) P^T needs only the Q+v tile and the resident table: issued as soon as the columns are free
-          if (b == 0) mbar_wait(qv_full, item & 1);
-          mbar_wait(bd_free, (blk & 1) ^ 1);
-          tc_fence_after();
-          const uint64_t dp = make_sw128_desc(smem_u32(s_ptab + b * 128 * 128));
-          const uint32_t idbd = (b == nb - 1) ? idesc_bd_last : idesc_bd;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + TM_BD, dqv + 2 * k, dp + 2 * k, idbd, k != 0);
-          umma_commit(bd_full);
-          if (b == nb - 1) umma_commit(qv_empty);
-          // S_ac = (Q+u) K^T
-          if (b == 0) mbar_wait(qu_full, item & 1);
-          mbar_wait(&k_full[st], (blk >> 1) & 1);
-          mbar_wait(ac_free, (blk & 1) ^ 1);
-          tc_fence_after();
-          const uint64_t dk = make_sw128_desc(smem_u32(s_k + st * ATC_TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + TM_AC, dqu + 2 * k, dk + 2 * k, idesc_ac, k != 0);
-          umma_commit(ac_full);
-          umma_commit(&k_empty[st]);
-          if (b == nb - 1) umma_commit(qu_empty);
-          if (blk > 0) issue_pv(blk - 1, uint32_t(b == 0 ? nb - 1 : b - 1));
-        }
-      }
-      if (total > 0) issue_pv(total - 1, uint32_t(nb - 1));
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warps
-    // thread = (query row rho, key quarter qt of every 128-key block); the four threads of a row sit in four warps of the
-    // same TMEM lane quadrant.  The loop is software pipelined over the CTA's blocks: in the iteration that finishes
-    // block j (exp, P, O rescale) the thread first stages the S_bd window of block j+1 (so the MMA warp can start S_bd of
-    // block j+2 while the exponentials run) and afterwards does the rel-shift add and the row-maximum exchange of j+1.
-    const int sw = warp - 2;
-    const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
-    const int qt = sw >> 2;
-    const int rho = quad * 32 + lane;
-    const int half = rho >> 6, qi = rho & 63;
-    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    uint8_t* stage = s_stage + (threadIdx.x - 64) * ATC_STAGE_PITCH;
-    const __half* stage_rd = reinterpret_cast<const __half*>(stage) + (31 - lane);
-    float* my_x = reinterpret_cast<float*>(stage + 128);          // [0],[1]: row maxima by block parity, [2]: row sum
-    const float* peer_x[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int pq = (qt + 1 + j) & 3;
-      peer_x[j] = reinterpret_cast<const float*>(s_stage + ((pq * 4 + (sw & 3)) * 32 + lane) * ATC_STAGE_PITCH + 128);
-    }
-    const int cb = 96 - 32 * quad + 32 * qt;           // first S_bd column this warp stages (warp-uniform)
-    const int bar_id = 1 + quad;
-
-    float s[32];                                       // skewed log2-domain scores of the current block
-    float m_run = -1e30f, l_run = 0.f, m_new = -1e30f;
-    int cur_b = 0;                                     // block index inside its item, current block
-    int cur_g = 2 * first_pair + half;                 // chunk of this row, current item
-    int nx_b = 0, nx_pair = first_pair;                // (block, pair) of the block being pulled / skewed
-    int nx_ulo = 0, nx_uhi = 0;
-    int ep_g = -1;                                     // chunk whose item is complete but not yet written out
-    float ep_l = 0.f;
-
-    // pull the S_bd window of block `blk` (nx_*) out of TMEM into the fp16 skew row
-    auto pull = [&](uint32_t blk) {
-      mbar_wait(bd_full, blk & 1);
-      tc_fence_after();
-      if (nx_b == 0) {
-        const int2 rg = p.range[2 * nx_pair + half];
-        nx_ulo = rg.x + 64 * half; nx_uhi = rg.y + 64 * half;   // valid union slots for this row
-      }
-      const float sc = PRE ? 1.0f : p.scale_log2e;
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {                 // one 32-column half of the window at a time (register budget)
-        uint32_t rb[32];
-        tmem_ld32(tmem_base + lane_addr + TM_BD + cb + 32 * hb, rb);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 w0;
-          w0.x = pack_half2(__uint_as_float(rb[8 * q]) * sc, __uint_as_float(rb[8 * q + 1]) * sc);
-          w0.y = pack_half2(__uint_as_float(rb[8 * q + 2]) * sc, __uint_as_float(rb[8 * q + 3]) * sc);
-          w0.z = pack_half2(__uint_as_float(rb[8 * q + 4]) * sc, __uint_as_float(rb[8 * q + 5]) * sc);
-          w0.w = pack_half2(__uint_as_float(rb[8 * q + 6]) * sc, __uint_as_float(rb[8 * q + 7]) * sc);
-          *reinterpret_cast<uint4*>(stage + 64 * hb + 16 * q) = w0;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bd_free);             // this warp's S_bd windows are in shared memory
-    };
-    // rel-shift add + mask of the pulled block -> s, row maximum exchange -> m_new (for that block)
-    auto skew = [&](uint32_t blk) {
-      uint32_t ra[32];                                 // raw S_ac of this thread's 32 keys
-      mbar_wait(ac_full, blk & 1);
-      tc_fence_after();
-      tmem_ld32(tmem_base + lane_addr + TM_AC + 32 * qt, ra);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ac_free);
-      float mx = -1e30f;
-      const int u0 = 128 * nx_b + 32 * qt;
-      const bool edge = (u0 < nx_ulo) || (u0 + 32 > nx_uhi);
-      if (p.experiment & 2) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) { s[k] = __uint_as_float(ra[k]); mx = fmaxf(mx, s[k]); }
-      } else if (__any_sync(0xffffffffu, edge)) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int uq = u0 + k;
-          float v = PRE ? __uint_as_float(ra[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(ra[k]), p.scale_log2e, __half2float(stage_rd[k]));
-          v = (uq >= nx_ulo && uq < nx_uhi) ? v : -INFINITY;
-          s[k] = v;
-          mx = fmaxf(mx, v);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v = PRE ? __uint_as_float(ra[k]) + __half2float(stage_rd[k]) : fmaf(__uint_as_float(ra[k]), p.scale_log2e, __half2float(stage_rd[k]));
-          s[k] = v;
-          mx = fmaxf(mx, v);
-        }
-      }
-      my_x[blk & 1] = mx;
-      if (trs && blk < 64) trs[blk * 8 + 5] = clock64();
-      named_bar_sync(bar_id, 128);
-      if (trs && blk < 64) trs[blk * 8 + 6] = clock64();
-      const float m_prev = (nx_b == 0) ? -1e30f : m_run;      // a new item starts from scratch
-      m_new = fmaxf(fmaxf(m_prev, mx), fmaxf(fmaxf(peer_x[0][blk & 1], peer_x[1][blk & 1]), peer_x[2][blk & 1]));
-    };
-    // write the finished item ep_g: O / l -> ctx (each thread stores 16 of the head's 64 output columns of its row)
-    auto write_out = [&]() {
-      const float l_tot = ep_l + peer_x[0][2] + peer_x[1][2] + peer_x[2][2];
-      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;     // no valid key: zero context (attention.py:133-136)
-      uint32_t r[16];
-      tmem_ld16(tmem_base + lane_addr + TM_O + 16 * qt, r);
-      tmem_ld_wait();
-      if (ep_g < p.n_chunks && !(p.experiment & 1)) {
-        __nv_bfloat16* orow = p.ctx + ((long long)ep_g * 64 + qi) * d + h * 64 + 16 * qt;
-        uint32_t o[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = pack_bf16(__uint_as_float(r[2 * q]) * inv, __uint_as_float(r[2 * q + 1]) * inv);
-        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow), "r"(o[0]), "r"(o[1]), "r"(o[2]),
-                     "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
-                     : "memory");
-      }
-      ep_g = -1;
-    };
-
-    if (total > 0) {
-      pull(0);
-      skew(0);
-      if (++nx_b == nb) { nx_b = 0; nx_pair += stride; }
-    }
-    for (uint32_t blk = 0; blk < total; ++blk) {
-      const bool more = blk + 1 < total;
-      if (trs && blk < 64) trs[blk * 8 + 0] = clock64();
-      if (more) pull(blk + 1);
-      if (trs && blk < 64) trs[blk * 8 + 1] = clock64();
-      // ---- exponentials of block blk
-      if (cur_b == 0) { m_run = -1e30f; l_run = 0.f; }
-      const float alpha = fast_exp2(m_run - m_new);
-      float sum = 0.f;
-      uint32_t pk[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float p0 = (p.experiment & 4) ? s[2 * e] - m_new : fast_exp2(s[2 * e] - m_new);
-        const float p1 = (p.experiment & 4) ? s[2 * e + 1] - m_new : fast_exp2(s[2 * e + 1] - m_new);
-        sum += p0 + p1;
-        pk[e] = pack_bf16(p0, p1);
-      }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-      if (trs && blk < 64) trs[blk * 8 + 2] = clock64();
-      if (blk > 0) mbar_wait(pv_done, (blk - 1) & 1);   // previous P V retired: the P columns and O are ours again
-      tc_fence_after();
-      if (trs && blk < 64) trs[blk * 8 + 3] = clock64();
-      if (ep_g >= 0) write_out();                       // the previous item is complete: O is final until the next P V
-      tmem_st16(tmem_base + lane_addr + TM_P + 16 * qt, pk);
-      if (cur_b > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale this thread's 16 columns of the running output
-        uint32_t r[16];
-        tmem_ld16(tmem_base + lane_addr + TM_O + 16 * qt, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-        tmem_st16(tmem_base + lane_addr + TM_O + 16 * qt, r);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      if (trs && blk < 64) trs[blk * 8 + 4] = clock64();
-      if (cur_b == nb - 1) {                            // item complete once its last P V retires
-        ep_g = cur_g; ep_l = l_run;
-        my_x[2] = l_run;                                // published by the next named barrier
-      }
-      // ---- rel-shift add + maximum exchange of block blk + 1
-      if (more) {
-        skew(blk + 1);
-        cur_b = nx_b; cur_g = 2 * nx_pair + half;
-        if (++nx_b == nb) { nx_b = 0; nx_pair += stride; }
-      } else {
-        named_bar_sync(bar_id, 128);                    // publish the last row sums
-      }
-    }
-    if (total > 0) {
-      mbar_wait(pv_done, (total - 1) & 1);
-      tc_fence_after();
-      if (ep_g >= 0) write_out();
       tc_fence_before();
     }
   }
@@ -1182,14 +820,9 @@ inline bool launch_attention_ring_dk(const AttnParams& a, cudaStream_t st, std::
   if (!make_tma_2d_bf16(&tq, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 128, 64, err)) return false;
   if (!make_tma_2d_bf16(&tk, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 64, 64, err)) return false;
   if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 64, 64, err)) return false;
-  static bool attr_set = false;
   const size_t smem = atcr_smem_bytes<DK>();
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_ring_kernel<DK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_ring_kernel<DK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(attention_ring): ") + cudaGetErrorString(e); return false; }
-    attr_set = true;
-  }
+  if (!ensure_smem_optin(attention_ring_kernel<DK, true>, smem, err, "attention_ring")) return false;
+  if (!ensure_smem_optin(attention_ring_kernel<DK, false>, smem, err, "attention_ring")) return false;
   if (a.prescaled) attention_ring_kernel<DK, true><<<per_head * a.heads, ATCR_THREADS, smem, st>>>(tq, tk, tp, p);
   else attention_ring_kernel<DK, false><<<per_head * a.heads, ATCR_THREADS, smem, st>>>(tq, tk, tp, p);
   ++g_kernel_launches;
@@ -1201,7 +834,7 @@ inline bool launch_attention_ring(const AttnParams& a, cudaStream_t st, std::str
   return (a.d / a.heads) == 128 ? launch_attention_ring_dk<128>(a, st, err) : launch_attention_ring_dk<64>(a, st, err);
 }
 
-inline bool launch_attention_tc(const AttnParams& a, int version, cudaStream_t st, std::string* err) {
+inline bool launch_attention_tc(const AttnParams& a, cudaStream_t st, std::string* err) {
   // tile = 128 query rows = 128 / c consecutive chunks; their union key window has l + 128 + r slots
   const int W = a.l + a.c + a.r;
   const int U = a.l + 128 + a.r;
@@ -1215,8 +848,6 @@ inline bool launch_attention_tc(const AttnParams& a, int version, cudaStream_t s
   p.heads = a.heads; p.nb = (U + 127) / 128; p.scale_log2e = a.scale * 1.4426950408889634f;
   p.c_log2 = c_log2; p.tab_row0 = a.c - 128;
   p.n_last = (W - 128 * (p.nb - 1) <= 65) ? 192 : 256;   // widest S_bd column a valid score of the last block can need
-  p.trace = attention_trace_buffer();
-  { const char* ex = getenv("CF_ATTN_EXPERIMENT"); p.experiment = ex ? atoi(ex) : 0; }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1229,19 +860,9 @@ inline bool launch_attention_tc(const AttnParams& a, int version, cudaStream_t s
   CUtensorMap tq, tp;
   if (!make_tma_2d_bf16(&tq, a.qkv, qkv_rows, uint64_t(4) * a.d, uint64_t(4) * a.d, 128, 64, err)) return false;
   if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 64, 64, err)) return false;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC_SMEM_BYTES));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC_SMEM_BYTES));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC2_SMEM_BYTES));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ATC2_SMEM_BYTES));
-    if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute(attention_tc): ") + cudaGetErrorString(e); return false; }
-    attr_set = true;
-  }
-  if (version == 2) {
-    if (a.prescaled) attention_tc2_kernel<true><<<per_head * a.heads, ATC2_THREADS, ATC2_SMEM_BYTES, st>>>(tq, tp, p);
-    else attention_tc2_kernel<false><<<per_head * a.heads, ATC2_THREADS, ATC2_SMEM_BYTES, st>>>(tq, tp, p);
-  } else if (a.prescaled) attention_tc_kernel<true><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
+  if (!ensure_smem_optin(attention_tc_kernel<true>, ATC_SMEM_BYTES, err, "attention_tc")) return false;
+  if (!ensure_smem_optin(attention_tc_kernel<false>, ATC_SMEM_BYTES, err, "attention_tc")) return false;
+  if (a.prescaled) attention_tc_kernel<true><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
   else attention_tc_kernel<false><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();

@@ -116,204 +116,6 @@ __global__ void __launch_bounds__(128) frontend_conv0_dw1_kernel(Fe1Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tensor-core version of conv0 + ReLU + depthwise conv1 (same output as frontend_conv0_dw1_kernel).
-// For each of the 9 depthwise taps (a,b) the 3x3 conv0 evaluated at (2*t2+a, 2*f2+b) is one UMMA k-step:
-//     G_ab[pos, ch] = A_ab[pos, 0..15] . W0'[ch, 0..15],   A_ab = {9 im2col inputs, 1.0 (bias column), 0...},
-//                                                          W0'  = {w0[ch][0..8], b0[ch], 0...}          (bf16)
-// and the CUDA cores only do  out[pos, ch] = b1[ch] + sum_ab w1[ch,ab] * relu(G_ab[pos, ch])  on the accumulators
-// (18 instead of 90 FMAs per output).  Tile = 128 positions of one chunk; channels in 32 slices of 16 (UMMA 128x16x16,
-// operands in the no-swizzle K-major core-matrix layout); the two worker groups (4 warps each, one warp per TMEM lane
-// quadrant) own the slices of one half of the channels each and one 9-tap TMEM buffer each.
-//   warp 0 : TMEM allocator + MMA issuer;  warps 1..8 : input staging, im2col, epilogue.
-// ---------------------------------------------------------------------------------------------
-constexpr int FETC_THREADS = 288;
-
-template <int D>
-__global__ void __launch_bounds__(FETC_THREADS, 1) frontend_conv0_dw1_tc_kernel(Fe1Params p, int total_tiles) {
-  static_assert(D % 32 == 0, "D");
-  constexpr int SLICES = D / 16;            // channel slices of 16
-  constexpr int SL_PER_GRP = SLICES / 2;
-  constexpr int MAX_ROWS = 39;
-  extern __shared__ __align__(1024) uint8_t fet_smem[];
-  uint8_t* sA = fet_smem;                                         // 9 taps x [128 x 16] bf16 = 9 x 4096 B
-  uint8_t* sW = sA + 9 * 4096;                                    // SLICES x [16 x 16] bf16 = SLICES x 512 B
-  float* sW1 = reinterpret_cast<float*>(sW + SLICES * 512);       // [SLICES][10][16]: 9 taps + bias b1
-  float* s_in = sW1 + SLICES * 160;                               // MAX_ROWS * feat_dim
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_in + MAX_ROWS * 80);
-  uint64_t* a_ready = bars;        // workers -> MMA, 256 arrivals
-  uint64_t* d_full = bars + 1;     // [2] MMA -> group
-  uint64_t* d_free = bars + 3;     // [2] group -> MMA, 128 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_chunk = p.T2 * p.F2;
-  const int tiles_per_chunk = (per_chunk + 127) / 128;
-
-  if (threadIdx.x == 0) {
-    mbar_init(a_ready, 256);
-    for (int g = 0; g < 2; ++g) { mbar_init(&d_full[g], 1); mbar_init(&d_free[g], 128); }
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  // weights -> shared-memory operand images (once per CTA)
-  for (int i = threadIdx.x; i < D; i += FETC_THREADS) {
-    const float* wp = p.wpack + i * 20;
-    const int sl = i >> 4, cl = i & 15;
-    __nv_bfloat16* row0 = reinterpret_cast<__nv_bfloat16*>(sW + sl * 512 + (cl >> 3) * 256 + (cl & 7) * 16);
-    __nv_bfloat16* row1 = row0 + 64;        // second K group: +128 B
-#pragma unroll
-    for (int k = 0; k < 8; ++k) row0[k] = __float2bfloat16(wp[k]);
-    row1[0] = __float2bfloat16(wp[8]);
-    row1[1] = __float2bfloat16(wp[9]);      // conv0 bias rides on the constant-1 input column
-#pragma unroll
-    for (int k = 2; k < 8; ++k) row1[k] = __float2bfloat16(0.f);
-#pragma unroll
-    for (int t = 0; t < 9; ++t) sW1[sl * 160 + t * 16 + cl] = wp[10 + t];
-    sW1[sl * 160 + 144 + cl] = wp[19];
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 16);
-      uint32_t tile_it = 0, cnt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
-        mbar_wait(a_ready, tile_it & 1);
-        tc_fence_after();
-        for (int i = 0; i < SL_PER_GRP; ++i, ++cnt) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(&d_free[g], (cnt & 1) ^ 1);
-            tc_fence_after();
-            const int slice = g * SL_PER_GRP + i;
-            const uint64_t db = make_nosw_desc(smem_u32(sW + slice * 512), 128, 256);
-#pragma unroll
-            for (int t = 0; t < 9; ++t)
-              umma_bf16_ss(tmem_base + g * 144 + t * 16, make_nosw_desc(smem_u32(sA + t * 4096), 128, 256), db, idesc, 0);
-            umma_commit(&d_full[g]);
-          }
-        }
-      }
-    }
-  } else {
-    const int wt = threadIdx.x - 32;            // 0..255
-    const int grp = (warp - 1) >> 2;
-    const int quad = warp & 3;
-    const int trow = quad * 32 + lane;          // position row of the tile this thread owns in the epilogue
-    const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + grp * 144;
-    uint32_t cnt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int chunk = tile / tiles_per_chunk;
-      const int pos0 = (tile - chunk * tiles_per_chunk) * 128;
-      const int npos = min(128, per_chunk - pos0);
-      const ChunkSrc cs = p.chunks[chunk];
-      named_bar_sync(1, 256);                   // previous tile fully consumed (all its MMAs have retired)
-      // ---- stage the input rows this tile needs (CMVN after zero padding, encoder.py:615-616)
-      const int t2_first = pos0 / p.F2;
-      const int t2_last = (pos0 + npos - 1) / p.F2;
-      const int row0 = 4 * t2_first;
-      const int nrows = 4 * (t2_last - t2_first) + 7;
-      for (int i = wt; i < nrows * p.feat_dim; i += 256) {
-        const int rr = i / p.feat_dim, k = i - rr * p.feat_dim;
-        const int t = row0 + rr;
-        float v = 0.f;
-        if (t < cs.in_len && t < p.in_rows) v = __ldg(p.feats + (cs.feat_row + t) * p.feat_dim + k);
-        if (p.cmvn_mean) v = (v - __ldg(p.cmvn_mean + k)) * __ldg(p.cmvn_istd + k);
-        s_in[i] = v;
-      }
-      named_bar_sync(1, 256);
-      // ---- im2col: thread pair per position, taps split 5 / 4
-      {
-        const int pl = wt & 127, hp = wt >> 7;
-        const int pos = pos0 + pl;
-        const bool active = pl < npos;
-        const int t2 = active ? pos / p.F2 : t2_first;
-        const int f2 = active ? pos - t2 * p.F2 : 0;
-        const float* src = s_in + (4 * (t2 - t2_first)) * p.feat_dim + 4 * f2;
-        uint8_t* dst = sA + (pl >> 3) * 256 + (pl & 7) * 16;
-        const int tap0 = hp ? 5 : 0, tap1 = hp ? 9 : 5;
-        for (int t = tap0; t < tap1; ++t) {
-          const int a = t / 3, b = t - 3 * a;
-          const float* q = src + (2 * a) * p.feat_dim + 2 * b;
-          uint4 lo, hi;
-          if (active) {
-            lo.x = pack_bf16(q[0], q[1]);
-            lo.y = pack_bf16(q[2], q[p.feat_dim]);
-            lo.z = pack_bf16(q[p.feat_dim + 1], q[p.feat_dim + 2]);
-            lo.w = pack_bf16(q[2 * p.feat_dim], q[2 * p.feat_dim + 1]);
-            hi = make_uint4(pack_bf16(q[2 * p.feat_dim + 2], 1.0f), 0u, 0u, 0u);
-          } else {
-            lo = make_uint4(0u, 0u, 0u, 0u);
-            hi = lo;
-          }
-          *reinterpret_cast<uint4*>(dst + t * 4096) = lo;
-          *reinterpret_cast<uint4*>(dst + t * 4096 + 128) = hi;
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(a_ready);
-      // ---- epilogue: this group's 16 channel slices
-      const bool row_ok = trow < npos;
-      __nv_bfloat16* orow = p.out + ((long long)chunk * per_chunk + pos0 + trow) * D;
-      for (int i = 0; i < SL_PER_GRP; ++i, ++cnt) {
-        const int slice = grp * SL_PER_GRP + i;
-        const float* w1 = sW1 + slice * 160;
-        float acc[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b = *reinterpret_cast<const float4*>(w1 + 144 + 4 * q);
-          acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w;
-        }
-        mbar_wait(&d_full[grp], cnt & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int t3 = 0; t3 < 3; ++t3) {
-          uint32_t v0[16], v1[16], v2[16];
-          tmem_ld16(taddr + (3 * t3) * 16, v0);
-          tmem_ld16(taddr + (3 * t3 + 1) * 16, v1);
-          tmem_ld16(taddr + (3 * t3 + 2) * 16, v2);
-          tmem_ld_wait();
-          if (t3 == 2) { tc_fence_before(); mbar_arrive(&d_free[grp]); }   // all nine taps are in registers
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 wa = *reinterpret_cast<const float4*>(w1 + (3 * t3) * 16 + 4 * q);
-            const float4 wb = *reinterpret_cast<const float4*>(w1 + (3 * t3 + 1) * 16 + 4 * q);
-            const float4 wc = *reinterpret_cast<const float4*>(w1 + (3 * t3 + 2) * 16 + 4 * q);
-            acc[4 * q] = fmaf(wa.x, fmaxf(__uint_as_float(v0[4 * q]), 0.f), acc[4 * q]);
-            acc[4 * q + 1] = fmaf(wa.y, fmaxf(__uint_as_float(v0[4 * q + 1]), 0.f), acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(wa.z, fmaxf(__uint_as_float(v0[4 * q + 2]), 0.f), acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(wa.w, fmaxf(__uint_as_float(v0[4 * q + 3]), 0.f), acc[4 * q + 3]);
-            acc[4 * q] = fmaf(wb.x, fmaxf(__uint_as_float(v1[4 * q]), 0.f), acc[4 * q]);
-            acc[4 * q + 1] = fmaf(wb.y, fmaxf(__uint_as_float(v1[4 * q + 1]), 0.f), acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(wb.z, fmaxf(__uint_as_float(v1[4 * q + 2]), 0.f), acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(wb.w, fmaxf(__uint_as_float(v1[4 * q + 3]), 0.f), acc[4 * q + 3]);
-            acc[4 * q] = fmaf(wc.x, fmaxf(__uint_as_float(v2[4 * q]), 0.f), acc[4 * q]);
-            acc[4 * q + 1] = fmaf(wc.y, fmaxf(__uint_as_float(v2[4 * q + 1]), 0.f), acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(wc.z, fmaxf(__uint_as_float(v2[4 * q + 2]), 0.f), acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(wc.w, fmaxf(__uint_as_float(v2[4 * q + 3]), 0.f), acc[4 * q + 3]);
-          }
-        }
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + slice * 16);
-          dst[0] = make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
-          dst[1] = make_uint4(pack_bf16(acc[8], acc[9]), pack_bf16(acc[10], acc[11]), pack_bf16(acc[12], acc[13]), pack_bf16(acc[14], acc[15]));
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
-}
-
-template <int D>
-constexpr size_t frontend_tc_smem_bytes() { return 9 * 4096 + (D / 16) * 512 + (D / 16) * 160 * 4 + 39 * 80 * 4 + 128; }
-
-// ---------------------------------------------------------------------------------------------
 // Channel-major tensor-core version of conv0 + ReLU + depthwise conv1 (same output as the two kernels above).
 // Work unit = one output time row (chunk, t2): the three conv0 rows t1 = 2*t2 + {0,1,2} it depends on are ONE UMMA per
 // block of 128 channels, with the roles swapped relative to the kernel above:

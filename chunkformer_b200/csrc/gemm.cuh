@@ -31,26 +31,24 @@ struct GemmEpiParams {
   const int2* row_range = nullptr;  // EPI_F32: row valid iff range[row / rows_per_chunk].x <= row % rows_per_chunk < .y
   int rows_per_chunk = 1;
   int resid_tma = 0;             // EPI_F32: residual sub-tiles are TMA-loaded into the staging tiles (set by launch_gemm)
-  int debug = 0;                 // tools only (CF_GEMM_DEBUG): 1 = epilogue does nothing, 2 = no loads / MMAs (timing ablations),
+#ifdef CF_ABLATION
+  int debug = 0;                 // ablation builds only (tools/, -DCF_ABLATION): 1 = epilogue does nothing, 2 = no loads / MMAs,
                                  // 4 = bf16 epilogue computes but neither stages nor stores, 8 = bf16 epilogue stores straight from registers,
-                                 // 16 = bf16 epilogue stores every tile to the first 128 rows (no DRAM write traffic)
+                                 // 16 = bf16 epilogue stores every tile to the first 128 rows (no DRAM write traffic), 32 = no TMA store
   void* raw_out = nullptr; long long raw_ldo = 0;   // output as a plain pointer (debug 8)
-  int half_slot = 0;             // EPI_BF16, 1-CTA kernel: 32-column store boxes through two 8 KB half slots (set by launch_gemm)
+#endif
   float* part_best = nullptr;    // EPI_ARGMAX: [M, 2 * n_tiles]
   float* part_second = nullptr;
   int* part_index = nullptr;
-  // EPI_F32 only: LayerNorm fused behind the residual update.  After a CTA has stored every column tile of a 128-row
-  // block it normalises those rows straight from L2 (the fp32 rows it has just written), so the stand-alone LayerNorm
-  // pass and its HBM read of x disappear.  ln_mode 1: y = LN1(x);  2: x <- LN1(x), y = LN2(x) (norm_final + next norm).
-  int ln_mode = 0;
-  float* ln_x = nullptr;            // = the GEMM output (fp32, row pitch ln_ldx)
-  long long ln_ldx = 0;
-  __nv_bfloat16* ln_y = nullptr;    // [M, N] bf16
-  const float* ln1_w = nullptr; const float* ln1_b = nullptr;
-  const float* ln2_w = nullptr; const float* ln2_b = nullptr;
-  const int* ln_row_limit = nullptr;   // optional: rows with (row % ln_rows_per_seq) >= limit[row / ln_rows_per_seq] give y = 0
-  int ln_rows_per_seq = 1;
 };
+
+// Timing / ablation switches exist only in the tools build (python -m chunkformer_b200.build --ablation); in the product
+// library CF_DBG folds to 0 and every ablation branch is compiled out.
+#ifdef CF_ABLATION
+#define CF_DBG(ep, bits) (((ep).debug & (bits)) != 0)
+#else
+#define CF_DBG(ep, bits) (0)
+#endif
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
@@ -98,91 +96,12 @@ CF_DEVINL void stage_store16(uint8_t* tile, int row, int slot, uint4 v) {
   *reinterpret_cast<uint4*>(tile + row * 128 + ((slot ^ (row & 7)) << 4)) = v;
 }
 
-// Tile schedule of a persistent CTA (or CTA pair) `cta` of `ncta`: by default tiles are dealt round-robin in (m, n) order
-// (balanced to one tile); with the fused LayerNorm a CTA owns whole 128/256-row blocks (all their column tiles back to back).
-CF_DEVINL bool gemm_tile_of(int t, int cta, int ncta, int m_tiles, int n_tiles, bool block_major, int& m_blk, int& n_blk) {
-  if (block_major) {
-    m_blk = cta + (t / n_tiles) * ncta;
-    n_blk = t % n_tiles;
-    return m_blk < m_tiles;
-  }
+// Tile schedule of a persistent CTA (or CTA pair) `cta` of `ncta`: tiles are dealt round-robin in (m, n) order (balanced to one tile).
+CF_DEVINL bool gemm_tile_of(int t, int cta, int ncta, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
   const int tile = cta + t * ncta;
   m_blk = tile / n_tiles;
   n_blk = tile - m_blk * n_tiles;
   return tile < m_tiles * n_tiles;
-}
-
-// LayerNorm of `nrows` freshly stored fp32 rows (N = 256 or 512 columns) by the 8 epilogue warps of a CTA: warp per row,
-// fp32 two-pass statistics, reads through L2 (ld.global.cg: the rows were written by this CTA's TMA stores).
-CF_DEVINL void gemm_fused_layernorm(const GemmEpiParams& ep, int row0, int M, int N, int epi_warp, int lane) {
-  const int v4 = N >> 7;                       // float4 per lane (2 or 4)
-  const float inv_n = 1.0f / float(N);
-  constexpr int RB = 4;                        // rows in flight per warp (latency hiding for the L2 reads)
-  for (int r0 = epi_warp * RB; r0 < GEMM_BM; r0 += GEMM_EPI_WARPS * RB) {
-    float4 raw[RB][4];
-#pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      const int row = row0 + r0 + j;
-      const float* xr = ep.ln_x + (long long)row * ep.ln_ldx;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        raw[j][k] = (row < M && k < v4) ? __ldcg(reinterpret_cast<const float4*>(xr + k * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      const int row = row0 + r0 + j;
-      if (row >= M) break;
-      float* xr = ep.ln_x + (long long)row * ep.ln_ldx;
-      float v[16];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { v[4 * k] = raw[j][k].x; v[4 * k + 1] = raw[j][k].y; v[4 * k + 2] = raw[j][k].z; v[4 * k + 3] = raw[j][k].w; }
-      auto normalise = [&](const float* w, const float* b) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s += v[i];
-        const float mean = warp_sum(s) * inv_n;
-        float q = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < v4) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const float dlt = v[4 * k + i] - mean; q += dlt * dlt; }
-          }
-        const float rstd = rsqrtf(warp_sum(q) * inv_n + 1e-5f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < v4) {
-            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + k * 128 + lane * 4));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(b + k * 128 + lane * 4));
-            v[4 * k] = (v[4 * k] - mean) * rstd * ww.x + bb.x;
-            v[4 * k + 1] = (v[4 * k + 1] - mean) * rstd * ww.y + bb.y;
-            v[4 * k + 2] = (v[4 * k + 2] - mean) * rstd * ww.z + bb.z;
-            v[4 * k + 3] = (v[4 * k + 3] - mean) * rstd * ww.w + bb.w;
-          }
-      };
-      normalise(ep.ln1_w, ep.ln1_b);
-      if (ep.ln_mode == 2) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < v4) *reinterpret_cast<float4*>(xr + k * 128 + lane * 4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        normalise(ep.ln2_w, ep.ln2_b);
-      }
-      bool zero = false;
-      if (ep.ln_row_limit) {
-        const int sq = row / ep.ln_rows_per_seq;
-        zero = (row - sq * ep.ln_rows_per_seq) >= ep.ln_row_limit[sq];
-      }
-      __nv_bfloat16* yr = ep.ln_y + (long long)row * N;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < v4) {
-          uint2 o;
-          o.x = zero ? 0u : pack_bf16(v[4 * k], v[4 * k + 1]);
-          o.y = zero ? 0u : pack_bf16(v[4 * k + 2], v[4 * k + 3]);
-          *reinterpret_cast<uint2*>(yr + k * 128 + lane * 4) = o;
-        }
-    }
-  }
 }
 
 CF_DEVINL uint4 stage_load16(const uint8_t* tile, int row, int slot) {
@@ -362,45 +281,6 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       if (issuer) { tma_store_2d(tma_c, stg, col0, row0); tma_store_commit(); }
     }
   } else {
-    if (EPI == EPI_BF16 && ep.half_slot) {
-      // Four sub-rounds of 32 columns (64 bytes per row, 64-byte swizzle) through two 8 KB half slots of the group's staging
-      // tile: the TMA store of one half drains while the other is filled.  With one 16 KB slot per group every round waited
-      // for the previous store to finish reading shared memory; the ablation (CF_GEMM_DEBUG=4 / 16) put that wait, not the
-      // SiLU math or the DRAM writes, at 0.06 of the kernel's 0.35 ms.
-#pragma unroll 1
-      for (int sr = 0; sr < 4; ++sr) {
-        const int tcol = sr * 32;
-        const int col0 = gcol0 + tcol;
-        if (col0 >= N) break;
-        uint8_t* stg = stg2 + (rc++ & 1) * (GEMM_STAGING_BYTES / 2);
-        uint32_t r[32];
-        tmem_ld32(taddr + tcol, r);
-        float b[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q);
-          b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
-        }
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store before last has read this half
-        named_bar_sync(bar_id, 128);
-        tmem_ld_wait();
-        uint32_t o[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float v0 = __uint_as_float(r[j]) + b[j], v1 = __uint_as_float(r[j + 1]) + b[j + 1];
-          if (ACT == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-          if (ACT == ACT_SILU) { v0 = silu_fast(v0); v1 = silu_fast(v1); }
-          o[j >> 1] = pack_bf16(v0, v1);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(stg + trow * 64 + ((q ^ ((trow >> 1) & 3)) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        fence_proxy_async();
-        named_bar_sync(bar_id, 128);
-        if (issuer) { tma_store_2d(tma_c, stg, col0, row0); tma_store_commit(); }
-      }
-      return;
-    }
     // bf16 outputs: EPI_BF16 -> two 64-column sub-tiles per group; EPI_GLU -> one 64-column sub-tile (128 acc columns)
     constexpr int ROUNDS = (EPI == EPI_GLU) ? 1 : 2;
     constexpr int CH_PER_ROUND = (EPI == EPI_GLU) ? 4 : 2;
@@ -410,7 +290,7 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       if (acol0 >= N) break;
       constexpr uint32_t SLOT_MASK = gemm_staging_slots(EPI) / 2 - 1;
       uint8_t* stg = stg2 + (rc++ & SLOT_MASK) * GEMM_STAGING_BYTES;
-      const bool no_stage = (ep.debug & 12) != 0;
+      const bool no_stage = CF_DBG(ep, 12) != 0;
       if (!no_stage) {
         if (issuer) { if (SLOT_MASK) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); else tma_store_wait_read(); }
         named_bar_sync(bar_id, 128);
@@ -452,7 +332,8 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
             if (ACT == ACT_SILU) { v0 = silu_fast(v0); v1 = silu_fast(v1); }
             o[j >> 1] = pack_bf16(v0, v1);
           }
-          if (ep.debug & 8) {
+#ifdef CF_ABLATION
+          if CF_DBG(ep, 8) {
             if (row0 + trow < M && col0 < N) {
               __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(ep.raw_out) + (long long)(row0 + trow) * ep.raw_ldo + col0;
 #pragma unroll
@@ -461,10 +342,12 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
                              "r"(o[8 * q + 2]), "r"(o[8 * q + 3]), "r"(o[8 * q + 4]), "r"(o[8 * q + 5]), "r"(o[8 * q + 6]), "r"(o[8 * q + 7])
                              : "memory");
             }
-          } else if (ep.debug & 4) {
+          } else if CF_DBG(ep, 4) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) asm volatile("" ::"r"(o[q]));
-          } else {
+          } else
+#endif
+          {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               stage_store16(stg, trow, 4 * cc + q, make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
@@ -474,9 +357,9 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       if (no_stage) continue;
       fence_proxy_async();
       named_bar_sync(bar_id, 128);
-      if (issuer && !(ep.debug & 32)) {
+      if (issuer && !CF_DBG(ep, 32)) {
         const int ocol = (EPI == EPI_GLU) ? (gcol0 >> 1) : acol0;
-        tma_store_2d(tma_c, stg, ocol, (ep.debug & 16) ? 0 : row0);   // debug 16: every tile lands on the first 128 rows (L2 only)
+        tma_store_2d(tma_c, stg, ocol, CF_DBG(ep, 16) ? 0 : row0);   // debug 16: every tile lands on the first 128 rows (L2 only)
         tma_store_commit();
       }
     }
@@ -514,7 +397,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (N + BN - 1) / BN;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  const bool block_major = (EPI == EPI_F32) && ep.ln_mode != 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -543,8 +425,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t stage = 0, phase = 0;
       for (int t = 0;; ++t) {
         int m_blk, n_blk;
-        if (!gemm_tile_of(t, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
-        for (int kb = 0; kb < k_blocks && !(ep.debug & 2); ++kb) {
+        if (!gemm_tile_of(t, blockIdx.x, gridDim.x, m_tiles, n_tiles, m_blk, n_blk)) break;
+        for (int kb = 0; kb < k_blocks && !CF_DBG(ep, 2); ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -566,12 +448,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t stage = 0, phase = 0;
       for (int it = 0;; ++it) {
         int m_blk, n_blk;
-        if (!gemm_tile_of(it, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
+        if (!gemm_tile_of(it, blockIdx.x, gridDim.x, m_tiles, n_tiles, m_blk, n_blk)) break;
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        if (ep.debug & 2) {
+        if CF_DBG(ep, 2) {
           if (elect_one()) umma_commit(&tfull_bar[acc]);
           __syncwarp();
           continue;
@@ -608,26 +490,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint32_t rc = 0;                    // rounds of this group so far (TMA-residual epilogue)
     if (res_tma && issuer) {            // residual sub-tile of the very first round
       int m0, n0;
-      if (gemm_tile_of(0, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m0, n0)) {
+      if (gemm_tile_of(0, blockIdx.x, gridDim.x, m_tiles, n_tiles, m0, n0)) {
         mbar_arrive_expect_tx(&res_full[grp * 2], GEMM_STAGING_BYTES);
         tma_load_2d(stg, &tma_r, &res_full[grp * 2], n0 * BN + grp * 128, m0 * GEMM_BM);
       }
     }
-    int pending_row0 = -1;              // row block whose stores are in flight and whose LayerNorm is still to do
-    auto run_pending_ln = [&](bool last) {
-      if (pending_row0 < 0) return;
-      // the block's stores were committed one tile ago (4 newer bulk groups per issuer), so this wait is normally free
-      if (issuer) {
-        if (last) tma_store_wait_all(); else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      named_bar_sync(3, 32 * GEMM_EPI_WARPS);
-      gemm_fused_layernorm(ep, pending_row0, M, N, ew, lane);
-      pending_row0 = -1;
-    };
     for (int it = 0;; ++it) {
       int m_blk, n_blk;
-      if (!gemm_tile_of(it, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
+      if (!gemm_tile_of(it, blockIdx.x, gridDim.x, m_tiles, n_tiles, m_blk, n_blk)) break;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -636,15 +506,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t pf_bytes = 0;
       if (EPI == EPI_F32 && ep.resid != nullptr && !res_tma) {
         int m2, n2;
-        if (gemm_tile_of(it + 1, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m2, n2)) {
+        if (gemm_tile_of(it + 1, blockIdx.x, gridDim.x, m_tiles, n_tiles, m2, n2)) {
           const int prow = m2 * GEMM_BM + trow, pcol = n2 * BN + grp * 128;
           if (prow < M && pcol < N) { pf_next = ep.resid + (long long)prow * ep.ld_resid + pcol; pf_bytes = uint32_t(min(128, N - pcol)) * 4u; }
         }
       }
-      if (ep.debug & 1) {
+      if CF_DBG(ep, 1) {
       } else if (res_tma) {
         int m2, n2, nrow0 = -1, ncol0 = 0;
-        if (gemm_tile_of(it + 1, blockIdx.x, gridDim.x, m_tiles, n_tiles, block_major, m2, n2)) { nrow0 = m2 * GEMM_BM; ncol0 = n2 * BN + grp * 128; }
+        if (gemm_tile_of(it + 1, blockIdx.x, gridDim.x, m_tiles, n_tiles, m2, n2)) { nrow0 = m2 * GEMM_BM; ncol0 = n2 * BN + grp * 128; }
         gemm_epilogue_f32_tma(taddr, m_blk * GEMM_BM, trow, n_blk * BN + grp * 128, M, stg, bar_id, issuer, &tma_c, &tma_r, ep,
                               &res_full[grp * 2], rc, nrow0, ncol0);
       } else {
@@ -654,12 +524,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (EPI == EPI_F32 && block_major) {
-        run_pending_ln(false);
-        if (n_blk == n_tiles - 1) pending_row0 = m_blk * GEMM_BM;
-      }
     }
-    if (EPI == EPI_F32 && block_major) run_pending_ln(true);
     if (issuer && EPI != EPI_ARGMAX) tma_store_wait_all();   // global writes complete before the CTA exits
   }
 
@@ -755,7 +620,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   const int m_tiles = (M + 255) / 256;
   const int n_tiles = (N + BN - 1) / BN;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
-  const bool block_major = (EPI == EPI_F32) && ep.ln_mode != 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -784,8 +648,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       uint32_t stage = 0, phase = 0;
       for (int t = 0;; ++t) {
         int m_blk, n_blk;
-        if (!gemm_tile_of(t, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
-        for (int kb = 0; kb < k_blocks && !(ep.debug & 2); ++kb) {
+        if (!gemm_tile_of(t, cluster_id, num_clusters, m_tiles, n_tiles, m_blk, n_blk)) break;
+        for (int kb = 0; kb < k_blocks && !CF_DBG(ep, 2); ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
@@ -807,12 +671,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       uint32_t stage = 0, phase = 0;
       for (int it = 0;; ++it) {
         int m_blk, n_blk;
-        if (!gemm_tile_of(it, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
+        if (!gemm_tile_of(it, cluster_id, num_clusters, m_tiles, n_tiles, m_blk, n_blk)) break;
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        if (ep.debug & 2) {
+        if CF_DBG(ep, 2) {
           if (elect_one()) umma_commit_2sm(&tfull_bar[acc]);
           __syncwarp();
           continue;
@@ -846,25 +710,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     uint32_t rc = 0;
     if (res_tma && issuer) {
       int m0, n0;
-      if (gemm_tile_of(0, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m0, n0)) {
+      if (gemm_tile_of(0, cluster_id, num_clusters, m_tiles, n_tiles, m0, n0)) {
         mbar_arrive_expect_tx(&res_full[grp * 2], GEMM_STAGING_BYTES);
         tma_load_2d(stg, &tma_r, &res_full[grp * 2], n0 * BN + grp * 128, m0 * 256 + int(rank) * 128);
       }
     }
-    int pending_row0 = -1;
-    auto run_pending_ln = [&](bool last) {
-      if (pending_row0 < 0) return;
-      if (issuer) {
-        if (last) tma_store_wait_all(); else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      named_bar_sync(3, 32 * GEMM_EPI_WARPS);
-      gemm_fused_layernorm(ep, pending_row0, M, N, ew, lane);
-      pending_row0 = -1;
-    };
     for (int it = 0;; ++it) {
       int m_blk, n_blk;
-      if (!gemm_tile_of(it, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m_blk, n_blk)) break;
+      if (!gemm_tile_of(it, cluster_id, num_clusters, m_tiles, n_tiles, m_blk, n_blk)) break;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -873,15 +726,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       uint32_t pf_bytes = 0;
       if (EPI == EPI_F32 && ep.resid != nullptr && !res_tma) {
         int m2, n2;
-        if (gemm_tile_of(it + 1, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m2, n2)) {
+        if (gemm_tile_of(it + 1, cluster_id, num_clusters, m_tiles, n_tiles, m2, n2)) {
           const int prow = m2 * 256 + int(rank) * 128 + trow, pcol = n2 * BN + grp * 128;
           if (prow < M && pcol < N) { pf_next = ep.resid + (long long)prow * ep.ld_resid + pcol; pf_bytes = uint32_t(min(128, N - pcol)) * 4u; }
         }
       }
-      if (ep.debug & 1) {
+      if CF_DBG(ep, 1) {
       } else if (res_tma) {
         int m2, n2, nrow0 = -1, ncol0 = 0;
-        if (gemm_tile_of(it + 1, cluster_id, num_clusters, m_tiles, n_tiles, block_major, m2, n2)) { nrow0 = m2 * 256 + int(rank) * 128; ncol0 = n2 * BN + grp * 128; }
+        if (gemm_tile_of(it + 1, cluster_id, num_clusters, m_tiles, n_tiles, m2, n2)) { nrow0 = m2 * 256 + int(rank) * 128; ncol0 = n2 * BN + grp * 128; }
         gemm_epilogue_f32_tma(taddr, m_blk * 256 + int(rank) * 128, trow, n_blk * BN + grp * 128, M, stg, bar_id, issuer, &tma_c, &tma_r, ep,
                               &res_full[grp * 2], rc, nrow0, ncol0);
       } else {
@@ -891,12 +744,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
-      if (EPI == EPI_F32 && block_major) {
-        run_pending_ln(false);
-        if (n_blk == n_tiles - 1) pending_row0 = m_blk * 256 + int(rank) * 128;
-      }
     }
-    if (EPI == EPI_F32 && block_major) run_pending_ln(true);
     if (issuer && EPI != EPI_ARGMAX) tma_store_wait_all();
   }
 

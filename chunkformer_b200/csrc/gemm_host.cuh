@@ -62,6 +62,8 @@ inline bool make_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, u
   return make_tma_2d(map, ptr, false, rows, cols, ld, box_rows, box_cols, err);
 }
 
+struct KernelTiming;
+
 struct GemmLaunch {
   const void* A; long long lda;  // [M, K] bf16
   const void* B; long long ldb;  // [N, K] bf16 (nn.Linear weight layout)
@@ -69,23 +71,50 @@ struct GemmLaunch {
   int epi, act;
   void* out; long long ldo;      // bf16 [M, N] (EPI_BF16), bf16 [M, N/2] (EPI_GLU), fp32 [M, N] (EPI_F32); unused for EPI_ARGMAX
   GemmEpiParams ep;
+  int variant = -1;              // -1 = by problem size, 0 = 1-CTA kernel, 1 = 2-CTA (cta_group::2) kernel
+  KernelTiming* timing = nullptr;  // optional per-handle event timing of one kernel family (bench.py roofline)
+  int family = 0;                // kernel family tag recorded with the timing (cf_kernel_family in the public header)
 };
 
-// Optional event timing of one GEMM family inside a real step (bench.py roofline: average duration of the dominant kernel
-// over the timed region, on the launching stream).  timing_select(): epi * 16 + act of the family to time, or -1 = off.
-struct GemmTiming {
-  int select = -1;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+// Event timing of selected kernel families inside real steps (bench.py roofline: average launch duration of the dominant
+// kernel over the timed region, measured on the launching stream).  Owned by a handle; `mask` = bit set of families to time.
+struct KernelTiming {
+  unsigned mask = 0;
+  struct Rec { cudaEvent_t a, b; int family; };
+  std::vector<Rec> pool;
   size_t used = 0;
+  bool begin(int family, cudaStream_t st) {
+    if (!(mask & (1u << family))) return false;
+    if (used == pool.size()) { Rec r{}; cudaEventCreate(&r.a); cudaEventCreate(&r.b); pool.push_back(r); }
+    pool[used].family = family;
+    cudaEventRecord(pool[used].a, st);
+    return true;
+  }
+  void end(cudaStream_t st) { cudaEventRecord(pool[used++].b, st); }
+  ~KernelTiming() { for (auto& r : pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
 };
-inline GemmTiming& gemm_timing() { static GemmTiming t; return t; }
 
-// 0 = 1-CTA kernel, 1 = 2-CTA (cta_group::2) kernel; set by launch_gemm from the problem size / CF_GEMM_2CTA.
-inline int& gemm_variant_override() { static int v = -1; return v; }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: opt in once per (kernel, device).
+template <typename Kern>
+inline bool ensure_smem_optin(Kern kern, size_t bytes, std::string* err, const char* what) {
+  static std::mutex mu;
+  static unsigned long long done = 0;          // bit per device ordinal (< 64)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && (done >> dev) & 1ull) return true;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute(") + what + "): " + cudaGetErrorString(e);
+    return false;
+  }
+  if (dev < 64) done |= 1ull << dev;
+  return true;
+}
 
 template <int EPI, int ACT>
 inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
-  int use2 = gemm_variant_override();
+  int use2 = g.variant;
   // Measured on B200 (tools/bench_gemm_shapes.py): the pair kernel wins when the K loop dominates (K >= 1024: FFN w_2,
   // embed.out); for K = 512 the epilogue dominates and the 1-CTA kernel is faster. Small M: a 256-row tile is mostly padding.
   if (use2 < 0) use2 = (g.M >= 2048 && g.K >= 1024) ? 1 : 0;
@@ -102,19 +131,14 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
       if (err) *err = "gemm: output pointer missing or leading dimension not 16-byte aligned";
       return false;
     }
-    // measured: FFN w_1 0.335 -> 0.330 ms, QKV 0.325 -> 0.325 ms (the exposed cost of the epilogue is the TMA store itself,
-    // not the wait for the staging slot; profiles/README.md), so the simpler single-slot path stays the default
-    static const int half_env = [] { const char* e = getenv("CF_GEMM_HALFSLOT"); return e ? atoi(e) : 0; }();
-    ep.half_slot = (EPI == EPI_BF16 && !use2 && half_env) ? 1 : 0;
-    if (ep.half_slot) {
-      // 32-column (64-byte) store boxes: two half slots per staging tile, the store of one drains while the other is filled
-      if (!make_tma_2d(&tc, g.out, false, g.M, ocols, g.ldo, GEMM_BM, 32, err, false, true)) return false;
-    } else if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
+    if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
   }
   tr = tc;
   ep.resid_tma = 0;
+#ifdef CF_ABLATION
   { const char* dbg = getenv("CF_GEMM_DEBUG"); ep.debug = dbg ? atoi(dbg) : 0; }
   ep.raw_out = g.out; ep.raw_ldo = g.ldo;
+#endif
   // residual through TMA when every epilogue group of every tile has four full rounds and the pitch is TMA-legal
   if (EPI == EPI_F32 && g.ep.resid != nullptr && g.N % GEMM_BN == 0 && (g.ep.ld_resid * 4) % 16 == 0 &&
       (reinterpret_cast<uintptr_t>(g.ep.resid) & 15) == 0) {
@@ -123,28 +147,15 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
   }
   if (use2) {
     auto kern2 = gemm2_tcgen05_kernel<EPI, ACT>;
-    static bool attr2_set = false;
     const size_t smem2 = gemm2_smem_bytes(EPI);
-    if (!attr2_set) {
-      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2));
-      if (e != cudaSuccess) {
-        if (err) *err = std::string("cudaFuncSetAttribute(gemm2): ") + cudaGetErrorString(e);
-        return false;
-      }
-      attr2_set = true;
-    }
+    if (!ensure_smem_optin(kern2, smem2, err, "gemm2")) return false;
     const int tiles2 = ((g.M + 255) / 256) * ((g.N + GEMM_BN - 1) / GEMM_BN);
     if (tiles2 == 0) return true;
     int clusters = num_sms / 2;
     if (clusters > tiles2) clusters = tiles2;
-    GemmTiming& tm2 = gemm_timing();
-    const bool timed2 = tm2.select == EPI * 16 + ACT;
-    if (timed2) {
-      if (tm2.used == tm2.pool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); tm2.pool.push_back({a, b}); }
-      cudaEventRecord(tm2.pool[tm2.used].first, stream);
-    }
+    const bool timed2 = g.timing && g.timing->begin(g.family, stream);
     kern2<<<2 * clusters, GEMM_THREADS, smem2, stream>>>(ta, tb, tc, tr, g.M, g.N, g.K, ep);
-    if (timed2) cudaEventRecord(tm2.pool[tm2.used++].second, stream);
+    if (timed2) g.timing->end(stream);
     ++g_kernel_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -154,28 +165,15 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
     return true;
   }
   auto kern = gemm_tcgen05_kernel<EPI, ACT>;
-  static bool attr_set = false;
   const size_t smem = gemm_smem_bytes(EPI);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) {
-      if (err) *err = std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e);
-      return false;
-    }
-    attr_set = true;
-  }
+  if (!ensure_smem_optin(kern, smem, err, "gemm")) return false;
   const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM, n_tiles = (g.N + GEMM_BN - 1) / GEMM_BN;
   const int tiles = m_tiles * n_tiles;
   if (tiles == 0) return true;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  GemmTiming& tm = gemm_timing();
-  const bool timed = tm.select == EPI * 16 + ACT;
-  if (timed) {
-    if (tm.used == tm.pool.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); tm.pool.push_back({a, b}); }
-    cudaEventRecord(tm.pool[tm.used].first, stream);
-  }
+  const bool timed = g.timing && g.timing->begin(g.family, stream);
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, tc, tr, g.M, g.N, g.K, ep);
-  if (timed) cudaEventRecord(tm.pool[tm.used++].second, stream);
+  if (timed) g.timing->end(stream);
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

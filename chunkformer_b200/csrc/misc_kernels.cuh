@@ -234,4 +234,16 @@ __global__ void __launch_bounds__(CTC_COMPACT_THREADS) ctc_compact_scatter_kerne
   }
 }
 
+// fp32 -> bf16 (round to nearest even), 4 elements per thread and iteration, grid-stride.  Used by cf_ctc_greedy when the caller
+// hands over the fp32 encoder output (the reference's tensor type) instead of cf_encode's bf16 twin.
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+
 }  // namespace cf

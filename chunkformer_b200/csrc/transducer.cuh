@@ -251,7 +251,12 @@ struct RnntJointParams {
   const float* bo;           // [V]
   const long long* seg_start; const int* seg_len;   // device [B]
   int J, V, n_vtiles;
-  int debug;                 // timing experiments: 1 = no tanh / E loads, 2 = no K loop, 4 = no reductions
+#ifdef CF_ABLATION
+  int debug;                 // ablation build only (CF_RNNT_DEBUG): 1 = no tanh / E loads, 2 = no K loop
+#define CF_RNNT_DBG(p, bit) ((p).debug & (bit))
+#else
+#define CF_RNNT_DBG(p, bit) 0
+#endif
   // fused projection (cluster launch): g_b = Wc . h_top'(b) + bc computed by the cluster of the utterance's joint CTAs
   const float* Wc; const float* bc; int H, layers;
   // in-cluster greedy control (FUSED): the decide step of the utterance runs in CTA 0 of its cluster
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(RNNT_JTHREADS) rnnt_joint_kernel(RnntJointPara
     const float* e = p.E + (p.seg_start[b] + t0) * (long long)p.J;
     for (int i = threadIdx.x; i < RNNT_JR * p.J; i += RNNT_JTHREADS) {
       const int f = i / p.J, k = i - f * p.J;
-      a[i] = f < nf ? ((p.debug & 1) ? 0.5f : tanhf(e[(long long)f * p.J + k] + g_s[k])) : 0.f;
+      a[i] = f < nf ? (CF_RNNT_DBG(p, 1) ? 0.5f : tanhf(e[(long long)f * p.J + k] + g_s[k])) : 0.f;
     }
   }
   __syncthreads();
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(RNNT_JTHREADS) rnnt_joint_kernel(RnntJointPara
     for (int i = 0; i < RNNT_VPT; ++i) acc[r][i] = 0.f;
   // warp kq takes the 4-wide k groups kq, kq + JK, ...; four groups (16 weight vectors of 16 bytes) in flight per step
   const float4* wp = reinterpret_cast<const float4*>(p.WoT);
-  for (int k0 = 0; k0 < ((p.debug & 2) ? 0 : p.J); k0 += 4 * 4 * RNNT_JK) {
+  for (int k0 = 0; k0 < (CF_RNNT_DBG(p, 2) ? 0 : p.J); k0 += 4 * 4 * RNNT_JK) {
     float4 w[4][RNNT_VPT];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {

@@ -43,6 +43,7 @@ class ChunkFormerEncoderB200:
         _lib.check(self._L.cf_finalize_weights(self._h), self._h, "cf_finalize_weights")
         self._ws: Optional[torch.Tensor] = None
         self._ctc_ws: Optional[torch.Tensor] = None
+        self._last_out = None        # (fp32 output, its bf16 twin) of the latest encode: ctc_greedy(out) then needs no cast
         self._copy_stream = None
         self._live_events = []
         # attributes the reference facade reads (chunkformer_model.py:344-389)
@@ -77,10 +78,11 @@ class ChunkFormerEncoderB200:
     def _flat_feats(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
         """Ragged utterances -> one flat device buffer [sum T_i, feat].
 
-        Host tensors are copied on a side stream in pieces of about 32 MB, each followed by an event that is handed to the
-        library (cf_encode_feature_events): the front-end of the following cf_encode starts on the first rows while the rest
-        of the batch is still crossing PCIe (pinned host tensors copy asynchronously; pageable ones are staged by the
-        driver).  Device tensors are copied on the current stream."""
+        Every tensor (host or device) is copied on a side stream in pieces of about 32 MB, each followed by an event that is
+        handed to the library (cf_encode_feature_events): the front-end of the following cf_encode starts on the first rows
+        while the rest of the batch is still crossing PCIe (pinned host tensors copy asynchronously; pageable ones are
+        staged by the driver).  The caller validates shapes BEFORE calling this: the events armed here are consumed by the
+        next cf_encode."""
         total = sum(int(x.shape[0]) for x in xs)
         F = self.geo.feat_dim
         flat = torch.empty((total, F), dtype=torch.float32, device=self.device)
@@ -127,6 +129,7 @@ class ChunkFormerEncoderB200:
                                _lib.CF_F32 if out_dtype == torch.float32 else _lib.CF_BF16, _lib.ptr(out16),
                                c_void_p(ws.data_ptr()), ws.numel(), self._stream())
         _lib.check(rc, self._h, "cf_encode")
+        self._last_out = (out, out16) if out16 is not None else None
         return out, (out if out_dtype == torch.bfloat16 else out16)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -146,25 +149,38 @@ class ChunkFormerEncoderB200:
         lens = [int(v) for v in xs_origin_lens.tolist()]
         if len(lens) != len(xs):
             raise ValueError("xs and xs_origin_lens disagree on the batch size")
+        for x, t in zip(xs, lens):
+            if x.dim() != 2 or x.shape[1] != self.geo.feat_dim or x.shape[0] < t or t < 0:
+                raise ValueError("every utterance must be (T_i, feat_dim) with T_i >= xs_origin_lens[i] >= 0")
         if offset.shape[0] == 0:
             offset = torch.zeros(len(xs), dtype=torch.long, device=xs_origin_lens.device)
         offs = [int(v) for v in offset.tolist()]
-        plan = Plan(chunk_size, left_context_size, right_context_size, lens, offs, self.geo.kernel)
-        feats = self._flat_feats([x[:t] for x, t in zip(xs, lens)])
-        streaming = att_cache.dim() == 4 and att_cache.size(0) > 0 and att_cache.size(1) > 0
         L, H, d, lo = self.geo.layers, self.geo.heads, self.geo.d_model, self.geo.kernel // 2
+        # the reference hands cache slice i to layer i whenever the cache tensors have a leading dimension
+        # (encoder.py:655-661); with left_context_size == 0 the K/V part is empty but the conv cache still carries over
+        streaming = (att_cache.dim() == 4 and att_cache.size(0) > 0) or (cnn_cache.dim() == 3 and cnn_cache.size(0) > 0)
         new_att = new_cnn = None
         if streaming:
-            if tuple(att_cache.shape) != (L, left_context_size, H, 2 * d // H) or tuple(cnn_cache.shape) != (L, d, lo):
+            if len(xs) != 1:
+                raise ValueError("streaming caches need a single utterance per call")
+            if tuple(cnn_cache.shape) != (L, d, lo) or \
+                    (left_context_size > 0 and tuple(att_cache.shape) != (L, left_context_size, H, 2 * d // H)):
                 raise ValueError("cache shapes must be (L, left_context, H, 2*d_k) and (L, d, kernel//2)")
-            new_att = att_cache.to(self.device, torch.float32).contiguous().clone()
+            if left_context_size > 0:
+                new_att = att_cache.to(self.device, torch.float32).contiguous().clone()
+            else:                                # no K/V rows to carry; the library still wants a (dummy) buffer
+                new_att = torch.zeros((L, 1, H, 2 * d // H), device=self.device)
             new_cnn = cnn_cache.to(self.device, torch.float32).contiguous().clone()
-        out, _ = self.encode_plan(plan, feats, new_att, new_cnn, truncated_context_size)
+        plan = Plan(chunk_size, left_context_size, right_context_size, lens, offs, self.geo.kernel)
+        feats = self._flat_feats([x[:t] for x, t in zip(xs, lens)])
+        out, _ = self.encode_plan(plan, feats, new_att, new_cnn, truncated_context_size, want_bf16=True)
         xs_lens = torch.as_tensor(plan.enc_lens, dtype=torch.int32, device=xs_origin_lens.device)
         offset += xs_lens.to(offset.dtype)
         if not streaming:
             new_att = torch.zeros((L, 0, 0, 0), device=self.device)
             new_cnn = torch.zeros((L, 0, 0), device=self.device)
+        elif left_context_size == 0:
+            new_att = torch.zeros((L, 0, H, 2 * d // H), device=self.device)
         return out.view(plan.n, chunk_size, d), xs_lens, plan.n_chunks, new_att, new_cnn, offset
 
     # ------------------------------------------------------------------------------------------------------------
@@ -172,7 +188,7 @@ class ChunkFormerEncoderB200:
     @torch.no_grad()
     def forward_chunk(self, xs: torch.Tensor, att_cache: torch.Tensor = torch.zeros((0, 0, 0, 0, 0)),
                       cnn_cache: torch.Tensor = torch.zeros((0, 0, 0, 0)), chunk_size: int = 0, left_context_size: int = 0,
-                      right_context_size: int = 0, offset: int = 0):
+                      right_context_size: int = 0, offset: int = 0, donate_caches: bool = False):
         """One streaming step for B concurrent streams; drop-in for ChunkFormerEncoder.forward_chunk (encoder.py:310-390) at
         right_context_size = 0 (every shipped streaming preset, apps/realtime-asr/config.py:86-110).
 
@@ -182,7 +198,11 @@ class ChunkFormerEncoderB200:
 
         With r = 0 a step is, per stream, the masked-chunk path on one chunk with that stream's caches and
         truncated_context_size = c (oracle.forward_chunk, pinned against the reference).  All B streams share one encoder pass
-        (cf_encode_streams): every stream carries its left context as placeholder rows that cf_encode fills from the caches."""
+        (cf_encode_streams): every stream carries its left context as placeholder rows that cf_encode fills from the caches.
+
+        donate_caches=True: the passed device fp32 caches are updated in place and returned (a serving loop hands the returned
+        caches straight back in, so the copies the reference's functional style implies, 1 GB per step for CTC-large at 256
+        streams, are pure waste); the default keeps the reference's behaviour of leaving the arguments untouched."""
         if right_context_size != 0:
             raise NotImplementedError("forward_chunk is built for right_context_size = 0 (the shipped streaming presets)")
         c, l = int(chunk_size), int(left_context_size)
@@ -202,8 +222,12 @@ class ChunkFormerEncoderB200:
         # overwritten with the stream's caches inside cf_encode) + the real chunk; the negative plan offset masks the part of
         # the left context that is not filled yet (valid cache rows = min(offset, l))
         ph = -(-max(l, lo) // c)
-        new_att = att_cache.to(self.device, torch.float32).contiguous().clone()
-        new_cnn = cnn_cache.to(self.device, torch.float32).contiguous().clone()
+
+        def own(t):
+            if donate_caches and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous():
+                return t
+            return t.to(self.device, torch.float32).contiguous().clone()
+        new_att, new_cnn = own(att_cache), own(cnn_cache)
         t_tot = ph * 8 * c + T
         x_dev = torch.zeros((B, t_tot, xs.shape[2]), dtype=torch.float32, device=self.device)
         x_dev[:, ph * 8 * c:] = xs.to(self.device, torch.float32)
@@ -229,7 +253,7 @@ class ChunkFormerEncoderB200:
         cnn = torch.zeros((0, 0, 0, 0))
         outs, offset = [], 0
         for i in range(0, xp.shape[1] - size + stride, stride):
-            o, _, att, cnn = self.forward_chunk(xp[:, i:i + size], att, cnn, c, l, 0, offset)
+            o, _, att, cnn = self.forward_chunk(xp[:, i:i + size], att, cnn, c, l, 0, offset, donate_caches=True)
             outs.append(o)
             offset += c
         out = torch.cat(outs, dim=1)
@@ -288,15 +312,24 @@ class ChunkFormerEncoderB200:
         if self.geo.vocab <= 0:
             raise ValueError("model has no CTC head")
         lead = enc.shape[:-1]
-        e = enc.reshape(-1, self.geo.d_model).to(self.device, torch.bfloat16).contiguous()
+        e = enc.reshape(-1, self.geo.d_model)
+        if e.device != self.device:
+            e = e.to(self.device)
+        last = self._last_out
+        if last is not None and e.dtype == torch.float32 and e.data_ptr() == last[0].data_ptr() and e.numel() == last[0].numel():
+            e = last[1]                           # the bf16 twin cf_encode wrote next to this fp32 output
+        if e.dtype not in (torch.float32, torch.bfloat16):
+            e = e.float()
+        e = e.contiguous()
         rows = e.shape[0]
         tokens = torch.empty(rows, dtype=torch.int64, device=self.device)
         margin = torch.empty(rows, dtype=torch.float32, device=self.device) if want_margin else None
         logp = torch.empty((rows, self.geo.vocab), dtype=torch.float32, device=self.device) if want_logp else None
-        need = int(self._L.cf_ctc_workspace_bytes(self._h, rows))
+        dt = _lib.CF_F32 if e.dtype == torch.float32 else _lib.CF_BF16      # fp32 rows are rounded to bf16 by the library's own kernel
+        need = int(self._L.cf_ctc_workspace_bytes(self._h, rows, dt))
         if self._ctc_ws is None or self._ctc_ws.numel() < need:
             self._ctc_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        rc = self._L.cf_ctc_greedy(self._h, c_void_p(e.data_ptr()), rows, c_void_p(tokens.data_ptr()), _lib.ptr(margin),
+        rc = self._L.cf_ctc_greedy(self._h, c_void_p(e.data_ptr()), dt, rows, c_void_p(tokens.data_ptr()), _lib.ptr(margin),
                                    _lib.ptr(logp), c_void_p(self._ctc_ws.data_ptr()), self._ctc_ws.numel(), self._stream())
         _lib.check(rc, self._h, "cf_ctc_greedy")
         res = [tokens.view(lead)]

@@ -13,6 +13,7 @@ CF_F32, CF_BF16 = 0, 1
 CF_OK, CF_ERR_INVALID, CF_ERR_CUDA, CF_ERR_STATE, CF_ERR_WORKSPACE = 0, -1, -2, -3, -4
 EPI_BF16, EPI_GLU, EPI_F32, EPI_ARGMAX = 0, 1, 2, 4
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+FAMILY_OTHER, FAMILY_FFN_W1, FAMILY_FFN_W2, FAMILY_FFN_FUSED = 0, 1, 2, 3
 
 
 class CfConfig(ctypes.Structure):
@@ -29,12 +30,8 @@ SIGNATURES = {
     "cf_encode_feature_events": (c_int, [c_void_p, c_int, POINTER(c_int64), POINTER(c_void_p)]),
     "cf_fbank_num_frames": (c_int64, [c_int64, c_int, c_int, c_int]),
     "cf_fbank": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "cf_set_gemm_variant": (None, [c_int]),
-    "cf_set_attention_version": (None, [c_int]),
-    "cf_gemm_timing_begin": (None, [c_int, c_int]),
-    "cf_gemm_timing_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int)]),
-    "cf_debug_attention_trace": (None, [c_void_p]),
-    "cf_set_fused_layernorm": (None, [c_int]),
+    "cf_kernel_timing_begin": (c_int, [c_void_p, ctypes.c_uint]),
+    "cf_kernel_timing_end": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), POINTER(c_int)]),
     "cf_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),
     "cf_finalize_weights": (c_int, [c_void_p]),
     "cf_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int64),
@@ -50,8 +47,8 @@ SIGNATURES = {
     "cf_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                           c_size_t, c_void_p]),
     "cf_encode_streams": (c_int, [c_void_p, c_int, c_int]),
-    "cf_ctc_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
-    "cf_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cf_ctc_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int]),
+    "cf_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cf_ctc_compact_workspace_bytes": (c_size_t, [c_int64]),
     "cf_ctc_compact": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
@@ -64,7 +61,7 @@ SIGNATURES = {
     "cf_rnnt_greedy": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int32), c_int, c_int, c_int, c_void_p,
                                c_void_p, c_void_p, POINTER(c_int64), c_void_p, c_size_t, c_void_p]),
     "cf_op_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                           c_int64, c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                           c_int64, c_float, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cf_op_layernorm": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_void_p]),
     "cf_op_dwconv": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -2,9 +2,11 @@
 the B200 encoder.  Same method names, argument names / defaults, return types and errors; the checkpoint directory
 layout (config.yaml, global_cmvn, pytorch_model.{bin,pt,ckpt}, vocab.txt, label_mapping.json) is read as is.
 
-Out of scope here: Hugging Face Hub download (no network), the transducer search and audio-file
-decoding through pydub; `endless_decode` / `batch_decode` / `classify_audio` accept either a path to a wav file
-(torchaudio) or an already extracted (T, 80) fbank tensor."""
+`model: transducer` checkpoints decode through the CUDA greedy search (transducer.py).  Out of scope here:
+Hugging Face Hub download (no network) and audio-file decoding through pydub; `endless_decode` / `batch_decode` /
+`classify_audio` accept either a path to a wav file (torchaudio) or an already extracted (T, 80) fbank tensor.
+`batch_decode(..., devices=[...])` replaces the reference's arrival-order admission by duration-balanced scheduling over
+several GPUs of one box."""
 import json
 import math
 import os
@@ -68,6 +70,8 @@ class ChunkFormerModel:
         geo = EncoderGeometry.from_encoder_conf(enc_conf, self.config.get("input_dim", 80), vocab, has_cmvn)
         self.geometry = geo
         self.encoder = ChunkFormerEncoderB200(geo, state_dict, self.device)
+        self._state_dict = state_dict               # kept for weight replicas on further GPUs (batch_decode(devices=...))
+        self._replicas = {}
         self.ctc = _CTCHead(self.encoder) if vocab else None
         # chunkformer-rnnt-*: LSTM predictor + joint behind the encoder (utils/init_model.py:118-133)
         self.transducer = None
@@ -236,16 +240,67 @@ class ChunkFormerModel:
         return tokens
 
     # ---------------------------------------------------------------------------------------------- batch
+    def _decode_group_enqueue(self, encoder, transducer, xs, lens, c, l, r):
+        """Encoder + greedy CTC ids (or the encoder rows for a transducer) of one masked batch, left on the device."""
+        out, enc_lens, n_chunks, _, _, _ = encoder.forward_parallel_chunk(
+            xs=xs, xs_origin_lens=torch.tensor(lens, dtype=torch.int), chunk_size=c, left_context_size=l,
+            right_context_size=r, offset=torch.zeros(len(xs), dtype=torch.int))
+        starts, row = [], 0
+        for n in n_chunks:
+            starts.append(row * c)
+            row += int(n)
+        valid = [max(int(m), 0) for m in enc_lens]
+        tokens = encoder.ctc_greedy(out) if self.model_type == "asr_model" else None
+        return dict(encoder=encoder, transducer=transducer, out=out, tokens=tokens, n_chunks=n_chunks, starts=starts, valid=valid)
+
+    def _decode_group_collect(self, g):
+        """Host side of one group: device-side compaction / transducer search, ids -> text."""
+        if self.model_type != "asr_model":
+            # chunkformer_model.py:532-543: batch_greedy_search; the flat chunk rows are searched in place
+            out = g["out"]
+            pairs = g["transducer"].search_flat(out.reshape(-1, out.shape[-1]), g["starts"], g["valid"])
+            hyps = [tok.tolist() for tok, _ in pairs]
+            return get_output(hyps, self.char_dict, self.model_type) if self.char_dict is not None else hyps
+        if self.char_dict is not None:
+            # CTC collapse on the device (cf_ctc_compact mode 0): one short id list per utterance comes back
+            pairs = g["encoder"].ctc_compact(g["tokens"], g["starts"], g["valid"], mode=0)
+            return [ids_to_text(tok.tolist(), self.char_dict).strip() for tok, _ in pairs]
+        hyps = g["tokens"].split(g["n_chunks"], dim=0)
+        return [h.flatten()[:m] for h, m in zip(hyps, g["valid"])]
+
+    def _replica(self, device):
+        """Encoder (+ transducer head) replica on another GPU of this box: weights are replicated, work is sharded
+        (SURVEY.md 8e)."""
+        device = torch.device(device)
+        if device == self.device:
+            return self.encoder, self.transducer
+        if device not in self._replicas:
+            enc = ChunkFormerEncoderB200(self.geometry, self._state_dict, device)
+            tr = None
+            if self.transducer is not None:
+                blank = int(self.config.get("ctc_conf", {}).get("ctc_blank_id", 0))
+                tr = TransducerGreedyB200(self._state_dict, blank=blank, device=device)
+            self._replicas[device] = (enc, tr)
+        return self._replicas[device]
+
     @torch.no_grad()
     def batch_decode(self, audio_paths: List, chunk_size: Optional[int] = 64, left_context_size: Optional[int] = 128,
-                     right_context_size: Optional[int] = 128, total_batch_duration: int = 1800):
-        """chunkformer_model.py:461-552: greedy arrival-order admission, one masked batch per group."""
+                     right_context_size: Optional[int] = 128, total_batch_duration: int = 1800, devices: Optional[List] = None):
+        """chunkformer_model.py:461-552: greedy arrival-order admission, one masked batch per group.
+
+        devices=[...] (an extension): the admission is replaced by duration-balanced scheduling over several
+        GPUs of this box.  `total_batch_duration` stays the per-GPU budget of one masked batch; utterances are dealt to the
+        devices longest first by chunk count (shard.partition_by_chunks), every device runs its share as one masked batch,
+        all devices of a round are enqueued before any result is read back, and the results come back in input order.
+        Utterances are independent in a masked batch, so the texts equal the single-device ones."""
         if self.model_type == "asr_model" and self.ctc is None or self.model_type != "asr_model" and self.transducer is None:
             raise ValueError("batch_decode needs a CTC head (asr_model) or an LSTM predictor + joint (transducer)")
         c = chunk_size if chunk_size is not None else 64
         l = left_context_size if left_context_size is not None else 128
         r = right_context_size if right_context_size is not None else 128
         budget0 = int(total_batch_duration // 0.01) // 2
+        if devices is not None and len(devices) > 0:
+            return self._batch_decode_balanced(audio_paths, c, l, r, budget0, [torch.device(d) for d in devices])
         decodes, xs, lens, budget = [], [], [], budget0
         for i, a in enumerate(audio_paths):
             x, n = self._load_audio_and_extract_features(a)
@@ -253,40 +308,41 @@ class ChunkFormerModel:
             lens.append(n)
             budget -= n
             if budget <= 0 or i == len(audio_paths) - 1:
-                out, enc_lens, n_chunks, _, _, _ = self.encoder.forward_parallel_chunk(
-                    xs=xs, xs_origin_lens=torch.tensor(lens, dtype=torch.int), chunk_size=c, left_context_size=l,
-                    right_context_size=r, offset=torch.zeros(len(xs), dtype=torch.int))
-                if self.model_type != "asr_model":
-                    # chunkformer_model.py:532-543: batch_greedy_search; the flat chunk rows are searched in place
-                    starts, row = [], 0
-                    for n in n_chunks:
-                        starts.append(row * c)
-                        row += int(n)
-                    pairs = self.transducer.search_flat(out.reshape(-1, out.shape[-1]), starts,
-                                                        [max(int(m), 0) for m in enc_lens])
-                    hyps = [tok.tolist() for tok, _ in pairs]
-                    if self.char_dict is not None:
-                        hyps = get_output(hyps, self.char_dict, self.model_type)
-                    decodes.extend(hyps)
-                    xs, lens, budget = [], [], budget0
-                    continue
-                tokens = self.ctc.argmax(out)
-                if self.char_dict is not None and self.model_type == "asr_model":
-                    # CTC collapse on the device (cf_ctc_compact mode 0): one short id list per utterance comes back
-                    starts, row = [], 0
-                    for n in n_chunks:
-                        starts.append(row * c)
-                        row += int(n)
-                    pairs = self.encoder.ctc_compact(tokens, starts, [max(int(m), 0) for m in enc_lens], mode=0)
-                    hyps = [ids_to_text(tok.tolist(), self.char_dict).strip() for tok, _ in pairs]
-                else:
-                    hyps = tokens.split(n_chunks, dim=0)
-                    hyps = [h.flatten()[:max(int(m), 0)] for h, m in zip(hyps, enc_lens)]
-                    if self.char_dict is not None:
-                        hyps = get_output(hyps, self.char_dict, self.model_type)
-                decodes.extend(hyps)
+                g = self._decode_group_enqueue(self.encoder, self.transducer, xs, lens, c, l, r)
+                decodes.extend(self._decode_group_collect(g))
                 xs, lens, budget = [], [], budget0
         return decodes
+
+    def _batch_decode_balanced(self, audio_paths, c, l, r, budget0, devices):
+        from .shard import chunks_of, partition_by_chunks
+        feats = [self._load_audio_and_extract_features(a) for a in audio_paths]
+        lens = [n for _, n in feats]
+        order = sorted(range(len(lens)), key=lambda i: -chunks_of(lens[i], c))
+        # rounds: longest first until the round holds one budget per device (a single utterance may exceed it, as in the
+        # reference, where a group closes only after the budget is spent)
+        rounds, cur, frames = [], [], 0
+        for i in order:
+            cur.append(i)
+            frames += lens[i]
+            if frames >= budget0 * len(devices):
+                rounds.append(cur)
+                cur, frames = [], 0
+        if cur:
+            rounds.append(cur)
+        results = [None] * len(lens)
+        for rd in rounds:
+            bins = partition_by_chunks([lens[i] for i in rd], c, len(devices))
+            groups = []
+            for dev, b in zip(devices, bins):                   # enqueue every device before reading anything back
+                if not b:
+                    continue
+                idx = [rd[k] for k in b]
+                enc, tr = self._replica(dev)
+                groups.append((idx, self._decode_group_enqueue(enc, tr, [feats[i][0] for i in idx], [lens[i] for i in idx], c, l, r)))
+            for idx, g in groups:
+                for i, hyp in zip(idx, self._decode_group_collect(g)):
+                    results[i] = hyp
+        return results
 
     # ---------------------------------------------------------------------------------------------- classification
     @torch.no_grad()

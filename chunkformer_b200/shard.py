@@ -91,17 +91,29 @@ def gather_variable(t: torch.Tensor, group=None) -> List[torch.Tensor]:
     return [o[: int(s)] for o, s in zip(outs, sizes)]
 
 
+def comm_device(group=None, device=None) -> torch.device:
+    """Device the collectives of `group` run on: the caller's choice, else the current CUDA device under NCCL and the CPU
+    otherwise.  EVERY rank must use the same kind of device, also a rank that got no work (its tensors are empty, not absent)."""
+    import torch.distributed as dist
+    if device is not None:
+        return torch.device(device)
+    if "nccl" in str(dist.get_backend(group)):
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def decode_batch_sharded(tokens_fn: Callable[[List[torch.Tensor], List[int]], List[torch.Tensor]],
-                         xs: Sequence[torch.Tensor], lens: Sequence[int], c: int, group=None) -> List[torch.Tensor]:
+                         xs: Sequence[torch.Tensor], lens: Sequence[int], c: int, group=None, device=None) -> List[torch.Tensor]:
     """Every rank encodes its LPT share of the batch with `tokens_fn(xs_subset, lens_subset) -> [tokens per utterance]`
-    and the per-utterance greedy token ids are gathered once, back in the original order, on every rank."""
+    and the per-utterance greedy token ids are gathered once, back in the original order, on every rank (on `device`, see
+    comm_device; ranks whose bin is empty, i.e. more ranks than utterances, take part with empty tensors)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     bins = partition_by_chunks(lens, c, world)
     mine = bins[rank]
     toks = tokens_fn([xs[i] for i in mine], [int(lens[i]) for i in mine]) if mine else []
-    dev = toks[0].device if toks else torch.device("cpu")
-    flat = torch.cat([t.reshape(-1).to(torch.int64) for t in toks]) if toks else torch.zeros(0, dtype=torch.int64, device=dev)
+    dev = comm_device(group, device)
+    flat = torch.cat([t.reshape(-1).to(dev, torch.int64) for t in toks]) if toks else torch.zeros(0, dtype=torch.int64, device=dev)
     counts = torch.tensor([t.numel() for t in toks], dtype=torch.int64, device=dev)
     all_flat = gather_variable(flat, group)
     all_counts = gather_variable(counts, group)
@@ -116,10 +128,10 @@ def decode_batch_sharded(tokens_fn: Callable[[List[torch.Tensor], List[int]], Li
 
 
 def encode_recording_sharded(encode_fn: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor, c: int, l: int, r: int,
-                             layers: int, mode: str = "exact", group=None) -> torch.Tensor:
+                             layers: int, mode: str = "exact", group=None, device=None) -> torch.Tensor:
     """Each rank encodes its chunk range (+ halos) of one long recording with `encode_fn(frames) -> (rows, d)` (all valid
     rows of that slice encoded as a stand-alone utterance) and keeps its own rows; one gather at the end returns the
-    full (M, d) output on every rank."""
+    full (M, d) output on every rank (on `device`, see comm_device)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     sh = split_recording(int(x.shape[0]), c, l, r, layers, world, mode)[rank]
@@ -127,15 +139,12 @@ def encode_recording_sharded(encode_fn: Callable[[torch.Tensor], torch.Tensor], 
         out = encode_fn(x[sh.in_start:sh.in_end])[sh.keep_lo:sh.keep_hi]
     else:
         out = None
-    d = torch.tensor([0 if out is None else out.shape[1]], dtype=torch.int64)
-    if out is None:
-        # learn the feature width from the other ranks (ranks without work still take part in the gather)
-        ds = [torch.zeros_like(d) for _ in range(world)]
-        dist.all_gather(ds, d.to(x.device) if x.is_cuda else d, group=group)
-        width = int(max(int(v) for v in ds))
-        out = torch.zeros((0, width), dtype=torch.float32, device=x.device)
-    else:
-        ds = [torch.zeros_like(d) for _ in range(world)]
-        dist.all_gather(ds, d.to(out.device) if out.is_cuda else d, group=group)
+    dev = comm_device(group, device)
+    # feature width: ranks without work learn it from the others (they still take part in the gather, with zero rows)
+    d = torch.tensor([0 if out is None else out.shape[1]], dtype=torch.int64, device=dev)
+    ds = [torch.zeros_like(d) for _ in range(world)]
+    dist.all_gather(ds, d, group=group)
+    width = int(max(int(v) for v in ds))
+    out = torch.zeros((0, width), dtype=torch.float32, device=dev) if out is None else out.to(dev, torch.float32)
     parts = gather_variable(out.contiguous(), group)
     return torch.cat(parts, dim=0)

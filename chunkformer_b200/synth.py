@@ -122,3 +122,39 @@ def synth_transducer_state_dict(vocab: int, embed: int, hidden: int, layers: int
     linear("joint.ffn_out", vocab, join_dim, 4.0)
     sd["joint.ffn_out.bias"][0] += blank_bias
     return sd
+
+
+def check_bench_batch(golden, out: torch.Tensor, tokens: torch.Tensor, n_chunks, enc_lens, margin_tol: float) -> dict:
+    """Compare one encode of the benchmark batch (BASELINE.json configs[1]) with the golden of the UNMODIFIED reference for
+    that batch (tests/golden/bench_batch.npz, written by tests/golden/make_golden_bench.py; `golden` = the loaded npz).
+    out (n, c, d) / tokens (n, c) as forward_parallel_chunk / ctc_greedy return them.  Used by the -m gpu parity test and by
+    bench.py after its timed steps (`parity_checked`).  Returns the measured errors; the caller applies the bar."""
+    import numpy as np
+    c, d = out.shape[1], out.shape[2]
+    stride = int(golden["cfg"][3])
+    if [int(v) for v in n_chunks] != [int(v) for v in golden["n_chunks"]] or \
+            [int(v) for v in enc_lens] != [int(v) for v in golden["enc_lens"]]:
+        raise AssertionError("chunk counts / encoder lengths differ from the reference golden")
+    idx_all, idx_sample, row = [], [], 0
+    for nck, m in zip(n_chunks, enc_lens):
+        m = max(int(m), 0)
+        base = row * c
+        idx_all.append(torch.arange(base, base + m))
+        idx_sample.append(torch.arange(base, base + m, stride))
+        row += int(nck)
+    idx_all = torch.cat(idx_all).to(out.device)
+    idx_sample = torch.cat(idx_sample).to(out.device)
+    flat = out.reshape(-1, d)
+    rows = flat[idx_sample].float().cpu()
+    want_rows = torch.from_numpy(golden["rows"].astype(np.float32))
+    diff = rows - want_rows
+    rowsum = flat[idx_all].float().sum(1).cpu()
+    tok = tokens.reshape(-1)[idx_all].cpu()
+    want_tok = torch.from_numpy(golden["tokens"].astype(np.int64))
+    margin = torch.from_numpy(golden["margin"].astype(np.float32))
+    bad = (tok != want_tok)
+    return {"rows_compared": int(rows.shape[0]), "max_abs": float(diff.abs().max()),
+            "rel_rms": float(diff.pow(2).mean().sqrt() / want_rows.pow(2).mean().sqrt()),
+            "rowsum_max_abs": float((rowsum - torch.from_numpy(golden["rowsum"])).abs().max()),
+            "tokens_compared": int(tok.numel()), "token_mismatches": int(bad.sum()),
+            "token_mismatches_above_tol": int((bad & (margin >= margin_tol)).sum()), "margin_tol": margin_tol}

@@ -63,13 +63,11 @@ CF_API const char* cf_last_error(const cf_handle* h);
 CF_API const char* cf_version(void);
 /* Number of kernels this library has launched in the process so far (bench.py reports the per-step count). */
 CF_API long long cf_launch_count(void);
-/* Force the GEMM kernel variant: 0 = 1-CTA, 1 = 2-CTA pair (cta_group::2), -1 = choose by problem size (default). */
 /* Optional, before cf_encode: the feature buffer is still being filled by copies on another stream.  events[i] (cudaEvent_t)
  * fires when feature rows < rows_ready[i] are in place (rows_ready ascending).  cf_encode makes its stream wait only for the
  * rows each front-end slab reads, so the host-to-device copy overlaps the front-end; the list is consumed by that call.
  * Replaces the reference's blocking xs.to(device) (chunkformer_model.py:395-401). */
 CF_API int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_ready, void* const* events);
-CF_API void cf_set_gemm_variant(int variant);
 /* Kaldi-compatible log-mel filterbank on the device: replaces torchaudio.compliance.kaldi.fbank(waveform, num_mel_bins,
  * frame_length, frame_shift, dither=0.0, energy_floor=0.0, sample_frequency) as called right before the path
  * (chunkformer_model.py:307-315).  pcm: n_samples device floats in 16-bit range; out: [cf_fbank_num_frames(...), num_mel_bins]
@@ -77,20 +75,18 @@ CF_API void cf_set_gemm_variant(int variant);
 CF_API int64_t cf_fbank_num_frames(int64_t n_samples, int sample_rate, int frame_length_ms, int frame_shift_ms);
 CF_API int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int sample_rate, int num_mel_bins, int frame_length_ms,
                     int frame_shift_ms, float* out, void* stream);
-/* Measurement: CUDA events around every launch of one GEMM family (epilogue kind `epi`, activation `act`; the FFN
- * up-projection is CF_EPI_BF16 + SiLU) on the launching stream, from cf_gemm_timing_begin until cf_gemm_timing_end, which
- * returns the summed device time and the number of launches (bench.py: roofline of the dominant kernel inside real steps). */
-CF_API void cf_gemm_timing_begin(int epi, int act);
-CF_API int cf_gemm_timing_end(double* total_ms, int* launches);
-/* tcgen05 attention kernel generation used by cf_encode: 1 = 8 softmax warps, P through shared memory; 2 (default) = 16
- * softmax warps, P kept in TMEM. */
-CF_API void cf_set_attention_version(int version);
-/* Debug: device buffer of 3 * 512 int64 that receives an SM-clock timeline of CTA 0 of the version-2 attention kernel
- * (producer / MMA issuer / one softmax thread; see tools/attention_timeline.py); NULL switches it off. */
-CF_API void cf_debug_attention_trace(long long* device_buffer);
-/* 0 (default): LayerNorms run as separate HBM-roofline kernels; 1: fused behind the residual GEMMs (the epilogue warps
- * normalise the rows they just stored, out of L2) - measured slower on B200, kept for A/B measurements. */
-CF_API void cf_set_fused_layernorm(int on);
+/* Measurement hook (bench.py roofline): CUDA events around every launch of the selected kernel families made by this handle's
+ * cf_encode calls, on the launching stream, from cf_kernel_timing_begin until cf_kernel_timing_end(family), which returns the
+ * summed device time and the number of launches of that family.  family_mask = OR of (1 << CF_FAMILY_*).  State lives on
+ * the handle (a handle is used by one thread at a time). */
+enum cf_kernel_family {
+  CF_FAMILY_OTHER = 0,
+  CF_FAMILY_FFN_W1 = 1,      /* FFN up-projection + SiLU (positionwise_feed_forward.py:59) */
+  CF_FAMILY_FFN_W2 = 2,      /* FFN down-projection + 0.5 * residual */
+  CF_FAMILY_FFN_FUSED = 3    /* w_1 -> SiLU -> w_2 -> residual in one kernel */
+};
+CF_API int cf_kernel_timing_begin(cf_handle* h, unsigned family_mask);
+CF_API int cf_kernel_timing_end(cf_handle* h, int family, double* total_ms, int* launches);
 
 /* ---- weights ----------------------------------------------------------------------------------------------------- */
 /* Replaces: load_checkpoint -> model.load_state_dict(strict=False) (chunkformer/utils/checkpoint.py:26-41).
@@ -149,11 +145,12 @@ CF_API int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, void* a
 CF_API int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_chunks);
 
 /* ---- CTC head ---------------------------------------------------------------------------------------------------- */
-CF_API size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows);
+CF_API size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows, int enc_dtype);
 /* Replaces: CTC.log_softmax + argmax (chunkformer/modules/ctc.py:73-91; chunkformer_model.py:437-438, 526-527).
- * enc: device bf16 [rows, d_model]. tokens_out: device int64 [rows]. margin_out: optional device fp32 [rows] = best logit
- * minus runner-up (for tolerance-aware comparisons). logp_out: optional device fp32 [rows, vocab] log-softmax. */
-CF_API int cf_ctc_greedy(cf_handle* h, const void* enc_bf16, int64_t rows, int64_t* tokens_out, float* margin_out,
+ * enc: device [rows, d_model], CF_BF16 (the out_bf16 of cf_encode) or CF_F32 (rounded to bf16 by a kernel of this library
+ * inside the call).  tokens_out: device int64 [rows]. margin_out: optional device fp32 [rows] = best logit minus runner-up
+ * (for tolerance-aware comparisons). logp_out: optional device fp32 [rows, vocab] log-softmax. */
+CF_API int cf_ctc_greedy(cf_handle* h, const void* enc, int enc_dtype, int64_t rows, int64_t* tokens_out, float* margin_out,
                   float* logp_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Replaces: remove_duplicates_and_blank (chunkformer/utils/model_utils.py:23-32) and the per-frame blank filter of
@@ -202,11 +199,12 @@ CF_API int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, const 
 /* ---- kernel-level entry points (parity tests, profiling) --------------------------------------------------------- */
 /* C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 GEMM with a fused epilogue; epi: 0 bf16 out = act(acc+bias), 1 GLU (bf16,
  * N/2 columns, value/gate rows interleaved), 2 fp32 out = resid + rowmask*alpha*(acc+bias), 4 argmax partials
- * [M, 2*ceil(N/256)]; act: 0 none 1 relu 2 silu. All pointers device. */
+ * [M, 2*ceil(N/256)]; act: 0 none 1 relu 2 silu; variant: -1 = kernel chosen by problem size, 0 = 1-CTA kernel, 1 = 2-CTA
+ * pair (cta_group::2) kernel.  All pointers device. */
 CF_API int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int epi, int act,
                const float* bias, const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range,
                int rows_per_chunk, void* out, int64_t ldo, float* part_best, float* part_second, int32_t* part_index,
-               void* stream);
+               int variant, void* stream);
 /* mode 0: y=LN1(x); 1: x<-LN1(x), y=LN2(x); 2: out=LN2(LN1(x)). */
 CF_API int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1, const float* b1,
                     const float* w2, const float* b2, int64_t rows, void* stream);

@@ -343,6 +343,50 @@ def ctc_greedy(sd: Dict[str, torch.Tensor], enc: torch.Tensor):
 
 
 @torch.no_grad()
+def endless_decode_tokens(sd: Dict[str, torch.Tensor], heads: int, layers: int, x: torch.Tensor, c: int, l: int, r: int,
+                          total_batch_duration: float):
+    """The segment loop of endless_decode (chunkformer_model.py:391-438) on this oracle: sequential segments with the K/V and
+    conv caches carried over, rows computed only as right context dropped, greedy CTC over the concatenation.
+    Returns (tokens (T',), top-2 margins (T',), [dict(len, trunc, offset) per encoder call])."""
+    kernel = sd["encoder.encoders.0.conv_module.depthwise_conv.weight"].shape[-1]
+    d = sd["encoder.after_norm.weight"].shape[0]
+    trunc, _, segs = endless_segments(int(x.shape[0]), c, r, layers, total_batch_duration, kernel // 2)
+    att = torch.zeros(layers, l, heads, 2 * d // heads)
+    cnn = torch.zeros(layers, d, kernel // 2)
+    off, outs, calls = [0], [], []
+    for (s, e, last) in segs:
+        calls.append(dict(len=e - s, trunc=trunc, offset=off[0]))
+        o, ol, _, att, cnn, noff = forward_parallel_chunk(sd, heads, [x[s:e]], [e - s], c, l, r, att, cnn, trunc, off, layers)
+        o = o.reshape(-1, d)[: max(int(ol[0]), 0)]
+        if not last:
+            o = o[:trunc]
+        off = [int(noff[0]) - int(ol[0]) + o.shape[0]]
+        outs.append(o)
+    tok, margin = ctc_greedy(sd, torch.cat(outs, 0))
+    return tok, margin, calls
+
+
+@torch.no_grad()
+def batch_decode_tokens(sd: Dict[str, torch.Tensor], heads: int, xs: Sequence[torch.Tensor], c: int, l: int, r: int,
+                        total_batch_duration: float):
+    """batch_decode (chunkformer_model.py:481-529) on this oracle: arrival-order admission, one masked batch per group.
+    Returns ([tokens per utterance], [margins per utterance], group sizes)."""
+    lens = [int(t.shape[0]) for t in xs]
+    toks, margins, sizes = [], [], []
+    for grp in batch_groups(lens, total_batch_duration):
+        out, enc_lens, n_chunks, _, _, _ = forward_parallel_chunk(sd, heads, [xs[i] for i in grp], [lens[i] for i in grp], c, l, r)
+        tok, mg = ctc_greedy(sd, out)
+        row = 0
+        for u, nck in enumerate(n_chunks):
+            m = max(int(enc_lens[u]), 0)
+            toks.append(tok[row:row + nck].reshape(-1)[:m])
+            margins.append(mg[row:row + nck].reshape(-1)[:m])
+            row += nck
+        sizes.append(len(grp))
+    return toks, margins, sizes
+
+
+@torch.no_grad()
 def ctc_log_softmax(sd: Dict[str, torch.Tensor], enc: torch.Tensor) -> torch.Tensor:
     logits = enc @ sd["ctc.ctc_lo.weight"].T + sd["ctc.ctc_lo.bias"]
     return torch.log_softmax(logits, dim=-1)

@@ -3,9 +3,11 @@ checkpoints and fbank, and against the golden vectors produced by the unmodified
 
 Stated tolerance (BASELINE.json north_star): the reference computes in fp32; the kernels use bf16 operands
 with fp32 accumulation, fp32 residual stream and fp32 LayerNorm/softmax statistics.  Encoder outputs (unit rms after
-the final LayerNorm) must agree to max-abs <= 0.12 and relative rms <= 2 % (the reference's own bf16-autocast run differs
-from its fp32 run by 0.098 / 1.6 %); greedy CTC tokens must be identical wherever the fp32 top-2 logit margin exceeds
-MARGIN_TOL = 0.08 (2x the observed logit error of 0.036)."""
+the final LayerNorm) must agree to max-abs <= 0.05 and relative rms <= 1 % (the reference's own bf16-autocast run differs
+from its fp32 run by 0.098 / 1.6 %; the kernels measure 0.02 / 0.4 % on CTC-large, so the bar sits at about 2.5x the measured
+error: a regression that triples it fails); greedy CTC tokens must be identical wherever the fp32 top-2 logit margin exceeds
+MARGIN_TOL = 0.08 (2x the observed logit error of 0.036).  Every comparison appends its measured error to
+gpurun_out/parity_errors.txt when that directory exists (the numbers quoted in DESIGN.md come from there)."""
 import os
 
 import numpy as np
@@ -13,13 +15,13 @@ import pytest
 import torch
 
 from chunkformer_b200.encoder import ChunkFormerEncoderB200
-from chunkformer_b200.geometry import EncoderGeometry
+from chunkformer_b200.geometry import CTC_SMALL, RNNT_LARGE, EncoderGeometry
 from chunkformer_b200.synth import synth_fbank, synth_state_dict
 from oracle import chunkformer_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-MAX_ABS, REL_RMS, MARGIN_TOL = 0.12, 0.02, 0.08
+MAX_ABS, REL_RMS, MARGIN_TOL = 0.05, 0.01, 0.08
 
 SMALL = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=3, kernel=15, vocab=300)
 SMALL_CMVN = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=2, kernel=15, vocab=300, has_cmvn=True)
@@ -36,11 +38,19 @@ def _model(geo, seed):
     return _models[key]
 
 
+def _log_error(what, max_abs, rel):
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_errors.txt"), "a") as f:
+            f.write(f"{what}\tmax_abs={max_abs:.5f}\trel_rms={rel:.5f}\n")
+
+
 def _compare(got, ref, what=""):
     got, ref = got.float().cpu(), ref.float().cpu()
     diff = (got - ref)
     max_abs = diff.abs().max().item()
     rel = (diff.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-9)).item()
+    _log_error(what, max_abs, rel)
     assert max_abs <= MAX_ABS and rel <= REL_RMS, f"{what}: max_abs={max_abs:.4f} rel_rms={rel:.4f}"
     return max_abs, rel
 
@@ -205,6 +215,89 @@ def test_full_size_masked_batch_properties():
         assert (a - b).abs().max().item() < 2e-2, u
         ref, _, _, _, _, _ = O.forward_parallel_chunk(sd, LARGE.heads, [xs[u]], [lens[u]], 64, 128, 128)
         _compare(a, ref.reshape(-1, 512)[:m], f"utterance {u} inside the 14 400 s batch vs oracle")
+
+
+# ------------------------------------------------------------------------------------------------ shipped geometries, ring attention
+@pytest.mark.parametrize("name,geo", [("rnnt_large", RNNT_LARGE), ("ctc_small", CTC_SMALL)])
+@pytest.mark.parametrize("cfg", [(64, 128, 128), (16, 64, 0)])
+def test_shipped_geometries_match_oracle(name, geo, cfg):
+    """End-to-end parity for the two in-tree YAML geometries no other e2e test covers: rnnt-large /
+    classification (d 512, H 4 -> d_k = 128, L 12: BASELINE configs[3]) and ctc-small (d 256, H 4, F 2048, L 12: the streaming
+    table's model), at the benchmark window 64/128/128 and the streaming preset 16/64/0 (BASELINE configs[4])."""
+    c, l, r = cfg
+    sd, enc = _model(geo, 7)
+    lens = [3000, 700, 77, 5200, 15]
+    xs = [synth_fbank(t, seed=500 + k) for k, t in enumerate(lens)]
+    ref, ref_lens, ref_nck, _, _, _ = O.forward_parallel_chunk(sd, geo.heads, xs, lens, c, l, r)
+    out, out_lens, nck, *_ = enc.forward_parallel_chunk(xs, torch.tensor(lens, dtype=torch.int32), c, l, r,
+                                                        offset=torch.zeros(len(lens), dtype=torch.int32))
+    assert nck == ref_nck and out_lens.tolist() == ref_lens.tolist()
+    a = _valid_rows(out, nck, out_lens, geo.d_model)
+    b = _valid_rows(ref, nck, out_lens, geo.d_model)
+    _compare(a, b, f"{name} {cfg}")
+    tok, margin = O.ctc_greedy(sd, b)
+    got_tok = enc.ctc_greedy(a.to(DEV))
+    ok = (got_tok.cpu() == tok) | (margin < MARGIN_TOL)
+    assert bool(ok.all()), f"{int((~ok).sum())} token mismatches above the margin tolerance"
+
+
+DK64 = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=3, kernel=15, vocab=300)
+DK128 = EncoderGeometry(d_model=256, heads=2, ffn=512, layers=3, kernel=15, vocab=300)
+
+
+@pytest.mark.parametrize("geo", [DK64, DK128], ids=["dk64", "dk128"])
+@pytest.mark.parametrize("cfg", [(128, 128, 128), (256, 128, 64), (64, 256, 128), (128, 0, 0), (32, 300, 40)])
+def test_ring_attention_windows_through_the_encoder(geo, cfg):
+    """Window shapes that route to attention_ring_kernel (chunk >= 128, l + r > 256, every d_k = 128 shape), end to end through
+    the encoder against the oracle; ragged batch with utterances shorter than one chunk and longer than several."""
+    c, l, r = cfg
+    sd, enc = _model(geo, 13)
+    lens = [8 * c * 3 + 301, 700, 40, 8 * c + 7]
+    xs = [synth_fbank(t, seed=600 + k) for k, t in enumerate(lens)]
+    ref, ref_lens, ref_nck, _, _, _ = O.forward_parallel_chunk(sd, geo.heads, xs, lens, c, l, r)
+    out, out_lens, nck, *_ = enc.forward_parallel_chunk(xs, torch.tensor(lens, dtype=torch.int32), c, l, r,
+                                                        offset=torch.zeros(len(lens), dtype=torch.int32))
+    assert nck == ref_nck and out_lens.tolist() == ref_lens.tolist()
+    _compare(_valid_rows(out, nck, out_lens, geo.d_model), _valid_rows(ref, nck, out_lens, geo.d_model), f"ring {cfg}")
+
+
+@pytest.mark.parametrize("geo", [DK64, DK128], ids=["dk64", "dk128"])
+@pytest.mark.parametrize("Tp", [130, 374, 1000])
+def test_full_attention_long_utterances(geo, Tp):
+    """chunk_size <= 0 = one chunk of T' frames per utterance (encoder.py:490-493), T' >= 128 so that the tcgen05 ring kernel
+    runs with a ragged last 128-row tile (BASELINE configs[4] "full-attention classification"); padded batch of three."""
+    sd, enc = _model(geo, 13)
+    T = 8 * (Tp - 1) + 15
+    lens = [T, T - 333, 200]
+    xb = torch.zeros(len(lens), T, 80)
+    for k, t in enumerate(lens):
+        xb[k, :t] = synth_fbank(t, seed=700 + k)
+    ref, ref_mask = O.forward_encoder(sd, geo.heads, xb, lens, Tp, 0, 0)
+    out, mask = enc.forward_encoder(xb, torch.tensor(lens), -1, -1, -1)
+    assert out.shape == ref.shape and torch.equal(mask.cpu(), ref_mask)
+    for b, m in enumerate(ref_mask.squeeze(1).sum(-1).tolist()):
+        _compare(out[b, :m], ref[b, :m], f"full attention T'={Tp} utt {b}")
+
+
+def test_benchmark_batch_against_reference_golden(golden_dir):
+    """BASELINE.json configs[1], the workload bench.py times: 19 utterances, 14 400 s, CTC-large 64/128/128, against the golden
+    the UNMODIFIED reference produced for this very batch (tests/golden/make_golden_bench.py): chunk counts and encoder lengths
+    exact; every 64th valid output row within the parity bar; per-row checksums; greedy tokens identical wherever the
+    reference's fp32 top-2 margin exceeds the tolerance."""
+    from chunkformer_b200.synth import check_bench_batch, masked_batch_lengths
+    g = np.load(os.path.join(golden_dir, "bench_batch.npz"))
+    sd, enc = _model(LARGE, 0)
+    lens = masked_batch_lengths()
+    assert lens == g["lens"].tolist()
+    xs = [synth_fbank(t, seed=1 + k) for k, t in enumerate(lens)]
+    out, out_lens, nck, *_ = enc.forward_parallel_chunk(xs, torch.tensor(lens, dtype=torch.int32), 64, 128, 128,
+                                                        offset=torch.zeros(len(lens), dtype=torch.int32))
+    tokens = enc.ctc_greedy(out)
+    rep = check_bench_batch(g, out, tokens, nck, out_lens.tolist(), MARGIN_TOL)
+    _log_error("benchmark batch vs reference golden (every 64th row)", rep["max_abs"], rep["rel_rms"])
+    print(rep)
+    assert rep["max_abs"] <= MAX_ABS and rep["rel_rms"] <= REL_RMS and rep["token_mismatches_above_tol"] == 0
+    assert rep["rowsum_max_abs"] <= 0.35          # sum of 512 values, each within the bar: sqrt(512) * 0.015
 
 
 # ------------------------------------------------------------------------------------------------ frame-synchronous streaming

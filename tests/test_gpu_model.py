@@ -136,6 +136,110 @@ def test_batch_decode_matches_oracle(asr):
             k += 1
 
 
+def _record_encoder_calls(enc, calls):
+    orig = enc.forward_parallel_chunk
+
+    def wrapped(*a, **kw):
+        calls.append(dict(lens=[int(v) for v in kw["xs_origin_lens"].tolist()], trunc=int(kw.get("truncated_context_size", 0)),
+                          offset=[int(v) for v in kw["offset"].tolist()]))
+        return orig(*a, **kw)
+    enc.forward_parallel_chunk = wrapped
+    return orig
+
+
+def test_endless_decode_reference_golden(asr, golden_dir):
+    """endless_decode of THIS facade against goldens of the unmodified reference's endless_decode (fbank loader patched,
+    tests/golden/make_golden_decode.py): every encoder call gets the reference's segment length / truncated_context_size /
+    offset (exact), and the returned token ids are the reference's wherever its fp32 top-2 margin exceeds the tolerance."""
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "decode.npz"))
+    texts = json.load(open(os.path.join(golden_dir, "decode_texts.json"), encoding="utf8"))
+    n = len([k for k in g.files if k.startswith("endless") and k.endswith("_cfg")])
+    assert n >= 5
+    calls = []
+    orig = _record_encoder_calls(asr.encoder, calls)
+    keep = asr.char_dict
+    try:
+        for k in range(n):
+            T, seed, c, l, r = (int(v) for v in g[f"endless{k}_cfg"])
+            tbd, ms = (float(v) for v in g[f"endless{k}_tbd_ms"])
+            x = synth_fbank(T, seed=seed)
+            calls.clear()
+            asr.char_dict = None
+            got = asr.endless_decode(x, c, l, r, total_batch_duration=tbd).reshape(-1).cpu()
+            assert [cl["lens"][0] for cl in calls] == g[f"endless{k}_seg_lens"].tolist(), k
+            assert [cl["trunc"] for cl in calls] == g[f"endless{k}_seg_trunc"].tolist(), k
+            assert [cl["offset"][0] for cl in calls] == g[f"endless{k}_seg_offset"].tolist(), k
+            want = torch.from_numpy(g[f"endless{k}_tokens"].astype(np.int64))
+            margin = torch.from_numpy(g[f"endless{k}_margin"])
+            assert got.shape == want.shape, k
+            ok = (got == want) | (margin < MARGIN_TOL)
+            assert bool(ok.all()), (k, int((~ok).sum()))
+            asr.char_dict = keep
+            if bool((got == want).all()):                 # identical ids -> identical strings and stamps
+                assert asr.endless_decode(x, c, l, r, total_batch_duration=tbd, return_timestamps=True,
+                                          max_silence_duration=ms) == texts[f"endless{k}_stamps"]
+    finally:
+        asr.char_dict = keep
+        asr.encoder.forward_parallel_chunk = orig
+
+
+def test_batch_decode_reference_golden(asr, golden_dir):
+    """batch_decode against goldens of the unmodified reference's batch_decode: same admission groups, same token ids above
+    the margin tolerance."""
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "decode.npz"))
+    n = len([k for k in g.files if k.startswith("batch") and k.endswith("_cfg")])
+    calls = []
+    orig = _record_encoder_calls(asr.encoder, calls)
+    keep = asr.char_dict
+    try:
+        asr.char_dict = None
+        for k in range(n):
+            seed0, c, l, r = (int(v) for v in g[f"batch{k}_cfg"])
+            tbd = float(g[f"batch{k}_tbd"][0])
+            lens = g[f"batch{k}_lens"].tolist()
+            xs = [synth_fbank(t, seed=seed0 + j) for j, t in enumerate(lens)]
+            calls.clear()
+            hyps = asr.batch_decode(xs, c, l, r, total_batch_duration=tbd)
+            assert [len(cl["lens"]) for cl in calls] == g[f"batch{k}_group_sizes"].tolist(), k
+            assert [h.numel() for h in hyps] == g[f"batch{k}_hyp_lens"].tolist(), k
+            got = torch.cat([h.reshape(-1).cpu() for h in hyps])
+            want = torch.from_numpy(g[f"batch{k}_tokens"].astype(np.int64))
+            margin = torch.from_numpy(g[f"batch{k}_margin"])
+            ok = (got == want) | (margin < MARGIN_TOL)
+            assert bool(ok.all()), (k, int((~ok).sum()))
+    finally:
+        asr.char_dict = keep
+        asr.encoder.forward_parallel_chunk = orig
+
+
+@pytest.mark.parametrize("two_gpus", [False, True])
+def test_batch_decode_devices_balanced_equals_oracle(asr, two_gpus):
+    """batch_decode(devices=[...]): duration-balanced scheduling over several encoders.  Results come back in
+    input order and every utterance's ids are the oracle's for that utterance alone (utterances are independent in a masked
+    batch) wherever the fp32 margin exceeds the tolerance.  With one GPU the two 'devices' are the same one (the scheduling
+    logic is what is tested); with two, weights are replicated to the second GPU."""
+    if two_gpus and torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    devices = ["cuda:0", "cuda:1"] if two_gpus else ["cuda:0", "cuda:0"]
+    sd = _oracle_sd()
+    lens = [900, 77, 1500, 300, 2200, 15, 640, 3100]
+    xs = [synth_fbank(t, seed=90 + k) for k, t in enumerate(lens)]
+    texts = asr.batch_decode(xs, 16, 32, 16, total_batch_duration=30, devices=devices)
+    assert len(texts) == len(lens) and all(isinstance(t, str) for t in texts)
+    asr.char_dict, keep = None, asr.char_dict
+    try:
+        hyps = asr.batch_decode(xs, 16, 32, 16, total_batch_duration=30, devices=devices)
+    finally:
+        asr.char_dict = keep
+    toks, margins, _ = O.batch_decode_tokens(sd, GEO.heads, xs, 16, 32, 16, 1e9)
+    for k in range(len(lens)):
+        a = hyps[k].cpu()
+        assert a.shape == toks[k].shape, k
+        assert bool(((a == toks[k]) | (margins[k] < MARGIN_TOL)).all()), k
+
+
 def test_classify_audio_full_and_chunked(tmp_path):
     geo = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=2, kernel=15, vocab=0)
     sd = synth_state_dict(geo, 31)

@@ -110,3 +110,52 @@ def test_world_size_2_gloo_sharded_equals_unsharded():
         assert p.exitcode == 0
     assert ok_batch
     assert shp == full_shp and err < 1e-4, (shp, full_shp, err)
+
+
+def _worker_idle_ranks(rank, world, port, q):
+    """More ranks than utterances / chunks: idle ranks take part in the gathers with empty tensors on the same device."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    sd = synth_state_dict(TINY, 3)
+    c, l, r = 8, 16, 8
+    lens = [300, 45]
+    xs = [synth_fbank(t, seed=50 + k) for k, t in enumerate(lens)]
+
+    def tokens_fn(sub_xs, sub_lens):
+        out, enc_lens, n_chunks, _, _, _ = O.forward_parallel_chunk(sd, TINY.heads, sub_xs, sub_lens, c, l, r)
+        tok, _ = O.ctc_greedy(sd, out)
+        res, row = [], 0
+        for u, nck in enumerate(n_chunks):
+            res.append(tok[row:row + nck].reshape(-1)[: max(int(enc_lens[u]), 0)])
+            row += nck
+        return res
+    got = decode_batch_sharded(tokens_fn, xs, lens, c)
+    ref = tokens_fn(xs, lens)
+    ok_batch = all(torch.equal(a, b) for a, b in zip(got, ref))
+    x = synth_fbank(100, seed=78)                        # 2 chunks over 3 ranks: rank 0 owns none
+
+    def encode_fn(frames):
+        out, enc_lens, _, _, _, _ = O.forward_parallel_chunk(sd, TINY.heads, [frames], [frames.shape[0]], c, l, r)
+        return out.reshape(-1, TINY.d_model)[: int(enc_lens[0])]
+    full = encode_fn(x)
+    sharded = encode_recording_sharded(encode_fn, x, c, l, r, TINY.layers, "exact")
+    err = float((full - sharded).abs().max()) if full.shape == sharded.shape else float("inf")
+    if rank == 0:
+        q.put((ok_batch, err, tuple(sharded.shape), tuple(full.shape)))
+    dist.destroy_process_group()
+
+
+def test_world_size_3_gloo_with_idle_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_idle_ranks, args=(rk, 3, port, q)) for rk in range(3)]
+    for p in procs:
+        p.start()
+    ok_batch, err, shp, full_shp = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok_batch
+    assert shp == full_shp and err < 1e-4, (shp, full_shp, err)

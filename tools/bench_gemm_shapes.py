@@ -21,10 +21,9 @@ for name, M, N, K, epi, act in shapes:
     parts = (torch.empty((M, nt), device="cuda"), torch.empty((M, nt), device="cuda"), torch.empty((M, nt), device="cuda", dtype=torch.int32)) if epi == 4 else (None, None, None)
     line = f"{name:18s} M={M} N={N} K={K}: "
     for v in (0, 1):
-        L.cf_set_gemm_variant(v)
         def run():
             cflib.check(L.cf_op_gemm(p(A), K, p(W), K, M, N, K, epi, act, p(b), p(res), ocols if res is not None else 0, 0.5, None, 1,
-                                     p(out), ocols, p(parts[0]), p(parts[1]), p(parts[2]), st))
+                                     p(out), ocols, p(parts[0]), p(parts[1]), p(parts[2]), v, st))
         for _ in range(3): run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,4 +34,3 @@ for name, M, N, K, epi, act in shapes:
         line += f" {'2cta' if v else '1cta'} {ms:.3f} ms ({2.0 * M * N * K / ms / 1e9:.0f} TF)"
     print(line)
     del A, W, out, res
-L.cf_set_gemm_variant(-1)

@@ -19,7 +19,7 @@ for name, geo in (("ctc-small (d256 H4 L12)", CTC_SMALL), ("ctc-large (d512 H8 L
             torch.cuda.synchronize(); t0 = time.perf_counter()
             n = 10
             for s in range(n):
-                o, _, att, cnn = enc.forward_chunk(x, att, cnn, c, l, 0, offset=(3 + s) * c)
+                o, _, att, cnn = enc.forward_chunk(x, att, cnn, c, l, 0, offset=(3 + s) * c, donate_caches=True)
                 tok = enc.ctc_greedy(o).cpu()
             torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n
             print(f"{name} chunk {c} left {l}: B={B:3d} {dt * 1e3:7.2f} ms per step ({dt * 1e3 / B:5.2f} per stream) "

@@ -14,8 +14,7 @@ b = torch.zeros(N, device="cuda")
 out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 def p(t): return c_void_p(t.data_ptr())
-L.cf_set_gemm_variant(variant)
-def run(): cflib.check(L.cf_op_gemm(p(A), K, p(W), K, M, N, K, 0, 2, p(b), None, 0, 1.0, None, 1, p(out), N, None, None, None, st))
+def run(): cflib.check(L.cf_op_gemm(p(A), K, p(W), K, M, N, K, 0, 2, p(b), None, 0, 1.0, None, 1, p(out), N, None, None, None, variant, st))
 for _ in range(5): run()
 torch.cuda.synchronize()
 proc = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)

@@ -14,8 +14,8 @@ H = torch.empty((rows, F), device="cuda", dtype=torch.bfloat16)
 X = torch.randn((rows, d), device="cuda")
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 def p(t): return c_void_p(t.data_ptr())
-def ffn1(): cflib.check(L.cf_op_gemm(p(A), d, p(W1), d, rows, F, d, 0, 2, p(b1), None, 0, 1.0, None, 1, p(H), F, None, None, None, st))
-def ffn2(): cflib.check(L.cf_op_gemm(p(H), F, p(W2), F, rows, d, F, 2, 0, p(b2), p(X), d, 0.5, None, 1, p(X), d, None, None, None, st))
+def ffn1(): cflib.check(L.cf_op_gemm(p(A), d, p(W1), d, rows, F, d, 0, 2, p(b1), None, 0, 1.0, None, 1, p(H), F, None, None, None, -1, st))
+def ffn2(): cflib.check(L.cf_op_gemm(p(H), F, p(W2), F, rows, d, F, 2, 0, p(b2), p(X), d, 0.5, None, 1, p(X), d, None, None, None, -1, st))
 for f in (ffn1, ffn2):
     for _ in range(3): f()
     torch.cuda.synchronize()

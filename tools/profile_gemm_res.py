@@ -13,7 +13,7 @@ X = torch.randn((rows, d), device="cuda")
 junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 def p(t): return c_void_p(t.data_ptr())
-def run(): cflib.check(L.cf_op_gemm(p(A), d, p(W), d, rows, d, d, 2, 0, p(b), p(X), d, 1.0, None, 1, p(X), d, None, None, None, st))
+def run(): cflib.check(L.cf_op_gemm(p(A), d, p(W), d, rows, d, d, 2, 0, p(b), p(X), d, 1.0, None, 1, p(X), d, None, None, None, -1, st))
 for _ in range(3): run()
 torch.cuda.synchronize()
 ts = []

@@ -14,7 +14,7 @@ out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
 for name, act in (("ffn1 silu", 2), ("qkv", 0)):
     def run():
         cflib.check(L.cf_op_gemm(c_void_p(A.data_ptr()), K, c_void_p(W.data_ptr()), K, M, N, K, 0, act, c_void_p(b.data_ptr()), None, 0, 1.0,
-                                 None, 1, c_void_p(out.data_ptr()), N, None, None, None, st))
+                                 None, 1, c_void_p(out.data_ptr()), N, None, None, None, -1, st))
     for _ in range(3): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
