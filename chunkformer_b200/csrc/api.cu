@@ -1382,6 +1382,22 @@ extern "C" int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb
   return CF_OK;
 }
 
+extern "C" int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias,
+                             const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk,
+                             int mode, const float* ln1_w, const float* ln1_b, const float* ln2_w, const float* ln2_b,
+                             float* x_out, int64_t ldx, void* y_out, int64_t ldy, const int32_t* row_limit, int rows_per_seq,
+                             void* stream) {
+  if (!A || !B) return fail(nullptr, CF_ERR_INVALID, "cf_op_gemm_ln: null argument");
+  GemmLnLaunch g{};
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.bias = bias; g.resid = resid; g.ld_resid = ld_resid;
+  g.alpha = alpha; g.row_range = reinterpret_cast<const int2*>(row_range); g.rows_per_chunk = rows_per_chunk; g.mode = mode;
+  g.ln1_w = ln1_w; g.ln1_b = ln1_b; g.ln2_w = ln2_w; g.ln2_b = ln2_b; g.x_out = x_out; g.ldx = ldx; g.y_out = y_out; g.ldy = ldy;
+  g.row_limit = row_limit; g.rows_per_seq = rows_per_seq;
+  std::string err;
+  if (!launch_gemm_ln(g, current_sms(), static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  return CF_OK;
+}
+
 extern "C" int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1,
                                const float* b1, const float* w2, const float* b2, int64_t rows, void* stream) {
   LnParams q{};

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "gemm_ln.cuh"
 
 namespace cf {
 
@@ -94,22 +95,32 @@ struct KernelTiming {
   ~KernelTiming() { for (auto& r : pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
 };
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: opt in once per (kernel, device).
-template <typename Kern>
-inline bool ensure_smem_optin(Kern kern, size_t bytes, std::string* err, const char* what) {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): opt in once for each pair.  (Keyed by the kernel's
+// address: all instantiations of one kernel template share a function-pointer TYPE.)
+inline bool ensure_smem_optin_ptr(const void* kern, size_t bytes, std::string* err, const char* what) {
   static std::mutex mu;
-  static unsigned long long done = 0;          // bit per device ordinal (< 64)
+  static std::vector<std::pair<const void*, unsigned long long>> done;   // kernel -> bit per device ordinal (< 64)
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
-  if (dev < 64 && (done >> dev) & 1ull) return true;
+  unsigned long long* mask = nullptr;
+  for (auto& kv : done)
+    if (kv.first == kern) { mask = &kv.second; break; }
+  if (mask && dev < 64 && ((*mask >> dev) & 1ull)) return true;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
   if (e != cudaSuccess) {
     if (err) *err = std::string("cudaFuncSetAttribute(") + what + "): " + cudaGetErrorString(e);
     return false;
   }
-  if (dev < 64) done |= 1ull << dev;
+  if (dev < 64) {
+    if (!mask) { done.push_back({kern, 0ull}); mask = &done.back().second; }
+    *mask |= 1ull << dev;
+  }
   return true;
+}
+template <typename Kern>
+inline bool ensure_smem_optin(Kern kern, size_t bytes, std::string* err, const char* what) {
+  return ensure_smem_optin_ptr(reinterpret_cast<const void*>(kern), bytes, err, what);
 }
 
 template <int EPI, int ACT>
@@ -202,6 +213,80 @@ inline bool launch_gemm(const GemmLaunch& g, int num_sms, cudaStream_t stream, s
     case EPI_ARGMAX: return launch_gemm_epi<EPI_ARGMAX, ACT_NONE>(g, num_sms, stream, err);
   }
   if (err) *err = "gemm: unknown epilogue";
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// residual GEMM + fused LayerNorm(s) on a CTA pair (gemm_ln.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+struct GemmLnLaunch {
+  const void* A; long long lda;       // [M, K] bf16
+  const void* B; long long ldb;       // [N, K] bf16, N = 256 or 512
+  int M, N, K;
+  const float* bias;                  // [N]
+  const float* resid; long long ld_resid;   // fp32 [M, N] or nullptr
+  float alpha;
+  const int2* row_range; int rows_per_chunk;
+  int mode;                           // GemmLnMode
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  float* x_out; long long ldx;        // LNM_Y / LNM_XY: the fp32 residual stream; LNM_FINAL: fp32 result (nullable)
+  void* y_out; long long ldy;         // bf16 [M, N] (LNM_FINAL: nullable)
+  const int* row_limit; int rows_per_seq;
+  KernelTiming* timing = nullptr; int family = 0;
+};
+
+template <int NC>
+inline bool launch_gemm_ln_nc(const GemmLnLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
+  CUtensorMap ta, tb, tx, tr, ty;
+  if (!make_tma_2d_bf16(&ta, g.A, g.M, g.K, g.lda, GEMM_BM, GEMM_BK, err)) return false;
+  if (!make_tma_2d_bf16(&tb, g.B, g.N, g.K, g.ldb, NC, GEMM_BK, err)) return false;
+  tx = ta; tr = ta; ty = ta;
+  if (g.x_out && !make_tma_2d(&tx, g.x_out, true, g.M, uint64_t(g.N), g.ldx, GEMM_BM, 32, err)) return false;
+  if (g.resid && !make_tma_2d(&tr, g.resid, true, g.M, uint64_t(g.N), g.ld_resid, GEMM_BM, 32, err)) return false;
+  if (g.y_out && !make_tma_2d(&ty, g.y_out, false, g.M, uint64_t(g.N), g.ldy, GEMM_BM, 64, err)) return false;
+  GemmLnParams ep;
+  ep.bias = g.bias; ep.has_resid = g.resid != nullptr; ep.alpha = g.alpha; ep.row_range = g.row_range;
+  ep.rows_per_chunk = g.rows_per_chunk > 0 ? g.rows_per_chunk : 1; ep.mode = g.mode;
+  ep.ln1_w = g.ln1_w; ep.ln1_b = g.ln1_b; ep.ln2_w = g.ln2_w; ep.ln2_b = g.ln2_b;
+  ep.row_limit = g.row_limit; ep.rows_per_seq = g.rows_per_seq > 0 ? g.rows_per_seq : 1;
+  ep.store_f32 = g.x_out != nullptr; ep.store_bf16 = g.y_out != nullptr;
+  auto kern = gemm_ln_kernel<NC>;
+  const size_t smem = gemmln_smem_bytes<NC>();
+  if (!ensure_smem_optin(kern, smem, err, "gemm_ln")) return false;
+  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM;
+  if (m_tiles == 0) return true;
+  int clusters = num_sms / 2;
+  if (clusters > m_tiles) clusters = m_tiles;
+  const bool timed = g.timing && g.timing->begin(g.family, stream);
+  kern<<<2 * clusters, GEMM_THREADS, smem, stream>>>(ta, tb, tx, tr, ty, g.M, g.K, ep);
+  if (timed) g.timing->end(stream);
+  ++g_kernel_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("gemm_ln launch: ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+inline bool launch_gemm_ln(const GemmLnLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
+  if (g.K % GEMM_BK != 0 || g.K <= 0 || g.lda % 8 != 0 || g.ldb % 8 != 0) {
+    if (err) *err = "gemm_ln: K must be a positive multiple of 64 and leading dimensions multiples of 8";
+    return false;
+  }
+  if (g.mode != LNM_Y && g.mode != LNM_XY && g.mode != LNM_FINAL) { if (err) *err = "gemm_ln: unknown mode"; return false; }
+  if ((g.mode != LNM_FINAL && (!g.x_out || !g.y_out)) || (g.mode == LNM_FINAL && !g.x_out && !g.y_out) || !g.bias || !g.ln1_w || !g.ln1_b ||
+      (g.mode != LNM_Y && (!g.ln2_w || !g.ln2_b))) {
+    if (err) *err = "gemm_ln: missing output or LayerNorm parameters";
+    return false;
+  }
+  if ((g.x_out && (g.ldx * 4) % 16 != 0) || (g.resid && (g.ld_resid * 4) % 16 != 0) || (g.y_out && (g.ldy * 2) % 16 != 0)) {
+    if (err) *err = "gemm_ln: leading dimensions must give 16-byte aligned rows";
+    return false;
+  }
+  if (g.N == 512) return launch_gemm_ln_nc<256>(g, num_sms, stream, err);
+  if (g.N == 256) return launch_gemm_ln_nc<128>(g, num_sms, stream, err);
+  if (err) *err = "gemm_ln: N (= d_model) must be 256 or 512";
   return false;
 }
 

@@ -1,0 +1,442 @@
+// Residual GEMM with the following LayerNorm(s) fused into the epilogue, on a pair of CTAs (thread-block cluster of 2):
+//
+//     x_new = resid + rowmask * alpha * (A W^T + bias)                         (encoder_layer.py:190-246, every "x = x + ..." line)
+//     LNM_Y     : x <- x_new,             y = LN1(x_new)                        (norm_mha / norm_conv / norm_ff, first norm_ff_macaron)
+//     LNM_XY    : x <- LN1(x_new),        y = LN2(LN1(x_new))                   (norm_final of layer i + norm_ff_macaron of layer i + 1)
+//     LNM_FINAL : out = LN2(LN1(x_new))   fp32 and / or bf16                    (norm_final of the last layer + after_norm, encoder.py:670-671)
+//
+// A LayerNorm row spans all N = d_model output columns, so one cluster owns a 128-row block: CTA r of the pair computes
+// columns [r * NC, r * NC + NC), NC = N / 2 (UMMA 128 x NC x 16, cta_group::1, accumulators double-buffered in TMEM across row
+// blocks), and the two CTAs exchange per-row partial statistics (count, mean, M2: Chan's parallel variance, no E[x^2] - mean^2
+// cancellation) through distributed shared memory: each epilogue thread (one row, NC / 2 columns) writes its partial into its
+// own CTA's table and the peer's (st.shared::cluster) and arrives on both CTAs' mbarrier; after the wait every thread merges
+// the four partials of its row in a fixed order, so both CTAs normalise with bit-identical mean / rstd.
+//
+// x_new never makes a round trip through memory before it is normalised: pass 1 writes it to global memory (TMA store) AND
+// back into the accumulator's TMEM columns (tcgen05.st), pass 2 re-reads it from TMEM.  The stand-alone LayerNorm kernels
+// (one HBM read of x and one write of y per LayerNorm: 10 % of the round-1 step at 100 % of HBM bandwidth) disappear.
+//
+//   warp 0 : TMA producer (A 128 x 64 and W NC x 64 per stage)      warp 1 : TMEM allocator + MMA issuer
+//   warps 2..9 : epilogue, two groups of four warps (one per TMEM lane quadrant), group g owns NC / 2 columns of the CTA's tile;
+//                residual sub-tiles (128 rows x 32 fp32) arrive by TMA in the group's two 16 KB staging slots, one round ahead
+#pragma once
+#include "gemm.cuh"
+
+namespace cf {
+
+enum GemmLnMode : int { LNM_Y = 1, LNM_XY = 2, LNM_FINAL = 3 };
+
+struct GemmLnParams {
+  const float* bias = nullptr;         // [N]
+  int has_resid = 0;                   // residual sub-tiles are read through tma_r
+  float alpha = 1.0f;
+  const int2* row_range = nullptr;     // row valid iff range[row / rows_per_chunk].x <= row % rows_per_chunk < .y (convolution.py:253)
+  int rows_per_chunk = 1;
+  int mode = LNM_Y;
+  const float* ln1_w = nullptr; const float* ln1_b = nullptr;
+  const float* ln2_w = nullptr; const float* ln2_b = nullptr;
+  const int* row_limit = nullptr;      // LNM_Y: rows with (row % rows_per_seq) >= limit[row / rows_per_seq] give y = 0
+  int rows_per_seq = 1;
+  int store_f32 = 1, store_bf16 = 1;   // LNM_FINAL: which outputs exist
+};
+
+template <int NC> __host__ __device__ constexpr int gemmln_stages() { return NC == 256 ? 3 : 4; }
+template <int NC> constexpr size_t gemmln_smem_bytes() {
+  return size_t(gemmln_stages<NC>()) * (GEMM_BM * 128 + NC * 128) + 4 * GEMM_STAGING_BYTES + 2 * 4 * 128 * sizeof(float2) + 1024 + 256;
+}
+
+CF_DEVINL void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// Bounded wait with cluster-scope acquire (the releases come from the peer CTA's threads).
+CF_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+// Running (count, mean, M2) of a row segment; `add32` folds in 32 values with a two-pass chunk variance, `merge` is Chan's rule.
+struct RowStats {
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  CF_DEVINL void merge(float nb, float mb, float m2b) {
+    const float nt = n + nb;
+    const float delta = mb - mean;
+    const float f = nb / nt;
+    mean = fmaf(delta, f, mean);
+    m2 = m2 + m2b + delta * delta * n * f;
+    n = nt;
+  }
+  CF_DEVINL void add32(const float (&v)[32]) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += v[j];
+    const float mc = s * (1.0f / 32.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float dlt = v[j] - mc; q = fmaf(dlt, dlt, q); }
+    if (n == 0.f) { n = 32.f; mean = mc; m2 = q; } else merge(32.f, mc, q);
+  }
+};
+
+template <int NC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_r,
+               const __grid_constant__ CUtensorMap tma_y, int M, int K, GemmLnParams ep) {
+  constexpr int STAGES = gemmln_stages<NC>();
+  constexpr uint32_t A_BYTES = GEMM_BM * 128;
+  constexpr uint32_t B_BYTES = NC * 128;
+  constexpr uint32_t TMEM_COLS = 2 * NC;
+  constexpr int NCG = NC / 2;          // columns per epilogue group
+  constexpr int NR = NCG / 32;         // 32-column rounds per group and pass
+  constexpr int N = 2 * NC;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sStage = sB + STAGES * B_BYTES;                                   // [2 groups][2 slots] x 16 KB
+  float2* s_stat = reinterpret_cast<float2*>(sStage + 4 * GEMM_STAGING_BYTES);   // [2 buffers][4 partials][128 rows] (mean, M2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * 4 * 128);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint64_t* res_full = tempty_bar + 2;       // [2 groups][2 slots]
+  uint64_t* stat_bar = res_full + 4;         // [2] used alternately; 16 warp arrivals per exchange: 8 local + 8 from the peer CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int k_blocks = K / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_x);
+    tma_prefetch_desc(&tma_y);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], GEMM_EPI_WARPS); }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
+    mbar_init(&stat_bar[0], 2 * GEMM_EPI_WARPS);
+    mbar_init(&stat_bar[1], 2 * GEMM_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();                          // the peer's barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    uint32_t stage = 0, phase = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, int(rank) * NC);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, NC);
+    const uint64_t da0 = make_sw128_desc(smem_u32(sA));
+    const uint64_t db0 = make_sw128_desc(smem_u32(sB));
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * NC;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da = da0 + uint64_t((stage * A_BYTES) >> 4);
+          const uint64_t db = db0 + uint64_t((stage * B_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int grp = ew >> 2;
+    const bool issuer = ((ew & 3) == 0) && lane == 0;
+    const int bar_id = 1 + grp;
+    const int trow = quad * 32 + lane;
+    uint8_t* stg = sStage + grp * 2 * GEMM_STAGING_BYTES;
+    uint64_t* rfull = &res_full[grp * 2];
+    const int gcol0 = int(rank) * NC + grp * NCG;       // first global column of this group's slab
+    const bool has_res = ep.has_resid != 0;
+    uint32_t q = 0;                 // staging uses of this group so far (slot = q & 1)
+    uint32_t nload[2] = {0u, 0u};   // residual loads issued into each slot (mbarrier phase bookkeeping, identical in every thread)
+    uint32_t xr = 0;                // statistics exchanges so far
+    const float inv_n = 1.0f / float(N);
+
+    // a slot may be rewritten by the threads once the TMA store that last read it (two uses ago) has drained it
+    auto acquire_slot = [&]() {
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      named_bar_sync(bar_id, 128);
+    };
+    auto issue_resid = [&](uint32_t slot, int col0, int row0) {      // issuer only
+      mbar_arrive_expect_tx(&rfull[slot], GEMM_STAGING_BYTES);
+      tma_load_2d(stg + slot * GEMM_STAGING_BYTES, &tma_r, &rfull[slot], col0, row0);
+    };
+    // per-row statistics over all N columns: this thread's partial + the other group's + the peer CTA's two
+    auto exchange = [&](const RowStats& mine, float& mean, float& rstd) {
+      const uint32_t buf = xr & 1u;
+      const uint32_t slot_id = rank * 2u + uint32_t(grp);
+      float2* p = s_stat + (buf * 4u + slot_id) * 128u + trow;
+      *p = make_float2(mine.mean, mine.m2);
+      st_cluster_f32x2(mapa_rank(smem_u32(p), rank ^ 1u), mine.mean, mine.m2);
+      __syncwarp();
+      // exchange k uses table / barrier k & 1: an arrival for exchange k + 2 can only be made by a warp that has passed exchange
+      // k + 1, i.e. after every warp of both CTAs has arrived for (and therefore finished reading) exchange k
+      if (lane == 0) {
+        mbar_arrive_cluster(mapa_rank(smem_u32(&stat_bar[buf]), rank ^ 1u));
+        mbar_arrive_cluster(mapa_rank(smem_u32(&stat_bar[buf]), rank));
+      }
+      mbar_wait_cluster(&stat_bar[buf], (xr >> 1) & 1u);
+      RowStats tot;
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const float2 v = s_stat[(buf * 4u + sl) * 128u + trow];
+        if (sl == 0) { tot.n = float(NCG); tot.mean = v.x; tot.m2 = v.y; } else tot.merge(float(NCG), v.x, v.y);
+      }
+      mean = tot.mean;
+      rstd = rsqrtf(tot.m2 * inv_n + 1e-5f);
+      ++xr;
+    };
+
+    if (has_res && cluster_id < m_tiles) {        // residual sub-tile of the very first round
+      if (issuer) issue_resid(0, gcol0, cluster_id * GEMM_BM);
+      ++nload[0];
+    }
+    int it = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int row0 = m_blk * GEMM_BM;
+      const int row = row0 + trow;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * NC + grp * NCG;
+      bool keep = true;
+      if (ep.row_range != nullptr && row < M) {
+        const int ch = row / ep.rows_per_chunk;
+        const int rr = row - ch * ep.rows_per_chunk;
+        const int2 rg = ep.row_range[ch];
+        keep = (rr >= rg.x && rr < rg.y);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+
+      // ---------------- pass 1: x_new = resid + keep * alpha * (acc + bias) -> TMEM (+ global for LNM_Y), statistics
+      RowStats st1;
+#pragma unroll 1
+      for (int cc = 0; cc < NR; ++cc, ++q) {
+        const int col0 = gcol0 + cc * 32;
+        const uint32_t slot = q & 1u;
+        uint8_t* tile = stg + slot * GEMM_STAGING_BYTES;
+        uint32_t r[32];
+        tmem_ld32(taddr + cc * 32, r);
+        if (has_res) {
+          if (cc + 1 < NR) {                       // next round's residual into the other slot
+            if (issuer) { tma_store_wait_read(); issue_resid(slot ^ 1u, col0 + 32, row0); }
+            ++nload[slot ^ 1u];
+          }
+        } else if (ep.mode == LNM_Y) {
+          acquire_slot();
+        }
+        float4 b[8];
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) b[qd] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + qd);
+        if (has_res) mbar_wait(&rfull[slot], (nload[slot] - 1u) & 1u);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res) {
+            const uint4 xr4 = stage_load16(tile, trow, qd);
+            x = make_float4(__uint_as_float(xr4.x), __uint_as_float(xr4.y), __uint_as_float(xr4.z), __uint_as_float(xr4.w));
+          }
+          v[4 * qd] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd]) + b[qd].x, x.x) : x.x;
+          v[4 * qd + 1] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 1]) + b[qd].y, x.y) : x.y;
+          v[4 * qd + 2] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 2]) + b[qd].z, x.z) : x.z;
+          v[4 * qd + 3] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 3]) + b[qd].w, x.w) : x.w;
+          if (ep.mode == LNM_Y)
+            stage_store16(tile, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
+                                                     __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+        tmem_st32(taddr + cc * 32, r);
+        st1.add32(v);
+        if (ep.mode == LNM_Y) fence_proxy_async();
+        named_bar_sync(bar_id, 128);               // every thread is done with this slot (and with the one reloaded next round)
+        if (ep.mode == LNM_Y && issuer) { tma_store_2d(&tma_x, tile, col0, row0); tma_store_commit(); }
+      }
+      tmem_st_wait();
+      float mean1, rstd1;
+      exchange(st1, mean1, rstd1);
+
+      // ---------------- LNM_XY / LNM_FINAL: x_mid = LN1(x_new) -> TMEM (+ global for LNM_XY), statistics of x_mid
+      float mean2 = 0.f, rstd2 = 1.f;
+      if (ep.mode != LNM_Y) {
+        RowStats st2;
+#pragma unroll 1
+        for (int cc = 0; cc < NR; ++cc) {
+          const int col0 = gcol0 + cc * 32;
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          uint8_t* tile = stg + (q & 1u) * GEMM_STAGING_BYTES;
+          if (ep.mode == LNM_XY) acquire_slot();
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int qd = 0; qd < 8; ++qd) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(ep.ln1_w + col0) + qd);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln1_b + col0) + qd);
+            v[4 * qd] = fmaf((__uint_as_float(r[4 * qd]) - mean1) * rstd1, w.x, bb.x);
+            v[4 * qd + 1] = fmaf((__uint_as_float(r[4 * qd + 1]) - mean1) * rstd1, w.y, bb.y);
+            v[4 * qd + 2] = fmaf((__uint_as_float(r[4 * qd + 2]) - mean1) * rstd1, w.z, bb.z);
+            v[4 * qd + 3] = fmaf((__uint_as_float(r[4 * qd + 3]) - mean1) * rstd1, w.w, bb.w);
+            if (ep.mode == LNM_XY)
+              stage_store16(tile, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
+                                                       __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+          tmem_st32(taddr + cc * 32, r);
+          st2.add32(v);
+          if (ep.mode == LNM_XY) {
+            fence_proxy_async();
+            named_bar_sync(bar_id, 128);
+            if (issuer) { tma_store_2d(&tma_x, tile, col0, row0); tma_store_commit(); }
+            ++q;
+          }
+        }
+        tmem_st_wait();
+        exchange(st2, mean2, rstd2);
+      }
+
+      // ---------------- last pass: the normalised rows.  fp32 (LNM_FINAL only), then bf16
+      const float mean_l = ep.mode == LNM_Y ? mean1 : mean2, rstd_l = ep.mode == LNM_Y ? rstd1 : rstd2;
+      const float* lw = ep.mode == LNM_Y ? ep.ln1_w : ep.ln2_w;
+      const float* lb = ep.mode == LNM_Y ? ep.ln1_b : ep.ln2_b;
+      bool zero = false;
+      if (ep.mode == LNM_Y && ep.row_limit != nullptr && row < M) {
+        const int sq = row / ep.rows_per_seq;
+        zero = (row - sq * ep.rows_per_seq) >= ep.row_limit[sq];
+      }
+      if (ep.mode == LNM_FINAL && ep.store_f32) {
+#pragma unroll 1
+        for (int cc = 0; cc < NR; ++cc, ++q) {
+          const int col0 = gcol0 + cc * 32;
+          uint8_t* tile = stg + (q & 1u) * GEMM_STAGING_BYTES;
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          acquire_slot();
+          tmem_ld_wait();
+#pragma unroll
+          for (int qd = 0; qd < 8; ++qd) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(lw + col0) + qd);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(lb + col0) + qd);
+            stage_store16(tile, trow, qd,
+                          make_uint4(__float_as_uint(fmaf((__uint_as_float(r[4 * qd]) - mean_l) * rstd_l, w.x, bb.x)),
+                                     __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 1]) - mean_l) * rstd_l, w.y, bb.y)),
+                                     __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 2]) - mean_l) * rstd_l, w.z, bb.z)),
+                                     __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 3]) - mean_l) * rstd_l, w.w, bb.w))));
+          }
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (issuer) { tma_store_2d(&tma_x, tile, col0, row0); tma_store_commit(); }
+        }
+      }
+      if (ep.mode != LNM_FINAL || ep.store_bf16) {
+#pragma unroll 1
+        for (int u = 0; u < NR / 2; ++u, ++q) {        // 64 bf16 columns (128 bytes per row) per staging use
+          uint8_t* tile = stg + (q & 1u) * GEMM_STAGING_BYTES;
+          acquire_slot();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int cc = 2 * u + hf;
+            const int col0 = gcol0 + cc * 32;
+            uint32_t r[32];
+            tmem_ld32(taddr + cc * 32, r);
+            float4 w[8], bb[8];
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              w[qd] = __ldg(reinterpret_cast<const float4*>(lw + col0) + qd);
+              bb[qd] = __ldg(reinterpret_cast<const float4*>(lb + col0) + qd);
+            }
+            tmem_ld_wait();
+            uint32_t o[16];
+#pragma unroll
+            for (int qd = 0; qd < 8; ++qd) {
+              const float y0 = fmaf((__uint_as_float(r[4 * qd]) - mean_l) * rstd_l, w[qd].x, bb[qd].x);
+              const float y1 = fmaf((__uint_as_float(r[4 * qd + 1]) - mean_l) * rstd_l, w[qd].y, bb[qd].y);
+              const float y2 = fmaf((__uint_as_float(r[4 * qd + 2]) - mean_l) * rstd_l, w[qd].z, bb[qd].z);
+              const float y3 = fmaf((__uint_as_float(r[4 * qd + 3]) - mean_l) * rstd_l, w[qd].w, bb[qd].w);
+              o[2 * qd] = zero ? 0u : pack_bf16(y0, y1);
+              o[2 * qd + 1] = zero ? 0u : pack_bf16(y2, y3);
+            }
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+              stage_store16(tile, trow, 4 * hf + qd, make_uint4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]));
+          }
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (issuer) { tma_store_2d(&tma_y, tile, gcol0 + 64 * u, row0); tma_store_commit(); }
+        }
+      }
+      // the accumulator (and the x kept in it) is free again
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      // residual sub-tile of the next row block's first round into the slot its first use will take
+      const int next_blk = m_blk + num_clusters;
+      if (has_res && next_blk < m_tiles) {
+        if (issuer) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          issue_resid(q & 1u, gcol0, next_blk * GEMM_BM);
+        }
+        ++nload[q & 1u];
+      }
+    }
+    if (issuer) tma_store_wait_all();            // global writes complete before the CTA exits
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // the peer may still write this CTA's statistics table / signal its barrier
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace cf

@@ -205,6 +205,15 @@ CF_API int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, in
                const float* bias, const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range,
                int rows_per_chunk, void* out, int64_t ldo, float* part_best, float* part_second, int32_t* part_index,
                int variant, void* stream);
+/* Residual GEMM with the following LayerNorm(s) fused into its epilogue (a CTA pair per 128-row block exchanges row statistics
+ * over distributed shared memory): x_new = resid + rowmask * alpha * (A B^T + bias), N = d_model in {256, 512};
+ * mode 1: x_out = x_new, y_out = LN1(x_new) (rows beyond row_limit zeroed); 2: x_out = LN1(x_new), y_out = LN2(x_out);
+ * 3: x_out (fp32, nullable) / y_out (bf16, nullable) = LN2(LN1(x_new)).  Replaces every "x = x + f(norm(x))" step of
+ * encoder_layer.py:190-246 together with the LayerNorm that follows it. */
+CF_API int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias,
+                  const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk, int mode,
+                  const float* ln1_w, const float* ln1_b, const float* ln2_w, const float* ln2_b, float* x_out, int64_t ldx,
+                  void* y_out, int64_t ldy, const int32_t* row_limit, int rows_per_seq, void* stream);
 /* mode 0: y=LN1(x); 1: x<-LN1(x), y=LN2(x); 2: out=LN2(LN1(x)). */
 CF_API int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1, const float* b1,
                     const float* w2, const float* b2, int64_t rows, void* stream);

@@ -392,3 +392,63 @@ def test_frontend_conv0_dw1(impl, d, c, cmvn):
     err = (out.float() - ref).abs().max().item()
     assert err < 5e-2, err
     assert (out.float() - ref).abs().mean().item() < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ residual GEMM + fused LayerNorm(s)
+def _ln_ref(x, w, b):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 512, 512), (1000, 512, 512), (333, 256, 256), (5000, 512, 2048), (40000, 512, 512),
+                                   (777, 256, 2304), (20000, 256, 2048)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("with_resid,with_mask", [(True, False), (True, True), (False, False)])
+def test_gemm_ln_pair_kernel(M, N, K, mode, with_resid, with_mask):
+    """gemm_ln_kernel (CTA pair, row statistics over DSMEM) against fp32 torch: x_new = resid + rowmask * alpha * (A W^T + b)
+    followed by one or two LayerNorms, every output the kernel writes; ragged last row block, row masks, zeroed rows."""
+    L = cflib.load()
+    A = _rand((M, K), 1.0, 1).bfloat16()
+    W = _rand((N, K), 1.0 / math.sqrt(K), 2).bfloat16()
+    bias = _rand((N,), 0.5, 3)
+    resid = (_rand((M, N), 2.0, 4) + 0.7) if with_resid else None       # non-zero row mean: exercises the variance merge
+    alpha = 0.5 if with_resid else math.sqrt(N)
+    w1, b1 = 1.0 + _rand((N,), 0.1, 5), _rand((N,), 0.1, 6)
+    w2, b2 = 1.0 + _rand((N,), 0.1, 7), _rand((N,), 0.1, 8)
+    rpc = 16
+    n_chunks = (M + rpc - 1) // rpc
+    rng = None
+    keep = torch.ones(M, dtype=torch.bool, device=DEV)
+    if with_mask:
+        g = torch.Generator().manual_seed(9)
+        lo = torch.randint(0, 4, (n_chunks,), generator=g)
+        hi = torch.randint(10, rpc + 1, (n_chunks,), generator=g)
+        rng = torch.stack([lo, hi], 1).to(torch.int32).to(DEV)
+        rr = torch.arange(M, device=DEV) % rpc
+        ch = torch.arange(M, device=DEV) // rpc
+        keep = (rr >= rng[ch, 0]) & (rr < rng[ch, 1])
+    rows_per_seq = 50
+    limit = None
+    zero = torch.zeros(M, dtype=torch.bool, device=DEV)
+    if mode == 1 and with_mask:
+        n_seq = (M + rows_per_seq - 1) // rows_per_seq
+        limit = torch.randint(30, rows_per_seq + 1, (n_seq,), generator=torch.Generator().manual_seed(10)).to(torch.int32).to(DEV)
+        zero = (torch.arange(M, device=DEV) % rows_per_seq) >= limit[torch.arange(M, device=DEV) // rows_per_seq]
+    x_out = torch.full((M, N), 7.0, device=DEV)
+    y_out = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    rc = L.cf_op_gemm_ln(_p(A), K, _p(W), K, M, N, K, _p(bias), _p(resid), N if resid is not None else 0, alpha, _p(rng), rpc, mode,
+                         _p(w1), _p(b1), _p(w2), _p(b2), _p(x_out), N, _p(y_out), N, _p(limit), rows_per_seq, _stream())
+    cflib.check(rc, None, "cf_op_gemm_ln")
+    torch.cuda.synchronize()
+    upd = alpha * (A.float() @ W.float().T + bias) * keep.unsqueeze(1)
+    x_new = upd + (resid if resid is not None else 0.0)
+    if mode == 1:
+        want_x, want_y = x_new, _ln_ref(x_new, w1, b1)
+        want_y = want_y * (~zero).unsqueeze(1)
+    elif mode == 2:
+        want_x = _ln_ref(x_new, w1, b1)
+        want_y = _ln_ref(want_x, w2, b2)
+    else:
+        want_x = _ln_ref(_ln_ref(x_new, w1, b1), w2, b2)
+        want_y = want_x
+    assert (x_out - want_x).abs().max().item() < 2e-3 * max(1.0, float(want_x.abs().max()))
+    assert (y_out.float() - want_y).abs().max().item() < 3e-2
