@@ -71,6 +71,8 @@ struct cf_handle {
   PinnedStage stage[4];
   int stage_next = 0;
   cf::KernelTiming timing;
+  // per-handle options (cf_set_option)
+  int opt_fused_layernorm = 1;   // LayerNorms fused into the epilogue of the residual GEMM in front of them (gemm_ln.cuh)
   struct FbankTables { int sr = 0, bins = 0, flen = 0, fshift = 0; float* window = nullptr; float* mel_w = nullptr; int2* mel_rng = nullptr; int* mel_cnt = nullptr; };
   std::vector<FbankTables> fbank_tables;
   // feature-arrival events of the next cf_encode call (cf_encode_feature_events): rows < ev_rows[i] are present once ev[i] fires
@@ -93,6 +95,12 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
   } while (0)
 
 extern "C" long long cf_launch_count(void) { return cf::g_kernel_launches.load(); }
+extern "C" int cf_set_option(cf_handle* h, const char* name, int value) {
+  if (!h || !name) return fail(h, CF_ERR_INVALID, "cf_set_option: null argument");
+  const std::string k(name);
+  if (k == "fused_layernorm") { h->opt_fused_layernorm = value != 0; return CF_OK; }
+  return fail(h, CF_ERR_INVALID, "cf_set_option: unknown option " + k);
+}
 extern "C" int cf_kernel_timing_begin(cf_handle* h, unsigned family_mask) {
   if (!h) return fail(nullptr, CF_ERR_INVALID, "cf_kernel_timing_begin: null handle");
   h->timing.mask = family_mask;
@@ -799,6 +807,20 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.timing = &h->timing; g.family = e.family;
     return launch_gemm(g, h->num_sms, st, &err);
   };
+  // residual GEMM + the LayerNorm(s) that follow it, one kernel (gemm_ln.cuh)
+  struct LnArgs { int mode = LNM_Y; const float* w1 = nullptr; const float* b1 = nullptr; const float* w2 = nullptr;
+                  const float* b2 = nullptr; float* x_out = nullptr; void* y_out = nullptr; bool limit = false; };
+  auto gemm_ln = [&](const void* A, long long lda, const void* B, long long ldb, long long M, int K, const EpiArgs& e,
+                     const LnArgs& q) -> bool {
+    GemmLnLaunch g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = int(M); g.N = d; g.K = K; g.bias = e.bias; g.resid = e.resid;
+    g.ld_resid = e.ld_resid; g.alpha = e.alpha; g.row_range = e.row_range; g.rows_per_chunk = e.rows_per_chunk; g.mode = q.mode;
+    g.ln1_w = q.w1; g.ln1_b = q.b1; g.ln2_w = q.w2; g.ln2_b = q.b2; g.x_out = q.x_out; g.ldx = d; g.y_out = q.y_out; g.ldy = d;
+    g.row_limit = q.limit ? w.seq_limit : nullptr; g.rows_per_seq = q.limit ? p->rows_per_seq : 1;
+    g.timing = &h->timing; g.family = e.family;
+    return launch_gemm_ln(g, h->num_sms, st, &err);
+  };
+  const bool fuse_ln = h->opt_fused_layernorm != 0;
 #define CF_TRY(expr) do { if (!(expr)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err); } while (0)
 
   // ---- front-end: slabs of chunks through conv0+dw1 -> pw1 -> dw2 -> pw2 -> out Linear
@@ -836,6 +858,11 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(gemm(w.a2, d, h->fe_w6, d, (long long)S * c * F3, d, d, EPI_BF16, e2));
       // (xW + b) * sqrt(d)  (subsampling.py:164, embedding.py:198)
       EpiArgs e3; e3.bias = h->fe_bout; e3.out = w.x + (size_t)g0 * c * d; e3.ldo = d; e3.alpha = sqrtf(float(d));
+      if (fuse_ln) {   // + norm_ff_macaron of layer 0
+        LnArgs q; q.mode = LNM_Y; q.w1 = h->layers[0].ln_ffm_w; q.b1 = h->layers[0].ln_ffm_b;
+        q.x_out = w.x + (size_t)g0 * c * d; q.y_out = w.y + (size_t)g0 * c * d;
+        CF_TRY(gemm_ln(w.b2, (long long)F3 * d, h->fe_wout, (long long)F3 * d, (long long)S * c, F3 * d, e3, q));
+      } else
       CF_TRY(gemm(w.b2, (long long)F3 * d, h->fe_wout, (long long)F3 * d, (long long)S * c, d, F3 * d, EPI_F32, e3));
     }
   }
@@ -851,16 +878,19 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     return run_layernorm(mode, d, q, st, &err);
   };
   const bool use_tc = kAttentionTcReady && attention_tc_supported(c, l, r, dk);
-  CF_TRY(ln(0, h->layers[0].ln_ffm_w, h->layers[0].ln_ffm_b, nullptr, nullptr, nullptr, w.y, false));
+  if (!fuse_ln) CF_TRY(ln(0, h->layers[0].ln_ffm_w, h->layers[0].ln_ffm_b, nullptr, nullptr, nullptr, w.y, false));
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = h->layers[i];
     // macaron FFN: x += 0.5 * W2 SiLU(W1 LN(x) + b1) + b2
     { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
       CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
-      CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
+      if (fuse_ln) {
+        LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_mha_w; q.b1 = lw.ln_mha_b; q.x_out = w.x; q.y_out = w.y;
+        CF_TRY(gemm_ln(w.hbuf, F, lw.ffm_w2, F, Mr, F, e, q));
+      } else CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
     // self-attention
-    CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
+    if (!fuse_ln) CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
     if (att_cache && l > 0 && ns == 0) {
       const int tot = l * H * 2 * dk;
       att_cache_import_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<const float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d);
@@ -885,9 +915,12 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk)); a.prescaled = 1;
       CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
     { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
-      CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
+      if (fuse_ln) {
+        LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_conv_w; q.b1 = lw.ln_conv_b; q.x_out = w.x; q.y_out = w.y; q.limit = p->mode == 1;
+        CF_TRY(gemm_ln(w.ctx, d, lw.o_w, d, Mr, d, e, q));
+      } else CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
     // convolution module
-    CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
+    if (!fuse_ln) CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
     if (cnn_cache && ns == 0) { cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo); ++cf::g_kernel_launches; }
     { EpiArgs e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
       CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mr, 2 * d, d, EPI_GLU, e)); }
@@ -904,12 +937,30 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, (long long)w.g_rows, h->num_sms)); }
     { EpiArgs e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       e.row_range = w.out_range; e.rows_per_chunk = c;
-      CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
+      if (fuse_ln) {
+        LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_ff_w; q.b1 = lw.ln_ff_b; q.x_out = w.x; q.y_out = w.y;
+        CF_TRY(gemm_ln(w.z, d, lw.pw2_w, d, Mr, d, e, q));
+      } else CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
     // FFN
-    CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
+    if (!fuse_ln) CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
     { EpiArgs e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
       CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mr, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
+      if (fuse_ln) {
+        LnArgs q;
+        q.w1 = lw.ln_fin_w; q.b1 = lw.ln_fin_b;
+        if (i + 1 < L) {
+          q.mode = LNM_XY; q.w2 = h->layers[i + 1].ln_ffm_w; q.b2 = h->layers[i + 1].ln_ffm_b; q.x_out = w.x; q.y_out = w.y;
+        } else {   // norm_final of the last layer + after_norm (encoder.py:670-671)
+          q.mode = LNM_FINAL; q.w2 = h->after_w; q.b2 = h->after_b;
+          q.x_out = out_dtype == CF_F32 ? static_cast<float*>(out) : nullptr;
+          q.y_out = out_dtype == CF_BF16 ? out : out_bf16;
+        }
+        CF_TRY(gemm_ln(w.hbuf, F, lw.ff_w2, F, Mr, F, e, q));
+        if (i + 1 == L && out_dtype == CF_BF16 && out_bf16 && out_bf16 != out)
+          CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+        continue;
+      }
       CF_TRY(gemm(w.hbuf, F, lw.ff_w2, F, Mr, d, F, EPI_F32, e)); }
     if (i + 1 < L) {
       CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));

@@ -56,6 +56,10 @@ class ChunkFormerEncoderB200:
     def output_size(self) -> int:
         return self._output_size
 
+    def set_option(self, name: str, value: int) -> None:
+        """Per-handle tuning knob of the library (cf_set_option), e.g. "fused_layernorm" 0 / 1 for A/B measurements."""
+        _lib.check(self._L.cf_set_option(self._h, name.encode(), int(value)), self._h, "cf_set_option")
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

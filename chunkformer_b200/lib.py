@@ -30,6 +30,7 @@ SIGNATURES = {
     "cf_encode_feature_events": (c_int, [c_void_p, c_int, POINTER(c_int64), POINTER(c_void_p)]),
     "cf_fbank_num_frames": (c_int64, [c_int64, c_int, c_int, c_int]),
     "cf_fbank": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "cf_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "cf_kernel_timing_begin": (c_int, [c_void_p, ctypes.c_uint]),
     "cf_kernel_timing_end": (c_int, [c_void_p, c_int, POINTER(ctypes.c_double), POINTER(c_int)]),
     "cf_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, POINTER(c_int64)]),

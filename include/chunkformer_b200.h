@@ -75,6 +75,9 @@ CF_API int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_rea
 CF_API int64_t cf_fbank_num_frames(int64_t n_samples, int sample_rate, int frame_length_ms, int frame_shift_ms);
 CF_API int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int sample_rate, int num_mel_bins, int frame_length_ms,
                     int frame_shift_ms, float* out, void* stream);
+/* Per-handle option.  "fused_layernorm" (default 1): the LayerNorm(s) behind every residual GEMM run in that GEMM's epilogue
+ * (0 = stand-alone LayerNorm kernels; kept for A/B measurement, results agree to fp32 rounding). */
+CF_API int cf_set_option(cf_handle* h, const char* name, int value);
 /* Measurement hook (bench.py roofline): CUDA events around every launch of the selected kernel families made by this handle's
  * cf_encode calls, on the launching stream, from cf_kernel_timing_begin until cf_kernel_timing_end(family), which returns the
  * summed device time and the number of launches of that family.  family_mask = OR of (1 << CF_FAMILY_*).  State lives on
