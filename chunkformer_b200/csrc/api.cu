@@ -73,6 +73,7 @@ struct cf_handle {
   cf::KernelTiming timing;
   // per-handle options (cf_set_option)
   int opt_fused_layernorm = 1;   // LayerNorms fused into the epilogue of the residual GEMM in front of them (gemm_ln.cuh)
+  int opt_fused_ffn = 0;         // feed-forward modules as one kernel each, hidden activation kept on chip (ffn_fused.cuh)
   struct FbankTables { int sr = 0, bins = 0, flen = 0, fshift = 0; float* window = nullptr; float* mel_w = nullptr; int2* mel_rng = nullptr; int* mel_cnt = nullptr; };
   std::vector<FbankTables> fbank_tables;
   // feature-arrival events of the next cf_encode call (cf_encode_feature_events): rows < ev_rows[i] are present once ev[i] fires
@@ -99,6 +100,7 @@ extern "C" int cf_set_option(cf_handle* h, const char* name, int value) {
   if (!h || !name) return fail(h, CF_ERR_INVALID, "cf_set_option: null argument");
   const std::string k(name);
   if (k == "fused_layernorm") { h->opt_fused_layernorm = value != 0; return CF_OK; }
+  if (k == "fused_ffn") { h->opt_fused_ffn = value != 0; return CF_OK; }
   return fail(h, CF_ERR_INVALID, "cf_set_option: unknown option " + k);
 }
 extern "C" int cf_kernel_timing_begin(cf_handle* h, unsigned family_mask) {
@@ -821,6 +823,16 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     return launch_gemm_ln(g, h->num_sms, st, &err);
   };
   const bool fuse_ln = h->opt_fused_layernorm != 0;
+  const bool fuse_ffn = fuse_ln && h->opt_fused_ffn != 0 && ffn_fused_supported(d, F);
+  // whole feed-forward module: x <- x + 0.5 * (W2 SiLU(W1 y + b1) + b2) followed by the LayerNorm(s) of `q`
+  auto ffn = [&](const bf16* w1, const float* b1, const bf16* w2, const float* b2, const LnArgs& q) -> bool {
+    FfnLaunch g{};
+    g.Y = w.y; g.ldy_in = d; g.W1 = w1; g.b1 = b1; g.W2 = w2; g.b2 = b2; g.M = int(Mr); g.d = d; g.F = F; g.resid = w.x;
+    g.ld_resid = d; g.alpha = 0.5f; g.mode = q.mode; g.ln1_w = q.w1; g.ln1_b = q.b1; g.ln2_w = q.w2; g.ln2_b = q.b2;
+    g.x_out = q.x_out; g.ldx = d; g.y_out = q.y_out; g.ldy = d;
+    g.timing = &h->timing; g.family = CF_FAMILY_FFN_FUSED;
+    return launch_ffn_fused(g, h->num_sms, st, &err);
+  };
 #define CF_TRY(expr) do { if (!(expr)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err); } while (0)
 
   // ---- front-end: slabs of chunks through conv0+dw1 -> pw1 -> dw2 -> pw2 -> out Linear
@@ -882,6 +894,10 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = h->layers[i];
     // macaron FFN: x += 0.5 * W2 SiLU(W1 LN(x) + b1) + b2
+    if (fuse_ffn) {
+      LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_mha_w; q.b1 = lw.ln_mha_b; q.x_out = w.x; q.y_out = w.y;
+      CF_TRY(ffn(lw.ffm_w1, lw.ffm_b1, lw.ffm_w2, lw.ffm_b2, q));
+    } else {
     { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
       CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
@@ -889,6 +905,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
         LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_mha_w; q.b1 = lw.ln_mha_b; q.x_out = w.x; q.y_out = w.y;
         CF_TRY(gemm_ln(w.hbuf, F, lw.ffm_w2, F, Mr, F, e, q));
       } else CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
+    }
     // self-attention
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
     if (att_cache && l > 0 && ns == 0) {
@@ -943,6 +960,21 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       } else CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
     // FFN
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
+    if (fuse_ffn) {
+      LnArgs q;
+      q.w1 = lw.ln_fin_w; q.b1 = lw.ln_fin_b;
+      if (i + 1 < L) {
+        q.mode = LNM_XY; q.w2 = h->layers[i + 1].ln_ffm_w; q.b2 = h->layers[i + 1].ln_ffm_b; q.x_out = w.x; q.y_out = w.y;
+      } else {   // norm_final of the last layer + after_norm (encoder.py:670-671)
+        q.mode = LNM_FINAL; q.w2 = h->after_w; q.b2 = h->after_b;
+        q.x_out = out_dtype == CF_F32 ? static_cast<float*>(out) : nullptr;
+        q.y_out = out_dtype == CF_BF16 ? out : out_bf16;
+      }
+      CF_TRY(ffn(lw.ff_w1, lw.ff_b1, lw.ff_w2, lw.ff_b2, q));
+      if (i + 1 == L && out_dtype == CF_BF16 && out_bf16 && out_bf16 != out)
+        CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
     { EpiArgs e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
       CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mr, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
@@ -1446,6 +1478,19 @@ extern "C" int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t 
   g.row_limit = row_limit; g.rows_per_seq = rows_per_seq;
   std::string err;
   if (!launch_gemm_ln(g, current_sms(), static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+  return CF_OK;
+}
+
+extern "C" int cf_op_ffn(const void* y_bf16, int64_t ldy_in, const void* w1, const float* b1, const void* w2, const float* b2, int M,
+                         int d, int F, const float* resid, int64_t ld_resid, float alpha, int mode, const float* ln1_w,
+                         const float* ln1_b, const float* ln2_w, const float* ln2_b, float* x_out, int64_t ldx, void* y_out,
+                         int64_t ldy, void* stream) {
+  FfnLaunch g{};
+  g.Y = y_bf16; g.ldy_in = ldy_in; g.W1 = w1; g.b1 = b1; g.W2 = w2; g.b2 = b2; g.M = M; g.d = d; g.F = F; g.resid = resid;
+  g.ld_resid = ld_resid; g.alpha = alpha; g.mode = mode; g.ln1_w = ln1_w; g.ln1_b = ln1_b; g.ln2_w = ln2_w; g.ln2_b = ln2_b;
+  g.x_out = x_out; g.ldx = ldx; g.y_out = y_out; g.ldy = ldy;
+  std::string err;
+  if (!launch_ffn_fused(g, current_sms(), static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
   return CF_OK;
 }
 

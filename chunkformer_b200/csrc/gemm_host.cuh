@@ -12,6 +12,7 @@
 
 #include "gemm.cuh"
 #include "gemm_ln.cuh"
+#include "ffn_fused.cuh"
 
 namespace cf {
 
@@ -288,6 +289,73 @@ inline bool launch_gemm_ln(const GemmLnLaunch& g, int num_sms, cudaStream_t stre
   if (g.N == 256) return launch_gemm_ln_nc<128>(g, num_sms, stream, err);
   if (err) *err = "gemm_ln: N (= d_model) must be 256 or 512";
   return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// fused feed-forward module: w_1 -> SiLU -> w_2 -> residual -> LayerNorm(s) (ffn_fused.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+struct FfnLaunch {
+  const void* Y; long long ldy_in;     // [M, d] bf16 (LayerNorm output feeding the module)
+  const void* W1; const float* b1;     // [F, d] bf16, [F]
+  const void* W2; const float* b2;     // [d, F] bf16, [d]
+  int M, d, F;
+  const float* resid; long long ld_resid;   // fp32 [M, d]
+  float alpha;                         // 0.5 (macaron half-step residual)
+  int mode;                            // GemmLnMode
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  float* x_out; long long ldx;
+  void* y_out; long long ldy;
+  KernelTiming* timing = nullptr; int family = 0;
+};
+
+inline bool ffn_fused_supported(int d, int F) { return (d == 256 || d == 512) && F > 0 && F % FFN_CHUNK == 0; }
+
+template <int NC>
+inline bool launch_ffn_fused_nc(const FfnLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
+  CUtensorMap ty, tw1, tw2, tx, tr, tyo;
+  if (!make_tma_2d_bf16(&ty, g.Y, g.M, g.d, g.ldy_in, GEMM_BM, GEMM_BK, err)) return false;
+  if (!make_tma_2d_bf16(&tw1, g.W1, g.F, g.d, g.d, FFN_HC, GEMM_BK, err)) return false;
+  if (!make_tma_2d_bf16(&tw2, g.W2, g.d, g.F, g.F, NC, GEMM_BK, err)) return false;
+  tx = ty; tr = ty; tyo = ty;
+  if (g.x_out && !make_tma_2d(&tx, g.x_out, true, g.M, uint64_t(g.d), g.ldx, GEMM_BM, 32, err)) return false;
+  if (g.resid && !make_tma_2d(&tr, g.resid, true, g.M, uint64_t(g.d), g.ld_resid, GEMM_BM, 32, err)) return false;
+  if (g.y_out && !make_tma_2d(&tyo, g.y_out, false, g.M, uint64_t(g.d), g.ldy, GEMM_BM, 64, err)) return false;
+  GemmLnParams ep;
+  ep.bias = g.b2; ep.has_resid = g.resid != nullptr; ep.alpha = g.alpha; ep.mode = g.mode;
+  ep.ln1_w = g.ln1_w; ep.ln1_b = g.ln1_b; ep.ln2_w = g.ln2_w; ep.ln2_b = g.ln2_b;
+  ep.store_f32 = g.x_out != nullptr; ep.store_bf16 = g.y_out != nullptr;
+  auto kern = ffn_fused_kernel<NC>;
+  const size_t smem = ffn_smem_bytes<NC>();
+  if (!ensure_smem_optin(kern, smem, err, "ffn_fused")) return false;
+  const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM;
+  if (m_tiles == 0) return true;
+  int clusters = num_sms / 2;
+  if (clusters > m_tiles) clusters = m_tiles;
+  const bool timed = g.timing && g.timing->begin(g.family, stream);
+  kern<<<2 * clusters, GEMM_THREADS, smem, stream>>>(ty, tw1, tw2, tx, tr, tyo, g.M, g.F, g.b1, ep);
+  if (timed) g.timing->end(stream);
+  ++g_kernel_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("ffn_fused launch: ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+inline bool launch_ffn_fused(const FfnLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
+  if (!ffn_fused_supported(g.d, g.F)) { if (err) *err = "ffn_fused: d_model must be 256 or 512 and linear_units a multiple of 256"; return false; }
+  if (g.mode != LNM_Y && g.mode != LNM_XY && g.mode != LNM_FINAL) { if (err) *err = "ffn_fused: unknown mode"; return false; }
+  if (!g.Y || !g.W1 || !g.W2 || !g.b1 || !g.b2 || !g.ln1_w || !g.ln1_b || (g.mode != LNM_Y && (!g.ln2_w || !g.ln2_b)) ||
+      (g.mode != LNM_FINAL && (!g.x_out || !g.y_out)) || (g.mode == LNM_FINAL && !g.x_out && !g.y_out)) {
+    if (err) *err = "ffn_fused: missing operand, output or LayerNorm parameters";
+    return false;
+  }
+  if (g.ldy_in % 8 != 0 || (g.x_out && (g.ldx * 4) % 16 != 0) || (g.resid && (g.ld_resid * 4) % 16 != 0) || (g.y_out && (g.ldy * 2) % 16 != 0)) {
+    if (err) *err = "ffn_fused: leading dimensions must give 16-byte aligned rows";
+    return false;
+  }
+  return g.d == 512 ? launch_ffn_fused_nc<256>(g, num_sms, stream, err) : launch_ffn_fused_nc<128>(g, num_sms, stream, err);
 }
 
 }  // namespace cf

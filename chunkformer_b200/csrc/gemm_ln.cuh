@@ -89,6 +89,254 @@ struct RowStats {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The LayerNorm epilogue of one group of four warps (128 threads = 128 rows, one TMEM lane quadrant per warp) over NCG
+// accumulator columns: shared by gemm_ln_kernel (two groups per CTA, NCG = NC / 2) and ffn_fused_kernel (one group per CTA,
+// NCG = NC).  The group owns two 16 KB staging slots used alternately (`q` counts the uses): residual sub-tiles (128 rows x
+// 32 fp32) land in them by TMA one round ahead, results leave through them by TMA store.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NCG>
+struct LnEpilogue {
+  static constexpr int NR = NCG / 32;   // 32-column rounds per pass
+  // wiring (constant for the kernel)
+  const CUtensorMap* tma_x; const CUtensorMap* tma_r; const CUtensorMap* tma_y;
+  const GemmLnParams* ep;
+  uint8_t* stg;            // this group's two staging slots
+  uint64_t* rfull;         // [2] residual-arrival barriers of the two slots
+  uint64_t* stat_bar;      // [2] statistics barriers (n_part warps-worth of arrivals each: every epilogue warp of both CTAs)
+  float2* s_stat;          // [2 buffers][n_part][128 rows] (mean, M2)
+  int n_part;              // partial statistics per row = epilogue groups per CTA * 2
+  int part_id;             // this group's slot in the table: rank * groups_per_cta + group
+  uint32_t rank;
+  int bar_id, trow, lane, M, n_total;
+  bool issuer;
+  // state
+  uint32_t q = 0;                 // staging uses so far (slot = q & 1)
+  uint32_t nl0 = 0, nl1 = 0;      // residual loads issued into each slot (mbarrier phase bookkeeping, identical in every thread)
+  CF_DEVINL void count_load(uint32_t slot) { if (slot) ++nl1; else ++nl0; }
+  CF_DEVINL uint32_t loads(uint32_t slot) const { return slot ? nl1 : nl0; }
+  uint32_t xr = 0;                // statistics exchanges so far
+
+  // a slot may be rewritten by the threads once the TMA store that last read it (two uses ago) has drained it
+  CF_DEVINL void acquire_slot() {
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    named_bar_sync(bar_id, 128);
+  }
+  CF_DEVINL void issue_resid(uint32_t slot, int col0, int row0) {      // issuer only
+    mbar_arrive_expect_tx(&rfull[slot], GEMM_STAGING_BYTES);
+    tma_load_2d(stg + slot * GEMM_STAGING_BYTES, tma_r, &rfull[slot], col0, row0);
+  }
+  // residual sub-tile of the first round of the row block at row0 into the slot its first use will take
+  CF_DEVINL void prefetch_first(int gcol0, int row0, bool after_stores) {
+    if (!ep->has_resid) return;
+    if (issuer) {
+      if (after_stores) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      issue_resid(q & 1u, gcol0, row0);
+    }
+    count_load(q & 1u);
+  }
+  // per-row statistics over all columns of the row: this thread's partial + the other groups' of both CTAs.
+  // Exchange k uses table / barrier k & 1: an arrival for exchange k + 2 can only be made by a warp that has passed exchange
+  // k + 1, i.e. after every warp of both CTAs has arrived for (and therefore finished reading) exchange k.
+  CF_DEVINL void exchange(const RowStats& mine, float& mean, float& rstd) {
+    const uint32_t buf = xr & 1u;
+    float2* p = s_stat + (buf * uint32_t(n_part) + uint32_t(part_id)) * 128u + trow;
+    *p = make_float2(mine.mean, mine.m2);
+    st_cluster_f32x2(mapa_rank(smem_u32(p), rank ^ 1u), mine.mean, mine.m2);
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive_cluster(mapa_rank(smem_u32(&stat_bar[buf]), rank ^ 1u));
+      mbar_arrive_cluster(mapa_rank(smem_u32(&stat_bar[buf]), rank));
+    }
+    mbar_wait_cluster(&stat_bar[buf], (xr >> 1) & 1u);
+    RowStats tot;
+    for (int sl = 0; sl < n_part; ++sl) {
+      const float2 v = s_stat[(buf * uint32_t(n_part) + sl) * 128u + trow];
+      if (sl == 0) { tot.n = float(NCG); tot.mean = v.x; tot.m2 = v.y; } else tot.merge(float(NCG), v.x, v.y);
+    }
+    mean = tot.mean;
+    rstd = rsqrtf(tot.m2 / float(n_total) + 1e-5f);
+    ++xr;
+  }
+
+  // One 128-row block: the accumulator slab at `taddr` (this thread's TMEM lane, NCG fp32 columns), global columns
+  // [gcol0, gcol0 + NCG), rows [row0, row0 + 128).  next_row0 >= 0: the row block this group handles next (residual prefetch).
+  // The caller waits for the accumulator before and releases it after.
+  CF_DEVINL void tile(uint32_t taddr, int row0, int gcol0, int next_row0) {
+    const GemmLnParams& e = *ep;
+    const bool has_res = e.has_resid != 0;
+    const int row = row0 + trow;
+    bool keep = true;
+    if (e.row_range != nullptr && row < M) {
+      const int ch = row / e.rows_per_chunk;
+      const int rr = row - ch * e.rows_per_chunk;
+      const int2 rg = e.row_range[ch];
+      keep = (rr >= rg.x && rr < rg.y);
+    }
+    // ---------------- pass 1: x_new = resid + keep * alpha * (acc + bias) -> TMEM (+ global for LNM_Y), statistics
+    RowStats st1;
+#pragma unroll 1
+    for (int cc = 0; cc < NR; ++cc, ++q) {
+      const int col0 = gcol0 + cc * 32;
+      const uint32_t slot = q & 1u;
+      uint8_t* tl = stg + slot * GEMM_STAGING_BYTES;
+      uint32_t r[32];
+      tmem_ld32(taddr + cc * 32, r);
+      if (has_res) {
+        if (cc + 1 < NR) {                       // next round's residual into the other slot
+          if (issuer) { tma_store_wait_read(); issue_resid(slot ^ 1u, col0 + 32, row0); }
+          count_load(slot ^ 1u);
+        }
+      } else if (e.mode == LNM_Y) {
+        acquire_slot();
+      }
+      float4 b[8];
+#pragma unroll
+      for (int qd = 0; qd < 8; ++qd) b[qd] = __ldg(reinterpret_cast<const float4*>(e.bias + col0) + qd);
+      if (has_res) mbar_wait(&rfull[slot], (loads(slot) - 1u) & 1u);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int qd = 0; qd < 8; ++qd) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res) {
+          const uint4 xr4 = stage_load16(tl, trow, qd);
+          x = make_float4(__uint_as_float(xr4.x), __uint_as_float(xr4.y), __uint_as_float(xr4.z), __uint_as_float(xr4.w));
+        }
+        v[4 * qd] = keep ? fmaf(e.alpha, __uint_as_float(r[4 * qd]) + b[qd].x, x.x) : x.x;
+        v[4 * qd + 1] = keep ? fmaf(e.alpha, __uint_as_float(r[4 * qd + 1]) + b[qd].y, x.y) : x.y;
+        v[4 * qd + 2] = keep ? fmaf(e.alpha, __uint_as_float(r[4 * qd + 2]) + b[qd].z, x.z) : x.z;
+        v[4 * qd + 3] = keep ? fmaf(e.alpha, __uint_as_float(r[4 * qd + 3]) + b[qd].w, x.w) : x.w;
+        if (e.mode == LNM_Y)
+          stage_store16(tl, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
+                                                 __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+      tmem_st32(taddr + cc * 32, r);
+      st1.add32(v);
+      if (e.mode == LNM_Y) fence_proxy_async();
+      named_bar_sync(bar_id, 128);               // every thread is done with this slot (and with the one reloaded next round)
+      if (e.mode == LNM_Y && issuer) { tma_store_2d(tma_x, tl, col0, row0); tma_store_commit(); }
+    }
+    tmem_st_wait();
+    float mean1, rstd1;
+    exchange(st1, mean1, rstd1);
+
+    // ---------------- LNM_XY / LNM_FINAL: x_mid = LN1(x_new) -> TMEM (+ global for LNM_XY), statistics of x_mid
+    float mean2 = 0.f, rstd2 = 1.f;
+    if (e.mode != LNM_Y) {
+      RowStats st2;
+#pragma unroll 1
+      for (int cc = 0; cc < NR; ++cc) {
+        const int col0 = gcol0 + cc * 32;
+        uint32_t r[32];
+        tmem_ld32(taddr + cc * 32, r);
+        uint8_t* tl = stg + (q & 1u) * GEMM_STAGING_BYTES;
+        if (e.mode == LNM_XY) acquire_slot();
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(e.ln1_w + col0) + qd);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(e.ln1_b + col0) + qd);
+          v[4 * qd] = fmaf((__uint_as_float(r[4 * qd]) - mean1) * rstd1, w.x, bb.x);
+          v[4 * qd + 1] = fmaf((__uint_as_float(r[4 * qd + 1]) - mean1) * rstd1, w.y, bb.y);
+          v[4 * qd + 2] = fmaf((__uint_as_float(r[4 * qd + 2]) - mean1) * rstd1, w.z, bb.z);
+          v[4 * qd + 3] = fmaf((__uint_as_float(r[4 * qd + 3]) - mean1) * rstd1, w.w, bb.w);
+          if (e.mode == LNM_XY)
+            stage_store16(tl, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
+                                                   __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+        tmem_st32(taddr + cc * 32, r);
+        st2.add32(v);
+        if (e.mode == LNM_XY) {
+          fence_proxy_async();
+          named_bar_sync(bar_id, 128);
+          if (issuer) { tma_store_2d(tma_x, tl, col0, row0); tma_store_commit(); }
+          ++q;
+        }
+      }
+      tmem_st_wait();
+      exchange(st2, mean2, rstd2);
+    }
+
+    // ---------------- last pass: the normalised rows.  fp32 (LNM_FINAL only), then bf16
+    const float mean_l = e.mode == LNM_Y ? mean1 : mean2, rstd_l = e.mode == LNM_Y ? rstd1 : rstd2;
+    const float* lw = e.mode == LNM_Y ? e.ln1_w : e.ln2_w;
+    const float* lb = e.mode == LNM_Y ? e.ln1_b : e.ln2_b;
+    bool zero = false;
+    if (e.mode == LNM_Y && e.row_limit != nullptr && row < M) {
+      const int sq = row / e.rows_per_seq;
+      zero = (row - sq * e.rows_per_seq) >= e.row_limit[sq];
+    }
+    if (e.mode == LNM_FINAL && e.store_f32) {
+#pragma unroll 1
+      for (int cc = 0; cc < NR; ++cc, ++q) {
+        const int col0 = gcol0 + cc * 32;
+        uint8_t* tl = stg + (q & 1u) * GEMM_STAGING_BYTES;
+        uint32_t r[32];
+        tmem_ld32(taddr + cc * 32, r);
+        acquire_slot();
+        tmem_ld_wait();
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(lw + col0) + qd);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(lb + col0) + qd);
+          stage_store16(tl, trow, qd,
+                        make_uint4(__float_as_uint(fmaf((__uint_as_float(r[4 * qd]) - mean_l) * rstd_l, w.x, bb.x)),
+                                   __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 1]) - mean_l) * rstd_l, w.y, bb.y)),
+                                   __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 2]) - mean_l) * rstd_l, w.z, bb.z)),
+                                   __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 3]) - mean_l) * rstd_l, w.w, bb.w))));
+        }
+        fence_proxy_async();
+        named_bar_sync(bar_id, 128);
+        if (issuer) { tma_store_2d(tma_x, tl, col0, row0); tma_store_commit(); }
+      }
+    }
+    if (e.mode != LNM_FINAL || e.store_bf16) {
+#pragma unroll 1
+      for (int u = 0; u < NR / 2; ++u, ++q) {        // 64 bf16 columns (128 bytes per row) per staging use
+        uint8_t* tl = stg + (q & 1u) * GEMM_STAGING_BYTES;
+        acquire_slot();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int cc = 2 * u + hf;
+          const int col0 = gcol0 + cc * 32;
+          uint32_t r[32];
+          tmem_ld32(taddr + cc * 32, r);
+          float4 w[8], bb[8];
+#pragma unroll
+          for (int qd = 0; qd < 8; ++qd) {
+            w[qd] = __ldg(reinterpret_cast<const float4*>(lw + col0) + qd);
+            bb[qd] = __ldg(reinterpret_cast<const float4*>(lb + col0) + qd);
+          }
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int qd = 0; qd < 8; ++qd) {
+            const float y0 = fmaf((__uint_as_float(r[4 * qd]) - mean_l) * rstd_l, w[qd].x, bb[qd].x);
+            const float y1 = fmaf((__uint_as_float(r[4 * qd + 1]) - mean_l) * rstd_l, w[qd].y, bb[qd].y);
+            const float y2 = fmaf((__uint_as_float(r[4 * qd + 2]) - mean_l) * rstd_l, w[qd].z, bb[qd].z);
+            const float y3 = fmaf((__uint_as_float(r[4 * qd + 3]) - mean_l) * rstd_l, w[qd].w, bb[qd].w);
+            o[2 * qd] = zero ? 0u : pack_bf16(y0, y1);
+            o[2 * qd + 1] = zero ? 0u : pack_bf16(y2, y3);
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd)
+            stage_store16(tl, trow, 4 * hf + qd, make_uint4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]));
+        }
+        fence_proxy_async();
+        named_bar_sync(bar_id, 128);
+        if (issuer) { tma_store_2d(tma_y, tl, gcol0 + 64 * u, row0); tma_store_commit(); }
+      }
+    }
+    (void)next_row0;
+  }
+};
+
 template <int NC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -190,248 +438,28 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int ew = warp - 2;
     const int quad = warp & 3;
     const int grp = ew >> 2;
-    const bool issuer = ((ew & 3) == 0) && lane == 0;
-    const int bar_id = 1 + grp;
-    const int trow = quad * 32 + lane;
-    uint8_t* stg = sStage + grp * 2 * GEMM_STAGING_BYTES;
-    uint64_t* rfull = &res_full[grp * 2];
+    LnEpilogue<NCG> le;
+    le.tma_x = &tma_x; le.tma_r = &tma_r; le.tma_y = &tma_y; le.ep = &ep;
+    le.stg = sStage + grp * 2 * GEMM_STAGING_BYTES; le.rfull = &res_full[grp * 2]; le.stat_bar = stat_bar; le.s_stat = s_stat;
+    le.n_part = 4; le.part_id = int(rank) * 2 + grp; le.rank = rank; le.bar_id = 1 + grp; le.trow = quad * 32 + lane;
+    le.lane = lane; le.M = M; le.n_total = N; le.issuer = ((ew & 3) == 0) && lane == 0;
     const int gcol0 = int(rank) * NC + grp * NCG;       // first global column of this group's slab
-    const bool has_res = ep.has_resid != 0;
-    uint32_t q = 0;                 // staging uses of this group so far (slot = q & 1)
-    uint32_t nload[2] = {0u, 0u};   // residual loads issued into each slot (mbarrier phase bookkeeping, identical in every thread)
-    uint32_t xr = 0;                // statistics exchanges so far
-    const float inv_n = 1.0f / float(N);
-
-    // a slot may be rewritten by the threads once the TMA store that last read it (two uses ago) has drained it
-    auto acquire_slot = [&]() {
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      named_bar_sync(bar_id, 128);
-    };
-    auto issue_resid = [&](uint32_t slot, int col0, int row0) {      // issuer only
-      mbar_arrive_expect_tx(&rfull[slot], GEMM_STAGING_BYTES);
-      tma_load_2d(stg + slot * GEMM_STAGING_BYTES, &tma_r, &rfull[slot], col0, row0);
-    };
-    // per-row statistics over all N columns: this thread's partial + the other group's + the peer CTA's two
-    auto exchange = [&](const RowStats& mine, float& mean, float& rstd) {
-      const uint32_t buf = xr & 1u;
-      const uint32_t slot_id = rank * 2u + uint32_t(grp);
-      float2* p = s_stat + (buf * 4u + slot_id) * 128u + trow;
-      *p = make_float2(mine.mean, mine.m2);
-      st_cluster_f32x2(mapa_rank(smem_u32(p), rank ^ 1u), mine.mean, mine.m2);
-      __syncwarp();
-      // exchange k uses table / barrier k & 1: an arrival for exchange k + 2 can only be made by a warp that has passed exchange
-      // k + 1, i.e. after every warp of both CTAs has arrived for (and therefore finished reading) exchange k
-      if (lane == 0) {
-        mbar_arrive_cluster(mapa_rank(smem_u32(&stat_bar[buf]), rank ^ 1u));
-        mbar_arrive_cluster(mapa_rank(smem_u32(&stat_bar[buf]), rank));
-      }
-      mbar_wait_cluster(&stat_bar[buf], (xr >> 1) & 1u);
-      RowStats tot;
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl) {
-        const float2 v = s_stat[(buf * 4u + sl) * 128u + trow];
-        if (sl == 0) { tot.n = float(NCG); tot.mean = v.x; tot.m2 = v.y; } else tot.merge(float(NCG), v.x, v.y);
-      }
-      mean = tot.mean;
-      rstd = rsqrtf(tot.m2 * inv_n + 1e-5f);
-      ++xr;
-    };
-
-    if (has_res && cluster_id < m_tiles) {        // residual sub-tile of the very first round
-      if (issuer) issue_resid(0, gcol0, cluster_id * GEMM_BM);
-      ++nload[0];
-    }
+    if (cluster_id < m_tiles) le.prefetch_first(gcol0, cluster_id * GEMM_BM, false);
     int it = 0;
     for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int row0 = m_blk * GEMM_BM;
-      const int row = row0 + trow;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * NC + grp * NCG;
-      bool keep = true;
-      if (ep.row_range != nullptr && row < M) {
-        const int ch = row / ep.rows_per_chunk;
-        const int rr = row - ch * ep.rows_per_chunk;
-        const int2 rg = ep.row_range[ch];
-        keep = (rr >= rg.x && rr < rg.y);
-      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-
-      // ---------------- pass 1: x_new = resid + keep * alpha * (acc + bias) -> TMEM (+ global for LNM_Y), statistics
-      RowStats st1;
-#pragma unroll 1
-      for (int cc = 0; cc < NR; ++cc, ++q) {
-        const int col0 = gcol0 + cc * 32;
-        const uint32_t slot = q & 1u;
-        uint8_t* tile = stg + slot * GEMM_STAGING_BYTES;
-        uint32_t r[32];
-        tmem_ld32(taddr + cc * 32, r);
-        if (has_res) {
-          if (cc + 1 < NR) {                       // next round's residual into the other slot
-            if (issuer) { tma_store_wait_read(); issue_resid(slot ^ 1u, col0 + 32, row0); }
-            ++nload[slot ^ 1u];
-          }
-        } else if (ep.mode == LNM_Y) {
-          acquire_slot();
-        }
-        float4 b[8];
-#pragma unroll
-        for (int qd = 0; qd < 8; ++qd) b[qd] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + qd);
-        if (has_res) mbar_wait(&rfull[slot], (nload[slot] - 1u) & 1u);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int qd = 0; qd < 8; ++qd) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res) {
-            const uint4 xr4 = stage_load16(tile, trow, qd);
-            x = make_float4(__uint_as_float(xr4.x), __uint_as_float(xr4.y), __uint_as_float(xr4.z), __uint_as_float(xr4.w));
-          }
-          v[4 * qd] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd]) + b[qd].x, x.x) : x.x;
-          v[4 * qd + 1] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 1]) + b[qd].y, x.y) : x.y;
-          v[4 * qd + 2] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 2]) + b[qd].z, x.z) : x.z;
-          v[4 * qd + 3] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 3]) + b[qd].w, x.w) : x.w;
-          if (ep.mode == LNM_Y)
-            stage_store16(tile, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
-                                                     __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-        tmem_st32(taddr + cc * 32, r);
-        st1.add32(v);
-        if (ep.mode == LNM_Y) fence_proxy_async();
-        named_bar_sync(bar_id, 128);               // every thread is done with this slot (and with the one reloaded next round)
-        if (ep.mode == LNM_Y && issuer) { tma_store_2d(&tma_x, tile, col0, row0); tma_store_commit(); }
-      }
-      tmem_st_wait();
-      float mean1, rstd1;
-      exchange(st1, mean1, rstd1);
-
-      // ---------------- LNM_XY / LNM_FINAL: x_mid = LN1(x_new) -> TMEM (+ global for LNM_XY), statistics of x_mid
-      float mean2 = 0.f, rstd2 = 1.f;
-      if (ep.mode != LNM_Y) {
-        RowStats st2;
-#pragma unroll 1
-        for (int cc = 0; cc < NR; ++cc) {
-          const int col0 = gcol0 + cc * 32;
-          uint32_t r[32];
-          tmem_ld32(taddr + cc * 32, r);
-          uint8_t* tile = stg + (q & 1u) * GEMM_STAGING_BYTES;
-          if (ep.mode == LNM_XY) acquire_slot();
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int qd = 0; qd < 8; ++qd) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(ep.ln1_w + col0) + qd);
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.ln1_b + col0) + qd);
-            v[4 * qd] = fmaf((__uint_as_float(r[4 * qd]) - mean1) * rstd1, w.x, bb.x);
-            v[4 * qd + 1] = fmaf((__uint_as_float(r[4 * qd + 1]) - mean1) * rstd1, w.y, bb.y);
-            v[4 * qd + 2] = fmaf((__uint_as_float(r[4 * qd + 2]) - mean1) * rstd1, w.z, bb.z);
-            v[4 * qd + 3] = fmaf((__uint_as_float(r[4 * qd + 3]) - mean1) * rstd1, w.w, bb.w);
-            if (ep.mode == LNM_XY)
-              stage_store16(tile, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
-                                                       __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-          tmem_st32(taddr + cc * 32, r);
-          st2.add32(v);
-          if (ep.mode == LNM_XY) {
-            fence_proxy_async();
-            named_bar_sync(bar_id, 128);
-            if (issuer) { tma_store_2d(&tma_x, tile, col0, row0); tma_store_commit(); }
-            ++q;
-          }
-        }
-        tmem_st_wait();
-        exchange(st2, mean2, rstd2);
-      }
-
-      // ---------------- last pass: the normalised rows.  fp32 (LNM_FINAL only), then bf16
-      const float mean_l = ep.mode == LNM_Y ? mean1 : mean2, rstd_l = ep.mode == LNM_Y ? rstd1 : rstd2;
-      const float* lw = ep.mode == LNM_Y ? ep.ln1_w : ep.ln2_w;
-      const float* lb = ep.mode == LNM_Y ? ep.ln1_b : ep.ln2_b;
-      bool zero = false;
-      if (ep.mode == LNM_Y && ep.row_limit != nullptr && row < M) {
-        const int sq = row / ep.rows_per_seq;
-        zero = (row - sq * ep.rows_per_seq) >= ep.row_limit[sq];
-      }
-      if (ep.mode == LNM_FINAL && ep.store_f32) {
-#pragma unroll 1
-        for (int cc = 0; cc < NR; ++cc, ++q) {
-          const int col0 = gcol0 + cc * 32;
-          uint8_t* tile = stg + (q & 1u) * GEMM_STAGING_BYTES;
-          uint32_t r[32];
-          tmem_ld32(taddr + cc * 32, r);
-          acquire_slot();
-          tmem_ld_wait();
-#pragma unroll
-          for (int qd = 0; qd < 8; ++qd) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(lw + col0) + qd);
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(lb + col0) + qd);
-            stage_store16(tile, trow, qd,
-                          make_uint4(__float_as_uint(fmaf((__uint_as_float(r[4 * qd]) - mean_l) * rstd_l, w.x, bb.x)),
-                                     __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 1]) - mean_l) * rstd_l, w.y, bb.y)),
-                                     __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 2]) - mean_l) * rstd_l, w.z, bb.z)),
-                                     __float_as_uint(fmaf((__uint_as_float(r[4 * qd + 3]) - mean_l) * rstd_l, w.w, bb.w))));
-          }
-          fence_proxy_async();
-          named_bar_sync(bar_id, 128);
-          if (issuer) { tma_store_2d(&tma_x, tile, col0, row0); tma_store_commit(); }
-        }
-      }
-      if (ep.mode != LNM_FINAL || ep.store_bf16) {
-#pragma unroll 1
-        for (int u = 0; u < NR / 2; ++u, ++q) {        // 64 bf16 columns (128 bytes per row) per staging use
-          uint8_t* tile = stg + (q & 1u) * GEMM_STAGING_BYTES;
-          acquire_slot();
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int cc = 2 * u + hf;
-            const int col0 = gcol0 + cc * 32;
-            uint32_t r[32];
-            tmem_ld32(taddr + cc * 32, r);
-            float4 w[8], bb[8];
-#pragma unroll
-            for (int qd = 0; qd < 8; ++qd) {
-              w[qd] = __ldg(reinterpret_cast<const float4*>(lw + col0) + qd);
-              bb[qd] = __ldg(reinterpret_cast<const float4*>(lb + col0) + qd);
-            }
-            tmem_ld_wait();
-            uint32_t o[16];
-#pragma unroll
-            for (int qd = 0; qd < 8; ++qd) {
-              const float y0 = fmaf((__uint_as_float(r[4 * qd]) - mean_l) * rstd_l, w[qd].x, bb[qd].x);
-              const float y1 = fmaf((__uint_as_float(r[4 * qd + 1]) - mean_l) * rstd_l, w[qd].y, bb[qd].y);
-              const float y2 = fmaf((__uint_as_float(r[4 * qd + 2]) - mean_l) * rstd_l, w[qd].z, bb[qd].z);
-              const float y3 = fmaf((__uint_as_float(r[4 * qd + 3]) - mean_l) * rstd_l, w[qd].w, bb[qd].w);
-              o[2 * qd] = zero ? 0u : pack_bf16(y0, y1);
-              o[2 * qd + 1] = zero ? 0u : pack_bf16(y2, y3);
-            }
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              stage_store16(tile, trow, 4 * hf + qd, make_uint4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]));
-          }
-          fence_proxy_async();
-          named_bar_sync(bar_id, 128);
-          if (issuer) { tma_store_2d(&tma_y, tile, gcol0 + 64 * u, row0); tma_store_commit(); }
-        }
-      }
+      const int next_blk = m_blk + num_clusters;
+      le.tile(taddr, m_blk * GEMM_BM, gcol0, next_blk < m_tiles ? next_blk * GEMM_BM : -1);
       // the accumulator (and the x kept in it) is free again
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      // residual sub-tile of the next row block's first round into the slot its first use will take
-      const int next_blk = m_blk + num_clusters;
-      if (has_res && next_blk < m_tiles) {
-        if (issuer) {
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          issue_resid(q & 1u, gcol0, next_blk * GEMM_BM);
-        }
-        ++nload[q & 1u];
-      }
+      if (next_blk < m_tiles) le.prefetch_first(gcol0, next_blk * GEMM_BM, true);
     }
-    if (issuer) tma_store_wait_all();            // global writes complete before the CTA exits
+    if (le.issuer) tma_store_wait_all();            // global writes complete before the CTA exits
   }
 
   tc_fence_before();

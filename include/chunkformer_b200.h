@@ -76,7 +76,9 @@ CF_API int64_t cf_fbank_num_frames(int64_t n_samples, int sample_rate, int frame
 CF_API int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int sample_rate, int num_mel_bins, int frame_length_ms,
                     int frame_shift_ms, float* out, void* stream);
 /* Per-handle option.  "fused_layernorm" (default 1): the LayerNorm(s) behind every residual GEMM run in that GEMM's epilogue
- * (0 = stand-alone LayerNorm kernels; kept for A/B measurement, results agree to fp32 rounding). */
+ * (0 = stand-alone LayerNorm kernels; kept for A/B measurement).  "fused_ffn" (default 1, needs fused_layernorm): every
+ * feed-forward module runs as one kernel that keeps the hidden activation on chip (0 = w_1 GEMM, hidden activation through
+ * global memory, w_2 GEMM). */
 CF_API int cf_set_option(cf_handle* h, const char* name, int value);
 /* Measurement hook (bench.py roofline): CUDA events around every launch of the selected kernel families made by this handle's
  * cf_encode calls, on the launching stream, from cf_kernel_timing_begin until cf_kernel_timing_end(family), which returns the
@@ -217,6 +219,13 @@ CF_API int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t ldb,
                   const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk, int mode,
                   const float* ln1_w, const float* ln1_b, const float* ln2_w, const float* ln2_b, float* x_out, int64_t ldx,
                   void* y_out, int64_t ldy, const int32_t* row_limit, int rows_per_seq, void* stream);
+/* Whole feed-forward module in one kernel (positionwise_feed_forward.py:51-60 + encoder_layer.py:190-199 / 236-246):
+ * x_new = resid + alpha * (W2 SiLU(W1 y + b1) + b2), then the LayerNorm modes of cf_op_gemm_ln.  The [M, F] hidden activation
+ * stays on chip (a CTA pair per 128-row block exchanges SiLU tiles over distributed shared memory).  d in {256, 512},
+ * F % 256 == 0; w1 [F, d], w2 [d, F] bf16 row-major (nn.Linear layout). */
+CF_API int cf_op_ffn(const void* y_bf16, int64_t ldy_in, const void* w1, const float* b1, const void* w2, const float* b2, int M,
+              int d, int F, const float* resid, int64_t ld_resid, float alpha, int mode, const float* ln1_w, const float* ln1_b,
+              const float* ln2_w, const float* ln2_b, float* x_out, int64_t ldx, void* y_out, int64_t ldy, void* stream);
 /* mode 0: y=LN1(x); 1: x<-LN1(x), y=LN2(x); 2: out=LN2(LN1(x)). */
 CF_API int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1, const float* b1,
                     const float* w2, const float* b2, int64_t rows, void* stream);

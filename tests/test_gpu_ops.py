@@ -452,3 +452,39 @@ def test_gemm_ln_pair_kernel(M, N, K, mode, with_resid, with_mask):
         want_y = want_x
     assert (x_out - want_x).abs().max().item() < 2e-3 * max(1.0, float(want_x.abs().max()))
     assert (y_out.float() - want_y).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("M,d,F", [(128, 512, 2048), (1000, 512, 2048), (333, 256, 2048), (20000, 512, 2048), (5000, 256, 512),
+                                   (40001, 512, 1024)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_ffn_fused_kernel(M, d, F, mode):
+    """ffn_fused_kernel (w_1 -> SiLU -> w_2 -> residual -> LayerNorm(s) in one kernel, hidden activation exchanged between the
+    two CTAs of a cluster over DSMEM) against fp32 torch with the hidden activation rounded to bf16 as the kernel does."""
+    L = cflib.load()
+    y = _rand((M, d), 1.0, 1).bfloat16()
+    W1 = _rand((F, d), 1.0 / math.sqrt(d), 2).bfloat16()
+    b1 = _rand((F,), 0.3, 3)
+    W2 = _rand((d, F), 1.0 / math.sqrt(F), 4).bfloat16()
+    b2 = _rand((d,), 0.3, 5)
+    resid = _rand((M, d), 2.0, 6) + 0.5
+    w1, bb1 = 1.0 + _rand((d,), 0.1, 7), _rand((d,), 0.1, 8)
+    w2, bb2 = 1.0 + _rand((d,), 0.1, 9), _rand((d,), 0.1, 10)
+    x_out = torch.full((M, d), 7.0, device=DEV)
+    y_out = torch.full((M, d), 7.0, device=DEV, dtype=torch.bfloat16)
+    rc = L.cf_op_ffn(_p(y), d, _p(W1), _p(b1), _p(W2), _p(b2), M, d, F, _p(resid), d, 0.5, mode, _p(w1), _p(bb1), _p(w2), _p(bb2),
+                     _p(x_out), d, _p(y_out), d, _stream())
+    cflib.check(rc, None, "cf_op_ffn")
+    torch.cuda.synchronize()
+    hid = torch.nn.functional.silu(y.float() @ W1.float().T + b1).bfloat16().float()
+    x_new = resid + 0.5 * (hid @ W2.float().T + b2)
+    if mode == 1:
+        want_x, want_y = x_new, _ln_ref(x_new, w1, bb1)
+    elif mode == 2:
+        want_x = _ln_ref(x_new, w1, bb1)
+        want_y = _ln_ref(want_x, w2, bb2)
+    else:
+        want_x = _ln_ref(_ln_ref(x_new, w1, bb1), w2, bb2)
+        want_y = want_x
+    # tanh.approx SiLU + bf16 hidden activation: a few 1e-3 on O(1) outputs
+    assert (x_out - want_x).abs().max().item() < 1e-2 * max(1.0, float(want_x.abs().max()))
+    assert (y_out.float() - want_y).abs().max().item() < 4e-2

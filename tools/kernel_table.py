@@ -11,8 +11,12 @@ from chunkformer_b200.synth import masked_batch_lengths, synth_fbank, synth_stat
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--out", default="")
+ap.add_argument("--opt", action="append", default=[], help="library option name=value (cf_set_option), repeatable")
 a = ap.parse_args()
 enc = ChunkFormerEncoderB200(CTC_LARGE, synth_state_dict(CTC_LARGE, 0), "cuda:0")
+for kv in a.opt:
+    k, v = kv.split("=")
+    enc.set_option(k, int(v))
 lens = masked_batch_lengths(a.scale)
 feats = torch.cat([synth_fbank(t, seed=1 + k) for k, t in enumerate(lens)], 0).cuda()
 def step():
