@@ -173,6 +173,12 @@ struct LnEpilogue {
       const int2 rg = e.row_range[ch];
       keep = (rr >= rg.x && rr < rg.y);
     }
+    // the residual slab of the row block this group handles next -> L2 now, so that its sub-tile loads (issued only one round
+    // ahead, there are two staging slots) are L2 hits instead of HBM round trips
+    if (issuer && has_res && next_row0 >= 0) {
+#pragma unroll 1
+      for (int cc = 0; cc < NR; ++cc) tma_prefetch_2d(tma_r, gcol0 + cc * 32, next_row0);
+    }
     // ---------------- pass 1: x_new = resid + keep * alpha * (acc + bias) -> TMEM (+ global for LNM_Y), statistics
     RowStats st1;
 #pragma unroll 1
@@ -333,7 +339,6 @@ struct LnEpilogue {
         if (issuer) { tma_store_2d(tma_y, tl, gcol0 + 64 * u, row0); tma_store_commit(); }
       }
     }
-    (void)next_row0;
   }
 };
 

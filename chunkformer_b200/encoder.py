@@ -18,6 +18,17 @@ from .plan import Plan
 _EMPTY = (0,)
 
 
+class UploadedFeatures:
+    """A batch of utterances on its way to the device (ChunkFormerEncoderB200.upload_async): the flat feature buffer, the
+    utterance lengths and the copy events.  Pass it to forward_parallel_chunk in place of the list of tensors."""
+
+    def __init__(self, flat, lens, events, rows_ready):
+        self.flat, self.lens, self.events, self.rows_ready = flat, lens, events, rows_ready
+
+    def __len__(self):
+        return len(self.lens)
+
+
 class ChunkFormerEncoderB200:
     """B200 encoder + CTC head built from a reference-layout state_dict (keys `encoder.*`, `ctc.ctc_lo.*`)."""
 
@@ -79,29 +90,31 @@ class ChunkFormerEncoderB200:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def _flat_feats(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
-        """Ragged utterances -> one flat device buffer [sum T_i, feat].
+    def upload_async(self, xs: Sequence[torch.Tensor], lens: Optional[Sequence[int]] = None) -> UploadedFeatures:
+        """Start copying ragged utterances into one flat device buffer [sum T_i, feat] and return at once.
 
-        Every tensor (host or device) is copied on a side stream in pieces of about 32 MB, each followed by an event that is
-        handed to the library (cf_encode_feature_events): the front-end of the following cf_encode starts on the first rows
-        while the rest of the batch is still crossing PCIe (pinned host tensors copy asynchronously; pageable ones are
-        staged by the driver).  The caller validates shapes BEFORE calling this: the events armed here are consumed by the
-        next cf_encode."""
-        total = sum(int(x.shape[0]) for x in xs)
+        The copies run on a side stream, in pieces of about 32 MB, each followed by an event; forward_parallel_chunk hands the
+        events to the library (cf_encode_feature_events), whose front-end waits only for the rows each slab of chunks reads, so
+        the encoder starts on the first rows while the rest is still crossing PCIe (pinned host tensors copy asynchronously;
+        pageable ones are staged by the driver).  The buffer is allocated from the side stream's pool, so the upload of the
+        NEXT batch does not wait for the encoder pass of the current one: a decoding loop calls upload_async for batch k + 1
+        before forward_parallel_chunk for batch k and the host-to-device copy disappears behind the compute (what the
+        reference's blocking xs.to(device), chunkformer_model.py:395-401, cannot do)."""
+        lens = [int(x.shape[0]) for x in xs] if lens is None else [int(t) for t in lens]
         F = self.geo.feat_dim
-        flat = torch.empty((total, F), dtype=torch.float32, device=self.device)
-        cur = torch.cuda.current_stream(self.device)
+        for x, t in zip(xs, lens):
+            if x.dim() != 2 or x.shape[1] != F or x.shape[0] < t or t < 0:
+                raise ValueError("every utterance must be (T_i, feat_dim) with T_i >= xs_origin_lens[i] >= 0")
+        total = sum(lens)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         cs = self._copy_stream
-        cs.wait_stream(cur)                      # the block may have been used by work queued earlier on this stream
-        flat.record_stream(cs)
         piece = max(1, (32 << 20) // (4 * F))    # rows per piece
         rows_ready, events = [], []
         row = 0
         with torch.cuda.stream(cs):
-            for x in xs:
-                t = int(x.shape[0])
+            flat = torch.empty((total, F), dtype=torch.float32, device=self.device)   # a block of the copy stream's pool
+            for x, t in zip(xs, lens):
                 if x.dtype != torch.float32:
                     x = x.float()
                 for a in range(0, t, piece):
@@ -112,13 +125,19 @@ class ChunkFormerEncoderB200:
                     events.append(ev)
                     rows_ready.append(row + b)
                 row += t
-        self._live_events = events               # keep the events alive until the next call
-        n = len(events)
+        return UploadedFeatures(flat, lens, events, rows_ready)
+
+    def _arm_feature_events(self, up: UploadedFeatures) -> torch.Tensor:
+        """Hand the copy events of `up` to the library for the cf_encode call that follows, and tie the buffer's lifetime to
+        the consuming stream."""
+        up.flat.record_stream(torch.cuda.current_stream(self.device))
+        self._live_events = up.events            # keep the events alive until the next call
+        n = len(up.events)
         if n:
-            rr = (c_int64 * n)(*rows_ready)
-            evp = (c_void_p * n)(*[c_void_p(e.cuda_event) for e in events])
+            rr = (c_int64 * n)(*up.rows_ready)
+            evp = (c_void_p * n)(*[c_void_p(e.cuda_event) for e in up.events])
             _lib.check(self._L.cf_encode_feature_events(self._h, n, rr, evp), self._h, "cf_encode_feature_events")
-        return flat
+        return up.flat
 
     def encode_plan(self, plan: Plan, feats: torch.Tensor, att_cache=None, cnn_cache=None, trunc: int = 0,
                     out_dtype=torch.float32, want_bf16: bool = False):
@@ -138,7 +157,7 @@ class ChunkFormerEncoderB200:
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_parallel_chunk(self, xs: List[torch.Tensor], xs_origin_lens: torch.Tensor, chunk_size: int = -1,
+    def forward_parallel_chunk(self, xs, xs_origin_lens: torch.Tensor, chunk_size: int = -1,
                                left_context_size: int = -1, right_context_size: int = -1,
                                att_cache: torch.Tensor = torch.zeros((0, 0, 0)),
                                cnn_cache: torch.Tensor = torch.zeros((0, 0)), truncated_context_size: int = 0,
@@ -146,6 +165,7 @@ class ChunkFormerEncoderB200:
                                ) -> Tuple[torch.Tensor, torch.Tensor, List[int], torch.Tensor, torch.Tensor, torch.Tensor]:
         """Masked-batch encoder forward; drop-in for ChunkFormerEncoder.forward_parallel_chunk (encoder.py:503-681).
 
+        xs: list of (T_i, feat) tensors (host or device), or the UploadedFeatures of an earlier upload_async call.
         Returns (xs (n, c, d) fp32, xs_lens int32 (B), n_chunks list, att_cache, cnn_cache, offset); like the reference,
         `offset` is advanced in place and the caches come back empty ((L,0,0,0) / (L,0,0)) when none were passed."""
         if chunk_size <= 0 or left_context_size < 0 or right_context_size < 0:
@@ -153,9 +173,13 @@ class ChunkFormerEncoderB200:
         lens = [int(v) for v in xs_origin_lens.tolist()]
         if len(lens) != len(xs):
             raise ValueError("xs and xs_origin_lens disagree on the batch size")
-        for x, t in zip(xs, lens):
-            if x.dim() != 2 or x.shape[1] != self.geo.feat_dim or x.shape[0] < t or t < 0:
-                raise ValueError("every utterance must be (T_i, feat_dim) with T_i >= xs_origin_lens[i] >= 0")
+        if isinstance(xs, UploadedFeatures):
+            if xs.lens != lens:
+                raise ValueError("xs_origin_lens differs from the lengths the features were uploaded with")
+        else:
+            for x, t in zip(xs, lens):
+                if x.dim() != 2 or x.shape[1] != self.geo.feat_dim or x.shape[0] < t or t < 0:
+                    raise ValueError("every utterance must be (T_i, feat_dim) with T_i >= xs_origin_lens[i] >= 0")
         if offset.shape[0] == 0:
             offset = torch.zeros(len(xs), dtype=torch.long, device=xs_origin_lens.device)
         offs = [int(v) for v in offset.tolist()]
@@ -176,7 +200,8 @@ class ChunkFormerEncoderB200:
                 new_att = torch.zeros((L, 1, H, 2 * d // H), device=self.device)
             new_cnn = cnn_cache.to(self.device, torch.float32).contiguous().clone()
         plan = Plan(chunk_size, left_context_size, right_context_size, lens, offs, self.geo.kernel)
-        feats = self._flat_feats([x[:t] for x, t in zip(xs, lens)])
+        # everything is validated: start (or pick up) the upload and arm its events for the cf_encode call that follows
+        feats = self._arm_feature_events(xs if isinstance(xs, UploadedFeatures) else self.upload_async(xs, lens))
         out, _ = self.encode_plan(plan, feats, new_att, new_cnn, truncated_context_size, want_bf16=True)
         xs_lens = torch.as_tensor(plan.enc_lens, dtype=torch.int32, device=xs_origin_lens.device)
         offset += xs_lens.to(offset.dtype)
