@@ -73,6 +73,8 @@ struct cf_handle {
   cf::KernelTiming timing;
   // per-handle options (cf_set_option)
   int opt_fused_layernorm = 1;   // LayerNorms fused into the epilogue of the residual GEMM in front of them (gemm_ln.cuh)
+  int opt_ffn_slab_rows = 0;     // > 0: the two FFN GEMMs run slab by slab of this many rows, the hidden activation of a slab
+                                 // (rows x F bf16) is produced and consumed while it is still in L2
   int opt_fused_ffn = 0;         // feed-forward modules as one kernel each, hidden activation kept on chip (ffn_fused.cuh)
   struct FbankTables { int sr = 0, bins = 0, flen = 0, fshift = 0; float* window = nullptr; float* mel_w = nullptr; int2* mel_rng = nullptr; int* mel_cnt = nullptr; };
   std::vector<FbankTables> fbank_tables;
@@ -101,6 +103,7 @@ extern "C" int cf_set_option(cf_handle* h, const char* name, int value) {
   const std::string k(name);
   if (k == "fused_layernorm") { h->opt_fused_layernorm = value != 0; return CF_OK; }
   if (k == "fused_ffn") { h->opt_fused_ffn = value != 0; return CF_OK; }
+  if (k == "ffn_slab_rows") { h->opt_ffn_slab_rows = value > 0 ? ((value + 127) / 128) * 128 : 0; return CF_OK; }
   return fail(h, CF_ERR_INVALID, "cf_set_option: unknown option " + k);
 }
 extern "C" int cf_kernel_timing_begin(cf_handle* h, unsigned family_mask) {
@@ -732,6 +735,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   CF_CUDA(h, cudaSetDevice(h->device));
   const EncodeWs w = carve_encode(h, p, workspace);
   if (w.total > workspace_bytes) return fail(h, CF_ERR_WORKSPACE, "cf_encode: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(h, CF_ERR_INVALID, "cf_encode: workspace must be 256-byte aligned");
   const int d = h->cfg.d_model, F = h->cfg.ffn, L = h->cfg.layers, H = h->cfg.heads, dk = d / H;
   const int c = p->c, l = p->l, r = p->r, lo = p->lorder;
   const int n = p->n;
@@ -751,50 +755,59 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   int rc = get_pos_table(h, c, l, r, st, &pos);
   if (rc != CF_OK) return rc;
 
-  // ---- tables: packed into one pinned staging block owned by the handle and uploaded asynchronously (no host
-  // synchronisation; a ring of four blocks, each guarded by an event recorded behind its copies)
+  // ---- tables: built in a pinned staging block owned by the handle, laid out exactly like the workspace's table region, and
+  // pulled into the workspace by one small kernel that reads the mapped host memory (no host synchronisation, and no
+  // copy-engine operation that would queue behind the feature upload; a ring of four blocks, each guarded by an event)
+  auto launch_zero = [&](void* dst, size_t bytes) {      // bytes and dst are multiples of 16 here
+    if (bytes == 0) return;
+    const long long n16 = (long long)(bytes / 16);
+    zero16_kernel<<<unsigned(std::min<long long>((n16 + 255) / 256, 4LL * h->num_sms)), 256, 0, st>>>(static_cast<uint4*>(dst), n16);
+    ++cf::g_kernel_launches;
+  };
   {
-    const size_t b_cs = size_t(n) * sizeof(ChunkSrc), b_ar = size_t(n + 16) * sizeof(int2), b_r = size_t(n) * sizeof(int2);
-    const size_t b_sl = p->mode == 1 ? size_t(p->B) * sizeof(int) : 0;
-    const size_t need = b_cs + b_ar + 2 * b_r + b_sl;
+    uint8_t* dev0 = reinterpret_cast<uint8_t*>(w.chunk_src);
+    const size_t o_ar = reinterpret_cast<uint8_t*>(w.att_range) - dev0, o_cr = reinterpret_cast<uint8_t*>(w.conv_range) - dev0;
+    const size_t o_or = reinterpret_cast<uint8_t*>(w.out_range) - dev0, o_sl = reinterpret_cast<uint8_t*>(w.seq_limit) - dev0;
+    const size_t need = ((o_sl + size_t(p->B) * sizeof(int)) + 15) & ~size_t(15);
     PinnedStage& sg = h->stage[h->stage_next];
     h->stage_next = (h->stage_next + 1) % 4;
     if (sg.in_flight) { CF_CUDA(h, cudaEventSynchronize(sg.done)); sg.in_flight = false; }
     if (sg.bytes < need) {
       if (sg.host) cudaFreeHost(sg.host);
       sg.host = nullptr; sg.bytes = 0;
-      CF_CUDA(h, cudaHostAlloc(&sg.host, need + need / 2, cudaHostAllocDefault));
+      CF_CUDA(h, cudaHostAlloc(&sg.host, need + need / 2, cudaHostAllocMapped | cudaHostAllocPortable));
       sg.bytes = need + need / 2;
     }
     if (!sg.done) CF_CUDA(h, cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
     uint8_t* base = static_cast<uint8_t*>(sg.host);
+    memset(base, 0, need);
     ChunkSrc* cs = reinterpret_cast<ChunkSrc*>(base);
-    int2* ar = reinterpret_cast<int2*>(base + b_cs);
-    int2* cr = reinterpret_cast<int2*>(base + b_cs + b_ar);
-    int2* orr = reinterpret_cast<int2*>(base + b_cs + b_ar + b_r);
+    int2* ar = reinterpret_cast<int2*>(base + o_ar);
+    int2* cr = reinterpret_cast<int2*>(base + o_cr);
+    int2* orr = reinterpret_cast<int2*>(base + o_or);
     for (int g = 0; g < n; ++g) {
       cs[g].feat_row = p->chunk_feat_row[g]; cs[g].in_len = p->chunk_in_len[g]; cs[g].pad_ = 0;
       const cf_chunk_entry& e = p->chunks[g];
       ar[g] = make_int2(e.att_lo, e.att_hi); cr[g] = make_int2(e.conv_lo, e.conv_hi); orr[g] = make_int2(e.out_lo, e.out_hi);
     }
-    for (int g = n; g < n + 16; ++g) ar[g] = make_int2(0, 0);   // phantom chunks of the last attention tile stay empty
-    CF_CUDA(h, cudaMemcpyAsync(w.chunk_src, cs, b_cs, cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaMemcpyAsync(w.att_range, ar, b_ar, cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaMemcpyAsync(w.conv_range, cr, b_r, cudaMemcpyHostToDevice, st));
-    CF_CUDA(h, cudaMemcpyAsync(w.out_range, orr, b_r, cudaMemcpyHostToDevice, st));
-    if (p->mode == 1) {
-      int* sl = reinterpret_cast<int*>(base + b_cs + b_ar + 2 * b_r);
-      memcpy(sl, p->seq_valid_rows.data(), b_sl);
-      CF_CUDA(h, cudaMemcpyAsync(w.seq_limit, sl, b_sl, cudaMemcpyHostToDevice, st));
-    }
+    // (the 16 phantom chunks behind the last attention tile stay empty: zeroed above)
+    if (p->mode == 1) memcpy(base + o_sl, p->seq_valid_rows.data(), size_t(p->B) * sizeof(int));
+    void* mapped = nullptr;
+    CF_CUDA(h, cudaHostGetDevicePointer(&mapped, sg.host, 0));
+    const long long n16 = (long long)(need / 16);
+    copy16_kernel<<<unsigned(std::min<long long>((n16 + 255) / 256, 2LL * h->num_sms)), 256, 0, st>>>(static_cast<const uint4*>(mapped),
+                                                                                                   reinterpret_cast<uint4*>(dev0), n16);
+    ++cf::g_kernel_launches;
+    CF_CUDA(h, cudaGetLastError());
     CF_CUDA(h, cudaEventRecord(sg.done, st));
     sg.in_flight = true;
   }
   // zero the halo rows of the flat buffers once (cache rows are rewritten per layer when streaming)
-  CF_CUDA(h, cudaMemsetAsync(w.qkv, 0, size_t(l) * 4 * d * sizeof(bf16), st));
-  CF_CUDA(h, cudaMemsetAsync(w.qkv + (size_t(l) + Mr) * 4 * d, 0, (w.qkv_rows - size_t(l) - Mr) * 4 * d * sizeof(bf16), st));
-  CF_CUDA(h, cudaMemsetAsync(w.g, 0, size_t(lo) * d * sizeof(bf16), st));
-  CF_CUDA(h, cudaMemsetAsync(w.g + (size_t(lo) + Mr) * d, 0, (w.g_rows - size_t(lo) - Mr) * d * sizeof(bf16), st));
+  launch_zero(w.qkv, size_t(l) * 4 * d * sizeof(bf16));
+  launch_zero(w.qkv + (size_t(l) + Mr) * 4 * d, (w.qkv_rows - size_t(l) - Mr) * 4 * d * sizeof(bf16));
+  launch_zero(w.g, size_t(lo) * d * sizeof(bf16));
+  launch_zero(w.g + (size_t(lo) + Mr) * d, (w.g_rows - size_t(lo) - Mr) * d * sizeof(bf16));
+  CF_CUDA(h, cudaGetLastError());
 
   struct EpiArgs { const float* bias = nullptr; void* out = nullptr; long long ldo = 0; int act = ACT_NONE;
                    const float* resid = nullptr; long long ld_resid = 0; float alpha = 1.0f;
@@ -832,6 +845,22 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.x_out = q.x_out; g.ldx = d; g.y_out = q.y_out; g.ldy = d;
     g.timing = &h->timing; g.family = CF_FAMILY_FFN_FUSED;
     return launch_ffn_fused(g, h->num_sms, st, &err);
+  };
+  // feed-forward module as two GEMMs (w_1 + SiLU -> hidden activation in global memory -> w_2 + residual + LayerNorm(s)),
+  // optionally slab by slab so that a slab's hidden activation never has to leave L2
+  auto ffn_two = [&](const bf16* w1, const float* b1, const bf16* w2, const float* b2, const LnArgs& q0) -> bool {
+    const long long slab = h->opt_ffn_slab_rows > 0 ? h->opt_ffn_slab_rows : Mr;
+    for (long long r0 = 0; r0 < Mr; r0 += slab) {
+      const long long rows = std::min(slab, Mr - r0);
+      EpiArgs e1; e1.bias = b1; e1.out = w.hbuf; e1.ldo = F; e1.act = ACT_SILU; e1.family = CF_FAMILY_FFN_W1;
+      if (!gemm(w.y + r0 * d, d, w1, d, rows, F, d, EPI_BF16, e1)) return false;
+      EpiArgs e2; e2.bias = b2; e2.resid = w.x + r0 * d; e2.ld_resid = d; e2.alpha = 0.5f; e2.family = CF_FAMILY_FFN_W2;
+      LnArgs q = q0;
+      if (q.x_out) q.x_out += r0 * d;
+      if (q.y_out) q.y_out = static_cast<bf16*>(q.y_out) + r0 * d;
+      if (!gemm_ln(w.hbuf, F, w2, F, rows, F, e2, q)) return false;
+    }
+    return true;
   };
 #define CF_TRY(expr) do { if (!(expr)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err); } while (0)
 
@@ -894,9 +923,10 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   for (int i = 0; i < L; ++i) {
     const LayerW& lw = h->layers[i];
     // macaron FFN: x += 0.5 * W2 SiLU(W1 LN(x) + b1) + b2
-    if (fuse_ffn) {
+    if (fuse_ln) {
       LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_mha_w; q.b1 = lw.ln_mha_b; q.x_out = w.x; q.y_out = w.y;
-      CF_TRY(ffn(lw.ffm_w1, lw.ffm_b1, lw.ffm_w2, lw.ffm_b2, q));
+      if (fuse_ffn) CF_TRY(ffn(lw.ffm_w1, lw.ffm_b1, lw.ffm_w2, lw.ffm_b2, q));
+      else CF_TRY(ffn_two(lw.ffm_w1, lw.ffm_b1, lw.ffm_w2, lw.ffm_b2, q));
     } else {
     { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
       CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
@@ -960,7 +990,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       } else CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
     // FFN
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
-    if (fuse_ffn) {
+    if (fuse_ln) {
       LnArgs q;
       q.w1 = lw.ln_fin_w; q.b1 = lw.ln_fin_b;
       if (i + 1 < L) {
@@ -970,7 +1000,8 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
         q.x_out = out_dtype == CF_F32 ? static_cast<float*>(out) : nullptr;
         q.y_out = out_dtype == CF_BF16 ? out : out_bf16;
       }
-      CF_TRY(ffn(lw.ff_w1, lw.ff_b1, lw.ff_w2, lw.ff_b2, q));
+      if (fuse_ffn) CF_TRY(ffn(lw.ff_w1, lw.ff_b1, lw.ff_w2, lw.ff_b2, q));
+      else CF_TRY(ffn_two(lw.ff_w1, lw.ff_b1, lw.ff_w2, lw.ff_b2, q));
       if (i + 1 == L && out_dtype == CF_BF16 && out_bf16 && out_bf16 != out)
         CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
       continue;

@@ -246,4 +246,16 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
   }
 }
 
+// 16-byte-granular copy / zero fill by SMs.  cf_encode uses them instead of cudaMemcpyAsync / cudaMemsetAsync on the compute
+// stream: a copy-engine operation queues behind every host-to-device feature copy issued earlier (one DMA FIFO per direction),
+// which serialised the whole 461 MB upload in front of the encoder (measured: +6 ms per end-to-end step).  `src` may be mapped
+// pinned host memory (the plan tables): the SMs read it over PCIe directly.
+__global__ void copy16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void zero16_kernel(uint4* __restrict__ dst, long long n16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 }  // namespace cf
