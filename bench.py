@@ -344,10 +344,10 @@ def main():
         tokens = enc.ctc_greedy(out16)
         return plan, tokens, out16
 
-    def step_e2e(up=None):
+    def step_e2e():
         """One step through the public API with HOST inputs: features cross PCIe (pinned host -> device), encoder, greedy CTC,
-        token ids back to the host.  `up` = this step's upload if it was started earlier (upload_async)."""
-        out, enc_lens, n_chunks, _, _, _ = enc.forward_parallel_chunk(xs_host if up is None else up, lens_t, C, L, R,
+        token ids back to the host."""
+        out, enc_lens, n_chunks, _, _, _ = enc.forward_parallel_chunk(xs_host, lens_t, C, L, R,
                                                                       offset=torch.zeros(len(lens), dtype=torch.int32))
         tokens = enc.ctc_greedy(out)
         return tokens.to("cpu", non_blocking=False)
@@ -396,10 +396,12 @@ def main():
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     value = world * audio * args.steps / (ms_total / 1000.0) / 3600.0
 
-    # ---- end to end through the public API with host buffers.  Two loops, both with every step's host-to-device copy and
-    # device-to-host read inside the timed region: (1) serial: each step uploads, encodes, reads back; (2) pipelined, as a
-    # decoding service (and batch_decode) runs it: the upload of step k + 1 is started (upload_async) before step k is encoded,
-    # so the copy engine works while the SMs do.  (2) is the headline `e2e.value`; (1) is reported beside it.
+    # ---- end to end through the public API with host buffers: every step uploads its features (pinned host -> device, inside
+    # forward_parallel_chunk: the copy runs on a side stream and the front-end starts on the first rows while the rest is still
+    # crossing PCIe), encodes, decodes greedily and reads the token ids back.  Wall clock around K steps.
+    # (Also tried: starting the upload of step k + 1 before step k is encoded (upload_async); the copy then runs under the
+    # attention / FFN kernels instead of under the front-end and the step got SLOWER: 73.1 vs 71.6 ms on one GPU, 121 vs 71 ms
+    # with two ranks sharing the host; profiles/README.md.)
     for _ in range(2):
         step_e2e()
     barrier()
@@ -407,19 +409,9 @@ def main():
     for _ in range(args.steps):
         tok_host = step_e2e()
     torch.cuda.synchronize()
-    e2e_serial_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    barrier()
-    t0 = time.perf_counter()
-    up = enc.upload_async(xs_host, lens)
-    for k in range(args.steps):
-        nxt = enc.upload_async(xs_host, lens) if k + 1 < args.steps else None
-        tok_host = step_e2e(up)
-        up = nxt
-    torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_serial_s, op=dist.ReduceOp.MAX)
     e2e_value = world * audio * args.steps / float(e2e_s.item()) / 3600.0
     h2d = int(sum(x.numel() * 4 for x in xs_host))
     d2h = int(tok_host.numel() * tok_host.element_size())
@@ -540,11 +532,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1000.0 * float(e2e_s.item()) / args.steps,
                         "h2d_link_gbs": h2d_gbs,
-                        "serial": {"value": world * audio * args.steps / float(e2e_serial_s.item()) / 3600.0,
-                                   "ms_per_step": 1000.0 * float(e2e_serial_s.item()) / args.steps,
-                                   "api": "forward_parallel_chunk(host fbank) + ctc_greedy + tokens.cpu(), one step after the other"},
-                        "api": "ChunkFormerEncoderB200.upload_async(host fbank of step k+1) overlapped with forward_parallel_chunk("
-                               "uploaded step k) + ctc_greedy + tokens.cpu(); every step's H2D and D2H inside the timed region"},
+                        "api": "ChunkFormerEncoderB200.forward_parallel_chunk(pinned host fbank) + ctc_greedy + tokens.cpu(), one step "
+                               "after the other; every step's H2D and D2H inside the timed region"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base,
                 "parity_checked": bool(parity and parity["ok"]), "parity": parity, "strong": strong, "reference_gpu": ref_gpu}
         print(json.dumps(line), flush=True)

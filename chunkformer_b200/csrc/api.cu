@@ -89,6 +89,23 @@ static int fail(cf_handle* h, int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+// Entry points switch to their handle's device (or, without a handle, to the device that owns the data) and restore the
+// caller's current device on every exit path: a process that drives several GPUs (batch_decode(devices=...)) must not find
+// its current device changed behind its back.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (dev >= 0 && dev != prev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+static int device_of(const void* ptr) {       // device owning a device pointer, -1 if unknown
+  cudaPointerAttributes at;
+  if (ptr && cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) return at.device;
+  cudaGetLastError();
+  return -1;
+}
 #define CF_CUDA(h, call)                                                                              \
   do {                                                                                                \
     cudaError_t e__ = (call);                                                                         \
@@ -153,7 +170,7 @@ extern "C" int cf_create(const cf_config* cfg, int device, cf_handle** out) {
   CF_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return fail(nullptr, CF_ERR_CUDA, "cf_create: device is not sm_100 (kernels are built for sm_100a only)");
-  CF_CUDA(nullptr, cudaSetDevice(device));
+  DeviceGuard guard(device);
   std::unique_ptr<cf_handle> h(new cf_handle());
   h->cfg = *cfg;
   h->device = device;
@@ -167,7 +184,7 @@ extern "C" int cf_create(const cf_config* cfg, int device, cf_handle** out) {
 
 extern "C" void cf_destroy(cf_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->arena) cudaFree(h->arena);
   for (auto& t : h->pos_tables)
     if (t.dev) cudaFree(t.dev);
@@ -364,7 +381,7 @@ extern "C" int cf_finalize_weights(cf_handle* h) {
     std::vector<float> z(size_t(std::max(std::max(4 * d, F), 2 * d)), 0.f);
     ab.f32(z, &h->zeros);
   }
-  CF_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   CF_CUDA(h, cudaMalloc(&h->arena, ab.host.size()));
   h->arena_bytes = ab.host.size();
   CF_CUDA(h, cudaMemcpy(h->arena, ab.host.data(), ab.host.size(), cudaMemcpyHostToDevice));
@@ -732,7 +749,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   if ((att_cache != nullptr) != (cnn_cache != nullptr))
     return fail(h, CF_ERR_INVALID, "cf_encode: pass both caches or neither");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CF_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const EncodeWs w = carve_encode(h, p, workspace);
   if (w.total > workspace_bytes) return fail(h, CF_ERR_WORKSPACE, "cf_encode: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(h, CF_ERR_INVALID, "cf_encode: workspace must be 256-byte aligned");
@@ -1061,7 +1078,7 @@ extern "C" int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int s
   const int64_t T = cf_fbank_num_frames(n_samples, sample_rate, frame_length_ms, frame_shift_ms);
   if (T == 0) return CF_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CF_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const cf_handle::FbankTables* tb = nullptr;
   for (auto& t : h->fbank_tables)
     if (t.sr == sample_rate && t.bins == num_mel_bins && t.flen == flen && t.fshift == fshift) tb = &t;
@@ -1134,7 +1151,7 @@ extern "C" int cf_ctc_greedy(cf_handle* h, const void* enc, int enc_dtype, int64
   if (rows <= 0) return CF_OK;
   if (workspace_bytes < cf_ctc_workspace_bytes(h, rows, enc_dtype)) return fail(h, CF_ERR_WORKSPACE, "cf_ctc_greedy: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CF_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const int d = h->cfg.d_model, V = h->cfg.vocab;
   const int nt = 2 * ((V + 255) / 256);
   Carver cv(workspace);
@@ -1184,6 +1201,7 @@ extern "C" int cf_ctc_compact(const int64_t* tokens, int64_t rows, const int64_t
     return fail(nullptr, CF_ERR_INVALID, "cf_ctc_compact: null argument");
   if (rows < 0 || n_seg < 0 || (mode != 0 && mode != 1)) return fail(nullptr, CF_ERR_INVALID, "cf_ctc_compact: bad size or mode");
   if (workspace_bytes < cf_ctc_compact_workspace_bytes(rows)) return fail(nullptr, CF_ERR_WORKSPACE, "cf_ctc_compact: workspace too small");
+  DeviceGuard guard(device_of(tokens));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (rows == 0) {   // nothing to scan: every offset is 0
     cudaError_t e = cudaMemsetAsync(out_offsets, 0, sizeof(int64_t) * (size_t(n_seg) + 1), st);
@@ -1251,7 +1269,7 @@ extern "C" int cf_rnnt_create(const cf_rnnt_config* cfg, int device, cf_rnnt** o
 }
 extern "C" void cf_rnnt_destroy(cf_rnnt* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   delete h;
 }
 
@@ -1269,7 +1287,7 @@ extern "C" int cf_rnnt_finalize_weights(cf_rnnt* h) {
   if (!h) return rfail(nullptr, CF_ERR_INVALID, "cf_rnnt_finalize_weights: null handle");
   if (h->finalized) return CF_OK;
   const cf_rnnt_config& c = h->cfg;
-  CF_RCUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   auto need = [&](const std::string& k, std::vector<int64_t> want, const std::vector<float>** out) -> bool {
     auto it = h->host.find(k);
     if (it == h->host.end()) { h->err = "cf_rnnt_finalize_weights: missing tensor " + k; return false; }
@@ -1381,7 +1399,7 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
   RnntWs w = rnnt_carve(c, rows, n_utt, workspace);
   if (workspace_bytes < w.bytes) return rfail(h, CF_ERR_WORKSPACE, "cf_rnnt_greedy: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CF_RCUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   CF_RCUDA(h, cudaMemcpyAsync(w.seg_start, seg_start, sizeof(int64_t) * n_utt, cudaMemcpyHostToDevice, st));
   CF_RCUDA(h, cudaMemcpyAsync(w.seg_len, seg_len, sizeof(int32_t) * n_utt, cudaMemcpyHostToDevice, st));
   if (rows > 0) {
@@ -1483,6 +1501,7 @@ extern "C" int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb
                           const float* bias, const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range,
                           int rows_per_chunk, void* out, int64_t ldo, float* part_best, float* part_second,
                           int32_t* part_index, int variant, void* stream) {
+  DeviceGuard guard(device_of(A));
   if (!A || !B || !bias) return fail(nullptr, CF_ERR_INVALID, "cf_op_gemm: null argument");
   GemmLaunch g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.epi = epi; g.act = act; g.out = out; g.ldo = ldo;
@@ -1501,6 +1520,7 @@ extern "C" int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t 
                              int mode, const float* ln1_w, const float* ln1_b, const float* ln2_w, const float* ln2_b,
                              float* x_out, int64_t ldx, void* y_out, int64_t ldy, const int32_t* row_limit, int rows_per_seq,
                              void* stream) {
+  DeviceGuard guard(device_of(A));
   if (!A || !B) return fail(nullptr, CF_ERR_INVALID, "cf_op_gemm_ln: null argument");
   GemmLnLaunch g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.bias = bias; g.resid = resid; g.ld_resid = ld_resid;
@@ -1516,6 +1536,7 @@ extern "C" int cf_op_ffn(const void* y_bf16, int64_t ldy_in, const void* w1, con
                          int d, int F, const float* resid, int64_t ld_resid, float alpha, int mode, const float* ln1_w,
                          const float* ln1_b, const float* ln2_w, const float* ln2_b, float* x_out, int64_t ldx, void* y_out,
                          int64_t ldy, void* stream) {
+  DeviceGuard guard(device_of(y_bf16));
   FfnLaunch g{};
   g.Y = y_bf16; g.ldy_in = ldy_in; g.W1 = w1; g.b1 = b1; g.W2 = w2; g.b2 = b2; g.M = M; g.d = d; g.F = F; g.resid = resid;
   g.ld_resid = ld_resid; g.alpha = alpha; g.mode = mode; g.ln1_w = ln1_w; g.ln1_b = ln1_b; g.ln2_w = ln2_w; g.ln2_b = ln2_b;
@@ -1527,6 +1548,7 @@ extern "C" int cf_op_ffn(const void* y_bf16, int64_t ldy_in, const void* w1, con
 
 extern "C" int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, void* y_bf16, const float* w1,
                                const float* b1, const float* w2, const float* b2, int64_t rows, void* stream) {
+  DeviceGuard guard(device_of(x_in));
   LnParams q{};
   q.x_in = x_in; q.x_out = x_out; q.y = static_cast<bf16*>(y_bf16); q.w1 = w1; q.b1 = b1; q.w2 = w2; q.b2 = b2;
   q.rows = rows; q.row_limit = nullptr; q.rows_per_seq = 1;
@@ -1537,6 +1559,7 @@ extern "C" int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out,
 
 extern "C" int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16, const float* w, const float* bias,
                             const float* ln_w, const float* ln_b, const int32_t* range, int c, int n_chunks, void* stream) {
+  DeviceGuard guard(device_of(g_bf16));
   DwConvParams q{};
   q.g = static_cast<const bf16*>(g_bf16); q.z = static_cast<bf16*>(z_bf16); q.w = w; q.bias = bias; q.ln_w = ln_w;
   q.ln_b = ln_b; q.range = reinterpret_cast<const int2*>(range); q.c = c; q.n_chunks = n_chunks;
@@ -1549,6 +1572,7 @@ extern "C" int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16,
 
 extern "C" int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_bf16, const int32_t* range, void* ctx_bf16,
                                int n_chunks, int c, int l, int r, int d, int heads, int prescaled, void* stream) {
+  DeviceGuard guard(device_of(qkv_bf16));
   AttnParams a{};
   a.qkv = static_cast<const bf16*>(qkv_bf16); a.pos = static_cast<const bf16*>(pos_bf16);
   a.range = reinterpret_cast<const int2*>(range); a.ctx = static_cast<bf16*>(ctx_bf16);
@@ -1562,6 +1586,7 @@ extern "C" int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_b
 extern "C" int cf_op_frontend_conv(int impl, int d, const float* feats, const int64_t* chunk_feat_row, const int32_t* chunk_in_len,
                                    int n_chunks, int chunk_size, int feat_dim, const float* wpack, const float* cmvn_mean,
                                    const float* cmvn_istd, void* out_bf16, void* stream) {
+  DeviceGuard guard(device_of(feats));
   if (!feats || !chunk_feat_row || !chunk_in_len || !wpack || !out_bf16) return fail(nullptr, CF_ERR_INVALID, "cf_op_frontend_conv: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   std::vector<ChunkSrc> cs(n_chunks);

@@ -96,10 +96,11 @@ class ChunkFormerEncoderB200:
         The copies run on a side stream, in pieces of about 32 MB, each followed by an event; forward_parallel_chunk hands the
         events to the library (cf_encode_feature_events), whose front-end waits only for the rows each slab of chunks reads, so
         the encoder starts on the first rows while the rest is still crossing PCIe (pinned host tensors copy asynchronously;
-        pageable ones are staged by the driver).  The buffer is allocated from the side stream's pool, so the upload of the
-        NEXT batch does not wait for the encoder pass of the current one: a decoding loop calls upload_async for batch k + 1
-        before forward_parallel_chunk for batch k and the host-to-device copy disappears behind the compute (what the
-        reference's blocking xs.to(device), chunkformer_model.py:395-401, cannot do)."""
+        pageable ones are staged by the driver): what the reference's blocking xs.to(device), chunkformer_model.py:395-401,
+        cannot do.  The buffer is allocated from the side stream's pool, so an upload never waits for encoder work queued
+        earlier.  (Starting the upload of batch k + 1 before batch k is encoded is possible with this call, but measured slower
+        than uploading inside the step: the copy then competes with the attention / FFN kernels instead of hiding under the
+        front-end; profiles/README.md.)"""
         lens = [int(x.shape[0]) for x in xs] if lens is None else [int(t) for t in lens]
         F = self.geo.feat_dim
         for x, t in zip(xs, lens):

@@ -311,17 +311,10 @@ class ChunkFormerModel:
                 if budget <= 0 or i == len(audio_paths) - 1:
                     yield xs, lens
                     xs, lens, budget = [], [], budget0
-        # the features of group k + 1 start crossing PCIe before group k is encoded (upload_async), results in arrival order
         decodes = []
-        it = groups()
-        cur = next(it, None)
-        cur_up = self.encoder.upload_async(cur[0], cur[1]) if cur is not None else None
-        while cur is not None:
-            nxt = next(it, None)
-            nxt_up = self.encoder.upload_async(nxt[0], nxt[1]) if nxt is not None else None
-            g = self._decode_group_enqueue(self.encoder, self.transducer, cur_up, cur[1], c, l, r)
+        for xs, lens in groups():
+            g = self._decode_group_enqueue(self.encoder, self.transducer, xs, lens, c, l, r)
             decodes.extend(self._decode_group_collect(g))
-            cur, cur_up = nxt, nxt_up
         return decodes
 
     def _batch_decode_balanced(self, audio_paths, c, l, r, budget0, devices):
