@@ -42,7 +42,7 @@ def import_reference(root: str = REF_ROOT):
     return ChunkFormerModel, ChunkFormerConfig
 
 
-def reference_config_dict(d=512, heads=8, ffn=2048, layers=17, vocab=5000, kernel=15):
+def reference_config_dict(d=512, heads=8, ffn=2048, layers=17, vocab=5000, kernel=15, conv_norm="layer_norm"):
     """Config dict for a random-init reference ASR model; the attention decoder is unused on the path
     and kept minimal."""
     return dict(
@@ -52,7 +52,7 @@ def reference_config_dict(d=512, heads=8, ffn=2048, layers=17, vocab=5000, kerne
             dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1,
             input_layer="dw_striding", normalize_before=True, cnn_module_kernel=kernel,
             use_cnn_module=True, activation_type="swish", pos_enc_layer_type="chunk_rel_pos",
-            selfattention_layer_type="chunk_rel_seflattn", cnn_module_norm="layer_norm",
+            selfattention_layer_type="chunk_rel_seflattn", cnn_module_norm=conv_norm,
             dynamic_conv=True),
         decoder="bitransformer",
         decoder_conf=dict(attention_heads=4, linear_units=64, num_blocks=1, r_num_blocks=1,
@@ -66,7 +66,7 @@ def reference_config_dict(d=512, heads=8, ffn=2048, layers=17, vocab=5000, kerne
 def build_reference(geo, state_dict, root: str = REF_ROOT):
     """Reference model of geometry `geo` carrying `state_dict` (encoder.* / ctc.* keys; the unused decoder stays random)."""
     Model, Config = import_reference(root)
-    cfg = reference_config_dict(geo.d_model, geo.heads, geo.ffn, geo.layers, geo.vocab, geo.kernel)
+    cfg = reference_config_dict(geo.d_model, geo.heads, geo.ffn, geo.layers, geo.vocab, geo.kernel, geo.conv_norm)
     model = Model(Config.from_dict(cfg)).eval()
     if geo.has_cmvn:
         from chunkformer.modules.cmvn import GlobalCMVN

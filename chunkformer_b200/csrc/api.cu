@@ -80,7 +80,7 @@ struct cf_handle {
   std::vector<FbankTables> fbank_tables;
   // feature-arrival events of the next cf_encode call (cf_encode_feature_events): rows < ev_rows[i] are present once ev[i] fires
   std::vector<int64_t> ev_rows;
-  int streams_n = 0, streams_ph = 0;   // multi-stream spec of the next cf_encode call (cf_encode_streams)
+  int streams_n = 0, streams_ph = 0, streams_adv = 0;   // multi-stream spec of the next cf_encode call (cf_encode_streams)
   std::vector<cudaEvent_t> ev;
 };
 
@@ -161,6 +161,7 @@ extern "C" int cf_create(const cf_config* cfg, int device, cf_handle** out) {
   if (cfg->kernel != 15) return fail(nullptr, CF_ERR_INVALID, "cf_create: cnn_module_kernel must be 15");
   if (cfg->layers <= 0 || cfg->feat_dim < 15 || cfg->vocab < 0)
     return fail(nullptr, CF_ERR_INVALID, "cf_create: bad layers / feat_dim / vocab");
+  if (cfg->conv_norm != 0 && cfg->conv_norm != 1) return fail(nullptr, CF_ERR_INVALID, "cf_create: conv_norm must be 0 (layer_norm) or 1 (batch_norm)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
     cudaGetLastError();
@@ -354,9 +355,25 @@ extern "C" int cf_finalize_weights(cf_handle* h) {
     {
       const auto& W = get(p + "conv_module.depthwise_conv.weight", int64_t(d) * KW);
       const auto& B = get(p + "conv_module.depthwise_conv.bias", d);
-      if (missing.empty()) { ab.f32(W, &w.dw_w); ab.f32(B, &w.dw_b); }
+      if (h->cfg.conv_norm == 1) {
+        // eval-mode BatchNorm1d (convolution.py:83-89, 245-248) is a per-channel affine on the depthwise conv output:
+        // a (conv + b_d) + s with a = gamma / sqrt(running_var + eps), s = beta - a * running_mean; folded into the taps and bias
+        const auto& G = get(p + "conv_module.norm.weight", d);
+        const auto& Bt = get(p + "conv_module.norm.bias", d);
+        const auto& Mu = get(p + "conv_module.norm.running_mean", d);
+        const auto& Var = get(p + "conv_module.norm.running_var", d);
+        if (missing.empty()) {
+          std::vector<float> Wf(W), Bf(B), ones(d, 1.0f), zeros(d, 0.0f);
+          for (int ch = 0; ch < d; ++ch) {
+            const float a = G[ch] / sqrtf(Var[ch] + 1e-5f);
+            for (int t = 0; t < KW; ++t) Wf[size_t(ch) * KW + t] *= a;
+            Bf[ch] = a * (B[ch] - Mu[ch]) + Bt[ch];
+          }
+          ab.f32(Wf, &w.dw_w); ab.f32(Bf, &w.dw_b); ab.f32(ones, &w.cn_w); ab.f32(zeros, &w.cn_b);
+        }
+      } else if (missing.empty()) { ab.f32(W, &w.dw_w); ab.f32(B, &w.dw_b); }
     }
-    nrm("conv_module.norm", &w.cn_w, &w.cn_b);
+    if (h->cfg.conv_norm != 1) nrm("conv_module.norm", &w.cn_w, &w.cn_b);
     lin("conv_module.pointwise_conv2", d, d, &w.pw2_w, &w.pw2_b);
     nrm("norm_ff_macaron", &w.ln_ffm_w, &w.ln_ffm_b);
     nrm("norm_mha", &w.ln_mha_w, &w.ln_mha_b);
@@ -709,9 +726,9 @@ extern "C" size_t cf_workspace_bytes(const cf_handle* h, const cf_plan* p) {
 // --------------------------------------------------------------------------------------------------------------------
 // The next cf_encode call carries `n_streams` concurrent streams (frame-synchronous streaming): the plan holds one utterance
 // of `placeholder_chunks` + 1 chunks per stream and the caches are (L, B, H, l, 2 d_k) / (L, B, d, lorder), updated in place.
-extern "C" int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_chunks) {
-  if (!h || n_streams < 0 || placeholder_chunks < 0) return fail(h, CF_ERR_INVALID, "cf_encode_streams: bad argument");
-  h->streams_n = n_streams; h->streams_ph = placeholder_chunks;
+extern "C" int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_chunks, int advance) {
+  if (!h || n_streams < 0 || placeholder_chunks < 0 || advance < 0) return fail(h, CF_ERR_INVALID, "cf_encode_streams: bad argument");
+  h->streams_n = n_streams; h->streams_ph = placeholder_chunks; h->streams_adv = advance;
   return CF_OK;
 }
 
@@ -732,7 +749,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   if (p->kernel != h->cfg.kernel) return fail(h, CF_ERR_INVALID, "cf_encode: plan conv kernel differs from the model's");
   // per-call state armed by cf_encode_streams / cf_encode_feature_events is consumed here, so that every exit path clears it
   const int ns = h->streams_n, ph = h->streams_ph;
-  h->streams_n = 0; h->streams_ph = 0;
+  // frames a stream advances per step: the plan's chunk, or less when the chunk carries right-context frames behind it
+  const int adv = (h->streams_adv > 0 && ns > 0) ? h->streams_adv : p->c;
+  h->streams_n = 0; h->streams_ph = 0; h->streams_adv = 0;
   std::vector<cudaEvent_t> ev;
   std::vector<int64_t> ev_rows;
   ev.swap(h->ev);
@@ -744,6 +763,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       if (p->n_chunks[u] != ph + 1) return fail(h, CF_ERR_INVALID, "cf_encode: every stream must span placeholder_chunks + 1 chunks");
     if (ph * p->c < std::max(p->l, p->lorder) || p->r != 0)
       return fail(h, CF_ERR_INVALID, "cf_encode: placeholder rows must cover the left context and the conv cache; right context must be 0");
+    if (adv > p->c) return fail(h, CF_ERR_INVALID, "cf_encode: a stream cannot advance by more than the plan's chunk size");
   } else if ((att_cache || cnn_cache) && (p->mode != 0 || p->B != 1))
     return fail(h, CF_ERR_INVALID, "cf_encode: streaming caches need a masked-batch plan with one utterance");
   if ((att_cache != nullptr) != (cnn_cache != nullptr))
@@ -971,7 +991,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       const long long tot = (long long)ns * l * H * 2 * dk;
       float* cl = static_cast<float*>(att_cache) + size_t(i) * tot;
       att_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, c, l, 0);
-      att_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, c, l, 1);
+      att_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, adv, l, 1);
       cf::g_kernel_launches += 2;
     }
     { AttnParams a{};
@@ -993,12 +1013,14 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       const long long tot = (long long)ns * d * lo;
       float* cl = static_cast<float*>(cnn_cache) + size_t(i) * tot;
       cnn_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.g, ns, d, lo, (ph + 1) * c, ph * c, c, lo, 0);
-      cnn_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.g, ns, d, lo, (ph + 1) * c, ph * c, c, lo, 1);
+      cnn_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.g, ns, d, lo, (ph + 1) * c, ph * c, adv, lo, 1);
       cf::g_kernel_launches += 2;
     }
     { DwConvParams q{};
       q.g = w.g; q.z = w.z; q.w = lw.dw_w; q.bias = lw.dw_b; q.ln_w = lw.cn_w; q.ln_b = lw.cn_b; q.range = w.conv_range; q.c = c; q.n_chunks = n;
-      CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, (long long)w.g_rows, h->num_sms)); }
+      q.no_norm = h->cfg.conv_norm == 1;
+      q.sub_chunk = adv < c ? adv : 0;     // streaming with right context: the conv is cut at the true chunk grid
+      CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, q.sub_chunk > 0 ? 0 : (long long)w.g_rows, h->num_sms)); }
     { EpiArgs e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
       e.row_range = w.out_range; e.rows_per_chunk = c;
       if (fuse_ln) {

@@ -108,6 +108,10 @@ struct DwConvParams {
   const int2* range;    // [n_chunks] valid window-slot range
   int c;                // chunk size (frames)
   int n_chunks;
+  int sub_chunk;        // > 0 (streaming with right context, generic kernel only): output frame f of a chunk only sees window
+                        // slots left of the end of its sub-chunk of `sub_chunk` frames, q < (f / sub_chunk + 1) * sub_chunk + lorder
+                        // (convolution.py:150-167 with chunk_size = sub_chunk on a sequence of chunk + right-context frames)
+  int no_norm;          // 1: no LayerNorm (cnn_module_norm = batch_norm: the eval-mode affine is folded into w / bias), z = SiLU(conv)
 };
 
 
@@ -182,10 +186,13 @@ __global__ void __launch_bounds__(D / 2) dwconv_ln_silu_kernel(DwConvParams p) {
 #pragma unroll
   for (int f = 0; f < FG; ++f) {
     float a0 = bias0, a1 = bias1;
+    // first window slot this output frame may NOT see (right edge of its sub-chunk + lorder); no limit without sub-chunks
+    const int lim = p.sub_chunk > 0 ? ((f0 + f) / p.sub_chunk + 1) * p.sub_chunk + KW / 2 : 0x7fffffff;
 #pragma unroll
     for (int t = 0; t < KW; ++t) {
-      a0 = fmaf(w0[t], bf16_lo(in[f + t]), a0);
-      a1 = fmaf(w1[t], bf16_hi(in[f + t]), a1);
+      const bool ok = f0 + f + t < lim;
+      a0 = fmaf(w0[t], ok ? bf16_lo(in[f + t]) : 0.f, a0);
+      a1 = fmaf(w1[t], ok ? bf16_hi(in[f + t]) : 0.f, a1);
     }
     o0[f] = a0; o1[f] = a1;
   }
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(D / 2) dwconv_ln_silu_kernel(DwConvParams p) {
   uint32_t* zp = reinterpret_cast<uint32_t*>(p.z) + ((long long)chunk * p.c + f0) * (D / 2) + tid;
 #pragma unroll
   for (int f = 0; f < FG; ++f) {
-    const float mean = s_mean[f], rstd = s_rstd[f];
+    const float mean = p.no_norm ? 0.f : s_mean[f], rstd = p.no_norm ? 1.f : s_rstd[f];
     const float y0 = (o0[f] - mean) * rstd * lw0 + lb0;
     const float y1 = (o1[f] - mean) * rstd * lw1 + lb1;
     zp[(long long)f * (D / 2)] = pack_bf16(silu(y0), silu(y1));
@@ -358,6 +365,7 @@ dwconv_ln_silu_tma_kernel(const __grid_constant__ CUtensorMap tma_g, DwConvParam
       const float var = fmaxf(q * (1.0f / D) - mean * mean, 0.f);
       rs = rsqrtf(var + 1e-5f);
       nm = -mean * rs;
+      if (p.no_norm) { rs = 1.f; nm = 0.f; }
     }
     uint32_t* zp = reinterpret_cast<uint32_t*>(p.z) + ((long long)chunk * p.c + f0) * (D / 2) + tid;
 #pragma unroll

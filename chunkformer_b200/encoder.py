@@ -39,7 +39,8 @@ class ChunkFormerEncoderB200:
             raise RuntimeError("ChunkFormerEncoderB200 runs on CUDA devices only (no CPU fallback)")
         self._L = _lib.load()
         cfg = _lib.CfConfig(geometry.d_model, geometry.heads, geometry.ffn, geometry.layers, geometry.kernel,
-                            geometry.vocab, geometry.feat_dim, 1 if geometry.has_cmvn else 0)
+                            geometry.vocab, geometry.feat_dim, 1 if geometry.has_cmvn else 0,
+                            1 if geometry.conv_norm == "batch_norm" else 0)
         h = c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.check(self._L.cf_create(ctypes.byref(cfg), int(idx), ctypes.byref(h)), None, "cf_create")
@@ -219,28 +220,34 @@ class ChunkFormerEncoderB200:
     def forward_chunk(self, xs: torch.Tensor, att_cache: torch.Tensor = torch.zeros((0, 0, 0, 0, 0)),
                       cnn_cache: torch.Tensor = torch.zeros((0, 0, 0, 0)), chunk_size: int = 0, left_context_size: int = 0,
                       right_context_size: int = 0, offset: int = 0, donate_caches: bool = False):
-        """One streaming step for B concurrent streams; drop-in for ChunkFormerEncoder.forward_chunk (encoder.py:310-390) at
-        right_context_size = 0 (every shipped streaming preset, apps/realtime-asr/config.py:86-110).
+        """One streaming step for B concurrent streams; drop-in for ChunkFormerEncoder.forward_chunk (encoder.py:310-390).
 
-        xs (B, 8 (c - 1) + 15, feat) = the new c encoder frames of every stream; att_cache (L, B, H, l, 2 d_k) and cnn_cache
-        (L, B, d, 7) as returned by the previous step (empty = zeros = start of the streams); offset = encoder frames already
-        consumed.  Returns (out (B, c, d), ones mask (B, 1, c), new att_cache, new cnn_cache).
+        xs (B, 8 (c + r - 1) + 15, feat) = the new c encoder frames of every stream plus r frames of right context; att_cache
+        (L, B, H, l, 2 d_k) and cnn_cache (L, B, d, 7) as returned by the previous step (empty = zeros = start of the streams);
+        offset = encoder frames already consumed.  Returns (out (B, c + r, d), ones mask (B, 1, c + r), new att_cache,
+        new cnn_cache); the caller keeps the first c rows of every step but the last (forward_chunk_by_chunk does).
 
-        With r = 0 a step is, per stream, the masked-chunk path on one chunk with that stream's caches and
-        truncated_context_size = c (oracle.forward_chunk, pinned against the reference).  All B streams share one encoder pass
-        (cf_encode_streams): every stream carries its left context as placeholder rows that cf_encode fills from the caches.
+        A step is, per stream, the masked-chunk path on ONE chunk of c + r frames with that stream's caches: the reference
+        embeds and attends chunk + right context as a single chunk with left context l (encoder.py:341-347), cuts the conv
+        module at the chunk grid (chunk_size = c inside convolution.py:150-167) and ends the returned caches where the chunk
+        ends (encoder.py:376-385); oracle.forward_chunk restates it, pinned against the reference (tests/golden/stream.npz,
+        stream_right.npz).  All B streams share one encoder pass (cf_encode_streams): every stream carries its left context
+        as placeholder rows that cf_encode fills from the caches.  With r = 0 (every shipped streaming preset,
+        apps/realtime-asr/config.py:86-110) the tcgen05 attention kernels run; chunk + r is in general not a tile-friendly
+        size, those steps take the CUDA-core attention fallback.
 
         donate_caches=True: the passed device fp32 caches are updated in place and returned (a serving loop hands the returned
         caches straight back in, so the copies the reference's functional style implies, 1 GB per step for CTC-large at 256
         streams, are pure waste); the default keeps the reference's behaviour of leaving the arguments untouched."""
-        if right_context_size != 0:
-            raise NotImplementedError("forward_chunk is built for right_context_size = 0 (the shipped streaming presets)")
-        c, l = int(chunk_size), int(left_context_size)
-        if c <= 0 or l < self.geo.kernel // 2 or xs.dim() != 3:
-            raise ValueError("forward_chunk needs xs (B, T, feat), chunk_size > 0 and left_context_size >= kernel // 2")
+        c, l, r = int(chunk_size), int(left_context_size), int(right_context_size)
+        if c <= 0 or r < 0 or l < self.geo.kernel // 2 or xs.dim() != 3:
+            raise ValueError("forward_chunk needs xs (B, T, feat), chunk_size > 0, right_context_size >= 0 and "
+                             "left_context_size >= kernel // 2")
         B, T, _ = xs.shape
-        if T != 8 * (c - 1) + 15:
-            raise ValueError(f"forward_chunk expects {8 * (c - 1) + 15} input frames per step for chunk_size {c}, got {T}")
+        cc = c + r                                   # frames embedded and attended as one chunk
+        if T != 8 * (cc - 1) + 15:
+            raise ValueError(f"forward_chunk expects {8 * (cc - 1) + 15} input frames per step for chunk_size {c} and "
+                             f"right_context_size {r}, got {T}")
         L, H, d, lo = self.geo.layers, self.geo.heads, self.geo.d_model, self.geo.kernel // 2
         if att_cache.numel() == 0:
             att_cache = torch.zeros((L, B, H, l, 2 * d // H), device=self.device)
@@ -251,40 +258,38 @@ class ChunkFormerEncoderB200:
         # one pass for all streams: stream s = an utterance of `ph` placeholder chunks (zeros in, their K/V and conv rows are
         # overwritten with the stream's caches inside cf_encode) + the real chunk; the negative plan offset masks the part of
         # the left context that is not filled yet (valid cache rows = min(offset, l))
-        ph = -(-max(l, lo) // c)
+        ph = -(-max(l, lo) // cc)
 
         def own(t):
             if donate_caches and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous():
                 return t
             return t.to(self.device, torch.float32).contiguous().clone()
         new_att, new_cnn = own(att_cache), own(cnn_cache)
-        t_tot = ph * 8 * c + T
+        t_tot = ph * 8 * cc + T
         x_dev = torch.zeros((B, t_tot, xs.shape[2]), dtype=torch.float32, device=self.device)
-        x_dev[:, ph * 8 * c:] = xs.to(self.device, torch.float32)
-        plan = Plan(c, l, 0, [t_tot] * B, [-(ph * c - min(int(offset), l))] * B, self.geo.kernel)
-        _lib.check(self._L.cf_encode_streams(self._h, B, ph), self._h, "cf_encode_streams")
+        x_dev[:, ph * 8 * cc:] = xs.to(self.device, torch.float32)
+        plan = Plan(cc, l, 0, [t_tot] * B, [-(ph * cc - min(int(offset), l))] * B, self.geo.kernel)
+        _lib.check(self._L.cf_encode_streams(self._h, B, ph, c), self._h, "cf_encode_streams")
         o, _ = self.encode_plan(plan, x_dev.view(B * t_tot, -1), new_att, new_cnn, 0)
-        out = o.view(B, (ph + 1) * c, d)[:, ph * c:].contiguous()
-        return out, torch.ones((B, 1, c), dtype=torch.bool, device=self.device), new_att, new_cnn
+        out = o.view(B, (ph + 1) * cc, d)[:, ph * cc:].contiguous()
+        return out, torch.ones((B, 1, cc), dtype=torch.bool, device=self.device), new_att, new_cnn
 
     @torch.no_grad()
     def forward_chunk_by_chunk(self, xs: torch.Tensor, xs_lens: torch.Tensor, chunk_size: int = 0, left_context_size: int = 0,
                                right_context_size: int = 0):
         """Streaming simulation over whole utterances; drop-in for ChunkFormerEncoder.forward_chunk_by_chunk
-        (encoder.py:392-459) at right_context_size = 0.  Returns (out (B, steps * c, d), masks (B, 1, T'))."""
-        if right_context_size != 0:
-            raise NotImplementedError("forward_chunk_by_chunk is built for right_context_size = 0")
-        c, l = int(chunk_size), int(left_context_size)
+        (encoder.py:392-459).  Returns (out (B, steps * c [+ r rows of the last step], d), masks (B, 1, T'))."""
+        c, l, r = int(chunk_size), int(left_context_size), int(right_context_size)
         B, T, _ = xs.shape
-        size, stride = 8 * (c - 1) + 15, 8 * c
+        size, stride = 8 * (c - 1) + 15 + 8 * r, 8 * c
         pad = stride - ((T - size) % stride)
         xp = torch.nn.functional.pad(xs.to(self.device, torch.float32), (0, 0, 0, pad))
         att = torch.zeros((0, 0, 0, 0, 0))
         cnn = torch.zeros((0, 0, 0, 0))
         outs, offset = [], 0
         for i in range(0, xp.shape[1] - size + stride, stride):
-            o, _, att, cnn = self.forward_chunk(xp[:, i:i + size], att, cnn, c, l, 0, offset, donate_caches=True)
-            outs.append(o)
+            o, _, att, cnn = self.forward_chunk(xp[:, i:i + size], att, cnn, c, l, r, offset, donate_caches=True)
+            outs.append(o[:, :c] if i + size < xp.shape[1] else o)      # encoder.py:449
             offset += c
         out = torch.cat(outs, dim=1)
 

@@ -20,6 +20,7 @@ class EncoderGeometry:
     vocab: int = 5000
     feat_dim: int = 80
     has_cmvn: bool = False
+    conv_norm: str = "layer_norm"      # cnn_module_norm: "layer_norm" | "batch_norm" (eval-mode BatchNorm1d, convolution.py:83-89)
 
     @property
     def d_k(self) -> int:
@@ -45,8 +46,9 @@ class EncoderGeometry:
             raise ValueError("only pos_enc_layer_type=chunk_rel_pos is supported")
         if ec.get("selfattention_layer_type", "chunk_rel_seflattn") != "chunk_rel_seflattn":
             raise ValueError("only selfattention_layer_type=chunk_rel_seflattn is supported")
-        if ec.get("cnn_module_norm", "batch_norm") != "layer_norm":
-            raise ValueError("only cnn_module_norm=layer_norm is supported")
+        conv_norm = ec.get("cnn_module_norm", "batch_norm")        # the reference constructor's default (encoder.py:59)
+        if conv_norm not in ("layer_norm", "batch_norm"):
+            raise ValueError("cnn_module_norm must be layer_norm or batch_norm")
         if not ec.get("dynamic_conv", False):
             raise ValueError("dynamic_conv must be true (the reference's masked-batch path requires it)")
         if not ec.get("normalize_before", True) or not ec.get("macaron_style", True):
@@ -60,7 +62,7 @@ class EncoderGeometry:
         return cls(d_model=ec.get("output_size", 256), heads=ec.get("attention_heads", 4),
                    ffn=ec.get("linear_units", 2048), layers=ec.get("num_blocks", 6),
                    kernel=ec.get("cnn_module_kernel", 15), vocab=vocab, feat_dim=input_dim,
-                   has_cmvn=has_cmvn)
+                   has_cmvn=has_cmvn, conv_norm=conv_norm)
 
 
 CTC_LARGE = EncoderGeometry(512, 8, 2048, 17, 15, 5000)       # docs/paper.pdf III.A, Table III

@@ -17,7 +17,7 @@ FAMILY_OTHER, FAMILY_FFN_W1, FAMILY_FFN_W2, FAMILY_FFN_FUSED = 0, 1, 2, 3
 
 
 class CfConfig(ctypes.Structure):
-    _fields_ = [(n, c_int32) for n in ("d_model", "heads", "ffn", "layers", "kernel", "vocab", "feat_dim", "has_cmvn")]
+    _fields_ = [(n, c_int32) for n in ("d_model", "heads", "ffn", "layers", "kernel", "vocab", "feat_dim", "has_cmvn", "conv_norm")]
 
 
 # every symbol include/chunkformer_b200.h declares: (restype, argtypes)
@@ -47,7 +47,7 @@ SIGNATURES = {
     "cf_workspace_bytes": (c_size_t, [c_void_p, c_void_p]),
     "cf_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                           c_size_t, c_void_p]),
-    "cf_encode_streams": (c_int, [c_void_p, c_int, c_int]),
+    "cf_encode_streams": (c_int, [c_void_p, c_int, c_int, c_int]),
     "cf_ctc_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int]),
     "cf_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cf_ctc_compact_workspace_bytes": (c_size_t, [c_int64]),

@@ -66,6 +66,10 @@ def synth_state_dict(geo: EncoderGeometry, seed: int = 0) -> Dict[str, torch.Ten
         linear(p + "conv_module.pointwise_conv1", 2 * d, d, shape=(2 * d, d, 1))
         linear(p + "conv_module.depthwise_conv", d, K, shape=(d, 1, K))
         norm(p + "conv_module.norm")
+        if geo.conv_norm == "batch_norm":          # BatchNorm1d buffers (inference uses the running statistics)
+            sd[p + "conv_module.norm.running_mean"] = _n(g, (d,), 0.3)
+            sd[p + "conv_module.norm.running_var"] = 0.5 + torch.rand((d,), generator=g, dtype=torch.float32)
+            sd[p + "conv_module.norm.num_batches_tracked"] = torch.tensor(100, dtype=torch.long)
         linear(p + "conv_module.pointwise_conv2", d, d, shape=(d, d, 1))
         for name in ("norm_ff", "norm_mha", "norm_ff_macaron", "norm_conv", "norm_final"):
             norm(p + name)

@@ -52,6 +52,8 @@ typedef struct cf_config {
   int32_t vocab;      /* CTC output size, 0 = no CTC head */
   int32_t feat_dim;   /* input_size (80) */
   int32_t has_cmvn;   /* encoder.global_cmvn.{mean,istd} present */
+  int32_t conv_norm;  /* cnn_module_norm of the conv module: 0 = layer_norm, 1 = batch_norm (eval mode: running statistics,
+                         folded into the depthwise conv at weight load; convolution.py:83-89) */
 } cf_config;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------------- */
@@ -147,7 +149,11 @@ CF_API int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, void* a
  * min(frames already consumed, left_context)) masks the part of the cache that is not filled yet) and its caches as device fp32
  * att_cache (L, n_streams, H, left_context, 2 d_k) / cnn_cache (L, n_streams, d, 7), the layouts forward_chunk takes and
  * returns; both are updated in place.  The rows of the last chunk of every utterance are the step's output. */
-CF_API int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_chunks);
+/* advance = frames every stream moves forward per step: 0 or the plan's chunk size for right_context_size = 0; with a right
+ * context r the plan's chunk is chunk + r (chunk and right context are embedded and attended as ONE chunk, encoder.py:341-347),
+ * advance = chunk: the caches then end where the chunk ends (encoder.py:376-385) and the conv module is cut into sub-chunks of
+ * `advance` frames with zeros to their right (convolution.py:150-167). */
+CF_API int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_chunks, int advance);
 
 /* ---- CTC head ---------------------------------------------------------------------------------------------------- */
 CF_API size_t cf_ctc_workspace_bytes(const cf_handle* h, int64_t rows, int enc_dtype);

@@ -168,6 +168,15 @@ def rel_pos_table(d: int, c: int, l: int, r: int) -> torch.Tensor:
     return pe
 
 
+def _conv_norm(sd, cm, z):
+    """The conv module's norm over the channel dimension (convolution.py:83-89): LayerNorm, or eval-mode BatchNorm1d (running
+    statistics) when the checkpoint carries them (cnn_module_norm: batch_norm, the constructor default)."""
+    if cm + "norm.running_mean" in sd:
+        return (z - sd[cm + "norm.running_mean"]) / torch.sqrt(sd[cm + "norm.running_var"] + 1e-5) * sd[cm + "norm.weight"] \
+            + sd[cm + "norm.bias"]
+    return _ln(z, sd[cm + "norm.weight"], sd[cm + "norm.bias"])
+
+
 def _ln(x, w, b, eps=1e-5):
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
@@ -242,8 +251,11 @@ def _attention(sd, p, H, y, plan: Plan, pe, att_cache, trunc):
     return ctx @ sd[p + "linear_out.weight"].T + sd[p + "linear_out.bias"], new_cache
 
 
-def _conv_module(sd, p, y, plan: Plan, cnn_cache, trunc):
-    """convolution.py:194-255 on flat frames.  y: (n*c, d).  Returns (out, new_cache (d, lorder) or None)."""
+def _conv_module(sd, p, y, plan: Plan, cnn_cache, trunc, sub_chunk: int = 0):
+    """convolution.py:194-255 on flat frames.  y: (n*c, d).  Returns (out, new_cache (d, lorder) or None).
+    sub_chunk > 0 (frame-synchronous streaming with right context, encoder.py:310-385 -> convolution.py:101-192 with
+    chunk_size = sub_chunk): the plan's chunk holds chunk + right-context frames, and the dynamic conv cuts it into sub-chunks
+    of `sub_chunk` frames, each seeing real left context but ZEROS to its right (convolution.py:150-167)."""
     c, lo = plan.c, plan.lorder
     n = plan.n
     d = y.shape[1]
@@ -260,10 +272,14 @@ def _conv_module(sd, p, y, plan: Plan, cnn_cache, trunc):
     gw = gf[win] * torch.from_numpy(plan.conv_mask).unsqueeze(-1)                   # (n, c+2lo, d)
     wd = sd[p + "depthwise_conv.weight"].view(d, -1)                                # (d, K)
     z = torch.zeros(n, c, d)
+    fr = torch.arange(c)
     for tau in range(wd.shape[1]):
-        z = z + gw[:, tau:tau + c, :] * wd[:, tau]
+        term = gw[:, tau:tau + c, :] * wd[:, tau]
+        if sub_chunk > 0:                   # window slot f + tau <-> frame f - lo + tau must lie left of the sub-chunk's end
+            term = term * ((fr + tau) < ((fr // sub_chunk + 1) * sub_chunk + lo)).view(1, c, 1)
+        z = z + term
     z = z + sd[p + "depthwise_conv.bias"]
-    z = _ln(z, sd[p + "norm.weight"], sd[p + "norm.bias"])
+    z = _conv_norm(sd, p, z)
     z = z * torch.sigmoid(z)
     w2 = sd[p + "pointwise_conv2.weight"].view(d, d)
     out = z.view(n * c, d) @ w2.T + sd[p + "pointwise_conv2.bias"]
@@ -271,14 +287,14 @@ def _conv_module(sd, p, y, plan: Plan, cnn_cache, trunc):
     return out * centre, new_cache
 
 
-def _layer(sd, i, H, x, plan, pe, att_cache, cnn_cache, trunc):
+def _layer(sd, i, H, x, plan, pe, att_cache, cnn_cache, trunc, sub_chunk: int = 0):
     """encoder_layer.py:155-248 (pre-norm, macaron, dropout = identity)."""
     p = f"encoder.encoders.{i}."
     ln = lambda name, t: _ln(t, sd[p + name + ".weight"], sd[p + name + ".bias"])  # noqa: E731
     x = x + 0.5 * _ffn(sd, p + "feed_forward_macaron", ln("norm_ff_macaron", x))
     a, new_att = _attention(sd, p + "self_attn.", H, ln("norm_mha", x), plan, pe, att_cache, trunc)
     x = x + a
-    cv, new_cnn = _conv_module(sd, p + "conv_module.", ln("norm_conv", x), plan, cnn_cache, trunc)
+    cv, new_cnn = _conv_module(sd, p + "conv_module.", ln("norm_conv", x), plan, cnn_cache, trunc, sub_chunk)
     x = x + cv
     x = x + 0.5 * _ffn(sd, p + "feed_forward", ln("norm_ff", x))
     return ln("norm_final", x), new_att, new_cnn
@@ -302,7 +318,7 @@ def forward_parallel_chunk(sd: Dict[str, torch.Tensor], heads: int, xs: Sequence
                            att_cache: Optional[torch.Tensor] = None,
                            cnn_cache: Optional[torch.Tensor] = None,
                            truncated_context_size: int = 0,
-                           offsets: Optional[Sequence[int]] = None, num_layers: Optional[int] = None):
+                           offsets: Optional[Sequence[int]] = None, num_layers: Optional[int] = None, conv_sub_chunk: int = 0):
     """ChunkFormerEncoder.forward_parallel_chunk (encoder.py:503-681).
 
     att_cache (L, l, H, 2*d_k) / cnn_cache (L, d, lorder) or None (= the reference's empty caches).
@@ -322,7 +338,7 @@ def forward_parallel_chunk(sd: Dict[str, torch.Tensor], heads: int, xs: Sequence
     for i in range(L):
         x, a, cv = _layer(sd, i, heads, x, plan, pe,
                           None if att_cache is None else att_cache[i],
-                          None if cnn_cache is None else cnn_cache[i], truncated_context_size)
+                          None if cnn_cache is None else cnn_cache[i], truncated_context_size, conv_sub_chunk)
         new_att.append(a)
         new_cnn.append(cv)
     x = _ln(x, sd["encoder.after_norm.weight"], sd["encoder.after_norm.bias"])
@@ -472,7 +488,7 @@ def forward_encoder(sd: Dict[str, torch.Tensor], heads: int, xs: torch.Tensor, x
         for tau in range(wd.shape[1]):
             z = z + gw[:, :, tau:tau + c, :] * wd[:, tau]
         z = z + sd[cm + "depthwise_conv.bias"]
-        z = _ln(z, sd[cm + "norm.weight"], sd[cm + "norm.bias"])
+        z = _conv_norm(sd, cm, z)
         z = (z * torch.sigmoid(z)).view(B, Tpad, d)[:, :Tp]
         cv = z @ sd[cm + "pointwise_conv2.weight"].view(d, d).T + sd[cm + "pointwise_conv2.bias"]
         x = x + cv * valid.unsqueeze(-1)
@@ -487,46 +503,46 @@ def forward_encoder(sd: Dict[str, torch.Tensor], heads: int, xs: torch.Tensor, x
 # --------------------------------------------------------------------------------------------
 def forward_chunk(sd, heads: int, xs: torch.Tensor, att_cache: torch.Tensor, cnn_cache: torch.Tensor, c: int, l: int, r: int = 0,
                   offset: int = 0):
-    """ChunkFormerEncoder.forward_chunk (encoder.py:310-390) for right_context_size = 0 (every shipped streaming preset:
-    apps/realtime-asr/config.py:86-110).  xs (B, 8(c-1)+15, feat); att_cache (L, B, H, l, 2 d_k); cnn_cache (L, B, d, lorder).
+    """ChunkFormerEncoder.forward_chunk (encoder.py:310-390).  xs (B, 8(c + r - 1) + 15, feat); att_cache (L, B, H, l, 2 d_k);
+    cnn_cache (L, B, d, lorder).
 
-    With r = 0 one step is, per stream, exactly the masked-chunk call on a single chunk with the stream's caches and
-    truncated_context_size = c: the attention sees [cache (l rows, valid where >= l - offset) | c frames] (attention.py:323-330
-    + the flipped `< c + offset` mask of encoder.py:349-355), the conv sees [cache (7) | c frames | zeros], and the returned
-    caches are the last l / 7 rows (encoder.py:376-388) = rows [c, c + l) / [c - 7, c) of cache + frames.
+    One step is, per stream, the masked-chunk call on a single chunk of c + r frames with the stream's caches: the embedding
+    and the attention treat chunk + right context as ONE chunk of c + r frames with left context l and no right context
+    (encoder.py:341-347, attention.py:323-330; keys = [cache (l rows, valid where >= l - offset, the flipped mask of
+    encoder.py:349-355) | c + r frames]); the conv module runs with chunk_size = c, i.e. it cuts the c + r frames into
+    sub-chunks of c frames with zeros to the right of each (convolution.py:150-167); the returned caches end where the
+    CHUNK ends, not the right context: rows [c, c + l) / [c - 7, c) of cache + frames (encoder.py:376-385).
     Pinned against the reference in tests/test_oracle_golden.py::test_streaming_*.
-    Returns (out (B, c, d), new att_cache, new cnn_cache)."""
-    if r != 0:
-        raise NotImplementedError("forward_chunk is restated for right_context_size = 0 only")
+    Returns (out (B, c + r, d), new att_cache, new cnn_cache)."""
     B = xs.shape[0]
+    cc = c + r
     outs, atts, cnns = [], [], []
     for b in range(B):
         a_in = att_cache[:, b].transpose(1, 2)                      # (L, l, H, 2 d_k)
-        o, _, _, a, cv, _ = forward_parallel_chunk(sd, heads, [xs[b]], [int(xs.shape[1])], c, l, 0, a_in, cnn_cache[:, b], c,
-                                                   [int(offset)])
-        outs.append(o.reshape(-1, o.shape[-1])[:c])
+        o, _, _, a, cv, _ = forward_parallel_chunk(sd, heads, [xs[b]], [int(xs.shape[1])], cc, l, 0, a_in, cnn_cache[:, b], c,
+                                                   [int(offset)], conv_sub_chunk=c if r > 0 else 0)
+        outs.append(o.reshape(-1, o.shape[-1])[:cc])
         atts.append(a.transpose(1, 2))                              # back to (L, H, l, 2 d_k)
         cnns.append(cv)
     return torch.stack(outs), torch.stack(atts, 1), torch.stack(cnns, 1)
 
 
 def forward_chunk_by_chunk(sd, heads: int, xs: torch.Tensor, xs_lens: Sequence[int], c: int, l: int, r: int = 0):
-    """ChunkFormerEncoder.forward_chunk_by_chunk (encoder.py:392-459), right context 0: (out (B, steps * c, d), mask (B, 1, T'))."""
-    if r != 0:
-        raise NotImplementedError("forward_chunk_by_chunk is restated for right_context_size = 0 only")
+    """ChunkFormerEncoder.forward_chunk_by_chunk (encoder.py:392-459): (out (B, steps * c [+ r for the last step], d),
+    mask (B, 1, T'))."""
     B, T, _ = xs.shape
     L = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("encoder.encoders."))
     d = sd["encoder.after_norm.weight"].shape[0]
     lo = sd["encoder.encoders.0.conv_module.depthwise_conv.weight"].shape[-1] // 2
-    size, stride = SUB * (c - 1) + CTX, SUB * c
+    size, stride = SUB * (c - 1) + CTX + SUB * r, SUB * c
     pad = stride - ((T - size) % stride)                            # encoder.py:417-419 (always pads, a full stride if aligned)
     xp = F.pad(xs.float(), (0, 0, 0, pad))
     att = torch.zeros((L, B, heads, l, 2 * d // heads))
     cnn = torch.zeros((L, B, d, lo))
     outs, offset = [], 0
     for i in range(0, xp.shape[1] - size + stride, stride):
-        o, att, cnn = forward_chunk(sd, heads, xp[:, i:i + size], att, cnn, c, l, 0, offset)
-        outs.append(o)
+        o, att, cnn = forward_chunk(sd, heads, xp[:, i:i + size], att, cnn, c, l, r, offset)
+        outs.append(o[:, :c] if i + size < xp.shape[1] else o)      # encoder.py:449: the right-context rows only of the last step
         offset += c
     out = torch.cat(outs, 1)
     enc_lens = [calc_length(int(t) + pad) for t in xs_lens]

@@ -27,7 +27,7 @@ LARGE = EncoderGeometry(d_model=512, heads=8, ffn=2048, layers=17, kernel=15, vo
 
 def build_reference(geo: EncoderGeometry, seed: int):
     Model, Config = import_reference()
-    cfg = reference_config_dict(geo.d_model, geo.heads, geo.ffn, geo.layers, geo.vocab, geo.kernel)
+    cfg = reference_config_dict(geo.d_model, geo.heads, geo.ffn, geo.layers, geo.vocab, geo.kernel, geo.conv_norm)
     model = Model(Config.from_dict(cfg)).eval()
     sd = synth_state_dict(geo, seed)
     enc = model.model.encoder

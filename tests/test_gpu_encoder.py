@@ -277,6 +277,32 @@ def test_shipped_geometries_match_oracle(name, geo, cfg):
     assert bool(ok.all()), f"{int((~ok).sum())} token mismatches above the margin tolerance"
 
 
+SMALL_BN = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=3, kernel=15, vocab=300, conv_norm="batch_norm")
+
+
+@pytest.mark.parametrize("cfg", [(16, 32, 16), (64, 128, 128)])
+def test_batch_norm_conv_module_matches_oracle(cfg):
+    """cnn_module_norm: batch_norm (the reference constructor's default, encoder.py:59): the eval-mode BatchNorm1d of the conv
+    module is folded into the depthwise conv at weight load; masked batch and padded-batch encode path against the oracle
+    (pinned to the unmodified reference by tests/golden/tiny_bn.npz)."""
+    c, l, r = cfg
+    sd, enc = _model(SMALL_BN, 17)
+    lens = [700, 9, 131, 8 * c * 3 + 77, 15, 2000]
+    xs = [synth_fbank(t, seed=100 + k) for k, t in enumerate(lens)]
+    ref, ref_lens, ref_nck, _, _, _ = O.forward_parallel_chunk(sd, SMALL_BN.heads, xs, lens, c, l, r)
+    out, out_lens, nck, *_ = enc.forward_parallel_chunk(xs, torch.tensor(lens, dtype=torch.int32), c, l, r,
+                                                        offset=torch.zeros(len(lens), dtype=torch.int32))
+    assert nck == ref_nck and out_lens.tolist() == ref_lens.tolist()
+    _compare(_valid_rows(out, nck, out_lens, 256), _valid_rows(ref, nck, out_lens, 256), f"batch_norm {cfg}")
+    xb = torch.zeros(2, 333, 80)
+    xb[0], xb[1, :180] = synth_fbank(333, seed=300), synth_fbank(180, seed=301)
+    ref2, ref_mask = O.forward_encoder(sd, SMALL_BN.heads, xb, [333, 180], c, l, r)
+    out2, mask = enc.forward_encoder(xb, torch.tensor([333, 180]), c, l, r)
+    assert torch.equal(mask.cpu(), ref_mask)
+    for b, m in enumerate(ref_mask.squeeze(1).sum(-1).tolist()):
+        _compare(out2[b, :m], ref2[b, :m], f"batch_norm forward_encoder {cfg} utt {b}")
+
+
 DK64 = EncoderGeometry(d_model=256, heads=4, ffn=512, layers=3, kernel=15, vocab=300)
 DK128 = EncoderGeometry(d_model=256, heads=2, ffn=512, layers=3, kernel=15, vocab=300)
 
@@ -362,10 +388,35 @@ def test_forward_chunk_by_chunk_matches_oracle(c, l, B, T):
     _compare(cnn_g, cnn_o, "cnn cache")
 
 
+@pytest.mark.parametrize("c,l,r,B,T", [(8, 16, 4, 2, 555), (4, 12, 4, 1, 300), (8, 24, 12, 2, 411), (16, 32, 7, 3, 700), (8, 40, 8, 2, 400)])
+def test_forward_chunk_with_right_context_matches_oracle(c, l, r, B, T):
+    """forward_chunk / forward_chunk_by_chunk with right_context_size > 0 (encoder.py:310-385) against the oracle, which is
+    pinned to the reference's own streaming path with right context (tests/test_oracle_golden.py::
+    test_streaming_with_right_context): every step's outputs, the c + r rows of an explicit step and both caches."""
+    sd, enc = _model(SMALL, 5)
+    xs = torch.stack([synth_fbank(T, seed=95 + b) for b in range(B)])
+    want, want_mask = O.forward_chunk_by_chunk(sd, SMALL.heads, xs, [T] * B, c, l, r)
+    got, got_mask = enc.forward_chunk_by_chunk(xs.to(DEV), torch.full((B,), T), c, l, r)
+    assert got.shape == want.shape and torch.equal(got_mask.cpu(), want_mask)
+    _compare(got, want, f"stream {c}/{l}/{r}")
+    L, H, d = SMALL.layers, SMALL.heads, SMALL.d_model
+    size, stride = 8 * (c - 1) + 15 + 8 * r, 8 * c
+    att_o, cnn_o = torch.zeros((L, B, H, l, 2 * d // H)), torch.zeros((L, B, d, 7))
+    att_g, cnn_g = torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))
+    for step in range(3):
+        chunk = xs[:, step * stride: step * stride + size]
+        o_o, att_o, cnn_o = O.forward_chunk(sd, H, chunk, att_o, cnn_o, c, l, r, offset=step * c)
+        o_g, m_g, att_g, cnn_g = enc.forward_chunk(chunk.to(DEV), att_g, cnn_g, c, l, r, offset=step * c)
+    assert tuple(o_g.shape) == (B, c + r, d) and tuple(m_g.shape) == (B, 1, c + r)
+    _compare(o_g, o_o, "step out (right context)")
+    _compare(att_g, att_o, "att cache (right context)")
+    _compare(cnn_g, cnn_o, "cnn cache (right context)")
+
+
 def test_forward_chunk_argument_errors():
     _, enc = _model(SMALL, 5)
     x = torch.zeros((1, 8 * 7 + 15, 80), device=DEV)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                       # a right context needs 8 r more input frames
         enc.forward_chunk(x, chunk_size=8, left_context_size=40, right_context_size=2)
     with pytest.raises(ValueError):
         enc.forward_chunk(x[:, :50], chunk_size=8, left_context_size=40)
@@ -409,12 +460,12 @@ def test_cf_encode_streams_rejects_inconsistent_plans():
     plan = Plan(c, l, 0, [T] * B, [-(ph * c)] * B)
     for n_streams, n_ph, a, cc, what in ((3, ph, att, cnn, "one utterance per stream"), (B, ph - 1, att, cnn, "placeholder_chunks"),
                                          (B, ph, None, None, "both caches")):
-        cflib.check(L.cf_encode_streams(enc._h, n_streams, n_ph), enc._h, "cf_encode_streams")
+        cflib.check(L.cf_encode_streams(enc._h, n_streams, n_ph, 0), enc._h, "cf_encode_streams")
         with pytest.raises(RuntimeError, match=what):
             enc.encode_plan(plan, x, a, cc, 0)
     out, _ = enc.encode_plan(plan, x)                       # disarmed: an ordinary masked-batch call works
     assert out.shape[0] == plan.rows
     plan_r = Plan(c, l, 8, [T] * B, [-(ph * c)] * B)
-    cflib.check(L.cf_encode_streams(enc._h, B, plan_r.n_chunks[0] - 1), enc._h, "cf_encode_streams")
+    cflib.check(L.cf_encode_streams(enc._h, B, plan_r.n_chunks[0] - 1, 0), enc._h, "cf_encode_streams")
     with pytest.raises(RuntimeError, match="right context"):
         enc.encode_plan(plan_r, x, att, cnn, 0)

@@ -163,5 +163,57 @@ def test_streaming_forward_chunk_caches(golden_dir):
         for got, key in ((o, "out"), (att, "att"), (cnn, "cnn")):
             want = torch.from_numpy(g[f"c{k}_step3_{key}"])
             assert got.shape == want.shape and float((got - want).abs().max()) < FTOL, key
-    with pytest.raises(NotImplementedError):
-        O.forward_chunk(sd, H, xs[:, :size], att, cnn, c, l, 2, 0)
+
+
+def test_streaming_with_right_context(golden_dir):
+    """forward_chunk / forward_chunk_by_chunk with right_context_size > 0 (encoder.py:310-385): chunk + right context embedded
+    and attended as one chunk, conv cut at the chunk grid, caches ending at the chunk: outputs of every step, the outputs of the
+    third explicit step (c + r rows) and both caches against the unmodified reference (tests/golden/stream_right.npz)."""
+    sd = synth_state_dict(TINY, 3)
+    L, H, d = TINY.layers, TINY.heads, TINY.d_model
+    g = _load(golden_dir, "stream_right.npz")
+    for k, (c, l, r, B, T) in enumerate(g["cases"].tolist()):
+        xs = torch.stack([synth_fbank(T, seed=40 + 7 * k + b) for b in range(B)])
+        out, mask = O.forward_chunk_by_chunk(sd, H, xs, [T] * B, c, l, r)
+        want = torch.from_numpy(g[f"c{k}_out"])
+        assert out.shape == want.shape and float((out - want).abs().max()) < FTOL, (c, l, r)
+        assert torch.equal(mask, torch.from_numpy(g[f"c{k}_mask"]))
+        size, stride = 8 * (c - 1) + 15 + 8 * r, 8 * c
+        att, cnn = torch.zeros((L, B, H, l, 2 * d // H)), torch.zeros((L, B, d, 7))
+        for step in range(3):
+            o, att, cnn = O.forward_chunk(sd, H, xs[:, step * stride: step * stride + size], att, cnn, c, l, r, offset=step * c)
+        for got, key in ((o, "out"), (att, "att"), (cnn, "cnn")):
+            want = torch.from_numpy(g[f"c{k}_step3_{key}"])
+            assert got.shape == want.shape and float((got - want).abs().max()) < FTOL, (key, c, l, r)
+
+
+def test_batch_norm_conv_module_matches_reference(golden_dir):
+    """cnn_module_norm: batch_norm (the reference constructor's default): eval-mode BatchNorm1d with running statistics in the
+    conv module, masked batch and padded-batch encode() against the unmodified reference (tests/golden/make_golden_bn.py)."""
+    geo = EncoderGeometry(d_model=64, heads=2, ffn=128, layers=2, kernel=15, vocab=50, conv_norm="batch_norm")
+    g = _load(golden_dir, "tiny_bn.npz")
+    sd = synth_state_dict(geo, 6)
+    for ci in range(2):
+        c, l, r = (int(v) for v in g[f"c{ci}_cfg"])
+        lens = [int(v) for v in g[f"c{ci}_lens"]]
+        xs = [synth_fbank(t, seed=100 + k) for k, t in enumerate(lens)]
+        out, enc_lens, n_chunks, _, _, _ = O.forward_parallel_chunk(sd, geo.heads, xs, lens, c, l, r)
+        assert n_chunks == [int(v) for v in g[f"c{ci}_n_chunks"]] and np.array_equal(enc_lens.numpy(), g[f"c{ci}_enc_lens"])
+        ref = torch.from_numpy(g[f"c{ci}_out"])
+        row = 0
+        for u, nck in enumerate(n_chunks):
+            m = max(int(enc_lens[u]), 0)
+            if m:
+                a = out[row:row + nck].reshape(-1, geo.d_model)[:m]
+                b = ref[row:row + nck].reshape(-1, geo.d_model)[:m]
+                assert float((a - b).abs().max()) < FTOL, (ci, u)
+            row += nck
+    c, l, r = (int(v) for v in g["e0_cfg"])
+    lens = [int(v) for v in g["e0_lens"]]
+    xb = torch.zeros(len(lens), max(lens), 80)
+    for k, t in enumerate(lens):
+        xb[k, :t] = synth_fbank(t, seed=300 + k)
+    out, mask = O.forward_encoder(sd, geo.heads, xb, lens, c, l, r)
+    ref = torch.from_numpy(g["e0_out"])
+    for b, m in enumerate(g["e0_out_lens"].tolist()):
+        assert float((out[b, :m] - ref[b, :m]).abs().max()) < FTOL, b
