@@ -1254,7 +1254,8 @@ struct cf_rnnt {
   std::string err;
   std::map<std::string, std::vector<float>> host;     // checkpoint tensors until finalize
   std::map<std::string, std::vector<int64_t>> shape;
-  float *embed = nullptr, *enc_w = nullptr, *enc_b = nullptr, *wc = nullptr, *bc = nullptr, *woT = nullptr, *bo = nullptr;
+  float *embed = nullptr, *enc_w = nullptr, *enc_b = nullptr, *wc = nullptr, *bc = nullptr, *woT = nullptr, *wo = nullptr, *bo = nullptr;
+  int opt_persistent = 1;          // the whole search as one persistent cooperative kernel when the model fits (cf_rnnt_set_option)
   std::vector<float*> w_ih, w_hh, b_ih, b_hh;
   std::vector<void*> owned;
   ~cf_rnnt() { for (void* q : owned) cudaFree(q); }
@@ -1293,6 +1294,12 @@ extern "C" void cf_rnnt_destroy(cf_rnnt* h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   delete h;
+}
+
+extern "C" int cf_rnnt_set_option(cf_rnnt* h, const char* name, int value) {
+  if (!h || !name) return rfail(h, CF_ERR_INVALID, "cf_rnnt_set_option: null argument");
+  if (std::string(name) == "persistent") { h->opt_persistent = value != 0; return CF_OK; }
+  return rfail(h, CF_ERR_INVALID, std::string("cf_rnnt_set_option: unknown option ") + name);
 }
 
 extern "C" int cf_rnnt_load_tensor(cf_rnnt* h, const char* key, const float* host_f32, int ndim, const int64_t* shape) {
@@ -1370,6 +1377,7 @@ extern "C" int cf_rnnt_finalize_weights(cf_rnnt* h) {
     for (int64_t v = 0; v < V; ++v)
       for (int64_t k = 0; k < J; ++k) wt[((k >> 2) * V + v) * 4 + (k & 3)] = (*ow)[v * J + k];   // [J / 4][V][4]
     RN_UP(wt.data(), wt.size(), &h->woT);
+    RN_UP(ow->data(), ow->size(), &h->wo);
   }
 #undef RN_NEED
 #undef RN_UP
@@ -1381,11 +1389,14 @@ extern "C" int cf_rnnt_finalize_weights(cf_rnnt* h) {
 struct RnntWs {
   RnntState s; float* E; long long* seg_start; int* seg_len; size_t bytes; size_t state_floats; int n_vtiles;
   int *list_b, *list_cur, *list_tok, *cnt2, *rem2;     // [2][B] x 3, [2], [2]: double-buffered by iteration parity (fused control)
+  unsigned* barrier; unsigned* jdone; int* iterations; int n_vtiles32;   // persistent kernel: grid-barrier counter, per-utterance tile
+                                                                         // arrivals, iteration count, vocabulary tiles of 32 entries
 };
 static RnntWs rnnt_carve(const cf_rnnt_config& c, int64_t rows, int B, void* base) {
   Carver cv(base);
   RnntWs w{};
   w.n_vtiles = (c.vocab + RNNT_JV - 1) / RNNT_JV;
+  w.n_vtiles32 = (c.vocab + 31) / 32;
   w.state_floats = size_t(2) * c.layers * B * c.hidden;
   w.E = cv.take<float>(size_t(rows) * c.join_dim);
   w.seg_start = cv.take<long long>(B); w.seg_len = cv.take<int>(B);
@@ -1394,8 +1405,9 @@ static RnntWs rnnt_carve(const cf_rnnt_config& c, int64_t rows, int B, void* bas
   w.s.n_active = cv.take<int>(1); w.s.remaining = cv.take<int>(1); w.s.overflow = cv.take<int>(1);
   w.s.h = cv.take<float>(w.state_floats); w.s.c = cv.take<float>(w.state_floats);
   w.s.g = cv.take<float>(size_t(B) * c.join_dim);
-  w.s.part_val = cv.take<float>(size_t(B) * RNNT_FB * w.n_vtiles);
-  w.s.part_idx = cv.take<int>(size_t(B) * RNNT_FB * w.n_vtiles);
+  w.s.part_val = cv.take<float>(size_t(B) * RNNT_FB * w.n_vtiles32);
+  w.s.part_idx = cv.take<int>(size_t(B) * RNNT_FB * w.n_vtiles32);
+  w.barrier = cv.take<unsigned>(1); w.iterations = cv.take<int>(1); w.jdone = cv.take<unsigned>(B);
   w.list_b = cv.take<int>(size_t(2) * B); w.list_cur = cv.take<int>(size_t(2) * B); w.list_tok = cv.take<int>(size_t(2) * B);
   w.cnt2 = cv.take<int>(2); w.rem2 = cv.take<int>(2);
   w.bytes = cv.off + 256;
@@ -1433,6 +1445,53 @@ extern "C" int cf_rnnt_greedy(cf_rnnt* h, const float* enc_f32, int64_t rows, co
                                        w.cnt2, w.rem2);
   ++cf::g_kernel_launches;
   CF_RCUDA(h, cudaGetLastError());
+  // ---- the whole search as one persistent cooperative kernel, when the model's weight slices fit one CTA per SM
+  if (h->opt_persistent) {
+    int dev = 0, sms = 0, coop = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int NV = w.n_vtiles32;
+    const size_t smem = sms > 0 ? rnnt_persist_smem_bytes(c.layers, c.embed, c.hidden, c.join_dim, sms) : 0;
+    if (coop && sms >= NV && c.join_dim % 32 == 0 && c.layers <= 8 && n_utt <= RNNT_PMAXB && smem <= size_t(max_smem)) {
+      std::string aerr;
+      if (!ensure_smem_optin(rnnt_persistent_kernel, smem, &aerr, "rnnt_persistent")) return rfail(h, CF_ERR_CUDA, aerr);
+      int per_sm = 0;
+      CF_RCUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rnnt_persistent_kernel, 256, smem));
+      if (per_sm >= 1) {
+        RnntPersistParams pp{};
+        pp.embed = h->embed;
+        for (int l = 0; l < c.layers; ++l) { pp.w_ih[l] = h->w_ih[l]; pp.w_hh[l] = h->w_hh[l]; pp.b_ih[l] = h->b_ih[l]; pp.b_hh[l] = h->b_hh[l]; }
+        pp.Wc = h->wc; pp.bc = h->bc; pp.Wo = h->wo; pp.bo = h->bo; pp.E = w.E; pp.seg_start = w.seg_start; pp.seg_len = w.seg_len;
+        pp.layers = c.layers; pp.Em = c.embed; pp.H = c.hidden; pp.J = c.join_dim; pp.V = c.vocab; pp.B = n_utt; pp.n_steps = n_steps;
+        pp.cap = capacity; pp.blank = c.blank; pp.NV = NV; pp.UG = sms / NV;
+        pp.list_b = w.list_b; pp.list_cur = w.list_cur; pp.list_tok = w.list_tok; pp.cnt2 = w.cnt2; pp.rem2 = w.rem2;
+        pp.out_tokens = reinterpret_cast<long long*>(out_tokens); pp.out_frames = out_frames; pp.out_counts = out_counts;
+        pp.barrier = w.barrier; pp.iterations = w.iterations; pp.jdone = w.jdone;
+        int64_t max_len = 0;
+        for (int b = 0; b < n_utt; ++b) max_len = seg_len[b] > max_len ? seg_len[b] : max_len;
+        pp.max_iters = max_len * (int64_t(n_steps) + 1) + 2;       // every iteration emits a symbol or moves a frame forward
+        CF_RCUDA(h, cudaMemsetAsync(w.barrier, 0, sizeof(unsigned), st));
+        CF_RCUDA(h, cudaMemsetAsync(w.iterations, 0, sizeof(int), st));
+        CF_RCUDA(h, cudaMemsetAsync(w.jdone, 0, sizeof(unsigned) * size_t(n_utt), st));
+        RnntState state = w.s;
+        void* args[] = {&pp, &state};
+        CF_RCUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_persistent_kernel), dim3(unsigned(sms)), dim3(256), args, smem, st));
+        ++cf::g_kernel_launches;
+        int host[3] = {0, 0, 0};   // iterations, overflow, remaining of the last iteration's parity
+        CF_RCUDA(h, cudaMemcpyAsync(&host[0], w.iterations, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CF_RCUDA(h, cudaMemcpyAsync(&host[1], w.s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CF_RCUDA(h, cudaStreamSynchronize(st));
+        int rem = 0;
+        CF_RCUDA(h, cudaMemcpy(&rem, w.rem2 + ((host[0] - 1) & 1), sizeof(int), cudaMemcpyDeviceToHost));
+        if (iterations_out) *iterations_out = host[0];
+        if (host[1]) return rfail(h, CF_ERR_WORKSPACE, "cf_rnnt_greedy: an utterance emitted more than `capacity` symbols");
+        if (rem != 0) return rfail(h, CF_ERR_STATE, "cf_rnnt_greedy: search did not terminate (internal error)");
+        return CF_OK;
+      }
+    }
+  }
   RnntJointParams jp{};
   jp.E = w.E; jp.WoT = h->woT; jp.bo = h->bo; jp.seg_start = w.seg_start; jp.seg_len = w.seg_len; jp.J = c.join_dim; jp.V = c.vocab;
   jp.n_vtiles = w.n_vtiles; jp.Wc = h->wc; jp.bc = h->bc; jp.H = c.hidden; jp.layers = c.layers;

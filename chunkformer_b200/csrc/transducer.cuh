@@ -12,6 +12,8 @@
 // Everything is fp32 on CUDA cores: the search is a chain of argmax decisions, so a reduced-precision joint would change
 // the hypothesis after its first near-tie; the work per iteration is a few MFLOP and latency-bound anyway.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cf {
@@ -574,6 +576,348 @@ __global__ void rnnt_init_kernel(RnntState s, const int* seg_len, int* out_count
     cnt2[1] = n; rem2[1] = n; cnt2[0] = 0; rem2[0] = 0;
     *s.n_active = n; *s.remaining = n; *s.overflow = 0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole search as ONE persistent cooperative kernel (round 2).  The launch-per-phase version above spends most of an
+// iteration on dependent-launch latency (about 4.5 us per launch) and on re-reading the predictor / joint weights from L2 behind
+// every launch (41.5 us per lock-step iteration).  Here every CTA stays resident for the whole search, keeps its slice of every
+// weight matrix in shared memory (fp32: LSTM gate rows of its hidden units, rows of the composed pred_ffn o projection, a
+// 32-entry vocabulary tile of ffn_out stored [k][entry]), and the phases of an iteration are separated by grid barriers
+// (one atomic per CTA on a monotonic counter, bounded spin):
+//   LSTM layer 0 .. L-1  (weight-stationary: CTA c owns hidden units c, c + G, ...; all utterances that just emitted)   | barrier each
+//   projection g_b = Wc h_top'(b) + bc   (CTA c owns rows c, c + G, ...)                                                   | barrier
+//   joint: CTA (vocabulary tile vt, utterance group ug): tanh(E[t_b .. t_b + 8) + g_b) . ffn_out[tile]^T, per-tile argmax  | barrier
+//   decide: greedy control of utterance b in CTA b mod G (same rules as rnnt_decide_kernel), next iteration's list         | barrier
+// Everything that another CTA wrote is read with ld.global.cg (L1 is not coherent); arithmetic is the same fp32 as above.
+// ---------------------------------------------------------------------------------------------------------------------
+struct RnntPersistParams {
+  const float* embed;                       // [V, E]
+  const float* w_ih[8]; const float* w_hh[8]; const float* b_ih[8]; const float* b_hh[8];
+  const float* Wc; const float* bc;         // [J, H], [J]
+  const float* Wo; const float* bo;         // [V, J] (row-major, as in the checkpoint), [V]
+  const float* E;                           // [rows, J] enc_ffn output
+  const long long* seg_start; const int* seg_len;
+  int layers, Em, H, J, V, B, n_steps, cap, blank;
+  int NV, UG;                               // vocabulary tiles of 32 entries, utterance groups (NV * UG <= grid)
+  int* list_b; int* list_cur; int* list_tok; int* cnt2; int* rem2;     // [2][B] x 3, [2], [2]: double-buffered by iteration parity
+  long long* out_tokens; int* out_frames; int* out_counts;
+  unsigned* barrier;                        // [1] zeroed before the launch
+  unsigned* jdone;                          // [B] vocabulary tiles delivered per utterance (monotonic), zeroed before the launch
+  int* iterations;                          // [1] iterations run (for the host)
+  long long max_iters;
+};
+
+constexpr int RNNT_PMAXB = 128;    // utterances the persistent kernel handles (its active list lives in shared memory)
+constexpr int RNNT_PUT = 8;        // utterances per LSTM input tile (shared memory)
+constexpr int RNNT_PJT = 16;       // utterances per projection input tile
+inline size_t rnnt_persist_smem_bytes(int layers, int Em, int H, int J, int G) {
+  const size_t upc = (H + G - 1) / G, rpc = (J + G - 1) / G;
+  size_t fl = 0;
+  for (int l = 0; l < layers; ++l) fl += upc * 4 * size_t((l == 0 ? Em : H) + H);
+  fl += rpc * size_t(H);                    // Wc rows
+  fl += size_t(J) * 32;                     // ffn_out tile [k][32]
+  // scratch: LSTM input vectors of RNNT_PUT utterances | projection inputs of RNNT_PJT utterances | 2 x 8 activation rows
+  fl += std::max(std::max(RNNT_PUT * size_t(std::max(Em, H) + H), RNNT_PJT * size_t(H)), 2 * RNNT_FB * size_t(J));
+  fl += 8 * 8 * 32;                         // K-slice partial sums [8 warps][8 frames][32 entries]
+  return fl * 4 + 3 * 4 * RNNT_PMAXB;       // + the iteration's active list
+}
+
+CF_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+CF_DEVINL void rnnt_grid_barrier(unsigned* counter, unsigned& epoch, unsigned G) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = epoch * G;
+    unsigned spins = 0;
+    while (ld_acquire_u32(counter) < target)
+      if (++spins > (1u << 25)) __trap();   // a scheduling bug must trap, never hang the GPU
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) rnnt_persistent_kernel(RnntPersistParams p, RnntState s) {
+  extern __shared__ __align__(16) float psm[];
+  __shared__ int s_last;
+  const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, J = p.J, B = p.B;
+  const int upc = (H + G - 1) / G, rpc = (J + G - 1) / G;
+  // ---- carve shared memory and load this CTA's weight slices once
+  float* sW[8];
+  float* cur_ptr = psm;
+  for (int l = 0; l < p.layers; ++l) { sW[l] = cur_ptr; cur_ptr += size_t(upc) * 4 * ((l == 0 ? p.Em : H) + H); }
+  float* sWc = cur_ptr; cur_ptr += size_t(rpc) * H;
+  float* sWo = cur_ptr; cur_ptr += size_t(J) * 32;
+  float* sX = cur_ptr;                                       // scratch (see rnnt_persist_smem_bytes)
+  {
+    const size_t a = RNNT_PUT * size_t(max(p.Em, H) + H), b = RNNT_PJT * size_t(H), c = 2 * RNNT_FB * size_t(J);
+    cur_ptr += max(max(a, b), c);
+  }
+  float* sRed = cur_ptr; cur_ptr += 8 * 8 * 32;              // [8 warps][8 frames][32 entries]
+  int* sLb = reinterpret_cast<int*>(cur_ptr);                // this iteration's active list: utterance, committed half, token
+  int* sLc = sLb + RNNT_PMAXB;
+  int* sLt = sLc + RNNT_PMAXB;
+  for (int l = 0; l < p.layers; ++l) {
+    const int In = l == 0 ? p.Em : H, K = In + H;
+    for (int i = 0; i < upc; ++i) {
+      const int j = cta + G * i;
+      for (int q = 0; q < 4; ++q) {
+        float* dst = sW[l] + (size_t(i) * 4 + q) * K;
+        for (int k = tid; k < K; k += 256)
+          dst[k] = j < H ? (k < In ? __ldg(p.w_ih[l] + size_t(q * H + j) * In + k) : __ldg(p.w_hh[l] + size_t(q * H + j) * H + (k - In))) : 0.f;
+      }
+    }
+  }
+  for (int i = 0; i < rpc; ++i) {
+    const int r = cta + G * i;
+    for (int k = tid; k < H; k += 256) sWc[size_t(i) * H + k] = r < J ? __ldg(p.Wc + size_t(r) * H + k) : 0.f;
+  }
+  const int vt = cta % p.NV, ug = cta / p.NV;
+  const bool joint_cta = ug < p.UG;
+  if (joint_cta)
+    for (int i = tid; i < J * 32; i += 256) {
+      const int k = i >> 5, e = i & 31, v = vt * 32 + e;
+      sWo[i] = v < p.V ? __ldg(p.Wo + size_t(v) * J + k) : 0.f;
+    }
+  __syncthreads();
+
+  const size_t half = size_t(p.layers) * B * H;
+  unsigned epoch = 0;
+  long long it = 0;
+  for (;; ++it) {
+    const int par = int(it & 1);
+    const int n_act = __ldcg(p.cnt2 + (par ^ 1));
+    if (cta == 0 && tid == 0) { p.cnt2[par] = 0; p.rem2[par] = 0; }      // appended to by this iteration's decide step
+    __syncthreads();
+    for (int i = tid; i < n_act; i += 256) {                              // one round trip for the whole list
+      sLb[i] = __ldcg(p.list_b + (par ^ 1) * B + i);
+      sLc[i] = __ldcg(p.list_cur + (par ^ 1) * B + i);
+      sLt[i] = __ldcg(p.list_tok + (par ^ 1) * B + i);
+    }
+    __syncthreads();
+    // ------------------------------------------------ predictor: LSTM layers for the utterances that just emitted
+    for (int l = 0; l < p.layers; ++l) {
+      const int In = l == 0 ? p.Em : H, K = In + H, K4 = K / 4, In4 = In / 4;
+      for (int u0 = 0; u0 < n_act; u0 += RNNT_PUT) {
+        const int nu = min(RNNT_PUT, n_act - u0);
+        __syncthreads();                                      // sX free
+        for (int i = tid; i < nu * K4; i += 256) {            // independent 16-byte loads: one L2 round trip for the tile
+          const int u = i / K4, k4 = i - u * K4;
+          const int b = sLb[u0 + u], cur = sLc[u0 + u];
+          float4 v;
+          if (k4 < In4) v = l == 0 ? __ldg(reinterpret_cast<const float4*>(p.embed + size_t(sLt[u0 + u]) * In) + k4)
+                                   : __ldcg(reinterpret_cast<const float4*>(s.h + (cur ^ 1) * half + (size_t(l - 1) * B + b) * H) + k4);
+          else v = __ldcg(reinterpret_cast<const float4*>(s.h + cur * half + (size_t(l) * B + b) * H) + (k4 - In4));
+          reinterpret_cast<float4*>(sX)[size_t(u) * K4 + k4] = v;
+        }
+        __syncthreads();
+        for (int item = warp; item < upc * nu; item += 8) {   // (unit slot, utterance of the tile)
+          const int i = item % upc, u = item / upc;
+          const int j = cta + G * i;
+          if (j >= H) continue;
+          const int b = sLb[u0 + u], cur = sLc[u0 + u];
+          const size_t at = (size_t(l) * B + b) * H + j;
+          float c_old = 0.f, bias[4] = {0.f, 0.f, 0.f, 0.f};
+          if (lane == 0) {                                    // requested before the dot products, consumed after them
+            c_old = __ldcg(s.c + cur * half + at);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bias[q] = __ldg(p.b_ih[l] + q * H + j) + __ldg(p.b_hh[l] + q * H + j);
+          }
+          const float4* w4 = reinterpret_cast<const float4*>(sW[l] + size_t(i) * 4 * K);
+          const float4* x4 = reinterpret_cast<const float4*>(sX + size_t(u) * K);
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int k4 = lane; k4 < K4; k4 += 32) {
+            const float4 x = x4[k4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 w = w4[size_t(q) * K4 + k4];
+              acc[q] += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
+          if (lane == 0) {
+            float gate[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gate[q] = acc[q] + bias[q];
+            const float c_new = sigmoidf_acc(gate[1]) * c_old + sigmoidf_acc(gate[0]) * tanhf(gate[2]);
+            s.c[(cur ^ 1) * half + at] = c_new;
+            s.h[(cur ^ 1) * half + at] = sigmoidf_acc(gate[3]) * tanhf(c_new);
+          }
+        }
+      }
+      rnnt_grid_barrier(p.barrier, epoch, G);
+    }
+    // ------------------------------------------------ projection rows of this CTA for the same utterances
+    for (int u0 = 0; u0 < n_act; u0 += RNNT_PJT) {
+      const int nu = min(RNNT_PJT, n_act - u0), H4 = H / 4;
+      __syncthreads();
+      for (int i = tid; i < nu * H4; i += 256) {
+        const int u = i / H4, k4 = i - u * H4;
+        const int b = sLb[u0 + u], cur = sLc[u0 + u];
+        reinterpret_cast<float4*>(sX)[size_t(u) * H4 + k4] =
+            __ldcg(reinterpret_cast<const float4*>(s.h + (cur ^ 1) * half + (size_t(p.layers - 1) * B + b) * H) + k4);
+      }
+      __syncthreads();
+      for (int item = warp; item < rpc * nu; item += 8) {
+        const int i = item % rpc, u = item / rpc;
+        const int r = cta + G * i;
+        if (r >= J) continue;
+        const float4* x4 = reinterpret_cast<const float4*>(sX + size_t(u) * H);
+        const float4* w4 = reinterpret_cast<const float4*>(sWc + size_t(i) * H);
+        float acc = 0.f;
+        for (int k4 = lane; k4 < H4; k4 += 32) {
+          const float4 x = x4[k4], w = w4[k4];
+          acc += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s.g[size_t(sLb[u0 + u]) * J + r] = acc + __ldg(p.bc + r);
+      }
+    }
+    rnnt_grid_barrier(p.barrier, epoch, G);
+    // ------------------------------------------------ joint over the next 8 frames of the unfinished utterances of this group, two
+    // utterances per round (warps 0-3: first, 4-7: second; a warp = one quarter of K, lane = vocabulary entry of the tile);
+    // the CTA that delivers the last vocabulary tile of an utterance runs its greedy control (greedy_search.py:24-76)
+    if (joint_cta) {
+      for (int b0 = ug; b0 < B; b0 += 2 * p.UG) {
+        int bb[2], t0[2], nf[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          bb[h2] = b0 + h2 * p.UG;
+          t0[h2] = bb[h2] < B ? __ldcg(s.t + bb[h2]) : 0;
+          nf[h2] = bb[h2] < B ? max(0, min(RNNT_FB, p.seg_len[bb[h2]] - t0[h2])) : 0;
+        }
+        if (nf[0] == 0 && nf[1] == 0) continue;               // uniform over the CTA
+        __syncthreads();                                      // sX / sRed free
+        for (int i = tid; i < 2 * RNNT_FB * J; i += 256) {
+          const int h2 = i / (RNNT_FB * J), r = i - h2 * RNNT_FB * J, f = r / J, k = r - f * J;
+          float v = 0.f;
+          if (f < nf[h2]) {
+            const float* e = p.E + (p.seg_start[bb[h2]] + t0[h2] + f) * (long long)J;
+            v = tanhf(__ldg(e + k) + __ldcg(s.g + size_t(bb[h2]) * J + k));
+          }
+          sX[i] = v;
+        }
+        __syncthreads();
+        {
+          const int h2 = warp >> 2, ks = warp & 3, kper = J / 4;
+          const float* ax = sX + size_t(h2) * RNNT_FB * J;
+          float acc[RNNT_FB];
+#pragma unroll
+          for (int f = 0; f < RNNT_FB; ++f) acc[f] = 0.f;
+          if (nf[h2] > 0)
+            for (int k0 = ks * kper; k0 < (ks + 1) * kper; k0 += 4) {
+              const float w0 = sWo[(k0 + 0) * 32 + lane], w1 = sWo[(k0 + 1) * 32 + lane];
+              const float w2 = sWo[(k0 + 2) * 32 + lane], w3 = sWo[(k0 + 3) * 32 + lane];
+#pragma unroll
+              for (int f = 0; f < RNNT_FB; ++f) {
+                const float4 a = *reinterpret_cast<const float4*>(ax + size_t(f) * J + k0);
+                acc[f] = fmaf(a.x, w0, acc[f]); acc[f] = fmaf(a.y, w1, acc[f]);
+                acc[f] = fmaf(a.z, w2, acc[f]); acc[f] = fmaf(a.w, w3, acc[f]);
+              }
+            }
+#pragma unroll
+          for (int f = 0; f < RNNT_FB; ++f) sRed[(warp * RNNT_FB + f) * 32 + lane] = acc[f];
+        }
+        __syncthreads();
+        // warp w finishes frames w and w + ... : 16 (utterance, frame) pairs over 8 warps
+        for (int pf = warp; pf < 2 * RNNT_FB; pf += 8) {
+          const int h2 = pf / RNNT_FB, f = pf - h2 * RNNT_FB, v = vt * 32 + lane;
+          if (f >= nf[h2]) continue;
+          float sum = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sum += sRed[((h2 * 4 + q) * RNNT_FB + f) * 32 + lane];
+          float val = v < p.V ? sum + __ldg(p.bo + v) : -INFINITY;
+          int idx = v < p.V ? v : 0x7fffffff;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+          }
+          if (lane == 0) {
+            const size_t at = (size_t(bb[h2]) * RNNT_FB + f) * p.NV + vt;
+            s.part_val[at] = val;
+            s.part_idx[at] = idx;
+          }
+        }
+        // last vocabulary tile of an utterance to arrive -> this CTA decides for it
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          int last = 0;
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+            if (nf[h2] > 0 && (atomicAdd(p.jdone + bb[h2], 1u) % unsigned(p.NV)) == unsigned(p.NV - 1)) last |= 1 << h2;
+          if (last) __threadfence();
+          s_last = last;
+        }
+        __syncthreads();
+        const int last = s_last;
+        if (last && warp == 0) {
+#pragma unroll 1
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if (!((last >> h2) & 1)) continue;
+            const int b = bb[h2];
+            int t = t0[h2];
+            const int len = p.seg_len[b];
+            const int f_l = lane >> 2, q_l = lane & 3;
+            const size_t at = (size_t(b) * RNNT_FB + f_l) * p.NV;
+            float val = -INFINITY; int idx = 0x7fffffff;
+            for (int w = q_l; w < p.NV; w += 4) {
+              const float ov = __ldcg(s.part_val + at + w); const int oi = __ldcg(s.part_idx + at + w);
+              if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, val, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+              if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+            }
+            const unsigned nb = __ballot_sync(0xffffffffu, q_l == 0 && idx != p.blank && t + f_l < len);
+            const int limit = min(RNNT_FB, len - t);
+            const int f_hit = nb ? (__ffs(nb) - 1) >> 2 : limit;
+            const int sym = __shfl_sync(0xffffffffu, idx, (f_hit < RNNT_FB ? f_hit : 0) * 4);
+            if (lane == 0) {
+              int step = __ldcg(s.step + b);
+              int n_out = __ldcg(s.count + b);
+              const int cur_old = __ldcg(s.cur + b);
+              if (f_hit > 0) step = 1;                  // blanks before the hit: next frame, slot 1
+              t += f_hit;
+              if (f_hit < limit) {
+                if (n_out >= p.cap) { *s.overflow = 1; t = len; }
+                else {
+                  p.out_tokens[size_t(b) * p.cap + n_out] = sym;
+                  p.out_frames[size_t(b) * p.cap + n_out] = t;
+                  s.count[b] = ++n_out;
+                  const int cur = cur_old ^ 1;          // the candidate predictor state becomes the committed one
+                  s.cur[b] = cur;
+                  if (++step > p.n_steps) { ++t; step = 1; }
+                  if (t < len) {
+                    const int slot = atomicAdd(p.cnt2 + par, 1);
+                    p.list_b[par * B + slot] = b; p.list_cur[par * B + slot] = cur; p.list_tok[par * B + slot] = sym;
+                  }
+                }
+              }
+              s.t[b] = t; s.step[b] = step;
+              if (t < len) atomicAdd(p.rem2 + par, 1);
+              else p.out_counts[b] = n_out;
+            }
+          }
+        }
+      }
+    }
+    rnnt_grid_barrier(p.barrier, epoch, G);
+    if (__ldcg(p.rem2 + par) == 0 || it + 1 >= p.max_iters) break;
+  }
+  if (cta == 0 && tid == 0) *p.iterations = int(it + 1);
 }
 
 }  // namespace cf

@@ -56,6 +56,7 @@ SIGNATURES = {
     "cf_rnnt_create": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
     "cf_rnnt_destroy": (None, [c_void_p]),
     "cf_rnnt_last_error": (c_char_p, [c_void_p]),
+    "cf_rnnt_set_option": (c_int, [c_void_p, c_char_p, c_int]),
     "cf_rnnt_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64)]),
     "cf_rnnt_finalize_weights": (c_int, [c_void_p]),
     "cf_rnnt_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int]),

@@ -54,6 +54,11 @@ class TransducerGreedyB200:
         self._check(self._L.cf_rnnt_finalize_weights(self._h), "cf_rnnt_finalize_weights")
         self.last_iterations = 0
 
+    def set_option(self, name: str, value: int) -> None:
+        """Per-handle option of the library (cf_rnnt_set_option): "persistent" 1 / 0 = the search as one persistent
+        cooperative kernel / one launch per phase."""
+        self._check(self._L.cf_rnnt_set_option(self._h, name.encode(), int(value)), "cf_rnnt_set_option")
+
     def _check(self, rc, what):
         if rc != 0:
             msg = self._L.cf_rnnt_last_error(getattr(self, "_h", None)).decode("utf-8", "replace")

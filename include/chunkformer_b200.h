@@ -194,6 +194,10 @@ CF_API int cf_rnnt_create(const cf_rnnt_config* cfg, int device, cf_rnnt** out);
 CF_API void cf_rnnt_destroy(cf_rnnt* h);
 CF_API const char* cf_rnnt_last_error(const cf_rnnt* h);
 /* One call per checkpoint tensor under `predictor.` / `joint.` (host fp32, any order), then finalize. */
+/* Per-handle option.  "persistent" (default 1): the whole search runs as one persistent cooperative kernel (weight slices
+ * resident in shared memory, grid barriers between the phases of an iteration) whenever the model fits one CTA per SM;
+ * 0 = one launch per phase (kept for A/B measurement and as the path for models that do not fit). */
+CF_API int cf_rnnt_set_option(cf_rnnt* h, const char* name, int value);
 CF_API int cf_rnnt_load_tensor(cf_rnnt* h, const char* state_dict_key, const float* host_f32, int ndim, const int64_t* shape);
 CF_API int cf_rnnt_finalize_weights(cf_rnnt* h);
 CF_API size_t cf_rnnt_workspace_bytes(const cf_rnnt* h, int64_t rows, int n_utt);

@@ -106,3 +106,30 @@ def test_many_utterances_use_several_predictor_tiles(V):
         _assert_same_until_near_tie(sd, enc[starts[b]:starts[b] + lens[b]], lens[b], 5, tok, fr, f"utt{b}")
         total += tok.numel()
     assert total > 100
+
+
+def test_persistent_kernel_equals_launch_per_phase():
+    """The persistent cooperative search kernel (weights resident in shared memory, grid barriers) against the launch-per-phase
+    path on the same handle: same symbols and frames, or the first difference sits at a decision whose fp32 top-2 margin is
+    below 1e-4 (the two sum the joint in different orders); rnnt-large head sizes, ragged batch with empty utterances."""
+    V, emb, hid, nl, po, E, J = 1024, 256, 512, 2, 512, 512, 512
+    sd = synth_transducer_state_dict(V, emb, hid, nl, po, E, J, blank_bias=7.2, seed=5)
+    gen = torch.Generator().manual_seed(19)
+    lens = [700, 0, 17, 1, 350, 64, 9, 1200, 33]
+    starts, pos = [], 0
+    for n in lens:
+        starts.append(pos)
+        pos += n + 5
+    enc = torch.randn((pos, E), generator=gen)
+    srch = TransducerGreedyB200(sd, device=DEV)
+    out = {}
+    for persistent in (1, 0):
+        srch.set_option("persistent", persistent)
+        out[persistent] = srch.search_flat(enc.to(DEV), starts, lens, n_steps=6)
+        assert srch.last_iterations > 0
+    srch.set_option("persistent", 1)
+    for b, ((t1, f1), (t0, f0)) in enumerate(zip(out[1], out[0])):
+        if t1.shape == t0.shape and bool((t1 == t0).all()) and bool((f1 == f0).all()):
+            continue
+        _assert_same_until_near_tie(sd, enc[starts[b]:starts[b] + lens[b]], lens[b], 6, t1, f1, f"persistent utt{b}")
+        _assert_same_until_near_tie(sd, enc[starts[b]:starts[b] + lens[b]], lens[b], 6, t0, f0, f"per-phase utt{b}")

@@ -24,11 +24,19 @@ L = cflib.load()
 for bb in biases:
     sd = synth_transducer_state_dict(1024, 256, 512, 2, 512, 512, 512, blank_bias=bb, seed=13)
     srch = TransducerGreedyB200(sd, device="cuda:0")
-    srch.search_flat(enc[:4096], [0], [4096])          # warm-up
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = srch.search_flat(enc, starts, enc_lens)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    syms = sum(t.numel() for t, _ in res)
-    print(f"blank_bias {bb}: {len(enc_lens)} utterances, {sum(enc_lens)} frames (longest {max(enc_lens)}), {syms} symbols "
-          f"(longest utterance {max(t.numel() for t, _ in res)}); {srch.last_iterations} iterations, {dt * 1e3:.1f} ms "
-          f"= {dt * 1e6 / srch.last_iterations:.1f} us per iteration; {14400 / dt / 3600:.1f} audio-h/s")
+    ref_tokens = None
+    for persistent in (1, 0):
+        srch.set_option("persistent", persistent)
+        srch.search_flat(enc[:4096], [0], [4096])          # warm-up
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        res = srch.search_flat(enc, starts, enc_lens)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        syms = sum(t.numel() for t, _ in res)
+        same = ""
+        if ref_tokens is None:
+            ref_tokens = [t for t, _ in res]
+        else:
+            same = "; same symbols as the persistent kernel: " + str(all(a.shape == b.shape and bool((a == b).all()) for a, (b, _) in zip(ref_tokens, res)))
+        print(f"blank_bias {bb} persistent={persistent}: {len(enc_lens)} utterances, {sum(enc_lens)} frames (longest {max(enc_lens)}), "
+              f"{syms} symbols (longest utterance {max(t.numel() for t, _ in res)}); {srch.last_iterations} iterations, {dt * 1e3:.1f} ms "
+              f"= {dt * 1e6 / srch.last_iterations:.1f} us per iteration; {14400 / dt / 3600:.1f} audio-h/s{same}", flush=True)
