@@ -49,10 +49,14 @@ def path_flops_per_chunk(geo, c, l, r):
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture (profiles/r01_ncu_gemm_ffn1_full.csv, first profiled launch); None if the summary is absent."""
+    capture (profiles/r02_ncu_gemm_ffn1_full.csv, else the round-1 capture of the same, unchanged kernel; first profiled launch);
+    None if no summary is there."""
     try:
         tot, seen = 0.0, 0
-        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_ffn1_full.csv")):
+        path = os.path.join(ROOT, "profiles", "r02_ncu_gemm_ffn1_full.csv")
+        if not os.path.exists(path):
+            path = os.path.join(ROOT, "profiles", "r01_ncu_gemm_ffn1_full.csv")
+        for line in open(path):
             if line.startswith("#"):
                 seen += 1
                 if seen > 1:
@@ -499,7 +503,8 @@ def main():
                     "flops_per_launch": flops,
                     "alone": {"ms_best_of_10": best_alone, "achieved": flops / (best_alone * 1e-3) / 1e12, "peak": burst,
                               "frac": flops / (best_alone * 1e-3) / 1e12 / burst, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"},
-                    "also": {"kernel": "gemm2_tcgen05_kernel<EPI_F32> (FFN w_2 + 0.5 * residual, 2-CTA, M=%d N=%d K=%d)" % (rows, d, F),
+                    "also": {"kernel": "gemm_ln_kernel (FFN w_2 + 0.5 * residual + the LayerNorm(s) behind it, CTA pair, M=%d N=%d K=%d; "
+                                       "flops of the GEMM only)" % (rows, d, F),
                              "ms_per_launch": fam["w2"][0] / max(fam["w2"][1], 1), "launches_timed": fam["w2"][1],
                              "achieved": flops / (fam["w2"][0] / max(fam["w2"][1], 1) * 1e-3) / 1e12 if fam["w2"][1] else None,
                              "frac": flops / (fam["w2"][0] / max(fam["w2"][1], 1) * 1e-3) / 1e12 / sustained if fam["w2"][1] else None},
