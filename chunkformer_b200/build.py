@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libchunkformer_b200.so")
 LIB_ABLATION = os.path.join(CSRC, "libchunkformer_b200_ablation.so")   # tools only: -DCF_ABLATION (timing / phase switches)
 SOURCES = ["api.cu", "plan.cpp"]
-HEADERS = ["common.cuh", "transducer.cuh", "gemm.cuh", "gemm_host.cuh", "norm_conv.cuh", "frontend.cuh", "attention_simt.cuh",
+HEADERS = ["common.cuh", "transducer.cuh", "gemm.cuh", "gemm_host.cuh", "gemm_ln.cuh", "ffn_fused.cuh", "norm_conv.cuh", "frontend.cuh", "attention_simt.cuh",
            "attention_tc.cuh", "fbank.cuh", "misc_kernels.cuh", "plan.h", os.path.join("..", "..", "include", "chunkformer_b200.h")]
 
 

@@ -73,6 +73,7 @@ struct cf_handle {
   cf::KernelTiming timing;
   // per-handle options (cf_set_option)
   int opt_fused_layernorm = 1;   // LayerNorms fused into the epilogue of the residual GEMM in front of them (gemm_ln.cuh)
+  int opt_ln_split = 1;          // ... with the normalisation passes on their own warps (gemm_ln_split_kernel)
   int opt_ffn_slab_rows = 0;     // > 0: the two FFN GEMMs run slab by slab of this many rows, the hidden activation of a slab
                                  // (rows x F bf16) is produced and consumed while it is still in L2
   int opt_fused_ffn = 0;         // feed-forward modules as one kernel each, hidden activation kept on chip (ffn_fused.cuh)
@@ -119,6 +120,7 @@ extern "C" int cf_set_option(cf_handle* h, const char* name, int value) {
   if (!h || !name) return fail(h, CF_ERR_INVALID, "cf_set_option: null argument");
   const std::string k(name);
   if (k == "fused_layernorm") { h->opt_fused_layernorm = value != 0; return CF_OK; }
+  if (k == "ln_split") { h->opt_ln_split = value != 0; return CF_OK; }
   if (k == "fused_ffn") { h->opt_fused_ffn = value != 0; return CF_OK; }
   if (k == "ffn_slab_rows") { h->opt_ffn_slab_rows = value > 0 ? ((value + 127) / 128) * 128 : 0; return CF_OK; }
   return fail(h, CF_ERR_INVALID, "cf_set_option: unknown option " + k);
@@ -869,7 +871,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.ld_resid = e.ld_resid; g.alpha = e.alpha; g.row_range = e.row_range; g.rows_per_chunk = e.rows_per_chunk; g.mode = q.mode;
     g.ln1_w = q.w1; g.ln1_b = q.b1; g.ln2_w = q.w2; g.ln2_b = q.b2; g.x_out = q.x_out; g.ldx = d; g.y_out = q.y_out; g.ldy = d;
     g.row_limit = q.limit ? w.seq_limit : nullptr; g.rows_per_seq = q.limit ? p->rows_per_seq : 1;
-    g.timing = &h->timing; g.family = e.family;
+    g.timing = &h->timing; g.family = e.family; g.variant = h->opt_ln_split;
     return launch_gemm_ln(g, h->num_sms, st, &err);
   };
   const bool fuse_ln = h->opt_fused_layernorm != 0;
@@ -1605,11 +1607,41 @@ extern "C" int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t 
   if (!A || !B) return fail(nullptr, CF_ERR_INVALID, "cf_op_gemm_ln: null argument");
   GemmLnLaunch g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.bias = bias; g.resid = resid; g.ld_resid = ld_resid;
-  g.alpha = alpha; g.row_range = reinterpret_cast<const int2*>(row_range); g.rows_per_chunk = rows_per_chunk; g.mode = mode;
+  g.alpha = alpha; g.row_range = reinterpret_cast<const int2*>(row_range); g.rows_per_chunk = rows_per_chunk;
+  g.mode = mode & 15; g.variant = (mode & 16) ? 0 : 1;     // mode + 16: the single-epilogue-group kernel (kept for A/B measurements)
   g.ln1_w = ln1_w; g.ln1_b = ln1_b; g.ln2_w = ln2_w; g.ln2_b = ln2_b; g.x_out = x_out; g.ldx = ldx; g.y_out = y_out; g.ldy = ldy;
   g.row_limit = row_limit; g.rows_per_seq = rows_per_seq;
   std::string err;
+#ifdef CF_ABLATION
+  long long* prof_dev = nullptr;
+  const int prof_ctas = current_sms();
+  if (getenv("CF_LN_PROF")) { cudaMalloc(&prof_dev, size_t(prof_ctas) * 48 * 8); cudaMemset(prof_dev, 0, size_t(prof_ctas) * 48 * 8); g.prof = prof_dev; }
+#endif
   if (!launch_gemm_ln(g, current_sms(), static_cast<cudaStream_t>(stream), &err)) return fail(nullptr, CF_ERR_CUDA, err);
+#ifdef CF_ABLATION
+  if (prof_dev) {
+    std::vector<long long> hp(size_t(prof_ctas) * 48);
+    cudaMemcpy(hp.data(), prof_dev, hp.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(prof_dev);
+    static const char* names[16] = {"producer total", "producer wait empty", "mma total", "mma wait tempty", "mma wait full", "P1 total",
+                                    "P1 wait tfull", "P1 wait resid", "P1 wait credit", "P1 named barrier", "P2 total", "P2 wait stats",
+                                    "P2 wait stats2", "P1 issuer store-read wait", "P1 tmem ld wait", "P1 barrier (warp 1)"};
+    fprintf(stderr, "gemm_ln_split profile (cycles, mean over CTAs; M=%d K=%d mode=%d):\n", M, K, g.mode);
+    for (int f = 0; f < 16; ++f) {
+      double sum = 0; int n = 0;
+      for (int c = 0; c < prof_ctas; ++c) if (hp[size_t(c) * 16 + 0] > 0) { sum += double(hp[size_t(c) * 16 + f]); ++n; }
+      fprintf(stderr, "  %-22s %12.0f\n", names[f], n ? sum / n : 0.0);
+    }
+    static const char* segn[9] = {"issue next resid", "bias ldg + resid wait", "tmem ld wait", "add + stage", "tmem st", "stats", "fence",
+                                  "named barrier", "tma store"};
+    for (int wsel = 0; wsel < 2; ++wsel)
+      for (int f = 0; f < 9; ++f) {
+        double sum = 0;
+        for (int c = 0; c < prof_ctas; ++c) sum += double(hp[(size_t(wsel + 1) * prof_ctas + c) * 16 + f]);
+        fprintf(stderr, "  P1 warp %d seg %-22s %12.0f\n", wsel, segn[f], sum / prof_ctas);
+      }
+  }
+#endif
   return CF_OK;
 }
 

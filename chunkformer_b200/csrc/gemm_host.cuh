@@ -234,6 +234,11 @@ struct GemmLnLaunch {
   void* y_out; long long ldy;         // bf16 [M, N] (LNM_FINAL: nullable)
   const int* row_limit; int rows_per_seq;
   KernelTiming* timing = nullptr; int family = 0;
+  int variant = 1;                    // 1: gemm_ln_split_kernel (normalisation passes on their own warps); 0: gemm_ln_kernel
+  int a_prefetch = 0;                 // L2 prefetch distance for A tiles in k-blocks (split kernel)
+#ifdef CF_ABLATION
+  long long* prof = nullptr;
+#endif
 };
 
 template <int NC>
@@ -251,16 +256,32 @@ inline bool launch_gemm_ln_nc(const GemmLnLaunch& g, int num_sms, cudaStream_t s
   ep.ln1_w = g.ln1_w; ep.ln1_b = g.ln1_b; ep.ln2_w = g.ln2_w; ep.ln2_b = g.ln2_b;
   ep.row_limit = g.row_limit; ep.rows_per_seq = g.rows_per_seq > 0 ? g.rows_per_seq : 1;
   ep.store_f32 = g.x_out != nullptr; ep.store_bf16 = g.y_out != nullptr;
-  auto kern = gemm_ln_kernel<NC>;
-  const size_t smem = gemmln_smem_bytes<NC>();
-  if (!ensure_smem_optin(kern, smem, err, "gemm_ln")) return false;
+  ep.a_prefetch = g.a_prefetch;
+#ifdef CF_ABLATION
+  ep.prof = g.prof;
+  { const char* e = getenv("CF_LN_DEBUG"); ep.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("CF_LN_PREFETCH"); if (e) ep.a_prefetch = atoi(e); }
+#endif
   const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM;
   if (m_tiles == 0) return true;
   int clusters = num_sms / 2;
   if (clusters > m_tiles) clusters = m_tiles;
-  const bool timed = g.timing && g.timing->begin(g.family, stream);
-  kern<<<2 * clusters, GEMM_THREADS, smem, stream>>>(ta, tb, tx, tr, ty, g.M, g.K, ep);
-  if (timed) g.timing->end(stream);
+  if (g.variant == 1) {
+    auto kern = gemm_ln_split_kernel<NC>;
+    const size_t smem = gemmln_split_smem_bytes<NC>();
+    if (!ensure_smem_optin(kern, smem, err, "gemm_ln_split")) return false;
+    const bool timed = g.timing && g.timing->begin(g.family, stream);
+    kern<<<2 * clusters, gemmln_split_threads<NC>(), smem, stream>>>(ta, tb, tx, tr, g.M, g.K, ep, g.x_out, g.ldx,
+                                                                    static_cast<__nv_bfloat16*>(g.y_out), g.ldy);
+    if (timed) g.timing->end(stream);
+  } else {
+    auto kern = gemm_ln_kernel<NC>;
+    const size_t smem = gemmln_smem_bytes<NC>();
+    if (!ensure_smem_optin(kern, smem, err, "gemm_ln")) return false;
+    const bool timed = g.timing && g.timing->begin(g.family, stream);
+    kern<<<2 * clusters, GEMM_THREADS, smem, stream>>>(ta, tb, tx, tr, ty, g.M, g.K, ep);
+    if (timed) g.timing->end(stream);
+  }
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

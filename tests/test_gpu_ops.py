@@ -403,8 +403,10 @@ def _ln_ref(x, w, b):
                                    (777, 256, 2304), (20000, 256, 2048)])
 @pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("with_resid,with_mask", [(True, False), (True, True), (False, False)])
-def test_gemm_ln_pair_kernel(M, N, K, mode, with_resid, with_mask):
-    """gemm_ln_kernel (CTA pair, row statistics over DSMEM) against fp32 torch: x_new = resid + rowmask * alpha * (A W^T + b)
+@pytest.mark.parametrize("variant", [0, 16])
+def test_gemm_ln_pair_kernel(M, N, K, mode, with_resid, with_mask, variant):
+    """gemm_ln_split_kernel (variant 0: the default, normalisation passes on their own warps) and gemm_ln_kernel (variant 16)
+    - CTA pair, row statistics over DSMEM - against fp32 torch: x_new = resid + rowmask * alpha * (A W^T + b)
     followed by one or two LayerNorms, every output the kernel writes; ragged last row block, row masks, zeroed rows."""
     L = cflib.load()
     A = _rand((M, K), 1.0, 1).bfloat16()
@@ -435,8 +437,8 @@ def test_gemm_ln_pair_kernel(M, N, K, mode, with_resid, with_mask):
         zero = (torch.arange(M, device=DEV) % rows_per_seq) >= limit[torch.arange(M, device=DEV) // rows_per_seq]
     x_out = torch.full((M, N), 7.0, device=DEV)
     y_out = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
-    rc = L.cf_op_gemm_ln(_p(A), K, _p(W), K, M, N, K, _p(bias), _p(resid), N if resid is not None else 0, alpha, _p(rng), rpc, mode,
-                         _p(w1), _p(b1), _p(w2), _p(b2), _p(x_out), N, _p(y_out), N, _p(limit), rows_per_seq, _stream())
+    rc = L.cf_op_gemm_ln(_p(A), K, _p(W), K, M, N, K, _p(bias), _p(resid), N if resid is not None else 0, alpha, _p(rng), rpc,
+                         mode + variant, _p(w1), _p(b1), _p(w2), _p(b2), _p(x_out), N, _p(y_out), N, _p(limit), rows_per_seq, _stream())
     cflib.check(rc, None, "cf_op_gemm_ln")
     torch.cuda.synchronize()
     upd = alpha * (A.float() @ W.float().T + bias) * keep.unsqueeze(1)
