@@ -74,6 +74,7 @@ struct cf_handle {
   // per-handle options (cf_set_option)
   int opt_fused_layernorm = 1;   // LayerNorms fused into the epilogue of the residual GEMM in front of them (gemm_ln.cuh)
   int opt_ln_split = 1;          // ... with the normalisation passes on their own warps (gemm_ln_split_kernel)
+  int opt_gemm_pair = -1;        // plain GEMMs: -1 = by shape (gemm_host.cuh), 0 = 1-CTA kernel, 1 = CTA-pair (cta_group::2) kernel
   int opt_ffn_slab_rows = 0;     // > 0: the two FFN GEMMs run slab by slab of this many rows, the hidden activation of a slab
                                  // (rows x F bf16) is produced and consumed while it is still in L2
   int opt_fused_ffn = 0;         // feed-forward modules as one kernel each, hidden activation kept on chip (ffn_fused.cuh)
@@ -121,6 +122,7 @@ extern "C" int cf_set_option(cf_handle* h, const char* name, int value) {
   const std::string k(name);
   if (k == "fused_layernorm") { h->opt_fused_layernorm = value != 0; return CF_OK; }
   if (k == "ln_split") { h->opt_ln_split = value != 0; return CF_OK; }
+  if (k == "gemm_pair") { h->opt_gemm_pair = value < 0 ? -1 : (value != 0); return CF_OK; }
   if (k == "fused_ffn") { h->opt_fused_ffn = value != 0; return CF_OK; }
   if (k == "ffn_slab_rows") { h->opt_ffn_slab_rows = value > 0 ? ((value + 127) / 128) * 128 : 0; return CF_OK; }
   return fail(h, CF_ERR_INVALID, "cf_set_option: unknown option " + k);
@@ -858,7 +860,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.out = e.out; g.ldo = e.ldo;
     g.ep.bias = e.bias; g.ep.resid = e.resid; g.ep.ld_resid = e.ld_resid; g.ep.alpha = e.alpha;
     g.ep.row_range = e.row_range; g.ep.rows_per_chunk = e.rows_per_chunk;
-    g.timing = &h->timing; g.family = e.family;
+    g.timing = &h->timing; g.family = e.family; g.variant = h->opt_gemm_pair;
     return launch_gemm(g, h->num_sms, st, &err);
   };
   // residual GEMM + the LayerNorm(s) that follow it, one kernel (gemm_ln.cuh)

@@ -559,6 +559,11 @@ CF_DEVINL uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {   // shared::c
 CF_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Without the cluster-scope release (which drains every outstanding store of the warp: ERRBAR): for hand-offs whose payload is
+// not ordinary memory, e.g. "my tcgen05.ld reads of this accumulator have completed" (tcgen05.wait::ld + fence::before_thread_sync).
+CF_DEVINL void mbar_arrive_cluster_norelease(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 CF_DEVINL void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -743,7 +748,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+      if (lane == 0) mbar_arrive_cluster_norelease(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
     }
     if (issuer && EPI != EPI_ARGMAX) tma_store_wait_all();
   }

@@ -127,9 +127,11 @@ inline bool ensure_smem_optin(Kern kern, size_t bytes, std::string* err, const c
 template <int EPI, int ACT>
 inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t stream, std::string* err) {
   int use2 = g.variant;
-  // Measured on B200 (tools/bench_gemm_shapes.py): the pair kernel wins when the K loop dominates (K >= 1024: FFN w_2,
-  // embed.out); for K = 512 the epilogue dominates and the 1-CTA kernel is faster. Small M: a 256-row tile is mostly padding.
-  if (use2 < 0) use2 = (g.M >= 2048 && g.K >= 1024) ? 1 : 0;
+  // Measured on B200 (tools/bench_gemm_shapes.py, profiles/README.md round 2): the pair kernel (half the B-operand traffic per
+  // CTA) wins on every large shape - FFN w_1 0.336 -> 0.309 ms, QKV 0.333 -> 0.292, GLU 0.151 -> 0.136, CTC 0.699 -> 0.666 -
+  // except the K = 512 fp32 + residual epilogue (0.180 vs 0.198), since its accumulator hand-off to the leader CTA no longer
+  // carries a cluster-scope release (it used to lose at K = 512).  Small M: a 256-row tile is mostly padding.
+  if (use2 < 0) use2 = (g.M >= 2048 && (g.K >= 1024 || EPI != EPI_F32)) ? 1 : 0;
   CUtensorMap ta, tb, tc, tr;
   GemmEpiParams ep = g.ep;
   if (!make_tma_2d_bf16(&ta, g.A, g.M, g.K, g.lda, GEMM_BM, GEMM_BK, err)) return false;
@@ -235,7 +237,6 @@ struct GemmLnLaunch {
   const int* row_limit; int rows_per_seq;
   KernelTiming* timing = nullptr; int family = 0;
   int variant = 1;                    // 1: gemm_ln_split_kernel (normalisation passes on their own warps); 0: gemm_ln_kernel
-  int a_prefetch = 0;                 // L2 prefetch distance for A tiles in k-blocks (split kernel)
 #ifdef CF_ABLATION
   long long* prof = nullptr;
 #endif
@@ -256,11 +257,9 @@ inline bool launch_gemm_ln_nc(const GemmLnLaunch& g, int num_sms, cudaStream_t s
   ep.ln1_w = g.ln1_w; ep.ln1_b = g.ln1_b; ep.ln2_w = g.ln2_w; ep.ln2_b = g.ln2_b;
   ep.row_limit = g.row_limit; ep.rows_per_seq = g.rows_per_seq > 0 ? g.rows_per_seq : 1;
   ep.store_f32 = g.x_out != nullptr; ep.store_bf16 = g.y_out != nullptr;
-  ep.a_prefetch = g.a_prefetch;
 #ifdef CF_ABLATION
   ep.prof = g.prof;
   { const char* e = getenv("CF_LN_DEBUG"); ep.debug = e ? atoi(e) : 0; }
-  { const char* e = getenv("CF_LN_PREFETCH"); if (e) ep.a_prefetch = atoi(e); }
 #endif
   const int m_tiles = (g.M + GEMM_BM - 1) / GEMM_BM;
   if (m_tiles == 0) return true;

@@ -38,7 +38,6 @@ struct GemmLnParams {
   const int* row_limit = nullptr;      // LNM_Y: rows with (row % rows_per_seq) >= limit[row / rows_per_seq] give y = 0
   int rows_per_seq = 1;
   int store_f32 = 1, store_bf16 = 1;   // LNM_FINAL: which outputs exist
-  int a_prefetch = 0;                  // gemm_ln_split_kernel: L2 prefetch distance for A tiles, in k-blocks (0 = off)
 #ifdef CF_ABLATION
   long long* prof = nullptr;           // tools build: [grid][16] cycles per role spent waiting / working (gemm_ln_split_kernel)
   int debug = 0;                       // tools build: phase ablation bits (gemm_ln_split_kernel; results are wrong)
@@ -624,17 +623,8 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     // ------------------------------------------------ TMA producer
     uint32_t stage = 0, phase = 0;
     CF_PROF_DECL(w_empty = 0, t_all = clock64());
-    // A is streamed from HBM exactly once (both CTAs of the pair read the same tile), and the ring holds only STAGES k-blocks:
-    // the tile PF k-blocks ahead (this row block's or the next one's) is pulled into L2 now, so that its TMA load is an L2 hit;
-    // the two CTAs prefetch alternate k-blocks
-    const int PF = ep.a_prefetch;
     for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters) {
       for (int kb = 0; kb < k_blocks; ++kb) {
-        if (PF > 0 && (uint32_t(kb) & 1u) == rank && lane == 0) {
-          int pk = kb + PF, pm = m_blk;
-          while (pk >= k_blocks) { pk -= k_blocks; pm += num_clusters; }
-          if (pm < m_tiles) tma_prefetch_2d(&tma_a, pk * GEMM_BK, pm * GEMM_BM);
-        }
         { CF_PROF_T0(); mbar_wait(&empty_bar[stage], phase ^ 1); CF_PROF_ADD(w_empty); }
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -751,28 +741,41 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           named_bar_sync(bar_id, 128);
         }
         CF_PROF_MARK(0);
-        float4 b[8];
-#pragma unroll
-        for (int qd = 0; qd < 8; ++qd) b[qd] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + qd);
         if (has_res) { CF_PROF_T0(); mbar_wait(&rfull[slot], ((slot ? nl1 : nl0) - 1u) & 1u); CF_PROF_ADD(w_res); }
         CF_PROF_MARK(1);
         { CF_PROF_T0(); tmem_ld_wait(); CF_PROF_ADD(w_tld); }
         CF_PROF_MARK(2);
+        // Two halves of 16 columns: the four residual reads of a half are issued together and all precede the half's four
+        // stores.  (Written as one load - compute - store sequence per 16 bytes the compiler must keep every load behind the
+        // previous store to the same tile: eight serialised shared-memory round trips per round, 1 800 of a round's 4 500 cycles.)
         float v[32];
 #pragma unroll
-        for (int qd = 0; qd < 8; ++qd) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res && !CF_LN_DBG(ep, 4)) {
-            const uint4 xr4 = stage_load16(tl, trow, qd);
-            x = make_float4(__uint_as_float(xr4.x), __uint_as_float(xr4.y), __uint_as_float(xr4.z), __uint_as_float(xr4.w));
+        for (int hf = 0; hf < 2; ++hf) {
+          uint4 xr4[4];
+          float4 b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int qd = 4 * hf + i;
+            xr4[i] = (has_res && !CF_LN_DBG(ep, 4)) ? stage_load16(tl, trow, qd) : make_uint4(0u, 0u, 0u, 0u);
+            b[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + qd);
           }
-          v[4 * qd] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd]) + b[qd].x, x.x) : x.x;
-          v[4 * qd + 1] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 1]) + b[qd].y, x.y) : x.y;
-          v[4 * qd + 2] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 2]) + b[qd].z, x.z) : x.z;
-          v[4 * qd + 3] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 3]) + b[qd].w, x.w) : x.w;
-          if (store_x && !CF_LN_DBG(ep, 4))
-            stage_store16(tl, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
-                                                   __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int qd = 4 * hf + i;
+            const float4 x = make_float4(__uint_as_float(xr4[i].x), __uint_as_float(xr4[i].y), __uint_as_float(xr4[i].z), __uint_as_float(xr4[i].w));
+            v[4 * qd] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd]) + b[i].x, x.x) : x.x;
+            v[4 * qd + 1] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 1]) + b[i].y, x.y) : x.y;
+            v[4 * qd + 2] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 2]) + b[i].z, x.z) : x.z;
+            v[4 * qd + 3] = keep ? fmaf(ep.alpha, __uint_as_float(r[4 * qd + 3]) + b[i].w, x.w) : x.w;
+          }
+          if (store_x && !CF_LN_DBG(ep, 4)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int qd = 4 * hf + i;
+              stage_store16(tl, trow, qd, make_uint4(__float_as_uint(v[4 * qd]), __float_as_uint(v[4 * qd + 1]),
+                                                     __float_as_uint(v[4 * qd + 2]), __float_as_uint(v[4 * qd + 3])));
+            }
+          }
         }
         CF_PROF_MARK(3);
 #pragma unroll
