@@ -495,7 +495,7 @@ def main():
             alone.append(e0.elapsed_time(e1))
             time.sleep(0.02)
         best_alone = min(alone)
-        roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<EPI_BF16, ACT_SILU> (FFN w_1 + SiLU, M=%d N=%d K=%d)" % (rows, F, d),
+        roofline = {"bound": "tensor", "kernel": "gemm2_tcgen05_kernel<EPI_BF16, ACT_SILU> (FFN w_1 + SiLU on CTA pairs, cta_group::2, M=%d N=%d K=%d)" % (rows, F, d),
                     "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": (achieved / sustained) if achieved else None,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the timed steps, %d launches)" % dom_n)
                     if peaks else "fallback 1.4 PFLOP/s sustained",
@@ -503,7 +503,7 @@ def main():
                     "flops_per_launch": flops,
                     "alone": {"ms_best_of_10": best_alone, "achieved": flops / (best_alone * 1e-3) / 1e12, "peak": burst,
                               "frac": flops / (best_alone * 1e-3) / 1e12 / burst, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)"},
-                    "also": {"kernel": "gemm_ln_kernel (FFN w_2 + 0.5 * residual + the LayerNorm(s) behind it, CTA pair, M=%d N=%d K=%d; "
+                    "also": {"kernel": "gemm_ln_split_kernel (FFN w_2 + 0.5 * residual + the LayerNorm(s) behind it, CTA pair, M=%d N=%d K=%d; "
                                        "flops of the GEMM only)" % (rows, d, F),
                              "ms_per_launch": fam["w2"][0] / max(fam["w2"][1], 1), "launches_timed": fam["w2"][1],
                              "achieved": flops / (fam["w2"][0] / max(fam["w2"][1], 1) * 1e-3) / 1e12 if fam["w2"][1] else None,

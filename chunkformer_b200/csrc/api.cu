@@ -73,7 +73,8 @@ struct cf_handle {
   cf::KernelTiming timing;
   // per-handle options (cf_set_option)
   int opt_fused_layernorm = 1;   // LayerNorms fused into the epilogue of the residual GEMM in front of them (gemm_ln.cuh)
-  int opt_ln_split = 1;          // ... with the normalisation passes on their own warps (gemm_ln_split_kernel)
+  int opt_ln_split = -1;         // ... 1: normalisation passes on their own warps (gemm_ln_split_kernel), 2: + cluster of four with
+                                 // cta_group::2 MMAs (gemm_ln_quad_kernel), -1: default (1), 0: gemm_ln_kernel
   int opt_gemm_pair = -1;        // plain GEMMs: -1 = by shape (gemm_host.cuh), 0 = 1-CTA kernel, 1 = CTA-pair (cta_group::2) kernel
   int opt_ffn_slab_rows = 0;     // > 0: the two FFN GEMMs run slab by slab of this many rows, the hidden activation of a slab
                                  // (rows x F bf16) is produced and consumed while it is still in L2
@@ -121,7 +122,7 @@ extern "C" int cf_set_option(cf_handle* h, const char* name, int value) {
   if (!h || !name) return fail(h, CF_ERR_INVALID, "cf_set_option: null argument");
   const std::string k(name);
   if (k == "fused_layernorm") { h->opt_fused_layernorm = value != 0; return CF_OK; }
-  if (k == "ln_split") { h->opt_ln_split = value != 0; return CF_OK; }
+  if (k == "ln_split") { h->opt_ln_split = value < 0 ? -1 : (value > 2 ? 2 : value); return CF_OK; }
   if (k == "gemm_pair") { h->opt_gemm_pair = value < 0 ? -1 : (value != 0); return CF_OK; }
   if (k == "fused_ffn") { h->opt_fused_ffn = value != 0; return CF_OK; }
   if (k == "ffn_slab_rows") { h->opt_ffn_slab_rows = value > 0 ? ((value + 127) / 128) * 128 : 0; return CF_OK; }
@@ -1610,7 +1611,8 @@ extern "C" int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t 
   GemmLnLaunch g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.bias = bias; g.resid = resid; g.ld_resid = ld_resid;
   g.alpha = alpha; g.row_range = reinterpret_cast<const int2*>(row_range); g.rows_per_chunk = rows_per_chunk;
-  g.mode = mode & 15; g.variant = (mode & 16) ? 0 : 1;     // mode + 16: the single-epilogue-group kernel (kept for A/B measurements)
+  g.mode = mode & 15;
+  g.variant = (mode & 16) ? 0 : ((mode & 32) ? 2 : ((mode & 64) ? 1 : -1));   // + 16: single-epilogue-group kernel, + 32: cluster of four, + 64: pair
   g.ln1_w = ln1_w; g.ln1_b = ln1_b; g.ln2_w = ln2_w; g.ln2_b = ln2_b; g.x_out = x_out; g.ldx = ldx; g.y_out = y_out; g.ldy = ldy;
   g.row_limit = row_limit; g.rows_per_seq = rows_per_seq;
   std::string err;

@@ -550,20 +550,30 @@ CF_DEVINL void mbar_wait_cluster_relaxed(uint64_t* bar, uint32_t parity) {
   __trap();
 }
 
+template <int NC> constexpr size_t gemmln_quad_smem_bytes() {
+  return size_t(4) * (GEMM_BM * 128 + (NC / 2) * 128) + 4 * GEMM_STAGING_BYTES + (2 * 2 + 2 * 2) * 128 * sizeof(float2) +
+         2 * 2 * gemmln_split_p2_groups<NC>() * 128 * sizeof(float2) + 1024 + 256;
+}
+CF_DEVINL void umma_commit_2sm_mask(uint64_t* bar, uint16_t mask) {   // arrive on `bar` (same offset) in the CTAs of `mask`
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 CF_DEVINL void st_global_v8(void* p, const uint32_t (&o)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
                "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
                : "memory");
 }
 
-template <int NC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemmln_split_threads<NC>(), 1)
-gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                     const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_r, int M, int K,
-                     GemmLnParams ep, float* __restrict__ x_out, long long ldx, __nv_bfloat16* __restrict__ y_out, long long ldy) {
-  constexpr int STAGES = gemmln_stages<NC>();
+template <int NC, bool QUAD>
+CF_DEVINL void gemm_ln_split_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const CUtensorMap& tma_x, const CUtensorMap& tma_r,
+                                  int M, int K, const GemmLnParams& ep, float* __restrict__ x_out, long long ldx,
+                                  __nv_bfloat16* __restrict__ y_out, long long ldy) {
+  constexpr int STAGES = QUAD ? 4 : gemmln_stages<NC>();
+  constexpr int BMC = QUAD ? 256 : GEMM_BM;          // rows per cluster and row block
   constexpr uint32_t A_BYTES = GEMM_BM * 128;
-  constexpr uint32_t B_BYTES = NC * 128;
+  constexpr uint32_t B_BYTES = (QUAD ? NC / 2 : NC) * 128;   // QUAD: this CTA's half of the pair's NC weight rows
   constexpr uint32_t TMEM_COLS = 2 * NC;
   constexpr int NCG = NC / 2;          // columns per pass-1 group
   constexpr int NR = NCG / 32;
@@ -594,11 +604,22 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  // pair kernel: rank = column half, statistics partner = rank ^ 1.  QUAD (cluster of four = two cta_group::2 pairs): CTA
+  // (pair p = column half, half i = rows [128 i, 128 i + 128) of the cluster's 256-row block) has cluster rank 2 p + i; the pair
+  // runs UMMA 256 x NC x 16 issued by its even-rank CTA, each CTA feeding its own 128 rows of A and half of the pair's weight
+  // rows (32 KB per k-block and CTA instead of 48); the statistics partner is the CTA with the same rows, rank ^ 2.
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = QUAD ? (crank >> 1) : crank;          // column half
+  const uint32_t half = QUAD ? (crank & 1u) : 0u;             // row half
+  const uint32_t peer = QUAD ? (crank ^ 2u) : (crank ^ 1u);   // cluster rank of the statistics partner
+  const uint32_t lead = crank & ~1u;                          // QUAD: cluster rank of this pair's MMA-issuing CTA
+  const uint16_t pair_mask = uint16_t(3u << (crank & 2u));
+  const bool leader = !QUAD || half == 0;
+  const int cluster_id = QUAD ? (blockIdx.x >> 2) : (blockIdx.x >> 1);
+  const int num_clusters = QUAD ? (gridDim.x >> 2) : (gridDim.x >> 1);
+  const int m_tiles = (M + BMC - 1) / BMC;
   const int k_blocks = K / GEMM_BK;
+  const int row_off = int(half) * GEMM_BM;                    // this CTA's first row inside the cluster's row block
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -606,14 +627,14 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     tma_prefetch_desc(&tma_x);
     tma_prefetch_desc(&tma_r);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], P2_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], QUAD ? 2 * P2_WARPS : P2_WARPS); }
     for (int s = 0; s < 4; ++s) mbar_init(&res_full[s], 1);
     for (int s = 0; s < 2; ++s) mbar_init(&stat_bar[s], P1_WARPS);     // + 256 bytes of remote partials per arrival (expect_tx)
     for (int s = 0; s < 2; ++s) mbar_init(&st2_bar[s], P2_WARPS);
     for (int s = 0; s < 2; ++s) mbar_init(&cred_bar[s], P2_WARPS);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { if (QUAD) tmem_alloc_2sm(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   cluster_sync_all();                          // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
@@ -627,9 +648,16 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       for (int kb = 0; kb < k_blocks; ++kb) {
         { CF_PROF_T0(); mbar_wait(&empty_bar[stage], phase ^ 1); CF_PROF_ADD(w_empty); }
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-          tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, int(rank) * NC);
+          if (QUAD) {                                  // completion of both CTAs' loads lands on the leader's barrier
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
+            const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), lead);
+            tma_load_2d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, m_blk * BMC + row_off);
+            tma_load_2d_2sm(sB + stage * B_BYTES, &tma_b, fb, kb * GEMM_BK, int(rank) * NC + int(half) * (NC / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+            tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, int(rank) * NC);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -639,14 +667,14 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     if (ep.prof && lane == 0) { ep.prof[blockIdx.x * 16 + 0] = clock64() - t_all; ep.prof[blockIdx.x * 16 + 1] = w_empty; }
 #endif
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, NC);
+    // ------------------------------------------------ MMA issuer (QUAD: the pair's even-rank CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(QUAD ? 256 : GEMM_BM, NC);
     const uint64_t da0 = make_sw128_desc(smem_u32(sA));
     const uint64_t db0 = make_sw128_desc(smem_u32(sB));
     uint32_t stage = 0, phase = 0;
     int it = 0;
     CF_PROF_DECL(w_tempty = 0, w_full = 0, t_all = clock64());
-    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters, ++it) {
+    for (int m_blk = cluster_id; leader && m_blk < m_tiles; m_blk += num_clusters, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       { CF_PROF_T0(); mbar_wait(&tempty_bar[acc], acc_phase ^ 1); CF_PROF_ADD(w_tempty); }
       tc_fence_after();
@@ -657,10 +685,17 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         if (elect_one()) {
           const uint64_t da = da0 + uint64_t((stage * A_BYTES) >> 4);
           const uint64_t db = db0 + uint64_t((stage * B_BYTES) >> 4);
+          if (QUAD) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_commit_2sm_mask(&empty_bar[stage], pair_mask);
+            if (kb == k_blocks - 1) umma_commit_2sm_mask(&tfull_bar[acc], pair_mask);
+          } else {
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&empty_bar[stage]);
+            if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -688,7 +723,7 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       tma_load_2d(stg + slot * GEMM_STAGING_BYTES, &tma_r, &rfull[slot], col0, row0);
     };
     if (has_res && cluster_id < m_tiles) {
-      if (issuer) issue_resid(0, gcol0, cluster_id * GEMM_BM);
+      if (issuer) issue_resid(0, gcol0, cluster_id * BMC + row_off);
       ++nl0;
     }
     int it = 0;
@@ -696,9 +731,9 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters, ++it) {
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * NC + grp * NCG;
-      const int row0 = m_blk * GEMM_BM;
+      const int row0 = m_blk * BMC + row_off;
       const int next_blk = m_blk + num_clusters;
-      const int next_row0 = next_blk < m_tiles ? next_blk * GEMM_BM : -1;
+      const int next_row0 = next_blk < m_tiles ? next_blk * BMC + row_off : -1;
       const int row = row0 + trow;
       bool keep = true;
       if (ep.row_range != nullptr && row < M) {
@@ -799,7 +834,7 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         float2* po = s_own + (par * 2u + uint32_t(grp)) * 128u + trow;
         float2* pp = s_peer + (par * 2u + uint32_t(grp)) * 128u + trow;
         *po = make_float2(st1.mean, st1.m2);
-        st_async_f32x2(mapa_rank(smem_u32(pp), rank ^ 1u), st1.mean, st1.m2, mapa_rank(smem_u32(&stat_bar[par]), rank ^ 1u));
+        st_async_f32x2(mapa_rank(smem_u32(pp), peer), st1.mean, st1.m2, mapa_rank(smem_u32(&stat_bar[par]), peer));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(&stat_bar[par], 32 * sizeof(float2));   // the same warp of the peer sends as much
@@ -831,7 +866,7 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += num_clusters, ++it) {
       const uint32_t acc = it & 1;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * NC + ccol0;
-      const int row = m_blk * GEMM_BM + trow;
+      const int row = m_blk * BMC + row_off + trow;
       const bool row_ok = row < M;
       const uint32_t par = uint32_t(it) & 1u;
       { CF_PROF_T0(); mbar_wait(&stat_bar[par], (uint32_t(it) >> 1) & 1u); CF_PROF_ADD(w_stat); }
@@ -853,7 +888,7 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         rstd1 = rsqrtf(tot.m2 / float(N) + 1e-5f);
         // credit: the partials are in registers (the merge above consumed them), the peer may overwrite its entries
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&cred_bar[par]), rank ^ 1u), rstd1);
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&cred_bar[par]), peer), rstd1);
       }
       float mean_l = mean1, rstd_l = rstd1;
       if (two) {
@@ -894,7 +929,7 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         const uint32_t buf = xr2 & 1u;
         float2* p = s_st2 + (buf * uint32_t(2 * P2G) + uint32_t(part2)) * 128u + trow;
         *p = make_float2(st2.mean, st2.m2);
-        st_async_f32x2(mapa_rank(smem_u32(p), rank ^ 1u), st2.mean, st2.m2, mapa_rank(smem_u32(&st2_bar[buf]), rank ^ 1u));
+        st_async_f32x2(mapa_rank(smem_u32(p), peer), st2.mean, st2.m2, mapa_rank(smem_u32(&st2_bar[buf]), peer));
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(&st2_bar[buf], 32 * sizeof(float2));
         { CF_PROF_T0(); mbar_wait(&st2_bar[buf], (xr2 >> 1) & 1u); CF_PROF_ADD(w_st2); }
@@ -959,10 +994,13 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           }
         }
       }
-      // the accumulator (and the x kept in it) is free again
+      // the accumulator (and the x kept in it) is free again (QUAD: the pair's MMA issuer waits for both CTAs)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (QUAD) mbar_arrive_cluster_norelease(mapa_rank(smem_u32(&tempty_bar[acc]), lead));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
 #ifdef CF_ABLATION
     if (ep.prof && pw == 0 && lane == 0) {
@@ -974,7 +1012,28 @@ gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 
   tc_fence_before();
   cluster_sync_all();      // the peer may still write this CTA's statistics tables / signal its barriers
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) { if (QUAD) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+template <int NC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemmln_split_threads<NC>(), 1)
+gemm_ln_split_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_r, int M, int K,
+                     const __grid_constant__ GemmLnParams ep, float* __restrict__ x_out, long long ldx, __nv_bfloat16* __restrict__ y_out,
+                     long long ldy) {
+  gemm_ln_split_body<NC, false>(tma_a, tma_b, tma_x, tma_r, M, K, ep, x_out, ldx, y_out, ldy);
+}
+
+// Cluster of four CTAs = two cta_group::2 pairs per 256-row block (see gemm_ln_split_body): half the weight-operand traffic
+// per CTA and a four-stage ring.  Only 33 clusters of four (132 of 148 SMs) can be resident on a B200 (GPC sizes), so this
+// pays only where the pair kernel starves on operands (K = 2048).
+template <int NC>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(gemmln_split_threads<NC>(), 1)
+gemm_ln_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_r, int M, int K,
+                    const __grid_constant__ GemmLnParams ep, float* __restrict__ x_out, long long ldx, __nv_bfloat16* __restrict__ y_out,
+                    long long ldy) {
+  gemm_ln_split_body<NC, true>(tma_a, tma_b, tma_x, tma_r, M, K, ep, x_out, ldx, y_out, ldy);
 }
 
 

@@ -224,8 +224,9 @@ CF_API int cf_op_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, in
  * over distributed shared memory): x_new = resid + rowmask * alpha * (A B^T + bias), N = d_model in {256, 512};
  * mode 1: x_out = x_new, y_out = LN1(x_new) (rows beyond row_limit zeroed); 2: x_out = LN1(x_new), y_out = LN2(x_out);
  * 3: x_out (fp32, nullable) / y_out (bf16, nullable) = LN2(LN1(x_new)).  Replaces every "x = x + f(norm(x))" step of
- * encoder_layer.py:190-246 together with the LayerNorm that follows it.  mode + 16 runs the first version of the kernel
- * (one set of epilogue warps for all passes), kept for A/B measurements; results are identical. */
+ * encoder_layer.py:190-246 together with the LayerNorm that follows it.  Default kernel: CTA pair with the normalisation passes on
+ * their own warps; mode + 32 selects the cluster-of-four version (cta_group::2 MMAs), mode + 16 the first version (one set of
+ * epilogue warps for all passes), mode + 64 the default explicitly: for A/B measurements, results are identical. */
 CF_API int cf_op_gemm_ln(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, const float* bias,
                   const float* resid, int64_t ld_resid, float alpha, const int32_t* row_range, int rows_per_chunk, int mode,
                   const float* ln1_w, const float* ln1_b, const float* ln2_w, const float* ln2_b, float* x_out, int64_t ldx,

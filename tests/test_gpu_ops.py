@@ -403,9 +403,10 @@ def _ln_ref(x, w, b):
                                    (777, 256, 2304), (20000, 256, 2048)])
 @pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("with_resid,with_mask", [(True, False), (True, True), (False, False)])
-@pytest.mark.parametrize("variant", [0, 16])
+@pytest.mark.parametrize("variant", [64, 16, 32])
 def test_gemm_ln_pair_kernel(M, N, K, mode, with_resid, with_mask, variant):
-    """gemm_ln_split_kernel (variant 0: the default, normalisation passes on their own warps) and gemm_ln_kernel (variant 16)
+    """gemm_ln_split_kernel (variant 64: normalisation passes on their own warps), gemm_ln_quad_kernel (32: cluster of four with
+    cta_group::2 MMAs) and gemm_ln_kernel (16)
     - CTA pair, row statistics over DSMEM - against fp32 torch: x_new = resid + rowmask * alpha * (A W^T + b)
     followed by one or two LayerNorms, every output the kernel writes; ragged last row block, row masks, zeroed rows."""
     L = cflib.load()

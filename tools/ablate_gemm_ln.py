@@ -17,14 +17,15 @@ w1, b1 = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
 junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 def p(t): return c_void_p(t.data_ptr())
+var = int(os.environ.get('CF_LN_VARIANT', '0'))     # 0 pair kernel, 32 cluster of four
 combos = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 8, 16, 32, 3, 7, 24, 31, 63]
 for K, mode in ((512, 1), (2048, 1)):
-    A = torch.randn((rows, K), device="cuda").bfloat16()
+    A = torch.randn((rows + 256, K), device="cuda").bfloat16()      # + 256 rows: CF_LN_ABLOCKED reads A as [K / 64][mpad][64]
     W = (torch.randn((d, K), device="cuda") / K ** 0.5).bfloat16()
     for dbg in combos:
         os.environ["CF_LN_DEBUG"] = str(dbg)
         def run():
-            cflib.check(L.cf_op_gemm_ln(p(A), K, p(W), K, rows, d, K, p(b), p(X), d, 0.5, None, 1, mode, p(w1), p(b1), p(w1), p(b1),
+            cflib.check(L.cf_op_gemm_ln(p(A), K, p(W), K, rows, d, K, p(b), p(X), d, 0.5, None, 1, mode + var, p(w1), p(b1), p(w1), p(b1),
                                         p(X), d, p(Y), d, None, 1, st))
         for _ in range(2): run()
         torch.cuda.synchronize()

@@ -14,7 +14,7 @@ w1, b1 = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
 junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 def p(t): return c_void_p(t.data_ptr())
-variants = [int(a) for a in sys.argv[1:]] or [0, 16]      # 0: gemm_ln_split_kernel (default), 16: gemm_ln_kernel
+variants = [int(a) for a in sys.argv[1:]] or [0, 64, 32, 16]      # 0: by shape, 64: gemm_ln_split_kernel, 32: gemm_ln_quad_kernel, 16: gemm_ln_kernel
 for K, mode, var in [(K, m, v) for (K, m) in ((512, 1), (2048, 1), (2048, 2)) for v in variants]:
     A = torch.randn((rows, K), device="cuda").bfloat16()
     W = (torch.randn((d, K), device="cuda") / K ** 0.5).bfloat16()

@@ -14,7 +14,8 @@ b = torch.zeros(d, device="cuda")
 w1, b1 = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 def p(t): return c_void_p(t.data_ptr())
-for K, mode in ((512, 1), (2048, 1), (2048, 2)):
+var = int(sys.argv[1]) if len(sys.argv) > 1 else 0      # 0 pair kernel, 32 cluster of four
+for K, mode in ((512, 1 + var), (2048, 1 + var), (2048, 2 + var)):
     A = torch.randn((rows, K), device="cuda").bfloat16()
     W = (torch.randn((d, K), device="cuda") / K ** 0.5).bfloat16()
     os.environ.pop("CF_LN_PROF", None)
