@@ -361,7 +361,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         if (lane == 0) mbar_arrive(s_free);            // this warp's part of S is in registers
         float* xch = s_xch + (blk & 1) * 256;
         xch[set * 128 + rho] = mx;
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + quad, 64);      // only the two warps that share this quadrant's rows exchange anything
         const float m_new = fmaxf(m_run, fmaxf(mx, xch[(set ^ 1) * 128 + rho]));
         const float alpha = fast_exp2(m_run - m_new);
         float sum = 0.f;
@@ -399,7 +399,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       ep_g = g; ep_l = l_run; ep_row0 = 128LL * pair;
     }
     if (ep_g >= 0) {
-      named_bar_sync(1, 256);
+      named_bar_sync(1 + quad, 64);      // only the two warps that share this quadrant's rows exchange anything
       mbar_wait(pv_done, (blk - 1) & 1);
       tc_fence_after();
       write_out();
@@ -736,7 +736,7 @@ attention_ring_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/
         }
         float* xch = s_xch + (blk & 1) * 256;
         xch[set * 128 + rho] = mx;
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + quad, 64);      // only the two warps that share this quadrant's rows exchange anything
         const float m_new = fmaxf(m_run, fmaxf(mx, xch[(set ^ 1) * 128 + rho]));
         const float alpha = fast_exp2(m_run - m_new);
         float sum = 0.f;
@@ -773,7 +773,7 @@ attention_ring_kernel(const __grid_constant__ CUtensorMap tma_q /*box 128 x 64*/
       ep_pending = true; ep_l = l_run; ep_row = real ? (long long)tl.qrow0 + rho : -1;
     }
     if (ep_pending) {
-      named_bar_sync(1, 256);
+      named_bar_sync(1 + quad, 64);      // only the two warps that share this quadrant's rows exchange anything
       mbar_wait(pv_done, (blk - 1) & 1);
       tc_fence_after();
       write_out();

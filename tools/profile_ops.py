@@ -17,7 +17,7 @@ pos[:R] = torch.randn((R, d), device="cuda").bfloat16()
 rng = torch.zeros((n + 2, 2), dtype=torch.int32); rng[:n, 1] = l + c + r; rng[0, 0] = l; rng = rng.cuda()
 ctx = torch.zeros((n * c, d), device="cuda", dtype=torch.bfloat16)
 def attn1(): cflib.check(L.cf_op_attention(1, p(qkv), p(pos), p(rng), p(ctx), n, c, l, r, d, H, 1, st))
-def attn2(): cflib.check(L.cf_op_attention(2, p(qkv), p(pos), p(rng), p(ctx), n, c, l, r, d, H, 1, st))
+def attn3(): cflib.check(L.cf_op_attention(3, p(qkv), p(pos), p(rng), p(ctx), n, c, l, r, d, H, 1, st))     # ring kernel (64-key blocks)
 g = torch.randn((n * c + 14 + 64, d), device="cuda").bfloat16()
 z = torch.empty((n * c, d), device="cuda", dtype=torch.bfloat16)
 w, b = torch.randn((d, 15), device="cuda") * 0.3, torch.randn(d, device="cuda") * 0.1
@@ -28,7 +28,7 @@ x = torch.randn((n * c, d), device="cuda")
 y = torch.empty((n * c, d), device="cuda", dtype=torch.bfloat16)
 def ln0(): cflib.check(L.cf_op_layernorm(0, d, p(x), None, p(y), p(lw), p(lb), None, None, n * c, st))
 only = sys.argv[1:]
-for f in (attn1, attn2, dwconv, ln0):
+for f in (attn1, attn3, dwconv, ln0):
     if only and f.__name__ not in only: continue
     for _ in range(3): f()
     torch.cuda.synchronize()
