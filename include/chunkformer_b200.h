@@ -78,9 +78,13 @@ CF_API int64_t cf_fbank_num_frames(int64_t n_samples, int sample_rate, int frame
 CF_API int cf_fbank(cf_handle* h, const float* pcm, int64_t n_samples, int sample_rate, int num_mel_bins, int frame_length_ms,
                     int frame_shift_ms, float* out, void* stream);
 /* Per-handle option.  "fused_layernorm" (default 1): the LayerNorm(s) behind every residual GEMM run in that GEMM's epilogue
- * (0 = stand-alone LayerNorm kernels; kept for A/B measurement).  "fused_ffn" (default 1, needs fused_layernorm): every
- * feed-forward module runs as one kernel that keeps the hidden activation on chip (0 = w_1 GEMM, hidden activation through
- * global memory, w_2 GEMM). */
+ * (0 = stand-alone LayerNorm kernels; kept for A/B measurement).  "fused_ffn" (default 0: measured slower; needs
+ * fused_layernorm): every feed-forward module runs as one kernel that keeps the hidden activation on chip (0 = w_1 GEMM, hidden
+ * activation through global memory, w_2 GEMM).  "ln_split" (default -1 = 1): which residual GEMM + LayerNorm kernel runs: 1 = CTA
+ * pair with the normalisation passes on their own warps, 2 = the same on a cluster of four with cta_group::2 MMAs, 0 = the first
+ * version.  "gemm_pair" (default -1 = by shape): plain GEMMs on the CTA-pair kernel (1) or the one-CTA kernel (0).
+ * "ffn_slab_rows" (default 0 = off): the two feed-forward GEMMs slab by slab.  All variants give the same results to fp32
+ * summation order; the knobs exist for A/B measurements (tools/ab_option.py). */
 CF_API int cf_set_option(cf_handle* h, const char* name, int value);
 /* Measurement hook (bench.py roofline): CUDA events around every launch of the selected kernel families made by this handle's
  * cf_encode calls, on the launching stream, from cf_kernel_timing_begin until cf_kernel_timing_end(family), which returns the
@@ -243,7 +247,8 @@ CF_API int cf_op_layernorm(int mode, int d, const float* x_in, float* x_out, voi
                     const float* w2, const float* b2, int64_t rows, void* stream);
 CF_API int cf_op_dwconv(int d, int kernel, const void* g_bf16, void* z_bf16, const float* w, const float* bias,
                  const float* ln_w, const float* ln_b, const int32_t* range, int c, int n_chunks, void* stream);
-/* impl 0 = generic CUDA-core kernel, 1 = tcgen05 kernel (c=64, d_k=64, l+c+r <= 320 multiple of 64).
+/* impl 0 = generic CUDA-core kernel, 1 = tcgen05 kernels (128-key-block kernel where it applies, else the ring kernel),
+ * 3 = ring kernel.
  * prescaled != 0: the Q+u / Q+v columns already carry (1/sqrt(d_k)) * log2(e), as cf_encode's fused projection writes them. */
 CF_API int cf_op_attention(int impl, const void* qkv_bf16, const void* pos_bf16, const int32_t* range, void* ctx_bf16,
                     int n_chunks, int c, int l, int r, int d, int heads, int prescaled, void* stream);

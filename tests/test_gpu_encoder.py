@@ -217,14 +217,17 @@ def test_full_size_masked_batch_properties():
         _compare(a, ref.reshape(-1, 512)[:m], f"utterance {u} inside the 14 400 s batch vs oracle")
 
 
-@pytest.mark.parametrize("option,on,default", [("fused_layernorm", 1, 1), ("fused_ffn", 1, 0), ("ffn_slab_rows", 256, 0)])
+@pytest.mark.parametrize("option,on,default", [("fused_layernorm", 1, 1), ("fused_ffn", 1, 0), ("ffn_slab_rows", 256, 0),
+                                               ("ln_split", 1, -1), ("ln_split", 2, -1), ("gemm_pair", 1, -1)])
 @pytest.mark.parametrize("geo,seed", [(SMALL, 11), (RNNT_LARGE, 7)])
 def test_fused_layernorm_equals_standalone_layernorm(geo, seed, option, on, default):
     """A/B of the two fusions on the same handle.  "fused_ffn": every feed-forward module as one kernel (ffn_fused.cuh) against
     w_1 GEMM -> hidden activation in global memory -> w_2 GEMM: the same bf16 hidden values either way.  "fused_layernorm":
     the LayerNorms fused into the residual GEMM epilogues (CTA pair + DSMEM statistics, gemm_ln.cuh) against the stand-alone
     LayerNorm kernels.  "ffn_slab_rows": the two FFN GEMMs slab by slab (hidden activation kept in L2) against one pass over all
-    rows: identical arithmetic, must agree exactly.  For the fusions: same bf16 GEMM inputs, fp32 statistics either way.  The two differ only in the
+    rows: identical arithmetic, must agree exactly.  "ln_split": the residual GEMM + LayerNorm kernel with the normalisation on
+    its own warps (1: CTA pair, 2: cluster of four with cta_group::2 MMAs) against its first version (0).  "gemm_pair": every plain
+    GEMM on the CTA-pair kernel (also the small, ragged ones) against the one-CTA kernel.  For the fusions: same bf16 GEMM inputs, fp32 statistics either way.  The two differ only in the
     summation order of the statistics (1 ulp of fp32), which now and then flips the bf16 rounding of a normalised activation;
     through 12 layers that grows to the size of the kernels' own distance from the fp32 oracle (measured 0.016 / 0.29 % on
     rnnt-large), so the bound is the parity bar's order of magnitude, not fp32 rounding."""
