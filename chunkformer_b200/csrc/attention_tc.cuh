@@ -20,8 +20,10 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "attention_simt.cuh"
 #include "gemm_host.cuh"
@@ -106,7 +108,15 @@ struct AttnTcParams {
   int c_log2, tab_row0, n_last;              // chunk size (log2); first resident table row (c - 128); S_bd columns of the last block
   int items_per_cta_stride;                  // CTAs per head
   float scale_log2e;
+#ifdef CF_ABLATION
+  long long* prof = nullptr;                 // tools build: [grid][16] cycles per phase of softmax warp 0 / the MMA warp
+#endif
 };
+#ifdef CF_ABLATION
+#define ATC_MARK(k) do { const long long _n = clock64(); seg[k] += _n - seg_t; seg_t = _n; } while (0)
+#else
+#define ATC_MARK(k) do {} while (0)
+#endif
 
 // PRE: Q+u / Q+v already carry (1/sqrt(d_k)) * log2(e) (folded into the fused QKV projection at weight load).
 template <bool PRE>
@@ -286,14 +296,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       }
       ep_g = -1;
     };
+#ifdef CF_ABLATION
+    long long seg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seg_t = clock64();
+    const long long t_begin = seg_t;
+#endif
     for (int pair = first_pair; pair < p.n_pairs; pair += p.items_per_cta_stride) {
       const int g = (pair << (7 - p.c_log2)) + cj;
       const int2 rg = p.range[g];
       const int ulo = rg.x + uoff, uhi = rg.y + uoff;   // valid union slots for this row
       float m_run = -1e30f, l_run = 0.f;
       for (int b = 0; b < nb; ++b, ++blk) {
+        ATC_MARK(7);
         mbar_wait(s_full, blk & 1);
         tc_fence_after();
+        ATC_MARK(0);
         float s[64];
         float mx = -1e30f;
         uint4 keep[4];                                 // packed fp16 S_bd columns [32, 64) of this thread's window:
@@ -356,17 +372,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
             }
           }
         }
+        ATC_MARK(1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free);            // this warp's part of S is in registers
         float* xch = s_xch + (blk & 1) * 256;
         xch[set * 128 + rho] = mx;
-        named_bar_sync(1 + quad, 64);      // only the two warps that share this quadrant's rows exchange anything
+        named_bar_sync(1 + quad, 64);
+        ATC_MARK(2);      // only the two warps that share this quadrant's rows exchange anything
         const float m_new = fmaxf(m_run, fmaxf(mx, xch[(set ^ 1) * 128 + rho]));
         const float alpha = fast_exp2(m_run - m_new);
         float sum = 0.f;
+        ATC_MARK(3);
         if (blk > 0) mbar_wait(pv_done, (blk - 1) & 1);   // previous P V retired: P tile and O are ours again
         tc_fence_after();
+        ATC_MARK(4);
         if (ep_g >= 0) write_out();                    // previous item: its row sums were published before the barrier above
         {
           uint32_t pk[32];                             // this thread's 64 probabilities as 32 packed bf16 pairs
@@ -378,6 +398,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
           }
           tmem_st32(tmem_base + lane_addr + TM_P + 32 * set, pk);
         }
+        ATC_MARK(5);
         l_run = l_run * alpha + sum;
         m_run = m_new;
         if (b > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale this set's half of the running output
@@ -392,6 +413,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        ATC_MARK(6);
       }
       // ---- item finished: publish the row sum (read by the partner thread after the next named barrier) and defer the
       // output to the next block's P V wait
@@ -405,6 +427,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
       write_out();
       tc_fence_before();
     }
+#ifdef CF_ABLATION
+    if (p.prof && (warp == 2 || warp == 7) && lane == 0) {
+      long long* pr = p.prof + (size_t(blockIdx.x) * 2 + (warp == 7)) * 16;
+      for (int k = 0; k < 8; ++k) pr[k] = seg[k];
+      pr[8] = clock64() - t_begin; pr[9] = blk;
+    }
+#endif
   }
 
   tc_fence_before();
@@ -862,8 +891,33 @@ inline bool launch_attention_tc(const AttnParams& a, cudaStream_t st, std::strin
   if (!make_tma_2d_bf16(&tp, a.pos, uint64_t(Rpad), uint64_t(a.d), uint64_t(a.d), 64, 64, err)) return false;
   if (!ensure_smem_optin(attention_tc_kernel<true>, ATC_SMEM_BYTES, err, "attention_tc")) return false;
   if (!ensure_smem_optin(attention_tc_kernel<false>, ATC_SMEM_BYTES, err, "attention_tc")) return false;
+#ifdef CF_ABLATION
+  const int prof_ctas = per_head * a.heads;
+  if (getenv("CF_ATTN_PROF")) { cudaMalloc(&p.prof, size_t(prof_ctas) * 32 * 8); cudaMemsetAsync(p.prof, 0, size_t(prof_ctas) * 32 * 8, st); }
+#endif
   if (a.prescaled) attention_tc_kernel<true><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
   else attention_tc_kernel<false><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
+#ifdef CF_ABLATION
+  if (p.prof) {
+    std::vector<long long> hp(size_t(prof_ctas) * 32);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hp.data(), p.prof, hp.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(p.prof);
+    static const char* names[10] = {"wait S (MMA)", "TMEM loads, staging, skew add, max", "s_free + max exchange barrier", "exponentials",
+                                    "wait previous P V", "write-out of previous item + P store", "O rescale + p_full", "loop overhead",
+                                    "total", "blocks"};
+    for (int w = 0; w < 2; ++w) {
+      fprintf(stderr, "attention_tc softmax warp %d (cycles per key block, mean over %d CTAs):\n", w ? 7 : 2, prof_ctas);
+      double blocks = 0;
+      for (int c = 0; c < prof_ctas; ++c) blocks += double(hp[(size_t(c) * 2 + w) * 16 + 9]);
+      for (int f = 0; f < 9; ++f) {
+        double sum = 0;
+        for (int c = 0; c < prof_ctas; ++c) sum += double(hp[(size_t(c) * 2 + w) * 16 + f]);
+        fprintf(stderr, "  %-40s %10.0f\n", names[f], blocks > 0 ? sum / blocks : 0.0);
+      }
+    }
+  }
+#endif
   ++g_kernel_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("attention_tc launch: ") + cudaGetErrorString(e); return false; }
