@@ -659,6 +659,31 @@ EncodeWs carve_encode(const cf_handle* h, const cf_plan* p, void* base) {
   return w;
 }
 
+// Image of the per-call tables exactly as they lie at the start of the workspace (chunk sources, attention / conv / output
+// ranges, per-sequence row limits): built on the host, then pulled into the workspace (cf_encode) or copied there once
+// (cf_plan_pin).
+static size_t table_image_bytes(const cf_plan* p, const EncodeWs& w) {
+  const size_t o_sl = reinterpret_cast<const uint8_t*>(w.seq_limit) - reinterpret_cast<const uint8_t*>(w.chunk_src);
+  return ((o_sl + size_t(p->B) * sizeof(int)) + 15) & ~size_t(15);
+}
+static void fill_table_image(const cf_plan* p, const EncodeWs& w, uint8_t* base, size_t need) {
+  const uint8_t* dev0 = reinterpret_cast<const uint8_t*>(w.chunk_src);
+  const size_t o_ar = reinterpret_cast<const uint8_t*>(w.att_range) - dev0, o_cr = reinterpret_cast<const uint8_t*>(w.conv_range) - dev0;
+  const size_t o_or = reinterpret_cast<const uint8_t*>(w.out_range) - dev0, o_sl = reinterpret_cast<const uint8_t*>(w.seq_limit) - dev0;
+  memset(base, 0, need);
+  ChunkSrc* cs = reinterpret_cast<ChunkSrc*>(base);
+  int2* ar = reinterpret_cast<int2*>(base + o_ar);
+  int2* cr = reinterpret_cast<int2*>(base + o_cr);
+  int2* orr = reinterpret_cast<int2*>(base + o_or);
+  for (int g = 0; g < p->n; ++g) {
+    cs[g].feat_row = p->chunk_feat_row[g]; cs[g].in_len = p->chunk_in_len[g]; cs[g].pad_ = 0;
+    const cf_chunk_entry& e = p->chunks[g];
+    ar[g] = make_int2(e.att_lo, e.att_hi); cr[g] = make_int2(e.conv_lo, e.conv_hi); orr[g] = make_int2(e.out_lo, e.out_hi);
+  }
+  // (the 16 phantom chunks behind the last attention tile stay empty: zeroed above)
+  if (p->mode == 1) memcpy(base + o_sl, p->seq_valid_rows.data(), size_t(p->B) * sizeof(int));
+}
+
 // Projected relative-position tables P_l = linear_pos_l(PE) for all layers (embedding.py:119-174, attention.py:482):
 // input independent, computed once per (c, l, r) and cached on the handle.
 int get_pos_table(cf_handle* h, int c, int l, int r, cudaStream_t st, const PosTable** out) {
@@ -724,6 +749,28 @@ int get_pos_table(cf_handle* h, int c, int l, int r, cudaStream_t st, const PosT
 extern "C" size_t cf_workspace_bytes(const cf_handle* h, const cf_plan* p) {
   if (!h || !p) return 0;
   return carve_encode(h, p, nullptr).total;
+}
+
+// Copy the plan's tables into the table region of `workspace` now (synchronously) and remember it: cf_encode calls with this
+// plan AND this workspace then skip the per-call table staging (a pinned ring guarded by events), issue nothing that depends
+// on host memory, and can be captured in a CUDA graph and replayed.  The caller must not run another plan through that
+// workspace in between; cf_plan_pin(h, p, NULL, 0, stream) undoes it.
+extern "C" int cf_plan_pin(cf_handle* h, cf_plan* p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !p) return fail(h, CF_ERR_INVALID, "cf_plan_pin: null argument");
+  if (!workspace) { p->resident_ws = nullptr; return CF_OK; }
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(h, CF_ERR_INVALID, "cf_plan_pin: workspace must be 256-byte aligned");
+  if (workspace_bytes < cf_workspace_bytes(h, p)) return fail(h, CF_ERR_WORKSPACE, "cf_plan_pin: workspace too small");
+  if (p->n == 0) return CF_OK;
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const EncodeWs w = carve_encode(h, p, workspace);
+  const size_t need = table_image_bytes(p, w);
+  std::vector<uint8_t> img(need);
+  fill_table_image(p, w, img.data(), need);
+  CF_CUDA(h, cudaMemcpyAsync(w.chunk_src, img.data(), need, cudaMemcpyHostToDevice, st));
+  CF_CUDA(h, cudaStreamSynchronize(st));
+  p->resident_ws = workspace;
+  return CF_OK;
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -806,11 +853,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     zero16_kernel<<<unsigned(std::min<long long>((n16 + 255) / 256, 4LL * h->num_sms)), 256, 0, st>>>(static_cast<uint4*>(dst), n16);
     ++cf::g_kernel_launches;
   };
-  {
+  if (p->resident_ws != workspace) {
     uint8_t* dev0 = reinterpret_cast<uint8_t*>(w.chunk_src);
-    const size_t o_ar = reinterpret_cast<uint8_t*>(w.att_range) - dev0, o_cr = reinterpret_cast<uint8_t*>(w.conv_range) - dev0;
-    const size_t o_or = reinterpret_cast<uint8_t*>(w.out_range) - dev0, o_sl = reinterpret_cast<uint8_t*>(w.seq_limit) - dev0;
-    const size_t need = ((o_sl + size_t(p->B) * sizeof(int)) + 15) & ~size_t(15);
+    const size_t need = table_image_bytes(p, w);
     PinnedStage& sg = h->stage[h->stage_next];
     h->stage_next = (h->stage_next + 1) % 4;
     if (sg.in_flight) { CF_CUDA(h, cudaEventSynchronize(sg.done)); sg.in_flight = false; }
@@ -821,19 +866,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       sg.bytes = need + need / 2;
     }
     if (!sg.done) CF_CUDA(h, cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
-    uint8_t* base = static_cast<uint8_t*>(sg.host);
-    memset(base, 0, need);
-    ChunkSrc* cs = reinterpret_cast<ChunkSrc*>(base);
-    int2* ar = reinterpret_cast<int2*>(base + o_ar);
-    int2* cr = reinterpret_cast<int2*>(base + o_cr);
-    int2* orr = reinterpret_cast<int2*>(base + o_or);
-    for (int g = 0; g < n; ++g) {
-      cs[g].feat_row = p->chunk_feat_row[g]; cs[g].in_len = p->chunk_in_len[g]; cs[g].pad_ = 0;
-      const cf_chunk_entry& e = p->chunks[g];
-      ar[g] = make_int2(e.att_lo, e.att_hi); cr[g] = make_int2(e.conv_lo, e.conv_hi); orr[g] = make_int2(e.out_lo, e.out_hi);
-    }
-    // (the 16 phantom chunks behind the last attention tile stay empty: zeroed above)
-    if (p->mode == 1) memcpy(base + o_sl, p->seq_valid_rows.data(), size_t(p->B) * sizeof(int));
+    fill_table_image(p, w, static_cast<uint8_t*>(sg.host), need);
     void* mapped = nullptr;
     CF_CUDA(h, cudaHostGetDevicePointer(&mapped, sg.host, 0));
     const long long n16 = (long long)(need / 16);

@@ -27,6 +27,7 @@ struct cf_plan {
   std::vector<int64_t> chunk_feat_row;  // first input row of each chunk in the flat feature buffer
   std::vector<int32_t> chunk_in_len;    // input rows present (zero padded beyond)
   std::vector<int32_t> seq_valid_rows;  // mode 1: per sequence calc_length(len) (LayerNorm zeroing limit)
+  const void* resident_ws = nullptr;    // cf_plan_pin: the workspace whose table region already holds this plan's tables
 };
 
 namespace cfplan {

@@ -142,13 +142,14 @@ class ChunkFormerEncoderB200:
         return up.flat
 
     def encode_plan(self, plan: Plan, feats: torch.Tensor, att_cache=None, cnn_cache=None, trunc: int = 0,
-                    out_dtype=torch.float32, want_bf16: bool = False):
-        """Run cf_encode on a prepared plan and a flat device feature buffer. Returns (out (rows, d), out_bf16|None)."""
+                    out_dtype=torch.float32, want_bf16: bool = False, workspace: Optional[torch.Tensor] = None):
+        """Run cf_encode on a prepared plan and a flat device feature buffer. Returns (out (rows, d), out_bf16|None).
+        workspace: a caller-owned uint8 device buffer of cf_workspace_bytes (StreamingGraph pins its plan's tables in one)."""
         d = self.geo.d_model
         out = torch.empty((plan.rows, d), dtype=out_dtype, device=self.device)
         out16 = torch.empty((plan.rows, d), dtype=torch.bfloat16, device=self.device) \
             if (want_bf16 and out_dtype != torch.bfloat16) else None
-        ws = self._workspace(plan)
+        ws = self._workspace(plan) if workspace is None else workspace
         rc = self._L.cf_encode(self._h, plan.handle, c_void_p(feats.data_ptr()), _lib.ptr(att_cache), _lib.ptr(cnn_cache),
                                int(trunc), c_void_p(out.data_ptr()),
                                _lib.CF_F32 if out_dtype == torch.float32 else _lib.CF_BF16, _lib.ptr(out16),
@@ -397,3 +398,101 @@ class ChunkFormerEncoderB200:
         total = o[-1]
         tok_h, fr_h = out_tok[:total].cpu(), out_fr[:total].cpu()
         return [(tok_h[o[s]:o[s + 1]], fr_h[o[s]:o[s + 1]]) for s in range(n)]
+
+
+class StreamingGraph:
+    """Frame-synchronous streaming of B concurrent streams with the steady-state step captured in a CUDA graph.
+
+    A streaming step of ChunkFormerEncoder.forward_chunk (encoder.py:310-390) is about 70 small launches per layer; below a few
+    dozen streams its time is the launches (3.2 ms per step for CTC-large at B = 1 on a B200), not the work.  Once every stream's
+    left context is filled (offset >= left_context_size) the step no longer changes: same plan, same buffers, caches updated in
+    place.  This class runs the first steps through forward_chunk (same caches, donated) and then replays one captured graph
+    of [copy the new frames in, cf_encode on the pinned plan (cf_plan_pin: no host-dependent operation), greedy CTC].
+    Results are those of forward_chunk (tests/test_gpu_encoder.py::test_streaming_graph_equals_forward_chunk).
+
+        sg = StreamingGraph(enc, B, chunk_size=16, left_context_size=64)
+        for frames in source:                     # frames (B, 8 (c - 1) + 15, feat), host or device
+            out, tokens = sg.step(frames)         # out (B, c, d) fp32, tokens (B, c) int64: views of static buffers
+
+    right_context_size > 0 is not offered here (those steps take forward_chunk)."""
+
+    def __init__(self, enc: "ChunkFormerEncoderB200", n_streams: int, chunk_size: int, left_context_size: int,
+                 with_ctc: bool = True):
+        c, l = int(chunk_size), int(left_context_size)
+        geo = enc.geo
+        lo = geo.kernel // 2
+        if n_streams <= 0 or c <= 0 or l < lo:
+            raise ValueError("StreamingGraph needs n_streams > 0, chunk_size > 0 and left_context_size >= kernel // 2")
+        self.enc, self.B, self.c, self.l = enc, int(n_streams), c, l
+        self.with_ctc = bool(with_ctc) and geo.vocab > 0
+        self.T = 8 * (c - 1) + 15
+        L, H, d = geo.layers, geo.heads, geo.d_model
+        dev = enc.device
+        self.att = torch.zeros((L, self.B, H, l, 2 * d // H), device=dev)
+        self.cnn = torch.zeros((L, self.B, d, lo), device=dev)
+        self.x_in = torch.zeros((self.B, self.T, geo.feat_dim), device=dev)
+        self.offset = 0
+        self._ph = -(-max(l, lo) // c)
+        self._t_tot = self._ph * 8 * c + self.T
+        self._x_dev = torch.zeros((self.B, self._t_tot, geo.feat_dim), device=dev)
+        self._plan = Plan(c, l, 0, [self._t_tot] * self.B, [-(self._ph * c - l)] * self.B, geo.kernel)
+        need = int(enc._L.cf_workspace_bytes(enc._h, self._plan.handle))
+        self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._graph = None
+        self._out = self._tok = None
+        self._stream = torch.cuda.Stream(dev)
+
+    def reset(self) -> None:
+        """Start new streams: empty caches, offset 0 (the captured graph is kept)."""
+        self.att.zero_()
+        self.cnn.zero_()
+        self.offset = 0
+
+    def _steady_step(self):
+        enc, B, c, d = self.enc, self.B, self.c, self.enc.geo.d_model
+        self._x_dev[:, self._ph * 8 * c:] = self.x_in
+        _lib.check(enc._L.cf_encode_streams(enc._h, B, self._ph, c), enc._h, "cf_encode_streams")
+        o, _ = enc.encode_plan(self._plan, self._x_dev.view(B * self._t_tot, -1), self.att, self.cnn, 0, workspace=self._ws)
+        out = o.view(B, (self._ph + 1) * c, d)[:, self._ph * c:].contiguous()
+        tok = enc.ctc_greedy(out) if self.with_ctc else None
+        return out, tok
+
+    def _capture(self) -> None:
+        enc = self.enc
+        cur = torch.cuda.current_stream(enc.device)
+        st = self._stream
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            _lib.check(enc._L.cf_plan_pin(enc._h, self._plan.handle, c_void_p(self._ws.data_ptr()), self._ws.numel(),
+                                          c_void_p(st.cuda_stream)), enc._h, "cf_plan_pin")
+            # one eager run on private copies of the caches: position tables, shared-memory opt-ins and workspaces exist afterwards
+            keep = (self.att, self.cnn)
+            self.att, self.cnn = self.att.clone(), self.cnn.clone()
+            self._steady_step()
+            self.att, self.cnn = keep
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            self._out, self._tok = self._steady_step()
+        self._graph = g
+        cur.wait_stream(st)
+
+    @torch.no_grad()
+    def step(self, xs: torch.Tensor):
+        """Consume the next chunk of every stream: xs (B, 8 (c - 1) + 15, feat).  Returns (out (B, c, d), tokens (B, c) or None);
+        both are overwritten by the next call."""
+        if tuple(xs.shape) != (self.B, self.T, self.enc.geo.feat_dim):
+            raise ValueError(f"StreamingGraph.step expects xs of shape {(self.B, self.T, self.enc.geo.feat_dim)}")
+        if self.offset < self.l:
+            # left context still filling: the plan masks the missing part, so these steps differ from one another
+            out, _, self.att, self.cnn = self.enc.forward_chunk(xs, self.att, self.cnn, self.c, self.l, 0, self.offset,
+                                                                donate_caches=True)
+            self.offset += self.c
+            return out, (self.enc.ctc_greedy(out) if self.with_ctc else None)
+        if self._graph is None:
+            self._capture()
+        self.x_in.copy_(xs, non_blocking=True)
+        self._graph.replay()
+        self.offset += self.c
+        return self._out, self._tok
+

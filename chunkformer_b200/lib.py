@@ -45,6 +45,7 @@ SIGNATURES = {
     "cf_plan_masks": (c_int, [c_void_p, POINTER(c_uint8), POINTER(c_uint8)]),
     "cf_plan_chunk_table": (c_int, [c_void_p, POINTER(c_int32)]),
     "cf_workspace_bytes": (c_size_t, [c_void_p, c_void_p]),
+    "cf_plan_pin": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cf_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                           c_size_t, c_void_p]),
     "cf_encode_streams": (c_int, [c_void_p, c_int, c_int, c_int]),

@@ -133,6 +133,11 @@ CF_API int cf_plan_chunk_table(const cf_plan* p, int32_t* table);
 
 /* ---- encoder ----------------------------------------------------------------------------------------------------- */
 CF_API size_t cf_workspace_bytes(const cf_handle* h, const cf_plan* p);
+/* Copy the plan's per-chunk tables into `workspace` once (synchronous).  cf_encode calls with this plan and this workspace then
+ * issue no operation that depends on host memory (no table staging), so a steady-state call - e.g. the streaming step of
+ * forward_chunk (encoder.py:310-390) once every stream's left context is filled, where the plan no longer changes - can be
+ * captured in a CUDA graph and replayed.  No other plan may use the workspace in between; workspace = NULL unpins. */
+CF_API int cf_plan_pin(cf_handle* h, cf_plan* p, void* workspace, size_t workspace_bytes, void* stream);
 /* Replaces: ChunkFormerEncoder.forward_parallel_chunk / forward_encoder from CMVN to after_norm
  * (encoder.py:615-671; encoder_layer.py:155-248; attention.py:420-505; convolution.py:194-255; subsampling.py:120-175).
  *   feats          device, fp32, flat [rows, feat_dim] (all utterances; see feat_row_offsets of the plan)

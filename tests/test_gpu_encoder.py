@@ -447,6 +447,30 @@ def test_forward_chunk_many_streams_equals_single_stream_calls():
     assert torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("c,l,B", [(8, 40, 3), (16, 64, 5), (4, 12, 1)])
+def test_streaming_graph_equals_forward_chunk(c, l, B):
+    """StreamingGraph (first steps through forward_chunk, then one captured CUDA graph replayed per step, plan tables pinned
+    in a private workspace with cf_plan_pin) gives exactly what step-by-step forward_chunk + ctc_greedy gives: same kernels,
+    same order, same buffers.  Also after reset() (new streams on the captured graph) and with host input."""
+    from chunkformer_b200.encoder import StreamingGraph
+    _, enc = _model(SMALL, 5)
+    size = 8 * (c - 1) + 15
+    gen = torch.Generator().manual_seed(23)
+    sg = StreamingGraph(enc, B, c, l)
+    for rnd in range(2):
+        att, cnn = torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))
+        for step in range(l // c + 6):
+            x = torch.randn((B, size, 80), generator=gen)
+            want, _, att, cnn = enc.forward_chunk(x.to(DEV), att, cnn, c, l, 0, offset=step * c)
+            want_tok = enc.ctc_greedy(want)
+            out, tok = sg.step(x if step % 2 else x.to(DEV))
+            assert torch.equal(out, want), (rnd, step, float((out - want).abs().max()))
+            assert torch.equal(tok, want_tok), (rnd, step)
+        assert torch.equal(sg.att, att) and torch.equal(sg.cnn, cnn)
+        sg.reset()
+    assert sg._graph is not None
+
+
 def test_cf_encode_streams_rejects_inconsistent_plans():
     """The multi-stream mode is armed per call and checked against the plan: wrong stream count, wrong chunks per stream,
     missing caches and a right context are refused with a message; a refused call disarms the mode."""

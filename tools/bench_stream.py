@@ -4,7 +4,7 @@ concurrent streams and the number of real-time streams one GPU sustains (a step 
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from chunkformer_b200.encoder import ChunkFormerEncoderB200
+from chunkformer_b200.encoder import ChunkFormerEncoderB200, StreamingGraph
 from chunkformer_b200.geometry import CTC_LARGE, CTC_SMALL
 from chunkformer_b200.synth import synth_state_dict
 
@@ -22,5 +22,16 @@ for name, geo in (("ctc-small (d256 H4 L12)", CTC_SMALL), ("ctc-large (d512 H8 L
                 o, _, att, cnn = enc.forward_chunk(x, att, cnn, c, l, 0, offset=(3 + s) * c, donate_caches=True)
                 tok = enc.ctc_greedy(o).cpu()
             torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n
+            # the same steady-state step as one captured CUDA graph (StreamingGraph)
+            sg = StreamingGraph(enc, B, c, l)
+            for s in range(l // c + 3):
+                sg.step(x)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for s in range(n):
+                o, tok = sg.step(x)
+                tok = tok.cpu()
+            torch.cuda.synchronize(); dg = (time.perf_counter() - t0) / n
             print(f"{name} chunk {c} left {l}: B={B:3d} {dt * 1e3:7.2f} ms per step ({dt * 1e3 / B:5.2f} per stream) "
-                  f"-> {int(c * 0.08 / (dt / B))} real-time streams per GPU")
+                  f"-> {int(c * 0.08 / (dt / B))} real-time streams per GPU;  CUDA graph {dg * 1e3:7.2f} ms per step "
+                  f"-> {int(c * 0.08 / (dg / B))} streams", flush=True)
+            del sg
