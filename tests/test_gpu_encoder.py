@@ -217,6 +217,39 @@ def test_full_size_masked_batch_properties():
         _compare(a, ref.reshape(-1, 512)[:m], f"utterance {u} inside the 14 400 s batch vs oracle")
 
 
+def test_full_size_encode_is_bitwise_reproducible():
+    """The whole path is deterministic (no atomics on floating-point data, fixed merge order of the LayerNorm partials in both
+    CTAs of a pair): the 14 400 s batch encoded four times gives bit-identical outputs and tokens.  A missing fence or barrier in
+    the cross-warp / cross-CTA hand-offs (st.async statistics, relaxed credits, TMEM accumulator hand-off of the CTA-pair GEMM)
+    shows up here as a run that differs."""
+    from chunkformer_b200.synth import masked_batch_lengths
+    _, enc = _model(LARGE, 0)
+    lens = masked_batch_lengths()
+    feats = torch.cat([synth_fbank(t, seed=1 + k) for k, t in enumerate(lens)], 0).to(DEV)
+    from chunkformer_b200.plan import Plan
+    first = None
+    for rep in range(4):
+        plan = Plan(64, 128, 128, lens, None, LARGE.kernel)
+        out, out16 = enc.encode_plan(plan, feats, want_bf16=True)
+        tok = enc.ctc_greedy(out)
+        if first is None:
+            first = (out.clone(), out16.clone(), tok.clone())
+        else:
+            assert torch.equal(out, first[0]) and torch.equal(out16, first[1]) and torch.equal(tok, first[2]), rep
+    for name, val in (("ln_split", 2), ("ln_split", 0), ("gemm_pair", 0)):       # the other kernel variants, twice each
+        enc.set_option(name, val)
+        try:
+            runs = []
+            for rep in range(2):
+                plan = Plan(64, 128, 128, lens, None, LARGE.kernel)
+                out, _ = enc.encode_plan(plan, feats)
+                runs.append(out.clone())
+            assert torch.equal(runs[0], runs[1]), (name, val)
+            assert float((runs[0] - first[0]).abs().max()) < 5e-2
+        finally:
+            enc.set_option(name, -1)
+
+
 @pytest.mark.parametrize("option,on,default", [("fused_layernorm", 1, 1), ("fused_ffn", 1, 0), ("ffn_slab_rows", 256, 0),
                                                ("ln_split", 1, -1), ("ln_split", 2, -1), ("gemm_pair", 1, -1)])
 @pytest.mark.parametrize("geo,seed", [(SMALL, 11), (RNNT_LARGE, 7)])
