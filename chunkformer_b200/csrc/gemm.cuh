@@ -31,6 +31,11 @@ struct GemmEpiParams {
   const int2* row_range = nullptr;  // EPI_F32: row valid iff range[row / rows_per_chunk].x <= row % rows_per_chunk < .y
   int rows_per_chunk = 1;
   int resid_tma = 0;             // EPI_F32: residual sub-tiles are TMA-loaded into the staging tiles (set by launch_gemm)
+  // bf16 / GLU outputs are stored through a 3-D tensor map {columns, rows, groups}.  Plain output: one group, scatter_rows = 0.
+  // Scattered output (compact streaming, api.cu): accumulator row m belongs to group m / scatter_rows and lands on row
+  // scatter_row0 + m % scatter_rows of that group (scatter_rows divides 128); a 128-row tile is then 128 / scatter_rows boxes
+  // of scatter_rows rows in one store.
+  int scatter_rows = 0, scatter_row0 = 0;
 #ifdef CF_ABLATION
   int debug = 0;                 // ablation builds only (tools/, -DCF_ABLATION): 1 = epilogue does nothing, 2 = no loads / MMAs,
                                  // 4 = bf16 epilogue computes but neither stages nor stores, 8 = bf16 epilogue stores straight from registers,
@@ -85,6 +90,11 @@ CF_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0,
 CF_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+CF_DEVINL void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 CF_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -359,7 +369,9 @@ CF_DEVINL void gemm_epilogue_slab(uint32_t taddr, int row0, int trow, int gcol0,
       named_bar_sync(bar_id, 128);
       if (issuer && !CF_DBG(ep, 32)) {
         const int ocol = (EPI == EPI_GLU) ? (gcol0 >> 1) : acol0;
-        tma_store_2d(tma_c, stg, ocol, CF_DBG(ep, 16) ? 0 : row0);   // debug 16: every tile lands on the first 128 rows (L2 only)
+        const int srow0 = CF_DBG(ep, 16) ? 0 : row0;   // debug 16: every tile lands on the first 128 rows (L2 only)
+        if (ep.scatter_rows > 0) tma_store_3d(tma_c, stg, ocol, ep.scatter_row0, srow0 / ep.scatter_rows);
+        else tma_store_3d(tma_c, stg, ocol, srow0, 0);
         tma_store_commit();
       }
     }

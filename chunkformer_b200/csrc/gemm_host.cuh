@@ -59,6 +59,26 @@ inline bool make_tma_2d(CUtensorMap* map, const void* ptr, bool is_f32, uint64_t
   }
   return true;
 }
+// 3-D tiled map {cols, rows, groups} of a row-major bf16 buffer: row pitch `ld` elements, group pitch `group_ld` elements.
+// groups = 1, box_groups = 1 is the 2-D case behind a 3-D instruction; otherwise a box of box_rows x box_groups rows gathers /
+// scatters the same rows of consecutive groups (128B swizzle, shared-memory image = box_groups x box_rows rows of 128 bytes).
+inline bool make_tma_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint64_t groups, uint64_t ld,
+                             uint64_t group_ld, uint32_t box_cols, uint32_t box_rows, uint32_t box_groups, std::string* err) {
+  auto enc = get_tensor_map_encoder(err);
+  if (!enc) return false;
+  cuuint64_t dims[3] = {cols, rows, groups};
+  cuuint64_t strides[2] = {ld * 2, group_ld * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, box_groups};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string(int(r));
+    return false;
+  }
+  return true;
+}
 inline bool make_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                              uint32_t box_rows, uint32_t box_cols, std::string* err) {
   return make_tma_2d(map, ptr, false, rows, cols, ld, box_rows, box_cols, err);
@@ -74,6 +94,8 @@ struct GemmLaunch {
   void* out; long long ldo;      // bf16 [M, N] (EPI_BF16), bf16 [M, N/2] (EPI_GLU), fp32 [M, N] (EPI_F32); unused for EPI_ARGMAX
   GemmEpiParams ep;
   int variant = -1;              // -1 = by problem size, 0 = 1-CTA kernel, 1 = 2-CTA (cta_group::2) kernel
+  // bf16 / GLU output scattered by row groups (GemmEpiParams::scatter_rows): `out` = row 0 of group 0, group pitch in elements
+  int scatter_rows = 0, scatter_row0 = 0, scatter_group_rows = 0; long long scatter_groups = 0;
   KernelTiming* timing = nullptr;  // optional per-handle event timing of one kernel family (bench.py roofline)
   int family = 0;                // kernel family tag recorded with the timing (cf_kernel_family in the public header)
 };
@@ -145,7 +167,18 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
       if (err) *err = "gemm: output pointer missing or leading dimension not 16-byte aligned";
       return false;
     }
-    if (!make_tma_2d(&tc, g.out, f32, g.M, ocols, g.ldo, GEMM_BM, f32 ? 32 : 64, err)) return false;
+    if (f32) {
+      if (!make_tma_2d(&tc, g.out, true, g.M, ocols, g.ldo, GEMM_BM, 32, err)) return false;
+    } else if (g.scatter_rows > 0) {     // 128 accumulator rows = 128 / scatter_rows groups x scatter_rows rows
+      if (GEMM_BM % g.scatter_rows != 0) { if (err) *err = "gemm: scatter_rows must divide 128"; return false; }
+      if (!make_tma_3d_bf16(&tc, g.out, ocols, uint64_t(g.scatter_group_rows), uint64_t(g.scatter_groups), uint64_t(g.ldo),
+                            uint64_t(g.scatter_group_rows) * uint64_t(g.ldo), 64, uint32_t(g.scatter_rows),
+                            uint32_t(GEMM_BM / g.scatter_rows), err)) return false;
+      ep.scatter_rows = g.scatter_rows; ep.scatter_row0 = g.scatter_row0;
+    } else {
+      if (!make_tma_3d_bf16(&tc, g.out, ocols, uint64_t(g.M), 1, uint64_t(g.ldo), uint64_t(g.M) * uint64_t(g.ldo), 64, GEMM_BM, 1, err))
+        return false;
+    }
   }
   tr = tc;
   ep.resid_tma = 0;
@@ -236,6 +269,8 @@ struct GemmLnLaunch {
   void* y_out; long long ldy;         // bf16 [M, N] (LNM_FINAL: nullable)
   const int* row_limit; int rows_per_seq;
   KernelTiming* timing = nullptr; int family = 0;
+  // A gathered by row groups (GemmLnParams::gather_rows; split / quad kernels only): A = row 0 of group 0
+  int gather_rows = 0, gather_row0 = 0, gather_group_rows = 0; long long gather_groups = 0;
   int variant = -1;                   // 1: gemm_ln_split_kernel (normalisation passes on their own warps); 0: gemm_ln_kernel;
                                       // 2: gemm_ln_quad_kernel (cluster of four, cta_group::2 MMAs); -1: default (1)
 #ifdef CF_ABLATION
@@ -269,6 +304,16 @@ inline bool launch_gemm_ln_nc(const GemmLnLaunch& g, int num_sms, cudaStream_t s
   // Default: the pair kernel.  The cluster of four is 9 % / 6 % faster alone at K = 2048 (0.430 -> 0.391 ms, 0.443 -> 0.417 with
   // two LayerNorms) but leaves 16 SMs idle, and inside the power-capped step the two are equal (67.9-68.6 vs 66.8-69.0 ms).
   const int variant = g.variant < 0 ? 1 : g.variant;
+  if (variant != 0) {      // split / quad kernels read A through a 3-D map (see GemmLnParams::gather_rows)
+    if (g.gather_rows > 0) {
+      if (GEMM_BM % g.gather_rows != 0) { if (err) *err = "gemm_ln: gather_rows must divide 128"; return false; }
+      if (!make_tma_3d_bf16(&ta, g.A, uint64_t(g.K), uint64_t(g.gather_group_rows), uint64_t(g.gather_groups), uint64_t(g.lda),
+                            uint64_t(g.gather_group_rows) * uint64_t(g.lda), GEMM_BK, uint32_t(g.gather_rows),
+                            uint32_t(GEMM_BM / g.gather_rows), err)) return false;
+      ep.gather_rows = g.gather_rows; ep.gather_row0 = g.gather_row0;
+    } else if (!make_tma_3d_bf16(&ta, g.A, uint64_t(g.K), uint64_t(g.M), 1, uint64_t(g.lda), uint64_t(g.M) * uint64_t(g.lda), GEMM_BK,
+                                 GEMM_BM, 1, err)) return false;
+  } else if (g.gather_rows > 0) { if (err) *err = "gemm_ln: the first-version kernel cannot gather A"; return false; }
   if (variant == 2) {
     // cluster of four (two cta_group::2 pairs per 256-row block); the number of co-resident clusters is asked of the driver
     // (33 on a B200: GPC sizes) and the kernel is persistent over that many

@@ -38,6 +38,10 @@ struct GemmLnParams {
   const int* row_limit = nullptr;      // LNM_Y: rows with (row % rows_per_seq) >= limit[row / rows_per_seq] give y = 0
   int rows_per_seq = 1;
   int store_f32 = 1, store_bf16 = 1;   // LNM_FINAL: which outputs exist
+  // gemm_ln_split_kernel / gemm_ln_quad_kernel read A through a 3-D tensor map {K, rows, groups}.  Plain A: one group,
+  // gather_rows = 0.  Gathered A (compact streaming, api.cu): row m of the GEMM is row gather_row0 + m % gather_rows of group
+  // m / gather_rows (gather_rows divides 128).
+  int gather_rows = 0, gather_row0 = 0;
 #ifdef CF_ABLATION
   long long* prof = nullptr;           // tools build: [grid][16] cycles per role spent waiting / working (gemm_ln_split_kernel)
   int debug = 0;                       // tools build: phase ablation bits (gemm_ln_split_kernel; results are wrong)
@@ -560,6 +564,13 @@ CF_DEVINL void umma_commit_2sm_mask(uint64_t* bar, uint16_t mask) {   // arrive 
                : "memory");
 }
 
+CF_DEVINL void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 CF_DEVINL void st_global_v8(void* p, const uint32_t (&o)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
                "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
@@ -651,11 +662,15 @@ CF_DEVINL void gemm_ln_split_body(const CUtensorMap& tma_a, const CUtensorMap& t
           if (QUAD) {                                  // completion of both CTAs' loads lands on the leader's barrier
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
             const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), lead);
-            tma_load_2d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, m_blk * BMC + row_off);
+            const int arow = m_blk * BMC + row_off;
+            if (ep.gather_rows > 0) tma_load_3d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, ep.gather_row0, arow / ep.gather_rows);
+            else tma_load_3d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, arow, 0);
             tma_load_2d_2sm(sB + stage * B_BYTES, &tma_b, fb, kb * GEMM_BK, int(rank) * NC + int(half) * (NC / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
-            tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            if (ep.gather_rows > 0)
+              tma_load_3d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, ep.gather_row0, m_blk * GEMM_BM / ep.gather_rows);
+            else tma_load_3d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM, 0);
             tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, int(rank) * NC);
           }
         }
