@@ -75,6 +75,8 @@ struct cf_handle {
   int opt_fused_layernorm = 1;   // LayerNorms fused into the epilogue of the residual GEMM in front of them (gemm_ln.cuh)
   int opt_ln_split = -1;         // ... 1: normalisation passes on their own warps (gemm_ln_split_kernel), 2: + cluster of four with
                                  // cta_group::2 MMAs (gemm_ln_quad_kernel), -1: default (1), 0: gemm_ln_kernel
+  int opt_stream_compact = 1;    // multi-stream steps: row-wise kernels on the real chunk of every stream only
+  long long last_out_rows = 0;   // rows of `out` the last cf_encode call wrote
   int opt_gemm_pair = -1;        // plain GEMMs: -1 = by shape (gemm_host.cuh), 0 = 1-CTA kernel, 1 = CTA-pair (cta_group::2) kernel
   int opt_ffn_slab_rows = 0;     // > 0: the two FFN GEMMs run slab by slab of this many rows, the hidden activation of a slab
                                  // (rows x F bf16) is produced and consumed while it is still in L2
@@ -123,6 +125,7 @@ extern "C" int cf_set_option(cf_handle* h, const char* name, int value) {
   const std::string k(name);
   if (k == "fused_layernorm") { h->opt_fused_layernorm = value != 0; return CF_OK; }
   if (k == "ln_split") { h->opt_ln_split = value < 0 ? -1 : (value > 2 ? 2 : value); return CF_OK; }
+  if (k == "stream_compact") { h->opt_stream_compact = value != 0; return CF_OK; }
   if (k == "gemm_pair") { h->opt_gemm_pair = value < 0 ? -1 : (value != 0); return CF_OK; }
   if (k == "fused_ffn") { h->opt_fused_ffn = value != 0; return CF_OK; }
   if (k == "ffn_slab_rows") { h->opt_ffn_slab_rows = value > 0 ? ((value + 127) / 128) * 128 : 0; return CF_OK; }
@@ -625,6 +628,8 @@ constexpr int FE_SLAB_CHUNKS = 256;
 
 struct EncodeWs {
   ChunkSrc* chunk_src; int2 *att_range, *conv_range, *out_range; int* seq_limit;
+  ChunkSrc* chunk_src_last; int2* out_range_last;      // per utterance: the entries of its LAST chunk (compact streaming)
+  size_t table_bytes;                                  // the table region = [chunk_src, chunk_src + table_bytes)
   float* x; bf16 *y, *hbuf, *qkv, *ctx, *g, *z, *a1, *b1, *a2, *b2;
   size_t qkv_rows, g_rows;
   size_t total;
@@ -642,6 +647,9 @@ EncodeWs carve_encode(const cf_handle* h, const cf_plan* p, void* base) {
   w.conv_range = cv.take<int2>(n);
   w.out_range = cv.take<int2>(n);
   w.seq_limit = cv.take<int>(size_t(p->B));
+  w.chunk_src_last = cv.take<ChunkSrc>(size_t(p->B));
+  w.out_range_last = cv.take<int2>(size_t(p->B));
+  w.table_bytes = (cv.off + 15) & ~size_t(15);
   w.x = cv.take<float>(Mr * d);
   w.y = cv.take<bf16>(Mr * d);
   w.hbuf = cv.take<bf16>(Mr * F);
@@ -663,8 +671,8 @@ EncodeWs carve_encode(const cf_handle* h, const cf_plan* p, void* base) {
 // ranges, per-sequence row limits): built on the host, then pulled into the workspace (cf_encode) or copied there once
 // (cf_plan_pin).
 static size_t table_image_bytes(const cf_plan* p, const EncodeWs& w) {
-  const size_t o_sl = reinterpret_cast<const uint8_t*>(w.seq_limit) - reinterpret_cast<const uint8_t*>(w.chunk_src);
-  return ((o_sl + size_t(p->B) * sizeof(int)) + 15) & ~size_t(15);
+  (void)p;
+  return w.table_bytes;                 // chunk_src is the first piece of the workspace
 }
 static void fill_table_image(const cf_plan* p, const EncodeWs& w, uint8_t* base, size_t need) {
   const uint8_t* dev0 = reinterpret_cast<const uint8_t*>(w.chunk_src);
@@ -682,6 +690,14 @@ static void fill_table_image(const cf_plan* p, const EncodeWs& w, uint8_t* base,
   }
   // (the 16 phantom chunks behind the last attention tile stay empty: zeroed above)
   if (p->mode == 1) memcpy(base + o_sl, p->seq_valid_rows.data(), size_t(p->B) * sizeof(int));
+  // per utterance, the entries of its last chunk: the chunk list of the row-wise kernels in compact streaming
+  ChunkSrc* csl = reinterpret_cast<ChunkSrc*>(base + (reinterpret_cast<const uint8_t*>(w.chunk_src_last) - dev0));
+  int2* orl = reinterpret_cast<int2*>(base + (reinterpret_cast<const uint8_t*>(w.out_range_last) - dev0));
+  int g_end = 0;
+  for (int u = 0; u < p->B; ++u) {
+    g_end += p->n_chunks[u];
+    if (p->n_chunks[u] > 0) { csl[u] = cs[g_end - 1]; orl[u] = orr[g_end - 1]; }
+  }
 }
 
 // Projected relative-position tables P_l = linear_pos_l(PE) for all layers (embedding.py:119-174, attention.py:482):
@@ -784,6 +800,8 @@ extern "C" int cf_encode_streams(cf_handle* h, int n_streams, int placeholder_ch
   return CF_OK;
 }
 
+extern "C" int64_t cf_encode_output_rows(const cf_handle* h) { return h ? int64_t(h->last_out_rows) : 0; }
+
 extern "C" int cf_encode_feature_events(cf_handle* h, int n, const int64_t* rows_ready, void* const* events) {
   if (!h || n < 0 || (n > 0 && (!rows_ready || !events))) return fail(h, CF_ERR_INVALID, "cf_encode_feature_events: bad argument");
   h->ev_rows.assign(rows_ready, rows_ready + n);
@@ -829,7 +847,19 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   const int c = p->c, l = p->l, r = p->r, lo = p->lorder;
   const int n = p->n;
   const long long Mr = (long long)n * c;
+  h->last_out_rows = Mr;
   if (Mr == 0) return CF_OK;
+  // Compact streaming: a stream is `ph` placeholder chunks (whose only purpose is to hold the left-context K / V and conv rows
+  // in front of the real chunk in the flat QKV / GLU buffers) + its real chunk.  Every row-wise kernel (front-end, GEMMs,
+  // LayerNorms) then works on the ns x c real rows only: the QKV / GLU GEMMs scatter their output into the per-stream layout and
+  // the GEMMs behind attention / the conv core gather their A operand from it (3-D tensor maps); attention and the conv core still
+  // walk every chunk.  `out` receives ns x c rows, stream after stream.
+  const bool compact = ns > 0 && adv == c && h->opt_stream_compact != 0 && h->opt_fused_layernorm != 0 && h->opt_ln_split != 0 &&
+                       h->opt_fused_ffn == 0 && (128 % c) == 0 && ev.empty();
+  const long long Mrow = compact ? (long long)ns * c : Mr;      // rows of the row-wise kernels
+  const int n_row = compact ? ns : n;                           // their chunks
+  const int grp_rows = (ph + 1) * c;                            // compact: rows of a stream's block in the QKV / GLU / ctx / z buffers
+  h->last_out_rows = Mrow;
   if (att_cache && trunc < 0) return fail(h, CF_ERR_INVALID, "cf_encode: truncated_context_size must be >= 0");
   if (!ev_rows.empty()) {
     long long need_all = 0;
@@ -877,16 +907,25 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     CF_CUDA(h, cudaEventRecord(sg.done, st));
     sg.in_flight = true;
   }
-  // zero the halo rows of the flat buffers once (cache rows are rewritten per layer when streaming)
-  launch_zero(w.qkv, size_t(l) * 4 * d * sizeof(bf16));
-  launch_zero(w.qkv + (size_t(l) + Mr) * 4 * d, (w.qkv_rows - size_t(l) - Mr) * 4 * d * sizeof(bf16));
-  launch_zero(w.g, size_t(lo) * d * sizeof(bf16));
-  launch_zero(w.g + (size_t(lo) + Mr) * d, (w.g_rows - size_t(lo) - Mr) * d * sizeof(bf16));
+  // zero the halo rows of the flat buffers once (cache rows are rewritten per layer when streaming); compact streaming: the
+  // placeholder rows are never written by a GEMM, so the whole buffers are cleared (their Q columns and the rows outside the
+  // cached context must be finite)
+  if (compact) {
+    launch_zero(w.qkv, w.qkv_rows * 4 * d * sizeof(bf16));
+    launch_zero(w.g, w.g_rows * d * sizeof(bf16));
+  } else {
+    launch_zero(w.qkv, size_t(l) * 4 * d * sizeof(bf16));
+    launch_zero(w.qkv + (size_t(l) + Mr) * 4 * d, (w.qkv_rows - size_t(l) - Mr) * 4 * d * sizeof(bf16));
+    launch_zero(w.g, size_t(lo) * d * sizeof(bf16));
+    launch_zero(w.g + (size_t(lo) + Mr) * d, (w.g_rows - size_t(lo) - Mr) * d * sizeof(bf16));
+  }
   CF_CUDA(h, cudaGetLastError());
 
   struct EpiArgs { const float* bias = nullptr; void* out = nullptr; long long ldo = 0; int act = ACT_NONE;
                    const float* resid = nullptr; long long ld_resid = 0; float alpha = 1.0f;
-                   const int2* row_range = nullptr; int rows_per_chunk = 1; int family = 0; };
+                   const int2* row_range = nullptr; int rows_per_chunk = 1; int family = 0;
+                   bool scatter = false;      // compact streaming: bf16 / GLU output rows go to the real chunk of every stream
+                   bool gather = false; };    // compact streaming: the A operand is the real chunk of every stream
   auto gemm = [&](const void* A, long long lda, const void* B, long long ldb, long long M, int N, int K, int epi,
                   const EpiArgs& e) -> bool {
     GemmLaunch g{};
@@ -895,6 +934,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.ep.bias = e.bias; g.ep.resid = e.resid; g.ep.ld_resid = e.ld_resid; g.ep.alpha = e.alpha;
     g.ep.row_range = e.row_range; g.ep.rows_per_chunk = e.rows_per_chunk;
     g.timing = &h->timing; g.family = e.family; g.variant = h->opt_gemm_pair;
+    if (e.scatter) { g.scatter_rows = c; g.scatter_row0 = ph * c; g.scatter_group_rows = grp_rows; g.scatter_groups = ns; }
     return launch_gemm(g, h->num_sms, st, &err);
   };
   // residual GEMM + the LayerNorm(s) that follow it, one kernel (gemm_ln.cuh)
@@ -908,6 +948,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     g.ln1_w = q.w1; g.ln1_b = q.b1; g.ln2_w = q.w2; g.ln2_b = q.b2; g.x_out = q.x_out; g.ldx = d; g.y_out = q.y_out; g.ldy = d;
     g.row_limit = q.limit ? w.seq_limit : nullptr; g.rows_per_seq = q.limit ? p->rows_per_seq : 1;
     g.timing = &h->timing; g.family = e.family; g.variant = h->opt_ln_split;
+    if (e.gather) { g.gather_rows = c; g.gather_row0 = ph * c; g.gather_group_rows = grp_rows; g.gather_groups = ns; }
     return launch_gemm_ln(g, h->num_sms, st, &err);
   };
   const bool fuse_ln = h->opt_fused_layernorm != 0;
@@ -915,7 +956,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   // whole feed-forward module: x <- x + 0.5 * (W2 SiLU(W1 y + b1) + b2) followed by the LayerNorm(s) of `q`
   auto ffn = [&](const bf16* w1, const float* b1, const bf16* w2, const float* b2, const LnArgs& q) -> bool {
     FfnLaunch g{};
-    g.Y = w.y; g.ldy_in = d; g.W1 = w1; g.b1 = b1; g.W2 = w2; g.b2 = b2; g.M = int(Mr); g.d = d; g.F = F; g.resid = w.x;
+    g.Y = w.y; g.ldy_in = d; g.W1 = w1; g.b1 = b1; g.W2 = w2; g.b2 = b2; g.M = int(Mrow); g.d = d; g.F = F; g.resid = w.x;
     g.ld_resid = d; g.alpha = 0.5f; g.mode = q.mode; g.ln1_w = q.w1; g.ln1_b = q.b1; g.ln2_w = q.w2; g.ln2_b = q.b2;
     g.x_out = q.x_out; g.ldx = d; g.y_out = q.y_out; g.ldy = d;
     g.timing = &h->timing; g.family = CF_FAMILY_FFN_FUSED;
@@ -924,9 +965,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   // feed-forward module as two GEMMs (w_1 + SiLU -> hidden activation in global memory -> w_2 + residual + LayerNorm(s)),
   // optionally slab by slab so that a slab's hidden activation never has to leave L2
   auto ffn_two = [&](const bf16* w1, const float* b1, const bf16* w2, const float* b2, const LnArgs& q0) -> bool {
-    const long long slab = h->opt_ffn_slab_rows > 0 ? h->opt_ffn_slab_rows : Mr;
-    for (long long r0 = 0; r0 < Mr; r0 += slab) {
-      const long long rows = std::min(slab, Mr - r0);
+    const long long slab = h->opt_ffn_slab_rows > 0 ? h->opt_ffn_slab_rows : Mrow;
+    for (long long r0 = 0; r0 < Mrow; r0 += slab) {
+      const long long rows = std::min(slab, Mrow - r0);
       EpiArgs e1; e1.bias = b1; e1.out = w.hbuf; e1.ldo = F; e1.act = ACT_SILU; e1.family = CF_FAMILY_FFN_W1;
       if (!gemm(w.y + r0 * d, d, w1, d, rows, F, d, EPI_BF16, e1)) return false;
       EpiArgs e2; e2.bias = b2; e2.resid = w.x + r0 * d; e2.ld_resid = d; e2.alpha = 0.5f; e2.family = CF_FAMILY_FFN_W2;
@@ -944,8 +985,9 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     const int T2 = 2 * c + 1, F1 = (h->cfg.feat_dim - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1, F3 = h->F3;
     if (F2 < 16) return fail(h, CF_ERR_INVALID, "cf_encode: feat_dim too small for the front-end tiling");
     size_t ev_next = 0;
-    for (int g0 = 0; g0 < n; g0 += FE_SLAB_CHUNKS) {
-      const int S = std::min(FE_SLAB_CHUNKS, n - g0);
+    const ChunkSrc* src_tab = compact ? w.chunk_src_last : w.chunk_src;
+    for (int g0 = 0; g0 < n_row; g0 += FE_SLAB_CHUNKS) {
+      const int S = std::min(FE_SLAB_CHUNKS, n_row - g0);
       if (!ev.empty()) {
         // features may still be arriving on another stream: wait only for the rows this slab reads
         long long need = 0;
@@ -956,7 +998,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
         }
       }
       Fe1Params f1{};
-      f1.feats = feats; f1.chunks = w.chunk_src + g0; f1.wpack = h->fe_wpack; f1.cmvn_mean = h->cmvn_mean; f1.cmvn_istd = h->cmvn_istd;
+      f1.feats = feats; f1.chunks = src_tab + g0; f1.wpack = h->fe_wpack; f1.cmvn_mean = h->cmvn_mean; f1.cmvn_istd = h->cmvn_istd;
       f1.out = w.a1; f1.n_chunks = S; f1.feat_dim = h->cfg.feat_dim; f1.T2 = T2; f1.F2 = F2; f1.in_rows = p->in_rows;
       if (!run_frontend_conv(h->cfg.feat_dim == 80 ? 2 : 0, d, f1, h->num_sms, st, &err)) return fail(h, CF_ERR_CUDA, "cf_encode: " + err);
       EpiArgs e1; e1.bias = h->fe_b3; e1.out = w.b1; e1.ldo = d; e1.act = ACT_RELU;
@@ -989,7 +1031,7 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
   auto ln = [&](int mode, const float* w1, const float* b1, const float* w2, const float* b2, float* xo, bf16* y,
                 bool limit) -> bool {
     LnParams q{};
-    q.x_in = w.x; q.x_out = xo; q.y = y; q.w1 = w1; q.b1 = b1; q.w2 = w2; q.b2 = b2; q.rows = Mr;
+    q.x_in = w.x; q.x_out = xo; q.y = y; q.w1 = w1; q.b1 = b1; q.w2 = w2; q.b2 = b2; q.rows = Mrow;
     q.row_limit = limit ? w.seq_limit : nullptr; q.rows_per_seq = limit ? p->rows_per_seq : 1;
     return run_layernorm(mode, d, q, st, &err);
   };
@@ -1004,12 +1046,12 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       else CF_TRY(ffn_two(lw.ffm_w1, lw.ffm_b1, lw.ffm_w2, lw.ffm_b2, q));
     } else {
     { EpiArgs e; e.bias = lw.ffm_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
-      CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mr, F, d, EPI_BF16, e)); }
+      CF_TRY(gemm(w.y, d, lw.ffm_w1, d, Mrow, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ffm_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
       if (fuse_ln) {
         LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_mha_w; q.b1 = lw.ln_mha_b; q.x_out = w.x; q.y_out = w.y;
-        CF_TRY(gemm_ln(w.hbuf, F, lw.ffm_w2, F, Mr, F, e, q));
-      } else CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mr, d, F, EPI_F32, e)); }
+        CF_TRY(gemm_ln(w.hbuf, F, lw.ffm_w2, F, Mrow, F, e, q));
+      } else CF_TRY(gemm(w.hbuf, F, lw.ffm_w2, F, Mrow, d, F, EPI_F32, e)); }
     }
     // self-attention
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_mha_w, lw.ln_mha_b, nullptr, nullptr, nullptr, w.y, false));
@@ -1018,8 +1060,8 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       att_cache_import_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<const float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d);
       ++cf::g_kernel_launches;
     }
-    { EpiArgs e; e.bias = lw.qkv_b; e.out = w.qkv + size_t(l) * 4 * d; e.ldo = 4 * d;
-      CF_TRY(gemm(w.y, d, lw.qkv_w, d, Mr, 4 * d, d, EPI_BF16, e)); }
+    { EpiArgs e; e.bias = lw.qkv_b; e.out = w.qkv + size_t(l) * 4 * d; e.ldo = 4 * d; e.scatter = compact;
+      CF_TRY(gemm(w.y, d, lw.qkv_w, d, Mrow, 4 * d, d, EPI_BF16, e)); }
     if (att_cache && l > 0 && ns == 0) {
       const int tot = l * H * 2 * dk;
       att_cache_export_kernel<<<(tot + 255) / 256, 256, 0, st>>>(static_cast<float*>(att_cache) + size_t(i) * tot, w.qkv, l, H, dk, d, trunc);
@@ -1028,24 +1070,25 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
     if (ns > 0 && l > 0) {   // placeholder rows <- caches, then caches <- last l rows of cache + frames, for every stream
       const long long tot = (long long)ns * l * H * 2 * dk;
       float* cl = static_cast<float*>(att_cache) + size_t(i) * tot;
-      att_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, c, l, 0);
-      att_cache_streams_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, adv, l, 1);
+      const unsigned blocks8 = unsigned((tot / 8 + 255) / 256);      // thread = 8 elements (d_k is a multiple of 8)
+      att_cache_streams_kernel<<<blocks8, 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, c, l, 0);
+      att_cache_streams_kernel<<<blocks8, 256, 0, st>>>(cl, w.qkv, ns, l, H, dk, d, (ph + 1) * c, ph * c, adv, l, 1);
       cf::g_kernel_launches += 2;
     }
     { AttnParams a{};
       a.qkv = w.qkv; a.pos = pos->dev + size_t(i) * pos->Rpad * d; a.range = w.att_range; a.ctx = w.ctx;
       a.n_chunks = n; a.c = c; a.l = l; a.r = r; a.d = d; a.heads = H; a.scale = 1.0f / sqrtf(float(dk)); a.prescaled = 1;
       CF_TRY(run_attention(use_tc ? 1 : 0, a, st, &err)); }
-    { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
+    { EpiArgs e; e.bias = lw.o_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f; e.gather = compact;
       if (fuse_ln) {
         LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_conv_w; q.b1 = lw.ln_conv_b; q.x_out = w.x; q.y_out = w.y; q.limit = p->mode == 1;
-        CF_TRY(gemm_ln(w.ctx, d, lw.o_w, d, Mr, d, e, q));
-      } else CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mr, d, d, EPI_F32, e)); }
+        CF_TRY(gemm_ln(w.ctx, d, lw.o_w, d, Mrow, d, e, q));
+      } else CF_TRY(gemm(w.ctx, d, lw.o_w, d, Mrow, d, d, EPI_F32, e)); }
     // convolution module
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_conv_w, lw.ln_conv_b, nullptr, nullptr, nullptr, w.y, p->mode == 1));
     if (cnn_cache && ns == 0) { cnn_cache_import_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo); ++cf::g_kernel_launches; }
-    { EpiArgs e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d;
-      CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mr, 2 * d, d, EPI_GLU, e)); }
+    { EpiArgs e; e.bias = lw.pw1_b; e.out = w.g + size_t(lo) * d; e.ldo = d; e.scatter = compact;
+      CF_TRY(gemm(w.y, d, lw.pw1_w, d, Mrow, 2 * d, d, EPI_GLU, e)); }
     if (cnn_cache && ns == 0) { cnn_cache_export_kernel<<<(d * lo + 255) / 256, 256, 0, st>>>(static_cast<float*>(cnn_cache) + size_t(i) * d * lo, w.g, d, lo, trunc); ++cf::g_kernel_launches; }
     if (ns > 0) {
       const long long tot = (long long)ns * d * lo;
@@ -1058,13 +1101,15 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       q.g = w.g; q.z = w.z; q.w = lw.dw_w; q.bias = lw.dw_b; q.ln_w = lw.cn_w; q.ln_b = lw.cn_b; q.range = w.conv_range; q.c = c; q.n_chunks = n;
       q.no_norm = h->cfg.conv_norm == 1;
       q.sub_chunk = adv < c ? adv : 0;     // streaming with right context: the conv is cut at the true chunk grid
-      CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, q.sub_chunk > 0 ? 0 : (long long)w.g_rows, h->num_sms)); }
+      const bool real_only = compact && c % 32 != 0;     // (the TMA kernel for chunk sizes 32 / 64 walks every chunk)
+      if (real_only) { q.n_chunks = ns; q.chunk_stride = ph + 1; q.chunk_first = ph; }
+      CF_TRY(run_dwconv(d, h->cfg.kernel, q, st, &err, (q.sub_chunk > 0 || real_only) ? 0 : (long long)w.g_rows, h->num_sms)); }
     { EpiArgs e; e.bias = lw.pw2_b; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 1.0f;
-      e.row_range = w.out_range; e.rows_per_chunk = c;
+      e.row_range = compact ? w.out_range_last : w.out_range; e.rows_per_chunk = c; e.gather = compact;
       if (fuse_ln) {
         LnArgs q; q.mode = LNM_Y; q.w1 = lw.ln_ff_w; q.b1 = lw.ln_ff_b; q.x_out = w.x; q.y_out = w.y;
-        CF_TRY(gemm_ln(w.z, d, lw.pw2_w, d, Mr, d, e, q));
-      } else CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mr, d, d, EPI_F32, e)); }
+        CF_TRY(gemm_ln(w.z, d, lw.pw2_w, d, Mrow, d, e, q));
+      } else CF_TRY(gemm(w.z, d, lw.pw2_w, d, Mrow, d, d, EPI_F32, e)); }
     // FFN
     if (!fuse_ln) CF_TRY(ln(0, lw.ln_ff_w, lw.ln_ff_b, nullptr, nullptr, nullptr, w.y, false));
     if (fuse_ln) {
@@ -1080,11 +1125,11 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
       if (fuse_ffn) CF_TRY(ffn(lw.ff_w1, lw.ff_b1, lw.ff_w2, lw.ff_b2, q));
       else CF_TRY(ffn_two(lw.ff_w1, lw.ff_b1, lw.ff_w2, lw.ff_b2, q));
       if (i + 1 == L && out_dtype == CF_BF16 && out_bf16 && out_bf16 != out)
-        CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+        CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mrow) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
       continue;
     }
     { EpiArgs e; e.bias = lw.ff_b1; e.out = w.hbuf; e.ldo = F; e.act = ACT_SILU; e.family = CF_FAMILY_FFN_W1;
-      CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mr, F, d, EPI_BF16, e)); }
+      CF_TRY(gemm(w.y, d, lw.ff_w1, d, Mrow, F, d, EPI_BF16, e)); }
     { EpiArgs e; e.bias = lw.ff_b2; e.out = w.x; e.ldo = d; e.resid = w.x; e.ld_resid = d; e.alpha = 0.5f; e.family = CF_FAMILY_FFN_W2;
       if (fuse_ln) {
         LnArgs q;
@@ -1096,24 +1141,24 @@ extern "C" int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, voi
           q.x_out = out_dtype == CF_F32 ? static_cast<float*>(out) : nullptr;
           q.y_out = out_dtype == CF_BF16 ? out : out_bf16;
         }
-        CF_TRY(gemm_ln(w.hbuf, F, lw.ff_w2, F, Mr, F, e, q));
+        CF_TRY(gemm_ln(w.hbuf, F, lw.ff_w2, F, Mrow, F, e, q));
         if (i + 1 == L && out_dtype == CF_BF16 && out_bf16 && out_bf16 != out)
-          CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+          CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mrow) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
         continue;
       }
-      CF_TRY(gemm(w.hbuf, F, lw.ff_w2, F, Mr, d, F, EPI_F32, e)); }
+      CF_TRY(gemm(w.hbuf, F, lw.ff_w2, F, Mrow, d, F, EPI_F32, e)); }
     if (i + 1 < L) {
       CF_TRY(ln(1, lw.ln_fin_w, lw.ln_fin_b, h->layers[i + 1].ln_ffm_w, h->layers[i + 1].ln_ffm_b, w.x, w.y, false));
     } else {
       // norm_final of the last layer + after_norm (encoder.py:670-671)
       LnParams q{};
-      q.x_in = w.x; q.w1 = lw.ln_fin_w; q.b1 = lw.ln_fin_b; q.w2 = h->after_w; q.b2 = h->after_b; q.rows = Mr;
+      q.x_in = w.x; q.w1 = lw.ln_fin_w; q.b1 = lw.ln_fin_b; q.w2 = h->after_w; q.b2 = h->after_b; q.rows = Mrow;
       q.x_out = out_dtype == CF_F32 ? static_cast<float*>(out) : nullptr;
       q.y = out_dtype == CF_BF16 ? static_cast<bf16*>(out) : static_cast<bf16*>(out_bf16);
       q.rows_per_seq = 1;
       CF_TRY(run_layernorm(2, d, q, st, &err));
       if (out_dtype == CF_BF16 && out_bf16 && out_bf16 != out)
-        CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mr) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+        CF_CUDA(h, cudaMemcpyAsync(out_bf16, out, size_t(Mrow) * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
     }
   }
   CF_CUDA(h, cudaGetLastError());

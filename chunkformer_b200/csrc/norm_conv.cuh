@@ -112,6 +112,8 @@ struct DwConvParams {
                         // slots left of the end of its sub-chunk of `sub_chunk` frames, q < (f / sub_chunk + 1) * sub_chunk + lorder
                         // (convolution.py:150-167 with chunk_size = sub_chunk on a sequence of chunk + right-context frames)
   int no_norm;          // 1: no LayerNorm (cnn_module_norm = batch_norm: the eval-mode affine is folded into w / bias), z = SiLU(conv)
+  int chunk_stride = 1, chunk_first = 0;   // generic kernel: work item i is chunk chunk_first + i * chunk_stride (compact streaming
+                                           // visits only the real chunk of every stream); n_chunks counts the visited chunks
 };
 
 
@@ -161,8 +163,9 @@ __global__ void __launch_bounds__(D / 2) dwconv_ln_silu_kernel(DwConvParams p) {
 
   const int tid = threadIdx.x;
   const int groups = p.c / FG;
-  const int chunk = blockIdx.x / groups;
-  const int f0 = (blockIdx.x - chunk * groups) * FG;   // first frame of this group inside the chunk
+  const int item = blockIdx.x / groups;
+  const int chunk = p.chunk_first + item * p.chunk_stride;
+  const int f0 = (blockIdx.x - item * groups) * FG;    // first frame of this group inside the chunk
   const int2 rg = p.range[chunk];
   const long long base_row = (long long)chunk * p.c + f0;  // buffer row of window slot (f0 + 0)
 

@@ -272,7 +272,10 @@ class ChunkFormerEncoderB200:
         plan = Plan(cc, l, 0, [t_tot] * B, [-(ph * cc - min(int(offset), l))] * B, self.geo.kernel)
         _lib.check(self._L.cf_encode_streams(self._h, B, ph, c), self._h, "cf_encode_streams")
         o, _ = self.encode_plan(plan, x_dev.view(B * t_tot, -1), new_att, new_cnn, 0)
-        out = o.view(B, (ph + 1) * cc, d)[:, ph * cc:].contiguous()
+        if int(self._L.cf_encode_output_rows(self._h)) == B * cc:      # compact step: only the real chunks were computed
+            out = o[:B * cc].view(B, cc, d)
+        else:
+            out = o.view(B, (ph + 1) * cc, d)[:, ph * cc:].contiguous()
         return out, torch.ones((B, 1, cc), dtype=torch.bool, device=self.device), new_att, new_cnn
 
     @torch.no_grad()
@@ -453,7 +456,10 @@ class StreamingGraph:
         self._x_dev[:, self._ph * 8 * c:] = self.x_in
         _lib.check(enc._L.cf_encode_streams(enc._h, B, self._ph, c), enc._h, "cf_encode_streams")
         o, _ = enc.encode_plan(self._plan, self._x_dev.view(B * self._t_tot, -1), self.att, self.cnn, 0, workspace=self._ws)
-        out = o.view(B, (self._ph + 1) * c, d)[:, self._ph * c:].contiguous()
+        if int(enc._L.cf_encode_output_rows(enc._h)) == B * c:           # compact step: only the real chunks were computed
+            out = o[:B * c].view(B, c, d)
+        else:
+            out = o.view(B, (self._ph + 1) * c, d)[:, self._ph * c:].contiguous()
         tok = enc.ctc_greedy(out) if self.with_ctc else None
         return out, tok
 

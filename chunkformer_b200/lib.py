@@ -49,6 +49,7 @@ SIGNATURES = {
     "cf_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                           c_size_t, c_void_p]),
     "cf_encode_streams": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "cf_encode_output_rows": (c_int64, [c_void_p]),
     "cf_ctc_workspace_bytes": (c_size_t, [c_void_p, c_int64, c_int]),
     "cf_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cf_ctc_compact_workspace_bytes": (c_size_t, [c_int64]),

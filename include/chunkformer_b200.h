@@ -65,6 +65,11 @@ CF_API const char* cf_last_error(const cf_handle* h);
 CF_API const char* cf_version(void);
 /* Number of kernels this library has launched in the process so far (bench.py reports the per-step count). */
 CF_API long long cf_launch_count(void);
+/* Rows of `out` the last cf_encode call on this handle wrote: the plan's rows, except for a multi-stream step
+ * (cf_encode_streams) in compact mode (option "stream_compact", default 1; chunk sizes that divide 128, right context 0), where
+ * every row-wise kernel works on the real chunk of every stream only and `out` holds n_streams x chunk rows, stream after
+ * stream (the placeholder rows in front of each stream's chunk exist only inside the K / V and conv buffers). */
+CF_API int64_t cf_encode_output_rows(const cf_handle* h);
 /* Optional, before cf_encode: the feature buffer is still being filled by copies on another stream.  events[i] (cudaEvent_t)
  * fires when feature rows < rows_ready[i] are in place (rows_ready ascending).  cf_encode makes its stream wait only for the
  * rows each front-end slab reads, so the host-to-device copy overlaps the front-end; the list is consumed by that call.

@@ -504,6 +504,33 @@ def test_streaming_graph_equals_forward_chunk(c, l, B):
     assert sg._graph is not None
 
 
+@pytest.mark.parametrize("geo,c,l,B", [(SMALL, 8, 40, 37), (SMALL, 16, 64, 5), (SMALL, 4, 12, 70), (RNNT_LARGE, 16, 64, 9)])
+def test_compact_streaming_equals_padded_streaming(geo, c, l, B):
+    """Multi-stream steps with the row-wise kernels on the real chunk of every stream only ("stream_compact", the default: QKV / GLU
+    outputs scattered into the per-stream K / V and conv layouts, attention / conv outputs gathered back, both through 3-D tensor
+    maps) against the same steps with every placeholder row computed: outputs and both caches, over the steps in which the left
+    context fills up and several more.  Rows never mix and every row's arithmetic is the same, so the two agree exactly."""
+    _, enc = _model(geo, 5)
+    size = 8 * (c - 1) + 15
+    gen = torch.Generator().manual_seed(29)
+    st = {1: (torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))), 0: (torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0)))}
+    try:
+        for step in range(l // c + 4):
+            x = torch.randn((B, size, 80), generator=gen).to(DEV)
+            outs = {}
+            for mode in (1, 0):
+                enc.set_option("stream_compact", mode)
+                att, cnn = st[mode]
+                o, _, att, cnn = enc.forward_chunk(x, att, cnn, c, l, 0, offset=step * c)
+                assert int(enc._L.cf_encode_output_rows(enc._h)) == (B * c if mode else B * (-(-max(l, 7) // c) + 1) * c)
+                st[mode] = (att, cnn)
+                outs[mode] = o.clone()
+            assert torch.equal(outs[1], outs[0]), (step, float((outs[1] - outs[0]).abs().max()))
+            assert torch.equal(st[1][0], st[0][0]) and torch.equal(st[1][1], st[0][1]), step
+    finally:
+        enc.set_option("stream_compact", 1)
+
+
 def test_cf_encode_streams_rejects_inconsistent_plans():
     """The multi-stream mode is armed per call and checked against the plan: wrong stream count, wrong chunks per stream,
     missing caches and a right context are refused with a message; a refused call disarms the mode."""

@@ -11,7 +11,7 @@ from chunkformer_b200.synth import synth_state_dict
 for name, geo in (("ctc-small (d256 H4 L12)", CTC_SMALL), ("ctc-large (d512 H8 L17)", CTC_LARGE)):
     enc = ChunkFormerEncoderB200(geo, synth_state_dict(geo, 0), "cuda:0")
     for (c, l) in ((8, 60), (4, 40), (16, 64)):
-        for B in (1, 32, 256):
+        for B in (1, 32, 256, 1024):
             x = torch.randn((B, 8 * (c - 1) + 15, 80), device="cuda")
             att, cnn = torch.zeros((0, 0, 0, 0, 0)), torch.zeros((0, 0, 0, 0))
             for s in range(3):
