@@ -162,7 +162,10 @@ CF_API int cf_encode(cf_handle* h, const cf_plan* p, const float* feats, void* a
  * max(left_context, 7); the placeholder input frames may be zeros; offsets[s] = -(placeholder_chunks * chunk_size -
  * min(frames already consumed, left_context)) masks the part of the cache that is not filled yet) and its caches as device fp32
  * att_cache (L, n_streams, H, left_context, 2 d_k) / cnn_cache (L, n_streams, d, 7), the layouts forward_chunk takes and
- * returns; both are updated in place.  The rows of the last chunk of every utterance are the step's output. */
+ * returns; both are updated in place.  The rows of the last chunk of every utterance are the step's output: in compact mode
+ * (the default where it applies, see cf_encode_output_rows) `out` holds exactly those rows, n_streams x chunk of them; otherwise
+ * `out` has the plan's rows and the step's output is rows [placeholder_chunks * chunk, (placeholder_chunks + 1) * chunk) of
+ * every utterance. */
 /* advance = frames every stream moves forward per step: 0 or the plan's chunk size for right_context_size = 0; with a right
  * context r the plan's chunk is chunk + r (chunk and right context are embedded and attended as ONE chunk, encoder.py:341-347),
  * advance = chunk: the caches then end where the chunk ends (encoder.py:376-385) and the conv module is cut into sub-chunks of
