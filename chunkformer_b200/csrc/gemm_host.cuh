@@ -176,8 +176,7 @@ inline bool launch_gemm_epi(const GemmLaunch& g, int num_sms, cudaStream_t strea
                             uint32_t(GEMM_BM / g.scatter_rows), err)) return false;
       ep.scatter_rows = g.scatter_rows; ep.scatter_row0 = g.scatter_row0;
     } else {
-      if (!make_tma_3d_bf16(&tc, g.out, ocols, uint64_t(g.M), 1, uint64_t(g.ldo), uint64_t(g.M) * uint64_t(g.ldo), 64, GEMM_BM, 1, err))
-        return false;
+      if (!make_tma_2d(&tc, g.out, false, g.M, ocols, g.ldo, GEMM_BM, 64, err)) return false;
     }
   }
   tr = tc;
@@ -304,15 +303,14 @@ inline bool launch_gemm_ln_nc(const GemmLnLaunch& g, int num_sms, cudaStream_t s
   // Default: the pair kernel.  The cluster of four is 9 % / 6 % faster alone at K = 2048 (0.430 -> 0.391 ms, 0.443 -> 0.417 with
   // two LayerNorms) but leaves 16 SMs idle, and inside the power-capped step the two are equal (67.9-68.6 vs 66.8-69.0 ms).
   const int variant = g.variant < 0 ? 1 : g.variant;
-  if (variant != 0) {      // split / quad kernels read A through a 3-D map (see GemmLnParams::gather_rows)
+  if (variant != 0) {      // split / quad kernels can gather A through a 3-D map (see GemmLnParams::gather_rows)
     if (g.gather_rows > 0) {
       if (GEMM_BM % g.gather_rows != 0) { if (err) *err = "gemm_ln: gather_rows must divide 128"; return false; }
       if (!make_tma_3d_bf16(&ta, g.A, uint64_t(g.K), uint64_t(g.gather_group_rows), uint64_t(g.gather_groups), uint64_t(g.lda),
                             uint64_t(g.gather_group_rows) * uint64_t(g.lda), GEMM_BK, uint32_t(g.gather_rows),
                             uint32_t(GEMM_BM / g.gather_rows), err)) return false;
       ep.gather_rows = g.gather_rows; ep.gather_row0 = g.gather_row0;
-    } else if (!make_tma_3d_bf16(&ta, g.A, uint64_t(g.K), uint64_t(g.M), 1, uint64_t(g.lda), uint64_t(g.M) * uint64_t(g.lda), GEMM_BK,
-                                 GEMM_BM, 1, err)) return false;
+    }
   } else if (g.gather_rows > 0) { if (err) *err = "gemm_ln: the first-version kernel cannot gather A"; return false; }
   if (variant == 2) {
     // cluster of four (two cta_group::2 pairs per 256-row block); the number of co-resident clusters is asked of the driver

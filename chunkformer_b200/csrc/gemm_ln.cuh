@@ -38,9 +38,8 @@ struct GemmLnParams {
   const int* row_limit = nullptr;      // LNM_Y: rows with (row % rows_per_seq) >= limit[row / rows_per_seq] give y = 0
   int rows_per_seq = 1;
   int store_f32 = 1, store_bf16 = 1;   // LNM_FINAL: which outputs exist
-  // gemm_ln_split_kernel / gemm_ln_quad_kernel read A through a 3-D tensor map {K, rows, groups}.  Plain A: one group,
-  // gather_rows = 0.  Gathered A (compact streaming, api.cu): row m of the GEMM is row gather_row0 + m % gather_rows of group
-  // m / gather_rows (gather_rows divides 128).
+  // Gathered A (compact streaming, api.cu; gemm_ln_split_kernel / gemm_ln_quad_kernel; gather_rows > 0, tma_a is then a 3-D map
+  // {K, rows, groups}): row m of the GEMM is row gather_row0 + m % gather_rows of group m / gather_rows (gather_rows divides 128).
   int gather_rows = 0, gather_row0 = 0;
 #ifdef CF_ABLATION
   long long* prof = nullptr;           // tools build: [grid][16] cycles per role spent waiting / working (gemm_ln_split_kernel)
@@ -664,13 +663,13 @@ CF_DEVINL void gemm_ln_split_body(const CUtensorMap& tma_a, const CUtensorMap& t
             const uint32_t fb = mapa_rank(smem_u32(&full_bar[stage]), lead);
             const int arow = m_blk * BMC + row_off;
             if (ep.gather_rows > 0) tma_load_3d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, ep.gather_row0, arow / ep.gather_rows);
-            else tma_load_3d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, arow, 0);
+            else tma_load_2d_2sm(sA + stage * A_BYTES, &tma_a, fb, kb * GEMM_BK, arow);
             tma_load_2d_2sm(sB + stage * B_BYTES, &tma_b, fb, kb * GEMM_BK, int(rank) * NC + int(half) * (NC / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
             if (ep.gather_rows > 0)
               tma_load_3d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, ep.gather_row0, m_blk * GEMM_BM / ep.gather_rows);
-            else tma_load_3d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM, 0);
+            else tma_load_2d(sA + stage * A_BYTES, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
             tma_load_2d(sB + stage * B_BYTES, &tma_b, &full_bar[stage], kb * GEMM_BK, int(rank) * NC);
           }
         }
