@@ -379,6 +379,30 @@ class ChunkFormerEncoderB200:
         return res[0] if len(res) == 1 else tuple(res)
 
     @torch.no_grad()
+    def ctc_prefix_beam_search(self, enc: torch.Tensor, enc_lens, beam_size: int = 10, blank_id: int = 0):
+        """CTC prefix beam search on encoder outputs: log_softmax(ctc_lo(enc)) by the library's CTC kernels, the first beam prune
+        (top-k per frame) on the device, the prefix search on the host (postprocess.prefix_beam_search_topk).  What
+        ASRModel.decode(methods=["ctc_prefix_beam_search"]) does behind the encoder (modules/asr_model.py:313-325 ->
+        modules/search.py:131-249).  enc: (B, T, d) fp32 / bf16 on the device (e.g. from forward_encoder); enc_lens: (B,) valid
+        frames.  Returns one postprocess.DecodeResult per utterance (tokens, score, times, nbest, nbest_scores, nbest_times).
+        One utterance at a time, so that only T x V log-probabilities exist at once."""
+        from .postprocess import DecodeResult, prefix_beam_search_topk
+        if enc.dim() != 3:
+            raise ValueError("enc must be (B, T, d)")
+        k = min(int(beam_size), self.geo.vocab)
+        out = []
+        for b in range(enc.shape[0]):
+            n = int(enc_lens[b])
+            if n <= 0:
+                out.append(DecodeResult([], 0.0, [], [[]], [0.0], [[]]))
+                continue
+            _, logp = self.ctc_greedy(enc[b, :n], want_logp=True)
+            top_logp, top_idx = logp.topk(k, dim=1)
+            nbest, scores, times = prefix_beam_search_topk(top_logp.cpu().numpy(), top_idx.cpu().numpy(), n, k, blank_id)
+            out.append(DecodeResult(nbest[0], scores[0], times[0], nbest, scores, times))
+        return out
+
+    @torch.no_grad()
     def ctc_compact(self, tokens: torch.Tensor, seg_start: Sequence[int], seg_len: Sequence[int], mode: int = 0,
                     blank_id: int = 0):
         """Device-side CTC compaction of greedy token ids (utils/model_utils.py:23-32, :186-196), so that only the kept
