@@ -110,6 +110,7 @@ struct AttnTcParams {
   float scale_log2e;
 #ifdef CF_ABLATION
   long long* prof = nullptr;                 // tools build: [grid][16] cycles per phase of softmax warp 0 / the MMA warp
+  int debug = 0;                             // tools build: 1 = no skew (S_bd read unshifted from TMEM, no shared-memory round trip; wrong results)
 #endif
 };
 #ifdef CF_ABLATION
@@ -318,6 +319,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_co
         for (int sb = 0; sb < 2; ++sb) {
           uint32_t r0[32];
           const uint32_t cbase = TM_BD + cb_thread;
+#ifdef CF_ABLATION
+          if (p.debug & 1) {                           // timing experiment: what the skew through shared memory costs
+            uint32_t rb[32];
+            tmem_ld32(tmem_base + lane_addr + cbase + 32 * sb, rb);
+            tmem_ld32(tmem_base + lane_addr + TM_AC + 64 * set + 32 * sb, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float v = __uint_as_float(r0[k]) + __uint_as_float(rb[k]);
+              s[32 * sb + k] = v;
+              mx = fmaxf(mx, v);
+            }
+            continue;
+          }
+#endif
           const float sc = PRE ? 1.0f : p.scale_log2e;
           auto pack4 = [&](int q) {
             uint4 w0;
@@ -893,6 +909,7 @@ inline bool launch_attention_tc(const AttnParams& a, cudaStream_t st, std::strin
   if (!ensure_smem_optin(attention_tc_kernel<false>, ATC_SMEM_BYTES, err, "attention_tc")) return false;
 #ifdef CF_ABLATION
   const int prof_ctas = per_head * a.heads;
+  { const char* e = getenv("CF_ATTN_DEBUG"); p.debug = e ? atoi(e) : 0; }
   if (getenv("CF_ATTN_PROF")) { cudaMalloc(&p.prof, size_t(prof_ctas) * 32 * 8); cudaMemsetAsync(p.prof, 0, size_t(prof_ctas) * 32 * 8, st); }
 #endif
   if (a.prescaled) attention_tc_kernel<true><<<per_head * a.heads, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, tp, p);
